@@ -1,0 +1,67 @@
+#!/bin/bash
+# oracle/build_ref.sh -- TEST INFRASTRUCTURE ONLY.
+#
+# Compiles the UNMODIFIED reference (default /root/reference) from the sources where
+# they lie into oracle/_ref/ (git-ignored build output, travels to the GPU box):
+#   libnhwref_enc.so / libnhwref_dec.so : canonical (zero-guard allocator) encoder and
+#       decoder + in-memory glue + stage taps.  This is the parity oracle.
+#   nhw-enc-canon / nhw-dec-canon       : the reference CLIs, canonical allocator.
+#   nhw-enc-stock / nhw-dec-stock       : README one-liner build (gcc *.c -O3), stock malloc.
+# The reference's own build system (CMake) is not used.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${NHW_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+TMP="$OUT/tmp"
+if [ ! -d "$REF/encoder" ]; then
+	echo "build_ref.sh: reference not found at $REF (prebuilt oracle/_ref is used as is)" >&2
+	exit 0
+fi
+mkdir -p "$OUT" "$TMP"
+CC="${CC:-gcc}"
+# -ffp-contract=off: the reference's x86-64 gcc -O3 build has no FMA; keep it that way.
+CFLAGS="-O3 -fPIC -w -ffp-contract=off"
+WRAP="-Wl,--wrap=malloc,--wrap=calloc,--wrap=free,--wrap=exit"
+
+ENC_SRCS="colorspace.c compress_pixel.c filters.c image_processing.c wavelet_filterbank.c"
+DEC_SRCS="compress_pixel.c filters.c wavelet_filterbank.c"
+
+# ---- encoder library (tap-instrumented nhw_encoder.c) ----
+python3 "$HERE/make_tapped.py" "$REF/encoder/nhw_encoder.c" "$HERE/taps_enc.txt" "$TMP/enc_tapped.c"
+objs=""
+for s in $ENC_SRCS; do
+	$CC $CFLAGS -I"$REF/encoder" -c "$REF/encoder/$s" -o "$TMP/enc_${s%.c}.o"
+	objs="$objs $TMP/enc_${s%.c}.o"
+done
+$CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$TMP/enc_tapped.c" -o "$TMP/enc_nhw_encoder.o"
+$CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$HERE/ref_enc_glue.c" -o "$TMP/enc_glue.o"
+$CC $CFLAGS -c "$HERE/zguard.c" -o "$TMP/zguard.o"
+$CC -shared -o "$OUT/libnhwref_enc.so" $objs "$TMP/enc_nhw_encoder.o" "$TMP/enc_glue.o" "$TMP/zguard.o" \
+	$WRAP -Wl,-Bsymbolic -lm -lpthread
+
+# ---- decoder library ----
+if [ -f "$HERE/taps_dec.txt" ]; then
+	python3 "$HERE/make_tapped.py" "$REF/decoder/nhw_decoder.c" "$HERE/taps_dec.txt" "$TMP/dec_tapped.c"
+	DEC_MAIN="$TMP/dec_tapped.c"
+else
+	DEC_MAIN="$REF/decoder/nhw_decoder.c"
+fi
+objs=""
+for s in $DEC_SRCS; do
+	$CC $CFLAGS -I"$REF/decoder" -c "$REF/decoder/$s" -o "$TMP/dec_${s%.c}.o"
+	objs="$objs $TMP/dec_${s%.c}.o"
+done
+$CC $CFLAGS -I"$REF/decoder" -I"$HERE" -c "$DEC_MAIN" -o "$TMP/dec_nhw_decoder.o"
+$CC $CFLAGS -I"$REF/decoder" -Dmain=nhwref_dec_cli_main -c "$REF/decoder/nhw_decoder_cli.c" -o "$TMP/dec_cli.o"
+$CC $CFLAGS -I"$REF/decoder" -I"$HERE" -c "$HERE/ref_dec_glue.c" -o "$TMP/dec_glue.o"
+$CC -shared -o "$OUT/libnhwref_dec.so" $objs "$TMP/dec_nhw_decoder.o" "$TMP/dec_cli.o" "$TMP/dec_glue.o" "$TMP/zguard.o" \
+	$WRAP -Wl,-Bsymbolic -lm -lpthread
+
+# ---- CLIs ----
+(cd "$REF/encoder" && $CC -O3 -w -ffp-contract=off *.c "$TMP/zguard.o" -o "$OUT/nhw-enc-canon" $WRAP -lm)
+(cd "$REF/decoder" && $CC -O3 -w -ffp-contract=off *.c "$TMP/zguard.o" -o "$OUT/nhw-dec-canon" $WRAP -lm)
+(cd "$REF/encoder" && $CC -O3 -w *.c -o "$OUT/nhw-enc-stock" -lm)
+(cd "$REF/decoder" && $CC -O3 -w *.c -o "$OUT/nhw-dec-stock" -lm)
+
+rm -rf "$TMP"
+echo "oracle/_ref built: $(ls "$OUT" | tr '\n' ' ')"
