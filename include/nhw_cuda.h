@@ -1,0 +1,107 @@
+/*
+ * include/nhw_cuda.h -- C-ABI of libnhw_cuda.so, the B200 (sm_100a) implementation of the
+ * NHW codec hot path.  Plain C, plain pointers and sizes; no torch / C++ types.
+ *
+ * The reference (rcanut/nhwcodec) has no plugin/FFI interface; its boundary is the set of
+ * extern functions its two CLI files call:
+ *     encoder/codec.h:184-189   encode_image, read_image_bmp, write_compressed_file,
+ *                               downsample_YUV420
+ *     decoder/codec.h:198-202   decode_image, parse_file
+ *     decoder/nhw_decoder_cli.c:58-59  setup_bmp_header, write_image_bmp
+ * Those per-image symbols are provided, with the reference's exact signatures, by
+ * libnhw_compat (include/nhw_compat.h) on top of the batch entry points below, so the
+ * reference's own nhw_encoder_cli.c / nhw_decoder_cli.c link against this library unchanged.
+ *
+ * Batch entry points replace the reference's one-process-per-image model: every image is an
+ * independent unit (all reference state lives in per-call structs, encoder/codec.h:112-181),
+ * errors are per-image status codes instead of exit() (encoder/compress_pixel.c:234,270-271).
+ */
+#ifndef NHW_CUDA_H
+#define NHW_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NHW_IMG_W 512
+#define NHW_IMG_H 512
+#define NHW_PIX_BYTES (512 * 512 * 3)      /* raw BMP pixel bytes per image (encoder/nhw_encoder.c:3086) */
+#define NHW_MAX_STREAM_BYTES (1u << 19)    /* per-image upper bound on a .nhw stream: 512 KiB */
+
+/* status / error codes (per image in status[], or as function return value) */
+#define NHW_OK 0
+#define NHW_ERR_CUDA (-1)                  /* CUDA runtime failure; see nhw_last_error() */
+#define NHW_ERR_ARG (-2)
+#define NHW_ERR_QUALITY (-3)               /* quality setting not supported by this build */
+#define NHW_ERR_CODEBOOK (-4)              /* reference would exit(-1): encoder/compress_pixel.c:234,270-271 */
+#define NHW_ERR_OVERFLOW (-5)              /* an internal list outgrew its slot (reference would write out of bounds) */
+#define NHW_ERR_NOMEM (-6)
+#define NHW_ERR_STREAM (-7)                /* malformed .nhw (decoder/nhw_decoder.c:1497-1500) */
+
+typedef struct nhw_ctx nhw_ctx;
+
+/* Create a codec context on CUDA device `device` with workspace for up to `max_batch`
+ * images in flight (larger batches are processed in chunks of max_batch).  Fails loudly
+ * (NHW_ERR_CUDA) when there is no usable GPU: there is no CPU fallback. */
+int nhw_create(int device, int max_batch, nhw_ctx **out);
+void nhw_destroy(nhw_ctx *ctx);
+const char *nhw_last_error(void);
+int nhw_version(void);
+
+/* ---- encode: replaces read_image_bmp's pixel path + downsample_YUV420 + encode_image +
+ * write_compressed_file (encoder/nhw_encoder_cli.c:179-183) for n images at once. ----
+ * rgb      : n * NHW_PIX_BYTES bytes, each image = the 786432 bytes that follow the BMP
+ *            header, in file order (host memory; pinned memory is faster).
+ * quality  : the reference's -q value (encoder/nhw_encoder_cli.c:118).
+ * out      : receives the .nhw streams back to back; offsets[i]..offsets[i+1] is image i.
+ * out_cap  : capacity of out in bytes.
+ * offsets  : n+1 entries.    status : n entries (NHW_OK or an error code).
+ * Returns NHW_OK if the call ran (inspect status[] per image), else a negative error. */
+int nhw_encode_batch(nhw_ctx *ctx, const uint8_t *rgb, int n, int quality,
+                     uint8_t *out, size_t out_cap, uint64_t *offsets, int32_t *status);
+
+/* Same with every buffer resident in device memory of the context's GPU (no host copies).
+ * out_dev holds n slots of NHW_MAX_STREAM_BYTES; len_dev[i] receives the stream length. */
+int nhw_encode_batch_device(nhw_ctx *ctx, const uint8_t *rgb_dev, int n, int quality,
+                            uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev);
+
+/* ---- decode: replaces decode_image + write_image_bmp's pixel path
+ * (decoder/nhw_decoder_cli.c:83-90) for n streams. ----
+ * in/offsets : concatenated .nhw streams (host).   rgb : n * NHW_PIX_BYTES bytes out. */
+int nhw_decode_batch(nhw_ctx *ctx, const uint8_t *in, const uint64_t *offsets, int n,
+                     uint8_t *rgb, int32_t *status);
+
+/* ---- stage-level entry points (device pointers), used by the parity tests and ncu runs.
+ * Layouts follow the reference's working planes (encoder/codec.h:112-123):
+ *   y_proc : n * 512*512 int16, the luma coefficient plane (`im_process`) after both DWT
+ *            levels, transposed orientation;
+ *   y_ll1  : n * 256*256 int16, the LL1 copy (`res256`, encoder/nhw_encoder.c:127-135);
+ *   c_proc : n * 2 * 256*256 int16, U then V coefficient planes;
+ *   c_ll1  : n * 2 * 128*128 int16, chroma LL1 copies (encoder/nhw_encoder.c:2270-2276).
+ * Any output pointer may be NULL. */
+int nhw_stage_frontend_device(nhw_ctx *ctx, const uint8_t *rgb_dev, int n, int quality,
+                              int16_t *y_proc, int16_t *y_ll1, int16_t *c_proc, int16_t *c_ll1);
+
+/* colour stage only: y (n*512*512 int16), u,v (n*256*256 u8 each) -- downsample_YUV420,
+ * encoder/colorspace.c:55.  pre != 0 also applies pre_processing (encoder/image_processing.c:558). */
+int nhw_stage_colorspace_device(nhw_ctx *ctx, const uint8_t *rgb_dev, int n, int quality, int pre,
+                                int16_t *y, uint8_t *u, uint8_t *v);
+
+/* Deterministic synthetic "natural-like" test images, generated on the device
+ * (SURVEY.md section 8d): image i of the call uses seed seed0+i.  kind 0 = natural-like,
+ * 1 = uniform noise.  sin_lut = 1024 int16 (device), see nhwcodec_b200/synth.py. */
+int nhw_synth_batch_device(nhw_ctx *ctx, uint8_t *rgb_dev, int n, uint32_t seed0, int kind,
+                           const int16_t *sin_lut_dev);
+
+/* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
+uint64_t nhw_launch_count(const nhw_ctx *ctx);
+
+/* names+times of the last call's kernels are not kept here: use CUDA events / ncu. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NHW_CUDA_H */

@@ -1,0 +1,32 @@
+// nhw_dev.cuh -- shared device-side definitions for libnhw_cuda (sm_100a only).
+//
+// Plane vocabulary follows the reference (encoder/codec.h:112-123): a luma working plane is
+// 512x512 int16 (row stride 512), a chroma working plane 256x256 int16 (row stride 256).
+// "proc" = im_process, "jpeg" = im_jpeg.  All planes of a batch are stored image-major.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define NHW_YW 512                 // luma width/height  (2*IM_DIM, encoder/codec.h:61)
+#define NHW_CW 256                 // chroma width/height (IM_DIM)
+#define NHW_YPLANE (512 * 512)     // elements in a luma plane   (4*IM_SIZE)
+#define NHW_CPLANE (256 * 256)     // elements in a chroma plane (IM_SIZE)
+#define NHW_RGB_BYTES (512 * 512 * 3)
+
+struct nhw_ctx;
+
+// Launch bookkeeping: every kernel launch goes through this so gpu_launches is a real count.
+#define NHW_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+	do {                                                                                  \
+		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
+		(ctx)->launches++;                                                                \
+	} while (0)
+
+// symmetric rounding division by 2^s used all over the reference's filters
+// (e.g. encoder/filters.c:89-93): v>=0 ? (v+h)>>s : -((-v+h)>>s)
+__device__ __forceinline__ int nhw_sround(int v, int half, int sh)
+{
+	return v >= 0 ? ((v + half) >> sh) : -((-v + half) >> sh);
+}
+
+__device__ __forceinline__ int nhw_iabs(int v) { return v < 0 ? -v : v; }

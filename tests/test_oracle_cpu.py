@@ -1,0 +1,103 @@
+"""CPU-side checks: the oracle is pinned to the known-answer hashes of SURVEY.md Appendix E,
+the synthetic generator is deterministic, and the C-ABI library exports what the header declares."""
+import ctypes
+import hashlib
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from nhwcodec_b200 import synth
+from nhwcodec_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# canonical encoder .nhw md5 / nhw-dec BMP md5 for the formula-defined image
+KAT = {
+    1: (12566, "168dd042ce71b4a5efb120fe410651de", "d6d7df502cc4379b7c36c9b2626475dc"),
+    8: (14966, "b692471fcf5804584875a9492c098992", "2a01d9282ffb1877aaec7a339fb64ee0"),
+    12: (16572, "78f70cb727e2d33886b31150df830ded", "72d541ea5dd4784c9a6a579af2d73aa9"),
+    16: (19639, "548273cad8a22d3717ee4329867a6606", "98873fe5ce80a606cac49e56ab33e9ca"),
+    17: (21768, "427478c045b4fbaa8341697bc682d1c6", "6dfb9f69c739d14b3b115db7a5a3d762"),
+    20: (24412, "9ea5053bd20fc35758652b0a0aa47b8d", "1d9ccf4e698182fcac1ae31992789caf"),
+    21: (25153, "dfa28fb62ec6e59d10dc2340e7b0b46c", "44ff53e2d061224ebc0e16a114e1eb3e"),
+    22: (25749, "66c8ab12f0d5518f8cde5da4fb605f64", "dd1b871c7abc417ffe662ec7924cd269"),
+    23: (26177, "d841a9bb3008bf06d46f149f23323d80", "e4f2b5a68bb5083abc18244fbeff069e"),
+}
+
+
+def smooth_pixels():
+    y, x = np.mgrid[0:512, 0:512]
+    r = (x // 2 + (3 * y) // 7) % 256
+    g = (y // 2 + (x * x) // 4096) % 256
+    b = ((x + y) // 4 + ((x * y) >> 9)) % 256
+    return np.stack([b, g, r], axis=-1).astype(np.uint8).reshape(-1)
+
+
+def bmp_header():
+    return b"BM" + struct.pack("<IHHI", 786486, 0, 0, 54) + struct.pack(
+        "<IiiHHIIiiII", 40, 512, 512, 1, 24, 0, 786432, 2835, 2835, 0, 0)
+
+
+def test_smooth_image_md5():
+    assert hashlib.md5(bmp_header() + smooth_pixels().tobytes()).hexdigest() == "7c01ee883f5846fdc4f70d50d248eab7"
+
+
+@pytest.mark.parametrize("q", sorted(KAT))
+def test_oracle_known_answers(ref, q):
+    size, enc_md5, dec_md5 = KAT[q]
+    stream = ref.ref_encode(smooth_pixels(), q)
+    assert len(stream) == size
+    assert hashlib.md5(stream).hexdigest() == enc_md5
+    pix = ref.ref_decode(stream)
+    # the reference decoder writes its own fixed 54-byte header (decoder/nhw_decoder_cli.c:61-65)
+    hdr = bytes([66, 77, 54, 0, 12, 0, 0, 0, 0, 0, 54, 0, 0, 0, 40, 0, 0, 0, 0, 2, 0, 0, 0, 2, 0, 0, 1, 0, 24, 0,
+                 0, 0, 0, 0, 0, 0, 12, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    assert hashlib.md5(hdr + pix.tobytes()).hexdigest() == dec_md5
+
+
+def test_oracle_is_deterministic(ref):
+    img = synth.noise(11)
+    a = ref.ref_encode(img, 20)
+    junk = [np.full(100000, 0xAB, dtype=np.uint8) for _ in range(8)]   # perturb the heap
+    del junk
+    b = ref.ref_encode(img, 20)
+    assert a == b
+
+
+def test_synth_golden():
+    # pins the generator: bench inputs and the committed goldens depend on these bytes
+    assert hashlib.md5(synth.natural(1000).tobytes()).hexdigest() == GOLD_SYNTH["natural1000"]
+    assert hashlib.md5(synth.noise(5).tobytes()).hexdigest() == GOLD_SYNTH["noise5"]
+    assert hashlib.md5(synth.textured(1002).tobytes()).hexdigest() == GOLD_SYNTH["textured1002"]
+
+
+GOLD_SYNTH = {
+    "natural1000": "70c368d4eaf6e48b0c4150dd63410b69",
+    "noise5": "02f67948cecdf07db5a12468b84c62ab",
+    "textured1002": "e1be29fab99d85b197bb864ceb9a85b9",
+}
+
+
+def test_library_exports_header_symbols():
+    if not os.path.exists(capi.LIB_PATH):
+        pytest.skip("libnhw_cuda.so not built")
+    hdr = open(os.path.join(ROOT, "include", "nhw_cuda.h")).read()
+    declared = set(re.findall(r"\b(nhw_[a-z_0-9]+)\s*\(", hdr))
+    declared.discard("nhw_ctx")
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    if not os.path.exists(capi.LIB_PATH):
+        pytest.skip("libnhw_cuda.so not built")
+    with pytest.raises(capi.NhwError):
+        capi.Codec(device=0, max_batch=1)
