@@ -1,0 +1,273 @@
+// enc_c.cuh -- chroma encoder stages (encoder/nhw_encoder.c:2255-2868; U and V run the same
+// skeleton on 256x256 planes, stride 256, with two small differences noted below), the chroma
+// quantisers offsetUV_recons256 / offsetUV (encoder/image_processing.c:3192-3353, 108-183)
+// and the chroma LL coder highres_compression (encoder/compress_pixel.c:878-1022).
+// q17..q23 (pre_processing_UV and the q<=16 thresholds are not built).
+#pragma once
+#include "enc_y3.cuh"
+
+#define CW 256   // chroma row stride
+
+// ---- offsetUV_recons256: LL (64x64) part.  comp=1 first call, comp=0 second call.
+NHW_HD void c_recons_ll_row(const EncImg &im, int r /* 0..63 */, int comp)
+{
+	const int16_t *P = im.cproc + r * CW;
+	int16_t *J = im.cjpeg + r * CW;
+	if (comp) {
+		for (int j = 0; j < 64; j += 2) {   // q>15 branch
+			if (r == 0) { J[j] = P[j]; J[j + 1] = (int16_t)(P[j + 1] & 65534); }
+			else { J[j] = (int16_t)(P[j] & 65534); J[j + 1] = P[j + 1]; }
+		}
+	} else {
+		for (int j = 0; j < 64; j++) J[j] = (P[j] > 0 && P[j] < 256) ? (int16_t)(P[j] & 65534) : P[j];
+	}
+}
+
+// ---- offsetUV_recons256: detail rows of the 128x128 level-2 region
+NHW_HD void c_recons_quant_row(const EncImg &im, int r /* 0..127 */, int m1, int comp)
+{
+	const int16_t *P = im.cproc + r * CW;
+	int16_t *J = im.cjpeg + r * CW;
+	for (int j = r < 64 ? 64 : 0; j < 128; j++) {
+		int a = P[j];
+		if ((a == -7 || a == -8) && !comp) {
+			if (j < 127 && (P[j + 1] == -7 || P[j + 1] == -8)) { J[j] = -11; J[j + 1] = -11; j++; continue; }
+		}
+		if (a < 0) {
+			a = -a;
+			if (P[j + 1] < 0 && P[j + 1] > -8) { if ((a & 7) < 6) a &= 65528; }
+			else if ((a & 7) < 7) a &= 65528;
+			a = -a;
+		}
+		if (a < m1 && a > -m1) { J[j] = 0; continue; }
+		a += 128;
+		if (a < 0) a = -((-a) & 65528);
+		else a &= 65528;
+		J[j] = (int16_t)(a > 128 ? a - 125 : a - 131);
+	}
+}
+
+// ---- chroma LL1 correction against the trial reconstruction (nhw_encoder.c:2316-2335,
+// 2629-2647).  U tests the right neighbour with >=0 / <=0, V with >0 / <0.
+NHW_HD void c_correct_row(const EncImg &im, int r /* 0..127 */, int is_v)
+{
+	const int16_t *P = im.cproc + r * CW, *L = im.cll1 + r * 128;
+	int16_t *J = im.cjpeg + r * CW;
+	for (int j = 0; j < 128; j++) {
+		int scan = P[j] - L[j];
+		int nx = P[j + 1] - L[j + 1];
+		int d = 0;
+		if (scan > 10) d = -6;
+		else if (scan > 7) d = -3;
+		else if (scan > 4) d = -2;
+		else if (scan > 3) d = -1;
+		else if (scan > 2 && (is_v ? nx > 0 : nx >= 0)) d = -1;
+		else if (scan < -10) d = 6;
+		else if (scan < -7) d = 3;
+		else if (scan < -4) d = 2;
+		else if (scan < -3) d = 1;
+		else if (scan < -2 && (is_v ? nx < 0 : nx <= 0)) d = 1;
+		J[j] = (int16_t)(L[j] + d);
+	}
+}
+
+// ---- residual tags 12400 / 12600 / 12900 / 13000 dropped into the first free (|c|<8) cell of
+// the three level-1 bands (nhw_encoder.c:2372-2424), q>=18.  Sequential along a row.
+NHW_HD bool c_drop_tag(int16_t *P, int scan, int tag)
+{
+	if (nhw_iabs(P[scan + 128]) < 8) { P[scan + 128] = (int16_t)tag; return true; }
+	if (nhw_iabs(P[scan + 32768]) < 8) { P[scan + 32768] = (int16_t)tag; return true; }
+	if (nhw_iabs(P[scan + 32768 + 128]) < 8) { P[scan + 32768 + 128] = (int16_t)tag; return true; }
+	return false;
+}
+
+NHW_HD void c_residual_tags_row(const EncImg &im, int q, int r /* 0..127 */)
+{
+	if (q < 18) return;
+	int16_t *P = im.cproc;
+	const int16_t *L = im.cll1;
+	const int res_uv = q > 17 ? 4 : 5;
+	int scan = r * CW, count = r * 128;
+	for (int j = 0; j < 128; j++, scan++, count++) {
+		int d = P[scan] - L[count];
+		if (d > 3 && d < 7) {
+			int n = P[scan + 1] - L[count + 1];
+			if (n > 2 && n < 7) {
+				if (c_drop_tag(P, scan, 12400)) { count++; scan++; j++; continue; }
+			}
+		} else if (d < -3 && d > -7) {
+			int n = P[scan + 1] - L[count + 1];
+			if (n < -2 && n > -8) {
+				if (c_drop_tag(P, scan, 12600)) { count++; scan++; j++; continue; }
+			}
+		}
+		if (nhw_iabs(d) > res_uv) {
+			if (d > 0) c_drop_tag(P, scan, 12900);
+			else if (d == -5) { if ((P[scan + 1] - L[count + 1]) < 0) c_drop_tag(P, scan, 13000); }
+			else c_drop_tag(P, scan, 13000);
+		}
+	}
+}
+
+// ---- chroma LL (64x64) -> tree1 bytes + exw escapes (nhw_encoder.c:2482-2515, 2781-2813).
+// exw entries go to a per-component list (im.tmp3 for U, im.tmp3+16384 for V) that the
+// container writer splices after the luma list with the two-zero separators.
+NHW_HDN int c_ll_to_bytes_image(const EncImg &im, int is_v)
+{
+	int16_t *P = im.cproc;
+	uint8_t *t = im.tree1;
+	uint8_t *exw = im.tmp3 + (is_v ? 16384 : 0);
+	int a = is_v ? 20480 : 16384, e = 0;
+	for (int r = 0; r < 64; r++) {
+		for (int j = 0; j < 64; j++) {
+			int scan = P[r * CW + j];
+			if (scan > 255 && (j > 0 || r > 0)) {
+				exw[e++] = (uint8_t)r; exw[e++] = (uint8_t)(j + 128);
+				int y = scan - 255;
+				exw[e++] = (uint8_t)(y > 255 ? 255 : y);
+				t[a] = t[a - 1]; a++;
+			} else if (scan < 0 && (j > 0 || r > 0)) {
+				exw[e++] = (uint8_t)r; exw[e++] = (uint8_t)j;
+				if (scan < -255) scan = -255;
+				exw[e++] = (uint8_t)(-scan);
+				t[a] = t[a - 1]; a++;
+			} else {
+				if (scan > 255) scan = 255;
+				else if (scan < 0) scan = 0;
+				t[a++] = (uint8_t)(scan & 254);
+			}
+			P[r * CW + j] = 0;
+		}
+	}
+	return e;
+}
+
+// bit 1 of every chroma LL byte, 8 per byte (res_U_64 / res_V_64, nhw_encoder.c:2517-2537), q>15
+NHW_HD void c_ll_bit1_plane(const EncImg &im, int is_v)
+{
+	const uint8_t *t = im.tree1 + (is_v ? 20480 : 16384);
+	uint8_t *o = im.res_uv64 + (is_v ? 512 : 0);
+	for (int k = 0; k < 512; k++) {
+		int b = 0;
+		for (int i = 0; i < 8; i++) b |= ((t[8 * k + i] >> 1) & 1) << (7 - i);
+		o[k] = (uint8_t)b;
+	}
+}
+
+// ---- offsetUV (image_processing.c:108-183): chroma coefficient -> byte, flat raster order
+NHW_HDN void c_offset_quant_image(const EncImg &im, int m2)
+{
+	int16_t *P = im.cproc;
+	for (int i = 0; i < 65536; i++) {
+		int a = P[i];
+		if (a > 10000) {
+			int b = a == 12400 ? 124 : a == 12600 ? 126 : a == 12900 ? 122 : a == 13000 ? 130 : -1;
+			if (b >= 0) { P[i] = (int16_t)b; continue; }
+		}
+		if (a > 127) {
+			int k = ((a & 0xfff8) - 128) >> 3;
+			P[i] = NHW_EXTRA1(k > 18 ? 18 : k);
+			continue;
+		} else if (a < -127) {
+			int k = (((-a) & 0xfff8) - 128) >> 3;
+			P[i] = NHW_EXTRA2(k > 18 ? 18 : k);
+			continue;
+		}
+		bool neg = a < 0;
+		if (a == -7 || a == -8) {
+			if ((i & 255) < 255 && (P[i + 1] == -7 || P[i + 1] == -8)) { P[i] = 120; P[i + 1] = 120; i++; continue; }
+		}
+		if (neg) {
+			a = -a;
+			if (P[i + 1] < 0 && P[i + 1] > -8) { if ((a & 7) < 6) a &= 504; }
+			else if ((a & 7) < 7) a &= 504;
+			a = -a;
+		} else if (a > 6 && (a & 7) >= 6) {
+			if ((i & 255) < 255 && P[i + 1] == 7) P[i + 1] = 8;
+		}
+		if (a < m2 && a > -m2) { P[i] = 128; continue; }
+		P[i] = (int16_t)((a + 128) & 248);
+	}
+}
+
+// ---- chroma scan: 8-column strips, two rows per step, U on even / V on odd bytes from 262144
+NHW_HD void c_scan_strip(const EncImg &im, int strip /* 0..31 */, int is_v)
+{
+	const int16_t *P = im.cproc + strip * 8;
+	uint8_t *s = im.scan + 262144 + is_v + strip * 4096;
+	for (int k = 0; k < 128; k++) {
+		const int16_t *r0 = P + (2 * k) * CW, *r1 = r0 + CW;
+		for (int t = 0; t < 8; t++) s[2 * t] = (uint8_t)r0[t];
+		for (int t = 0; t < 8; t++) s[16 + 2 * t] = (uint8_t)r1[7 - t];
+		s += 32;
+	}
+}
+
+// ---- highres_compression (compress_pixel.c:878-1022): both chroma LL planes, appended to
+// the luma LL code.  in: tree1[16384..24575]; io: im.llcode (highres_comp) from y_res_comp on.
+NHW_HDN void ll_dpcm_chroma_image(const EncImg &im)
+{
+	uint8_t *x = im.tree1;
+	uint8_t *out = im.llcode;
+	EncHdr *h = im.hdr;
+	for (int i = 16384; i < 24576; i++) x[i] &= 252;
+	int j = h->y_res_comp;
+	out[j++] = x[16384];
+	int a = 0, res = 0;
+	for (int i = 16385; i < 24576; i++) {
+		int scan = x[i] - x[i - 1];
+		int count = x[i + 1] - x[i];
+		if (scan == 0 && count == 0) {
+			while (x[i + a + 2] == x[i + a + 1]) {
+				a++;
+				if (a < 7) continue;
+				res = 1;             // a==7 || res==1
+				if (a >= 14) break;
+			}
+			i += a + 1;
+			if (res == 1) out[j] = (uint8_t)(64 + (7 << 3) + a - 7);
+			else {
+				i++;
+				int code = 64 + (a << 3);
+				int d = x[i] - x[i - 1], d2 = x[i + 1] - x[i];
+				if (d == 4) {
+					if (d2 == -4) {
+						if (x[i + 2] - x[i + 1] == 0) { code += 3; i += 2; }
+						else { code += 2; i++; }
+					} else code += 1;
+				} else if (d == -4) {
+					if (d2 == 4) {
+						if (x[i + 2] - x[i + 1] == 0) { code += 4; i += 2; }
+						else { code += 5; i++; }
+					} else code += 6;
+				} else if (d == 8) code += 7;
+				else i--;
+				out[j] = (uint8_t)code;
+			}
+			a = 0;
+			res = 0;
+			j++;
+		} else if (nhw_iabs(scan) <= 4 && nhw_iabs(count) <= 4) {
+			if (!scan && count == 4) res = 0;
+			else if (!scan && count == -4) res = 1;
+			else if (scan == 4 && !count) res = 2;
+			else if (scan == -4 && !count) res = 3;
+			else if (scan == 4 && count == 4) res = 4;
+			else if (scan == 4 && count == -4) res = 5;
+			else if (scan == -4 && count == 4) res = 6;
+			else if (scan == -4 && count == -4) res = 7;
+			int d3 = x[i + 2] - x[i + 1];
+			if (d3 == 0) { out[j++] = (uint8_t)(192 + (res << 2)); i += 2; }
+			else if (d3 == 4) { out[j++] = (uint8_t)(192 + (res << 2) + 1); i += 2; }
+			else if (d3 == -4) { out[j++] = (uint8_t)(192 + (res << 2) + 2); i += 2; }
+			else if (d3 == 8) { out[j++] = (uint8_t)(192 + (res << 2) + 3); i += 2; }
+			else { out[j++] = (uint8_t)(((scan + 16) << 1) + ((count + 16) >> 2)); i++; }
+			res = 0;
+		} else if (nhw_iabs(scan) <= 16 && nhw_iabs(count) <= 16) {
+			scan += 16; count += 16;
+			if (scan == 32 || count == 32) out[j++] = (uint8_t)(128 + (x[i] >> 2));
+			else { out[j++] = (uint8_t)((scan << 1) + (count >> 2)); i++; }
+		} else out[j++] = (uint8_t)(128 + (x[i] >> 2));
+	}
+	h->end_ch_res = j;
+}

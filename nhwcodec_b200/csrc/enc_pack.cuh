@@ -1,0 +1,243 @@
+// enc_pack.cuh -- entropy stage and container writer.
+//
+//   packet_stream_image : wavlts2packet, encoder/compress_pixel.c:53-469 (one call per stream:
+//                         part 0 = 262144 luma bytes, part 1 = 131072 interleaved chroma bytes)
+//   write_stream_image  : write_compressed_file, encoder/nhw_encoder.c:3100-3220
+//
+// Serial per image in this first version: histogram -> alphabet -> rank sort -> rank code
+// emission, MSB-first into 32-bit words.
+#pragma once
+#include "enc_c.cuh"
+#include "nhw_tables.cuh"
+
+#define NHW_ERR_CODEBOOK_DEV (-4)
+
+struct PackState {
+	int rle_buf[256];     // symbol histogram, later symbol -> rank
+	int rle_128[256];     // zero-run-length histogram, later run length -> rank
+	uint32_t weight[354];
+	uint16_t sym[354];    // (run length << 8) | 128  or  (1 << 8) | byte
+};
+
+// candidate alphabet in the reference's enumeration order (compress_pixel.c:136-229)
+template <typename F>
+NHW_HD void for_each_symbol(F f)
+{
+	for (int i = 0; i < 109; i += 2) f(i);
+	f(112);
+	for (int i = 120; i < 141; i++) f(i);
+	for (int i = 144; i < 256; i += 4) f(i);
+}
+
+NHW_HD void put_bits(uint32_t *w, int &a, int &pack, uint32_t code, int len)
+{
+	pack += len;
+	if (pack <= 32) w[a] |= code << (32 - pack);
+	else {
+		int match = pack - 32;
+		w[a] |= code >> match;
+		a++;
+		w[a] |= (code & ((1u << match) - 1u)) << (32 - match);
+		pack = match;
+	}
+}
+
+// Returns 0 or NHW_ERR_CODEBOOK_DEV.  `a` is the running word index across both parts.
+NHW_HDN int packet_stream_image(const EncImg &im, int part, int &a)
+{
+	PackState &st = *static_cast<PackState *>(im.pack_scratch);
+	uint8_t *s = im.scan;
+	EncHdr *h = im.hdr;
+	uint32_t *words = im.words;
+	const int p1 = part ? 262144 : 0, p2 = part ? 393216 : 262144;
+	int select = part ? 3 : 4;
+	uint8_t saved = 0;
+	if (!part) { saved = s[262144]; s[262144] = 3; }
+	else s[393215] = s[393214];
+	for (int i = 0; i < 256; i++) { st.rle_buf[i] = 0; st.rle_128[i] = 0; }
+	// ---- statistics (compress_pixel.c:81-107)
+	{
+		int e = 1, c = 0;
+		for (int i = p1; i < p2 - 1; i++) {
+			if (s[i] == 128) {
+				while (i < p2 - 1 && s[i + 1] == 128) {
+					e++; c = 1;
+					if (e > 255) { st.rle_128[254]++; e = 1; c = 0; continue; }
+					i++;
+				}
+			}
+			if (c) st.rle_128[e]++;
+			else st.rle_buf[s[i]]++;
+			e = 1; c = 0;
+		}
+	}
+	// ---- alphabet; raise `select` until it fits (compress_pixel.c:129-236)
+	int k;
+	for (;;) {
+		uint32_t w128 = st.rle_buf[128] > 0 ? (uint32_t)st.rle_buf[128] : 0u;
+		for (int j = 2; j < 256; j++) if (st.rle_128[j] > 0) w128 += (uint32_t)(j * st.rle_128[j]);
+		for (int j = 2; j < select; j++) st.rle_128[j] = 0;
+		for (int j = select; j < 256; j++) if (st.rle_128[j] > 0) w128 -= (uint32_t)(j * st.rle_128[j]);
+		st.rle_buf[128] = (int)w128;
+		k = 0;
+		for (int j = select; j < 256; j++)
+			if (st.rle_128[j] > 0) { st.sym[k] = (uint16_t)((j << 8) | 128); st.weight[k] = (uint32_t)st.rle_128[j]; k++; }
+		for_each_symbol([&](int i) {
+			if (st.rle_buf[i] > 0) { st.sym[k] = (uint16_t)((1 << 8) | i); st.weight[k] = (uint32_t)st.rle_buf[i]; k++; }
+		});
+		if (k <= 354) break;
+		select++;
+		if (select >= 100) return NHW_ERR_CODEBOOK_DEV;
+	}
+	// ---- stable sort by decreasing weight (the reference's bubble sort; ties keep order)
+	for (int i = 1; i < k; i++) {
+		uint32_t wv = st.weight[i];
+		uint16_t sv = st.sym[i];
+		int j = i - 1;
+		while (j >= 0 && st.weight[j] < wv) { st.weight[j + 1] = st.weight[j]; st.sym[j + 1] = st.sym[j]; j--; }
+		st.weight[j + 1] = wv;
+		st.sym[j + 1] = sv;
+	}
+	for (int i = 0; i < k; i++) {
+		if ((st.sym[i] >> 8) == 1) st.rle_buf[st.sym[i] & 0xff] = i;
+		else st.rle_128[st.sym[i] >> 8] = i;
+	}
+	const int b = st.sym[0] == ((1 << 8) | 128) ? 1 : 0;
+	if (part == 0 && b == 0 && k > 290) return NHW_ERR_CODEBOOK_DEV;
+	if (part == 1 && select != 4 && k > 290) return NHW_ERR_CODEBOOK_DEV;
+	const bool zone = (part == 0 && select == 4 && b == 1);
+	if (!zone && k > 290) return NHW_ERR_CODEBOOK_DEV;   // the reference would index past its code table
+	// ---- emission (compress_pixel.c:279-361)
+	uint8_t *s1 = im.tmp1, *s2 = im.tmp2;
+	int c = 0, j = 0, e = 1, pack = 0, tag = 0;
+	for (int i = p1; i < p2 - 1; i++) {
+		const int pixel = s[i];
+		int pos;
+		bool direct = false;
+		if (pixel == 153) { s1[c++] = 0; continue; }
+		if (pixel == 155) { s1[c++] = 1; continue; }
+		if (pixel == 157) { s2[j++] = 0; continue; }
+		if (pixel == 159) { s2[j++] = 1; continue; }
+		if (pixel != 128 && pixel < 136 && pixel > 120) {
+			pos = st.rle_buf[pixel] & 0xffff;
+			if (pixel > 131) i += 4;
+			direct = true;
+		} else if (pixel == 128) {
+			bool overflow = false;
+			while (i < p2 - 1 && s[i + 1] == 128) {
+				e++;
+				if (e > 255) { e = 254; i--; overflow = true; break; }
+				i++;
+			}
+			if (!overflow && e > 1 && e < select) { i -= e - 1; tag = e; e = 1; }
+		}
+		for (;;) {
+			if (!direct) pos = (e == 1 ? st.rle_buf[pixel] : st.rle_128[e]) & 0xffff;
+			direct = false;
+			if (pos >= 110 && pos < 174 && zone) put_bits(words, a, pack, (1u << 6) | (uint32_t)(pos - 110), 15);
+			else {
+				if (pos >= 174 && zone) pos -= 64;
+				if (pos >= NHW_CODE_DEPTH) return NHW_ERR_CODEBOOK_DEV;   // byte outside the alphabet
+				put_bits(words, a, pack, nhw_code_bits[pos], nhw_code_len[pos]);
+			}
+			e = 1;
+			if (tag > 0) { tag--; if (tag > 0) { i++; continue; } }
+			break;
+		}
+	}
+	// ---- side outputs
+	if (part == 0) {
+		h->size_data1 = a + 1;
+		h->wavelet_type = (select > 4 || b == 0) ? 4 : 0;
+		for (int t = 0; t < 8; t++) { s1[c + t] = 0; s2[j + t] = 0; }
+		int n1 = 0, n2 = 0;
+		for (int i = 0; i < ((c >> 3) + 1) * 8; i += 8) {
+			int v = 0;
+			for (int t = 0; t < 8; t++) v |= (s1[i + t] & 1) << (7 - t);
+			im.sel1[n1++] = (uint8_t)v;
+		}
+		for (int i = 0; i < ((j >> 3) + 1) * 8; i += 8) {
+			int v = 0;
+			for (int t = 0; t < 8; t++) v |= (s2[i + t] & 1) << (7 - t);
+			im.sel2[n2++] = (uint8_t)v;
+		}
+		h->select1 = n1;
+		h->select2 = n2;
+	} else h->size_data2 = a + 1;
+	// ---- codebook: ranked symbol list, de-interleaved (even then odd positions), runs of the
+	// marker byte compressed (compress_pixel.c:400-461)
+	const int marker = part ? 128 : 3;
+	uint8_t *raw = im.tmp3 + 40000, *de = im.tmp3 + 41000;   // raw list, then its de-interleaved copy
+	int n = 0;
+	for (int i = 0; i < k; i++) {
+		if ((st.sym[i] >> 8) == 1) raw[n++] = (uint8_t)(part ? ((st.sym[i] & 0xff) | 1) : (st.sym[i] & 0xff));
+		else { raw[n++] = (uint8_t)marker; raw[n++] = (uint8_t)(st.sym[i] >> 8); }
+	}
+	if (part) h->tree_end = n;
+	int m = 0;
+	for (int i = 0; i < n; i += 2) de[m++] = raw[i];
+	for (int i = 1; i < n; i += 2) de[m++] = raw[i];
+	de[n] = 0;   // canonical: the byte after the list is not the marker
+	uint8_t *outb = part ? im.codebook2 : im.codebook1;
+	int o = 0, run = 0;
+	for (int i = 0; i < n; i++) {
+		while (i < n && de[i] == marker) { run++; i++; }
+		if (run > 0) { outb[o++] = (uint8_t)marker; outb[o++] = (uint8_t)run; run = 0; i--; }
+		else outb[o++] = de[i];
+	}
+	if (part) h->size_tree2 = o; else h->size_tree1 = o;
+	if (!part) s[262144] = saved;
+	return 0;
+}
+
+// ---- container.  Returns the stream length.
+NHW_HD void put16(uint8_t *&p, int v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p += 2; }
+NHW_HD void put32(uint8_t *&p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); p += 4; }
+NHW_HD void putn(uint8_t *&p, const uint8_t *src, int n) { for (int i = 0; i < n; i++) p[i] = src[i]; p += n; }
+
+NHW_HDN int write_stream_image(const EncImg &im, uint8_t *out)
+{
+	const EncHdr *h = im.hdr;
+	const int q = h->quality;
+	uint8_t *p = out;
+	const int exw_end = h->exw_y_len + 2 + h->exw_u_len + 2 + h->exw_v_len;
+	*p++ = (uint8_t)(h->res_low + h->wavelet_type);
+	*p++ = (uint8_t)q;
+	put16(p, h->size_tree1);
+	put16(p, h->size_tree2);
+	put32(p, (uint32_t)h->size_data1);
+	put32(p, (uint32_t)h->size_data2);
+	put16(p, h->tree_end);
+	put16(p, exw_end);
+	if (q > 12) put16(p, h->res1_len);
+	if (q >= 19) { put16(p, h->res3_len); put16(p, h->res3_bit_len); }
+	if (q > 17) put16(p, h->res4_len);
+	if (q > 12) put16(p, h->res1_bit_len);
+	if (q >= 21) { put16(p, h->res5_len); put16(p, h->res5_bit_len); }
+	if (q > 21) { put32(p, (uint32_t)h->res6_len); put16(p, h->res6_bit_len); put16(p, h->char_res1_len); }
+	if (q > 22) put16(p, h->qsetting3_len);
+	put16(p, h->select1);
+	put16(p, h->select2);
+	if (q > 15) put16(p, h->highres_comp_len);
+	put16(p, h->end_ch_res);
+	putn(p, im.codebook1, h->size_tree1);
+	putn(p, im.codebook2, h->size_tree2);
+	putn(p, im.exw, h->exw_y_len);
+	*p++ = 0; *p++ = 0;
+	putn(p, im.tmp3, h->exw_u_len);
+	*p++ = 0; *p++ = 0;
+	putn(p, im.tmp3 + 16384, h->exw_v_len);
+	if (q > 12) { putn(p, im.res1, h->res1_len); putn(p, im.res1_bit, h->res1_bit_len); putn(p, im.res1_word, h->res1_word_len); }
+	if (q > 17) putn(p, im.res4, h->res4_len);
+	if (q >= 19) { putn(p, im.res3, h->res3_len); putn(p, im.res3_bit, h->res3_bit_len); putn(p, im.res3_word, h->res3_word_len); }
+	if (q >= 21) { putn(p, im.res5, h->res5_len); putn(p, im.res5_bit, h->res5_bit_len); putn(p, im.res5_word, h->res5_word_len); }
+	putn(p, im.sel1, h->select1);
+	putn(p, im.sel2, h->select2);
+	if (q > 15) {
+		putn(p, im.res_uv64, 1024);
+		putn(p, im.highres_word, h->highres_comp_len);
+	}
+	putn(p, im.llcode, h->end_ch_res);
+	for (int i = 0; i < h->size_data2; i++) put32(p, im.words[i]);
+	return (int)(p - out);
+}

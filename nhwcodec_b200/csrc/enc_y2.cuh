@@ -1,0 +1,373 @@
+// enc_y2.cuh -- luma encoder stages after the LL2 coder (encoder/nhw_encoder.c:749-2252):
+// level-1 thresholds, pattern tags, residual side channels (res1/res3/res5), clean-up,
+// quantisation to bytes (offsetY, encoder/image_processing.c:185-521), serpentine scan and
+// the byte-stream peephole passes.  q17..q21 (q>=22 side channels res6 are not built yet).
+#pragma once
+#include "enc_ll.cuh"
+
+// ---- E14 (nhw_encoder.c:783-803), q16..q19: small level-1 coefficients -> +-7
+NHW_HD void y_e14_threshold_row(const EncImg &im, int q, int ratio, int r /* 256..511 */)
+{
+	if (!(q < 20 && q > 15)) return;
+	int16_t *P = im.proc + r * YW;
+	for (int j = 0; j < 512; j++) {
+		int v = nhw_iabs(P[j]);
+		if (v >= ratio && (j < 256 ? v < 9 : v <= 14)) P[j] = (int16_t)(P[j] > 0 ? 7 : -7);
+	}
+}
+
+// ---- E15 (nhw_encoder.c:970-1074), q>16: mark runs of three small coefficients in two of
+// the level-1 detail bands.  Band A = rows 1..254, cols 257..510; band B = rows 257..510,
+// cols 1..254.  Only sideways neighbours matter (the reference's "row above" sub-branches sit
+// behind conditions an earlier branch of the same chain already claims, so they never run):
+// rows are independent.
+NHW_HD void y_e15_tags_row(const EncImg &im, int r /* 1..510 */)
+{
+	int j0, j1;
+	bool band_a;
+	if (r >= 1 && r <= 254) { j0 = 257; j1 = 511; band_a = true; }
+	else if (r >= 257 && r <= 510) { j0 = 1; j1 = 255; band_a = false; }
+	else return;
+	int16_t *P = im.proc + r * YW;
+	for (int j = j0; j < j1; j++) {
+		int v = P[j];
+		if (v > 4 && v < 8) {
+			if (in4to7(P[j - 1]) && in4to7(P[j + 1])) { P[j] = 12700; P[j - 1] = 10100; P[j + 1] = 10100; }
+		} else if (v < -4 && v > -8) {
+			if (in_m7to_m4(P[j - 1]) && in_m7to_m4(P[j + 1])) { P[j] = 12900; P[j - 1] = 10100; P[j + 1] = 10100; }
+		} else if (v == 8) {
+			if ((P[j - 1] & 65534) == 6 || (P[j + 1] & 65534) == 6) P[j] = 10;
+			else if (band_a && P[j + 1] == 8) { P[j] = 9; P[j + 1] = 9; }
+		} else if (v == -8) {
+			if (((-P[j - 1]) & 65534) == 6 || ((-P[j + 1]) & 65534) == 6) P[j] = -9;
+			else if (band_a && P[j + 1] == -8) { P[j] = -9; P[j + 1] = -9; }
+		}
+	}
+}
+
+// ---- E16 (nhw_encoder.c:1084-1325), q>12: residual LL1 - reconstruction, walked down one
+// column; codes 12100..14900 go into res256 (im.ll1), corrections into the two cells below
+// and into one cell of the vertical-detail band.  Columns are independent given that
+// neighbours' cells are only read (scan+1 / stage-1 belong to other columns: see note).
+NHW_HD int res_setting_of(int q) { return q >= 20 ? 3 : q >= 18 ? 4 : q >= 15 ? 6 : 8; }
+
+NHW_HD void e16_band_fix_w1(int16_t *P, int stage)
+{
+	if (P[stage] == 7) { if (P[stage - 1] >= 0 && P[stage - 1] < 8) P[stage] += 2; }
+	else if (P[stage] == 8) { if (P[stage - 1] >= -2 && P[stage - 1] < 8) P[stage] += 2; }
+}
+NHW_HD void e16_band_fix_w2(int16_t *P, int stage)
+{
+	if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
+	else if (P[stage] == 7 || (P[stage] & 65534) == 8) { if (P[stage - 1] >= -2) P[stage] += 3; }
+}
+NHW_HD void e16_band_fix_w3(int16_t *P, int16_t *L, int stage, int count, int q)
+{
+	if (q >= 21) { L[count] = 14500; return; }
+	if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
+	else if (P[stage] >= 0 && ((P[stage] + 2) & 65532) == 8) { if (P[stage - 1] >= -2) P[stage] = 10; }
+	else if (P[stage] > 14 && (P[stage] & 7) == 7) P[stage]++;
+}
+NHW_HD void e16_band_fix_w5(int16_t *P, int16_t *L, int stage, int count, int res, int q)
+{
+	L[count] = 14000;
+	if (res == -4) {
+		if (P[stage] == -7 || P[stage] == -8) { if (P[stage - 1] < 2 && P[stage - 1] > -8) P[stage] = -9; }
+	} else if (res < -6) {
+		if (res < -7 && q >= 21) L[count] = 14900;
+		else if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
+		else if (P[stage] == 7 || P[stage] == 8) { if (P[stage - 1] >= -1 && P[stage - 1] < 8) P[stage] += 3; }
+	}
+}
+
+// The whole stage is run by one thread per image in the reference's order (column-major):
+// a column reads `scan+1` cells of the next column and band cells `stage-1` written by the
+// previous column, so columns are not independent.
+NHW_HDN void y_e16_residual_image(const EncImg &im, int q)
+{
+	int16_t *P = im.proc, *L = im.ll1;
+	const int rs = res_setting_of(q);
+	for (int j = 0; j < 256; j++) {
+		int scan = j, count = j;
+		for (int row = 0; row < 255; row++, scan += YW, count += 256) {
+			const int stage = (j << 9) + row + 256;
+			int res = P[scan] - L[count];
+			int a = P[scan + YW] - L[count + 256];
+			int b = P[scan + 2 * YW] - L[count + 512];   // two rows down (reads past the band on the last rows)
+			enum { NONE, W1, W2, W3, W5 } go = NONE;
+			if (res == 2 && a == 2 && b >= 2) {
+				if (b < 5 || b > 6) { L[count] = 12400; P[scan + YW] -= 2; P[scan + 2 * YW] -= 2; }
+			} else if (((res == 2 && a == 3) || (res == 3 && a == 2)) && b > 1 && b < 6) {
+				L[count] = 12400; P[scan + YW] -= 2; P[scan + 2 * YW] -= 2;
+			} else if (res == 3 && a == 3) {
+				if (b > 0 && b < 6) { L[count] = 12400; P[scan + YW] -= 2; P[scan + 2 * YW] -= 2; }
+				else if (q >= 19) { L[count] = 12100; P[scan + YW] = L[count + 256]; }
+			} else if (a == -4 && (res == 2 || res == 3) && (b == 2 || b == 3)) {
+				if (res == 2 && b == 2) P[scan + YW]++;
+				else { L[count] = 12400; P[scan + YW] -= 2; P[scan + 2 * YW] -= 2; }
+			} else if (res == 1 && a == 3 && b == 2) {
+				if (row > 0 && (P[scan - YW] - L[count - 256]) >= 0) { L[count] = 12400; P[scan + YW] -= 2; P[scan + 2 * YW] -= 2; }
+			} else if ((res == 3 || res == 4 || res == 5 || res > 6) && (a == 3 || (a & 65534) == 4)) {
+				if (res > 6) { L[count] = 12500; P[scan + YW] = L[count + 256]; }
+				else if (q >= 19) { L[count] = 12100; P[scan + YW] = L[count + 256]; }
+				else if (q == 18) {
+					if (res < 5 && a == 5) L[count + 256] = 14100;
+					else if (res >= 5) L[count] = 14100;
+					else if (res == 3 && a >= 4) L[count + 256] = 14100;
+					P[scan + YW] = L[count + 256];
+				}
+			} else if ((res == 2 || res == 3) && (a == 2 || a == 3)) {
+				if (b == 0 || b == 1) {
+					int c1 = P[scan + 1] - L[count + 1];
+					if (c1 == 2 || c1 == 3) {
+						int c2 = P[scan + YW + 1] - L[count + 257];
+						if (c2 == 2 || c2 == 3) {
+							if ((P[scan + 2 * YW + 1] - L[count + 513]) > 0) { L[count] = 12400; P[scan + YW] -= 2; P[scan + 2 * YW] -= 2; }
+						}
+					}
+				}
+			} else if (a == 4 && (res == -2 || res == -3) && (-b == 2 || -b == 3)) {
+				if (res == -2 && -b == 2) P[scan + YW]--;
+				else { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
+			} else if ((res == -3 || res == -4 || res == -5 || res < -7) && (a == -3 || a == -4 || a == -5)) {
+				if (res < -7) { L[count] = 12600; P[scan + YW] = L[count + 256]; }
+				else if (q >= 19) { L[count] = 12200; P[scan + YW] = L[count + 256]; }
+				else if (q == 18) {
+					if (res > -5 && a == -5) L[count + 256] = 14000;
+					else if (res <= -5) L[count] = 14000;
+					else if (res == -3 && a <= -4) L[count + 256] = 14000;
+					P[scan + YW] = L[count + 256];
+				}
+			} else if (a == -2 || a == -3) {
+				if (res == -2 || res == -3) {
+					if (-b > 0) { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
+					else if (res == -3 && q >= 21) L[count] = 14500;
+					else if (b == 0) {
+						int c1 = P[scan + 1] - L[count + 1];
+						if (c1 == -2 || c1 == -3) {
+							int c2 = P[scan + YW + 1] - L[count + 257];
+							if (c2 == -2 || c2 == -3) {
+								if ((P[scan + 2 * YW + 1] - L[count + 513]) < 0) { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
+							}
+						}
+					} else if (res == -2) go = W2;
+					else go = W3;
+				} else if (res == -1 && a == -3 && b == -2) {
+					if (row > 0 && (P[scan - YW] - L[count - 256]) <= 0) { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
+				} else if (res == -1) {
+					if (-b == 3) { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
+					else go = W1;
+				} else if (res == -4) {
+					if (-b > 1 && -b < 4) { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
+					else go = W5;
+				}
+			} else if (res == 0 || res == -1) go = W1;
+			else if (res == -2) go = W2;
+			else if (res == -3) go = W3;
+			else if (res < -rs) go = W5;
+
+			if (go == W1) e16_band_fix_w1(P, stage);
+			else if (go == W2) e16_band_fix_w2(P, stage);
+			else if (go == W3) e16_band_fix_w3(P, L, stage, count, q);
+			else if (go == W5) e16_band_fix_w5(P, L, stage, count, res, q);
+		}
+	}
+}
+
+// ---- E16b (nhw_encoder.c:1327-1420): classify what is left, count the side-channel words
+NHW_HDN void y_e16b_classify_image(const EncImg &im, int q)
+{
+	int16_t *P = im.proc, *L = im.ll1;
+	const int rs = res_setting_of(q);
+	int w1 = 0, w3 = 0, w5 = 0;
+	for (int row = 0, count = 0; row < 256; row++) {
+		int scan = row * YW;
+		for (int j = 0; j < 256; j++, scan++, count++) {
+			const int stage = (j << 9) + row + 256;
+			if (L[count] < 12000) {
+				int res = P[scan] - L[count];
+				L[count] = 0;
+				if (res == 0 || res == 1) {
+					if (P[stage] == -7 || P[stage] == -8) { if (P[stage - 1] < 2 && P[stage - 1] > -8) P[stage] = -9; }
+				} else if (res == 2) {
+					if (P[stage] > 15 && !(P[stage] & 7)) P[stage]--;
+					else if (P[stage] == -7 || P[stage] == -8) { if (P[stage - 1] <= 1) P[stage] = -9; }
+					else if (P[stage] == -6) { if (P[stage - 1] <= -1 && P[stage - 1] > -8) P[stage] = -9; }
+				} else if (res == 3) {
+					if (q >= 21) { L[count] = 144; w5++; }
+					else if (P[stage] > 15 && !(P[stage] & 7)) P[stage]--;
+					else if (P[stage] <= 0 && (((-P[stage]) + 2) & 65532) == 8) { if (P[stage - 1] <= 2) P[stage] = -10; }
+				} else if (res > rs) {
+					L[count] = 141; w1++;
+					if (res == 4) {
+						if (P[stage] == 7 || (P[stage] & 65534) == 8) { if (P[stage - 1] >= 0 && P[stage - 1] < 8) P[stage] += 2; }
+					} else if (res > 6) {
+						if (res > 7 && q >= 21) { L[count] = 148; w5++; w1++; }
+						else if (P[stage] > 15 && !(P[stage] & 7)) P[stage]--;
+						else if (P[stage] == -6 || P[stage] == -7 || P[stage] == -8) { if (P[stage - 1] < 0 && P[stage - 1] > -8) P[stage] = -9; }
+					}
+				}
+			} else {
+				switch (L[count]) {
+				case 14000: L[count] = 140; w1++; break;
+				case 14500: L[count] = 145; w5++; break;
+				case 12200: L[count] = 122; w3++; break;
+				case 12100: L[count] = 121; w3++; break;
+				case 12300: L[count] = 123; w3++; break;
+				case 12400: L[count] = 124; w3++; break;
+				case 14100: L[count] = 141; w1++; break;
+				case 12500: L[count] = 125; w3++; w1++; break;
+				case 12600: L[count] = 126; w3++; w1++; break;
+				case 14900: L[count] = 149; w5++; w1++; break;
+				default: break;
+				}
+			}
+		}
+	}
+	im.hdr->res1_word_len = w1;
+	im.hdr->res3_word_len = w3;
+	im.hdr->res5_word_len = w5;
+}
+
+// ---- E18 (nhw_encoder.c:1498-1887): turn the codes left in res256 into the res1/res3/res5
+// side channels: column positions per row (254 = end of row), pair-delta packed, with the
+// positions' LSBs and the 1- or 2-bit words in separate bit planes.
+// which: 1, 3 or 5.  Scratch: tmp1 (positions), tmp2 (copy), tmp3 (words).
+NHW_HDN void y_e18_pack_list_image(const EncImg &im, int which)
+{
+	int16_t *L = im.ll1;
+	EncHdr *h = im.hdr;
+	uint8_t *pos = im.tmp1, *cpy = im.tmp2, *wrd = im.tmp3;
+	uint8_t *out, *out_bit, *out_word;
+	if (which == 1) { out = im.res1; out_bit = im.res1_bit; out_word = im.res1_word; }
+	else if (which == 3) { out = im.res3; out_bit = im.res3_bit; out_word = im.res3_word; }
+	else { out = im.res5; out_bit = im.res5_bit; out_word = im.res5_word; }
+	int count = 0, e = 0;
+	for (int row = 0; row < 256; row++) {
+		int scan = row * 256;
+		for (int j = 0; j < 256; j++, scan++) {
+			if (j == 254) { L[scan] = 0; L[scan + 1] = 0; pos[count++] = 254; j++; continue; }
+			int v = L[scan];
+			if (v == 0) continue;
+			int nv = -1, w = 0;
+			if (which == 1) {
+				if (v == 141) { nv = 0; w = 1; } else if (v == 140) { nv = 0; w = 0; }
+				else if (v == 126) { nv = 122; w = 0; } else if (v == 125) { nv = 121; w = 1; }
+				else if (v == 148) { nv = 144; w = 1; } else if (v == 149) { nv = 145; w = 0; }
+			} else if (which == 3) {
+				if (v == 121) { nv = 0; w = 1; } else if (v == 122) { nv = 0; w = 0; }
+				else if (v == 123) { nv = 0; w = 2; } else if (v == 124) { nv = 0; w = 3; }
+			} else {
+				if (v == 144) { nv = 0; w = 1; } else if (v == 145) { nv = 0; w = 0; }
+			}
+			if (nv < 0) continue;
+			pos[count++] = (uint8_t)j;
+			L[scan] = (int16_t)nv;
+			wrd[e++] = (uint8_t)w;
+		}
+	}
+	for (int i = 0; i < 8; i++) wrd[e + i] = 0;   // the reference reads up to 7 entries past the end
+	// drop end-of-row markers the decoder can infer from a decreasing position
+	for (int i = 0; i < count; i++) cpy[i] = pos[i];
+	int len = 1;
+	for (int i = 1; i < count - 1; i++) {
+		if (cpy[i] == 254 && cpy[i - 1] != 254 && cpy[i + 1] != 254) {
+			if (cpy[i - 1] <= cpy[i + 1]) pos[len++] = cpy[i];
+		} else pos[len++] = cpy[i];
+	}
+	pos[len++] = cpy[count - 1];
+	// LSB plane of the real positions (cpy reused as the compacted list)
+	int np = 0;
+	for (int i = 0; i < len; i++)
+		if (pos[i] != 254) cpy[np++] = pos[i];
+	for (int i = 0; i < 8; i++) cpy[np + i] = 0;
+	const int bit_len = (np >> 3) + 1;
+	for (int i = 0, o = 0; i < ((np >> 3) << 3) + 8; i += 8) {
+		int b = 0;
+		for (int k = 0; k < 8; k++) b |= (cpy[i + k] & 1) << (7 - k);
+		out_bit[o++] = (uint8_t)b;
+	}
+	// halve the positions and merge (small delta, small delta) pairs into one byte >= 128
+	int olen = 1;
+	out[0] = pos[0] >> 1;
+	for (int i = 1; i < len - 1; i++) {
+		int cur = pos[i] >> 1, d1 = cur - (pos[i - 1] >> 1);
+		if (d1 >= 0 && d1 < 8) {
+			int d2 = (pos[i + 1] >> 1) - cur;
+			if (d2 >= 0 && d2 < 16) { out[olen++] = (uint8_t)(128 + (d1 << 4) + d2); i++; }
+			else out[olen++] = (uint8_t)cur;
+		} else out[olen++] = (uint8_t)cur;
+	}
+	// word plane
+	int wbytes = 0;
+	for (int i = 0; i < ((e >> 3) << 3) + 8; i += 8) {
+		if (which == 3) {
+			out_word[wbytes++] = (uint8_t)(((wrd[i] & 3) << 6) | ((wrd[i + 1] & 3) << 4) | ((wrd[i + 2] & 3) << 2) | (wrd[i + 3] & 3));
+			out_word[wbytes++] = (uint8_t)(((wrd[i + 4] & 3) << 6) | ((wrd[i + 5] & 3) << 4) | ((wrd[i + 6] & 3) << 2) | (wrd[i + 7] & 3));
+		} else {
+			int b = 0;
+			for (int k = 0; k < 8; k++) b |= (wrd[i + k] & 1) << (7 - k);
+			out_word[wbytes++] = (uint8_t)b;
+		}
+	}
+	if (which == 1) { h->res1_len = olen; h->res1_bit_len = bit_len; h->res1_word_len = wbytes; }
+	else if (which == 3) { h->res3_len = olen; h->res3_bit_len = bit_len; h->res3_word_len = wbytes; }
+	else { h->res5_len = olen; h->res5_bit_len = bit_len; h->res5_word_len = wbytes; }
+}
+
+// ---- E19 (nhw_encoder.c:1893-1910): restore the level-2 region from the resIII snapshot,
+// zeroing LL2 except tagged cells
+NHW_HD void y_e19_restore_row(const EncImg &im, int r /* 0..255 */)
+{
+	int16_t *P = im.proc + r * YW;
+	const int16_t *S = im.ll2s + r * 256;
+	for (int j = 0; j < 256; j++) P[j] = (j < 128 && r < 128 && S[j] <= 8000) ? (int16_t)0 : S[j];
+}
+
+// ---- E20 (nhw_encoder.c:1914-2098): clean-up of the three level-1 detail bands.
+// pass 0: rows 1..254, cols 257..510   pass 1: rows 256..510, cols 1..255
+// pass 2: rows 256..510, cols 257..510.  In place, reads the row above after it was edited.
+NHW_HD void e20_cell(int16_t *P, int a, int j, int jmax, int lo, int yw, int yw2, int pass)
+{
+	if (nhw_iabs(P[a]) >= lo) {
+		if (nhw_iabs(P[a]) < yw2) {
+			int cnt = 0;
+			if (nhw_iabs(P[a - 1]) + 2 >= 8) cnt++;
+			if (nhw_iabs(P[a + 1]) + 2 >= 8) cnt++;
+			if (nhw_iabs(P[a - YW]) + 2 >= 8) cnt++;
+			if (nhw_iabs(P[a + YW]) + 2 >= 8) cnt++;
+			if (cnt < 3 && P[a] < yw && P[a] > -yw) {
+				if (pass == 0) { if (P[a] < -6) P[a] = -7; else if (P[a] > 6) P[a] = 7; }
+				else P[a] = (int16_t)(P[a] < 0 ? -7 : 7);
+			} else if (pass == 1 && cnt == 0 && nhw_iabs(P[a]) < yw2) P[a] = (int16_t)(P[a] < 0 ? -7 : 7);
+		}
+	} else P[a] = 0;
+	if (nhw_iabs(P[a]) > 6) {
+		int e = P[a];
+		if (e >= 8 && (e & 7) < 2) {
+			if (P[a + 1] > 7 && P[a + 1] < 10000) P[a + 1]--;
+		} else if (e == -7 && P[a + 1] == 8) P[a] = -8;
+		else if (e == 8 && P[a + 1] == -7) P[a + 1] = -8;
+		else if (e < -7 && ((-e) & 7) < 2) {
+			if (P[a + 1] < -14 && P[a + 1] < 10000) {
+				if (((-P[a + 1]) & 7) == 7) P[a + 1]++;
+				else if (((-P[a + 1]) & 7) < 2 && j < jmax && P[a + 2] <= 0) P[a + 1]++;
+			}
+		}
+	}
+}
+
+NHW_HDN void y_e20_cleanup_image(const EncImg &im, int q, int ratio)
+{
+	int16_t *P = im.proc;
+	int yw, yw2;
+	if (q > 22) { yw = 8; yw2 = 4; } else { yw = 9; yw2 = 9; }
+	for (int r = 1; r < 255; r++)
+		for (int j = 257; j < 511; j++) e20_cell(P, r * YW + j, j, 510, ratio - 2, yw, yw2, 0);
+	if (q > 22) { yw = 8; yw2 = 4; } else if (q > 17) { yw = 8; yw2 = 9; } else { yw = 9; yw2 = 9; }
+	for (int r = 256; r < 511; r++)
+		for (int j = 1; j < 256; j++) e20_cell(P, r * YW + j, j, 254, ratio - 2, yw, yw2, 1);
+	yw = q > 22 ? 8 : 11;
+	for (int r = 256; r < 511; r++)
+		for (int j = 257; j < 511; j++) e20_cell(P, r * YW + j, j, 510, ratio - 1, yw, yw, 2);
+}

@@ -1,0 +1,191 @@
+// enc_y3.cuh -- luma: quantisation of the coefficient plane to the byte alphabet
+// (offsetY, encoder/image_processing.c:185-521, q>16 branches), the serpentine scan
+// (encoder/nhw_encoder.c:2108-2132) and the three peephole passes over the byte stream
+// (encoder/nhw_encoder.c:2136-2252).
+#pragma once
+#include "enc_y2.cuh"
+
+// The two escape ladders are not perfectly regular, so keep them as tables.
+#ifdef __CUDA_ARCH__
+__constant__ uint8_t c_extra_words1[19] = {10, 12, 14, 18, 20, 22, 26, 28, 30, 34, 36, 38, 42, 44, 46, 50, 52, 54, 58};
+__constant__ uint8_t c_extra_words2[19] = {60, 62, 66, 68, 70, 74, 76, 78, 82, 84, 86, 90, 92, 94, 98, 100, 102, 106, 108};
+#define NHW_EXTRA1(k) c_extra_words1[k]
+#define NHW_EXTRA2(k) c_extra_words2[k]
+#else
+static const uint8_t h_extra_words1[19] = {10, 12, 14, 18, 20, 22, 26, 28, 30, 34, 36, 38, 42, 44, 46, 50, 52, 54, 58};
+static const uint8_t h_extra_words2[19] = {60, 62, 66, 68, 70, 74, 76, 78, 82, 84, 86, 90, 92, 94, 98, 100, 102, 106, 108};
+#define NHW_EXTRA1(k) h_extra_words1[k]
+#define NHW_EXTRA2(k) h_extra_words2[k]
+#endif
+
+// ---- offsetY loop 1 (image_processing.c:194-237): neighbouring multiples of 8 in the detail
+// bands; flat raster order (col 0 looks at the previous row's last, already-visited cell).
+NHW_HDN void y_offset_pairs_image(const EncImg &im)
+{
+	int16_t *P = im.proc;
+	for (int i = 0; i < 4 * 65536; i++) {
+		const int col = i & 511;
+		if (!(i >= 2 * 65536 || col >= 256)) continue;
+		if (!(P[i] > 7 && P[i + 1] > 7 && col < 511)) continue;
+		int a = P[i];
+		if ((a & 7) || (P[i + 1] & 7)) continue;
+		if (a > 15) {
+			if (i > 0) {
+				if (P[i - 1] <= 0) P[i]--;
+				else if (P[i + 1] > 15) {
+					if (col < 510 && P[i + 2] <= 0) P[i + 1]--;
+				}
+			}
+		} else if (P[i + 1] > 15) {
+			if (col < 510 && P[i + 2] <= 0) P[i + 1]--;
+		}
+	}
+}
+
+// ---- offsetY loops 2+3 (image_processing.c:239-311), q>16: patterns in the level-2 region
+NHW_HDN void y_offset_patterns_image(const EncImg &im)
+{
+	int16_t *P = im.proc;
+	for (int r = 0; r < 256; r++) {
+		int a = r * YW + 1;
+		for (int j = 1; j < 255; j++, a++) {
+			int v = P[a];
+			if (v > 3 && v < 8) {
+				if (in4to7(P[a - 1])) {
+					if (in4to7(P[a + 1])) { P[a] = 12700; P[a - 1] = 10100; j++; a++; }
+					else if (in4to7(P[a + YW - 1]) && in4to7(P[a + YW])) {
+						P[a - 1] = 12100; P[a] = 10100; P[a + YW - 1] = 10100; P[a + YW] = 10100; j++; a++;
+					}
+				}
+			} else if (v < -3 && v > -8) {
+				if (in_m7to_m4(P[a - 1])) {
+					if (in_m7to_m4(P[a + 1])) { P[a] = 12900; P[a - 1] = 10100; j++; a++; }
+					else if (in_m7to_m4(P[a + YW - 1]) && in_m7to_m4(P[a + YW])) {
+						P[a - 1] = 12200; P[a] = 10100; P[a + YW - 1] = 10100; P[a + YW] = 10100; j++; a++;
+					}
+				}
+			}
+		}
+	}
+	for (int r = 0; r < 256; r++) {
+		int a = r * YW;
+		for (int j = 0; j < 255; j++, a++) {
+			int v = P[a], w = P[a + 1];
+			if (v >= 5 && v <= 7) { if (w >= 5 && w <= 7) { P[a] = 10300; j++; a++; } }
+			else if (v <= -5 && v >= -7) { if (w <= -5 && w >= -7) { P[a] = 10204; j++; a++; } }
+		}
+	}
+}
+
+// ---- offsetY loop 4 (image_processing.c:312-519): coefficient -> byte
+NHW_HDN void y_offset_quant_image(const EncImg &im, int m1)
+{
+	int16_t *P = im.proc;
+	for (int i = 0; i < 4 * 65536; i++) {
+		const bool inrow = (i & 511) < 511;
+		int a = P[i];
+		if (a > 10000) {
+			int b = a == 10100 ? 128 : a == 12700 ? 127 : a == 12900 ? 129 : a == 10204 ? 125 : a == 10300 ? 126 :
+			        a == 12100 ? 121 : a == 12200 ? 122 : -1;
+			if (b >= 0) { P[i] = (int16_t)b; continue; }
+		}
+		if (a > 127) {
+			int k = ((a & 0xfff8) - 128) >> 3;
+			P[i] = NHW_EXTRA1(k > 18 ? 18 : k);
+			continue;
+		} else if (a < -127) {
+			int k = (((-a) & 0xfff8) - 128) >> 3;
+			P[i] = NHW_EXTRA2(k > 18 ? 18 : k);
+			continue;
+		}
+		if (a < -12 && ((-a) & 7) == 6) {
+			if (inrow && P[i + 1] == -7) P[i + 1] = -9;
+		}
+		if (a < 0) {
+			if (a == -7 && P[i + 1] == 8 && inrow) { P[i] = -8; a = -8; }
+			a = -a;
+			if (a > 14 && (a & 7) == 7 && P[i + 1] > 0 && P[i + 1] < 8) a -= 2;
+			if ((a & 7) < 7) a &= 504;
+			a = -a;
+		} else if (a == 8 && P[i + 1] == -7 && inrow) P[i + 1] = -8;
+		else if (a > 12 && (a & 7) >= 6) {
+			if (inrow && P[i + 1] == 7) P[i + 1] = 9;
+		}
+		if (a < m1 && a > -m1) { P[i] = 128; continue; }
+		P[i] = (int16_t)((a + 128) & 248);
+	}
+}
+
+// ---- E23: serpentine scan, 4-column strips, two rows per step, second row reversed
+NHW_HD void y_scan_strip(const EncImg &im, int strip /* 0..127 */)
+{
+	const int16_t *P = im.proc + strip * 4;
+	uint8_t *s = im.scan + strip * 2048;
+	for (int k = 0; k < 256; k++) {
+		const int16_t *r0 = P + (2 * k) * YW, *r1 = r0 + YW;
+		s[0] = (uint8_t)r0[0]; s[1] = (uint8_t)r0[1]; s[2] = (uint8_t)r0[2]; s[3] = (uint8_t)r0[3];
+		s[4] = (uint8_t)r1[3]; s[5] = (uint8_t)r1[2]; s[6] = (uint8_t)r1[1]; s[7] = (uint8_t)r1[0];
+		s += 8;
+	}
+}
+
+// ---- E24: peephole passes over the 262144 luma bytes
+NHW_HDN void y_peephole_image(const EncImg &im)
+{
+	uint8_t *s = im.scan;
+	const int N = 4 * 65536;
+	for (int i = 0; i < N - 4; i++) {
+		if (s[i] != 128 && s[i + 1] == 128) {
+			if (s[i + 2] == 128) {
+				if (s[i + 3] == 128) {
+					int x = s[i], y = s[i + 4];
+					if ((x == 136 || x == 120) && (y == 136 || y == 120)) {
+						s[i] = (uint8_t)(132 + (x == 120 ? 2 : 0) + (y == 120 ? 1 : 0));
+						s[i + 4] = 201;
+						i += 4;
+					} else i += 3;
+				} else i += 2;
+			} else i++;
+		}
+	}
+	s[0] = s[1] = s[2] = s[3] = 128;
+	s[N - 4] = s[N - 3] = s[N - 2] = s[N - 1] = 128;
+	int sel1 = 0, sel2 = 0;
+	for (int i = 4; i < N - 4; i++) {
+		if (s[i] != 136 && s[i] != 120) continue;
+		const bool nxt = (s[i + 1] == 120 || s[i + 1] == 136);
+		if (s[i + 2] == 128 && nxt && s[i - 1] == 128 && s[i - 2] == 128 && s[i - 3] == 128 && s[i - 4] == 128) {
+			s[i + 1] = (uint8_t)(s[i + 1] == 120 ? 157 : 159);
+			sel2++;
+		} else if (s[i - 1] == 128 && nxt && s[i + 2] == 128 && s[i + 3] == 128 && s[i + 4] == 128 && s[i + 5] == 128) {
+			s[i + 1] = (uint8_t)(s[i + 1] == 120 ? 157 : 159);
+			sel2++;
+		} else if (s[i - 1] == 128 && s[i - 2] == 128 && s[i - 3] == 128 && s[i - 4] == 128 && s[i + 1] == 128) {
+			s[i] = (uint8_t)(s[i] == 136 ? 153 : 155);
+			sel1++;
+		} else if (s[i - 1] == 128 && s[i + 1] == 128 && s[i + 2] == 128 && s[i + 3] == 128 && s[i + 4] == 128) {
+			s[i] = (uint8_t)(s[i] == 136 ? 153 : 155);
+			sel1++;
+		}
+	}
+	im.hdr->select1 = sel1;
+	im.hdr->select2 = sel2;
+	for (int i = 0, count = 0; i < N; i++) {
+		while (s[i] == 128 && s[i + 1] == 128) {
+			count++;
+			if (count > 255) {
+				for (int k = 0; k < 4; k++) {
+					if (s[i + k] == 153) s[i + k] = 124;
+					else if (s[i + k] == 155) s[i + k] = 123;
+				}
+				i--;
+				count = 0;
+			} else i++;
+		}
+		if (count >= 252) {
+			if (s[i + 1] == 153) s[i + 1] = 124;
+			else if (s[i + 1] == 155) s[i + 1] = 123;
+		}
+		count = 0;
+	}
+}

@@ -15,6 +15,8 @@
 // Level 2 needs no transpose at all (LL1 is consumed in the orientation level 1 left it in).
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
+#include "enc_img.cuh"
+#include "dwt_core.cuh"
 
 namespace {
 
@@ -59,14 +61,14 @@ __device__ __forceinline__ void rgb_to_ycc(int c0, int c1, int c2, const ColorPa
 
 __global__ void __launch_bounds__(256) k_colorspace(const uint8_t *__restrict__ rgb, int16_t *__restrict__ yout,
                                                     uint8_t *__restrict__ uout, uint8_t *__restrict__ vout,
-                                                    ColorParams p)
+                                                    size_t ystride, size_t cstride, ColorParams p)
 {
 	__shared__ uint8_t su[CS_ROWS + 1][512];
 	__shared__ uint8_t sv[CS_ROWS + 1][512];
 	const int img = blockIdx.y;
 	const int y0 = blockIdx.x * CS_ROWS;
 	const uint8_t *src = rgb + (size_t)img * NHW_RGB_BYTES;
-	int16_t *yp = yout ? yout + (size_t)img * NHW_YPLANE : nullptr;
+	int16_t *yp = yout ? yout + (size_t)img * ystride : nullptr;
 
 	for (int idx = threadIdx.x; idx < (CS_ROWS + 1) * 512; idx += 256) {
 		int row = idx >> 9, x = idx & 511;
@@ -105,8 +107,8 @@ __global__ void __launch_bounds__(256) k_colorspace(const uint8_t *__restrict__ 
 			U = (hu[0] + 2 * hu[1] + hu[2] + 2) >> 2;
 			V = (hv[0] + 2 * hv[1] + hv[2] + 2) >> 2;
 		}
-		if (uout) uout[(size_t)img * NHW_CPLANE + r * 256 + cx] = (uint8_t)U;
-		if (vout) vout[(size_t)img * NHW_CPLANE + r * 256 + cx] = (uint8_t)V;
+		if (uout) uout[(size_t)img * cstride + r * 256 + cx] = (uint8_t)U;
+		if (vout) vout[(size_t)img * cstride + r * 256 + cx] = (uint8_t)V;
 	}
 }
 
@@ -168,13 +170,13 @@ __device__ __forceinline__ unsigned lane_map(const int *e, int x0)
 #define PRE_WARPS 4
 
 __global__ void __launch_bounds__(32 * PRE_WARPS) k_pre_energy(const int16_t *__restrict__ y, int16_t *__restrict__ energy,
-                                                               uint32_t *__restrict__ rowmap)
+                                                               uint32_t *__restrict__ rowmap, size_t ystride, size_t astride)
 {
 	__shared__ __align__(16) int16_t rows[PRE_WARPS][3][512];
 	const int img = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int r = 1 + blockIdx.x * PRE_WARPS + warp;
 	if (r > 510) return;
-	const int16_t *src = y + (size_t)img * NHW_YPLANE;
+	const int16_t *src = y + (size_t)img * ystride;
 	for (int k = 0; k < 3; k++) {
 		const int4 *s4 = reinterpret_cast<const int4 *>(src + (r - 1 + k) * 512);
 		int4 a = s4[lane * 2], b = s4[lane * 2 + 1];
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(32 * PRE_WARPS) k_pre_energy(const int16_t *__
 		int x = x0 + t;
 		e[t] = (x >= 1 && x <= 510) ? lap_energy(up, mid, dn, x) : 0;
 	}
-	int16_t *dst = energy + (size_t)img * NHW_YPLANE + r * 512 + x0;
+	int16_t *dst = energy + (size_t)img * astride + r * 512 + x0;
 #pragma unroll
 	for (int t = 0; t < 16; t++) dst[t] = (int16_t)e[t];
 	unsigned m = lane_map(e, x0);
@@ -218,13 +220,13 @@ __global__ void k_pre_chain(const uint32_t *__restrict__ rowmap, uint8_t *__rest
 // final kernel values nhw_kernel[r][x] = sign * ((15|res| + count + carry) >> 4)
 __global__ void __launch_bounds__(32 * PRE_WARPS) k_pre_apply(const int16_t *__restrict__ energy,
                                                               const uint8_t *__restrict__ rowcarry,
-                                                              int16_t *__restrict__ kern)
+                                                              int16_t *__restrict__ kern, size_t astride)
 {
 	const int img = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int r = 1 + blockIdx.x * PRE_WARPS + warp;
 	if (r > 510) return;
 	const int x0 = lane * 16;
-	const int16_t *src = energy + (size_t)img * NHW_YPLANE + r * 512 + x0;
+	const int16_t *src = energy + (size_t)img * astride + r * 512 + x0;
 	int e[16];
 	{
 		const int4 *s4 = reinterpret_cast<const int4 *>(src);
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(32 * PRE_WARPS) k_pre_apply(const int16_t *__r
 			cls = carry_class((unsigned)(v & 15));
 		}
 	}
-	int16_t *dst = kern + (size_t)img * NHW_YPLANE + r * 512 + x0;
+	int16_t *dst = kern + (size_t)img * astride + r * 512 + x0;
 #pragma unroll
 	for (int t = 0; t < 16; t++) dst[t] = out[t];
 }
@@ -316,11 +318,11 @@ __device__ __forceinline__ void pair_nudge(int res, int cnt, int a, int &d0, int
 	}
 }
 
-__global__ void __launch_bounds__(256) k_pre_nudge(const int16_t *__restrict__ kern, int16_t *__restrict__ y)
+__global__ void __launch_bounds__(256) k_pre_nudge(const int16_t *__restrict__ kern, int16_t *__restrict__ y, size_t astride, size_t ystride)
 {
 	const int img = blockIdx.y, r = 1 + blockIdx.x, p = threadIdx.x;
 	if (p >= 255) return;
-	const int16_t *k = kern + (size_t)img * NHW_YPLANE + r * 512;
+	const int16_t *k = kern + (size_t)img * astride + r * 512;
 	int j = 1 + 2 * p;
 	int res = k[j], cnt = k[j + 1];
 	int a;
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(256) k_pre_nudge(const int16_t *__restrict__ k
 	else a = 0;
 	int d0, d1;
 	pair_nudge(res, cnt, a, d0, d1);
-	int16_t *dst = y + (size_t)img * NHW_YPLANE + r * 512 + j;
+	int16_t *dst = y + (size_t)img * ystride + r * 512 + j;
 	if (d0) dst[0] = (int16_t)(dst[0] + d0);
 	if (d1) dst[1] = (int16_t)(dst[1] + d1);
 }
@@ -337,68 +339,15 @@ __global__ void __launch_bounds__(256) k_pre_nudge(const int16_t *__restrict__ k
 // =====================================================================================
 // wavelet analysis
 // =====================================================================================
-// 5-tap low / 3-tap high of the first pass (downfilter53IV, filters.c:346-386), mirror
-// extension x[-1]=x[1], x[-2]=x[2], x[N]=x[N-2].  Results are stored as int16 like the reference.
-template <typename Ld>
-__device__ __forceinline__ int tap_low(Ld ld, int e, int N)
-{
-	int c = 2 * e;
-	int xm2 = ld(c >= 2 ? c - 2 : 2), xm1 = ld(c >= 1 ? c - 1 : 1), x0 = ld(c), xp1 = ld(c + 1);
-	int xp2 = ld(c + 2 < N ? c + 2 : N - 2);
-	return 6 * x0 + 2 * (xm1 + xp1) - (xm2 + xp2);
-}
-
-// high-pass residue r of the second-pass filters (filters.c:62-84,212-231): the pair parity
-// flag `m` makes the odd output of each pair round its predictor up when both sums are odd.
-template <typename Ld>
-__device__ __forceinline__ int tap_high_lifted(Ld ld, int e)
-{
-	int a = ld(2 * e) + ld(2 * e + 2);
-	if ((e & 1) && (a & 1) && ((ld(2 * e - 2) + ld(2 * e)) & 1)) a++;
-	return ld(2 * e + 1) - (a >> 1);
-}
-
-// remainder fed forward by downfilter53VI's low band (filters.c:245-246,266-274)
-__device__ __forceinline__ int vi_remainder(int r)
-{
-	if (r >= 0) { int q = r & 63; return q < 32 ? (q >> 2) : -((64 - q) >> 2); }
-	int q = (-r) & 63;
-	return q < 32 ? -(q >> 2) : ((64 - q) >> 2);
-}
-
-// one output of the second (column) pass.  `fine` selects downfilter53VI (rows of the
-// horizontal low band) vs downfilter53 (rows of the horizontal high band).
-template <typename Ld>
-__device__ __forceinline__ int second_pass_low(Ld ld, int e, int N, bool fine)
-{
-	int r = tap_low(ld, e, N);
-	if (!fine) return nhw_sround(r, 8, 4);
-	int acc = r;
-	if (e > 0) acc += vi_remainder(tap_low(ld, e - 1, N));
-	return nhw_sround((int)(int16_t)acc, 32, 6);
-}
-
-template <typename Ld>
-__device__ __forceinline__ int second_pass_high(Ld ld, int e, int N, bool fine)
-{
-	if (e == N / 2 - 1) {
-		int d = ld(N - 1) - ld(N - 2);
-		return fine ? (d >> 3) : ((d + 1) >> 1);
-	}
-	int r = tap_high_lifted(ld, e);
-	if (fine) return nhw_sround(r, 4, 3);
-	return r > 0 ? ((r + 1) >> 1) : (r >> 1);
-}
-
 // ---- level 1, row pass: X[y][x] -> R[y][k], k<N/2 low, k>=N/2 high.  One warp per row. ----
 template <int N>
-__global__ void __launch_bounds__(256) k_dwt_rows(const int16_t *__restrict__ in, int16_t *__restrict__ out, int plane)
+__global__ void __launch_bounds__(256) k_dwt_rows(const int16_t *__restrict__ in, int16_t *__restrict__ out, size_t in_stride, size_t out_stride)
 {
 	__shared__ __align__(16) int16_t srow[8][N + 8];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int y = blockIdx.x * 8 + warp;
-	const int16_t *src = in + (size_t)blockIdx.y * plane + y * N;
-	int16_t *dst = out + (size_t)blockIdx.y * plane + y * N;
+	const int16_t *src = in + (size_t)blockIdx.y * in_stride + y * N;
+	int16_t *dst = out + (size_t)blockIdx.y * out_stride + y * N;
 	for (int i = lane; i < N / 8; i += 32)
 		reinterpret_cast<int4 *>(srow[warp])[i] = reinterpret_cast<const int4 *>(src)[i];
 	__syncwarp();
@@ -406,19 +355,18 @@ __global__ void __launch_bounds__(256) k_dwt_rows(const int16_t *__restrict__ in
 	auto ld = [&](int i) { return (int)s[i]; };
 	for (int e = lane; e < N / 2; e += 32) {
 		dst[e] = (int16_t)tap_low(ld, e, N);
-		int h = (e == N / 2 - 1) ? ((s[N - 1] - s[N - 2]) << 1) : (2 * s[2 * e + 1] - (s[2 * e] + s[2 * e + 2]));
-		dst[N / 2 + e] = (int16_t)h;
+		dst[N / 2 + e] = (int16_t)first_pass_high(ld, e, N);
 	}
 }
 
 // ---- level 1, column pass + transpose: R[y][k] -> P[k][m].  CTA = 32 columns k. ----
 template <int N>
-__global__ void __launch_bounds__(256) k_dwt_cols_t(const int16_t *__restrict__ in, int16_t *__restrict__ out, int plane)
+__global__ void __launch_bounds__(256) k_dwt_cols_t(const int16_t *__restrict__ in, int16_t *__restrict__ out, size_t in_stride, size_t out_stride)
 {
 	extern __shared__ int16_t tile[];   // [N][33]
 	const int k0 = blockIdx.x * 32;
-	const int16_t *src = in + (size_t)blockIdx.y * plane;
-	int16_t *dst = out + (size_t)blockIdx.y * plane;
+	const int16_t *src = in + (size_t)blockIdx.y * in_stride;
+	int16_t *dst = out + (size_t)blockIdx.y * out_stride;
 	for (int i = threadIdx.x; i < N * 32; i += 256) {
 		int yy = i >> 5, kk = i & 31;
 		tile[yy * 33 + kk] = src[yy * N + k0 + kk];
@@ -443,15 +391,15 @@ __global__ void __launch_bounds__(256) k_dwt_cols_t(const int16_t *__restrict__ 
 // `res256`) as a dense NxN array.
 template <int N>
 __global__ void __launch_bounds__(N) k_dwt_level_smem(const int16_t *in, int16_t *out,
-                                                      int16_t *__restrict__ ll_copy, int plane, int stride,
-                                                      int in_transposed)
+                                                      int16_t *__restrict__ ll_copy, size_t in_stride, size_t out_stride,
+                                                      size_t ll_stride, int stride, int in_transposed)
 {
 	extern __shared__ int16_t sm[];
 	constexpr int S = N + 2;            // padded stride: conflict-free along both axes
 	int16_t *band = sm;                 // band[k*S + m] = J[m][k]
 	int16_t *rowbuf = sm + N * S;       // 2 rows of N
-	const int16_t *src = in + (size_t)blockIdx.x * plane;
-	int16_t *dst = out + (size_t)blockIdx.x * plane;
+	const int16_t *src = in + (size_t)blockIdx.x * in_stride;
+	int16_t *dst = out + (size_t)blockIdx.x * out_stride;
 	const int t = threadIdx.x;
 	if (in_transposed) {
 		for (int k = 0; k < N; k++) band[k * S + t] = src[k * stride + t];
@@ -460,7 +408,7 @@ __global__ void __launch_bounds__(N) k_dwt_level_smem(const int16_t *in, int16_t
 	}
 	__syncthreads();
 	if (ll_copy) {
-		int16_t *ll = ll_copy + (size_t)blockIdx.x * N * N;
+		int16_t *ll = ll_copy + (size_t)blockIdx.x * ll_stride;
 		for (int m = 0; m < N; m++) ll[m * N + t] = band[t * S + m];
 	}
 	// thread t owns column m=t of the row pass (walks k), then output column t of the column pass.
@@ -468,7 +416,7 @@ __global__ void __launch_bounds__(N) k_dwt_level_smem(const int16_t *in, int16_t
 	auto ldk = [&](int k) { return (int)band[k * S + m]; };
 	for (int e = 0; e < N / 2; e++) {
 		int lo = (int16_t)tap_low(ldk, e, N);
-		int hi = (e == N / 2 - 1) ? ((ldk(N - 1) - ldk(N - 2)) << 1) : (2 * ldk(2 * e + 1) - (ldk(2 * e) + ldk(2 * e + 2)));
+		int hi = first_pass_high(ldk, e, N);
 		rowbuf[m] = (int16_t)lo;
 		rowbuf[N + m] = (int16_t)hi;
 		__syncthreads();
@@ -485,17 +433,18 @@ __global__ void __launch_bounds__(N) k_dwt_level_smem(const int16_t *in, int16_t
 	}
 }
 
-__global__ void k_u8_to_s16(const uint8_t *__restrict__ in, int16_t *__restrict__ out, size_t count)
+__global__ void k_u8_to_s16(const uint8_t *__restrict__ in, int16_t *__restrict__ out, size_t in_stride, size_t out_stride)
 {
-	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < count) out[i] = in[i];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < NHW_CPLANE) out[(size_t)blockIdx.y * out_stride + i] = in[(size_t)blockIdx.y * in_stride + i];
 }
 
 }  // namespace
 
 namespace nhw {
 
-void colorspace(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y, uint8_t *u, uint8_t *v)
+void colorspace(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y, size_t ystride, uint8_t *u, uint8_t *v,
+                size_t cstride)
 {
 	static const int qtz[17] = {0, 15900, 16500, 17100, 18000, 18820, 19670, 20640, 21540, 23540, 25570, 27522, 27830, 27607, 28786, 31262, 32375};
 	ColorParams p;
@@ -505,20 +454,21 @@ void colorspace(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y, 
 	else if (quality >= 18) { p.mode = 1; p.yq = (double)(quality == 19 ? 0.975f : 0.93f); }
 	else if (quality == 17) p.mode = 2;
 	else { p.mode = 3; p.qtz = qtz[quality < 0 ? 0 : quality]; }
-	NHW_LAUNCH(c, k_colorspace, dim3(512 / CS_ROWS, n), 256, 0, rgb, y, u, v, p);
+	NHW_LAUNCH(c, k_colorspace, dim3(512 / CS_ROWS, n), 256, 0, rgb, y, u, v, ystride, cstride, p);
 }
 
-void pre_processing(nhw_ctx *c, int n, int quality, int16_t *y)
+void pre_processing(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystride)
 {
 	(void)quality;   // q17..q21 share one rule set; q>=22 never gets here; q<=16 is rejected upstream
 	dim3 grid((510 + PRE_WARPS - 1) / PRE_WARPS, n);
-	NHW_LAUNCH(c, k_pre_energy, grid, 32 * PRE_WARPS, 0, y, c->y_aux2, c->rowmap);
+	int16_t *energy = c->y_aux2 + NHW_GUARD_S, *kern = c->y_aux + NHW_GUARD_S;
+	NHW_LAUNCH(c, k_pre_energy, grid, 32 * PRE_WARPS, 0, y, energy, c->rowmap, ystride, (size_t)NHW_Y_SLOT);
 	NHW_LAUNCH(c, k_pre_chain, (n + 63) / 64, 64, 0, c->rowmap, c->rowcarry, n);
-	NHW_LAUNCH(c, k_pre_apply, grid, 32 * PRE_WARPS, 0, c->y_aux2, c->rowcarry, c->y_aux);
-	NHW_LAUNCH(c, k_pre_nudge, dim3(510, n), 256, 0, c->y_aux, y);
+	NHW_LAUNCH(c, k_pre_apply, grid, 32 * PRE_WARPS, 0, energy, c->rowcarry, kern, (size_t)NHW_Y_SLOT);
+	NHW_LAUNCH(c, k_pre_nudge, dim3(510, n), 256, 0, kern, y, (size_t)NHW_Y_SLOT, ystride);
 }
 
-static void level2_attrs()
+static void dwt_attrs()
 {
 	static bool done = false;
 	if (done) return;
@@ -529,35 +479,42 @@ static void level2_attrs()
 	done = true;
 }
 
-void dwt_luma(nhw_ctx *c, int n, int16_t *y_jpeg, int16_t *y_proc, int16_t *y_ll1)
+// level 1 (512) + level 2 (256) of the luma plane; jpeg is consumed, proc/ll1 produced
+void dwt_luma(nhw_ctx *c, int n, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride, int16_t *ll1,
+              size_t lstride)
 {
-	level2_attrs();
-	NHW_LAUNCH(c, k_dwt_rows<512>, dim3(512 / 8, n), 256, 0, y_jpeg, c->y_aux, NHW_YPLANE);
-	NHW_LAUNCH(c, k_dwt_cols_t<512>, dim3(512 / 32, n), 256, 512 * 33 * 2, c->y_aux, y_proc, NHW_YPLANE);
-	NHW_LAUNCH(c, k_dwt_level_smem<256>, n, 256, (256 * 258 + 512) * 2, y_proc, y_proc, y_ll1, NHW_YPLANE, 512, 1);
+	dwt_attrs();
+	int16_t *rows = c->y_aux + NHW_GUARD_S;
+	NHW_LAUNCH(c, k_dwt_rows<512>, dim3(512 / 8, n), 256, 0, jpeg, rows, jstride, (size_t)NHW_Y_SLOT);
+	NHW_LAUNCH(c, k_dwt_cols_t<512>, dim3(512 / 32, n), 256, 512 * 33 * 2, rows, proc, (size_t)NHW_Y_SLOT, pstride);
+	NHW_LAUNCH(c, k_dwt_level_smem<256>, n, 256, (256 * 258 + 512) * 2, proc, proc, ll1, pstride, pstride, lstride, 512, 1);
 }
 
-void chroma_to_short(nhw_ctx *c, int n, const uint8_t *u8, int16_t *c_jpeg)
+void chroma_to_short(nhw_ctx *c, int n_planes, const uint8_t *u8, size_t in_stride, int16_t *jpeg, size_t out_stride)
 {
-	size_t count = (size_t)n * 2 * NHW_CPLANE;
-	NHW_LAUNCH(c, k_u8_to_s16, (unsigned)((count + 255) / 256), 256, 0, u8, c_jpeg, count);
+	NHW_LAUNCH(c, k_u8_to_s16, dim3(NHW_CPLANE / 256, n_planes), 256, 0, u8, jpeg, in_stride, out_stride);
 }
 
-void dwt_chroma(nhw_ctx *c, int n, int16_t *c_jpeg, int16_t *c_proc, int16_t *c_ll1)
+// level 1 (256) + level 2 (128) of n_planes chroma planes
+void dwt_chroma(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
+                int16_t *ll1, size_t lstride)
 {
-	level2_attrs();
-	NHW_LAUNCH(c, k_dwt_rows<256>, dim3(256 / 8, 2 * n), 256, 0, c_jpeg, c->c_aux, NHW_CPLANE);
-	NHW_LAUNCH(c, k_dwt_cols_t<256>, dim3(256 / 32, 2 * n), 256, 256 * 33 * 2, c->c_aux, c_proc, NHW_CPLANE);
-	NHW_LAUNCH(c, k_dwt_level_smem<128>, 2 * n, 128, (128 * 130 + 256) * 2, c_proc, c_proc, c_ll1, NHW_CPLANE, 256, 1);
+	dwt_attrs();
+	int16_t *rows = c->c_aux + NHW_GUARD_S;
+	NHW_LAUNCH(c, k_dwt_rows<256>, dim3(256 / 8, n_planes), 256, 0, jpeg, rows, jstride, (size_t)NHW_C_SLOT);
+	NHW_LAUNCH(c, k_dwt_cols_t<256>, dim3(256 / 32, n_planes), 256, 256 * 33 * 2, rows, proc, (size_t)NHW_C_SLOT, pstride);
+	NHW_LAUNCH(c, k_dwt_level_smem<128>, n_planes, 128, (128 * 130 + 256) * 2, proc, proc, ll1, pstride, pstride, lstride, 256, 1);
 }
 
-void dwt_level2_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, int16_t *proc, int N, int stride)
+// one more analysis level on a band held in `im_jpeg` orientation (closed loop, encoder/nhw_encoder.c:281,2339)
+void dwt_level_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
+                         int N, int row_stride)
 {
-	level2_attrs();
+	dwt_attrs();
 	if (N == 256)
-		NHW_LAUNCH(c, k_dwt_level_smem<256>, n_planes, 256, (256 * 258 + 512) * 2, jpeg, proc, (int16_t *)nullptr, stride * stride, stride, 0);
+		NHW_LAUNCH(c, k_dwt_level_smem<256>, n_planes, 256, (256 * 258 + 512) * 2, jpeg, proc, (int16_t *)nullptr, jstride, pstride, (size_t)0, row_stride, 0);
 	else
-		NHW_LAUNCH(c, k_dwt_level_smem<128>, n_planes, 128, (128 * 130 + 256) * 2, jpeg, proc, (int16_t *)nullptr, stride * stride, stride, 0);
+		NHW_LAUNCH(c, k_dwt_level_smem<128>, n_planes, 128, (128 * 130 + 256) * 2, jpeg, proc, (int16_t *)nullptr, jstride, pstride, (size_t)0, row_stride, 0);
 }
 
 }  // namespace nhw

@@ -22,11 +22,3 @@ struct nhw_ctx;
 		(ctx)->launches++;                                                                \
 	} while (0)
 
-// symmetric rounding division by 2^s used all over the reference's filters
-// (e.g. encoder/filters.c:89-93): v>=0 ? (v+h)>>s : -((-v+h)>>s)
-__device__ __forceinline__ int nhw_sround(int v, int half, int sh)
-{
-	return v >= 0 ? ((v + half) >> sh) : -((-v + half) >> sh);
-}
-
-__device__ __forceinline__ int nhw_iabs(int v) { return v < 0 ? -v : v; }

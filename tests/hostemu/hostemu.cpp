@@ -1,0 +1,280 @@
+// tests/hostemu/hostemu.cpp -- TEST TOOLING ONLY, never part of the product library.
+//
+// Compiles the encoder's stage functions (nhwcodec_b200/csrc/enc_*.cuh, written as
+// __host__ __device__ code) with g++ and runs them sequentially on the CPU, so stage parity
+// against the reference taps can be iterated on a machine without a GPU.  It proves nothing
+// about the CUDA path by itself: the parity claims come from tests/ running the CUDA library
+// on a B200 against oracle/_ref.  Rows/strips are deliberately visited in REVERSE order where
+// the CUDA path runs them as independent threads, to catch hidden cross-row dependencies.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../nhwcodec_b200/csrc/enc_pack.cuh"
+
+namespace {
+
+struct Work {
+	std::vector<uint8_t> mem;
+	EncImg im;
+	EncHdr hdr;
+};
+
+template <typename T>
+T *carve(std::vector<uint8_t> &mem, size_t &off, size_t count, size_t guard_bytes)
+{
+	off = (off + 63) & ~size_t(63);
+	off += guard_bytes;
+	T *p = reinterpret_cast<T *>(mem.data() + off);
+	off += count * sizeof(T) + guard_bytes;
+	return p;
+}
+
+Work *make_work()
+{
+	Work *w = new Work();
+	w->mem.assign(16u << 20, 0);
+	size_t off = 0;
+	EncImg &im = w->im;
+	const size_t G = NHW_GUARD_S * 2;
+	im.proc = carve<int16_t>(w->mem, off, 512 * 512, G);
+	im.jpeg = carve<int16_t>(w->mem, off, 512 * 512, G);
+	im.aux = carve<int16_t>(w->mem, off, 512 * 512, G);
+	im.ll1 = carve<int16_t>(w->mem, off, 256 * 256, G);
+	im.ll2s = carve<int16_t>(w->mem, off, 256 * 256, G);
+	im.cproc = carve<int16_t>(w->mem, off, 256 * 256, G);
+	im.cjpeg = carve<int16_t>(w->mem, off, 256 * 256, G);
+	im.caux = carve<int16_t>(w->mem, off, 256 * 256, G);
+	im.cll1 = carve<int16_t>(w->mem, off, 128 * 128, G);
+	im.cll2s = carve<int16_t>(w->mem, off, 128 * 128, G);
+	im.scan = carve<uint8_t>(w->mem, off, NHW_SCAN_BYTES, NHW_GUARD_B);
+	im.tree1 = carve<uint8_t>(w->mem, off, NHW_CAP_TREE1, NHW_GUARD_B);
+	im.ch_res = carve<uint8_t>(w->mem, off, 16384, NHW_GUARD_B);
+	im.llcode = carve<uint8_t>(w->mem, off, 49152, NHW_GUARD_B);
+	im.exw = carve<uint8_t>(w->mem, off, 3 * 16384, NHW_GUARD_B);
+	im.res1 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
+	im.res1_bit = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
+	im.res1_word = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
+	im.res3 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
+	im.res3_bit = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
+	im.res3_word = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 4 + 16, NHW_GUARD_B);
+	im.res4 = carve<uint8_t>(w->mem, off, 8192, NHW_GUARD_B);
+	im.res5 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
+	im.res5_bit = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
+	im.res5_word = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
+	im.tmp1 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
+	im.tmp2 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
+	im.tmp3 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
+	im.highres_mem = carve<uint16_t>(w->mem, off, 16384, NHW_GUARD_B);
+	im.highres_word = carve<uint8_t>(w->mem, off, 16384, NHW_GUARD_B);
+	im.res_uv64 = carve<uint8_t>(w->mem, off, 1024, NHW_GUARD_B);
+	im.sel1 = carve<uint8_t>(w->mem, off, 32768 + 16, NHW_GUARD_B);
+	im.sel2 = carve<uint8_t>(w->mem, off, 32768 + 16, NHW_GUARD_B);
+	im.codebook1 = carve<uint8_t>(w->mem, off, 1024, NHW_GUARD_B);
+	im.codebook2 = carve<uint8_t>(w->mem, off, 1024, NHW_GUARD_B);
+	im.words = carve<uint32_t>(w->mem, off, 131072, NHW_GUARD_B);
+	im.pack_scratch = carve<PackState>(w->mem, off, 1, NHW_GUARD_B);
+	im.hdr = &w->hdr;
+	if (off > w->mem.size()) abort();
+	memset(&w->hdr, 0, sizeof w->hdr);
+	return w;
+}
+
+// ---- plain loops over the shared 1-D filter primitives ----
+// forward level: in(y,x) natural, N x N, row stride si -> out P(k,m), row stride so; tmp N*N
+void fwd_level(const int16_t *in, int si, bool in_transposed, int16_t *out, int so, int N, std::vector<int16_t> &tmp)
+{
+	tmp.resize((size_t)N * N);
+	for (int y = 0; y < N; y++) {
+		auto ld = [&](int x) { return (int)(in_transposed ? in[x * si + y] : in[y * si + x]); };
+		for (int e = 0; e < N / 2; e++) {
+			tmp[y * N + e] = (int16_t)tap_low(ld, e, N);
+			tmp[y * N + N / 2 + e] = (int16_t)first_pass_high(ld, e, N);
+		}
+	}
+	for (int k = 0; k < N; k++) {
+		auto ld = [&](int y) { return (int)tmp[y * N + k]; };
+		const bool fine = k < N / 2;
+		for (int e = 0; e < N / 2; e++) {
+			out[k * so + e] = (int16_t)second_pass_low(ld, e, N, fine);
+			out[k * so + N / 2 + e] = (int16_t)second_pass_high(ld, e, N, fine);
+		}
+	}
+}
+
+// inverse level: bands J(k,m) in `in` (stride s) -> natural image in `out` (stride s)
+void inv_level(const int16_t *in, int16_t *out, int s, int N, std::vector<int16_t> &tmp)
+{
+	const int M = N / 2;
+	tmp.resize((size_t)N * N);
+	for (int k = 0; k < N; k++) {
+		auto l = [&](int t) { return (int)in[k * s + t]; };
+		auto h = [&](int t) { return (int)in[k * s + M + t]; };
+		for (int t = 0; t < M; t++) {
+			int ev, od;
+			inverse_pair(l, h, t, M, false, ev, od);
+			tmp[k * N + 2 * t] = (int16_t)ev;
+			tmp[k * N + 2 * t + 1] = (int16_t)od;
+		}
+	}
+	for (int y = 0; y < N; y++) {
+		auto l = [&](int t) { return (int)tmp[t * N + y]; };
+		auto h = [&](int t) { return (int)tmp[(M + t) * N + y]; };
+		for (int t = 0; t < M; t++) {
+			int ev, od;
+			inverse_pair(l, h, t, M, true, ev, od);
+			out[y * s + 2 * t] = (int16_t)ev;
+			out[y * s + 2 * t + 1] = (int16_t)od;
+		}
+	}
+}
+
+void copy_region(int16_t *dst, int ds, const int16_t *src, int ss, int N)
+{
+	for (int r = 0; r < N; r++) memcpy(dst + r * ds, src + r * ss, N * sizeof(int16_t));
+}
+
+typedef void (*tap_fn)(const char *, const void *, size_t);
+
+}  // namespace
+
+extern "C" {
+
+void *he_new() { return make_work(); }
+void he_free(void *h) { delete static_cast<Work *>(h); }
+
+// Full encode of one image from the front-end's outputs: the pre-sharpened luma plane and
+// the two 4:2:0 chroma byte planes.  tap (optional) receives named intermediate buffers.
+// Returns the stream length or a negative status.
+int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *v8, int q, uint8_t *out, tap_fn tap)
+{
+	Work *w = static_cast<Work *>(hw);
+	std::fill(w->mem.begin(), w->mem.end(), 0);
+	memset(&w->hdr, 0, sizeof w->hdr);
+	const EncImg &im = w->im;
+	EncHdr *h = im.hdr;
+	h->quality = q;
+	const int ratio = 8;
+	std::vector<int16_t> tmp;
+	auto T = [&](const char *name, const void *p, size_t n) { if (tap) tap(name, p, n); };
+	if (q < 17 || q > 21) return -3;
+
+	// ---------------- luma ----------------
+	memcpy(im.jpeg, y_pre, 512 * 512 * 2);
+	fwd_level(im.jpeg, 512, false, im.proc, 512, 512, tmp);
+	for (int m = 0; m < 256; m++)
+		for (int k = 0; k < 256; k++) im.ll1[m * 256 + k] = im.proc[k * 512 + m];
+	fwd_level(im.proc, 512, true, im.proc, 512, 256, tmp);
+	T("y_dwt2_proc", im.proc, 512 * 512 * 2);
+	T("y_ll1", im.ll1, 65536 * 2);
+	for (int r = 255; r >= 0; r--) y_e6a_tag_row(im, r);
+	T("y_e6a_ll1", im.ll1, 65536 * 2);
+	y_recons_ll2_image(im, q, 1);
+	y_recons_patterns_image(im);
+	for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 1);
+	T("y_rec1_jpeg", im.jpeg, 512 * 512 * 2);
+	inv_level(im.jpeg, im.proc, 512, 256, tmp);
+	T("y_syn1_proc", im.proc, 512 * 512 * 2);
+	for (int r = 255; r >= 0; r--) y_e6c_apply_row(im, r);
+	T("y_e6c_proc", im.proc, 512 * 512 * 2);
+	T("y_e6c_ll1", im.ll1, 65536 * 2);
+	for (int r = 255; r >= 0; r--) y_e6d_correct_row(im, r);
+	T("y_e6d_jpeg", im.jpeg, 512 * 512 * 2);
+	fwd_level(im.jpeg, 512, false, im.proc, 512, 256, tmp);
+	T("y_dwt2b_proc", im.proc, 512 * 512 * 2);
+	copy_region(im.ll2s, 256, im.proc, 512, 256);
+	y_ll2_to_bytes_image(im, q);
+	T("y_e11_tree1", im.tree1, 16384);
+	T("y_e11_chres", im.ch_res, 16384);
+	T("y_e11_exw", im.exw, h->exw_y_len);
+	T("y_e11_res4", im.res4, h->res4_len);
+	ll_dpcm_luma_image(im, q);
+	T("y_e12_chres", im.llcode, h->y_res_comp);
+	copy_region(im.proc, 512, im.ll2s, 256, 256);
+	y_recons_ll2_image(im, q, 0);
+	y_recons_patterns_image(im);
+	for (int r = 255; r >= 0; r--) y_recons_tag57_row(im, r);
+	for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 0);
+	y_recons_shrink_image(im);
+	T("y_rec0_jpeg", im.jpeg, 512 * 512 * 2);
+	inv_level(im.jpeg, im.proc, 512, 256, tmp);
+	T("y_syn0_proc", im.proc, 512 * 512 * 2);
+	for (int r = 511; r >= 256; r--) y_e14_threshold_row(im, q, ratio, r);
+	T("y_e14_proc", im.proc, 512 * 512 * 2);
+	for (int r = 510; r >= 1; r--) y_e15_tags_row(im, r);
+	T("y_e15_proc", im.proc, 512 * 512 * 2);
+	y_e16_residual_image(im, q);
+	T("y_e16_proc", im.proc, 512 * 512 * 2);
+	T("y_e16_ll1", im.ll1, 65536 * 2);
+	y_e16b_classify_image(im, q);
+	T("y_e16b_proc", im.proc, 512 * 512 * 2);
+	T("y_e16b_ll1", im.ll1, 65536 * 2);
+	y_e18_pack_list_image(im, 1);
+	if (q >= 19) y_e18_pack_list_image(im, 3);
+	if (q >= 21) y_e18_pack_list_image(im, 5);
+	T("y_e18_ll1", im.ll1, 65536 * 2);
+	for (int r = 255; r >= 0; r--) y_e19_restore_row(im, r);
+	y_e20_cleanup_image(im, q, ratio);
+	T("y_e20_proc", im.proc, 512 * 512 * 2);
+	y_offset_pairs_image(im);
+	y_offset_patterns_image(im);
+	y_offset_quant_image(im, ratio);
+	T("y_e21_proc", im.proc, 512 * 512 * 2);
+	for (int s = 127; s >= 0; s--) y_scan_strip(im, s);
+	T("y_e23_scan", im.scan, 262144);
+	y_peephole_image(im);
+	T("y_e24_scan", im.scan, 262144);
+
+	// ---------------- chroma ----------------
+	for (int v = 0; v < 2; v++) {
+		const uint8_t *src = v ? v8 : u8;
+		const char *pfx = v ? "v" : "u";
+		char name[64];
+		auto TN = [&](const char *sfx, const void *p, size_t n) { snprintf(name, sizeof name, "%s_%s", pfx, sfx); T(name, p, n); };
+		for (int i = 0; i < 65536; i++) im.cjpeg[i] = src[i];
+		fwd_level(im.cjpeg, 256, false, im.cproc, 256, 256, tmp);
+		for (int m = 0; m < 128; m++)
+			for (int k = 0; k < 128; k++) im.cll1[m * 128 + k] = im.cproc[k * 256 + m];
+		fwd_level(im.cproc, 256, true, im.cproc, 256, 128, tmp);
+		TN("dwt2_proc", im.cproc, 65536 * 2);
+		TN("ll1", im.cll1, 16384 * 2);
+		for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 1);
+		for (int r = 127; r >= 0; r--) c_recons_quant_row(im, r, ratio, 1);
+		TN("rec1_jpeg", im.cjpeg, 65536 * 2);
+		inv_level(im.cjpeg, im.cproc, 256, 128, tmp);
+		TN("syn1_proc", im.cproc, 65536 * 2);
+		for (int r = 127; r >= 0; r--) c_correct_row(im, r, v);
+		TN("corr_jpeg", im.cjpeg, 65536 * 2);
+		fwd_level(im.cjpeg, 256, false, im.cproc, 256, 128, tmp);
+		TN("dwt2b_proc", im.cproc, 65536 * 2);
+		copy_region(im.cll2s, 128, im.cproc, 256, 128);
+		for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 0);
+		for (int r = 127; r >= 0; r--) c_recons_quant_row(im, r, ratio, 0);
+		inv_level(im.cjpeg, im.cproc, 256, 128, tmp);
+		TN("syn0_proc", im.cproc, 65536 * 2);
+		for (int r = 127; r >= 0; r--) c_residual_tags_row(im, q, r);
+		copy_region(im.cproc, 256, im.cll2s, 128, 128);
+		TN("tags_proc", im.cproc, 65536 * 2);
+		int e = c_ll_to_bytes_image(im, v);
+		if (v) h->exw_v_len = e; else h->exw_u_len = e;
+		if (q > 15) c_ll_bit1_plane(im, v);
+		c_offset_quant_image(im, ratio);
+		TN("quant_proc", im.cproc, 65536 * 2);
+		for (int s = 31; s >= 0; s--) c_scan_strip(im, s, v);
+	}
+	T("uv_scan", im.scan + 262144, 131072);
+	ll_dpcm_chroma_image(im);
+	T("llcode", im.llcode, h->end_ch_res);
+	int a = 0;
+	int rc = packet_stream_image(im, 0, a);
+	if (rc) return rc;
+	a++;
+	rc = packet_stream_image(im, 1, a);
+	if (rc) return rc;
+	T("hdr", h, sizeof *h);
+	return write_stream_image(im, out);
+}
+
+}  // extern "C"
