@@ -34,9 +34,10 @@ bool check(cudaError_t e, const char *what)
 using nhw::check;
 
 template <typename T>
-static bool dev_alloc(T **p, size_t count)
+static bool dev_alloc0(T **p, size_t count)
 {
-	return check(cudaMalloc((void **)p, count * sizeof(T)), "cudaMalloc");
+	if (!check(cudaMalloc((void **)p, count * sizeof(T)), "cudaMalloc")) return false;
+	return check(cudaMemset(*p, 0, count * sizeof(T)), "cudaMemset");
 }
 
 extern "C" {
@@ -62,22 +63,23 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	c->max_batch = max_batch;
 	const size_t B = (size_t)max_batch;
 	bool ok = check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-	ok = ok && dev_alloc(&c->rgb, B * NHW_RGB_BYTES);
-	ok = ok && dev_alloc(&c->y_jpeg, B * NHW_YPLANE) && dev_alloc(&c->y_proc, B * NHW_YPLANE);
-	ok = ok && dev_alloc(&c->y_aux, B * NHW_YPLANE) && dev_alloc(&c->y_aux2, B * NHW_YPLANE);
-	ok = ok && dev_alloc(&c->y_ll1, B * NHW_CPLANE) && dev_alloc(&c->y_ll2save, B * NHW_CPLANE);
-	ok = ok && dev_alloc(&c->c_u8, B * 2 * NHW_CPLANE);
-	ok = ok && dev_alloc(&c->c_jpeg, B * 2 * NHW_CPLANE) && dev_alloc(&c->c_proc, B * 2 * NHW_CPLANE);
-	ok = ok && dev_alloc(&c->c_aux, B * 2 * NHW_CPLANE) && dev_alloc(&c->c_ll1, B * 2 * 128 * 128);
-	ok = ok && dev_alloc(&c->rowmap, B * 512) && dev_alloc(&c->rowcarry, B * 512);
-	ok = ok && dev_alloc(&c->len_dev, B) && dev_alloc(&c->status_dev, B);
-	if (!ok) { nhw_destroy(c); return NHW_ERR_CUDA; }
-	// zero once: halos / never-written borders read as 0, matching the canonical oracle
-	cudaMemsetAsync(c->y_aux, 0, B * NHW_YPLANE * 2, c->stream);
-	cudaMemsetAsync(c->y_aux2, 0, B * NHW_YPLANE * 2, c->stream);
-	cudaMemsetAsync(c->rowmap, 0, B * 512 * 4, c->stream);
-	cudaMemsetAsync(c->rowcarry, 0, B * 512, c->stream);
-	if (!check(cudaStreamSynchronize(c->stream), "nhw_create sync")) { nhw_destroy(c); return NHW_ERR_CUDA; }
+	// every workspace array is zero-filled once: guard bands and never-written borders must
+	// read as 0 (canonical oracle semantics)
+	ok = ok && dev_alloc0(&c->rgb, B * NHW_RGB_BYTES);
+	ok = ok && dev_alloc0(&c->y_jpeg, B * NHW_Y_SLOT) && dev_alloc0(&c->y_proc, B * NHW_Y_SLOT);
+	ok = ok && dev_alloc0(&c->y_aux, B * NHW_Y_SLOT) && dev_alloc0(&c->y_aux2, B * NHW_Y_SLOT);
+	ok = ok && dev_alloc0(&c->y_ll1, B * NHW_C_SLOT) && dev_alloc0(&c->y_ll2save, B * NHW_C_SLOT);
+	ok = ok && dev_alloc0(&c->c_u8, B * 2 * NHW_CPLANE);
+	ok = ok && dev_alloc0(&c->c_jpeg, B * 2 * NHW_C_SLOT) && dev_alloc0(&c->c_proc, B * 2 * NHW_C_SLOT);
+	ok = ok && dev_alloc0(&c->c_aux, B * 2 * NHW_C_SLOT);
+	ok = ok && dev_alloc0(&c->c_ll1, B * 2 * NHW_Q_SLOT) && dev_alloc0(&c->c_ll2save, B * 2 * NHW_Q_SLOT);
+	ok = ok && dev_alloc0(&c->rowmap, B * 512) && dev_alloc0(&c->rowcarry, B * 512);
+	ok = ok && dev_alloc0(&c->enc_bytes, B * (size_t)ENC_BYTES_SLOT) && dev_alloc0(&c->enc_hdr, B);
+	ok = ok && dev_alloc0(&c->out_dev, B * (size_t)NHW_MAX_STREAM_BYTES) && dev_alloc0(&c->pack_dev, B * (size_t)NHW_MAX_STREAM_BYTES);
+	ok = ok && dev_alloc0(&c->len_dev, B) && dev_alloc0(&c->status_dev, B) && dev_alloc0(&c->offs_dev, B + 1);
+	ok = ok && check(cudaMallocHost((void **)&c->offs_host, (B + 1) * sizeof(uint64_t)), "cudaMallocHost");
+	ok = ok && check(cudaMallocHost((void **)&c->status_host, B * sizeof(int32_t)), "cudaMallocHost");
+	if (!ok || !check(cudaDeviceSynchronize(), "nhw_create sync")) { nhw_destroy(c); return NHW_ERR_CUDA; }
 	*out = c;
 	return NHW_OK;
 }
@@ -87,9 +89,12 @@ void nhw_destroy(nhw_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	void *ptrs[] = {c->rgb, c->y_jpeg, c->y_proc, c->y_aux, c->y_aux2, c->y_ll1, c->y_ll2save, c->c_u8, c->c_jpeg,
-	                c->c_proc, c->c_aux, c->c_ll1, c->rowmap, c->rowcarry, c->out_dev, c->len_dev, c->status_dev};
+	                c->c_proc, c->c_aux, c->c_ll1, c->c_ll2save, c->rowmap, c->rowcarry, c->enc_bytes, c->enc_hdr,
+	                c->out_dev, c->pack_dev, c->len_dev, c->status_dev, c->offs_dev};
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
+	if (c->offs_host) cudaFreeHost(c->offs_host);
+	if (c->status_host) cudaFreeHost(c->status_host);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -103,21 +108,23 @@ static int finish(nhw_ctx *c, const char *what)
 	return NHW_OK;
 }
 
-static bool quality_supported_frontend(int q) { return q >= 17 && q <= 23; }
+static bool quality_supported(int q) { return q >= 17 && q <= 21; }
 
 int nhw_stage_colorspace_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quality, int pre,
                                 int16_t *y, uint8_t *u, uint8_t *v)
 {
 	if (!c || !rgb_dev || n <= 0) return NHW_ERR_ARG;
 	if (quality < 1 || quality > 23) return NHW_ERR_QUALITY;
-	if (pre && !quality_supported_frontend(quality)) return NHW_ERR_QUALITY;
+	if (pre && !(quality >= 17 && quality <= 23)) return NHW_ERR_QUALITY;
 	cudaSetDevice(c->device);
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
 		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
-		int16_t *yy = y ? y + (size_t)i0 * NHW_YPLANE : c->y_jpeg;
-		nhw::colorspace(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, yy,
-		                u ? u + (size_t)i0 * NHW_CPLANE : nullptr, v ? v + (size_t)i0 * NHW_CPLANE : nullptr);
-		if (pre && quality < 22) nhw::pre_processing(c, m, quality, yy);
+		int16_t *yy = y ? y + (size_t)i0 * NHW_YPLANE : c->y_jpeg + NHW_GUARD_S;
+		size_t ys = y ? (size_t)NHW_YPLANE : (size_t)NHW_Y_SLOT;
+		nhw::colorspace(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, yy, ys,
+		                u ? u + (size_t)i0 * NHW_CPLANE : nullptr, v ? v + (size_t)i0 * NHW_CPLANE : nullptr,
+		                (size_t)NHW_CPLANE);
+		if (pre && quality < 22) nhw::pre_processing(c, m, quality, yy, ys);
 	}
 	return finish(c, "nhw_stage_colorspace_device");
 }
@@ -126,32 +133,24 @@ int nhw_stage_frontend_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int qua
                               int16_t *y_proc, int16_t *y_ll1, int16_t *c_proc, int16_t *c_ll1)
 {
 	if (!c || !rgb_dev || n <= 0) return NHW_ERR_ARG;
-	if (!quality_supported_frontend(quality)) return NHW_ERR_QUALITY;
+	if (!(quality >= 17 && quality <= 23)) return NHW_ERR_QUALITY;
 	cudaSetDevice(c->device);
+	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT, QS = NHW_Q_SLOT;
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
 		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
-		uint8_t *u8 = c->c_u8, *v8 = c->c_u8 + (size_t)m * NHW_CPLANE;
-		nhw::colorspace(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, c->y_jpeg, u8, v8);
-		if (quality < 22) nhw::pre_processing(c, m, quality, c->y_jpeg);
-		int16_t *yp = y_proc ? y_proc + (size_t)i0 * NHW_YPLANE : c->y_proc;
-		int16_t *yl = y_ll1 ? y_ll1 + (size_t)i0 * NHW_CPLANE : c->y_ll1;
-		nhw::dwt_luma(c, m, c->y_jpeg, yp, yl);
-		// chroma planes are laid out [U images..., V images...] inside a chunk
-		nhw::chroma_to_short(c, m, c->c_u8, c->c_jpeg);
-		nhw::dwt_chroma(c, m, c->c_jpeg, c->c_proc, c->c_ll1);
-		if (c_proc) {
-			// hand back as [image][U,V]
-			for (int k = 0; k < 2; k++)
-				cudaMemcpy2DAsync(c_proc + ((size_t)i0 * 2 + k) * NHW_CPLANE, 2 * NHW_CPLANE * 2,
-				                  c->c_proc + (size_t)k * m * NHW_CPLANE, NHW_CPLANE * 2, NHW_CPLANE * 2, m,
-				                  cudaMemcpyDeviceToDevice, c->stream);
-		}
-		if (c_ll1) {
-			for (int k = 0; k < 2; k++)
-				cudaMemcpy2DAsync(c_ll1 + ((size_t)i0 * 2 + k) * 16384, 2 * 16384 * 2,
-				                  c->c_ll1 + (size_t)k * m * 16384, 16384 * 2, 16384 * 2, m,
-				                  cudaMemcpyDeviceToDevice, c->stream);
-		}
+		int16_t *yj = c->y_jpeg + NHW_GUARD_S;
+		nhw::colorspace(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, yj, YS, c->c_u8, c->c_u8 + NHW_CPLANE,
+		                (size_t)2 * NHW_CPLANE);
+		if (quality < 22) nhw::pre_processing(c, m, quality, yj, YS);
+		// with caller buffers the planes are dense; otherwise they land in the context workspace
+		int16_t *yp = y_proc ? y_proc + (size_t)i0 * NHW_YPLANE : c->y_proc + NHW_GUARD_S;
+		int16_t *yl = y_ll1 ? y_ll1 + (size_t)i0 * NHW_CPLANE : c->y_ll1 + NHW_GUARD_S;
+		nhw::dwt_luma(c, m, yj, YS, yp, y_proc ? (size_t)NHW_YPLANE : YS, yl, y_ll1 ? (size_t)NHW_CPLANE : CS);
+		int16_t *cj = c->c_jpeg + NHW_GUARD_S;
+		nhw::chroma_to_short(c, 2 * m, c->c_u8, NHW_CPLANE, cj, CS);
+		int16_t *cp = c_proc ? c_proc + (size_t)i0 * 2 * NHW_CPLANE : c->c_proc + NHW_GUARD_S;
+		int16_t *cl = c_ll1 ? c_ll1 + (size_t)i0 * 2 * 16384 : c->c_ll1 + NHW_GUARD_S;
+		nhw::dwt_chroma(c, 2 * m, cj, CS, cp, c_proc ? (size_t)NHW_CPLANE : CS, cl, c_ll1 ? (size_t)16384 : QS);
 	}
 	return finish(c, "nhw_stage_frontend_device");
 }
@@ -167,17 +166,45 @@ int nhw_synth_batch_device(nhw_ctx *c, uint8_t *rgb_dev, int n, uint32_t seed0, 
 int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quality,
                             uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev)
 {
-	(void)c; (void)rgb_dev; (void)n; (void)quality; (void)out_dev; (void)len_dev; (void)status_dev;
-	nhw::set_error("nhw_encode_batch_device: full encode path not built yet");
-	return NHW_ERR_QUALITY;
+	if (!c || !rgb_dev || !out_dev || n <= 0) return NHW_ERR_ARG;
+	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q21 are)", quality); return NHW_ERR_QUALITY; }
+	cudaSetDevice(c->device);
+	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
+		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
+		nhw::encode_chunk(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, out_dev + (size_t)i0 * NHW_MAX_STREAM_BYTES,
+		                  len_dev ? len_dev + i0 : nullptr, status_dev ? status_dev + i0 : nullptr);
+	}
+	return finish(c, "nhw_encode_batch_device");
 }
 
 int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
                      uint8_t *out, size_t out_cap, uint64_t *offsets, int32_t *status)
 {
-	(void)c; (void)rgb; (void)n; (void)quality; (void)out; (void)out_cap; (void)offsets; (void)status;
-	nhw::set_error("nhw_encode_batch: full encode path not built yet");
-	return NHW_ERR_QUALITY;
+	if (!c || !rgb || !out || !offsets || n <= 0) return NHW_ERR_ARG;
+	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q21 are)", quality); return NHW_ERR_QUALITY; }
+	cudaSetDevice(c->device);
+	uint64_t pos = 0;
+	offsets[0] = 0;
+	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
+		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
+		if (!check(cudaMemcpyAsync(c->rgb, rgb + (size_t)i0 * NHW_RGB_BYTES, (size_t)m * NHW_RGB_BYTES,
+		                           cudaMemcpyHostToDevice, c->stream), "H2D pixels")) return NHW_ERR_CUDA;
+		nhw::encode_chunk(c, c->rgb, m, quality, c->out_dev, c->len_dev, c->status_dev);
+		nhw::pack_streams(c, m);
+		cudaMemcpyAsync(c->offs_host, c->offs_dev, (size_t)(m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+		cudaMemcpyAsync(c->status_host, c->status_dev, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+		int rc = finish(c, "nhw_encode_batch");
+		if (rc) return rc;
+		const uint64_t total = c->offs_host[m];
+		if (pos + total > out_cap) { nhw::set_error("output buffer too small"); return NHW_ERR_ARG; }
+		if (total && !check(cudaMemcpy(out + pos, c->pack_dev, total, cudaMemcpyDeviceToHost), "D2H streams")) return NHW_ERR_CUDA;
+		for (int i = 0; i < m; i++) {
+			offsets[i0 + i + 1] = pos + c->offs_host[i + 1];
+			if (status) status[i0 + i] = c->status_host[i];
+		}
+		pos += total;
+	}
+	return NHW_OK;
 }
 
 int nhw_decode_batch(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int n, uint8_t *rgb, int32_t *status)

@@ -11,6 +11,8 @@
 #include "nhw_tables.cuh"
 
 #define NHW_ERR_CODEBOOK_DEV (-4)
+#define NHW_ERR_OVERFLOW_DEV (-5)
+#define NHW_WORDS_LIMIT (131072 - 4)   // ENC_WORDS_CAP minus slack, enc_batch.cuh
 
 struct PackState {
 	int rle_buf[256];     // symbol histogram, later symbol -> rank
@@ -140,6 +142,7 @@ NHW_HDN int packet_stream_image(const EncImg &im, int part, int &a)
 				if (pos >= NHW_CODE_DEPTH) return NHW_ERR_CODEBOOK_DEV;   // byte outside the alphabet
 				put_bits(words, a, pack, nhw_code_bits[pos], nhw_code_len[pos]);
 			}
+			if (a >= NHW_WORDS_LIMIT) return NHW_ERR_OVERFLOW_DEV;
 			e = 1;
 			if (tag > 0) { tag--; if (tag > 0) { i++; continue; } }
 			break;

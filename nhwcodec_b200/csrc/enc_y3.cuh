@@ -5,15 +5,20 @@
 #pragma once
 #include "enc_y2.cuh"
 
-// The two escape ladders are not perfectly regular, so keep them as tables.
+// The two escape ladders (extra_words1/2, encoder/tree.h:54-55) are not perfectly regular, so
+// they stay tables: a __constant__ copy for the kernels, a host copy for the test harness.
+#define NHW_EXTRA_WORDS1 {10, 12, 14, 18, 20, 22, 26, 28, 30, 34, 36, 38, 42, 44, 46, 50, 52, 54, 58}
+#define NHW_EXTRA_WORDS2 {60, 62, 66, 68, 70, 74, 76, 78, 82, 84, 86, 90, 92, 94, 98, 100, 102, 106, 108}
+#ifdef __CUDACC__
+__constant__ uint8_t c_extra_words1[19] = NHW_EXTRA_WORDS1;
+__constant__ uint8_t c_extra_words2[19] = NHW_EXTRA_WORDS2;
+#endif
+static const uint8_t h_extra_words1[19] = NHW_EXTRA_WORDS1;
+static const uint8_t h_extra_words2[19] = NHW_EXTRA_WORDS2;
 #ifdef __CUDA_ARCH__
-__constant__ uint8_t c_extra_words1[19] = {10, 12, 14, 18, 20, 22, 26, 28, 30, 34, 36, 38, 42, 44, 46, 50, 52, 54, 58};
-__constant__ uint8_t c_extra_words2[19] = {60, 62, 66, 68, 70, 74, 76, 78, 82, 84, 86, 90, 92, 94, 98, 100, 102, 106, 108};
 #define NHW_EXTRA1(k) c_extra_words1[k]
 #define NHW_EXTRA2(k) c_extra_words2[k]
 #else
-static const uint8_t h_extra_words1[19] = {10, 12, 14, 18, 20, 22, 26, 28, 30, 34, 36, 38, 42, 44, 46, 50, 52, 54, 58};
-static const uint8_t h_extra_words2[19] = {60, 62, 66, 68, 70, 74, 76, 78, 82, 84, 86, 90, 92, 94, 98, 100, 102, 106, 108};
 #define NHW_EXTRA1(k) h_extra_words1[k]
 #define NHW_EXTRA2(k) h_extra_words2[k]
 #endif

@@ -1,0 +1,395 @@
+// encode.cu -- batch encoder driver: sequences the CUDA kernels of the full .nhw encode for a
+// chunk of images resident in device memory.  Replaces encode_image + write_compressed_file
+// (encoder/nhw_encoder.c:103-2878, 3100-3220) for a whole batch; every image is independent.
+//
+// Kernel granularity of this first complete version:
+//   * front end (front.cu)            : data-parallel, shared-memory tiled
+//   * inverse / forward transforms    : data-parallel
+//   * *_row stages                    : one thread per (image,row)
+//   * *_image stages                  : one thread per image (raster-order dependencies)
+// The per-image serial kernels are latency-bound and are the next thing to parallelise
+// (wavefronts / finite-state scans); they are correct and batch-parallel as they stand.
+#include "nhw_ctx.h"
+#include "nhw_dev.cuh"
+#include "enc_pack.cuh"
+#include "enc_batch.cuh"
+#include "../../include/nhw_cuda.h"
+
+namespace {
+
+__device__ __forceinline__ EncImg make_img(const EncBatch &b, int i, int comp)
+{
+	EncImg im;
+	im.proc = b.y_proc + (size_t)i * NHW_Y_SLOT;
+	im.jpeg = b.y_jpeg + (size_t)i * NHW_Y_SLOT;
+	im.aux = b.y_aux + (size_t)i * NHW_Y_SLOT;
+	im.ll1 = b.y_ll1 + (size_t)i * NHW_C_SLOT;
+	im.ll2s = b.y_ll2s + (size_t)i * NHW_C_SLOT;
+	const size_t p = (size_t)i * 2 + comp;
+	im.cproc = b.c_proc + p * NHW_C_SLOT;
+	im.cjpeg = b.c_jpeg + p * NHW_C_SLOT;
+	im.caux = b.c_aux + p * NHW_C_SLOT;
+	im.cll1 = b.c_ll1 + p * NHW_Q_SLOT;
+	im.cll2s = b.c_ll2s + p * NHW_Q_SLOT;
+	uint8_t *bytes = b.bytes + (size_t)i * ENC_BYTES_SLOT;
+	im.scan = bytes + OFF_SCAN;
+	im.tree1 = bytes + OFF_TREE1;
+	im.ch_res = bytes + OFF_CHRES;
+	im.llcode = bytes + OFF_LLCODE;
+	im.exw = bytes + OFF_EXW;
+	im.res1 = bytes + OFF_RES1;
+	im.res1_bit = bytes + OFF_RES1_BIT;
+	im.res1_word = bytes + OFF_RES1_WORD;
+	im.res3 = bytes + OFF_RES3;
+	im.res3_bit = bytes + OFF_RES3_BIT;
+	im.res3_word = bytes + OFF_RES3_WORD;
+	im.res4 = bytes + OFF_RES4;
+	im.res5 = bytes + OFF_RES5;
+	im.res5_bit = bytes + OFF_RES5_BIT;
+	im.res5_word = bytes + OFF_RES5_WORD;
+	im.tmp1 = bytes + OFF_TMP1;
+	im.tmp2 = bytes + OFF_TMP2;
+	im.tmp3 = bytes + OFF_TMP3;
+	im.highres_mem = reinterpret_cast<uint16_t *>(bytes + OFF_HRMEM);
+	im.highres_word = bytes + OFF_HRWORD;
+	im.res_uv64 = bytes + OFF_UV64;
+	im.sel1 = bytes + OFF_SEL1;
+	im.sel2 = bytes + OFF_SEL2;
+	im.codebook1 = bytes + OFF_BOOK1;
+	im.codebook2 = bytes + OFF_BOOK2;
+	im.words = reinterpret_cast<uint32_t *>(bytes + OFF_WORDS);
+	im.pack_scratch = bytes + OFF_PACK;
+	im.hdr = b.hdr + i;
+	return im;
+}
+
+// ---- generic launch shapes ----
+template <typename F>
+__global__ void k_image(EncBatch b, int n, F f)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) f(make_img(b, i, 0), i);
+}
+
+template <typename F>
+__global__ void k_plane(EncBatch b, int n2, F f)   // thread per chroma plane (2 per image)
+{
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n2) f(make_img(b, p >> 1, p & 1), p & 1);
+}
+
+template <typename F>
+__global__ void k_rows(EncBatch b, int rows, F f)   // grid (ceil(rows/64), n)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < rows) f(make_img(b, blockIdx.y, 0), r);
+}
+
+template <typename F>
+__global__ void k_plane_rows(EncBatch b, int rows, F f)   // grid (ceil(rows/64), 2n)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < rows) f(make_img(b, blockIdx.y >> 1, blockIdx.y & 1), r, blockIdx.y & 1);
+}
+
+template <typename F>
+void run_image(nhw_ctx *c, const EncBatch &b, int n, F f)
+{
+	NHW_LAUNCH(c, k_image, (n + 31) / 32, 32, 0, b, n, f);
+}
+template <typename F>
+void run_plane(nhw_ctx *c, const EncBatch &b, int n, F f)
+{
+	NHW_LAUNCH(c, k_plane, (2 * n + 31) / 32, 32, 0, b, 2 * n, f);
+}
+template <typename F>
+void run_rows(nhw_ctx *c, const EncBatch &b, int n, int rows, F f)
+{
+	NHW_LAUNCH(c, k_rows, dim3((rows + 63) / 64, n), 64, 0, b, rows, f);
+}
+template <typename F>
+void run_plane_rows(nhw_ctx *c, const EncBatch &b, int n, int rows, F f)
+{
+	NHW_LAUNCH(c, k_plane_rows, dim3((rows + 63) / 64, 2 * n), 64, 0, b, rows, f);
+}
+
+// ---- inverse transform of one level (wavelet_synthesis, encoder/wavelet_filterbank.c:305-496)
+// pass 1: rows of the band plane J(k,m) -> T(k,y) (no normalisation), natural row layout
+template <int N>
+__global__ void __launch_bounds__(256) k_idwt_rows(const int16_t *__restrict__ in, int16_t *__restrict__ out,
+                                                   size_t in_stride, size_t out_stride, int row_stride)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int k = blockIdx.x * 8 + warp;
+	const int16_t *src = in + (size_t)blockIdx.y * in_stride + k * row_stride;
+	int16_t *dst = out + (size_t)blockIdx.y * out_stride + k * row_stride;
+	constexpr int M = N / 2;
+	auto l = [&](int t) { return (int)src[t]; };
+	auto h = [&](int t) { return (int)src[M + t]; };
+	for (int t = lane; t < M; t += 32) {
+		int ev, od;
+		inverse_pair(l, h, t, M, false, ev, od);
+		*reinterpret_cast<uint32_t *>(dst + 2 * t) = (uint32_t)(uint16_t)ev | ((uint32_t)(uint16_t)od << 16);
+	}
+}
+
+// pass 2: columns of T -> natural image rows out(y, x), normalised.  CTA = 32 columns y.
+template <int N>
+__global__ void __launch_bounds__(256) k_idwt_cols_t(const int16_t *__restrict__ in, int16_t *__restrict__ out,
+                                                     size_t in_stride, size_t out_stride, int row_stride)
+{
+	extern __shared__ int16_t tile[];   // [N][33]
+	const int y0 = blockIdx.x * 32;
+	const int16_t *src = in + (size_t)blockIdx.y * in_stride;
+	int16_t *dst = out + (size_t)blockIdx.y * out_stride;
+	for (int i = threadIdx.x; i < N * 32; i += 256) {
+		int k = i >> 5, yy = i & 31;
+		tile[k * 33 + yy] = src[k * row_stride + y0 + yy];
+	}
+	__syncthreads();
+	constexpr int M = N / 2;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int yy = warp; yy < 32; yy += 8) {
+		auto l = [&](int t) { return (int)tile[t * 33 + yy]; };
+		auto h = [&](int t) { return (int)tile[(M + t) * 33 + yy]; };
+		int16_t *row = dst + (y0 + yy) * row_stride;
+		for (int t = lane; t < M; t += 32) {
+			int ev, od;
+			inverse_pair(l, h, t, M, true, ev, od);
+			*reinterpret_cast<uint32_t *>(row + 2 * t) = (uint32_t)(uint16_t)ev | ((uint32_t)(uint16_t)od << 16);
+		}
+	}
+}
+
+// copy an N x N region between planes of possibly different row strides (one thread per 2 cells)
+__global__ void k_copy_region(const int16_t *__restrict__ src, size_t src_slot, int src_stride,
+                              int16_t *__restrict__ dst, size_t dst_slot, int dst_stride, int N)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // pair index
+	const int per_row = N / 2;
+	if (idx >= N * per_row) return;
+	const int r = idx / per_row, c = (idx % per_row) * 2;
+	const uint32_t v = *reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.y * src_slot + r * src_stride + c);
+	*reinterpret_cast<uint32_t *>(dst + (size_t)blockIdx.y * dst_slot + r * dst_stride + c) = v;
+}
+
+__global__ void k_zero_bytes(uint8_t *base, size_t slot, size_t off, size_t count)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // 16-byte units
+	if (i * 16 < count) reinterpret_cast<uint4 *>(base + (size_t)blockIdx.y * slot + off)[i] = make_uint4(0, 0, 0, 0);
+}
+
+// final: container bytes
+__global__ void k_write_stream(EncBatch b, int n, uint8_t *out, uint32_t *len, int32_t *status)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	EncImg im = make_img(b, i, 0);
+	int st = im.hdr->status;
+	int L = 0;
+	if (st == 0) L = write_stream_image(im, out + (size_t)i * NHW_MAX_STREAM_BYTES);
+	if (len) len[i] = (uint32_t)L;
+	if (status) status[i] = st;
+}
+
+// exclusive prefix of the stream lengths (one CTA, n <= a few thousand) ...
+__global__ void k_stream_offsets(const uint32_t *__restrict__ len, uint64_t *__restrict__ offs, int n)
+{
+	__shared__ uint64_t part[1024];
+	const int t = threadIdx.x, per = (n + 1023) / 1024;
+	uint64_t s = 0;
+	for (int i = t * per; i < n && i < (t + 1) * per; i++) s += len[i];
+	part[t] = s;
+	__syncthreads();
+	if (t == 0) {
+		uint64_t run = 0;
+		for (int k = 0; k < 1024; k++) { uint64_t v = part[k]; part[k] = run; run += v; }
+		offs[n] = run;
+	}
+	__syncthreads();
+	uint64_t run = part[t];
+	for (int i = t * per; i < n && i < (t + 1) * per; i++) { offs[i] = run; run += len[i]; }
+}
+
+// ... and the gather of the fixed-size slots into one dense buffer (one CTA per image)
+__global__ void k_pack_streams(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ len,
+                               const uint64_t *__restrict__ offs, uint8_t *__restrict__ dense)
+{
+	const int i = blockIdx.x;
+	const uint8_t *src = slots + (size_t)i * NHW_MAX_STREAM_BYTES;
+	uint8_t *dst = dense + offs[i];
+	const uint32_t L = len[i];
+	for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) dst[k] = src[k];
+}
+
+void idwt_attrs()
+{
+	static bool done = false;
+	if (done) return;
+	cudaFuncSetAttribute(k_idwt_cols_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * 2);
+	cudaFuncSetAttribute(k_idwt_cols_t<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 33 * 2);
+	done = true;
+}
+
+}  // namespace
+
+namespace nhw {
+
+EncBatch enc_batch_of(nhw_ctx *c)
+{
+	EncBatch b;
+	b.y_proc = c->y_proc + NHW_GUARD_S;
+	b.y_jpeg = c->y_jpeg + NHW_GUARD_S;
+	b.y_aux = c->y_aux + NHW_GUARD_S;
+	b.y_ll1 = c->y_ll1 + NHW_GUARD_S;
+	b.y_ll2s = c->y_ll2save + NHW_GUARD_S;
+	b.c_proc = c->c_proc + NHW_GUARD_S;
+	b.c_jpeg = c->c_jpeg + NHW_GUARD_S;
+	b.c_aux = c->c_aux + NHW_GUARD_S;
+	b.c_ll1 = c->c_ll1 + NHW_GUARD_S;
+	b.c_ll2s = c->c_ll2save + NHW_GUARD_S;
+	b.bytes = c->enc_bytes;
+	b.hdr = c->enc_hdr;
+	return b;
+}
+
+// luma inverse level-2 transform: jpeg region (256x256) -> proc region, natural orientation
+static void idwt_luma256(nhw_ctx *c, const EncBatch &b, int n)
+{
+	idwt_attrs();
+	NHW_LAUNCH(c, k_idwt_rows<256>, dim3(256 / 8, n), 256, 0, b.y_jpeg, b.y_aux, (size_t)NHW_Y_SLOT, (size_t)NHW_Y_SLOT, 512);
+	NHW_LAUNCH(c, k_idwt_cols_t<256>, dim3(256 / 32, n), 256, 256 * 33 * 2, b.y_aux, b.y_proc, (size_t)NHW_Y_SLOT, (size_t)NHW_Y_SLOT, 512);
+}
+
+static void idwt_chroma128(nhw_ctx *c, const EncBatch &b, int n)
+{
+	idwt_attrs();
+	NHW_LAUNCH(c, k_idwt_rows<128>, dim3(128 / 8, 2 * n), 256, 0, b.c_jpeg, b.c_aux, (size_t)NHW_C_SLOT, (size_t)NHW_C_SLOT, 256);
+	NHW_LAUNCH(c, k_idwt_cols_t<128>, dim3(128 / 32, 2 * n), 256, 128 * 33 * 2, b.c_aux, b.c_proc, (size_t)NHW_C_SLOT, (size_t)NHW_C_SLOT, 256);
+}
+
+static void zero_bytes(nhw_ctx *c, const EncBatch &b, int n, size_t off, size_t count)
+{
+	size_t units = (count + 15) / 16;
+	NHW_LAUNCH(c, k_zero_bytes, dim3((unsigned)((units + 255) / 256), n), 256, 0, b.bytes, (size_t)ENC_BYTES_SLOT, off, count);
+}
+
+// Encode n <= max_batch images whose pixels are in device memory.  out_dev: n slots of
+// NHW_MAX_STREAM_BYTES.  All work is queued on c->stream; the caller synchronises.
+void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev)
+{
+	const EncBatch b = enc_batch_of(c);
+	const int ratio = 8;
+	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT, QS = NHW_Q_SLOT;
+
+	// ---- per-call state that must start at zero (canonical "fresh calloc" semantics)
+	cudaMemsetAsync(c->enc_hdr, 0, (size_t)n * sizeof(EncHdr), c->stream);
+	zero_bytes(c, b, n, OFF_TREE1 - 64, NHW_CAP_TREE1 + 64 + 64);
+	zero_bytes(c, b, n, OFF_SCAN + 262144, 131072 + 64);
+	zero_bytes(c, b, n, OFF_WORDS, ENC_WORDS_BYTES);
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { im.hdr->quality = q; });
+
+	// ---- front end: colour, 4:2:0, pre-sharpening, two analysis levels (front.cu)
+	uint8_t *u8 = c->c_u8;
+	colorspace(c, rgb, n, q, b.y_jpeg, YS, u8, u8 + NHW_CPLANE, (size_t)2 * NHW_CPLANE);
+	if (q < 22) pre_processing(c, n, q, b.y_jpeg, YS);
+	dwt_luma(c, n, b.y_jpeg, YS, b.y_proc, YS, b.y_ll1, CS);
+	chroma_to_short(c, 2 * n, u8, NHW_CPLANE, b.c_jpeg, CS);
+	dwt_chroma(c, 2 * n, b.c_jpeg, CS, b.c_proc, CS, b.c_ll1, QS);
+
+	// ---- luma closed loop (nhw_encoder.c:141-283)
+	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+		y_recons_ll2_image(im, q, 1);
+		y_recons_patterns_image(im);
+	});
+	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 1); });
+	idwt_luma256(c, b, n);
+	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6c_apply_row(im, r); });
+	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6d_correct_row(im, r); });
+	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
+
+	// ---- LL2 coding (nhw_encoder.c:623-757)
+	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+		y_ll2_to_bytes_image(im, q);
+		ll_dpcm_luma_image(im, q);
+	});
+	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_ll2s, CS, 256, b.y_proc, YS, 512, 256);
+
+	// ---- second reconstruction = what the decoder will see as LL1 (nhw_encoder.c:759-781)
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+		y_recons_ll2_image(im, q, 0);
+		y_recons_patterns_image(im);
+	});
+	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) {
+		y_recons_tag57_row(im, r);
+		y_recons_quant_row(im, r, ratio, 0);
+	});
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_recons_shrink_image(im); });
+	idwt_luma256(c, b, n);
+
+	// ---- level-1 thresholds, pattern tags, residual side channels (nhw_encoder.c:783-1887)
+	run_rows(c, b, n, 512, [=] __device__(const EncImg &im, int r) {
+		if (r >= 256) y_e14_threshold_row(im, q, ratio, r);
+		y_e15_tags_row(im, r);
+	});
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_e16_residual_image(im, q); });
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_e16b_classify_image(im, q); });
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+		y_e18_pack_list_image(im, 1);
+		if (q >= 19) y_e18_pack_list_image(im, 3);
+		if (q >= 21) y_e18_pack_list_image(im, 5);
+	});
+
+	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
+	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_e19_restore_row(im, r); });
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_e20_cleanup_image(im, q, ratio); });
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_offset_pairs_image(im); });
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_offset_patterns_image(im); });
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_offset_quant_image(im, ratio); });
+	run_rows(c, b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_peephole_image(im); });
+
+	// ---- chroma, U and V planes side by side (nhw_encoder.c:2255-2868)
+	run_plane_rows(c, b, n, 128, [=] __device__(const EncImg &im, int r, int) {
+		if (r < 64) c_recons_ll_row(im, r, 1);
+		c_recons_quant_row(im, r, ratio, 1);
+	});
+	idwt_chroma128(c, b, n);
+	run_plane_rows(c, b, n, 128, [=] __device__(const EncImg &im, int r, int v) { c_correct_row(im, r, v); });
+	dwt_level_from_jpeg(c, 2 * n, b.c_jpeg, CS, b.c_proc, CS, 128, 256);
+	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_proc, CS, 256, b.c_ll2s, QS, 128, 128);
+	run_plane_rows(c, b, n, 128, [=] __device__(const EncImg &im, int r, int) {
+		if (r < 64) c_recons_ll_row(im, r, 0);
+		c_recons_quant_row(im, r, ratio, 0);
+	});
+	idwt_chroma128(c, b, n);
+	run_plane_rows(c, b, n, 128, [=] __device__(const EncImg &im, int r, int) { c_residual_tags_row(im, q, r); });
+	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_ll2s, QS, 128, b.c_proc, CS, 256, 128);
+	run_plane(c, b, n, [=] __device__(const EncImg &im, int v) {
+		int e = c_ll_to_bytes_image(im, v);
+		if (v) im.hdr->exw_v_len = e; else im.hdr->exw_u_len = e;
+		if (q > 15) c_ll_bit1_plane(im, v);
+		c_offset_quant_image(im, ratio);
+	});
+	run_plane_rows(c, b, n, 32, [=] __device__(const EncImg &im, int s, int v) { c_scan_strip(im, s, v); });
+
+	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
+	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+		ll_dpcm_chroma_image(im);
+		int a = 0;
+		int rc = packet_stream_image(im, 0, a);
+		if (rc == 0) { a++; rc = packet_stream_image(im, 1, a); }
+		im.hdr->status = rc;
+	});
+	NHW_LAUNCH(c, k_write_stream, (n + 31) / 32, 32, 0, b, n, out_dev, len_dev, status_dev);
+}
+
+void pack_streams(nhw_ctx *c, int n)
+{
+	NHW_LAUNCH(c, k_stream_offsets, 1, 1024, 0, c->len_dev, c->offs_dev, n);
+	NHW_LAUNCH(c, k_pack_streams, n, 256, 0, c->out_dev, c->len_dev, c->offs_dev, c->pack_dev);
+}
+
+}  // namespace nhw

@@ -1,8 +1,10 @@
 // nhw_ctx.h -- host-side context of libnhw_cuda (internal; the public face is include/nhw_cuda.h)
 #pragma once
 #include <cuda_runtime.h>
-#include <stdint.h>
 #include <stddef.h>
+#include <stdint.h>
+
+#include "enc_batch.cuh"
 
 struct nhw_ctx {
 	int device;
@@ -10,37 +12,52 @@ struct nhw_ctx {
 	cudaStream_t stream;
 	uint64_t launches;
 
-	// ---- per-image workspace, each sized for max_batch images (device memory) ----
-	uint8_t *rgb;        // staged input pixels (host API only)          786432 B / image
-	int16_t *y_jpeg;     // luma `im_jpeg`                               512*512 int16
+	// ---- per-image workspace, each array sized for max_batch images (device memory).
+	// Plane arrays are made of slots (plane + zero guard bands, see enc_img.cuh).
+	uint8_t *rgb;        // staged input pixels (host API only), 786432 B / image
+	int16_t *y_jpeg;     // luma `im_jpeg`                       NHW_Y_SLOT
 	int16_t *y_proc;     // luma `im_process`
-	int16_t *y_aux;      // scratch plane (pre-sharpen kernel values / DWT row-pass output)
+	int16_t *y_aux;      // scratch plane (pre-sharpen kernel values / transform row passes)
 	int16_t *y_aux2;     // scratch plane (signed Laplacian energy)
-	int16_t *y_ll1;      // `res256` (LL1 copy)                          256*256 int16
-	int16_t *y_ll2save;  // `resIII` snapshot                            256*256 int16
-	uint8_t *c_u8;       // U then V byte planes                         2 * 256*256 u8
-	int16_t *c_jpeg;     // chroma `im_jpeg`, U then V                   2 * 256*256 int16
+	int16_t *y_ll1;      // `res256` (LL1 copy)                  NHW_C_SLOT
+	int16_t *y_ll2save;  // `resIII` snapshot                    NHW_C_SLOT
+	uint8_t *c_u8;       // 4:2:0 byte planes, [image][U,V]      2 * 65536 B
+	int16_t *c_jpeg;     // chroma `im_jpeg`, [image][U,V]       2 * NHW_C_SLOT
 	int16_t *c_proc;     // chroma `im_process`
 	int16_t *c_aux;      // chroma scratch
-	int16_t *c_ll1;      // chroma `res256`                              2 * 128*128 int16
-	uint32_t *rowmap;    // pre-sharpen carry maps                       512 u32
-	uint8_t *rowcarry;   // pre-sharpen carry-in class per row           512 u8
+	int16_t *c_ll1;      // chroma `res256`                      2 * NHW_Q_SLOT
+	int16_t *c_ll2save;  // chroma `resIII`                      2 * NHW_Q_SLOT
+	uint32_t *rowmap;    // pre-sharpen carry maps               512 u32
+	uint8_t *rowcarry;   // pre-sharpen carry-in class per row   512 u8
+	uint8_t *enc_bytes;  // byte-sized encoder state             ENC_BYTES_SLOT
+	EncHdr *enc_hdr;
 
-	uint8_t *out_dev;    // staged output streams (host API only)
+	uint8_t *out_dev;    // staged output streams (host API only), NHW_MAX_STREAM_BYTES / image
+	uint8_t *pack_dev;   // the chunk's streams packed back to back
 	uint32_t *len_dev;
 	int32_t *status_dev;
+	uint64_t *offs_dev;  // max_batch + 1
+	uint64_t *offs_host; // pinned
+	int32_t *status_host;
 };
 
 namespace nhw {
 
 // front.cu
-void colorspace(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y, uint8_t *u, uint8_t *v);
-void pre_processing(nhw_ctx *c, int n, int quality, int16_t *y);
-void dwt_luma(nhw_ctx *c, int n, int16_t *y_jpeg, int16_t *y_proc, int16_t *y_ll1);
-void chroma_to_short(nhw_ctx *c, int n, const uint8_t *u8, int16_t *c_jpeg);
-void dwt_chroma(nhw_ctx *c, int n, int16_t *c_jpeg, int16_t *c_proc, int16_t *c_ll1);
-// single-level transforms on planes of arbitrary stride, used by the closed loop
-void dwt_level2_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, int16_t *proc, int N, int stride);
+void colorspace(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y, size_t ystride, uint8_t *u, uint8_t *v,
+                size_t cstride);
+void pre_processing(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystride);
+void dwt_luma(nhw_ctx *c, int n, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride, int16_t *ll1,
+              size_t lstride);
+void chroma_to_short(nhw_ctx *c, int n_planes, const uint8_t *u8, size_t in_stride, int16_t *jpeg, size_t out_stride);
+void dwt_chroma(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
+                int16_t *ll1, size_t lstride);
+void dwt_level_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
+                         int N, int row_stride);
+
+// encode.cu
+void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev);
+void pack_streams(nhw_ctx *c, int n);   // out_dev slots + len_dev -> offs_dev, pack_dev
 
 // synth.cu
 void synth(nhw_ctx *c, uint8_t *rgb, int n, uint32_t seed0, int kind, const int16_t *sin_lut);
