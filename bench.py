@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the NHW hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's own CPU code)
+
+Metric (BASELINE.json): MPix/s of 512x512 batch encode at -q20, .nhw bytes bit-exact to the
+reference CPU encoder.  One "step" = one pass of the full encode over one batch of synthetic
+images (configs[1]: batch 4096 per GPU, natural-like generator of SURVEY.md section 8d).
+  value : whole-job MPix/s with the pixels already resident in HBM (device API), timed with
+          CUDA events on the codec's stream, max over ranks.
+  e2e   : the same metric through the host-buffer C-ABI call (nhw_encode_batch): pinned host
+          pixels in, .nhw bytes out, host<->device copies inside the timed region.
+  roofline     : the kernel with the largest share of the step, algorithmic bytes / its
+                 CUDA-event duration measured in the timed region, vs MEASURED_PEAKS.json.
+  cpu_baseline : oracle/_ref (the reference compiled with gcc -O3, canonical allocator) on the
+                 host cores, bounded sample (rank 0, N=1 only).
+Images shard trivially: each rank encodes its own batch, no data-path collective (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PIX = 512 * 512
+PIX_BYTES = PIX * 3
+METRIC = "encode_throughput_q20_512x512"
+UNIT = "MPix/s"
+
+# Algorithmic (compulsory) bytes per image of each kernel label, DESIGN.md section 5.
+# planes: Y int16 512x512 = 524288 B, LL1 int16 256x256 = 131072 B, chroma int16 256x256 = 131072 B.
+ALG_BYTES = {
+    "k_colorspace": 786432 + 524288 + 131072,          # RGB in; Y int16 + U,V u8 out
+    "k_pre_energy": 524288 + 524288,                   # Y in, energy plane out
+    "k_pre_apply": 524288 + 524288,
+    "k_pre_nudge": 524288 + 524288 + 524288,           # kernel plane in, Y in/out
+    "k_pre_chain": 2048 + 512,
+    "k_dwt_rows<512>": 2 * 524288,
+    "k_dwt_cols_t<512>": 2 * 524288,
+    "k_dwt_level_smem<256>": 131072 + 131072 + 131072,  # LL in, P2 out, LL1 copy out
+    "k_dwt_rows<256>": 2 * 2 * 131072,
+    "k_dwt_cols_t<256>": 2 * 2 * 131072,
+    "k_dwt_level_smem<128>": 2 * 3 * 32768,
+    "k_idwt_rows<256>": 2 * 131072,
+    "k_idwt_cols_t<256>": 2 * 131072,
+    "k_idwt_rows<128>": 2 * 2 * 32768,
+    "k_idwt_cols_t<128>": 2 * 2 * 32768,
+    "y_offset_quant": 2 * 524288,                      # plane in, bytes-in-int16 out (in place)
+    "y_offset_pairs": 2 * 524288 * 3 // 4,
+    "y_offset_patterns": 2 * 131072,
+    "y_e20_cleanup": 2 * 524288 * 3 // 4,
+    "y_peephole": 2 * 262144,
+    "y_scan": 524288 + 262144,
+    "entropy_pack": 2 * 393216,                        # two passes over the byte stream (+ output, added at run time)
+    "y_e16_residual": 2 * 131072 + 131072,
+    "y_e16b_classify": 2 * 131072 + 131072,
+    "y_e18_lists": 3 * 131072,
+    "y_recons1_serial": 2 * 131072,
+    "y_recons0_serial": 2 * 131072,
+    "y_recons0_shrink": 2 * 131072,
+    "y_ll2_code": 32768 + 3 * 16384,
+    "c_ll_quant": 2 * 2 * 131072,
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_rate(images, quality, seconds, threads):
+    """MPix/s of oracle/_ref (the reference's encode_image path, in memory) on `threads` host
+    threads, cycling over `images`, for about `seconds` seconds."""
+    from oracle import refbind
+    L = refbind.enc_stock_lib()
+    n = images.shape[0]
+    stop_at = time.perf_counter() + seconds
+    counts = [0] * threads
+
+    def work(t):
+        i = t
+        while time.perf_counter() < stop_at:
+            rc = L.nhwref_encode_discard(images[i % n].ctypes.data, int(quality))
+            if rc != 0:
+                raise RuntimeError("reference encoder failed: %d" % rc)
+            counts[t] += 1
+            i += threads
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    done = sum(counts)
+    return done * PIX / dt / 1e6, done, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from nhwcodec_b200 import synth
+    cores = host_cores()
+    distinct = 8
+    images = np.stack([synth.natural(1000 + i) for i in range(distinct)])
+    per_step = max(2 * cores, 8)
+    from oracle import refbind
+    L = refbind.enc_stock_lib()
+
+    def step():
+        idx = [0]
+        lock = threading.Lock()
+
+        def work():
+            while True:
+                with lock:
+                    i = idx[0]
+                    idx[0] += 1
+                if i >= per_step:
+                    return
+                L.nhwref_encode_discard(images[i % distinct].ctypes.data, args.quality)
+
+        ths = [threading.Thread(target=work) for _ in range(cores)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step * PIX / dt / 1e6
+    sample = "%d images/step (%d distinct natural-like seeds 1000+, cycled), in-memory downsample_YUV420+encode_image (stock allocator build), %d threads" % (
+        per_step, distinct, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/f64", "data": "synthetic",
+        "config": {"workload": "batch encode 512x512 RGB -q%d, natural-like synthetic (reference CPU arm, bounded sample)" % args.quality,
+                   "quality": args.quality, "images_per_step": per_step},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    from nhwcodec_b200 import Codec
+
+    rank, local, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B, q = args.batch, args.quality
+    codec = Codec(device=local, max_batch=B)
+    stream = torch.cuda.ExternalStream(codec.stream_ptr, device=torch.device("cuda", local))
+    rgb = torch.empty((B, PIX_BYTES), dtype=torch.uint8, device="cuda")
+    codec.synth(rgb, 1000 + rank * B, args.kind)
+    out = torch.empty((B, 1 << 19), dtype=torch.uint8, device="cuda")
+    lens = torch.zeros(B, dtype=torch.int32, device="cuda")
+    status = torch.zeros(B, dtype=torch.int32, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (value) ----------------
+    for _ in range(args.warmup):
+        codec.encode_device(rgb, q, out, lens, status)
+    assert int((status != 0).sum().item()) == 0, "encode reported per-image errors"
+    mean_stream = float(lens.float().mean().item())
+    sampler = ClockSampler(local)
+    barrier()
+    codec.profile(2)
+    launches0 = codec.launches
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        codec.encode_device(rgb, q, out, lens, status)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = codec.launches - launches0
+    table = codec.profile_table()
+    codec.profile(0)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps * PIX / (ms_max / 1e3) / 1e6
+
+    # ---------------- end to end through the host-buffer C-ABI (e2e) ----------------
+    rgb_host = torch.empty((B, PIX_BYTES), dtype=torch.uint8, pin_memory=True)
+    rgb_host.copy_(rgb)
+    cap = int(B * max(mean_stream * 1.5, 65536))
+    out_host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    offs = np.zeros(B + 1, dtype=np.uint64)
+    st = np.zeros(B, dtype=np.int32)
+    rgb_np, out_np = rgb_host.numpy(), out_host.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    codec.encode_into(rgb_np, q, out_np, offs, st)           # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        codec.encode_into(rgb_np, q, out_np, offs, st)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    d2h = int(offs[B])
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps * PIX / float(tt.item()) / 1e6
+
+    if rank == 0:
+        # ---------------- roofline of the dominant kernel ----------------
+        peak, peak_src = peaks()
+        total_kernel_ms = sum(v[0] for v in table.values())
+        kernels = []
+        for name, (kms, cnt) in sorted(table.items(), key=lambda kv: -kv[1][0]):
+            per_launch_ms = kms / max(cnt, 1)
+            b_img = ALG_BYTES.get(name)
+            if name == "entropy_pack" and b_img is not None:
+                b_img = b_img + int(mean_stream)
+            gbs = (b_img * B / (per_launch_ms / 1e3) / 1e9) if (b_img and per_launch_ms > 0) else None
+            kernels.append({"kernel": name, "ms_per_step": round(kms / args.steps, 4),
+                            "share": round(kms / total_kernel_ms, 4) if total_kernel_ms else None,
+                            "launches_per_step": cnt // max(args.steps, 1),
+                            "alg_bytes_per_image": b_img, "GBps": round(gbs, 2) if gbs else None,
+                            "frac": round(gbs / peak, 5) if gbs else None})
+        dom = kernels[0] if kernels else None
+        front = [k for k in kernels if k["kernel"] in ("k_colorspace", "k_pre_energy", "k_pre_chain", "k_pre_apply",
+                                                         "k_pre_nudge", "k_dwt_rows<512>", "k_dwt_cols_t<512>",
+                                                         "k_dwt_level_smem<256>")]
+        front_ms = sum(k["ms_per_step"] for k in front)
+        roofline = None
+        if dom:
+            roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                        "frac": dom["frac"], "traffic": None, "peak_source": peak_src, "share_of_step": dom["share"]}
+        frontend = None
+        if front_ms > 0:
+            gbs = 1572864 * B / (front_ms / 1e3) / 1e9
+            frontend = {"what": "colour + pre-sharpen + 2-level luma DWT (the north-star 'fused colorspace+DWT' work, "
+                                "8 kernels in this round)", "ms_per_step": round(front_ms, 4),
+                        "alg_bytes_per_image": 1572864, "GBps": round(gbs, 2), "frac": round(gbs / peak, 5)}
+
+        # ---------------- CPU baseline: the compiled reference on the host cores ----------------
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cores = host_cores()
+                sample_imgs = rgb[:min(B, 32)].cpu().numpy()
+                v, done, secs = cpu_reference_rate(sample_imgs, q, args.cpu_seconds, cores)
+                cpu = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "reference",
+                       "sample": "%d encodes of the first %d images of this batch in %.1f s, in-memory "
+                                 "downsample_YUV420+encode_image (oracle/_ref stock-allocator build, gcc -O3), %d threads" % (
+                                     done, sample_imgs.shape[0], secs, cores)}
+            except Exception as e:  # oracle/_ref missing on this box
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16 (+f64 colour)", "data": "synthetic",
+            "config": {"workload": "batch %d synthetic 512x512 RGB encode -q%d per GPU (BASELINE.json configs[1])" % (B, q),
+                       "quality": q, "batch_per_gpu": B, "generator": ["natural-like", "uniform-noise", "textured"][args.kind],
+                       "mean_stream_bytes": round(mean_stream, 1), "bit_exact": "verified by tests/test_encode_gpu.py",
+                       "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no flush needed" % (B * PIX_BYTES / 1e9)},
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": B * PIX_BYTES,
+                    "d2h_bytes_per_step": d2h + 8 * (B + 1) + 4 * B, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "frontend": frontend,
+            "cpu_baseline": cpu,
+            "kernels": kernels[:12],
+        }
+        print(json.dumps(line), flush=True)
+    codec.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step")
+    ap.add_argument("--quality", type=int, default=20)
+    ap.add_argument("--kind", type=int, default=0, help="0 natural-like, 1 uniform noise, 2 textured")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,7 +99,16 @@ int nhw_synth_batch_device(nhw_ctx *ctx, uint8_t *rgb_dev, int n, uint32_t seed0
 /* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
 uint64_t nhw_launch_count(const nhw_ctx *ctx);
 
-/* names+times of the last call's kernels are not kept here: use CUDA events / ncu. */
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on, so callers can
+ * bracket calls with their own CUDA events */
+void *nhw_stream(const nhw_ctx *ctx);
+
+/* Per-kernel timing with CUDA events recorded on that stream around each launch.
+ * enable: 0 = off, 1 = on, 2 = on and reset the accumulated table.
+ * nhw_profile_read writes one line per kernel label: "label\tmilliseconds\tlaunches\n"
+ * (accumulated since the last reset) and returns the number of bytes written. */
+int nhw_profile(nhw_ctx *ctx, int enable);
+long nhw_profile_read(nhw_ctx *ctx, char *buf, size_t cap);
 
 #ifdef __cplusplus
 }

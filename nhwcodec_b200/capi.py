@@ -19,6 +19,7 @@ EXPORTS = [
     "nhw_create", "nhw_destroy", "nhw_last_error", "nhw_version", "nhw_encode_batch",
     "nhw_encode_batch_device", "nhw_decode_batch", "nhw_stage_frontend_device",
     "nhw_stage_colorspace_device", "nhw_synth_batch_device", "nhw_launch_count",
+    "nhw_stream", "nhw_profile", "nhw_profile_read",
 ]
 
 _lib = None
@@ -58,6 +59,12 @@ def load_library():
     L.nhw_synth_batch_device.restype = i32
     L.nhw_launch_count.argtypes = [vp]
     L.nhw_launch_count.restype = u64
+    L.nhw_stream.argtypes = [vp]
+    L.nhw_stream.restype = vp
+    L.nhw_profile.argtypes = [vp, i32]
+    L.nhw_profile.restype = i32
+    L.nhw_profile_read.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
+    L.nhw_profile_read.restype = ctypes.c_long
     _lib = L
     return L
 
@@ -100,6 +107,25 @@ class Codec:
     @property
     def launches(self):
         return int(self.lib.nhw_launch_count(self.h))
+
+    @property
+    def stream_ptr(self):
+        """cudaStream_t of this context (wrap with torch.cuda.ExternalStream to record events)"""
+        return int(self.lib.nhw_stream(self.h) or 0)
+
+    def profile(self, mode):
+        """0 off, 1 on, 2 on + reset"""
+        self._check(self.lib.nhw_profile(self.h, int(mode)), "nhw_profile")
+
+    def profile_table(self):
+        """-> {kernel label: (total ms, launches)} accumulated since the last reset"""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self.lib.nhw_profile_read(self.h, buf, len(buf))
+        table = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split("\t")
+            table[name] = (float(ms), int(cnt))
+        return table
 
     # ---------------- host-buffer API (the reference-facing call) ----------------
     def encode(self, rgb, quality=20):

@@ -4,7 +4,10 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
 #include <new>
+#include <string>
+#include <vector>
 
 #include "../../include/nhw_cuda.h"
 #include "nhw_ctx.h"
@@ -32,6 +35,58 @@ bool check(cudaError_t e, const char *what)
 }  // namespace nhw
 
 using nhw::check;
+
+namespace nhw {
+
+struct ProfEntry { const char *label; cudaEvent_t a, b; };
+struct ProfState {
+	std::vector<ProfEntry> open;                 // launched, not yet resolved
+	std::vector<cudaEvent_t> pool;
+	std::map<std::string, std::pair<double, uint64_t>> acc;   // label -> (ms, launches)
+};
+
+static cudaEvent_t prof_event(ProfState *p)
+{
+	if (!p->pool.empty()) { cudaEvent_t e = p->pool.back(); p->pool.pop_back(); return e; }
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+
+void prof_begin(nhw_ctx *c, const char *label)
+{
+	if (!c->profile) return;
+	ProfState *p = static_cast<ProfState *>(c->prof);
+	ProfEntry en{label, prof_event(p), prof_event(p)};
+	cudaEventRecord(en.a, c->stream);
+	p->open.push_back(en);
+}
+
+void prof_end(nhw_ctx *c)
+{
+	if (!c->profile) return;
+	ProfState *p = static_cast<ProfState *>(c->prof);
+	cudaEventRecord(p->open.back().b, c->stream);
+}
+
+static void prof_resolve(nhw_ctx *c)
+{
+	ProfState *p = static_cast<ProfState *>(c->prof);
+	if (!p) return;
+	for (auto &en : p->open) {
+		float ms = 0.f;
+		if (cudaEventSynchronize(en.b) == cudaSuccess && cudaEventElapsedTime(&ms, en.a, en.b) == cudaSuccess) {
+			auto &slot = p->acc[en.label];
+			slot.first += ms;
+			slot.second += 1;
+		}
+		p->pool.push_back(en.a);
+		p->pool.push_back(en.b);
+	}
+	p->open.clear();
+}
+
+}  // namespace nhw
 
 template <typename T>
 static bool dev_alloc0(T **p, size_t count)
@@ -61,6 +116,7 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	memset(c, 0, sizeof *c);
 	c->device = device;
 	c->max_batch = max_batch;
+	c->prof = new nhw::ProfState();
 	const size_t B = (size_t)max_batch;
 	bool ok = check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
 	// every workspace array is zero-filled once: guard bands and never-written borders must
@@ -96,10 +152,47 @@ void nhw_destroy(nhw_ctx *c)
 	if (c->offs_host) cudaFreeHost(c->offs_host);
 	if (c->status_host) cudaFreeHost(c->status_host);
 	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->prof) {
+		nhw::ProfState *p = static_cast<nhw::ProfState *>(c->prof);
+		nhw::prof_resolve(c);
+		for (cudaEvent_t e : p->pool) cudaEventDestroy(e);
+		delete p;
+	}
 	delete c;
 }
 
 uint64_t nhw_launch_count(const nhw_ctx *c) { return c ? c->launches : 0; }
+
+void *nhw_stream(const nhw_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int nhw_profile(nhw_ctx *c, int enable)
+{
+	if (!c) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	nhw::prof_resolve(c);
+	if (enable == 2) static_cast<nhw::ProfState *>(c->prof)->acc.clear();   // reset counters, keep on
+	c->profile = enable ? 1 : 0;
+	return NHW_OK;
+}
+
+long nhw_profile_read(nhw_ctx *c, char *buf, size_t cap)
+{
+	if (!c || !buf || cap == 0) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	nhw::prof_resolve(c);
+	nhw::ProfState *p = static_cast<nhw::ProfState *>(c->prof);
+	size_t off = 0;
+	for (auto &kv : p->acc) {
+		int w = snprintf(buf + off, cap - off, "%s\t%.6f\t%llu\n", kv.first.c_str(), kv.second.first,
+		                 (unsigned long long)kv.second.second);
+		if (w < 0 || (size_t)w >= cap - off) break;
+		off += (size_t)w;
+	}
+	buf[off < cap ? off : cap - 1] = 0;
+	return (long)off;
+}
 
 static int finish(nhw_ctx *c, const char *what)
 {

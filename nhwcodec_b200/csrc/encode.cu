@@ -93,24 +93,24 @@ __global__ void k_plane_rows(EncBatch b, int rows, F f)   // grid (ceil(rows/64)
 }
 
 template <typename F>
-void run_image(nhw_ctx *c, const EncBatch &b, int n, F f)
+void run_image(nhw_ctx *c, const char *label, const EncBatch &b, int n, F f)
 {
-	NHW_LAUNCH(c, k_image, (n + 31) / 32, 32, 0, b, n, f);
+	NHW_LAUNCH_L(c, label, k_image, (n + 31) / 32, 32, 0, b, n, f);
 }
 template <typename F>
-void run_plane(nhw_ctx *c, const EncBatch &b, int n, F f)
+void run_plane(nhw_ctx *c, const char *label, const EncBatch &b, int n, F f)
 {
-	NHW_LAUNCH(c, k_plane, (2 * n + 31) / 32, 32, 0, b, 2 * n, f);
+	NHW_LAUNCH_L(c, label, k_plane, (2 * n + 31) / 32, 32, 0, b, 2 * n, f);
 }
 template <typename F>
-void run_rows(nhw_ctx *c, const EncBatch &b, int n, int rows, F f)
+void run_rows(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, F f)
 {
-	NHW_LAUNCH(c, k_rows, dim3((rows + 63) / 64, n), 64, 0, b, rows, f);
+	NHW_LAUNCH_L(c, label, k_rows, dim3((rows + 63) / 64, n), 64, 0, b, rows, f);
 }
 template <typename F>
-void run_plane_rows(nhw_ctx *c, const EncBatch &b, int n, int rows, F f)
+void run_plane_rows(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, F f)
 {
-	NHW_LAUNCH(c, k_plane_rows, dim3((rows + 63) / 64, 2 * n), 64, 0, b, rows, f);
+	NHW_LAUNCH_L(c, label, k_plane_rows, dim3((rows + 63) / 64, 2 * n), 64, 0, b, rows, f);
 }
 
 // ---- inverse transform of one level (wavelet_synthesis, encoder/wavelet_filterbank.c:305-496)
@@ -287,7 +287,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	zero_bytes(c, b, n, OFF_TREE1 - 64, NHW_CAP_TREE1 + 64 + 64);
 	zero_bytes(c, b, n, OFF_SCAN + 262144, 131072 + 64);
 	zero_bytes(c, b, n, OFF_WORDS, ENC_WORDS_BYTES);
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { im.hdr->quality = q; });
+	run_image(c, "init_hdr", b, n, [=] __device__(const EncImg &im, int) { im.hdr->quality = q; });
 
 	// ---- front end: colour, 4:2:0, pre-sharpening, two analysis levels (front.cu)
 	uint8_t *u8 = c->c_u8;
@@ -298,85 +298,85 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	dwt_chroma(c, 2 * n, b.c_jpeg, CS, b.c_proc, CS, b.c_ll1, QS);
 
 	// ---- luma closed loop (nhw_encoder.c:141-283)
-	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+	run_rows(c, "y_e6a_tag", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });
+	run_image(c, "y_recons1_serial", b, n, [=] __device__(const EncImg &im, int) {
 		y_recons_ll2_image(im, q, 1);
 		y_recons_patterns_image(im);
 	});
-	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 1); });
+	run_rows(c, "y_recons1_quant", b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 1); });
 	idwt_luma256(c, b, n);
-	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6c_apply_row(im, r); });
-	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6d_correct_row(im, r); });
+	run_rows(c, "y_e6c_apply", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6c_apply_row(im, r); });
+	run_rows(c, "y_e6d_correct", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6d_correct_row(im, r); });
 	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
 
 	// ---- LL2 coding (nhw_encoder.c:623-757)
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+	run_image(c, "y_ll2_code", b, n, [=] __device__(const EncImg &im, int) {
 		y_ll2_to_bytes_image(im, q);
 		ll_dpcm_luma_image(im, q);
 	});
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_ll2s, CS, 256, b.y_proc, YS, 512, 256);
 
 	// ---- second reconstruction = what the decoder will see as LL1 (nhw_encoder.c:759-781)
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+	run_image(c, "y_recons0_serial", b, n, [=] __device__(const EncImg &im, int) {
 		y_recons_ll2_image(im, q, 0);
 		y_recons_patterns_image(im);
 	});
-	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) {
+	run_rows(c, "y_recons0_quant", b, n, 256, [=] __device__(const EncImg &im, int r) {
 		y_recons_tag57_row(im, r);
 		y_recons_quant_row(im, r, ratio, 0);
 	});
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_recons_shrink_image(im); });
+	run_image(c, "y_recons0_shrink", b, n, [=] __device__(const EncImg &im, int) { y_recons_shrink_image(im); });
 	idwt_luma256(c, b, n);
 
 	// ---- level-1 thresholds, pattern tags, residual side channels (nhw_encoder.c:783-1887)
-	run_rows(c, b, n, 512, [=] __device__(const EncImg &im, int r) {
+	run_rows(c, "y_e14_e15_tags", b, n, 512, [=] __device__(const EncImg &im, int r) {
 		if (r >= 256) y_e14_threshold_row(im, q, ratio, r);
 		y_e15_tags_row(im, r);
 	});
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_e16_residual_image(im, q); });
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_e16b_classify_image(im, q); });
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+	run_image(c, "y_e16_residual", b, n, [=] __device__(const EncImg &im, int) { y_e16_residual_image(im, q); });
+	run_image(c, "y_e16b_classify", b, n, [=] __device__(const EncImg &im, int) { y_e16b_classify_image(im, q); });
+	run_image(c, "y_e18_lists", b, n, [=] __device__(const EncImg &im, int) {
 		y_e18_pack_list_image(im, 1);
 		if (q >= 19) y_e18_pack_list_image(im, 3);
 		if (q >= 21) y_e18_pack_list_image(im, 5);
 	});
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
-	run_rows(c, b, n, 256, [=] __device__(const EncImg &im, int r) { y_e19_restore_row(im, r); });
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_e20_cleanup_image(im, q, ratio); });
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_offset_pairs_image(im); });
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_offset_patterns_image(im); });
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_offset_quant_image(im, ratio); });
-	run_rows(c, b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) { y_peephole_image(im); });
+	run_rows(c, "y_e19_restore", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e19_restore_row(im, r); });
+	run_image(c, "y_e20_cleanup", b, n, [=] __device__(const EncImg &im, int) { y_e20_cleanup_image(im, q, ratio); });
+	run_image(c, "y_offset_pairs", b, n, [=] __device__(const EncImg &im, int) { y_offset_pairs_image(im); });
+	run_image(c, "y_offset_patterns", b, n, [=] __device__(const EncImg &im, int) { y_offset_patterns_image(im); });
+	run_image(c, "y_offset_quant", b, n, [=] __device__(const EncImg &im, int) { y_offset_quant_image(im, ratio); });
+	run_rows(c, "y_scan", b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
+	run_image(c, "y_peephole", b, n, [=] __device__(const EncImg &im, int) { y_peephole_image(im); });
 
 	// ---- chroma, U and V planes side by side (nhw_encoder.c:2255-2868)
-	run_plane_rows(c, b, n, 128, [=] __device__(const EncImg &im, int r, int) {
+	run_plane_rows(c, "c_recons1", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
 		if (r < 64) c_recons_ll_row(im, r, 1);
 		c_recons_quant_row(im, r, ratio, 1);
 	});
 	idwt_chroma128(c, b, n);
-	run_plane_rows(c, b, n, 128, [=] __device__(const EncImg &im, int r, int v) { c_correct_row(im, r, v); });
+	run_plane_rows(c, "c_correct", b, n, 128, [=] __device__(const EncImg &im, int r, int v) { c_correct_row(im, r, v); });
 	dwt_level_from_jpeg(c, 2 * n, b.c_jpeg, CS, b.c_proc, CS, 128, 256);
 	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_proc, CS, 256, b.c_ll2s, QS, 128, 128);
-	run_plane_rows(c, b, n, 128, [=] __device__(const EncImg &im, int r, int) {
+	run_plane_rows(c, "c_recons0", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
 		if (r < 64) c_recons_ll_row(im, r, 0);
 		c_recons_quant_row(im, r, ratio, 0);
 	});
 	idwt_chroma128(c, b, n);
-	run_plane_rows(c, b, n, 128, [=] __device__(const EncImg &im, int r, int) { c_residual_tags_row(im, q, r); });
+	run_plane_rows(c, "c_residual_tags", b, n, 128, [=] __device__(const EncImg &im, int r, int) { c_residual_tags_row(im, q, r); });
 	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_ll2s, QS, 128, b.c_proc, CS, 256, 128);
-	run_plane(c, b, n, [=] __device__(const EncImg &im, int v) {
+	run_plane(c, "c_ll_quant", b, n, [=] __device__(const EncImg &im, int v) {
 		int e = c_ll_to_bytes_image(im, v);
 		if (v) im.hdr->exw_v_len = e; else im.hdr->exw_u_len = e;
 		if (q > 15) c_ll_bit1_plane(im, v);
 		c_offset_quant_image(im, ratio);
 	});
-	run_plane_rows(c, b, n, 32, [=] __device__(const EncImg &im, int s, int v) { c_scan_strip(im, s, v); });
+	run_plane_rows(c, "c_scan", b, n, 32, [=] __device__(const EncImg &im, int s, int v) { c_scan_strip(im, s, v); });
 
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
-	run_image(c, b, n, [=] __device__(const EncImg &im, int) {
+	run_image(c, "entropy_pack", b, n, [=] __device__(const EncImg &im, int) {
 		ll_dpcm_chroma_image(im);
 		int a = 0;
 		int rc = packet_stream_image(im, 0, a);

@@ -11,6 +11,8 @@ struct nhw_ctx {
 	int max_batch;
 	cudaStream_t stream;
 	uint64_t launches;
+	int profile;         // per-kernel CUDA-event timing on/off (nhw_profile)
+	void *prof;          // nhw::ProfState
 
 	// ---- per-image workspace, each array sized for max_batch images (device memory).
 	// Plane arrays are made of slots (plane + zero guard bands, see enc_img.cuh).
@@ -61,6 +63,10 @@ void pack_streams(nhw_ctx *c, int n);   // out_dev slots + len_dev -> offs_dev, 
 
 // synth.cu
 void synth(nhw_ctx *c, uint8_t *rgb, int n, uint32_t seed0, int kind, const int16_t *sin_lut);
+
+// api.cu: per-kernel timing with CUDA events recorded on c->stream around each launch
+void prof_begin(nhw_ctx *c, const char *label);
+void prof_end(nhw_ctx *c);
 
 bool check(cudaError_t e, const char *what);
 void set_error(const char *fmt, ...);

@@ -16,9 +16,12 @@
 struct nhw_ctx;
 
 // Launch bookkeeping: every kernel launch goes through this so gpu_launches is a real count.
-#define NHW_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+#define NHW_LAUNCH_L(ctx, label, kernel, grid, block, smem, ...)                          \
 	do {                                                                                  \
+		nhw::prof_begin((ctx), (label));                                                  \
 		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
 		(ctx)->launches++;                                                                \
+		nhw::prof_end((ctx));                                                             \
 	} while (0)
+#define NHW_LAUNCH(ctx, kernel, grid, block, smem, ...) NHW_LAUNCH_L(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 

@@ -52,6 +52,20 @@ def enc_lib():
     return _enc
 
 
+_enc_stock = None
+
+
+def enc_stock_lib():
+    """The same reference objects on the stock allocator: CPU-baseline TIMING only."""
+    global _enc_stock
+    if _enc_stock is None:
+        L = ctypes.CDLL(os.path.join(_REF, "libnhwref_enc_stock.so"), mode=ctypes.RTLD_LOCAL)
+        L.nhwref_encode_discard.restype = ctypes.c_int
+        L.nhwref_encode_discard.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _enc_stock = L
+    return _enc_stock
+
+
 def dec_lib():
     global _dec
     if _dec is None:

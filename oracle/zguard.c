@@ -19,6 +19,7 @@
 
 #define NHW_GUARD 65536
 
+#ifndef NHW_NO_ZGUARD
 void *__real_malloc(size_t);
 void *__real_calloc(size_t, size_t);
 void __real_free(void *);
@@ -39,6 +40,12 @@ void __wrap_free(void *p)
 {
 	if (p) __real_free((char *)p - NHW_GUARD);
 }
+
+#else
+/* timing build (libnhwref_enc_stock.so): stock allocator, the glue's __real_* names map to libc */
+void *__real_malloc(size_t n) { return malloc(n); }
+void __real_free(void *p) { free(p); }
+#endif
 
 __thread jmp_buf nhwref_exit_jmp;
 __thread int nhwref_exit_armed = 0;
