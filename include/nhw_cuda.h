@@ -110,6 +110,13 @@ void *nhw_stream(const nhw_ctx *ctx);
 int nhw_profile(nhw_ctx *ctx, int enable);
 long nhw_profile_read(nhw_ctx *ctx, char *buf, size_t cap);
 
+/* Debug aids for stage-level parity bisection (tests only): stop issuing kernels after the
+ * `occurrence`-th launch of the kernel labelled `label` in the next encode call (NULL = off),
+ * and read a workspace array of image `img` of the last chunk back to the host.
+ * what: proc jpeg aux ll1 ll2s cproc_u cproc_v cjpeg_u cjpeg_v scan tree1 llcode hdr */
+int nhw_debug_stop_after(nhw_ctx *ctx, const char *label, int occurrence);
+int nhw_debug_read(nhw_ctx *ctx, const char *what, int img, void *host, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ EXPORTS = [
     "nhw_create", "nhw_destroy", "nhw_last_error", "nhw_version", "nhw_encode_batch",
     "nhw_encode_batch_device", "nhw_decode_batch", "nhw_stage_frontend_device",
     "nhw_stage_colorspace_device", "nhw_synth_batch_device", "nhw_launch_count",
-    "nhw_stream", "nhw_profile", "nhw_profile_read",
+    "nhw_stream", "nhw_profile", "nhw_profile_read", "nhw_debug_stop_after", "nhw_debug_read",
 ]
 
 _lib = None
@@ -61,6 +61,10 @@ def load_library():
     L.nhw_launch_count.restype = u64
     L.nhw_stream.argtypes = [vp]
     L.nhw_stream.restype = vp
+    L.nhw_debug_stop_after.argtypes = [vp, ctypes.c_char_p, i32]
+    L.nhw_debug_stop_after.restype = i32
+    L.nhw_debug_read.argtypes = [vp, ctypes.c_char_p, i32, vp, ctypes.c_size_t]
+    L.nhw_debug_read.restype = i32
     L.nhw_profile.argtypes = [vp, i32]
     L.nhw_profile.restype = i32
     L.nhw_profile_read.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
@@ -112,6 +116,14 @@ class Codec:
     def stream_ptr(self):
         """cudaStream_t of this context (wrap with torch.cuda.ExternalStream to record events)"""
         return int(self.lib.nhw_stream(self.h) or 0)
+
+    def debug_stop_after(self, label, occurrence=1):
+        self._check(self.lib.nhw_debug_stop_after(self.h, label.encode() if label else None, occurrence), "debug_stop")
+
+    def debug_read(self, what, img, dtype, count):
+        a = np.zeros(count, dtype=dtype)
+        self._check(self.lib.nhw_debug_read(self.h, what.encode(), img, a.ctypes.data, a.nbytes), "debug_read")
+        return a
 
     def profile(self, mode):
         """0 off, 1 on, 2 on + reset"""

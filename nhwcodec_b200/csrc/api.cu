@@ -53,6 +53,16 @@ static cudaEvent_t prof_event(ProfState *p)
 	return e;
 }
 
+// debug bisection aid: true = do not launch (a stop point was reached earlier in this call)
+bool dbg_skip(nhw_ctx *c, const char *label)
+{
+	if (!c->dbg_label[0]) return false;
+	if (c->dbg_stopped) return true;
+	if (strcmp(label, c->dbg_label) == 0 && ++c->dbg_seen >= c->dbg_count) c->dbg_stopped = 2;   // launch this one, then stop
+	if (c->dbg_stopped == 2) { c->dbg_stopped = 1; return false; }
+	return false;
+}
+
 void prof_begin(nhw_ctx *c, const char *label)
 {
 	if (!c->profile) return;
@@ -165,6 +175,40 @@ uint64_t nhw_launch_count(const nhw_ctx *c) { return c ? c->launches : 0; }
 
 void *nhw_stream(const nhw_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
+int nhw_debug_stop_after(nhw_ctx *c, const char *label, int occurrence)
+{
+	if (!c) return NHW_ERR_ARG;
+	c->dbg_label[0] = 0;
+	c->dbg_seen = c->dbg_stopped = 0;
+	c->dbg_count = occurrence > 0 ? occurrence : 1;
+	if (label) { strncpy(c->dbg_label, label, sizeof c->dbg_label - 1); c->dbg_label[sizeof c->dbg_label - 1] = 0; }
+	return NHW_OK;
+}
+
+int nhw_debug_read(nhw_ctx *c, const char *what, int img, void *host, size_t bytes)
+{
+	if (!c || !what || !host || img < 0 || img >= c->max_batch) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	const void *src = nullptr;
+	const size_t i = (size_t)img;
+	if (!strcmp(what, "proc")) src = c->y_proc + NHW_GUARD_S + i * NHW_Y_SLOT;
+	else if (!strcmp(what, "jpeg")) src = c->y_jpeg + NHW_GUARD_S + i * NHW_Y_SLOT;
+	else if (!strcmp(what, "aux")) src = c->y_aux + NHW_GUARD_S + i * NHW_Y_SLOT;
+	else if (!strcmp(what, "ll1")) src = c->y_ll1 + NHW_GUARD_S + i * NHW_C_SLOT;
+	else if (!strcmp(what, "ll2s")) src = c->y_ll2save + NHW_GUARD_S + i * NHW_C_SLOT;
+	else if (!strcmp(what, "cproc_u")) src = c->c_proc + NHW_GUARD_S + (2 * i) * NHW_C_SLOT;
+	else if (!strcmp(what, "cproc_v")) src = c->c_proc + NHW_GUARD_S + (2 * i + 1) * NHW_C_SLOT;
+	else if (!strcmp(what, "cjpeg_u")) src = c->c_jpeg + NHW_GUARD_S + (2 * i) * NHW_C_SLOT;
+	else if (!strcmp(what, "cjpeg_v")) src = c->c_jpeg + NHW_GUARD_S + (2 * i + 1) * NHW_C_SLOT;
+	else if (!strcmp(what, "scan")) src = c->enc_bytes + i * (size_t)ENC_BYTES_SLOT + OFF_SCAN;
+	else if (!strcmp(what, "tree1")) src = c->enc_bytes + i * (size_t)ENC_BYTES_SLOT + OFF_TREE1;
+	else if (!strcmp(what, "llcode")) src = c->enc_bytes + i * (size_t)ENC_BYTES_SLOT + OFF_LLCODE;
+	else if (!strcmp(what, "hdr")) src = c->enc_hdr + i;
+	else return NHW_ERR_ARG;
+	cudaStreamSynchronize(c->stream);
+	return check(cudaMemcpy(host, src, bytes, cudaMemcpyDeviceToHost), "nhw_debug_read") ? NHW_OK : NHW_ERR_CUDA;
+}
+
 int nhw_profile(nhw_ctx *c, int enable)
 {
 	if (!c) return NHW_ERR_ARG;
@@ -262,6 +306,7 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
 	if (!c || !rgb_dev || !out_dev || n <= 0) return NHW_ERR_ARG;
 	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q21 are)", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
+	c->dbg_seen = c->dbg_stopped = 0;
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
 		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
 		nhw::encode_chunk(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, out_dev + (size_t)i0 * NHW_MAX_STREAM_BYTES,

@@ -1,0 +1,167 @@
+// enc_par.cuh -- parallel forms of the raster-order luma stages.
+//
+// The reference walks planes in raster order and edits them in place, so a cell can depend on
+// cells edited earlier.  For each stage the dependency footprint is small and fixed; this file
+// states it and exposes the stage as
+//   * a WAVEFRONT cell: thread = row, step t handles column (t - skew*row); a row may run ahead
+//     of the row below by exactly `skew` columns, which is the smallest lag that lets it read
+//     the row below un-edited and the row above fully edited;
+//   * a ROW function where rows only couple through one boundary cell, handled explicitly;
+//   * a COLUMN function (residual coding walks columns).
+// The same functions are run in the same schedule by tests/hostemu (sequentially, rows of a
+// step in reverse order) to check the analysis against the reference taps.
+#pragma once
+#include "enc_pack.cuh"
+
+// ---- wavefront geometry of each stage -------------------------------------------------------
+struct WfGeom { int r0, rows, c0, cols, skew; };
+
+// offsetY_recons256 pattern substitution: region A then region B (image_processing.c:2759-2849).
+// cell (r,j) reads (r,j-1..j+1),(r+1,j-1..j); writes (r,j-1),(r,j),(r+1,j-1),(r+1,j): skew 3.
+NHW_HD WfGeom wf_recons_patterns_geom(int region) { return region == 0 ? WfGeom{0, 128, 129, 126, 3} : WfGeom{128, 127, 1, 254, 3}; }
+// returns the number of columns consumed (1 or 2)
+NHW_HD int wf_recons_patterns_cell(const EncImg &im, int r, int j)
+{
+	int a = r * YW + j, jj = j;
+	recons_pattern_cell(im.proc, im.jpeg, a, jj);
+	return jj - j + 1;
+}
+
+// offsetY_recons256 isolated-coefficient shrink (image_processing.c:3162-3187): reads all 8
+// neighbours, row above edited, row below not; writes (r,j): skew 2.
+NHW_HD WfGeom wf_shrink_geom() { return WfGeom{1, 254, 1, 254, 2}; }
+NHW_HD int wf_shrink_cell(const EncImg &im, int r, int j)
+{
+	int16_t *J = im.jpeg;
+	const int e = r * YW + j;
+	if (nhw_iabs(J[e]) < 8) return 1;
+	if (nhw_iabs(J[e - YW - 1]) >= 8 || nhw_iabs(J[e - YW]) >= 8 || nhw_iabs(J[e - YW + 1]) >= 8 ||
+	    nhw_iabs(J[e - 1]) >= 8 || nhw_iabs(J[e + 1]) >= 8 || nhw_iabs(J[e + YW - 1]) >= 8 ||
+	    nhw_iabs(J[e + YW]) >= 8 || nhw_iabs(J[e + YW + 1]) >= 8)
+		return 1;
+	if (r >= 128 || j >= 128) J[e] += J[e] > 0 ? -1 : 1;
+	return 1;
+}
+
+// clean-up of the level-1 detail bands (nhw_encoder.c:1923-2098), three passes.
+// cell (r,j) reads (r-1,j) edited, (r+1,j) un-edited, (r,j-1..j+2); writes (r,j),(r,j+1): skew 2.
+NHW_HD WfGeom wf_e20_geom(int pass) { return pass == 0 ? WfGeom{1, 254, 257, 254, 2} : pass == 1 ? WfGeom{256, 255, 1, 255, 2} : WfGeom{256, 255, 257, 254, 2}; }
+NHW_HD int wf_e20_cell(const EncImg &im, int q, int ratio, int pass, int r, int j)
+{
+	int yw, yw2, lo, jmax;
+	if (pass == 0) { if (q > 22) { yw = 8; yw2 = 4; } else { yw = 9; yw2 = 9; } lo = ratio - 2; jmax = 510; }
+	else if (pass == 1) { if (q > 22) { yw = 8; yw2 = 4; } else if (q > 17) { yw = 8; yw2 = 9; } else { yw = 9; yw2 = 9; } lo = ratio - 2; jmax = 254; }
+	else { yw = q > 22 ? 8 : 11; yw2 = yw; lo = ratio - 1; jmax = 510; }
+	e20_cell(im.proc, r * YW + j, j, jmax, lo, yw, yw2, pass);
+	return 1;
+}
+
+// offsetY pattern marks in the level-2 region (image_processing.c:239-290): same footprint as
+// the recons patterns: skew 3.
+NHW_HD WfGeom wf_offset_patterns_geom() { return WfGeom{0, 256, 1, 254, 3}; }
+NHW_HD int wf_offset_patterns_cell(const EncImg &im, int r, int j)
+{
+	int16_t *P = im.proc;
+	const int a = r * YW + j;
+	const int v = P[a];
+	if (v > 3 && v < 8) {
+		if (in4to7(P[a - 1])) {
+			if (in4to7(P[a + 1])) { P[a] = 12700; P[a - 1] = 10100; return 2; }
+			if (in4to7(P[a + YW - 1]) && in4to7(P[a + YW])) {
+				P[a - 1] = 12100; P[a] = 10100; P[a + YW - 1] = 10100; P[a + YW] = 10100; return 2;
+			}
+		}
+	} else if (v < -3 && v > -8) {
+		if (in_m7to_m4(P[a - 1])) {
+			if (in_m7to_m4(P[a + 1])) { P[a] = 12900; P[a - 1] = 10100; return 2; }
+			if (in_m7to_m4(P[a + YW - 1]) && in_m7to_m4(P[a + YW])) {
+				P[a - 1] = 12200; P[a] = 10100; P[a + YW - 1] = 10100; P[a + YW] = 10100; return 2;
+			}
+		}
+	}
+	return 1;
+}
+
+// ---- row forms ---------------------------------------------------------------------------------
+// offsetY like-signed 5..7 pairs (image_processing.c:291-311): sideways only.
+NHW_HD void y_offset_pairs57_row(const EncImg &im, int r /* 0..255 */)
+{
+	int16_t *P = im.proc + r * YW;
+	for (int j = 0; j < 255; j++) {
+		int v = P[j], w = P[j + 1];
+		if (v >= 5 && v <= 7) { if (w >= 5 && w <= 7) { P[j] = 10300; j++; } }
+		else if (v <= -5 && v >= -7) { if (w <= -5 && w >= -7) { P[j] = 10204; j++; } }
+	}
+}
+
+// offsetY loop 1 (image_processing.c:194-237).  The only cross-row read is P[i-1] at column 0
+// (the previous row's last cell) tested as <= 0; this pass only ever decrements cells > 15, so
+// that test has the same outcome before and after the previous row ran: rows are independent.
+NHW_HD void y_offset_mult8_row(const EncImg &im, int r /* 0..511 */)
+{
+	int16_t *P = im.proc;
+	for (int col = r < 256 ? 256 : 0; col < 511; col++) {
+		const int i = r * YW + col;
+		if (!(P[i] > 7 && P[i + 1] > 7)) continue;
+		int a = P[i];
+		if ((a & 7) || (P[i + 1] & 7)) continue;
+		if (a > 15) {
+			if (i > 0) {
+				if (P[i - 1] <= 0) P[i]--;
+				else if (P[i + 1] > 15) { if (col < 510 && P[i + 2] <= 0) P[i + 1]--; }
+			}
+		} else if (P[i + 1] > 15) {
+			if (col < 510 && P[i + 2] <= 0) P[i + 1]--;
+		}
+	}
+}
+
+// offsetY loop 4 (image_processing.c:312-519), one row.  `next0` is the NOT YET QUANTISED first
+// cell of the next row (0 after the last row): the one place the reference looks across the
+// row end without a bounds test.
+NHW_HD void y_offset_quant_row(const EncImg &im, int m1, int r, int next0)
+{
+	int16_t *P = im.proc + r * YW;
+	for (int c = 0; c < 512; c++) {
+		const bool inrow = c < 511;
+		const int nxt = inrow ? (int)P[c + 1] : next0;
+		int a = P[c];
+		if (a > 10000) {
+			int b = a == 10100 ? 128 : a == 12700 ? 127 : a == 12900 ? 129 : a == 10204 ? 125 : a == 10300 ? 126 :
+			        a == 12100 ? 121 : a == 12200 ? 122 : -1;
+			if (b >= 0) { P[c] = (int16_t)b; continue; }
+		}
+		if (a > 127) {
+			int k = ((a & 0xfff8) - 128) >> 3;
+			P[c] = NHW_EXTRA1(k > 18 ? 18 : k);
+			continue;
+		} else if (a < -127) {
+			int k = (((-a) & 0xfff8) - 128) >> 3;
+			P[c] = NHW_EXTRA2(k > 18 ? 18 : k);
+			continue;
+		}
+		if (a < -12 && ((-a) & 7) == 6) {
+			if (inrow && nxt == -7) P[c + 1] = -9;
+		}
+		if (a < 0) {
+			const int nx = inrow ? (int)P[c + 1] : next0;   // may just have become -9
+			if (a == -7 && nx == 8 && inrow) { P[c] = -8; a = -8; }
+			a = -a;
+			if (a > 14 && (a & 7) == 7 && nx > 0 && nx < 8) a -= 2;
+			if ((a & 7) < 7) a &= 504;
+			a = -a;
+		} else if (a == 8 && nxt == -7 && inrow) P[c + 1] = -8;
+		else if (a > 12 && (a & 7) >= 6) {
+			if (inrow && nxt == 7) P[c + 1] = 9;
+		}
+		if (a < m1 && a > -m1) { P[c] = 128; continue; }
+		P[c] = (int16_t)((a + 128) & 248);
+	}
+}
+
+// ---- residual coding with concurrent columns ---------------------------------------------------
+// snapshot layout inside the scratch plane: rows 0..257 of `proc` at the same flat indices,
+// then the 65536 LL1 cells followed by 1024 zeros (reads past the end must see 0).
+#define E16_SNAP_P_CELLS (258 * 512)
+#define E16_SNAP_L_OFF (260 * 512)
+#define E16_SNAP_L_CELLS (65536 + 1024)

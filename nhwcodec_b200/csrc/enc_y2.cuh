@@ -51,43 +51,44 @@ NHW_HD void y_e15_tags_row(const EncImg &im, int r /* 1..510 */)
 // neighbours' cells are only read (scan+1 / stage-1 belong to other columns: see note).
 NHW_HD int res_setting_of(int q) { return q >= 20 ? 3 : q >= 18 ? 4 : q >= 15 ? 6 : 8; }
 
-NHW_HD void e16_band_fix_w1(int16_t *P, int stage)
+NHW_HD void e16_band_fix_w1(int16_t *P, int stage, int left)
 {
-	if (P[stage] == 7) { if (P[stage - 1] >= 0 && P[stage - 1] < 8) P[stage] += 2; }
-	else if (P[stage] == 8) { if (P[stage - 1] >= -2 && P[stage - 1] < 8) P[stage] += 2; }
+	if (P[stage] == 7) { if (left >= 0 && left < 8) P[stage] += 2; }
+	else if (P[stage] == 8) { if (left >= -2 && left < 8) P[stage] += 2; }
 }
-NHW_HD void e16_band_fix_w2(int16_t *P, int stage)
+NHW_HD void e16_band_fix_w2(int16_t *P, int stage, int left)
 {
 	if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
-	else if (P[stage] == 7 || (P[stage] & 65534) == 8) { if (P[stage - 1] >= -2) P[stage] += 3; }
+	else if (P[stage] == 7 || (P[stage] & 65534) == 8) { if (left >= -2) P[stage] += 3; }
 }
-NHW_HD void e16_band_fix_w3(int16_t *P, int16_t *L, int stage, int count, int q)
+NHW_HD void e16_band_fix_w3(int16_t *P, int16_t *L, int stage, int count, int q, int left)
 {
 	if (q >= 21) { L[count] = 14500; return; }
 	if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
-	else if (P[stage] >= 0 && ((P[stage] + 2) & 65532) == 8) { if (P[stage - 1] >= -2) P[stage] = 10; }
+	else if (P[stage] >= 0 && ((P[stage] + 2) & 65532) == 8) { if (left >= -2) P[stage] = 10; }
 	else if (P[stage] > 14 && (P[stage] & 7) == 7) P[stage]++;
 }
-NHW_HD void e16_band_fix_w5(int16_t *P, int16_t *L, int stage, int count, int res, int q)
+NHW_HD void e16_band_fix_w5(int16_t *P, int16_t *L, int stage, int count, int res, int q, int left)
 {
 	L[count] = 14000;
 	if (res == -4) {
-		if (P[stage] == -7 || P[stage] == -8) { if (P[stage - 1] < 2 && P[stage - 1] > -8) P[stage] = -9; }
+		if (P[stage] == -7 || P[stage] == -8) { if (left < 2 && left > -8) P[stage] = -9; }
 	} else if (res < -6) {
 		if (res < -7 && q >= 21) L[count] = 14900;
 		else if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
-		else if (P[stage] == 7 || P[stage] == 8) { if (P[stage - 1] >= -1 && P[stage - 1] < 8) P[stage] += 3; }
+		else if (P[stage] == 7 || P[stage] == 8) { if (left >= -1 && left < 8) P[stage] += 3; }
 	}
 }
 
-// The whole stage is run by one thread per image in the reference's order (column-major):
-// a column reads `scan+1` cells of the next column and band cells `stage-1` written by the
-// previous column, so columns are not independent.
-NHW_HDN void y_e16_residual_image(const EncImg &im, int q)
+// One column j of the stage.  Pn/Ln are where cells of column j+1 (and the P(j,255) cell read
+// at row 0) come from: the reference walks columns left to right, so columns 0..254 must see
+// column j+1 as it was BEFORE the stage (a snapshot when columns run concurrently), while
+// column 255 wraps to cells that earlier columns have already finalised (live planes).
+NHW_HDN void y_e16_residual_col(const EncImg &im, int q, int j, const int16_t *Pn, const int16_t *Ln)
 {
 	int16_t *P = im.proc, *L = im.ll1;
 	const int rs = res_setting_of(q);
-	for (int j = 0; j < 256; j++) {
+	{
 		int scan = j, count = j;
 		for (int row = 0; row < 255; row++, scan += YW, count += 256) {
 			const int stage = (j << 9) + row + 256;
@@ -118,11 +119,11 @@ NHW_HDN void y_e16_residual_image(const EncImg &im, int q)
 				}
 			} else if ((res == 2 || res == 3) && (a == 2 || a == 3)) {
 				if (b == 0 || b == 1) {
-					int c1 = P[scan + 1] - L[count + 1];
+					int c1 = Pn[scan + 1] - Ln[count + 1];
 					if (c1 == 2 || c1 == 3) {
-						int c2 = P[scan + YW + 1] - L[count + 257];
+						int c2 = Pn[scan + YW + 1] - Ln[count + 257];
 						if (c2 == 2 || c2 == 3) {
-							if ((P[scan + 2 * YW + 1] - L[count + 513]) > 0) { L[count] = 12400; P[scan + YW] -= 2; P[scan + 2 * YW] -= 2; }
+							if ((Pn[scan + 2 * YW + 1] - Ln[count + 513]) > 0) { L[count] = 12400; P[scan + YW] -= 2; P[scan + 2 * YW] -= 2; }
 						}
 					}
 				}
@@ -143,11 +144,11 @@ NHW_HDN void y_e16_residual_image(const EncImg &im, int q)
 					if (-b > 0) { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
 					else if (res == -3 && q >= 21) L[count] = 14500;
 					else if (b == 0) {
-						int c1 = P[scan + 1] - L[count + 1];
+						int c1 = Pn[scan + 1] - Ln[count + 1];
 						if (c1 == -2 || c1 == -3) {
-							int c2 = P[scan + YW + 1] - L[count + 257];
+							int c2 = Pn[scan + YW + 1] - Ln[count + 257];
 							if (c2 == -2 || c2 == -3) {
-								if ((P[scan + 2 * YW + 1] - L[count + 513]) < 0) { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
+								if ((Pn[scan + 2 * YW + 1] - Ln[count + 513]) < 0) { L[count] = 12300; P[scan + YW] += 2; P[scan + 2 * YW] += 2; }
 							}
 						}
 					} else if (res == -2) go = W2;
@@ -166,23 +167,34 @@ NHW_HDN void y_e16_residual_image(const EncImg &im, int q)
 			else if (res == -3) go = W3;
 			else if (res < -rs) go = W5;
 
-			if (go == W1) e16_band_fix_w1(P, stage);
-			else if (go == W2) e16_band_fix_w2(P, stage);
-			else if (go == W3) e16_band_fix_w3(P, L, stage, count, q);
-			else if (go == W5) e16_band_fix_w5(P, L, stage, count, res, q);
+			if (go != NONE) {
+				const int left = row == 0 ? Pn[stage - 1] : P[stage - 1];
+				if (go == W1) e16_band_fix_w1(P, stage, left);
+				else if (go == W2) e16_band_fix_w2(P, stage, left);
+				else if (go == W3) e16_band_fix_w3(P, L, stage, count, q, left);
+				else if (go == W5) e16_band_fix_w5(P, L, stage, count, res, q, left);
+			}
 		}
 	}
 }
 
+// serial form (reference order); the CUDA path runs columns 0..254 concurrently against a
+// snapshot and column 255 afterwards (enc_par.cuh)
+NHW_HDN void y_e16_residual_image(const EncImg &im, int q)
+{
+	for (int j = 0; j < 256; j++) y_e16_residual_col(im, q, j, im.proc, im.ll1);
+}
+
 // ---- E16b (nhw_encoder.c:1327-1420): classify what is left, count the side-channel words
-NHW_HDN void y_e16b_classify_image(const EncImg &im, int q)
+// One column of the stage: cell (row,j) only touches its own LL1 code and band cell
+// P(j,256+row), and reads the band cell of (row-1,j): columns are independent.
+NHW_HDN void y_e16b_classify_col(const EncImg &im, int q, int j, int &w1, int &w3, int &w5)
 {
 	int16_t *P = im.proc, *L = im.ll1;
 	const int rs = res_setting_of(q);
-	int w1 = 0, w3 = 0, w5 = 0;
-	for (int row = 0, count = 0; row < 256; row++) {
-		int scan = row * YW;
-		for (int j = 0; j < 256; j++, scan++, count++) {
+	{
+		for (int row = 0; row < 256; row++) {
+			const int scan = row * YW + j, count = row * 256 + j;
 			const int stage = (j << 9) + row + 256;
 			if (L[count] < 12000) {
 				int res = P[scan] - L[count];
@@ -208,22 +220,25 @@ NHW_HDN void y_e16b_classify_image(const EncImg &im, int q)
 					}
 				}
 			} else {
-				switch (L[count]) {
-				case 14000: L[count] = 140; w1++; break;
-				case 14500: L[count] = 145; w5++; break;
-				case 12200: L[count] = 122; w3++; break;
-				case 12100: L[count] = 121; w3++; break;
-				case 12300: L[count] = 123; w3++; break;
-				case 12400: L[count] = 124; w3++; break;
-				case 14100: L[count] = 141; w1++; break;
-				case 12500: L[count] = 125; w3++; w1++; break;
-				case 12600: L[count] = 126; w3++; w1++; break;
-				case 14900: L[count] = 149; w5++; w1++; break;
-				default: break;
+				// every code left by the column pass is a multiple of 100; the byte code is code/100
+				const int v = L[count];
+				const bool w1c = v == 14000 || v == 14100, w3c = v == 12100 || v == 12200 || v == 12300 || v == 12400;
+				const bool w5c = v == 14500, w31 = v == 12500 || v == 12600, w51 = v == 14900;
+				if (w1c || w3c || w5c || w31 || w51) {
+					L[count] = (int16_t)(v / 100);
+					w1 += (w1c || w31 || w51) ? 1 : 0;
+					w3 += (w3c || w31) ? 1 : 0;
+					w5 += (w5c || w51) ? 1 : 0;
 				}
 			}
 		}
 	}
+}
+
+NHW_HDN void y_e16b_classify_image(const EncImg &im, int q)
+{
+	int w1 = 0, w3 = 0, w5 = 0;
+	for (int j = 0; j < 256; j++) y_e16b_classify_col(im, q, j, w1, w3, w5);
 	im.hdr->res1_word_len = w1;
 	im.hdr->res3_word_len = w3;
 	im.hdr->res5_word_len = w5;

@@ -9,9 +9,10 @@
 //   * *_image stages                  : one thread per image (raster-order dependencies)
 // The per-image serial kernels are latency-bound and are the next thing to parallelise
 // (wavefronts / finite-state scans); they are correct and batch-parallel as they stand.
+#include <stdlib.h>
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
-#include "enc_pack.cuh"
+#include "enc_par.cuh"
 #include "enc_batch.cuh"
 #include "../../include/nhw_cuda.h"
 
@@ -111,6 +112,62 @@ template <typename F>
 void run_plane_rows(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, F f)
 {
 	NHW_LAUNCH_L(c, label, k_plane_rows, dim3((rows + 63) / 64, 2 * n), 64, 0, b, rows, f);
+}
+
+// ---- wavefront executor: one CTA per image, thread = row of the stage's region; see enc_par.cuh
+template <typename Cell>
+__global__ void __launch_bounds__(256) k_wavefront(EncBatch b, WfGeom g, Cell cell)
+{
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int ri = threadIdx.x;
+	const int steps = g.cols + g.skew * (g.rows - 1);
+	int next = 0;
+	for (int t = 0; t < steps; t++) {
+		const int c = t - g.skew * ri;
+		if (ri < g.rows && c >= 0 && c < g.cols && c == next) next = c + cell(im, g.r0 + ri, g.c0 + c);
+		__syncthreads();
+	}
+}
+
+template <typename Cell>
+void run_wavefront(nhw_ctx *c, const char *label, const EncBatch &b, int n, WfGeom g, Cell cell)
+{
+	NHW_LAUNCH_L(c, label, k_wavefront, n, 256, 0, b, g, cell);
+}
+
+// ---- residual coding (E16): columns 0..254 concurrently against a snapshot, then column 255
+__global__ void __launch_bounds__(256) k_e16_residual(EncBatch b, int q)
+{
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int4 *ps = reinterpret_cast<const int4 *>(im.proc);
+	int4 *pd = reinterpret_cast<int4 *>(im.aux);
+	for (int i = threadIdx.x; i < E16_SNAP_P_CELLS / 8; i += 256) pd[i] = ps[i];
+	const int4 *ls = reinterpret_cast<const int4 *>(im.ll1);
+	int4 *ld = reinterpret_cast<int4 *>(im.aux + E16_SNAP_L_OFF);
+	for (int i = threadIdx.x; i < E16_SNAP_L_CELLS / 8; i += 256) ld[i] = i < 65536 / 8 ? ls[i] : make_int4(0, 0, 0, 0);
+	__syncthreads();
+	const int j = threadIdx.x;
+	if (j < 255) y_e16_residual_col(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF);
+	__syncthreads();
+	if (j == 255) y_e16_residual_col(im, q, 255, im.proc, im.ll1);
+}
+
+__global__ void __launch_bounds__(256) k_e16b_classify(EncBatch b, int q)
+{
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	int w1 = 0, w3 = 0, w5 = 0;   // the reference only uses these as malloc sizes
+	y_e16b_classify_col(im, q, threadIdx.x, w1, w3, w5);
+}
+
+// ---- offsetY to bytes, one thread per row; the look-ahead cell of the next row is sampled
+// before any row is rewritten
+__global__ void __launch_bounds__(512) k_offset_quant(EncBatch b, int m1)
+{
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int r = threadIdx.x;
+	const int next0 = r < 511 ? (int)im.proc[(r + 1) * YW] : 0;
+	__syncthreads();
+	y_offset_quant_row(im, m1, r, next0);
 }
 
 // ---- inverse transform of one level (wavelet_synthesis, encoder/wavelet_filterbank.c:305-496)
@@ -299,10 +356,10 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- luma closed loop (nhw_encoder.c:141-283)
 	run_rows(c, "y_e6a_tag", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });
-	run_image(c, "y_recons1_serial", b, n, [=] __device__(const EncImg &im, int) {
-		y_recons_ll2_image(im, q, 1);
-		y_recons_patterns_image(im);
-	});
+	run_image(c, "y_recons1_ll2", b, n, [=] __device__(const EncImg &im, int) { y_recons_ll2_image(im, q, 1); });
+	for (int reg = 0; reg < 2; reg++)
+		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
+		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
 	run_rows(c, "y_recons1_quant", b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 1); });
 	idwt_luma256(c, b, n);
 	run_rows(c, "y_e6c_apply", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6c_apply_row(im, r); });
@@ -318,15 +375,16 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_ll2s, CS, 256, b.y_proc, YS, 512, 256);
 
 	// ---- second reconstruction = what the decoder will see as LL1 (nhw_encoder.c:759-781)
-	run_image(c, "y_recons0_serial", b, n, [=] __device__(const EncImg &im, int) {
-		y_recons_ll2_image(im, q, 0);
-		y_recons_patterns_image(im);
-	});
+	run_image(c, "y_recons0_ll2", b, n, [=] __device__(const EncImg &im, int) { y_recons_ll2_image(im, q, 0); });
+	for (int reg = 0; reg < 2; reg++)
+		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
+		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
 	run_rows(c, "y_recons0_quant", b, n, 256, [=] __device__(const EncImg &im, int r) {
 		y_recons_tag57_row(im, r);
 		y_recons_quant_row(im, r, ratio, 0);
 	});
-	run_image(c, "y_recons0_shrink", b, n, [=] __device__(const EncImg &im, int) { y_recons_shrink_image(im); });
+	run_wavefront(c, "y_recons0_shrink", b, n, wf_shrink_geom(),
+	              [=] __device__(const EncImg &im, int r, int j) { return wf_shrink_cell(im, r, j); });
 	idwt_luma256(c, b, n);
 
 	// ---- level-1 thresholds, pattern tags, residual side channels (nhw_encoder.c:783-1887)
@@ -334,8 +392,11 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		if (r >= 256) y_e14_threshold_row(im, q, ratio, r);
 		y_e15_tags_row(im, r);
 	});
-	run_image(c, "y_e16_residual", b, n, [=] __device__(const EncImg &im, int) { y_e16_residual_image(im, q); });
-	run_image(c, "y_e16b_classify", b, n, [=] __device__(const EncImg &im, int) { y_e16b_classify_image(im, q); });
+	NHW_LAUNCH_L(c, "y_e16_residual", k_e16_residual, n, 256, 0, b, q);
+	if (getenv("NHW_E16B_ROWS"))
+		run_rows(c, "y_e16b_classify", b, n, 256, [=] __device__(const EncImg &im, int j) { int w1 = 0, w3 = 0, w5 = 0; y_e16b_classify_col(im, q, j, w1, w3, w5); });
+	else
+		NHW_LAUNCH_L(c, "y_e16b_classify", k_e16b_classify, n, 256, 0, b, q);
 	run_image(c, "y_e18_lists", b, n, [=] __device__(const EncImg &im, int) {
 		y_e18_pack_list_image(im, 1);
 		if (q >= 19) y_e18_pack_list_image(im, 3);
@@ -344,10 +405,14 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
 	run_rows(c, "y_e19_restore", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e19_restore_row(im, r); });
-	run_image(c, "y_e20_cleanup", b, n, [=] __device__(const EncImg &im, int) { y_e20_cleanup_image(im, q, ratio); });
-	run_image(c, "y_offset_pairs", b, n, [=] __device__(const EncImg &im, int) { y_offset_pairs_image(im); });
-	run_image(c, "y_offset_patterns", b, n, [=] __device__(const EncImg &im, int) { y_offset_patterns_image(im); });
-	run_image(c, "y_offset_quant", b, n, [=] __device__(const EncImg &im, int) { y_offset_quant_image(im, ratio); });
+	for (int pass = 0; pass < 3; pass++)
+		run_wavefront(c, "y_e20_cleanup", b, n, wf_e20_geom(pass),
+		              [=] __device__(const EncImg &im, int r, int j) { return wf_e20_cell(im, q, ratio, pass, r, j); });
+	run_rows(c, "y_offset_mult8", b, n, 512, [=] __device__(const EncImg &im, int r) { y_offset_mult8_row(im, r); });
+	run_wavefront(c, "y_offset_patterns", b, n, wf_offset_patterns_geom(),
+	              [=] __device__(const EncImg &im, int r, int j) { return wf_offset_patterns_cell(im, r, j); });
+	run_rows(c, "y_offset_pairs57", b, n, 256, [=] __device__(const EncImg &im, int r) { y_offset_pairs57_row(im, r); });
+	NHW_LAUNCH_L(c, "y_offset_quant", k_offset_quant, n, 512, 0, b, ratio);
 	run_rows(c, "y_scan", b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
 	run_image(c, "y_peephole", b, n, [=] __device__(const EncImg &im, int) { y_peephole_image(im); });
 

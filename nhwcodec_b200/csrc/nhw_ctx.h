@@ -11,6 +11,8 @@ struct nhw_ctx {
 	int max_batch;
 	cudaStream_t stream;
 	uint64_t launches;
+	char dbg_label[64];  // debug: stop issuing kernels after the dbg_count-th launch of this label
+	int dbg_count, dbg_seen, dbg_stopped;
 	int profile;         // per-kernel CUDA-event timing on/off (nhw_profile)
 	void *prof;          // nhw::ProfState
 
@@ -65,6 +67,7 @@ void pack_streams(nhw_ctx *c, int n);   // out_dev slots + len_dev -> offs_dev, 
 void synth(nhw_ctx *c, uint8_t *rgb, int n, uint32_t seed0, int kind, const int16_t *sin_lut);
 
 // api.cu: per-kernel timing with CUDA events recorded on c->stream around each launch
+bool dbg_skip(nhw_ctx *c, const char *label);
 void prof_begin(nhw_ctx *c, const char *label);
 void prof_end(nhw_ctx *c);
 

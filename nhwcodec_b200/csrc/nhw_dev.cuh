@@ -18,6 +18,7 @@ struct nhw_ctx;
 // Launch bookkeeping: every kernel launch goes through this so gpu_launches is a real count.
 #define NHW_LAUNCH_L(ctx, label, kernel, grid, block, smem, ...)                          \
 	do {                                                                                  \
+		if (nhw::dbg_skip((ctx), (label))) break;                                         \
 		nhw::prof_begin((ctx), (label));                                                  \
 		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                  \
 		(ctx)->launches++;                                                                \

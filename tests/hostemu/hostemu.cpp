@@ -12,7 +12,7 @@
 #include <string.h>
 #include <vector>
 
-#include "../../nhwcodec_b200/csrc/enc_pack.cuh"
+#include "../../nhwcodec_b200/csrc/enc_par.cuh"
 
 namespace {
 
@@ -138,6 +138,29 @@ void copy_region(int16_t *dst, int ds, const int16_t *src, int ss, int N)
 
 typedef void (*tap_fn)(const char *, const void *, size_t);
 
+// the CUDA wavefront schedule, run sequentially: step t lets row ri handle column t - skew*ri;
+// rows of one step are visited bottom-up so that any same-step dependency shows up as a diff
+template <typename Cell>
+void host_wavefront(WfGeom g, Cell cell)
+{
+	std::vector<int> next(g.rows, 0);
+	const int steps = g.cols + g.skew * (g.rows - 1);
+	for (int t = 0; t < steps; t++)
+		for (int ri = (getenv("HE_TOPDOWN") ? 0 : g.rows - 1); ri >= 0 && ri < g.rows; ri += (getenv("HE_TOPDOWN") ? 1 : -1)) {
+			const int c = t - g.skew * ri;
+			if (c >= 0 && c < g.cols && c == next[ri]) next[ri] = c + cell(g.r0 + ri, g.c0 + c);
+		}
+}
+
+void host_e16(const EncImg &im, int q)
+{
+	memcpy(im.aux, im.proc, E16_SNAP_P_CELLS * sizeof(int16_t));
+	memcpy(im.aux + E16_SNAP_L_OFF, im.ll1, 65536 * sizeof(int16_t));
+	memset(im.aux + E16_SNAP_L_OFF + 65536, 0, 1024 * sizeof(int16_t));
+	for (int jj = 254; jj >= 0; jj--) { int j = getenv("HE_TOPDOWN") ? 254 - jj : jj; y_e16_residual_col(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF); }
+	y_e16_residual_col(im, q, 255, im.proc, im.ll1);
+}
+
 }  // namespace
 
 extern "C" {
@@ -172,7 +195,8 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	for (int r = 255; r >= 0; r--) y_e6a_tag_row(im, r);
 	T("y_e6a_ll1", im.ll1, 65536 * 2);
 	y_recons_ll2_image(im, q, 1);
-	y_recons_patterns_image(im);
+	for (int reg = 0; reg < 2; reg++)
+		host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
 	for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 1);
 	T("y_rec1_jpeg", im.jpeg, 512 * 512 * 2);
 	inv_level(im.jpeg, im.proc, 512, 256, tmp);
@@ -194,10 +218,11 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	T("y_e12_chres", im.llcode, h->y_res_comp);
 	copy_region(im.proc, 512, im.ll2s, 256, 256);
 	y_recons_ll2_image(im, q, 0);
-	y_recons_patterns_image(im);
+	for (int reg = 0; reg < 2; reg++)
+		host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
 	for (int r = 255; r >= 0; r--) y_recons_tag57_row(im, r);
 	for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 0);
-	y_recons_shrink_image(im);
+	host_wavefront(wf_shrink_geom(), [&](int r, int j) { return wf_shrink_cell(im, r, j); });
 	T("y_rec0_jpeg", im.jpeg, 512 * 512 * 2);
 	inv_level(im.jpeg, im.proc, 512, 256, tmp);
 	T("y_syn0_proc", im.proc, 512 * 512 * 2);
@@ -205,7 +230,7 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	T("y_e14_proc", im.proc, 512 * 512 * 2);
 	for (int r = 510; r >= 1; r--) y_e15_tags_row(im, r);
 	T("y_e15_proc", im.proc, 512 * 512 * 2);
-	y_e16_residual_image(im, q);
+	host_e16(im, q);
 	T("y_e16_proc", im.proc, 512 * 512 * 2);
 	T("y_e16_ll1", im.ll1, 65536 * 2);
 	y_e16b_classify_image(im, q);
@@ -216,11 +241,17 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	if (q >= 21) y_e18_pack_list_image(im, 5);
 	T("y_e18_ll1", im.ll1, 65536 * 2);
 	for (int r = 255; r >= 0; r--) y_e19_restore_row(im, r);
-	y_e20_cleanup_image(im, q, ratio);
+	for (int pass = 0; pass < 3; pass++)
+		host_wavefront(wf_e20_geom(pass), [&](int r, int j) { return wf_e20_cell(im, q, ratio, pass, r, j); });
 	T("y_e20_proc", im.proc, 512 * 512 * 2);
-	y_offset_pairs_image(im);
-	y_offset_patterns_image(im);
-	y_offset_quant_image(im, ratio);
+	for (int r = 511; r >= 0; r--) y_offset_mult8_row(im, r);
+	host_wavefront(wf_offset_patterns_geom(), [&](int r, int j) { return wf_offset_patterns_cell(im, r, j); });
+	for (int r = 255; r >= 0; r--) y_offset_pairs57_row(im, r);
+	{
+		std::vector<int> next0(512);
+		for (int r = 0; r < 512; r++) next0[r] = r < 511 ? im.proc[(r + 1) * 512] : 0;
+		for (int r = 511; r >= 0; r--) y_offset_quant_row(im, ratio, r, next0[r]);
+	}
 	T("y_e21_proc", im.proc, 512 * 512 * 2);
 	for (int s = 127; s >= 0; s--) y_scan_strip(im, s);
 	T("y_e23_scan", im.scan, 262144);
