@@ -367,7 +367,7 @@ def run_ours(args):
             "roofline": roofline,
             "frontend": frontend,
             "cpu_baseline": cpu,
-            "kernels": kernels[:12],
+            "kernels": kernels[:16],
         }
         print(json.dumps(line), flush=True)
     codec.close()

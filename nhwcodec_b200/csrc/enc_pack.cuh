@@ -44,6 +44,89 @@ NHW_HD void put_bits(uint32_t *w, int &a, int &pack, uint32_t code, int len)
 	}
 }
 
+// Alphabet, rank order and rank tables from the two histograms (compress_pixel.c:129-273),
+// in three steps so that the CUDA path can run the sort across a CTA:
+//   pack_enumerate : candidate alphabet in the reference's enumeration order; raises `select`
+//                    (minimum coded zero-run length) until at most 354 entries remain
+//   (sort)         : stable, by decreasing weight (the reference's bubble sort keeps ties in order)
+//   pack_finish    : symbol -> rank / run length -> rank tables, overflow checks
+NHW_HDN int pack_enumerate(PackState &st, int &select, int &k)
+{
+	for (;;) {
+		uint32_t w128 = st.rle_buf[128] > 0 ? (uint32_t)st.rle_buf[128] : 0u;
+		for (int j = 2; j < 256; j++) if (st.rle_128[j] > 0) w128 += (uint32_t)(j * st.rle_128[j]);
+		for (int j = 2; j < select; j++) st.rle_128[j] = 0;
+		for (int j = select; j < 256; j++) if (st.rle_128[j] > 0) w128 -= (uint32_t)(j * st.rle_128[j]);
+		st.rle_buf[128] = (int)w128;
+		k = 0;
+		for (int j = select; j < 256; j++)
+			if (st.rle_128[j] > 0) { st.sym[k] = (uint16_t)((j << 8) | 128); st.weight[k] = (uint32_t)st.rle_128[j]; k++; }
+		for_each_symbol([&](int i) {
+			if (st.rle_buf[i] > 0) { st.sym[k] = (uint16_t)((1 << 8) | i); st.weight[k] = (uint32_t)st.rle_buf[i]; k++; }
+		});
+		if (k <= 354) return 0;
+		select++;
+		if (select >= 100) return NHW_ERR_CODEBOOK_DEV;
+	}
+}
+
+NHW_HDN int pack_finish(PackState &st, int part, int select, int k, int &b)
+{
+	for (int i = 0; i < k; i++) {
+		if ((st.sym[i] >> 8) == 1) st.rle_buf[st.sym[i] & 0xff] = i;
+		else st.rle_128[st.sym[i] >> 8] = i;
+	}
+	b = st.sym[0] == ((1 << 8) | 128) ? 1 : 0;
+	if (part == 0 && b == 0 && k > 290) return NHW_ERR_CODEBOOK_DEV;
+	if (part == 1 && select != 4 && k > 290) return NHW_ERR_CODEBOOK_DEV;
+	const bool zone = (part == 0 && select == 4 && b == 1);
+	if (!zone && k > 290) return NHW_ERR_CODEBOOK_DEV;   // the reference would index past its code table
+	return 0;
+}
+
+NHW_HDN int pack_alphabet(PackState &st, int part, int &select, int &k, int &b)
+{
+	int rc = pack_enumerate(st, select, k);
+	if (rc) return rc;
+	for (int i = 1; i < k; i++) {   // stable insertion sort, decreasing weight
+		uint32_t wv = st.weight[i];
+		uint16_t sv = st.sym[i];
+		int j = i - 1;
+		while (j >= 0 && st.weight[j] < wv) { st.weight[j + 1] = st.weight[j]; st.sym[j + 1] = st.sym[j]; j--; }
+		st.weight[j + 1] = wv;
+		st.sym[j + 1] = sv;
+	}
+	return pack_finish(st, part, select, k, b);
+}
+
+// Codebook section of the container for one stream (compress_pixel.c:400-461)
+NHW_HDN void pack_codebook(const EncImg &im, const PackState &st, int part, int k)
+{
+	EncHdr *h = im.hdr;
+	// ---- codebook: ranked symbol list, de-interleaved (even then odd positions), runs of the
+	// marker byte compressed (compress_pixel.c:400-461)
+	const int marker = part ? 128 : 3;
+	uint8_t *raw = im.tmp3 + 40000, *de = im.tmp3 + 41000;   // raw list, then its de-interleaved copy
+	int n = 0;
+	for (int i = 0; i < k; i++) {
+		if ((st.sym[i] >> 8) == 1) raw[n++] = (uint8_t)(part ? ((st.sym[i] & 0xff) | 1) : (st.sym[i] & 0xff));
+		else { raw[n++] = (uint8_t)marker; raw[n++] = (uint8_t)(st.sym[i] >> 8); }
+	}
+	if (part) h->tree_end = n;
+	int m = 0;
+	for (int i = 0; i < n; i += 2) de[m++] = raw[i];
+	for (int i = 1; i < n; i += 2) de[m++] = raw[i];
+	de[n] = 0;   // canonical: the byte after the list is not the marker
+	uint8_t *outb = part ? im.codebook2 : im.codebook1;
+	int o = 0, run = 0;
+	for (int i = 0; i < n; i++) {
+		while (i < n && de[i] == marker) { run++; i++; }
+		if (run > 0) { outb[o++] = (uint8_t)marker; outb[o++] = (uint8_t)run; run = 0; i--; }
+		else outb[o++] = de[i];
+	}
+	if (part) h->size_tree2 = o; else h->size_tree1 = o;
+}
+
 // Returns 0 or NHW_ERR_CODEBOOK_DEV.  `a` is the running word index across both parts.
 NHW_HDN int packet_stream_image(const EncImg &im, int part, int &a)
 {
@@ -73,42 +156,12 @@ NHW_HDN int packet_stream_image(const EncImg &im, int part, int &a)
 			e = 1; c = 0;
 		}
 	}
-	// ---- alphabet; raise `select` until it fits (compress_pixel.c:129-236)
-	int k;
-	for (;;) {
-		uint32_t w128 = st.rle_buf[128] > 0 ? (uint32_t)st.rle_buf[128] : 0u;
-		for (int j = 2; j < 256; j++) if (st.rle_128[j] > 0) w128 += (uint32_t)(j * st.rle_128[j]);
-		for (int j = 2; j < select; j++) st.rle_128[j] = 0;
-		for (int j = select; j < 256; j++) if (st.rle_128[j] > 0) w128 -= (uint32_t)(j * st.rle_128[j]);
-		st.rle_buf[128] = (int)w128;
-		k = 0;
-		for (int j = select; j < 256; j++)
-			if (st.rle_128[j] > 0) { st.sym[k] = (uint16_t)((j << 8) | 128); st.weight[k] = (uint32_t)st.rle_128[j]; k++; }
-		for_each_symbol([&](int i) {
-			if (st.rle_buf[i] > 0) { st.sym[k] = (uint16_t)((1 << 8) | i); st.weight[k] = (uint32_t)st.rle_buf[i]; k++; }
-		});
-		if (k <= 354) break;
-		select++;
-		if (select >= 100) return NHW_ERR_CODEBOOK_DEV;
+	int k = 0, b = 0;
+	{
+		const int rc = pack_alphabet(st, part, select, k, b);
+		if (rc) return rc;
 	}
-	// ---- stable sort by decreasing weight (the reference's bubble sort; ties keep order)
-	for (int i = 1; i < k; i++) {
-		uint32_t wv = st.weight[i];
-		uint16_t sv = st.sym[i];
-		int j = i - 1;
-		while (j >= 0 && st.weight[j] < wv) { st.weight[j + 1] = st.weight[j]; st.sym[j + 1] = st.sym[j]; j--; }
-		st.weight[j + 1] = wv;
-		st.sym[j + 1] = sv;
-	}
-	for (int i = 0; i < k; i++) {
-		if ((st.sym[i] >> 8) == 1) st.rle_buf[st.sym[i] & 0xff] = i;
-		else st.rle_128[st.sym[i] >> 8] = i;
-	}
-	const int b = st.sym[0] == ((1 << 8) | 128) ? 1 : 0;
-	if (part == 0 && b == 0 && k > 290) return NHW_ERR_CODEBOOK_DEV;
-	if (part == 1 && select != 4 && k > 290) return NHW_ERR_CODEBOOK_DEV;
 	const bool zone = (part == 0 && select == 4 && b == 1);
-	if (!zone && k > 290) return NHW_ERR_CODEBOOK_DEV;   // the reference would index past its code table
 	// ---- emission (compress_pixel.c:279-361)
 	uint8_t *s1 = im.tmp1, *s2 = im.tmp2;
 	int c = 0, j = 0, e = 1, pack = 0, tag = 0;
@@ -167,28 +220,7 @@ NHW_HDN int packet_stream_image(const EncImg &im, int part, int &a)
 		h->select1 = n1;
 		h->select2 = n2;
 	} else h->size_data2 = a + 1;
-	// ---- codebook: ranked symbol list, de-interleaved (even then odd positions), runs of the
-	// marker byte compressed (compress_pixel.c:400-461)
-	const int marker = part ? 128 : 3;
-	uint8_t *raw = im.tmp3 + 40000, *de = im.tmp3 + 41000;   // raw list, then its de-interleaved copy
-	int n = 0;
-	for (int i = 0; i < k; i++) {
-		if ((st.sym[i] >> 8) == 1) raw[n++] = (uint8_t)(part ? ((st.sym[i] & 0xff) | 1) : (st.sym[i] & 0xff));
-		else { raw[n++] = (uint8_t)marker; raw[n++] = (uint8_t)(st.sym[i] >> 8); }
-	}
-	if (part) h->tree_end = n;
-	int m = 0;
-	for (int i = 0; i < n; i += 2) de[m++] = raw[i];
-	for (int i = 1; i < n; i += 2) de[m++] = raw[i];
-	de[n] = 0;   // canonical: the byte after the list is not the marker
-	uint8_t *outb = part ? im.codebook2 : im.codebook1;
-	int o = 0, run = 0;
-	for (int i = 0; i < n; i++) {
-		while (i < n && de[i] == marker) { run++; i++; }
-		if (run > 0) { outb[o++] = (uint8_t)marker; outb[o++] = (uint8_t)run; run = 0; i--; }
-		else outb[o++] = de[i];
-	}
-	if (part) h->size_tree2 = o; else h->size_tree1 = o;
+	pack_codebook(im, st, part, k);
 	if (!part) s[262144] = saved;
 	return 0;
 }

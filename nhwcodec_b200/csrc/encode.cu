@@ -12,7 +12,7 @@
 #include <stdlib.h>
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
-#include "enc_par.cuh"
+#include "enc_seg.cuh"
 #include "enc_batch.cuh"
 #include "../../include/nhw_cuda.h"
 
@@ -168,6 +168,179 @@ __global__ void __launch_bounds__(512) k_offset_quant(EncBatch b, int m1)
 	const int next0 = r < 511 ? (int)im.proc[(r + 1) * YW] : 0;
 	__syncthreads();
 	y_offset_quant_row(im, m1, r, next0);
+}
+
+// ---- peephole passes over the luma scan, one CTA per image (enc_seg.cuh)
+#define PEEP_THREADS 512
+__global__ void __launch_bounds__(PEEP_THREADS) k_peephole(EncBatch b)
+{
+	__shared__ int n_heads, sel1, sel2;
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	uint8_t *s = im.scan;
+	const int N = 262144;
+	uint8_t *out = reinterpret_cast<uint8_t *>(im.aux);                 // 262144 result bytes
+	int *heads = reinterpret_cast<int *>(im.aux) + N / 4;               // chain heads after them
+	if (threadIdx.x == 0) { n_heads = 0; sel1 = 0; sel2 = 0; }
+	__syncthreads();
+	// pass A, phase 1: chain heads on the un-edited stream
+	for (int i = threadIdx.x; i < N - 4; i += PEEP_THREADS) {
+		const int x = s[i];
+		if ((x == 136 || x == 120) && peep_pair_candidate(s, i, N) && !peep_pair_candidate(s, i - 4, N))
+			heads[atomicAdd(&n_heads, 1)] = i;
+	}
+	__syncthreads();
+	// pass A, phase 2: merge along each chain (chains are disjoint)
+	for (int k = threadIdx.x; k < n_heads; k += PEEP_THREADS) peep_merge_chain(s, heads[k], N);
+	__syncthreads();
+	if (threadIdx.x < 4) { s[threadIdx.x] = 128; s[N - 4 + threadIdx.x] = 128; }
+	__syncthreads();
+	// passes B + C: every output byte from the pass-A stream
+	int a1 = 0, a2 = 0;
+	for (int i = threadIdx.x; i < N; i += PEEP_THREADS) {
+		int x1, x2;
+		out[i] = (uint8_t)peep_select_byte(s, i, N, x1, x2);
+		a1 += x1;
+		a2 += x2;
+	}
+	if (a1) atomicAdd(&sel1, a1);
+	if (a2) atomicAdd(&sel2, a2);
+	__syncthreads();
+	const uint4 *o4 = reinterpret_cast<const uint4 *>(out);
+	uint4 *s4 = reinterpret_cast<uint4 *>(s);
+	for (int i = threadIdx.x; i < N / 16; i += PEEP_THREADS) s4[i] = o4[i];
+	if (threadIdx.x == 0) { im.hdr->select1 = sel1; im.hdr->select2 = sel2; }
+}
+
+// ---- entropy stage, one CTA per image, one thread per stream segment (enc_seg.cuh)
+__device__ __forceinline__ void block_excl_scan3(int *a, int *b, int *c, int t)   // 256 entries each, in place
+{
+	__syncthreads();
+	if (t < 3) {
+		int *v = t == 0 ? a : t == 1 ? b : c;
+		int run = 0;
+		for (int k = 0; k < SEG_THREADS; k++) { int x = v[k]; v[k] = run; run += x; }
+		v[SEG_THREADS] = run;
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
+{
+	__shared__ uint16_t fnz[SEG_THREADS];
+	__shared__ int hist_sym[256], hist_run[256];
+	__shared__ int sbits[SEG_THREADS + 1], sn1[SEG_THREADS + 1], sn2[SEG_THREADS + 1];
+	__shared__ uint32_t s_weight[354];
+	__shared__ uint16_t s_sym[354];
+	__shared__ int s_select, s_k, s_b, s_rc, s_bad, s_word0;
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	PackState &st = *static_cast<PackState *>(im.pack_scratch);
+	uint8_t *s = im.scan;
+	EncHdr *h = im.hdr;
+	const int t = threadIdx.x;
+	if (t == 0) { s_word0 = 0; s_rc = 0; }
+	for (int part = 0; part < 2; part++) {
+		const int p1 = part ? 262144 : 0, p2 = part ? 393216 : 262144;
+		const int S = (p2 - p1) / SEG_THREADS;
+		uint8_t saved = 0;
+		if (t == 0) {
+			if (!part) { saved = s[262144]; s[262144] = 3; } else s[393215] = s[393214];
+			s_bad = 0;
+		}
+		hist_sym[t] = 0;
+		hist_run[t] = 0;
+		__syncthreads();
+		fnz[t] = (uint16_t)seg_first_nz(s, p1 + t * S, S);
+		__syncthreads();
+		SegStream ss{s, p1, p2, S, fnz};
+		seg_stats(ss, t, [&](bool run, int idx) { atomicAdd(run ? &hist_run[idx] : &hist_sym[idx], 1); });
+		__syncthreads();
+		st.rle_buf[t] = hist_sym[t];
+		st.rle_128[t] = hist_run[t];
+		__syncthreads();
+		if (t == 0) {
+			int select = part ? 3 : 4, k = 0;
+			int rc = pack_enumerate(st, select, k);
+			s_select = select; s_k = k;
+			if (rc) s_rc = rc;
+		}
+		__syncthreads();
+		if (s_rc) break;
+		const int k = s_k;
+		// stable rank sort by decreasing weight across the CTA
+		for (int i = t; i < k; i += SEG_THREADS) { s_weight[i] = st.weight[i]; s_sym[i] = st.sym[i]; }
+		__syncthreads();
+		for (int i = t; i < k; i += SEG_THREADS) {
+			const uint32_t w = s_weight[i];
+			int rank = 0;
+			for (int j = 0; j < k; j++) rank += (s_weight[j] > w || (s_weight[j] == w && j < i)) ? 1 : 0;
+			st.weight[rank] = w;
+			st.sym[rank] = s_sym[i];
+		}
+		__syncthreads();
+		if (t == 0) {
+			int bb = 0;
+			int rc = pack_finish(st, part, s_select, k, bb);
+			s_b = bb;
+			if (rc) s_rc = rc;
+		}
+		__syncthreads();
+		if (s_rc) break;
+		hist_sym[t] = st.rle_buf[t];     // now: byte -> rank, run length -> rank
+		hist_run[t] = st.rle_128[t];
+		__syncthreads();
+		const int select = s_select;
+		const bool zone = (part == 0 && select == 4 && s_b == 1);
+		// counting pass
+		{
+			int nb = 0, a1 = 0, a2 = 0;
+			int bad = seg_emit(ss, t, hist_sym, hist_run, select, zone, [&](uint32_t, int len) { nb += len; },
+			                   [&](int) { a1++; }, [&](int) { a2++; });
+			if (bad) s_bad = 1;
+			sbits[t] = nb; sn1[t] = a1; sn2[t] = a2;
+		}
+		block_excl_scan3(sbits, sn1, sn2, t);
+		const int total = sbits[SEG_THREADS];
+		const int nwords = total > 0 ? (total + 31) / 32 : 1;
+		const int word0 = s_word0;
+		if (s_bad || word0 + nwords >= NHW_WORDS_LIMIT) {
+			if (t == 0) s_rc = s_bad ? NHW_ERR_CODEBOOK_DEV : NHW_ERR_OVERFLOW_DEV;
+			__syncthreads();
+			break;
+		}
+		if (!part) {
+			for (int i = t; i < (sn1[SEG_THREADS] >> 3) + 1; i += SEG_THREADS) im.sel1[i] = 0;
+			for (int i = t; i < (sn2[SEG_THREADS] >> 3) + 1; i += SEG_THREADS) im.sel2[i] = 0;
+		}
+		__syncthreads();
+		// emission pass: codes are OR-ed into the (pre-zeroed) word array at their bit offsets
+		{
+			long off = sbits[t];
+			int o1 = sn1[t], o2 = sn2[t];
+			uint32_t *words = im.words;
+			auto or_byte = [](uint8_t *base, int idx, int bit) {
+				uint32_t *w = reinterpret_cast<uint32_t *>(base) + (idx >> 5);
+				atomicOr(w, (uint32_t)bit << (((idx >> 3) & 3) * 8 + (7 - (idx & 7))));
+			};
+			seg_emit(ss, t, hist_sym, hist_run, select, zone,
+			         [&](uint32_t code, int len) { seg_put_bits([&](int w, uint32_t v) { atomicOr(&words[w], v); }, word0, off, code, len); off += len; },
+			         [&](int bit) { if (!part && bit) or_byte(im.sel1, o1, 1); o1++; },
+			         [&](int bit) { if (!part && bit) or_byte(im.sel2, o2, 1); o2++; });
+		}
+		__syncthreads();
+		if (t == 0) {
+			if (!part) {
+				h->size_data1 = word0 + nwords;
+				h->wavelet_type = (select > 4 || s_b == 0) ? 4 : 0;
+				h->select1 = (sn1[SEG_THREADS] >> 3) + 1;
+				h->select2 = (sn2[SEG_THREADS] >> 3) + 1;
+				s[262144] = saved;
+			} else h->size_data2 = word0 + nwords;
+			s_word0 = word0 + nwords;
+			pack_codebook(im, st, part, k);
+		}
+		__syncthreads();
+	}
+	if (t == 0) h->status = s_rc;
 }
 
 // ---- inverse transform of one level (wavelet_synthesis, encoder/wavelet_filterbank.c:305-496)
@@ -414,7 +587,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_rows(c, "y_offset_pairs57", b, n, 256, [=] __device__(const EncImg &im, int r) { y_offset_pairs57_row(im, r); });
 	NHW_LAUNCH_L(c, "y_offset_quant", k_offset_quant, n, 512, 0, b, ratio);
 	run_rows(c, "y_scan", b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
-	run_image(c, "y_peephole", b, n, [=] __device__(const EncImg &im, int) { y_peephole_image(im); });
+	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 0, b);
 
 	// ---- chroma, U and V planes side by side (nhw_encoder.c:2255-2868)
 	run_plane_rows(c, "c_recons1", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
@@ -441,13 +614,8 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_plane_rows(c, "c_scan", b, n, 32, [=] __device__(const EncImg &im, int s, int v) { c_scan_strip(im, s, v); });
 
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
-	run_image(c, "entropy_pack", b, n, [=] __device__(const EncImg &im, int) {
-		ll_dpcm_chroma_image(im);
-		int a = 0;
-		int rc = packet_stream_image(im, 0, a);
-		if (rc == 0) { a++; rc = packet_stream_image(im, 1, a); }
-		im.hdr->status = rc;
-	});
+	run_image(c, "c_ll_code", b, n, [=] __device__(const EncImg &im, int) { ll_dpcm_chroma_image(im); });
+	NHW_LAUNCH_L(c, "entropy_pack", k_entropy, n, SEG_THREADS, 0, b);
 	NHW_LAUNCH(c, k_write_stream, (n + 31) / 32, 32, 0, b, n, out_dev, len_dev, status_dev);
 }
 

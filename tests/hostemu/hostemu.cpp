@@ -12,7 +12,7 @@
 #include <string.h>
 #include <vector>
 
-#include "../../nhwcodec_b200/csrc/enc_par.cuh"
+#include "../../nhwcodec_b200/csrc/enc_seg.cuh"
 
 namespace {
 
@@ -138,6 +138,85 @@ void copy_region(int16_t *dst, int ds, const int16_t *src, int ss, int N)
 
 typedef void (*tap_fn)(const char *, const void *, size_t);
 
+// segment-parallel peephole, run sequentially in the kernel's phase order
+void host_peephole(const EncImg &im)
+{
+	uint8_t *s = im.scan;
+	const int N = 262144;
+	std::vector<int> heads;
+	for (int i = 0; i < N - 4; i++)
+		if (peep_pair_candidate(s, i, N) && !peep_pair_candidate(s, i - 4, N)) heads.push_back(i);
+	for (size_t k = heads.size(); k-- > 0;) peep_merge_chain(s, heads[k], N);
+	s[0] = s[1] = s[2] = s[3] = 128;
+	s[N - 4] = s[N - 3] = s[N - 2] = s[N - 1] = 128;
+	std::vector<uint8_t> out(N);
+	int sel1 = 0, sel2 = 0;
+	for (int i = N - 1; i >= 0; i--) {
+		int a, b;
+		out[i] = (uint8_t)peep_select_byte(s, i, N, a, b);
+		sel1 += a;
+		sel2 += b;
+	}
+	memcpy(s, out.data(), N);
+	im.hdr->select1 = sel1;
+	im.hdr->select2 = sel2;
+}
+
+// segment-parallel entropy stage for one stream; word0 = first output word, returns status
+int host_entropy(const EncImg &im, int part, int &word0)
+{
+	PackState &st = *static_cast<PackState *>(im.pack_scratch);
+	uint8_t *s = im.scan;
+	EncHdr *h = im.hdr;
+	const int p1 = part ? 262144 : 0, p2 = part ? 393216 : 262144;
+	uint8_t saved = 0;
+	if (!part) { saved = s[262144]; s[262144] = 3; } else s[393215] = s[393214];
+	const int S = (p2 - p1) / SEG_THREADS;
+	std::vector<uint16_t> fnz(SEG_THREADS);
+	for (int t = 0; t < SEG_THREADS; t++) fnz[t] = (uint16_t)seg_first_nz(s, p1 + t * S, S);
+	SegStream ss{s, p1, p2, S, fnz.data()};
+	for (int i = 0; i < 256; i++) { st.rle_buf[i] = 0; st.rle_128[i] = 0; }
+	for (int t = SEG_THREADS - 1; t >= 0; t--)
+		seg_stats(ss, t, [&](bool run, int idx) { if (run) st.rle_128[idx]++; else st.rle_buf[idx]++; });
+	int select = part ? 3 : 4, k = 0, b = 0;
+	int rc = pack_alphabet(st, part, select, k, b);
+	if (rc) return rc;
+	const bool zone = (part == 0 && select == 4 && b == 1);
+	std::vector<long> bits(SEG_THREADS + 1, 0), n1(SEG_THREADS + 1, 0), n2(SEG_THREADS + 1, 0);
+	int bad = 0;
+	for (int t = 0; t < SEG_THREADS; t++) {
+		long nb = 0, a1 = 0, a2 = 0;
+		bad |= seg_emit(ss, t, st.rle_buf, st.rle_128, select, zone, [&](uint32_t, int len) { nb += len; },
+		                [&](int) { a1++; }, [&](int) { a2++; });
+		bits[t + 1] = bits[t] + nb; n1[t + 1] = n1[t] + a1; n2[t + 1] = n2[t] + a2;
+	}
+	if (bad) return NHW_ERR_CODEBOOK_DEV;
+	const long total = bits[SEG_THREADS];
+	const int nwords = total > 0 ? (int)((total + 31) / 32) : 1;
+	if (word0 + nwords >= NHW_WORDS_LIMIT) return NHW_ERR_OVERFLOW_DEV;
+	if (!part) {
+		memset(im.sel1, 0, (n1[SEG_THREADS] >> 3) + 1);
+		memset(im.sel2, 0, (n2[SEG_THREADS] >> 3) + 1);
+	}
+	for (int t = SEG_THREADS - 1; t >= 0; t--) {
+		long off = bits[t], o1 = n1[t], o2 = n2[t];
+		seg_emit(ss, t, st.rle_buf, st.rle_128, select, zone,
+		         [&](uint32_t code, int len) { seg_put_bits([&](int w, uint32_t v) { im.words[w] |= v; }, word0, off, code, len); off += len; },
+		         [&](int bit) { if (!part) im.sel1[o1 >> 3] |= (uint8_t)(bit << (7 - (o1 & 7))); o1++; },
+		         [&](int bit) { if (!part) im.sel2[o2 >> 3] |= (uint8_t)(bit << (7 - (o2 & 7))); o2++; });
+	}
+	if (!part) {
+		h->size_data1 = word0 + nwords;
+		h->wavelet_type = (select > 4 || b == 0) ? 4 : 0;
+		h->select1 = (int)(n1[SEG_THREADS] >> 3) + 1;
+		h->select2 = (int)(n2[SEG_THREADS] >> 3) + 1;
+	} else h->size_data2 = word0 + nwords;
+	word0 += nwords;
+	pack_codebook(im, st, part, k);
+	if (!part) s[262144] = saved;
+	return 0;
+}
+
 // the CUDA wavefront schedule, run sequentially: step t lets row ri handle column t - skew*ri;
 // rows of one step are visited bottom-up so that any same-step dependency shows up as a diff
 template <typename Cell>
@@ -255,7 +334,7 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	T("y_e21_proc", im.proc, 512 * 512 * 2);
 	for (int s = 127; s >= 0; s--) y_scan_strip(im, s);
 	T("y_e23_scan", im.scan, 262144);
-	y_peephole_image(im);
+	if (getenv("HE_SERIAL")) y_peephole_image(im); else host_peephole(im);
 	T("y_e24_scan", im.scan, 262144);
 
 	// ---------------- chroma ----------------
@@ -298,12 +377,21 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	T("uv_scan", im.scan + 262144, 131072);
 	ll_dpcm_chroma_image(im);
 	T("llcode", im.llcode, h->end_ch_res);
-	int a = 0;
-	int rc = packet_stream_image(im, 0, a);
-	if (rc) return rc;
-	a++;
-	rc = packet_stream_image(im, 1, a);
-	if (rc) return rc;
+	int rc;
+	if (getenv("HE_SERIAL")) {
+		int a = 0;
+		rc = packet_stream_image(im, 0, a);
+		if (rc) return rc;
+		a++;
+		rc = packet_stream_image(im, 1, a);
+		if (rc) return rc;
+	} else {
+		int word0 = 0;
+		rc = host_entropy(im, 0, word0);
+		if (rc) return rc;
+		rc = host_entropy(im, 1, word0);
+		if (rc) return rc;
+	}
 	T("hdr", h, sizeof *h);
 	return write_stream_image(im, out);
 }
