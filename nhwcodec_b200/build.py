@@ -53,7 +53,26 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     cmd = ["nvcc", "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
     subprocess.check_call(cmd)
+    build_host()
     return LIB
+
+
+def build_host():
+    """libnhw_compat.so (the reference's per-image entry points) and the nhw-enc CLI: plain C."""
+    compat = os.path.join(HERE, "libnhw_compat.so")
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-Wall", os.path.join(CSRC, "compat.c"), "-o", compat,
+                           "-L" + HERE, "-lnhw_cuda", "-Wl,-rpath,$ORIGIN"])
+    cli = os.path.join(HERE, "..", "cli")
+    subprocess.check_call(["gcc", "-O2", "-Wall", os.path.join(cli, "nhw_enc_cli.c"), "-o", os.path.join(cli, "nhw-enc"),
+                           "-L" + HERE, "-lnhw_compat", "-lnhw_cuda", "-Wl,-rpath,$ORIGIN/../nhwcodec_b200"])
+    # drop-in proof: the reference's OWN, unmodified CLI source compiled against its own header
+    # and linked against our two libraries (only where the reference tree is present)
+    ref_cli = "/root/reference/encoder/nhw_encoder_cli.c"
+    ref_out = os.path.join(HERE, "..", "oracle", "_ref")
+    if os.path.exists(ref_cli) and os.path.isdir(ref_out):
+        subprocess.check_call(["gcc", "-O2", "-w", "-I/root/reference/encoder", ref_cli, "-o",
+                               os.path.join(ref_out, "nhw-enc-dropin"), "-L" + HERE, "-lnhw_compat", "-lnhw_cuda",
+                               "-Wl,-rpath,$ORIGIN/../../nhwcodec_b200"])
 
 
 if __name__ == "__main__":

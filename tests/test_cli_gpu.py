@@ -1,0 +1,53 @@
+"""Drop-in boundary on the GPU: our nhw-enc and the reference's own CLI source linked against
+libnhw_compat/libnhw_cuda must write the canonical .nhw bytes."""
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+from test_oracle_cpu import bmp_header, smooth_pixels
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KAT_Q20 = "9ea5053bd20fc35758652b0a0aa47b8d"
+
+
+@pytest.fixture(scope="module")
+def smooth_bmp(tmp_path_factory):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    p = tmp_path_factory.mktemp("cli") / "smooth.bmp"
+    p.write_bytes(bmp_header() + smooth_pixels().tobytes())
+    return str(p)
+
+
+@pytest.mark.parametrize("exe", ["cli/nhw-enc", "oracle/_ref/nhw-enc-dropin"])
+def test_cli_known_answer(smooth_bmp, exe, tmp_path):
+    path = os.path.join(ROOT, exe)
+    if not os.path.exists(path):
+        pytest.skip(exe + " not built")
+    out = str(tmp_path / "out.nhw")
+    r = subprocess.run([path, "-q20", smooth_bmp, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    data = open(out, "rb").read()
+    assert len(data) == 24412
+    assert hashlib.md5(data).hexdigest() == KAT_Q20
+    # refuses to overwrite without -f, like the reference (encoder/nhw_encoder_cli.c:163-172)
+    r2 = subprocess.run([os.path.join(ROOT, "cli/nhw-enc"), "-q20", smooth_bmp, out], capture_output=True, text=True)
+    assert r2.returncode == 1
+    r3 = subprocess.run([os.path.join(ROOT, "cli/nhw-enc"), "-f", "-q20", smooth_bmp, out], capture_output=True, text=True)
+    assert r3.returncode == 0
+
+
+def test_cli_rejects_bad_input(tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    bad = tmp_path / "bad.bmp"
+    bad.write_bytes(b"XX" + b"\0" * 100)
+    r = subprocess.run([os.path.join(ROOT, "cli/nhw-enc"), str(bad), str(tmp_path / "o.nhw")], capture_output=True)
+    assert r.returncode == (-13) % 256     # HEADER_CHECK_ERROR_NO_VALID_SIG, encoder/nhw_encoder.c:63-71
+    r = subprocess.run([os.path.join(ROOT, "cli/nhw-enc"), "-q99", "a", "b"], capture_output=True)
+    assert r.returncode == 1

@@ -93,6 +93,39 @@ def test_library_exports_header_symbols():
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
 
 
+def test_compat_library_exports_reference_symbols():
+    """libnhw_compat must export the reference's own entry points"""
+    path = os.path.join(os.path.dirname(capi.LIB_PATH), "libnhw_compat.so")
+    if not os.path.exists(path) or not os.path.exists(capi.LIB_PATH):
+        pytest.skip("libraries not built")
+    ctypes.CDLL(capi.LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(path)
+    for name in ("read_image_bmp", "encode_image", "write_compressed_file", "bmp_header"):
+        assert hasattr(lib, name), name
+
+
+def test_compat_struct_layout_matches_reference(tmp_path):
+    """the ABI structs in include/nhw_compat.h must lay out exactly like encoder/codec.h"""
+    ref = "/root/reference/encoder/codec.h"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present")
+    import subprocess
+    src = tmp_path / "lay.c"
+    src.write_text("""#include <stdio.h>
+#include <stddef.h>
+#include HDR
+int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(codec_setup), sizeof(image_buffer),
+ sizeof(encode_state), offsetof(encode_state, nhw_res6_len), offsetof(encode_state, nhw_char_res1),
+ offsetof(encode_state, size_data1), offsetof(encode_state, high_qsetting3), offsetof(encode_state, ch_res),
+ offsetof(image_buffer, setup), offsetof(encode_state, highres_word)); return 0; }""")
+    outs = []
+    for hdr in (ref, os.path.join(ROOT, "include", "nhw_compat.h")):
+        exe = tmp_path / "lay"
+        subprocess.check_call(["gcc", "-DHDR=\"%s\"" % hdr, str(src), "-o", str(exe)])
+        outs.append(subprocess.check_output([str(exe)]))
+    assert outs[0] == outs[1], outs
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
