@@ -1,0 +1,350 @@
+// dec_core.cuh -- decoder stage functions (host/device), q17..q21.
+//
+//   dec_ll_dpcm          : LL byte decode of parse_file          decoder/nhw_decoder.c:1663-2026
+//   dec_prefix_luma/_chroma : retrieve_pixel_Y_comp / _UV_comp   decoder/compress_pixel.c:49-444, 446-641
+//   dec_expand_list      : res1/res3/res5 position lists          decoder/nhw_decoder.c:93-491
+//   dec_luma_* / dec_chroma_* : inline stages of decode_image     decoder/nhw_decoder.c:71-1474
+//   ycc_to_rgb           : write_image_bmp                        decoder/nhw_decoder_cli.c:108-291
+//
+// The prefix decoder does not use the reference's hand-built tables (decoder/tables.h): the code is
+// static (rank r <-> nhw_code_bits[r], nhw_code_len[r], the same pairs the encoder writes), so a
+// rank is found by matching the next bits against those pairs; the zone escape (nine bits
+// 000000001 + 6 bits) is checked first when the stream uses it.
+#pragma once
+#include "enc_seg.cuh"
+
+struct DecDesc {   // one per image, filled on the host from the .nhw header
+	int32_t status, quality, byte0;
+	int32_t size_tree1, size_tree2, size_data1, size_data2, tree_end, exw_Y_end;
+	int32_t res1_len, res1_bit_len, res3_len, res3_bit_len, res4_len, res5_len, res5_bit_len;
+	int32_t select1, select2, highres_comp_len, end_ch_res;
+	uint32_t off_tree1, off_tree2, off_exw, off_res1, off_res1_bit, off_res1_word, off_res4, off_res3, off_res3_bit,
+	    off_res3_word, off_res5, off_res5_bit, off_res5_word, off_sel1, off_sel2, off_u64, off_v64, off_highres,
+	    off_ch_res, off_words;
+	uint32_t blob_len;
+};
+
+struct DecImg {
+	const uint8_t *blob;     // the .nhw bytes
+	const DecDesc *d;
+	int16_t *proc, *jpeg, *aux;       // luma planes (512x512)
+	int16_t *uvcoef;                  // im_nhw3: 131072 interleaved chroma coefficients
+	int16_t *cproc, *cjpeg, *caux;    // chroma planes of one component (256x256)
+	uint8_t *res_comp;                // 24577 LL bytes
+	uint16_t *list[8];                // expanded position lists (res1 -,+ ; res5 -,+ ; res3 x4)
+	int32_t *list_len;                // 8 lengths + [8] = stale `count`, [9] = edge-flag count
+	uint16_t *flags;                  // edge-flag positions
+	uint16_t *book;                   // rank -> (run<<8 | byte)
+	uint8_t *yuv;                     // Y, U, V u8 planes 512x512 each
+};
+
+NHW_HD int nhw_extra_value(int word) { return word >= 0 && word < 110 ? (int)nhw_extra_table[word] : 0; }
+
+// ---- bit reader over the packed 32-bit words (stored little-endian, consumed MSB first)
+struct BitReader {
+	const uint8_t *b;
+	long pos;
+	NHW_HD uint32_t word(long i) const
+	{
+		const uint8_t *p = b + 4 * i;
+		return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+	}
+	NHW_HD uint32_t peek(int n) const   // next n (<=24) bits, MSB first
+	{
+		const long w = pos >> 5;
+		const int sh = (int)(pos & 31);
+		unsigned long long v = ((unsigned long long)word(w) << 32) | word(w + 1);
+		return (uint32_t)((v << sh) >> (64 - n));
+	}
+	NHW_HD void skip(int n) { pos += n; }
+};
+
+// rank of the next code (static prefix code).  Returns -1 if nothing matches.
+NHW_HD int dec_next_rank(BitReader &br, bool zone)
+{
+	const uint32_t v = br.peek(20);
+	if (zone && (v >> 11) == 1) {   // 000000001 + 6 bits
+		const int r = (int)((v >> 5) & 63) + 110;
+		br.skip(15);
+		return r;
+	}
+	// codes are listed by non-decreasing length: scan lengths, compare within the length's ranks
+	for (int r = 0; r < NHW_CODE_DEPTH; r++) {
+		const int len = nhw_code_len[r];
+		if ((v >> (20 - len)) == nhw_code_bits[r]) {
+			br.skip(len);
+			return (zone && r >= 110) ? r + 64 : r;
+		}
+	}
+	return -1;
+}
+
+// ---- codebook: un-RLE, re-interleave, build rank -> symbol table (compress_pixel.c:92-118, 455-478)
+NHW_HDN int dec_build_book(const uint8_t *tree, int size, int marker, int e_override, uint16_t *book, uint8_t *tmp /* 2*1024 */)
+{
+	uint8_t *flat = tmp, *inter = tmp + 1024;
+	int e = 0;
+	for (int i = 0; i < size && e < 1000; i++) {
+		if (tree[i] == marker) {
+			for (int j = 0; j < tree[i + 1] && e < 1000; j++) flat[e++] = (uint8_t)marker;
+			i++;
+		} else flat[e++] = tree[i];
+	}
+	if (e_override >= 0) e = e_override;
+	for (int i = 0; i < 1024; i++) inter[i] = 0;
+	int j = 0;
+	for (int i = 0; i < e; i += 2) inter[i] = flat[j++];
+	for (int i = 1; i < e; i += 2) inter[i] = flat[j++];
+	int n = 0;
+	for (int i = 0; i < e; i++) {
+		if (marker == 3) {   // luma: 3 = "zero run" marker followed by the run length
+			if (inter[i] == 3) { book[n++] = (uint16_t)((inter[i + 1] << 8) | 128); i++; }
+			else book[n++] = (uint16_t)(256 | inter[i]);
+		} else {             // chroma: even byte = (128, run length) pair, odd byte = symbol | 1
+			if (!(inter[i] & 1)) { book[n++] = (uint16_t)((inter[i + 1] << 8) | inter[i]); i++; }
+			else book[n++] = (uint16_t)(256 | (inter[i] & 0xfe));
+		}
+	}
+	return n;
+}
+
+// ---- luma prefix decode + run / select-bit logic (compress_pixel.c:120-444)
+NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
+{
+	const DecDesc *d = im.d;
+	const uint8_t *sel1 = im.blob + d->off_sel1, *sel2 = im.blob + d->off_sel2;
+	const bool zone = d->byte0 < 4;
+	BitReader br{im.blob + d->off_words, 0};
+	const long nbits = (long)d->size_data1 * 32;
+	const int p1 = 262144;
+	int e = 0, mem = 0, mem2 = 0, ac1 = 0, run_over = -257, t = 0, t2 = 0;
+	auto bit1 = [&](int k) { return (sel1[k >> 3] >> (7 - (k & 7))) & 1; };
+	auto bit2 = [&](int k) { return (sel2[k >> 3] >> (7 - (k & 7))) & 1; };
+	auto z = [&](int k) { return k >= 0 ? im3[k] == 0 : true; };   // reads below 0 see the zero guard
+	while (br.pos < nbits + 64) {
+		const int dec = dec_next_rank(br, zone);
+		if (dec < 0) return NHW_ERR_CODEBOOK_DEV;
+		const int sym = im.book[dec];
+		const int word = sym & 0xff, run = sym >> 8;
+		if (word == 0x80) {
+			mem++;
+			if (mem2 == 1) {
+				if (e >= 5 && z(e - 2) && z(e - 3) && z(e - 4) && z(e - 5)) { im3[e++] = bit2(t2++) ? 11 : -11; }
+				else if (run >= 4 && z(e - 2)) { im3[e++] = bit2(t2++) ? 11 : -11; }
+				mem2 = 0;
+			} else if (mem == 2 && !ac1) {
+				if (e >= 4 && z(e - 1) && z(e - 2) && z(e - 3) && z(e - 4) && (e + run - 257) >= run_over) {
+					im3[e++] = bit1(t++) ? -11 : 11;
+					mem = 1;
+				} else if (run >= 4 && e > 0 && z(e - 1) && !ac1 && (e + run - 257) >= run_over) {
+					im3[e++] = bit1(t++) ? -11 : 11;
+					mem = 1;
+				}
+			} else if (run >= 4 && e > 0 && z(e - 1) && !ac1 && (e + run - 257) >= run_over) {
+				im3[e++] = bit1(t++) ? -11 : 11;
+				mem = 1;
+			}
+			if (run == 254) { ac1 = 1; mem = 0; run_over = e; }
+			else ac1 = 0;
+			e += run;
+		} else {
+			mem = 0; mem2 = 0; ac1 = 0;
+			bool done = true;
+			if (word == 136) { im3[e++] = 11; mem2 = 1; }
+			else if (word == 120) { im3[e++] = -11; mem2 = 1; }
+			else if (word >= 132 && word <= 135) {
+				im3[e] = (int16_t)(word < 134 ? 11 : -11);
+				e += 4;
+				im3[e++] = (int16_t)((word & 1) ? -11 : 11);
+			}
+			else if (word == 127) im3[e++] = 1008;
+			else if (word == 129) im3[e++] = 1009;
+			else if (word == 125) im3[e++] = 1006;
+			else if (word == 126) im3[e++] = 1007;
+			else if (word == 121) im3[e++] = 1010;
+			else if (word == 122) im3[e++] = 1011;
+			else if (word == 124) im3[e++] = 11;
+			else if (word == 123) im3[e++] = -11;
+			else done = false;
+			if (!done) {
+				const int x = word < 110 ? nhw_extra_value(word) : 0;
+				if (x > 0) im3[e++] = (int16_t)(123 + (x << 3));
+				else if (x < 0) im3[e++] = (int16_t)((x << 3) - 123);
+				else im3[e++] = (int16_t)(word > 0x80 ? word - 125 : word - 131);
+			}
+		}
+		if (e >= p1 - 1) return 0;
+	}
+	return NHW_ERR_CODEBOOK_DEV;   // ran out of bits
+}
+
+// ---- chroma prefix decode (compress_pixel.c:479-641): no zone, no select bits
+NHW_HDN int dec_prefix_chroma(const DecImg &im, int16_t *im3 /* 131072, zeroed */)
+{
+	const DecDesc *d = im.d;
+	BitReader br{im.blob + d->off_words + 4 * (size_t)d->size_data1, 0};
+	const long nbits = (long)(d->size_data2 - d->size_data1) * 32;
+	const int p1 = 131071;
+	int e = 0;
+	while (br.pos < nbits + 64) {
+		const int dec = dec_next_rank(br, false);
+		if (dec < 0) return NHW_ERR_CODEBOOK_DEV;
+		const int sym = im.book[dec];
+		const int word = sym & 0xff;
+		if (word == 0x80) e += sym >> 8;
+		else {
+			const int x = word < 110 ? nhw_extra_value(word) : 0;
+			if (word < 110 && x > 0) im3[e++] = (int16_t)(123 + (x << 3));
+			else if (word < 110 && x < 0) im3[e++] = (int16_t)((x << 3) - 123);
+			else if (word >= 110 && word == 124) im3[e++] = 5005;
+			else if (word >= 110 && word == 126) im3[e++] = 5006;
+			else if (word >= 110 && word == 122) im3[e++] = 5003;
+			else if (word >= 110 && word == 130) im3[e++] = 5004;
+			else im3[e++] = (int16_t)(word > 0x80 ? word - 125 : word - 131);
+		}
+		if (e >= p1 - 1) return 0;
+	}
+	return NHW_ERR_CODEBOOK_DEV;
+}
+
+// ---- LL bytes (parse_file, nhw_decoder.c:1663-2026).  All arithmetic is modulo 256 like the
+// reference's unsigned char stores.
+NHW_HDN void dec_ll_dpcm(const DecImg &im)
+{
+	const DecDesc *d = im.d;
+	const uint8_t *ch = im.blob + d->off_ch_res, *hr = im.blob + d->off_highres;
+	uint8_t *o = im.res_comp;
+	const int q = d->quality, mode = d->byte0 & 3;
+	int j = 1, i = 1, a = 0;
+	o[0] = ch[0];
+	auto rel = [&](int delta) { o[j] = (uint8_t)(o[j - 1] + delta); j++; };
+	auto triple = [&](int c0, int c1) {   // 3 deltas packed in two bytes (marker 64)
+		rel((((c0 >> 1) & 31) << 1) - 32);
+		rel(((((c0 & 1) << 3) | (c1 >> 5)) << 1) - 16);
+		rel(((c1 & 31) << 1) - 32);
+	};
+	for (; j < 16384; i++) {
+		const int c = ch[i];
+		if (c >= 128) {
+			if (q > 15) o[j++] = hr[a++];
+			o[j++] = (uint8_t)((c - 128) << 1);
+		} else if (mode == 0) {
+			if (c < 16) {
+				const int run = (c >> 3) & 1;
+				const uint8_t v = o[j - 1];
+				for (int e = 0; e < run + 2; e++) o[j++] = v;
+				const int k = c & 7;
+				if (k == 1) rel(2);
+				else if (k == 2) { rel(2); rel(-2); }
+				else if (k == 3) { rel(2); rel(0); }
+				else if (k == 4) { rel(-2); rel(2); }
+				else if (k == 5) { rel(-2); rel(0); }
+				else if (k == 6) rel(-2);
+				else if (k == 7) rel(4);
+			} else if (c < 32) {
+				rel(c >= 24 ? 4 : 2);
+				rel(((c & 7) << 1) - 8);
+			} else if (c < 64) {
+				const int x = c - 32;
+				rel(((x >> 3) << 1) - 6);
+				rel(((x & 7) << 1) - 8);
+			} else { i++; triple(c - 64, ch[i]); }
+		} else if (mode == 1) {
+			if (c < 32) {
+				const int run = (c >> 2) & 7;
+				const uint8_t v = o[j - 1];
+				for (int e = 0; e < run + 2; e++) o[j++] = v;
+				const int k = c & 3;
+				if (k == 1) rel(2);
+				else if (k == 2) rel(-2);
+				else if (k == 3) rel(0);
+			} else if (c < 64) {
+				const int x = c - 32;
+				rel(((x >> 3) << 1) - 4);
+				rel(((x & 7) << 1) - 8);
+			} else { i++; triple(c - 64, ch[i]); }
+		} else {
+			if (c < 64) {
+				const int run = c & 63;
+				const uint8_t v = o[j - 1];
+				for (int e = 0; e < run + 2; e++) o[j++] = v;
+			} else { i++; triple(c - 64, ch[i]); }
+		}
+	}
+	o[16384] = ch[i++];
+	for (j = 16385; j < 24576; i++) {
+		const int c = ch[i];
+		if (c >= 192) {
+			const int x = c - 192, k = x >> 2;
+			const int d0 = k < 2 ? 0 : (k == 2 || k == 4 || k == 5) ? 4 : -4;
+			const int d1 = (k == 0 || k == 4 || k == 6) ? 4 : (k == 1 || k == 5 || k == 7) ? -4 : 0;
+			rel(d0);
+			rel(d1);
+			const int m = x & 3;
+			rel(m == 0 ? 0 : m == 1 ? 4 : m == 2 ? -4 : 8);
+		} else if (c >= 128) o[j++] = (uint8_t)((c - 128) << 2);
+		else if (c >= 64) {
+			int run = (c >> 3) & 7;
+			const uint8_t v = o[j - 1];
+			if (run == 7) {
+				run = (c & 7) + 7;
+				for (int e = 0; e < run + 2; e++) o[j++] = v;
+			} else {
+				for (int e = 0; e < run + 2; e++) o[j++] = v;
+				const int k = c & 7;
+				if (k == 1) rel(4);
+				else if (k == 2) { rel(4); rel(-4); }
+				else if (k == 3) { rel(4); rel(-4); rel(0); }
+				else if (k == 4) { rel(-4); rel(4); rel(0); }
+				else if (k == 5) { rel(-4); rel(4); }
+				else if (k == 6) rel(-4);
+				else if (k == 7) rel(8);
+			}
+		} else {
+			rel(((c >> 3) << 2) - 16);
+			rel(((c & 7) << 2) - 16);
+		}
+	}
+	if (q > 15) {
+		const uint8_t *u = im.blob + d->off_u64, *v = im.blob + d->off_v64;
+		for (int k = 0; k < 4096; k++) {
+			o[16384 + k] = (uint8_t)(o[16384 + k] + (((u[k >> 3] >> (7 - (k & 7))) & 1) << 1));
+			o[20480 + k] = (uint8_t)(o[20480 + k] + (((v[k >> 3] >> (7 - (k & 7))) & 1) << 1));
+		}
+	}
+}
+
+// ---- position list expansion (nhw_decoder.c:93-183 and its res5/res3 twins).
+// in: packed list (pair-delta bytes >=128, 127 = row step), LSB plane.  out: col + (row<<8).
+// Returns the number of entries; cap = 8*bit_len like the reference's calloc.
+NHW_HDN int dec_expand_list(const uint8_t *res, int len, const uint8_t *bits, int bit_len, uint16_t *out)
+{
+	const int cap = bit_len << 3;
+	for (int i = 0; i < cap; i++) out[i] = 0;
+	int stage = 0, count;
+	auto last = [&]() { return stage > 0 ? (int)out[stage - 1] : 0; };   // [-1] reads the zero guard
+	int prev = res[0];                       // value of res[i-1] as the reference leaves it behind
+	if (res[0] == 127) count = 1;
+	else { out[stage++] = (uint16_t)(res[0] << 1); count = 0; }
+	for (int i = 1; i < len; i++) {
+		int cur = res[i];
+		if (cur >= 128) {
+			const int e = (cur - 128) >> 4, scan = cur & 15;
+			if (prev != 127) {
+				int j = (last() & 255) + (e << 1);
+				if (j >= 254) { count++; cur = 127; }
+				else out[stage++] = (uint16_t)(j + (count << 8));
+				j += scan << 1;
+				if (j >= 254) { count++; cur = 127; }
+				else out[stage++] = (uint16_t)(j + (count << 8));
+			} else { cur = 127; count += 2; }
+		} else if (cur == 127) count++;
+		else {
+			if ((cur << 1) < (last() & 255) && prev != 127) count++;
+			out[stage++] = (uint16_t)((cur << 1) + (count << 8));
+		}
+		prev = cur;
+	}
+	for (int i = 0; i < cap; i++) out[i] = (uint16_t)(out[i] + ((bits[i >> 3] >> (7 - (i & 7))) & 1));
+	return stage;
+}

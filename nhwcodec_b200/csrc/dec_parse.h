@@ -1,0 +1,50 @@
+// dec_parse.h -- host-side header walk of one .nhw stream (decoder/nhw_decoder.c:1494-1661,
+// SURVEY.md Appendix A): fills the per-image descriptor the decode kernels work from.
+// Plain C++ (no CUDA), shared by api.cu and the host test harness.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "dec_core.cuh"
+
+static inline int nhw_parse_header(const uint8_t *p, size_t len, DecDesc *d)
+{
+	memset(d, 0, sizeof *d);
+	if (len < 36) return -7;
+	size_t pos = 0;
+	auto u8 = [&]() -> int { return p[pos++]; };
+	auto u16 = [&]() -> int { int v = p[pos] | (p[pos + 1] << 8); pos += 2; return v; };
+	auto u32 = [&]() -> int { uint32_t v = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24); pos += 4; return (int)v; };
+	d->byte0 = u8();
+	const int q = d->quality = u8();
+	if (d->byte0 > 6) return -7;                       // "Not an .nhw file"
+	d->size_tree1 = u16(); d->size_tree2 = u16();
+	d->size_data1 = u32(); d->size_data2 = u32();
+	d->tree_end = u16(); d->exw_Y_end = u16();
+	if (q > 12) d->res1_len = u16();
+	if (q >= 19) { d->res3_len = u16(); d->res3_bit_len = u16(); }
+	if (q > 17) d->res4_len = u16();
+	if (q > 12) d->res1_bit_len = u16();
+	if (q >= 21) { d->res5_len = u16(); d->res5_bit_len = u16(); }
+	if (q > 21) return -3;                             // res6 / char_res1 side channels: not built
+	d->select1 = u16(); d->select2 = u16();
+	if (q > 15) d->highres_comp_len = u16();
+	d->end_ch_res = u16();
+	auto take = [&](uint32_t &off, size_t n) { off = (uint32_t)pos; pos += n; };
+	take(d->off_tree1, d->size_tree1);
+	take(d->off_tree2, d->size_tree2);
+	take(d->off_exw, d->exw_Y_end);
+	if (q > 12) { take(d->off_res1, d->res1_len); take(d->off_res1_bit, d->res1_bit_len); take(d->off_res1_word, d->res1_bit_len); }
+	if (q > 17) take(d->off_res4, d->res4_len);
+	if (q >= 19) { take(d->off_res3, d->res3_len); take(d->off_res3_bit, d->res3_bit_len); take(d->off_res3_word, 2 * (size_t)d->res3_bit_len); }
+	if (q >= 21) { take(d->off_res5, d->res5_len); take(d->off_res5_bit, d->res5_bit_len); take(d->off_res5_word, d->res5_bit_len); }
+	take(d->off_sel1, d->select1);
+	take(d->off_sel2, d->select2);
+	if (q > 15) { take(d->off_u64, 512); take(d->off_v64, 512); take(d->off_highres, d->highres_comp_len); }
+	take(d->off_ch_res, d->end_ch_res);
+	take(d->off_words, 4 * (size_t)d->size_data2);
+	d->blob_len = (uint32_t)len;
+	if (pos > len || d->size_data1 <= 0 || d->size_data2 < d->size_data1) return -7;
+	if (q < 17) return -3;
+	return 0;
+}

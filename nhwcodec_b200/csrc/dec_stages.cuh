@@ -1,0 +1,340 @@
+// dec_stages.cuh -- inline stages of decode_image (decoder/nhw_decoder.c:71-1474) and the colour
+// conversion of write_image_bmp (decoder/nhw_decoder_cli.c:108-291), q17..q21.
+// *_row / *_strip functions are independent per row/strip; *_image functions are raster-ordered.
+#pragma once
+#include "dec_core.cuh"
+
+// ---- D2: inverse serpentine scan (nhw_decoder.c:71-91): coefficient stream -> transposed plane
+NHW_HD void dec_y_descan_strip(const int16_t *coef, int16_t *J, int strip /* 0..127 */)
+{
+	const int16_t *s = coef + strip * 2048;
+	int16_t *P = J + strip * 4;
+	for (int k = 0; k < 256; k++) {
+		int16_t *r0 = P + (2 * k) * YW, *r1 = r0 + YW;
+		r0[0] = s[0]; r0[1] = s[1]; r0[2] = s[2]; r0[3] = s[3];
+		r1[3] = s[4]; r1[2] = s[5]; r1[1] = s[6]; r1[0] = s[7];
+		s += 8;
+	}
+}
+
+// ---- D3: expand + split the side-channel lists (nhw_decoder.c:93-491).  list_len[8] receives
+// the value the reference's `count` variable is left with (it is read, stale, by D4).
+NHW_HDN void dec_lists_image(const DecImg &im, uint16_t *tmp /* 65536 */)
+{
+	const DecDesc *d = im.d;
+	const int q = d->quality;
+	int stale = 0;
+	for (int k = 0; k < 8; k++) im.list_len[k] = 0;
+	for (int pass = 0; pass < 2; pass++) {   // res1 (q>12), then res5 (q>=21): one word bit per entry
+		if (pass == 0 ? !(q > 12) : !(q >= 21)) continue;
+		const uint8_t *res = im.blob + (pass ? d->off_res5 : d->off_res1);
+		const uint8_t *bits = im.blob + (pass ? d->off_res5_bit : d->off_res1_bit);
+		const uint8_t *word = im.blob + (pass ? d->off_res5_word : d->off_res1_word);
+		const int len = pass ? d->res5_len : d->res1_len, bit_len = pass ? d->res5_bit_len : d->res1_bit_len;
+		dec_expand_list(res, len, bits, bit_len, tmp);
+		uint16_t *minus = im.list[2 * pass], *plus = im.list[2 * pass + 1];
+		int nm = 0, np = 0, c = 0;
+		for (int i = 0; i < bit_len - 1; i++)
+			for (int b = 7; b >= 0; b--) {
+				if ((word[i] >> b) & 1) minus[nm++] = tmp[c++];
+				else plus[np++] = tmp[c++];
+			}
+		im.list_len[2 * pass] = nm;
+		im.list_len[2 * pass + 1] = np;
+		stale = c;
+	}
+	if (q >= 19) {   // res3: two word bits per entry, four classes
+		dec_expand_list(im.blob + d->off_res3, d->res3_len, im.blob + d->off_res3_bit, d->res3_bit_len, tmp);
+		const uint8_t *word = im.blob + d->off_res3_word;
+		int n[4] = {0, 0, 0, 0}, c = 0;
+		for (int i = 0; i < (d->res3_bit_len << 1) - 2; i++)
+			for (int b = 6; b >= 0; b -= 2) {
+				const int sel = (word[i] >> b) & 3;   // 0 -> nhwres4 (+4,+3), 1 -> nhwres3 (-4,-3), 2 -> +2 x3, 3 -> -2 x3
+				im.list[4 + sel][n[sel]++] = tmp[c++];
+			}
+		for (int k = 0; k < 4; k++) im.list_len[4 + k] = n[k];
+		stale = c;
+	}
+	im.list_len[8] = stale;
+}
+
+// ---- D4: marker expansion, in place and in raster order (nhw_decoder.c:493-607)
+NHW_HDN void dec_y_markers_image(const DecImg &im)
+{
+	int16_t *J = im.jpeg;
+	const int q = im.d->quality;
+	for (int r = 0; r < 256; r++)
+		for (int j = 0; j < 512; j++) {
+			const int s = r * YW + j, v = J[s];
+			if (v <= 1000) continue;
+			if (v == 1008) { J[s - 1] = 5; J[s + 1] = 5; J[s] = (int16_t)(j < 256 ? 5 : 6); }
+			else if (v == 1009) { J[s - 1] = -5; J[s + 1] = -5; J[s] = (int16_t)(j < 256 ? -6 : -7); }
+			else if (v == 1010) { J[s] = 5; J[s + 1] = 5; J[s + YW] = 5; J[s + YW + 1] = 5; }
+			else if (v == 1011) { J[s] = -5; J[s + 1] = -5; J[s + YW] = -5; J[s + YW + 1] = -5; }
+			else if (v == 1006) { J[s] = -6; J[s + 1] = -6; }
+			else if (v == 1007) { J[s] = 6; J[s + 1] = 6; }
+		}
+	int count = im.list_len[8];
+	for (int half = 0; half < 2; half++)
+		for (int r = 256; r < 512; r++)
+			for (int j = half ? 256 : 0; j < (half ? 512 : 256); j++) {
+				const int s = r * YW + j, v = J[s];
+				if (v > 1000) {
+					if (v == 1008) { J[s - 1] = 5; J[s] = 6; J[s + 1] = 5; }
+					else if (v == 1009) { J[s - 1] = -5; J[s] = -7; J[s + 1] = -5; }
+					else if (v == 1006 || v == 1007) {
+						const int16_t w = (int16_t)(v == 1006 ? -7 : 7);
+						if ((s & 511) < 256) { J[s] = w; J[s + 1] = w; }
+						else { J[s - 256] = w; J[s - 768] = w; J[s] = 0; }
+					}
+				} else if (half && nhw_iabs(v) > 8 && nhw_iabs(v) < 16 && q < 23) {
+					if (j > 256 && j < 511) {
+						if (nhw_iabs(J[s - 1]) < 8) count++;
+						if (nhw_iabs(J[s + 1]) < 8) count++;
+						if (nhw_iabs(J[s - YW]) < 8) count++;
+						if (nhw_iabs(J[s + YW]) < 8) count++;
+						if (count >= 2) J[s] += v > 0 ? 1 : -1;
+						count = 0;
+					}
+				}
+			}
+}
+
+// ---- D5-D7: LL2 fill, res4 parity restore, exw overrides (nhw_decoder.c:609-658)
+NHW_HDN int dec_y_ll_image(const DecImg &im)
+{
+	int16_t *J = im.jpeg;
+	const DecDesc *d = im.d;
+	for (int r = 0; r < 128; r++)
+		for (int j = 0; j < 128; j++) J[r * YW + j] = im.res_comp[r * 128 + j];
+	if (d->quality > 17) {
+		const uint8_t *r4 = im.blob + d->off_res4;
+		int count = 0;
+		for (int i = 0; i < d->res4_len; i++) {
+			if (r4[i] == 128) { count++; continue; }
+			const int e = (count << 9) + (r4[i] > 128 ? r4[i] - 129 : r4[i] - 1);
+			for (int k = 0; k < 4; k++)
+				if (!(J[e + k] & 1)) J[e + k]++;
+			if (r4[i] > 128) count++;
+		}
+	}
+	const uint8_t *x = im.blob + d->off_exw;
+	int i = 0;
+	for (; i < d->exw_Y_end; i += 3) {
+		if (!x[i] && !x[i + 1]) break;
+		int col = x[i + 1], val;
+		if (col >= 128) { val = x[i + 2] + 255; col -= 128; }
+		else val = -x[i + 2];
+		J[(x[i] << 9) + col] = (int16_t)val;
+	}
+	return i;   // exw1: where the chroma entries start (after the 0,0 separator)
+}
+
+// ---- D8: shrink isolated coefficients of the level-2 bands, in place (nhw_decoder.c:685-711)
+NHW_HDN void dec_y_shrink_image(const DecImg &im)
+{
+	int16_t *J = im.jpeg;
+	for (int r = 1; r < 255; r++)
+		for (int j = 1; j < 255; j++) {
+			const int s = r * YW + j;
+			if (nhw_iabs(J[s]) <= 8) continue;
+			if (nhw_iabs(J[s - YW - 1]) > 8 || nhw_iabs(J[s - YW]) > 8 || nhw_iabs(J[s - YW + 1]) > 8 ||
+			    nhw_iabs(J[s - 1]) > 8 || nhw_iabs(J[s + 1]) > 8 || nhw_iabs(J[s + YW - 1]) > 8 ||
+			    nhw_iabs(J[s + YW]) > 8 || nhw_iabs(J[s + YW + 1]) > 8)
+				continue;
+			if (r >= 128 || j >= 128) J[s] += J[s] > 0 ? -1 : 1;
+		}
+}
+
+// ---- D10: residual add-backs on the reconstructed LL1 (nhw_decoder.c:721-787)
+NHW_HDN void dec_y_addbacks_image(const DecImg &im)
+{
+	int16_t *P = im.proc;
+	const int q = im.d->quality;
+	auto at = [](uint16_t v) { return ((v & 65280) << 1) + (v & 255); };
+	if (q >= 21) {
+		for (int i = 0; i < im.list_len[2]; i++) P[at(im.list[2][i])] -= 3;
+		for (int i = 0; i < im.list_len[3]; i++) P[at(im.list[3][i])] += 3;
+	}
+	if (q > 12) {
+		const int e = q >= 18 ? 5 : q >= 15 ? 7 : 9;
+		for (int i = 0; i < im.list_len[0]; i++) P[at(im.list[0][i])] -= e;
+		for (int i = 0; i < im.list_len[1]; i++) P[at(im.list[1][i])] += e;
+	}
+	if (q >= 19) {
+		for (int i = 0; i < im.list_len[5]; i++) { const int a = at(im.list[5][i]); P[a] -= 4; P[a + YW] -= 3; }
+		for (int i = 0; i < im.list_len[4]; i++) { const int a = at(im.list[4][i]); P[a] += 4; P[a + YW] += 3; }
+		for (int i = 0; i < im.list_len[6]; i++) { const int a = at(im.list[6][i]); P[a] += 2; P[a + YW] += 2; P[a + 2 * YW] += 2; }
+		for (int i = 0; i < im.list_len[7]; i++) { const int a = at(im.list[7][i]); P[a] -= 2; P[a + YW] -= 2; P[a + 2 * YW] -= 2; }
+	}
+}
+
+NHW_HD int dec_lap8(const int16_t *P, int s, int stride)
+{
+	return (P[s] << 3) - P[s - 1] - P[s + 1] - P[s - stride] - P[s + stride] - P[s - stride - 1] - P[s + stride - 1] -
+	       P[s - stride + 1] - P[s + stride + 1];
+}
+
+// ---- D11+D12: edge flags on LL1 (flagged cells carry +16000 while the pass runs, so later
+// stencils see them), then the flag list in raster order (nhw_decoder.c:789-839)
+NHW_HDN void dec_y_edge_flags_image(const DecImg &im)
+{
+	int16_t *P = im.proc;
+	for (int r = 1; r < 255; r++)
+		for (int j = 1; j < 254; j++) {
+			int s = r * YW + j;
+			const int res = dec_lap8(P, s, YW);
+			j++; s++;
+			const int cnt = dec_lap8(P, s, YW);
+			if (res > 41 && res < 108 && cnt < 16) P[s - 1] += 16000;
+			else if (res < -41 && res > -108 && cnt > -16) P[s - 1] += 16000;
+			else if (cnt > 41 && cnt < 108 && res < 16) P[s] += 16000;
+			else if (cnt < -41 && cnt > -108 && res > -16) P[s] += 16000;
+		}
+	int n = 0;
+	for (int r = 1; r < 255; r++)
+		for (int j = 0; j < 256; j++) {
+			const int s = r * YW + j;
+			if (P[s] > 10000) { im.flags[n++] = (uint16_t)((r << 8) + j); P[s] -= 16000; }
+		}
+	im.list_len[9] = n;
+}
+
+// ---- D14: conditional 5-tap smoothing at the flagged positions, list order (nhw_decoder.c:848-867)
+NHW_HDN void dec_y_smooth_flags_image(const DecImg &im)
+{
+	int16_t *J = im.jpeg;
+	for (int i = 0; i < im.list_len[9]; i++) {
+		const int s = ((im.flags[i] >> 8) << 10) + (im.flags[i] & 255);
+		const int res = dec_lap8(J, s, YW);
+		if (nhw_iabs(res) < 116) J[s] = (int16_t)(((J[s] << 2) + J[s - 1] + J[s + 1] + J[s - YW] + J[s + YW] + 4) >> 3);
+	}
+}
+
+NHW_HD uint8_t dec_clip8(int v) { return (uint8_t)((v >> 8) != 0 ? (v < 0 ? 0 : 255) : v); }
+
+// ---- chroma (nhw_decoder.c:895-1183 / 1185-1474), one component
+NHW_HD void dec_c_descan_strip(const int16_t *coef, int16_t *J, int strip /* 0..31 */, int is_v)
+{
+	const int16_t *s = coef + is_v + strip * 4096;
+	int16_t *P = J + strip * 8;
+	for (int k = 0; k < 128; k++) {
+		int16_t *r0 = P + (2 * k) * CW, *r1 = r0 + CW;
+		for (int t = 0; t < 8; t++) r0[t] = s[2 * t];
+		for (int t = 0; t < 8; t++) r1[7 - t] = s[16 + 2 * t];
+		s += 32;
+	}
+}
+
+// LL fill + exw overrides; exw_pos = index into the exw list (advanced past this component)
+NHW_HDN int dec_c_ll_image(const DecImg &im, int is_v, int exw_pos)
+{
+	int16_t *J = im.cjpeg;
+	const DecDesc *d = im.d;
+	const uint8_t *src = im.res_comp + (is_v ? 20480 : 16384);
+	const int bias = d->quality > 15 ? 0 : 1;
+	for (int r = 0; r < 64; r++)
+		for (int j = 0; j < 64; j++) J[r * CW + j] = (int16_t)(src[r * 64 + j] + bias);
+	const uint8_t *x = im.blob + d->off_exw;
+	int i = exw_pos + 2;
+	for (; i < d->exw_Y_end; i += 3) {
+		if (!x[i] && !x[i + 1]) break;
+		int col = x[i + 1], val;
+		if (col >= 128) { val = x[i + 2] + 255; col -= 128; }
+		else val = -x[i + 2];
+		J[(x[i] << 8) + col] = (int16_t)val;
+	}
+	return i;
+}
+
+// markers 5003..5006 in the level-1 bands push +-6 / +-4,+-4 into the reconstructed LL
+// (nhw_decoder.c:991-1069).  P = reconstruction (128x128 region of cproc), J = band plane.
+NHW_HDN void dec_c_markers_image(const DecImg &im)
+{
+	int16_t *P = im.cproc, *J = im.cjpeg;
+	for (int r = 0; r < 256; r++)
+		for (int j = (r < 128 ? 128 : 0); j < 256; j++) {
+			const int s = r * CW + j, v = J[s];
+			if (v <= 5000) continue;
+			int t = s;
+			if (r < 128) t -= 128;
+			else t -= 32768 + (j < 128 ? 0 : 128);
+			if (v == 5005) { P[t] -= 4; P[t + 1] -= 4; J[s] = 0; }
+			else if (v == 5006) { P[t] += 4; P[t + 1] += 4; J[s] = 0; }
+			else if (v == 5003) { P[t] -= 6; J[s] = 0; }
+			else if (v == 5004) { P[t] += 6; J[s] = 0; }
+		}
+}
+
+// in-place 8-neighbour sharpen, raster order (nhw_decoder.c:1085-1109), then clip to 0..255
+NHW_HDN void dec_c_sharpen_image(const DecImg &im)
+{
+	int16_t *P = im.cproc;
+	const int thr = im.d->quality <= 14 ? 35 : 60;
+	for (int r = 1; r < 255; r++)
+		for (int j = 1; j < 255; j++) {
+			const int s = r * CW + j;
+			const int res = dec_lap8(P, s, CW);
+			if (nhw_iabs(res) > thr) {
+				if (res > 0) P[s] += res > 160 ? 3 : 2;
+				else P[s] -= res < -160 ? 3 : 2;
+			}
+		}
+	for (int i = 0; i < 65536; i++)
+		if ((P[i] >> 8) != 0) P[i] = (int16_t)(P[i] < 0 ? 0 : 255);
+}
+
+// 2x upsample of the clipped 256x256 plane to 512x512 bytes: rows first, then columns, both
+// (a+b+1)>>1 with the last row/column repeated (nhw_decoder.c:1137-1181)
+NHW_HD void dec_c_upsample_row(const int16_t *P, uint8_t *out, int y /* 0..511 */)
+{
+	const int r = y >> 1;
+	auto v = [&](int c) -> int {
+		if ((y & 1) == 0 || r == 255) return P[r * CW + c];
+		return (P[r * CW + c] + P[(r + 1) * CW + c] + 1) >> 1;
+	};
+	uint8_t *o = out + y * 512;
+	for (int c = 0; c < 255; c++) {
+		const int a = (uint8_t)v(c), b = (uint8_t)v(c + 1);
+		o[2 * c] = (uint8_t)a;
+		o[2 * c + 1] = (uint8_t)((a + b + 1) >> 1);
+	}
+	o[510] = o[511] = (uint8_t)v(255);
+}
+
+// ---- D17: YCbCr -> RGB (nhw_decoder_cli.c:139-229), IEEE-exact like the encoder's colour stage.
+// mode 0: q>=20   1: q18,19 (Y scaled in float first)   2: q17
+struct DecColor { int mode; float y_inv; };
+
+#ifdef __CUDA_ARCH__
+#define NHW_DMUL(a, b) __dmul_rn((a), (b))
+#define NHW_DADD(a, b) __dadd_rn((a), (b))
+#define NHW_DSUB(a, b) __dsub_rn((a), (b))
+#define NHW_FMUL(a, b) __fmul_rn((a), (b))
+#define NHW_D2I(a) __double2int_rz(a)
+#else
+#define NHW_DMUL(a, b) ((a) * (b))
+#define NHW_DADD(a, b) ((a) + (b))
+#define NHW_DSUB(a, b) ((a) - (b))
+#define NHW_FMUL(a, b) ((a) * (b))
+#define NHW_D2I(a) ((int)(a))
+#endif
+
+NHW_HD void dec_ycc_to_rgb(int y8, int u8, int v8, const DecColor &c, uint8_t *rgb)
+{
+	const double U = (double)(u8 - 128), V = (double)(v8 - 128);
+	double Y = (double)y8;
+	if (c.mode == 1) Y = (double)NHW_FMUL((float)y8, c.y_inv);
+	double r = NHW_DADD(Y, NHW_DMUL(1.402, V));
+	double g = NHW_DSUB(NHW_DSUB(Y, NHW_DMUL(0.34414, U)), NHW_DMUL(0.71414, V));
+	double b = NHW_DADD(Y, NHW_DMUL(1.772, U));
+	if (c.mode == 2) {
+		const double k = (double)c.y_inv;
+		r = NHW_DMUL(r, k);
+		g = NHW_DMUL(g, k);
+		b = NHW_DMUL(b, k);
+	}
+	rgb[0] = dec_clip8(NHW_D2I(NHW_DADD(r, 0.5)));
+	rgb[1] = dec_clip8(NHW_D2I(NHW_DADD(g, 0.5)));
+	rgb[2] = dec_clip8(NHW_D2I(NHW_DADD(b, 0.5)));
+}

@@ -12,7 +12,8 @@
 #include <string.h>
 #include <vector>
 
-#include "../../nhwcodec_b200/csrc/enc_seg.cuh"
+#include "../../nhwcodec_b200/csrc/dec_stages.cuh"
+#include "../../nhwcodec_b200/csrc/dec_parse.h"
 
 namespace {
 
@@ -242,7 +243,91 @@ void host_e16(const EncImg &im, int q)
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// decoder pipeline on the host (same stage functions as the CUDA path)
+static void inv_rows(const int16_t *in, int in_stride, int16_t *out, int out_stride, int rows, int M, bool norm)
+{
+	for (int k = 0; k < rows; k++) {
+		auto l = [&](int t) { return (int)in[k * in_stride + t]; };
+		auto h = [&](int t) { return (int)in[k * in_stride + M + t]; };
+		for (int t = 0; t < M; t++) {
+			int ev, od;
+			inverse_pair(l, h, t, M, norm, ev, od);
+			out[k * out_stride + 2 * t] = (int16_t)ev;
+			out[k * out_stride + 2 * t + 1] = (int16_t)od;
+		}
+	}
+}
+
+static void transpose_sq(const int16_t *in, int16_t *out, int stride, int N)
+{
+	for (int i = 0; i < N; i++)
+		for (int j = 0; j < N; j++) out[i * stride + j] = in[j * stride + i];
+}
+
+static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *yuv_out)
+{
+	DecDesc d;
+	int rc = nhw_parse_header(blob, len, &d);
+	if (rc) return rc;
+	std::vector<int16_t> proc(262144 + 8192, 0), jpeg(262144 + 8192, 0), aux(262144 + 8192, 0), uv(131072 + 64, 0);
+	std::vector<int16_t> cproc(65536 + 8192, 0), cjpeg(65536 + 8192, 0), caux(65536 + 8192, 0), tmp;
+	std::vector<uint8_t> res_comp(24577 + 64, 0), yuv(3 * 262144), btmp(2048);
+	std::vector<uint16_t> lists(8 * 65536), flags(65536), book(1024, 0), ltmp(65536 + 64);
+	int32_t list_len[16] = {0};
+	DecImg im;
+	im.blob = blob; im.d = &d;
+	im.proc = proc.data() + 4096; im.jpeg = jpeg.data() + 4096; im.aux = aux.data() + 4096;
+	im.uvcoef = uv.data();
+	im.cproc = cproc.data() + 4096; im.cjpeg = cjpeg.data() + 4096; im.caux = caux.data() + 4096;
+	im.res_comp = res_comp.data();
+	for (int k = 0; k < 8; k++) im.list[k] = lists.data() + k * 65536;
+	im.list_len = list_len; im.flags = flags.data(); im.book = book.data(); im.yuv = yuv.data();
+
+	dec_ll_dpcm(im);
+	dec_build_book(blob + d.off_tree1, d.size_tree1, 3, -1, im.book, btmp.data());
+	rc = dec_prefix_luma(im, im.proc);
+	if (rc) return rc;
+	for (int s = 127; s >= 0; s--) dec_y_descan_strip(im.proc, im.jpeg, s);
+	dec_lists_image(im, ltmp.data());
+	dec_y_markers_image(im);
+	int exw = dec_y_ll_image(im);
+	dec_y_shrink_image(im);
+	inv_level(im.jpeg, im.proc, 512, 256, tmp);                 // LL1 reconstruction, natural orientation
+	dec_y_addbacks_image(im);
+	dec_y_edge_flags_image(im);
+	transpose_sq(im.proc, im.jpeg, 512, 256);
+	inv_rows(im.jpeg, 512, im.proc, 512, 512, 256, false);      // wavelet_synthesis2: first half
+	transpose_sq(im.proc, im.jpeg, 512, 512);
+	dec_y_smooth_flags_image(im);
+	inv_rows(im.jpeg, 512, im.proc, 512, 512, 256, true);       // wavelet_synthesis(...,3): second half
+	for (int i = 0; i < 262144; i++) im.yuv[i] = dec_clip8(im.proc[i]);
+
+	std::fill(book.begin(), book.end(), 0);
+	dec_build_book(blob + d.off_tree2, d.size_tree2, 128, d.tree_end, im.book, btmp.data());
+	rc = dec_prefix_chroma(im, im.uvcoef);
+	if (rc) return rc;
+	for (int v = 0; v < 2; v++) {
+		for (int s = 31; s >= 0; s--) dec_c_descan_strip(im.uvcoef, im.cjpeg, s, v);
+		exw = dec_c_ll_image(im, v, exw);
+		inv_level(im.cjpeg, im.cproc, 256, 128, tmp);
+		dec_c_markers_image(im);
+		transpose_sq(im.cproc, im.cjpeg, 256, 128);
+		inv_level(im.cjpeg, im.cproc, 256, 256, tmp);
+		dec_c_sharpen_image(im);
+		for (int y = 511; y >= 0; y--) dec_c_upsample_row(im.cproc, im.yuv + (1 + v) * 262144, y);
+	}
+	DecColor col;
+	col.mode = d.quality >= 20 ? 0 : d.quality >= 18 ? 1 : 2;
+	col.y_inv = d.quality == 19 ? 1.025641f : d.quality == 18 ? 1.075269f : 1.063830f;
+	for (int i = 0; i < 262144; i++) dec_ycc_to_rgb(im.yuv[i], im.yuv[262144 + i], im.yuv[524288 + i], col, rgb + 3 * i);
+	if (yuv_out) memcpy(yuv_out, im.yuv, 3 * 262144);
+	return 0;
+}
+
 extern "C" {
+
+int he_decode(const uint8_t *blob, long len, uint8_t *rgb, uint8_t *yuv_out) { return host_decode(blob, (size_t)len, rgb, yuv_out); }
 
 void *he_new() { return make_work(); }
 void he_free(void *h) { delete static_cast<Work *>(h); }
