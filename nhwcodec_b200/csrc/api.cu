@@ -12,6 +12,7 @@
 #include "../../include/nhw_cuda.h"
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
+#include "dec_parse.h"
 
 namespace nhw {
 
@@ -143,6 +144,9 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	ok = ok && dev_alloc0(&c->enc_bytes, B * (size_t)ENC_BYTES_SLOT) && dev_alloc0(&c->enc_hdr, B);
 	ok = ok && dev_alloc0(&c->out_dev, B * (size_t)NHW_MAX_STREAM_BYTES) && dev_alloc0(&c->pack_dev, B * (size_t)NHW_MAX_STREAM_BYTES);
 	ok = ok && dev_alloc0(&c->len_dev, B) && dev_alloc0(&c->status_dev, B) && dev_alloc0(&c->offs_dev, B + 1);
+	ok = ok && dev_alloc0(&c->dec_yuv, B * (size_t)NHW_RGB_BYTES);
+	ok = ok && check(cudaMalloc(&c->dec_desc_dev, B * sizeof(DecDesc)), "cudaMalloc");
+	ok = ok && check(cudaMallocHost(&c->dec_desc_host, B * sizeof(DecDesc)), "cudaMallocHost");
 	ok = ok && check(cudaMallocHost((void **)&c->offs_host, (B + 1) * sizeof(uint64_t)), "cudaMallocHost");
 	ok = ok && check(cudaMallocHost((void **)&c->status_host, B * sizeof(int32_t)), "cudaMallocHost");
 	if (!ok || !check(cudaDeviceSynchronize(), "nhw_create sync")) { nhw_destroy(c); return NHW_ERR_CUDA; }
@@ -159,6 +163,9 @@ void nhw_destroy(nhw_ctx *c)
 	                c->out_dev, c->pack_dev, c->len_dev, c->status_dev, c->offs_dev};
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
+	if (c->dec_yuv) cudaFree(c->dec_yuv);
+	if (c->dec_desc_dev) cudaFree(c->dec_desc_dev);
+	if (c->dec_desc_host) cudaFreeHost(c->dec_desc_host);
 	if (c->offs_host) cudaFreeHost(c->offs_host);
 	if (c->status_host) cudaFreeHost(c->status_host);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -347,9 +354,34 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 
 int nhw_decode_batch(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int n, uint8_t *rgb, int32_t *status)
 {
-	(void)c; (void)in; (void)offsets; (void)n; (void)rgb; (void)status;
-	nhw::set_error("nhw_decode_batch: decode path not built yet");
-	return NHW_ERR_QUALITY;
+	if (!c || !in || !offsets || !rgb || n <= 0) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	c->dbg_seen = c->dbg_stopped = 0;
+	DecDesc *desc = static_cast<DecDesc *>(c->dec_desc_host);
+	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
+		const int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
+		const uint64_t base = offsets[i0], total = offsets[i0 + m] - base;
+		if (total + 64 > (uint64_t)c->max_batch * NHW_MAX_STREAM_BYTES) { nhw::set_error("input chunk too large"); return NHW_ERR_ARG; }
+		for (int i = 0; i < m; i++) {
+			const uint64_t o = offsets[i0 + i] - base, len = offsets[i0 + i + 1] - offsets[i0 + i];
+			c->offs_host[i] = o;
+			c->status_host[i] = nhw_parse_header(in + base + o, (size_t)len, &desc[i]);
+		}
+		bool ok = check(cudaMemcpyAsync(c->pack_dev, in + base, total, cudaMemcpyHostToDevice, c->stream), "H2D streams");
+		// the bit reader may look a few words past the last code: keep that tail defined
+		ok = ok && check(cudaMemsetAsync(c->pack_dev + total, 0, 64, c->stream), "memset tail");
+		ok = ok && check(cudaMemcpyAsync(c->dec_desc_dev, desc, (size_t)m * sizeof(DecDesc), cudaMemcpyHostToDevice, c->stream), "H2D desc");
+		ok = ok && check(cudaMemcpyAsync(c->offs_dev, c->offs_host, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream), "H2D offs");
+		ok = ok && check(cudaMemcpyAsync(c->status_dev, c->status_host, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream), "H2D status");
+		if (!ok) return NHW_ERR_CUDA;
+		nhw::decode_chunk(c, c->pack_dev, c->offs_dev, static_cast<const DecDesc *>(c->dec_desc_dev), c->status_dev, m, c->rgb);
+		cudaMemcpyAsync(rgb + (size_t)i0 * NHW_RGB_BYTES, c->rgb, (size_t)m * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, c->stream);
+		cudaMemcpyAsync(c->status_host, c->status_dev, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+		int rc = finish(c, "nhw_decode_batch");
+		if (rc) return rc;
+		for (int i = 0; status && i < m; i++) status[i0 + i] = c->status_host[i];
+	}
+	return NHW_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,234 @@
+// decode.cu -- batch decoder driver: .nhw streams (device-resident, described by DecDesc) ->
+// 786432 BMP pixel bytes per image.  Replaces decode_image + write_image_bmp's pixel path
+// (decoder/nhw_decoder.c:54-1476, decoder/nhw_decoder_cli.c:108-291) for a whole batch.
+//
+// First complete version: the bit-serial prefix decode and the raster-order inline stages run
+// one thread per image (they are the decoder's serial spine); the
+// transforms, transposes, chroma upsampling and the colour conversion are data-parallel.
+#include <stdlib.h>
+
+#include "nhw_ctx.h"
+#include "nhw_dev.cuh"
+#include "dec_stages.cuh"
+#include "../../include/nhw_cuda.h"
+
+namespace {
+
+// decode-time carve-up of the per-image byte slot (the encoder's layout is not live during decode)
+enum : int {
+	DOFF_RESCOMP = 4096,
+	DOFF_BOOK = DOFF_RESCOMP + 24640,
+	DOFF_BTMP = DOFF_BOOK + 2048,
+	DOFF_LISTLEN = DOFF_BTMP + 2048,
+	DOFF_FLAGS = DOFF_LISTLEN + 256,
+	DOFF_LTMP = DOFF_FLAGS + 131072,
+	DOFF_LISTS = DOFF_LTMP + 131072 + 256,        // 8 lists x 65536 entries
+	DOFF_END = DOFF_LISTS + 8 * 131072,
+};
+static_assert(DOFF_END <= ENC_BYTES_SLOT, "decode scratch must fit the per-image byte slot");
+
+struct DecBatch {
+	const uint8_t *blobs;         // dense concatenation of the chunk's streams
+	const uint64_t *blob_off;     // per image
+	const DecDesc *desc;
+	int16_t *y_proc, *y_jpeg, *y_aux, *uvcoef;
+	int16_t *c_proc, *c_jpeg, *c_aux;
+	uint8_t *bytes;
+	uint8_t *yuv;                 // n x 3 x 262144
+	int32_t *status;
+};
+
+__device__ __forceinline__ DecImg make_dec(const DecBatch &b, int i, int comp)
+{
+	DecImg im;
+	im.blob = b.blobs + b.blob_off[i];
+	im.d = b.desc + i;
+	im.proc = b.y_proc + (size_t)i * NHW_Y_SLOT;
+	im.jpeg = b.y_jpeg + (size_t)i * NHW_Y_SLOT;
+	im.aux = b.y_aux + (size_t)i * NHW_Y_SLOT;
+	im.uvcoef = b.uvcoef + (size_t)i * NHW_Y_SLOT;
+	const size_t p = (size_t)i * 2 + comp;
+	im.cproc = b.c_proc + p * NHW_C_SLOT;
+	im.cjpeg = b.c_jpeg + p * NHW_C_SLOT;
+	im.caux = b.c_aux + p * NHW_C_SLOT;
+	uint8_t *bytes = b.bytes + (size_t)i * ENC_BYTES_SLOT;
+	im.res_comp = bytes + DOFF_RESCOMP;
+	im.book = reinterpret_cast<uint16_t *>(bytes + DOFF_BOOK);
+	im.list_len = reinterpret_cast<int32_t *>(bytes + DOFF_LISTLEN);
+	im.flags = reinterpret_cast<uint16_t *>(bytes + DOFF_FLAGS);
+	for (int k = 0; k < 8; k++) im.list[k] = reinterpret_cast<uint16_t *>(bytes + DOFF_LISTS) + (size_t)k * 65536;
+	im.yuv = b.yuv + (size_t)i * 786432;
+	return im;
+}
+
+template <typename F>
+__global__ void kd_image(DecBatch b, int n, F f)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && b.status[i] == 0) f(make_dec(b, i, 0), i);
+}
+template <typename F>
+__global__ void kd_plane(DecBatch b, int n2, F f)
+{
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n2 && b.status[p >> 1] == 0) f(make_dec(b, p >> 1, p & 1), p & 1);
+}
+template <typename F>
+__global__ void kd_rows(DecBatch b, int rows, F f)   // grid (ceil(rows/64), n)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < rows && b.status[blockIdx.y] == 0) f(make_dec(b, blockIdx.y, 0), r);
+}
+template <typename F>
+__global__ void kd_plane_rows(DecBatch b, int rows, F f)   // grid (ceil(rows/64), 2n)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < rows && b.status[blockIdx.y >> 1] == 0) f(make_dec(b, blockIdx.y >> 1, blockIdx.y & 1), r, blockIdx.y & 1);
+}
+
+template <typename F> void d_image(nhw_ctx *c, const char *l, const DecBatch &b, int n, F f) { NHW_LAUNCH_L(c, l, kd_image, (n + 31) / 32, 32, 0, b, n, f); }
+template <typename F> void d_plane(nhw_ctx *c, const char *l, const DecBatch &b, int n, F f) { NHW_LAUNCH_L(c, l, kd_plane, (2 * n + 31) / 32, 32, 0, b, 2 * n, f); }
+template <typename F> void d_rows(nhw_ctx *c, const char *l, const DecBatch &b, int n, int rows, F f) { NHW_LAUNCH_L(c, l, kd_rows, dim3((rows + 63) / 64, n), 64, 0, b, rows, f); }
+template <typename F> void d_plane_rows(nhw_ctx *c, const char *l, const DecBatch &b, int n, int rows, F f) { NHW_LAUNCH_L(c, l, kd_plane_rows, dim3((rows + 63) / 64, 2 * n), 64, 0, b, rows, f); }
+
+// ---- inverse filter passes (upfilter53I + III / VI, decoder/filters.c:143-194)
+// rows: every row k of the band plane -> 2M outputs, optionally normalised
+template <int M, bool NORM>
+__global__ void __launch_bounds__(256) kd_inv_rows(const int16_t *in, int16_t *out, size_t in_slot, size_t out_slot, int stride)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int k = blockIdx.x * 8 + warp;
+	const int16_t *src = in + (size_t)blockIdx.y * in_slot + k * stride;
+	int16_t *dst = out + (size_t)blockIdx.y * out_slot + k * stride;
+	auto l = [&](int t) { return (int)src[t]; };
+	auto h = [&](int t) { return (int)src[M + t]; };
+	for (int t = lane; t < M; t += 32) {
+		int ev, od;
+		inverse_pair(l, h, t, M, NORM, ev, od);
+		*reinterpret_cast<uint32_t *>(dst + 2 * t) = (uint32_t)(uint16_t)ev | ((uint32_t)(uint16_t)od << 16);
+	}
+}
+
+// square transpose of the top-left N x N cells of a plane into another plane (32x32 tiles)
+__global__ void __launch_bounds__(256) kd_transpose(const int16_t *in, int16_t *out, size_t in_slot, size_t out_slot, int stride)
+{
+	__shared__ int16_t tile[32][33];
+	const int16_t *src = in + (size_t)blockIdx.z * in_slot;
+	int16_t *dst = out + (size_t)blockIdx.z * out_slot;
+	const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	for (int r = ty; r < 32; r += 8) tile[r][tx] = src[(y0 + r) * stride + x0 + tx];
+	__syncthreads();
+	for (int r = ty; r < 32; r += 8) dst[(x0 + r) * stride + y0 + tx] = tile[tx][r];
+}
+
+__global__ void kd_zero(int16_t *p, size_t slot, size_t count16)   // count16 = number of 16-byte units
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count16) reinterpret_cast<uint4 *>(p + (size_t)blockIdx.y * slot)[i] = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void kd_clip_y(DecBatch b)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b.status[blockIdx.y] != 0) return;
+	const int16_t *P = b.y_proc + (size_t)blockIdx.y * NHW_Y_SLOT;
+	b.yuv[(size_t)blockIdx.y * 786432 + i] = dec_clip8(P[i]);
+}
+
+__global__ void kd_color(DecBatch b, uint8_t *rgb)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	uint8_t *o = rgb + (size_t)blockIdx.y * 786432 + 3 * (size_t)i;
+	if (b.status[blockIdx.y] != 0) { o[0] = o[1] = o[2] = 0; return; }
+	const int quality = b.desc[blockIdx.y].quality;   // each stream carries its own quality byte
+	DecColor col;
+	col.mode = quality >= 20 ? 0 : quality >= 18 ? 1 : 2;
+	col.y_inv = quality == 19 ? 1.025641f : quality == 18 ? 1.075269f : 1.063830f;
+	const uint8_t *yuv = b.yuv + (size_t)blockIdx.y * 786432;
+	dec_ycc_to_rgb(yuv[i], yuv[262144 + i], yuv[524288 + i], col, o);
+}
+
+}  // namespace
+
+namespace nhw {
+
+// from encode.cu (same inverse kernels, natural-orientation output)
+void idwt_rows_cols(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *tmp, int16_t *out, size_t slot, int N, int stride);
+
+// Decode n <= max_batch streams.  blobs/offs/desc/status are device arrays for this chunk; rgb_dev
+// receives n x 786432 bytes.  All work is queued on c->stream.
+void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const DecDesc *desc, int32_t *status, int n,
+                  uint8_t *rgb_dev)
+{
+	DecBatch b;
+	b.blobs = blobs; b.blob_off = offs; b.desc = desc; b.status = status;
+	b.y_proc = c->y_proc + NHW_GUARD_S; b.y_jpeg = c->y_jpeg + NHW_GUARD_S; b.y_aux = c->y_aux + NHW_GUARD_S;
+	b.uvcoef = c->y_aux2 + NHW_GUARD_S;
+	b.c_proc = c->c_proc + NHW_GUARD_S; b.c_jpeg = c->c_jpeg + NHW_GUARD_S; b.c_aux = c->c_aux + NHW_GUARD_S;
+	b.bytes = c->enc_bytes; b.yuv = c->dec_yuv;
+	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT;
+
+	// coefficient planes start at zero: zero runs are skipped, not written (decoder/nhw_decoder.c:2029)
+	NHW_LAUNCH(c, kd_zero, dim3(262144 * 2 / 16 / 256, n), 256, 0, b.y_proc, YS, (size_t)(262144 * 2 / 16));
+	NHW_LAUNCH(c, kd_zero, dim3(131072 * 2 / 16 / 256, n), 256, 0, b.uvcoef, YS, (size_t)(131072 * 2 / 16));
+
+	// ---- luma
+	d_image(c, "d_ll_prefix_y", b, n, [=] __device__(const DecImg &im, int i) {
+		dec_ll_dpcm(im);
+		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 2048;
+		dec_build_book(im.blob + im.d->off_tree1, im.d->size_tree1, 3, -1, im.book, btmp);
+		int rc = dec_prefix_luma(im, im.proc);
+		if (rc) b.status[i] = rc;
+	});
+	d_rows(c, "d_descan_y", b, n, 128, [=] __device__(const DecImg &im, int s) { dec_y_descan_strip(im.proc, im.jpeg, s); });
+	d_image(c, "d_lists", b, n, [=] __device__(const DecImg &im, int) {
+		dec_lists_image(im, reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(im.flags) + 131072));
+	});
+	d_image(c, "d_markers_ll_shrink", b, n, [=] __device__(const DecImg &im, int) {
+		dec_y_markers_image(im);
+		im.list_len[10] = dec_y_ll_image(im);
+		dec_y_shrink_image(im);
+	});
+	idwt_rows_cols(c, n, b.y_jpeg, b.y_aux, b.y_proc, YS, 256, 512);
+	d_image(c, "d_addbacks_flags", b, n, [=] __device__(const DecImg &im, int) {
+		dec_y_addbacks_image(im);
+		dec_y_edge_flags_image(im);
+	});
+	NHW_LAUNCH(c, kd_transpose, dim3(8, 8, n), 256, 0, b.y_proc, b.y_jpeg, YS, YS, 512);
+	NHW_LAUNCH_L(c, "d_inv_rows512", (kd_inv_rows<256, false>), dim3(512 / 8, n), 256, 0, b.y_jpeg, b.y_proc, YS, YS, 512);
+	NHW_LAUNCH(c, kd_transpose, dim3(16, 16, n), 256, 0, b.y_proc, b.y_jpeg, YS, YS, 512);
+	d_image(c, "d_smooth_flags", b, n, [=] __device__(const DecImg &im, int) { dec_y_smooth_flags_image(im); });
+	NHW_LAUNCH_L(c, "d_inv_rows512n", (kd_inv_rows<256, true>), dim3(512 / 8, n), 256, 0, b.y_jpeg, b.y_proc, YS, YS, 512);
+	NHW_LAUNCH(c, kd_clip_y, dim3(262144 / 256, n), 256, 0, b);
+
+	// ---- chroma
+	d_image(c, "d_prefix_uv", b, n, [=] __device__(const DecImg &im, int i) {
+		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 2048;
+		for (int k = 0; k < 1024; k++) im.book[k] = 0;
+		dec_build_book(im.blob + im.d->off_tree2, im.d->size_tree2, 128, im.d->tree_end, im.book, btmp);
+		int rc = dec_prefix_chroma(im, im.uvcoef);
+		if (rc) b.status[i] = rc;
+	});
+	d_plane_rows(c, "d_descan_uv", b, n, 32, [=] __device__(const DecImg &im, int s, int v) { dec_c_descan_strip(im.uvcoef, im.cjpeg, s, v); });
+	d_image(c, "d_ll_uv", b, n, [=] __device__(const DecImg &im0, int i) {
+		int exw = im0.list_len[10];
+		for (int v = 0; v < 2; v++) {
+			DecImg im = make_dec(b, i, v);
+			exw = dec_c_ll_image(im, v, exw);
+		}
+	});
+	idwt_rows_cols(c, 2 * n, b.c_jpeg, b.c_aux, b.c_proc, CS, 128, 256);
+	d_plane(c, "d_markers_uv", b, n, [=] __device__(const DecImg &im, int) { dec_c_markers_image(im); });
+	NHW_LAUNCH(c, kd_transpose, dim3(4, 4, 2 * n), 256, 0, b.c_proc, b.c_jpeg, CS, CS, 256);
+	idwt_rows_cols(c, 2 * n, b.c_jpeg, b.c_aux, b.c_proc, CS, 256, 256);
+	d_plane(c, "d_sharpen_uv", b, n, [=] __device__(const DecImg &im, int) { dec_c_sharpen_image(im); });
+	d_plane_rows(c, "d_upsample_uv", b, n, 512, [=] __device__(const DecImg &im, int y, int v) {
+		dec_c_upsample_row(im.cproc, im.yuv + (size_t)(1 + v) * 262144, y);
+	});
+
+	// ---- colour
+	NHW_LAUNCH(c, kd_color, dim3(262144 / 256, n), 256, 0, b, rgb_dev);
+}
+
+}  // namespace nhw

@@ -8,10 +8,10 @@
 
 #ifdef __CUDACC__
 #define NHW_HD __host__ __device__ __forceinline__
-#define NHW_HDN __host__ __device__
+#define NHW_HDN __host__ __device__ inline
 #else
 #define NHW_HD inline
-#define NHW_HDN
+#define NHW_HDN inline
 #endif
 
 #define NHW_GUARD_S 4096                       // guard, in int16 elements (8 KiB) on each side

@@ -491,6 +491,19 @@ static void idwt_luma256(nhw_ctx *c, const EncBatch &b, int n)
 	NHW_LAUNCH(c, k_idwt_cols_t<256>, dim3(256 / 32, n), 256, 256 * 33 * 2, b.y_aux, b.y_proc, (size_t)NHW_Y_SLOT, (size_t)NHW_Y_SLOT, 512);
 }
 
+// generic form used by the decoder: N x N bands at row stride `stride`, planes `slot` apart
+void idwt_rows_cols(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *tmp, int16_t *out, size_t slot, int N, int stride)
+{
+	idwt_attrs();
+	if (N == 256) {
+		NHW_LAUNCH(c, k_idwt_rows<256>, dim3(256 / 8, n_planes), 256, 0, in, tmp, slot, slot, stride);
+		NHW_LAUNCH(c, k_idwt_cols_t<256>, dim3(256 / 32, n_planes), 256, 256 * 33 * 2, tmp, out, slot, slot, stride);
+	} else {
+		NHW_LAUNCH(c, k_idwt_rows<128>, dim3(128 / 8, n_planes), 256, 0, in, tmp, slot, slot, stride);
+		NHW_LAUNCH(c, k_idwt_cols_t<128>, dim3(128 / 32, n_planes), 256, 128 * 33 * 2, tmp, out, slot, slot, stride);
+	}
+}
+
 static void idwt_chroma128(nhw_ctx *c, const EncBatch &b, int n)
 {
 	idwt_attrs();

@@ -6,6 +6,8 @@
 
 #include "enc_batch.cuh"
 
+struct DecDesc;
+
 struct nhw_ctx {
 	int device;
 	int max_batch;
@@ -42,6 +44,9 @@ struct nhw_ctx {
 	int32_t *status_dev;
 	uint64_t *offs_dev;  // max_batch + 1
 	uint64_t *offs_host; // pinned
+	uint8_t *dec_yuv;    // decoder: Y,U,V byte planes 512x512, 786432 B / image
+	void *dec_desc_dev;  // decoder: DecDesc per image (device) and its pinned host staging
+	void *dec_desc_host;
 	int32_t *status_host;
 };
 
@@ -62,6 +67,10 @@ void dwt_level_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t j
 // encode.cu
 void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev);
 void pack_streams(nhw_ctx *c, int n);   // out_dev slots + len_dev -> offs_dev, pack_dev
+
+// decode.cu
+void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const struct DecDesc *desc, int32_t *status, int n,
+                  uint8_t *rgb_dev);
 
 // synth.cu
 void synth(nhw_ctx *c, uint8_t *rgb, int n, uint32_t seed0, int kind, const int16_t *sin_lut);
