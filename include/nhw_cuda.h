@@ -74,6 +74,13 @@ int nhw_encode_batch_device(nhw_ctx *ctx, const uint8_t *rgb_dev, int n, int qua
 int nhw_decode_batch(nhw_ctx *ctx, const uint8_t *in, const uint64_t *offsets, int n,
                      uint8_t *rgb, int32_t *status);
 
+/* Same, but stops before the colour conversion: yuv receives, per image, the three 512x512
+ * byte planes Y, U, V (786432 bytes) that decode_image leaves in im_bufferY/U/V for
+ * write_image_bmp (decoder/nhw_decoder.c:877-891,1137-1181).  quality (n entries, may be NULL)
+ * receives each stream's quality byte. */
+int nhw_decode_batch_planes(nhw_ctx *ctx, const uint8_t *in, const uint64_t *offsets, int n,
+                            uint8_t *yuv, int32_t *quality, int32_t *status);
+
 /* ---- stage-level entry points (device pointers), used by the parity tests and ncu runs.
  * Layouts follow the reference's working planes (encoder/codec.h:112-123):
  *   y_proc : n * 512*512 int16, the luma coefficient plane (`im_process`) after both DWT

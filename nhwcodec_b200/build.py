@@ -65,6 +65,11 @@ def build_host():
     cli = os.path.join(HERE, "..", "cli")
     subprocess.check_call(["gcc", "-O2", "-Wall", os.path.join(cli, "nhw_enc_cli.c"), "-o", os.path.join(cli, "nhw-enc"),
                            "-L" + HERE, "-lnhw_compat", "-lnhw_cuda", "-Wl,-rpath,$ORIGIN/../nhwcodec_b200"])
+    compat_dec = os.path.join(HERE, "libnhw_compat_dec.so")
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-Wall", os.path.join(CSRC, "compat_dec.c"), "-o", compat_dec,
+                           "-L" + HERE, "-lnhw_cuda", "-Wl,-rpath,$ORIGIN"])
+    subprocess.check_call(["gcc", "-O2", "-Wall", os.path.join(cli, "nhw_dec_cli.c"), "-o", os.path.join(cli, "nhw-dec"),
+                           "-L" + HERE, "-lnhw_cuda", "-Wl,-rpath,$ORIGIN/../nhwcodec_b200"])
     # drop-in proof: the reference's OWN, unmodified CLI source compiled against its own header
     # and linked against our two libraries (only where the reference tree is present)
     ref_cli = "/root/reference/encoder/nhw_encoder_cli.c"
@@ -73,6 +78,9 @@ def build_host():
         subprocess.check_call(["gcc", "-O2", "-w", "-I/root/reference/encoder", ref_cli, "-o",
                                os.path.join(ref_out, "nhw-enc-dropin"), "-L" + HERE, "-lnhw_compat", "-lnhw_cuda",
                                "-Wl,-rpath,$ORIGIN/../../nhwcodec_b200"])
+        subprocess.check_call(["gcc", "-O2", "-w", "-ffp-contract=off", "-I/root/reference/decoder",
+                               "/root/reference/decoder/nhw_decoder_cli.c", "-o", os.path.join(ref_out, "nhw-dec-dropin"),
+                               "-L" + HERE, "-lnhw_compat_dec", "-lnhw_cuda", "-Wl,-rpath,$ORIGIN/../../nhwcodec_b200"])
 
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@ MAX_STREAM_BYTES = 1 << 19
 # every symbol include/nhw_cuda.h declares (tests check the library exports all of them)
 EXPORTS = [
     "nhw_create", "nhw_destroy", "nhw_last_error", "nhw_version", "nhw_encode_batch",
-    "nhw_encode_batch_device", "nhw_decode_batch", "nhw_stage_frontend_device",
+    "nhw_encode_batch_device", "nhw_decode_batch", "nhw_decode_batch_planes", "nhw_stage_frontend_device",
     "nhw_stage_colorspace_device", "nhw_synth_batch_device", "nhw_launch_count",
     "nhw_stream", "nhw_profile", "nhw_profile_read", "nhw_debug_stop_after", "nhw_debug_read",
 ]
@@ -51,6 +51,8 @@ def load_library():
     L.nhw_encode_batch_device.restype = i32
     L.nhw_decode_batch.argtypes = [vp, vp, vp, i32, vp, vp]
     L.nhw_decode_batch.restype = i32
+    L.nhw_decode_batch_planes.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    L.nhw_decode_batch_planes.restype = i32
     L.nhw_stage_frontend_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     L.nhw_stage_frontend_device.restype = i32
     L.nhw_stage_colorspace_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]

@@ -352,9 +352,10 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 	return NHW_OK;
 }
 
-int nhw_decode_batch(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int n, uint8_t *rgb, int32_t *status)
+static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int n, uint8_t *rgb, uint8_t *yuv,
+                             int32_t *quality, int32_t *status)
 {
-	if (!c || !in || !offsets || !rgb || n <= 0) return NHW_ERR_ARG;
+	if (!c || !in || !offsets || (!rgb && !yuv) || n <= 0) return NHW_ERR_ARG;
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
 	DecDesc *desc = static_cast<DecDesc *>(c->dec_desc_host);
@@ -366,6 +367,7 @@ int nhw_decode_batch(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int
 			const uint64_t o = offsets[i0 + i] - base, len = offsets[i0 + i + 1] - offsets[i0 + i];
 			c->offs_host[i] = o;
 			c->status_host[i] = nhw_parse_header(in + base + o, (size_t)len, &desc[i]);
+			if (quality) quality[i0 + i] = desc[i].quality;
 		}
 		bool ok = check(cudaMemcpyAsync(c->pack_dev, in + base, total, cudaMemcpyHostToDevice, c->stream), "H2D streams");
 		// the bit reader may look a few words past the last code: keep that tail defined
@@ -375,13 +377,27 @@ int nhw_decode_batch(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int
 		ok = ok && check(cudaMemcpyAsync(c->status_dev, c->status_host, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream), "H2D status");
 		if (!ok) return NHW_ERR_CUDA;
 		nhw::decode_chunk(c, c->pack_dev, c->offs_dev, static_cast<const DecDesc *>(c->dec_desc_dev), c->status_dev, m, c->rgb);
-		cudaMemcpyAsync(rgb + (size_t)i0 * NHW_RGB_BYTES, c->rgb, (size_t)m * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, c->stream);
+		if (rgb) cudaMemcpyAsync(rgb + (size_t)i0 * NHW_RGB_BYTES, c->rgb, (size_t)m * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, c->stream);
+		if (yuv) cudaMemcpyAsync(yuv + (size_t)i0 * NHW_RGB_BYTES, c->dec_yuv, (size_t)m * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, c->stream);
 		cudaMemcpyAsync(c->status_host, c->status_dev, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
 		int rc = finish(c, "nhw_decode_batch");
 		if (rc) return rc;
 		for (int i = 0; status && i < m; i++) status[i0 + i] = c->status_host[i];
 	}
 	return NHW_OK;
+}
+
+int nhw_decode_batch(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int n, uint8_t *rgb, int32_t *status)
+{
+	if (!rgb) return NHW_ERR_ARG;
+	return decode_batch_impl(c, in, offsets, n, rgb, nullptr, nullptr, status);
+}
+
+int nhw_decode_batch_planes(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int n, uint8_t *yuv, int32_t *quality,
+                            int32_t *status)
+{
+	if (!yuv) return NHW_ERR_ARG;
+	return decode_batch_impl(c, in, offsets, n, nullptr, yuv, quality, status);
 }
 
 }  // extern "C"

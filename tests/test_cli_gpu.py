@@ -51,3 +51,24 @@ def test_cli_rejects_bad_input(tmp_path):
     assert r.returncode == (-13) % 256     # HEADER_CHECK_ERROR_NO_VALID_SIG, encoder/nhw_encoder.c:63-71
     r = subprocess.run([os.path.join(ROOT, "cli/nhw-enc"), "-q99", "a", "b"], capture_output=True)
     assert r.returncode == 1
+
+
+KAT_DEC_Q20 = "1d9ccf4e698182fcac1ae31992789caf"   # nhw-dec output of the canonical q20 stream
+
+
+@pytest.mark.parametrize("exe", ["cli/nhw-dec", "oracle/_ref/nhw-dec-dropin"])
+def test_decoder_cli_known_answer(smooth_bmp, exe, tmp_path):
+    """our nhw-dec, and the reference's own decoder CLI source linked against libnhw_compat_dec,
+    must write the BMP the reference nhw-dec writes"""
+    path = os.path.join(ROOT, exe)
+    if not os.path.exists(path):
+        pytest.skip(exe + " not built")
+    nhw = str(tmp_path / "s.nhw")
+    r = subprocess.run([os.path.join(ROOT, "cli/nhw-enc"), "-q20", smooth_bmp, nhw], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = str(tmp_path / "out.bmp")
+    r = subprocess.run([path, nhw, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    data = open(out, "rb").read()
+    assert len(data) == 786486
+    assert hashlib.md5(data).hexdigest() == KAT_DEC_Q20

@@ -126,6 +126,27 @@ int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(codec_se
     assert outs[0] == outs[1], outs
 
 
+def test_decoder_compat_struct_layout_matches_reference(tmp_path):
+    ref = "/root/reference/decoder/codec.h"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present")
+    import subprocess
+    outs = []
+    for hdr, ib, cs in ((ref, "image_buffer", "codec_setup"),
+                        (os.path.join(ROOT, "include", "nhw_compat_dec.h"), "nhw_dec_image_buffer", "nhw_dec_codec_setup")):
+        src = tmp_path / "layd.c"
+        src.write_text("""#include <stdio.h>
+#include <stddef.h>
+#include "%s"
+int main(){ printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(%s), sizeof(%s), offsetof(%s, im_bufferY),
+ offsetof(%s, im_bufferU), offsetof(%s, im_bufferV), offsetof(%s, setup), offsetof(%s, quality_setting)); return 0; }"""
+                       % (hdr, ib, cs, ib, ib, ib, ib, cs))
+        exe = tmp_path / "layd"
+        subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+        outs.append(subprocess.check_output([str(exe)]))
+    assert outs[0] == outs[1], outs
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
