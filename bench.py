@@ -306,6 +306,33 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps * PIX / float(tt.item()) / 1e6
 
+    # ---------------- decode of the streams just produced (host API: .nhw bytes in, pixels out) ----------------
+    dec = None
+    try:
+        rgb_back = torch.empty((B, PIX_BYTES), dtype=torch.uint8, pin_memory=True)
+        rgb_back_np = rgb_back.numpy()
+        dst = np.zeros(B, dtype=np.int32)
+        codec.decode_into(out_np, offs, B, rgb_back_np, dst)      # warm-up
+        codec.profile(2)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            codec.decode_into(out_np, offs, B, rgb_back_np, dst)
+        torch.cuda.synchronize()
+        ddt = time.perf_counter() - t0
+        dtable = codec.profile_table()
+        codec.profile(0)
+        td = torch.tensor([ddt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dkern = sorted(((k, v[0] / e2e_steps) for k, v in dtable.items()), key=lambda kv: -kv[1])
+        dec = {"value": round(world * B * e2e_steps * PIX / float(td.item()) / 1e6, 3), "unit": UNIT,
+               "what": "nhw_decode_batch on the %d streams of the encode above, host buffers, copies inside the timed region" % B,
+               "errors": int((dst != 0).sum()), "h2d_bytes_per_step": d2h, "d2h_bytes_per_step": B * PIX_BYTES,
+               "kernel_ms_per_step": {k: round(ms, 3) for k, ms in dkern[:10]}}
+    except Exception as e:   # noqa: BLE001
+        dec = {"value": None, "unit": UNIT, "what": "decode failed: %s" % e}
+
     if rank == 0:
         # ---------------- roofline of the dominant kernel ----------------
         peak, peak_src = peaks()
@@ -367,6 +394,7 @@ def run_ours(args):
             "roofline": roofline,
             "frontend": frontend,
             "cpu_baseline": cpu,
+            "decode": dec,
             "kernels": kernels[:16],
         }
         print(json.dumps(line), flush=True)

@@ -174,6 +174,12 @@ class Codec:
         self._check(rc, "nhw_decode_batch")
         return rgb, status
 
+    def decode_into(self, blob, offsets, n, rgb, status):
+        """zero-allocation variant for bench.py: blob/offsets as produced by encode_into"""
+        rc = self.lib.nhw_decode_batch(self.h, blob.ctypes.data, offsets.ctypes.data, int(n), rgb.ctypes.data,
+                                       status.ctypes.data)
+        self._check(rc, "nhw_decode_batch")
+
     # ---------------- device-resident API (torch tensors on this GPU) ----------------
     def encode_device(self, rgb_t, quality, out_t, len_t, status_t):
         n = rgb_t.shape[0]
