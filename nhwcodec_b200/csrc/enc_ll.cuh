@@ -11,14 +11,14 @@
 
 // ---- E10 + E11: LL2 plane -> byte list.  Values outside 0..255 go to the exw_Y escape list;
 // rows of four odd samples in a row are tagged and announced in nhw_res4 (q>17).
-NHW_HDN void y_ll2_to_bytes_image(const EncImg &im, int q)
+// P = LL2 band at row stride PS (see y_recons_ll2_core)
+NHW_HDN void y_ll2_to_bytes_core(const EncImg &im, int16_t *P, int PS, int q)
 {
-	int16_t *P = im.proc;
 	EncHdr *h = im.hdr;
 	int res = 0;
 	if (q > 17) {
 		for (int r = 0; r < 128; r++) {
-			int c = r * YW, stage = 0;
+			int c = r * PS, stage = 0;
 			for (int j = 0; j < 125; j++, c++) {
 				if (nhw_odd(P[c]) && nhw_odd(P[c + 1]) && nhw_odd(P[c + 2]) && nhw_odd(P[c + 3]) &&
 				    nhw_iabs(P[c] - P[c + 3]) > 1) {
@@ -33,28 +33,27 @@ NHW_HDN void y_ll2_to_bytes_image(const EncImg &im, int q)
 	int a = 0, e = 0;
 	res = 0;
 	for (int r = 0; r < 128; r++) {
-		const int i = r * YW;
 		int stage = 0;
-		int c = i;
+		int c = r * PS;
 		for (int j = 0; j < 128; j++, c++) {
 			int scan = P[c];
 			if (q > 17 && scan > 10000) {
 				if (scan > 20000) { scan -= 24000; im.res4[res++] = (uint8_t)(j + 1); stage++; }
 				else scan -= 16000;
-			} else if (nhw_odd(scan) && c > i && nhw_odd(P[c + 1])) {
+			} else if (nhw_odd(scan) && j > 0 && nhw_odd(P[c + 1])) {
 				if (j < 126 && nhw_odd(P[c + 2])) {
 					if (nhw_iabs(scan - P[c + 2]) > 1 && q > 17) P[c + 1]++;
-				} else if (i < 65536 - YW - 2 && nhw_odd(P[c + YW]) && nhw_odd(P[c + YW + 1]) && !nhw_odd(P[c + YW + 2])) {
-					if (P[c + YW] < 10000 && q > 17) P[c + YW]++;
+				} else if (r < 127 && nhw_odd(P[c + PS]) && nhw_odd(P[c + PS + 1]) && !nhw_odd(P[c + PS + 2])) {
+					if (P[c + PS] < 10000 && q > 17) P[c + PS]++;
 				}
-			} else if (nhw_odd(scan) && i >= YW && i < 65536 - 3 * YW) {
-				if (nhw_odd(P[c + YW]) && nhw_odd(P[c + YW + 1])) {
-					if (nhw_odd(P[c + 2 * YW]) && !nhw_odd(P[c + 3 * YW])) {
-						if (P[c + YW] < 10000 && q > 17) P[c + YW]++;
+			} else if (nhw_odd(scan) && r >= 1 && r < 125) {
+				if (nhw_odd(P[c + PS]) && nhw_odd(P[c + PS + 1])) {
+					if (nhw_odd(P[c + 2 * PS]) && !nhw_odd(P[c + 3 * PS])) {
+						if (P[c + PS] < 10000 && q > 17) P[c + PS]++;
 					}
 				}
 			}
-			if (scan > 255 && (j > 0 || i > 0)) {
+			if (scan > 255 && (j > 0 || r > 0)) {
 				im.exw[e++] = (uint8_t)r;
 				im.exw[e++] = (uint8_t)(j + 128);
 				int y = scan - 255;
@@ -63,7 +62,7 @@ NHW_HDN void y_ll2_to_bytes_image(const EncImg &im, int q)
 				im.tree1[a] = im.tree1[a - 1];
 				im.ch_res[a] = im.tree1[a - 1];
 				a++;
-			} else if (scan < 0 && (j > 0 || i > 0)) {
+			} else if (scan < 0 && (j > 0 || r > 0)) {
 				im.exw[e++] = (uint8_t)r;
 				im.exw[e++] = (uint8_t)j;
 				if (scan < -255) scan = -255;
@@ -86,6 +85,11 @@ NHW_HDN void y_ll2_to_bytes_image(const EncImg &im, int q)
 	}
 	h->exw_y_len = e;
 }
+
+NHW_HDN void y_ll2_to_bytes_image(const EncImg &im, int q) { y_ll2_to_bytes_core(im, im.proc, YW, q); }
+
+NHW_HDN int ll_dpcm_luma_core(const EncImg &im, const uint8_t *x, uint8_t *work, int q);
+NHW_HDN int ll_dpcm_luma_image(const EncImg &im, int q) { return ll_dpcm_luma_core(im, im.tree1, im.tmp1, q); }
 
 // ---- shared pieces of the three DPCM modes (compress_pixel.c:511-830) ----
 struct LlCoder {
@@ -124,9 +128,10 @@ NHW_HD void ll_emit_triple(LlCoder &c, int &i, int scan, int count, int e)
 NHW_HD bool ll_triple_ok(const LlCoder &c, int i) { return nhw_iabs(c.x[i + 2] - c.x[i + 1]) <= 32 && i < 16382; }
 
 // luma LL2: chooses RES_LOW mode 0/1/2 from run statistics, then codes.  Returns the mode.
-NHW_HDN int ll_dpcm_luma_image(const EncImg &im, int q)
+// x = the 16384 LL2 bytes followed by at least 32 readable zero bytes (tree1, or a shared-memory
+// copy); work = >= 24640 bytes of scratch for the marked code (tmp1, or shared memory).
+NHW_HDN int ll_dpcm_luma_core(const EncImg &im, const uint8_t *x, uint8_t *work, int q)
 {
-	const uint8_t *x = im.tree1;
 	EncHdr *h = im.hdr;
 	const int N = 16384;
 	// run statistics (compress_pixel.c:482-502)
@@ -144,7 +149,7 @@ NHW_HDN int ll_dpcm_luma_image(const EncImg &im, int q)
 	int mode = Y > 299 ? 2 : (a > 179 ? 1 : 0);
 
 	LlCoder c;
-	c.x = x; c.out = im.tmp1; c.full = im.ch_res; c.word = im.highres_word; c.mem = im.highres_mem;
+	c.x = x; c.out = work; c.full = im.ch_res; c.word = im.highres_word; c.mem = im.highres_mem;
 	c.j = 1; c.nmem = 0; c.q = q;
 	c.out[0] = x[0];
 	a = 0;

@@ -45,12 +45,13 @@ NHW_HD void y_e6a_tag_row(const EncImg &im, int r)
 
 // ---- offsetY_recons256, LL2 part (image_processing.c:2610-2737).  Serial: a row nudges
 // cells of the next row before that row is visited.
-NHW_HDN void y_recons_ll2_image(const EncImg &im, int q, int part)
+// P = LL2 band at row stride PS (the plane itself, PS = 512, or a shared-memory copy of its
+// first 128 rows x 132 columns); J = im_jpeg (row stride 512); tmp = 16384 cells of scratch.
+NHW_HDN void y_recons_ll2_core(int16_t *P, int PS, int16_t *J, int16_t *tmp, const uint16_t *hmem, int hmem_len, int q, int part)
 {
-	int16_t *P = im.proc, *J = im.jpeg;
 	if (q > 17) {
 		for (int r = 0; r < 128; r++) {
-			int a = r * YW;
+			int a = r * PS;
 			for (int j = 0; j < 125; j++, a++) {
 				if (nhw_odd(P[a]) && nhw_odd(P[a + 1]) && nhw_odd(P[a + 2]) && nhw_odd(P[a + 3]) &&
 				    nhw_iabs(P[a] - P[a + 3]) > 1) {
@@ -64,60 +65,63 @@ NHW_HDN void y_recons_ll2_image(const EncImg &im, int q, int part)
 		}
 	}
 	for (int r = 0; r < 128; r++) {
-		int i = r * YW;
-		int a = i;
-		for (int j = 0; j < 128; j++, a++) {
+		int a = r * PS, aj = r * YW;
+		for (int j = 0; j < 128; j++, a++, aj++) {
 			if (P[a] > 10000) {
-				if (!part) J[a] = P[a];
+				if (!part) J[aj] = P[a];
 				else {
 					P[a] -= 16000;
-					J[a] = P[a];
-					J[a + 1] = (P[a + 1] > 0 && P[a + 1] < 256) ? (int16_t)(P[a + 1] & 65534) : P[a + 1];
+					J[aj] = P[a];
+					J[aj + 1] = (P[a + 1] > 0 && P[a + 1] < 256) ? (int16_t)(P[a + 1] & 65534) : P[a + 1];
 					j++;
 					a++;
+					aj++;
 				}
 				continue;
-			} else if (nhw_odd(P[a]) && a > i && nhw_odd(P[a + 1])) {
+			} else if (nhw_odd(P[a]) && j > 0 && nhw_odd(P[a + 1])) {
 				if (j < 126 && nhw_odd(P[a + 2])) {
 					if (nhw_iabs(P[a] - P[a + 2]) > 1 && q > 17) P[a + 1]++;
-				} else if (i < 65536 - YW - 2 && nhw_odd(P[a + YW]) && nhw_odd(P[a + YW + 1]) && !nhw_odd(P[a + YW + 2])) {
-					if (P[a + YW] < 10000 && q > 17) P[a + YW]++;
+				} else if (r < 127 && nhw_odd(P[a + PS]) && nhw_odd(P[a + PS + 1]) && !nhw_odd(P[a + PS + 2])) {
+					if (P[a + PS] < 10000 && q > 17) P[a + PS]++;
 				}
-			} else if (nhw_odd(P[a]) && i >= YW && i < 65536 - 3 * YW) {
-				if (nhw_odd(P[a + YW]) && nhw_odd(P[a + YW + 1])) {
-					if (nhw_odd(P[a + 2 * YW]) && !nhw_odd(P[a + 3 * YW])) {
-						if (P[a + YW] < 10000 && q > 17) P[a + YW]++;
+			} else if (nhw_odd(P[a]) && r >= 1 && r < 125) {
+				if (nhw_odd(P[a + PS]) && nhw_odd(P[a + PS + 1])) {
+					if (nhw_odd(P[a + 2 * PS]) && !nhw_odd(P[a + 3 * PS])) {
+						if (P[a + PS] < 10000 && q > 17) P[a + PS]++;
 					}
 				}
 			}
-			if (part) J[a] = (P[a] > 0 && P[a] < 256) ? (int16_t)(P[a] & 65534) : P[a];
+			if (part) J[aj] = (P[a] > 0 && P[a] < 256) ? (int16_t)(P[a] & 65534) : P[a];
 		}
 	}
 	if (!part) {
-		// highres_tmp (image_processing.c:2715-2736) lives in im.caux-independent scratch: im.aux
-		int16_t *tmp = im.aux;
+		// highres_tmp (image_processing.c:2715-2736)
 		int t = 0;
 		for (int r = 0; r < 128; r++) {
-			int a = r * YW;
-			for (int j = 0; j < 128; j++, a++) {
+			int a = r * PS, aj = r * YW;
+			for (int j = 0; j < 128; j++, a++, aj++) {
 				if (P[a] < 10000) {
 					tmp[t++] = P[a];
-					J[a] = (P[a] >= 0 && P[a] < 256) ? (int16_t)(P[a] & 65534) : P[a];
+					J[aj] = (P[a] >= 0 && P[a] < 256) ? (int16_t)(P[a] & 65534) : P[a];
 				} else {
 					P[a] -= 16000;
 					tmp[t++] = P[a];
-					J[a] = P[a];
+					J[aj] = P[a];
 				}
 			}
 		}
 		if (q > 15) {
-			const int n = im.hdr->highres_mem_len;
-			for (int k = 0; k < n; k++) {
-				int m = im.highres_mem[k];
+			for (int k = 0; k < hmem_len; k++) {
+				int m = hmem[k];
 				J[((m >> 7) << 9) + (m & 127)] = tmp[m];
 			}
 		}
 	}
+}
+
+NHW_HDN void y_recons_ll2_image(const EncImg &im, int q, int part)
+{
+	y_recons_ll2_core(im.proc, YW, im.jpeg, im.aux, im.highres_mem, im.hdr->highres_mem_len, q, part);
 }
 
 // ---- offsetY_recons256, 3-in-a-row / vertical-pair substitutions in the level-2 detail

@@ -248,39 +248,58 @@ NHW_HDN void y_e16b_classify_image(const EncImg &im, int q)
 // side channels: column positions per row (254 = end of row), pair-delta packed, with the
 // positions' LSBs and the 1- or 2-bit words in separate bit planes.
 // which: 1, 3 or 5.  Scratch: tmp1 (positions), tmp2 (copy), tmp3 (words).
+// Step 1, one row: collect the column positions (and word bits) of the codes that belong to list
+// `which`, rewrite those cells, end the row with the 254 marker.  With pos == NULL only counts.
+// Returns the number of codes found (the row contributes that many + 1 positions).
+NHW_HD int y_e18_collect_row(const EncImg &im, int which, int row, uint8_t *pos, uint8_t *wrd)
+{
+	int16_t *L = im.ll1 + row * 256;
+	int n = 0;
+	for (int j = 0; j < 254; j++) {
+		const int v = L[j];
+		if (v == 0) continue;
+		int nv = -1, w = 0;
+		if (which == 1) {
+			if (v == 141) { nv = 0; w = 1; } else if (v == 140) { nv = 0; w = 0; }
+			else if (v == 126) { nv = 122; w = 0; } else if (v == 125) { nv = 121; w = 1; }
+			else if (v == 148) { nv = 144; w = 1; } else if (v == 149) { nv = 145; w = 0; }
+		} else if (which == 3) {
+			if (v == 121) { nv = 0; w = 1; } else if (v == 122) { nv = 0; w = 0; }
+			else if (v == 123) { nv = 0; w = 2; } else if (v == 124) { nv = 0; w = 3; }
+		} else {
+			if (v == 144) { nv = 0; w = 1; } else if (v == 145) { nv = 0; w = 0; }
+		}
+		if (nv < 0) continue;
+		if (pos) { pos[n] = (uint8_t)j; wrd[n] = (uint8_t)w; L[j] = (int16_t)nv; }
+		n++;
+	}
+	if (pos) { pos[n] = 254; L[254] = 0; L[255] = 0; }
+	return n;
+}
+
+NHW_HDN void y_e18_finish_list_image(const EncImg &im, int which, int count, int e);
+
 NHW_HDN void y_e18_pack_list_image(const EncImg &im, int which)
 {
-	int16_t *L = im.ll1;
+	uint8_t *pos = im.tmp1, *wrd = im.tmp3;
+	int count = 0, e = 0;
+	for (int row = 0; row < 256; row++) {
+		const int n = y_e18_collect_row(im, which, row, pos + count, wrd + e);
+		count += n + 1;
+		e += n;
+	}
+	y_e18_finish_list_image(im, which, count, e);
+}
+
+// Steps 2..6 on the collected lists: tmp1 = `count` positions, tmp3 = `e` word values.
+NHW_HDN void y_e18_finish_list_image(const EncImg &im, int which, int count, int e)
+{
 	EncHdr *h = im.hdr;
 	uint8_t *pos = im.tmp1, *cpy = im.tmp2, *wrd = im.tmp3;
 	uint8_t *out, *out_bit, *out_word;
 	if (which == 1) { out = im.res1; out_bit = im.res1_bit; out_word = im.res1_word; }
 	else if (which == 3) { out = im.res3; out_bit = im.res3_bit; out_word = im.res3_word; }
 	else { out = im.res5; out_bit = im.res5_bit; out_word = im.res5_word; }
-	int count = 0, e = 0;
-	for (int row = 0; row < 256; row++) {
-		int scan = row * 256;
-		for (int j = 0; j < 256; j++, scan++) {
-			if (j == 254) { L[scan] = 0; L[scan + 1] = 0; pos[count++] = 254; j++; continue; }
-			int v = L[scan];
-			if (v == 0) continue;
-			int nv = -1, w = 0;
-			if (which == 1) {
-				if (v == 141) { nv = 0; w = 1; } else if (v == 140) { nv = 0; w = 0; }
-				else if (v == 126) { nv = 122; w = 0; } else if (v == 125) { nv = 121; w = 1; }
-				else if (v == 148) { nv = 144; w = 1; } else if (v == 149) { nv = 145; w = 0; }
-			} else if (which == 3) {
-				if (v == 121) { nv = 0; w = 1; } else if (v == 122) { nv = 0; w = 0; }
-				else if (v == 123) { nv = 0; w = 2; } else if (v == 124) { nv = 0; w = 3; }
-			} else {
-				if (v == 144) { nv = 0; w = 1; } else if (v == 145) { nv = 0; w = 0; }
-			}
-			if (nv < 0) continue;
-			pos[count++] = (uint8_t)j;
-			L[scan] = (int16_t)nv;
-			wrd[e++] = (uint8_t)w;
-		}
-	}
 	for (int i = 0; i < 8; i++) wrd[e + i] = 0;   // the reference reads up to 7 entries past the end
 	// drop end-of-row markers the decoder can infer from a decreasing position
 	for (int i = 0; i < count; i++) cpy[i] = pos[i];

@@ -159,6 +159,78 @@ __global__ void __launch_bounds__(256) k_e16b_classify(EncBatch b, int q)
 	y_e16b_classify_col(im, q, threadIdx.x, w1, w3, w5);
 }
 
+// ---- serial LL2 stages with the band staged in shared memory: one warp per image copies the
+// band (128 rows x 132 columns, the 4 extra columns are look-ahead), lane 0 runs the stage at
+// shared-memory latency, the warp writes the 128x128 band back.  ~34-48 KB per image lets
+// several images share an SM, which is what these latency-bound stages need.
+#define LL2_PS 132
+#define LL2_SMEM_BYTES (128 * LL2_PS * 2)
+template <typename F>
+__global__ void __launch_bounds__(32) k_ll2_staged(EncBatch b, F f)
+{
+	extern __shared__ __align__(16) int16_t sP[];
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int lane = threadIdx.x;
+	for (int r = 0; r < 128; r++) {
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(im.proc + r * YW);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(sP + r * LL2_PS);
+		for (int c = lane; c < LL2_PS / 2; c += 32) dst[c] = src[c];
+	}
+	__syncwarp();
+	if (lane == 0) f(im, sP);
+	__syncwarp();
+	for (int r = 0; r < 128; r++) {
+		uint32_t *dst = reinterpret_cast<uint32_t *>(im.proc + r * YW);
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(sP + r * LL2_PS);
+		for (int c = lane; c < 64; c += 32) dst[c] = src[c];
+	}
+}
+
+template <typename F>
+void run_ll2_staged(nhw_ctx *c, const char *label, const EncBatch &b, int n, size_t smem, F f)
+{
+	static bool attr = false;
+	(void)attr;
+	cudaFuncSetAttribute(k_ll2_staged<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	NHW_LAUNCH_L(c, label, k_ll2_staged, n, 32, smem, b, f);
+}
+
+// ---- res1/res3/res5 side-channel lists: rows collected in parallel (count, CTA prefix, write),
+// the short list post-processing by one thread
+__global__ void __launch_bounds__(256) k_e18_lists(EncBatch b, int q)
+{
+	__shared__ int cnt[257];
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int row = threadIdx.x;
+	for (int which = 1; which <= 5; which += 2) {
+		if ((which == 3 && q < 19) || (which == 5 && q < 21)) continue;
+		const int n = y_e18_collect_row(im, which, row, nullptr, nullptr);
+		cnt[row] = n;
+		__syncthreads();
+		if (row == 0) {
+			int run = 0;
+			for (int r = 0; r < 256; r++) { const int v = cnt[r]; cnt[r] = run; run += v; }
+			cnt[256] = run;
+		}
+		__syncthreads();
+		const int e0 = cnt[row];
+		y_e18_collect_row(im, which, row, im.tmp1 + e0 + row, im.tmp3 + e0);
+		__syncthreads();
+		if (row == 0) y_e18_finish_list_image(im, which, cnt[256] + 256, cnt[256]);
+		__syncthreads();
+	}
+}
+
+// ---- offsetUV to bytes, one thread per row of one chroma plane
+__global__ void __launch_bounds__(256) k_c_offset_quant(EncBatch b, int m2)
+{
+	const EncImg im = make_img(b, blockIdx.x >> 1, blockIdx.x & 1);
+	const int r = threadIdx.x;
+	const int next0 = r < 255 ? (int)im.cproc[(r + 1) * CW] : 0;
+	__syncthreads();
+	c_offset_quant_row(im, m2, r, next0);
+}
+
 // ---- offsetY to bytes, one thread per row; the look-ahead cell of the next row is sampled
 // before any row is rewritten
 __global__ void __launch_bounds__(512) k_offset_quant(EncBatch b, int m1)
@@ -542,7 +614,9 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- luma closed loop (nhw_encoder.c:141-283)
 	run_rows(c, "y_e6a_tag", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });
-	run_image(c, "y_recons1_ll2", b, n, [=] __device__(const EncImg &im, int) { y_recons_ll2_image(im, q, 1); });
+	run_ll2_staged(c, "y_recons1_ll2", b, n, LL2_SMEM_BYTES, [=] __device__(const EncImg &im, int16_t *sP) {
+		y_recons_ll2_core(sP, LL2_PS, im.jpeg, im.aux, im.highres_mem, 0, q, 1);
+	});
 	for (int reg = 0; reg < 2; reg++)
 		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
@@ -554,14 +628,22 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- LL2 coding (nhw_encoder.c:623-757)
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
-	run_image(c, "y_ll2_code", b, n, [=] __device__(const EncImg &im, int) {
-		y_ll2_to_bytes_image(im, q);
-		ll_dpcm_luma_image(im, q);
+	// LL2 -> bytes on the staged band; then the band's shared memory is reused for the byte list
+	// (16384 + zero tail) and the marked code the DPCM coder strips afterwards
+	run_ll2_staged(c, "y_ll2_code", b, n, 48 * 1024, [=] __device__(const EncImg &im, int16_t *sP) {
+		y_ll2_to_bytes_core(im, sP, LL2_PS, q);
+		uint8_t *x = reinterpret_cast<uint8_t *>(sP);          // 16448 bytes
+		uint8_t *work = x + 16448;                              // 24704 bytes (48 KB - 16448 - slack)
+		for (int i = 0; i < 16384; i++) x[i] = im.tree1[i];
+		for (int i = 16384; i < 16448; i++) x[i] = 0;
+		ll_dpcm_luma_core(im, x, work, q);
 	});
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_ll2s, CS, 256, b.y_proc, YS, 512, 256);
 
 	// ---- second reconstruction = what the decoder will see as LL1 (nhw_encoder.c:759-781)
-	run_image(c, "y_recons0_ll2", b, n, [=] __device__(const EncImg &im, int) { y_recons_ll2_image(im, q, 0); });
+	run_ll2_staged(c, "y_recons0_ll2", b, n, LL2_SMEM_BYTES, [=] __device__(const EncImg &im, int16_t *sP) {
+		y_recons_ll2_core(sP, LL2_PS, im.jpeg, im.aux, im.highres_mem, im.hdr->highres_mem_len, q, 0);
+	});
 	for (int reg = 0; reg < 2; reg++)
 		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
@@ -583,11 +665,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		run_rows(c, "y_e16b_classify", b, n, 256, [=] __device__(const EncImg &im, int j) { int w1 = 0, w3 = 0, w5 = 0; y_e16b_classify_col(im, q, j, w1, w3, w5); });
 	else
 		NHW_LAUNCH_L(c, "y_e16b_classify", k_e16b_classify, n, 256, 0, b, q);
-	run_image(c, "y_e18_lists", b, n, [=] __device__(const EncImg &im, int) {
-		y_e18_pack_list_image(im, 1);
-		if (q >= 19) y_e18_pack_list_image(im, 3);
-		if (q >= 21) y_e18_pack_list_image(im, 5);
-	});
+	NHW_LAUNCH_L(c, "y_e18_lists", k_e18_lists, n, 256, 0, b, q);
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
 	run_rows(c, "y_e19_restore", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e19_restore_row(im, r); });
@@ -622,8 +700,8 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		int e = c_ll_to_bytes_image(im, v);
 		if (v) im.hdr->exw_v_len = e; else im.hdr->exw_u_len = e;
 		if (q > 15) c_ll_bit1_plane(im, v);
-		c_offset_quant_image(im, ratio);
 	});
+	NHW_LAUNCH_L(c, "c_offset_quant", k_c_offset_quant, 2 * n, 256, 0, b, ratio);
 	run_plane_rows(c, "c_scan", b, n, 32, [=] __device__(const EncImg &im, int s, int v) { c_scan_strip(im, s, v); });
 
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)

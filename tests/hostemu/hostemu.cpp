@@ -455,7 +455,11 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		int e = c_ll_to_bytes_image(im, v);
 		if (v) h->exw_v_len = e; else h->exw_u_len = e;
 		if (q > 15) c_ll_bit1_plane(im, v);
-		c_offset_quant_image(im, ratio);
+		{
+			std::vector<int> next0(256);
+			for (int r = 0; r < 256; r++) next0[r] = r < 255 ? im.cproc[(r + 1) * 256] : 0;
+			for (int r = 255; r >= 0; r--) c_offset_quant_row(im, ratio, r, next0[r]);
+		}
 		TN("quant_proc", im.cproc, 65536 * 2);
 		for (int s = 31; s >= 0; s--) c_scan_strip(im, s, v);
 	}
