@@ -165,3 +165,73 @@ NHW_HD void y_offset_quant_row(const EncImg &im, int m1, int r, int next0)
 #define E16_SNAP_P_CELLS (258 * 512)
 #define E16_SNAP_L_OFF (260 * 512)
 #define E16_SNAP_L_CELLS (65536 + 1024)
+
+// ---- LL2 part of offsetY_recons256 (image_processing.c:2610-2737) in parallel form --------------
+// P = LL2 band at row stride PS (shared-memory copy), J = im_jpeg (stride 512).
+//   1. quad tagging: rows independent
+//   2. main loop: cell (r,j) reads (r,j..j+2),(r+1,j..j+2),(r+2,j),(r+3,j) and writes (r,j),(r,j+1),
+//      (r+1,j): the row above must be 3 columns ahead -> wavefront, skew 3
+//   3. second call only: un-tag + copy to jpeg (cells independent), then the highres_mem fix-ups
+NHW_HD WfGeom wf_ll2_geom() { return WfGeom{0, 128, 0, 128, 3}; }
+
+NHW_HD void y_recons_ll2_tag_row(int16_t *P, int PS, int r, int part)
+{
+	int a = r * PS;
+	for (int j = 0; j < 125; j++, a++) {
+		if (nhw_odd(P[a]) && nhw_odd(P[a + 1]) && nhw_odd(P[a + 2]) && nhw_odd(P[a + 3]) && nhw_iabs(P[a] - P[a + 3]) > 1) {
+			P[a] += 16000;
+			P[a + 2] += 16000;
+			if (!part) { P[a + 1] += 16000; P[a + 3] += 16000; }
+			j += 3;
+			a += 3;
+		}
+	}
+}
+
+// parity nudges shared by the recons pass and the LL2 -> bytes pass (same code in the reference)
+NHW_HD void ll2_parity_nudge(int16_t *P, int PS, int a, int r, int j, int v, int q)
+{
+	if (nhw_odd(v) && j > 0 && nhw_odd(P[a + 1])) {
+		if (j < 126 && nhw_odd(P[a + 2])) {
+			if (nhw_iabs(v - P[a + 2]) > 1 && q > 17) P[a + 1]++;
+		} else if (r < 127 && nhw_odd(P[a + PS]) && nhw_odd(P[a + PS + 1]) && !nhw_odd(P[a + PS + 2])) {
+			if (P[a + PS] < 10000 && q > 17) P[a + PS]++;
+		}
+	} else if (nhw_odd(v) && r >= 1 && r < 125) {
+		if (nhw_odd(P[a + PS]) && nhw_odd(P[a + PS + 1])) {
+			if (nhw_odd(P[a + 2 * PS]) && !nhw_odd(P[a + 3 * PS])) {
+				if (P[a + PS] < 10000 && q > 17) P[a + PS]++;
+			}
+		}
+	}
+}
+
+NHW_HD int y_recons_ll2_cell(int16_t *P, int PS, int16_t *J, int q, int part, int r, int j)
+{
+	const int a = r * PS + j, aj = r * YW + j;
+	if (P[a] > 10000) {
+		if (!part) { J[aj] = P[a]; return 1; }
+		P[a] -= 16000;
+		J[aj] = P[a];
+		J[aj + 1] = (P[a + 1] > 0 && P[a + 1] < 256) ? (int16_t)(P[a + 1] & 65534) : P[a + 1];
+		return 2;
+	}
+	ll2_parity_nudge(P, PS, a, r, j, P[a], q);
+	if (part) J[aj] = (P[a] > 0 && P[a] < 256) ? (int16_t)(P[a] & 65534) : P[a];
+	return 1;
+}
+
+NHW_HD void y_recons_ll2_tail_row(int16_t *P, int PS, int16_t *J, int16_t *tmp, int r)
+{
+	int a = r * PS, aj = r * YW, t = r * 128;
+	for (int j = 0; j < 128; j++, a++, aj++, t++) {
+		if (P[a] < 10000) {
+			tmp[t] = P[a];
+			J[aj] = (P[a] >= 0 && P[a] < 256) ? (int16_t)(P[a] & 65534) : P[a];
+		} else {
+			P[a] -= 16000;
+			tmp[t] = P[a];
+			J[aj] = P[a];
+		}
+	}
+}

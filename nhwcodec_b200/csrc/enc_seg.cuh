@@ -10,7 +10,7 @@
 // summary.  The functions are plain (no barriers/atomics inside) so the host harness can run
 // the identical per-segment logic sequentially; the kernels add the scans and atomics.
 #pragma once
-#include "enc_par.cuh"
+#include "enc_ll_par.cuh"
 
 #define SEG_THREADS 256
 

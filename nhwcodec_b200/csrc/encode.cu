@@ -186,6 +186,138 @@ __global__ void __launch_bounds__(32) k_ll2_staged(EncBatch b, F f)
 	}
 }
 
+// LL2 part of offsetY_recons256 in its parallel form (enc_par.cuh): band in shared memory,
+// thread = LL2 row; tagging rows -> wavefront (skew 3) -> second-call tail.
+__global__ void __launch_bounds__(128) k_recons_ll2_wave(EncBatch b, int q, int part)
+{
+	extern __shared__ __align__(16) int16_t sP[];
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int t = threadIdx.x;
+	for (int idx = t; idx < 128 * (LL2_PS / 2); idx += 128) {
+		const int r = idx / (LL2_PS / 2), c = idx % (LL2_PS / 2);
+		reinterpret_cast<uint32_t *>(sP + r * LL2_PS)[c] = reinterpret_cast<const uint32_t *>(im.proc + r * YW)[c];
+	}
+	__syncthreads();
+	if (q > 17) y_recons_ll2_tag_row(sP, LL2_PS, t, part);
+	__syncthreads();
+	const WfGeom g = wf_ll2_geom();
+	const int steps = g.cols + g.skew * (g.rows - 1);
+	int next = 0;
+	for (int s = 0; s < steps; s++) {
+		const int c = s - g.skew * t;
+		if (c >= 0 && c < g.cols && c == next) next = c + y_recons_ll2_cell(sP, LL2_PS, im.jpeg, q, part, t, c);
+		__syncthreads();
+	}
+	if (!part) {
+		y_recons_ll2_tail_row(sP, LL2_PS, im.jpeg, im.aux, t);
+		__syncthreads();
+		if (q > 15) {
+			const int n = im.hdr->highres_mem_len;
+			for (int k = t; k < n; k += 128) {
+				const int m = im.highres_mem[k];
+				im.jpeg[((m >> 7) << 9) + (m & 127)] = im.aux[m];
+			}
+		}
+	}
+	__syncthreads();
+	for (int idx = t; idx < 128 * 64; idx += 128) {
+		const int r = idx >> 6, c = idx & 63;
+		reinterpret_cast<uint32_t *>(im.proc + r * YW)[c] = reinterpret_cast<const uint32_t *>(sP + r * LL2_PS)[c];
+	}
+}
+
+// LL2 -> bytes + DPCM coding in parallel form (enc_ll_par.cuh), one CTA of 128 threads per image.
+// shared memory: band copy (later: output offsets), sample values (later: step links), res4 rows.
+#define LL2_CODE_SMEM (LL2_SMEM_BYTES + 16384 * 2 + 128 * 32 + 128 * 4 + 64)
+__global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
+{
+	extern __shared__ __align__(16) int16_t sP[];
+	int16_t *V = sP + 128 * LL2_PS;
+	uint8_t *r4 = reinterpret_cast<uint8_t *>(V + 16384);
+	int *n4 = reinterpret_cast<int *>(r4 + 128 * 32);
+	int *cnt = n4 + 128;            // [0] a8, [1] y16
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	EncHdr *h = im.hdr;
+	const int t = threadIdx.x;
+	for (int idx = t; idx < 128 * (LL2_PS / 2); idx += 128) {
+		const int r = idx / (LL2_PS / 2), c = idx % (LL2_PS / 2);
+		reinterpret_cast<uint32_t *>(sP + r * LL2_PS)[c] = reinterpret_cast<const uint32_t *>(im.proc + r * YW)[c];
+	}
+	if (t < 2) cnt[t] = 0;
+	__syncthreads();
+	n4[t] = q > 17 ? ll2_bytes_tag_row(sP, LL2_PS, t, r4 + t * 32) : 0;
+	__syncthreads();
+	{
+		const WfGeom g = wf_ll2_geom();
+		const int steps = g.cols + g.skew * (g.rows - 1);
+		for (int s = 0; s < steps; s++) {
+			const int c = s - g.skew * t;
+			if (c >= 0 && c < g.cols) ll2_bytes_cell(sP, LL2_PS, V, q, t, c);
+			__syncthreads();
+		}
+	}
+	for (int a = t; a < 16384; a += 128)
+		if (!ll2_is_escape(V[a], a)) ll2_bytes_store(im, a, V[a]);
+	__syncthreads();
+	if (t == 0) {
+		int e = 0;
+		for (int a = 1; a < 16384; a++)
+			if (ll2_is_escape(V[a], a)) ll2_bytes_escape(im, a, V[a], e);
+		h->exw_y_len = e;
+		if (q > 17) {
+			int n = 0;
+			for (int r = 0; r < 128; r++)
+				for (int k = 0; k < n4[r]; k++) im.res4[n++] = r4[r * 32 + k];
+			h->res4_len = n;
+		}
+	}
+	__syncthreads();
+	// ---- DPCM coder over the 16384 bytes just written (tree1)
+	const uint8_t *x = im.tree1;
+	uint16_t *info = reinterpret_cast<uint16_t *>(V);      // step link of every position
+	uint16_t *offs = reinterpret_cast<uint16_t *>(sP);     // output offset of the visited ones
+	{
+		int a8 = 0, y16 = 0;
+		for (int i = t + 1; i < 16384; i += 128)
+			if (x[i] == x[i - 1] && (i == 1 || x[i - 1] != x[i - 2])) ll_stats_run(x, i, 16384, a8, y16);
+		if (a8) atomicAdd(&cnt[0], a8);
+		if (y16) atomicAdd(&cnt[1], y16);
+	}
+	__syncthreads();
+	const int mode = cnt[1] > 299 ? 2 : (cnt[0] + cnt[1] > 179 ? 1 : 0);
+	for (int i = t; i < 16384; i += 128) {
+		offs[i] = 0xFFFF;
+		if (i >= 1) {
+			const LlStep s = ll_dpcm_step(x, i, mode, q);
+			info[i] = (uint16_t)(((s.next - i) << 2) | ((s.nbytes - 1) << 1) | s.raw);
+		}
+	}
+	__syncthreads();
+	if (t == 0) {
+		int off = 1, nmem = 0;
+		for (int i = 1; i < 16384;) {
+			const int inf = info[i];
+			offs[i] = (uint16_t)off;
+			off += 1 + ((inf >> 1) & 1);
+			if (inf & 1) { im.highres_word[nmem] = im.ch_res[i]; im.highres_mem[nmem++] = (uint16_t)i; }
+			i += inf >> 2;
+		}
+		im.llcode[0] = x[0];
+		h->highres_comp_len = nmem;
+		h->highres_mem_len = nmem;
+		h->res_low = mode;
+		h->y_res_comp = off;
+	}
+	__syncthreads();
+	for (int i = t + 1; i < 16384; i += 128) {
+		const int off = offs[i];
+		if (off == 0xFFFF) continue;
+		const LlStep s = ll_dpcm_step(x, i, mode, q);
+		im.llcode[off] = s.b[0];
+		if (s.nbytes == 2) im.llcode[off + 1] = s.b[1];
+	}
+}
+
 template <typename F>
 void run_ll2_staged(nhw_ctx *c, const char *label, const EncBatch &b, int n, size_t smem, F f)
 {
@@ -614,9 +746,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- luma closed loop (nhw_encoder.c:141-283)
 	run_rows(c, "y_e6a_tag", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });
-	run_ll2_staged(c, "y_recons1_ll2", b, n, LL2_SMEM_BYTES, [=] __device__(const EncImg &im, int16_t *sP) {
-		y_recons_ll2_core(sP, LL2_PS, im.jpeg, im.aux, im.highres_mem, 0, q, 1);
-	});
+	NHW_LAUNCH_L(c, "y_recons1_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 1);
 	for (int reg = 0; reg < 2; reg++)
 		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
@@ -628,22 +758,16 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- LL2 coding (nhw_encoder.c:623-757)
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
-	// LL2 -> bytes on the staged band; then the band's shared memory is reused for the byte list
-	// (16384 + zero tail) and the marked code the DPCM coder strips afterwards
-	run_ll2_staged(c, "y_ll2_code", b, n, 48 * 1024, [=] __device__(const EncImg &im, int16_t *sP) {
-		y_ll2_to_bytes_core(im, sP, LL2_PS, q);
-		uint8_t *x = reinterpret_cast<uint8_t *>(sP);          // 16448 bytes
-		uint8_t *work = x + 16448;                              // 24704 bytes (48 KB - 16448 - slack)
-		for (int i = 0; i < 16384; i++) x[i] = im.tree1[i];
-		for (int i = 16384; i < 16448; i++) x[i] = 0;
-		ll_dpcm_luma_core(im, x, work, q);
-	});
+	// LL2 -> bytes (wavefront) and the DPCM coder (step links + chain walk), see enc_ll_par.cuh
+	{
+		static bool attr = false;
+		if (!attr) { cudaFuncSetAttribute(k_ll2_code, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_CODE_SMEM); attr = true; }
+		NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
+	}
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_ll2s, CS, 256, b.y_proc, YS, 512, 256);
 
 	// ---- second reconstruction = what the decoder will see as LL1 (nhw_encoder.c:759-781)
-	run_ll2_staged(c, "y_recons0_ll2", b, n, LL2_SMEM_BYTES, [=] __device__(const EncImg &im, int16_t *sP) {
-		y_recons_ll2_core(sP, LL2_PS, im.jpeg, im.aux, im.highres_mem, im.hdr->highres_mem_len, q, 0);
-	});
+	NHW_LAUNCH_L(c, "y_recons0_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 0);
 	for (int reg = 0; reg < 2; reg++)
 		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });

@@ -232,6 +232,46 @@ void host_wavefront(WfGeom g, Cell cell)
 		}
 }
 
+// parallel form of the LL2 part of offsetY_recons256, on the plane itself (PS = 512)
+void host_recons_ll2(const EncImg &im, int q, int part)
+{
+	int16_t *P = im.proc, *J = im.jpeg;
+	if (q > 17) for (int r = 127; r >= 0; r--) y_recons_ll2_tag_row(P, 512, r, part);
+	host_wavefront(wf_ll2_geom(), [&](int r, int j) { return y_recons_ll2_cell(P, 512, J, q, part, r, j); });
+	if (!part) {
+		for (int r = 127; r >= 0; r--) y_recons_ll2_tail_row(P, 512, J, im.aux, r);
+		if (q > 15)
+			for (int k = im.hdr->highres_mem_len - 1; k >= 0; k--) {
+				const int m = im.highres_mem[k];
+				J[((m >> 7) << 9) + (m & 127)] = im.aux[m];
+			}
+	}
+}
+
+// parallel form of LL2 -> bytes + DPCM coding (enc_ll_par.cuh), on the plane itself
+void host_ll2_code(const EncImg &im, int q)
+{
+	int16_t *P = im.proc;
+	std::vector<int16_t> V(16384);
+	std::vector<uint8_t> r4(128 * 32);
+	std::vector<int> n4(128, 0);
+	if (q > 17) for (int r = 127; r >= 0; r--) n4[r] = ll2_bytes_tag_row(P, 512, r, &r4[r * 32]);
+	host_wavefront(wf_ll2_geom(), [&](int r, int j) { return ll2_bytes_cell(P, 512, V.data(), q, r, j); });
+	for (int a = 16383; a >= 0; a--)
+		if (!ll2_is_escape(V[a], a)) ll2_bytes_store(im, a, V[a]);
+	int e = 0;
+	for (int a = 0; a < 16384; a++)
+		if (ll2_is_escape(V[a], a)) ll2_bytes_escape(im, a, V[a], e);
+	im.hdr->exw_y_len = e;
+	if (q > 17) {
+		int n = 0;
+		for (int r = 0; r < 128; r++)
+			for (int k = 0; k < n4[r]; k++) im.res4[n++] = r4[r * 32 + k];
+		im.hdr->res4_len = n;
+	}
+	ll_dpcm_luma_steps(im, im.tree1, q);
+}
+
 void host_e16(const EncImg &im, int q)
 {
 	memcpy(im.aux, im.proc, E16_SNAP_P_CELLS * sizeof(int16_t));
@@ -358,7 +398,7 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	T("y_ll1", im.ll1, 65536 * 2);
 	for (int r = 255; r >= 0; r--) y_e6a_tag_row(im, r);
 	T("y_e6a_ll1", im.ll1, 65536 * 2);
-	y_recons_ll2_image(im, q, 1);
+	host_recons_ll2(im, q, 1);
 	for (int reg = 0; reg < 2; reg++)
 		host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
 	for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 1);
@@ -373,15 +413,15 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	fwd_level(im.jpeg, 512, false, im.proc, 512, 256, tmp);
 	T("y_dwt2b_proc", im.proc, 512 * 512 * 2);
 	copy_region(im.ll2s, 256, im.proc, 512, 256);
-	y_ll2_to_bytes_image(im, q);
+	if (getenv("HE_SERIAL")) y_ll2_to_bytes_image(im, q); else host_ll2_code(im, q);
 	T("y_e11_tree1", im.tree1, 16384);
 	T("y_e11_chres", im.ch_res, 16384);
 	T("y_e11_exw", im.exw, h->exw_y_len);
 	T("y_e11_res4", im.res4, h->res4_len);
-	ll_dpcm_luma_image(im, q);
+	if (getenv("HE_SERIAL")) ll_dpcm_luma_image(im, q);
 	T("y_e12_chres", im.llcode, h->y_res_comp);
 	copy_region(im.proc, 512, im.ll2s, 256, 256);
-	y_recons_ll2_image(im, q, 0);
+	host_recons_ll2(im, q, 0);
 	for (int reg = 0; reg < 2; reg++)
 		host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
 	for (int r = 255; r >= 0; r--) y_recons_tag57_row(im, r);
