@@ -284,6 +284,30 @@ def run_ours(args):
     ms_max = float(t.item())
     value = world * B * args.steps * PIX / (ms_max / 1e3) / 1e6
 
+    # ---------------- N>1 only: assemble all ranks' streams on rank 0 (the one exchange step) ----------------
+    gather = None
+    if dist is not None:
+        from nhwcodec_b200 import shard
+        lens_h = lens.cpu().numpy().astype(np.int64)
+        o = np.concatenate([[0], np.cumsum(lens_h)])
+        dense = torch.empty(int(o[-1]), dtype=torch.uint8, device="cuda")
+        for i in range(B):
+            dense[int(o[i]): int(o[i + 1])] = out[i, : int(lens_h[i])]
+        shard.gather_streams(dense, lens, world * B)            # warm-up (NCCL connection set-up)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        allb, alloffs = shard.gather_streams(dense, lens, world * B)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        total_bytes = int(alloffs[-1].item())
+        gather = {"what": "lengths all-gather + point-to-point stream assembly on rank 0 (NCCL), not part of `value`",
+                  "ms": round(float(tg.item()), 3), "bytes_total": total_bytes,
+                  "GBps_into_rank0": round((total_bytes - int(o[-1])) / (float(tg.item()) / 1e3) / 1e9, 2)}
+        del dense, allb
+
     # ---------------- end to end through the host-buffer C-ABI (e2e) ----------------
     rgb_host = torch.empty((B, PIX_BYTES), dtype=torch.uint8, pin_memory=True)
     rgb_host.copy_(rgb)
@@ -395,7 +419,8 @@ def run_ours(args):
             "frontend": frontend,
             "cpu_baseline": cpu,
             "decode": dec,
-            "kernels": kernels[:16],
+            "gather": gather,
+            "kernels": kernels[:40],
         }
         print(json.dumps(line), flush=True)
     codec.close()
