@@ -123,6 +123,10 @@ long nhw_profile_read(nhw_ctx *ctx, char *buf, size_t cap);
  * what: proc jpeg aux ll1 ll2s cproc_u cproc_v cjpeg_u cjpeg_v scan tree1 llcode hdr */
 int nhw_debug_stop_after(nhw_ctx *ctx, const char *label, int occurrence);
 int nhw_debug_read(nhw_ctx *ctx, const char *what, int img, void *host, size_t bytes);
+/* Runs all 2^24 RGB triples through the integer form of the q>=20 colour transform used by the
+ * fused front end and through the IEEE double/float form of encoder/colorspace.c:71-99;
+ * returns the number of triples on which they differ (must be 0), or a negative error. */
+long nhw_debug_color_check(nhw_ctx *ctx);
 
 #ifdef __cplusplus
 }

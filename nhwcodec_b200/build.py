@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnhw_cuda.so")
-SOURCES = ["api.cu", "front.cu", "synth.cu", "encode.cu", "decode.cu"]
+SOURCES = ["api.cu", "front.cu", "front_fused.cu", "synth.cu", "encode.cu", "decode.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # integer/IEEE-exact pipeline: never contract a*b+c

@@ -19,7 +19,7 @@ EXPORTS = [
     "nhw_create", "nhw_destroy", "nhw_last_error", "nhw_version", "nhw_encode_batch",
     "nhw_encode_batch_device", "nhw_decode_batch", "nhw_decode_batch_planes", "nhw_stage_frontend_device",
     "nhw_stage_colorspace_device", "nhw_synth_batch_device", "nhw_launch_count",
-    "nhw_stream", "nhw_profile", "nhw_profile_read", "nhw_debug_stop_after", "nhw_debug_read",
+    "nhw_stream", "nhw_profile", "nhw_profile_read", "nhw_debug_stop_after", "nhw_debug_read", "nhw_debug_color_check",
 ]
 
 _lib = None
@@ -67,6 +67,8 @@ def load_library():
     L.nhw_debug_stop_after.restype = i32
     L.nhw_debug_read.argtypes = [vp, ctypes.c_char_p, i32, vp, ctypes.c_size_t]
     L.nhw_debug_read.restype = i32
+    L.nhw_debug_color_check.argtypes = [vp]
+    L.nhw_debug_color_check.restype = ctypes.c_long
     L.nhw_profile.argtypes = [vp, i32]
     L.nhw_profile.restype = i32
     L.nhw_profile_read.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
@@ -126,6 +128,10 @@ class Codec:
         a = np.zeros(count, dtype=dtype)
         self._check(self.lib.nhw_debug_read(self.h, what.encode(), img, a.ctypes.data, a.nbytes), "debug_read")
         return a
+
+    def color_check(self):
+        """mismatches between the integer and the IEEE colour transform over all 2^24 triples"""
+        return int(self.lib.nhw_debug_color_check(self.h))
 
     def profile(self, mode):
         """0 off, 1 on, 2 on + reset"""

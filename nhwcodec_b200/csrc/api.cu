@@ -216,6 +216,13 @@ int nhw_debug_read(nhw_ctx *c, const char *what, int img, void *host, size_t byt
 	return check(cudaMemcpy(host, src, bytes, cudaMemcpyDeviceToHost), "nhw_debug_read") ? NHW_OK : NHW_ERR_CUDA;
 }
 
+long nhw_debug_color_check(nhw_ctx *c)
+{
+	if (!c) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	return nhw::color_fast_path_mismatches(c);
+}
+
 int nhw_profile(nhw_ctx *c, int enable)
 {
 	if (!c) return NHW_ERR_ARG;
@@ -282,19 +289,14 @@ int nhw_stage_frontend_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int qua
 	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT, QS = NHW_Q_SLOT;
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
 		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
-		int16_t *yj = c->y_jpeg + NHW_GUARD_S;
-		nhw::colorspace(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, yj, YS, c->c_u8, c->c_u8 + NHW_CPLANE,
-		                (size_t)2 * NHW_CPLANE);
-		if (quality < 22) nhw::pre_processing(c, m, quality, yj, YS);
 		// with caller buffers the planes are dense; otherwise they land in the context workspace
 		int16_t *yp = y_proc ? y_proc + (size_t)i0 * NHW_YPLANE : c->y_proc + NHW_GUARD_S;
 		int16_t *yl = y_ll1 ? y_ll1 + (size_t)i0 * NHW_CPLANE : c->y_ll1 + NHW_GUARD_S;
-		nhw::dwt_luma(c, m, yj, YS, yp, y_proc ? (size_t)NHW_YPLANE : YS, yl, y_ll1 ? (size_t)NHW_CPLANE : CS);
-		int16_t *cj = c->c_jpeg + NHW_GUARD_S;
-		nhw::chroma_to_short(c, 2 * m, c->c_u8, NHW_CPLANE, cj, CS);
 		int16_t *cp = c_proc ? c_proc + (size_t)i0 * 2 * NHW_CPLANE : c->c_proc + NHW_GUARD_S;
 		int16_t *cl = c_ll1 ? c_ll1 + (size_t)i0 * 2 * 16384 : c->c_ll1 + NHW_GUARD_S;
-		nhw::dwt_chroma(c, 2 * m, cj, CS, cp, c_proc ? (size_t)NHW_CPLANE : CS, cl, c_ll1 ? (size_t)16384 : QS);
+		nhw::front_fused(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, yp, y_proc ? (size_t)NHW_YPLANE : YS, yl,
+		                 y_ll1 ? (size_t)NHW_CPLANE : CS, c->c_u8, cp, c_proc ? (size_t)NHW_CPLANE : CS, cl,
+		                 c_ll1 ? (size_t)16384 : QS);
 	}
 	return finish(c, "nhw_stage_frontend_device");
 }

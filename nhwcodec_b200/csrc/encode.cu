@@ -737,12 +737,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_image(c, "init_hdr", b, n, [=] __device__(const EncImg &im, int) { im.hdr->quality = q; });
 
 	// ---- front end: colour, 4:2:0, pre-sharpening, two analysis levels (front.cu)
-	uint8_t *u8 = c->c_u8;
-	colorspace(c, rgb, n, q, b.y_jpeg, YS, u8, u8 + NHW_CPLANE, (size_t)2 * NHW_CPLANE);
-	if (q < 22) pre_processing(c, n, q, b.y_jpeg, YS);
-	dwt_luma(c, n, b.y_jpeg, YS, b.y_proc, YS, b.y_ll1, CS);
-	chroma_to_short(c, 2 * n, u8, NHW_CPLANE, b.c_jpeg, CS);
-	dwt_chroma(c, 2 * n, b.c_jpeg, CS, b.c_proc, CS, b.c_ll1, QS);
+	front_fused(c, rgb, n, q, b.y_proc, YS, b.y_ll1, CS, c->c_u8, b.c_proc, CS, b.c_ll1, QS);
 
 	// ---- luma closed loop (nhw_encoder.c:141-283)
 	run_rows(c, "y_e6a_tag", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });

@@ -56,11 +56,10 @@ namespace nhw {
 void colorspace(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y, size_t ystride, uint8_t *u, uint8_t *v,
                 size_t cstride);
 void pre_processing(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystride);
-void dwt_luma(nhw_ctx *c, int n, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride, int16_t *ll1,
-              size_t lstride);
-void chroma_to_short(nhw_ctx *c, int n_planes, const uint8_t *u8, size_t in_stride, int16_t *jpeg, size_t out_stride);
-void dwt_chroma(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
-                int16_t *ll1, size_t lstride);
+// front_fused.cu
+void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_proc, size_t ypstride, int16_t *y_ll1,
+                 size_t ylstride, uint8_t *uv_bytes, int16_t *c_proc, size_t cpstride, int16_t *c_ll1, size_t clstride);
+long color_fast_path_mismatches(nhw_ctx *c);
 void dwt_level_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
                          int N, int row_stride);
 

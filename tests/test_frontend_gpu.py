@@ -39,6 +39,12 @@ def test_colorspace(codec, ref, q):
         assert np.array_equal(v[i].cpu().numpy(), V), (q, i, "V")
 
 
+def test_color_fast_path_exhaustive(codec):
+    """the fused front end's integer q>=20 colour transform == the IEEE form (itself checked against
+    the reference above) on every one of the 2^24 RGB triples"""
+    assert codec.color_check() == 0
+
+
 @pytest.mark.parametrize("q", [20, 17, 21])
 def test_pre_processing(codec, ref, q):
     import torch
