@@ -66,3 +66,35 @@ __device__ __forceinline__ void rgb_to_ycc_q20(int c0, int c1, int c2, int &Y, i
 	U = U > 255 ? 255 : U;
 	V = V > 255 ? 255 : V;
 }
+
+// four pixels at once: one branch for the (rare) exact-tie case instead of one per pixel;
+// uv[k] = U | V << 16
+__device__ __forceinline__ void rgb4_to_ycc_q20(const int (&c0)[4], const int (&c1)[4], const int (&c2)[4], int (&Y)[4],
+                                                uint32_t (&uv)[4])
+{
+	uint32_t rem[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const uint32_t s = 299u * c0[k] + 587u * c1[k] + 114u * c2[k] + 500u;
+		const uint32_t q = __umulhi(s, 0x10624dd3u) >> 6;
+		Y[k] = (int)q;
+		rem[k] = s - 1000u * q;
+		const int eu = -1687 * c0[k] - 3313 * c1[k] + 5000 * c2[k];
+		const int ev = 5000 * c0[k] - 4187 * c1[k] - 813 * c2[k];
+		const uint32_t vu = (uint32_t)(eu + (eu >= 0 ? 1285000 : 1284000));
+		const uint32_t vv = (uint32_t)(ev + (ev >= 0 ? 1285000 : 1284000));
+		const uint32_t U = min(__umulhi(vu, 0xD1B71759u) >> 13, 255u);
+		const uint32_t V = min(__umulhi(vv, 0xD1B71759u) >> 13, 255u);
+		uv[k] = U | (V << 16);
+	}
+	if (rem[0] == 0u || rem[1] == 0u || rem[2] == 0u || rem[3] == 0u) {
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if (rem[k] == 0u) {
+				const double d0 = (double)c0[k], d1 = (double)c1[k], d2 = (double)c2[k];
+				const double t = __dadd_rn(__dadd_rn(__dmul_rn(0.299, d0), __dmul_rn(0.587, d1)), __dmul_rn(0.114, d2));
+				Y[k] = __double2int_rz(__dadd_rn(t, 0.5));
+			}
+		}
+	}
+}

@@ -9,8 +9,9 @@
 #pragma once
 #include "enc_img.cuh"
 
-// symmetric rounding division by 2^sh: v>=0 ? (v+half)>>sh : -((-v+half)>>sh)
-NHW_HD int nhw_sround(int v, int half, int sh) { return v >= 0 ? ((v + half) >> sh) : -((-v + half) >> sh); }
+// symmetric rounding division by 2^sh (half = 2^(sh-1)): v>=0 ? (v+half)>>sh : -((-v+half)>>sh).
+// For v<0 that is ceil((v-half)/2^sh) = (v+half-1)>>sh, hence the branch-free form.
+NHW_HD int nhw_sround(int v, int half, int sh) { return (v + half + (v >> 31)) >> sh; }
 NHW_HD int nhw_iabs(int v) { return v < 0 ? -v : v; }
 
 // 5-tap low of every forward filter, mirror extension x[-1]=x[1], x[-2]=x[2], x[N]=x[N-2]

@@ -45,7 +45,10 @@ struct __align__(128) FrontSmem {
 	uint8_t rgb[RGB_ROWS * 1536];        // TMA destination, rows of the current strip
 	uint8_t yring[RING][512];            // luma bytes, row y at slot y % RING
 	uint8_t uvh[2][RING][256];           // horizontally filtered U / V at even pixels
-	int16_t rring[RING][512];            // horizontal-pass output R[y][k]
+	int16_t rring[RING + 19][512];       // horizontal-pass output R[y][k]; slots 0..18 are mirrored at
+	                                     // RING..RING+18 so a 19-row window never wraps
+	uint16_t plut[PAIR_CATS * PAIR_CATS + 1];   // pair rule tables (pre_core.cuh)
+	uint8_t pcat[512];
 	uint32_t rowmap_lo[16], rowmap_hi[16];   // class map of each row of the strip
 	uint32_t part_lo[16], part_hi[16];       // class map of the row up to x = 508
 	int e509[16], e510[16];                  // signed energies of the row's last pair
@@ -53,6 +56,9 @@ struct __align__(128) FrontSmem {
 	int strip_flag[2];                       // pair flag left behind by the row above strip i
 	unsigned long long mbar;
 };
+
+__device__ uint8_t g_pair_cat[512];
+__device__ uint16_t g_pair_lut[PAIR_CATS * PAIR_CATS];
 
 // ---- mbarrier / bulk-copy primitives (sm_90+ PTX) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,7 +137,7 @@ __device__ __forceinline__ uint32_t pack2(int a, int b) { return (uint32_t)(uint
 
 // horizontal filter of one row held as 16 values per lane (x[0..15] = columns 16*lane..),
 // written to R[0..255] (low) and R[256..511] (high).  downfilter53IV, encoder/filters.c:346-386.
-__device__ __forceinline__ void row_pass_regs(const int (&x)[16], int lane, int16_t *R)
+__device__ __forceinline__ void row_pass_regs(const int (&x)[16], int lane, int16_t *R, bool mirror)
 {
 	int xm2 = __shfl_up_sync(0xffffffffu, x[14], 1), xm1 = __shfl_up_sync(0xffffffffu, x[15], 1);
 	int xp = __shfl_down_sync(0xffffffffu, x[0], 1);
@@ -150,6 +156,10 @@ __device__ __forceinline__ void row_pass_regs(const int (&x)[16], int lane, int1
 	uint4 H = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
 	reinterpret_cast<uint4 *>(R)[lane] = L;
 	reinterpret_cast<uint4 *>(R + 256)[lane] = H;
+	if (mirror) {
+		reinterpret_cast<uint4 *>(R + RING * 512)[lane] = L;
+		reinterpret_cast<uint4 *>(R + RING * 512 + 256)[lane] = H;
+	}
 }
 
 __device__ __forceinline__ void unpack16(const uint4 &w, int (&x)[16])
@@ -212,6 +222,8 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 		S.strip_carry[0] = 0;
 		S.strip_flag[0] = 0;
 	}
+	S.pcat[tid] = g_pair_cat[tid];
+	if (tid < PAIR_CATS * PAIR_CATS) S.plut[tid] = g_pair_lut[tid];
 	__syncthreads();
 	if (tid == 0) bulk_load(S.rgb, src, RGB_ROWS * 1536, &S.mbar);
 
@@ -241,32 +253,31 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 				c0[1] = w0 >> 24; c1[1] = w1 & 255u; c2[1] = (w1 >> 8) & 255u;
 				c0[2] = (w1 >> 16) & 255u; c1[2] = w1 >> 24; c2[2] = w2 & 255u;
 				c0[3] = (w2 >> 8) & 255u; c1[3] = (w2 >> 16) & 255u; c2[3] = w2 >> 24;
-				int Y[4], U[4], V[4];
+				int Y[4];
+				uint32_t uv[4];   // U | V << 16
+				if (cp.mode == 0) {
+					rgb4_to_ycc_q20(c0, c1, c2, Y, uv);
+				} else {
 #pragma unroll
-				for (int k = 0; k < 4; k++) {
-					if (cp.mode == 0) rgb_to_ycc_q20(c0[k], c1[k], c2[k], Y[k], U[k], V[k]);
-					else rgb_to_ycc(c0[k], c1[k], c2[k], cp, Y[k], U[k], V[k]);
+					for (int k = 0; k < 4; k++) {
+						int U, V;
+						rgb_to_ycc(c0[k], c1[k], c2[k], cp, Y[k], U, V);
+						uv[k] = (uint32_t)U | ((uint32_t)V << 16);
+					}
 				}
 				reinterpret_cast<uint32_t *>(yrow)[step * 32 + lane] =
 				    (uint32_t)Y[0] | ((uint32_t)Y[1] << 8) | ((uint32_t)Y[2] << 16) | ((uint32_t)Y[3] << 24);
-				// [1 2 1]/4 on even pixels (colorspace.c:220-234); the pixel left of the lane comes
-				// from the neighbour lane, or from lane 31 of the previous step
-				const uint32_t mine = (uint32_t)U[3] | ((uint32_t)V[3] << 8);
-				uint32_t left = __shfl_up_sync(0xffffffffu, mine, 1);
+				// [1 2 1]/4 on even pixels (colorspace.c:220-234), U and V side by side in 16-bit
+				// halves; the pixel left of the lane comes from the neighbour lane, or from lane 31
+				// of the previous step
+				uint32_t left = __shfl_up_sync(0xffffffffu, uv[3], 1);
 				if (lane == 0) left = edge;
-				edge = __shfl_sync(0xffffffffu, mine, 31);
-				const int ul = left & 255u, vl = (left >> 8) & 255u;
-				int ua, va;
-				if (step == 0 && lane == 0) {
-					ua = (U[0] + U[1] + 1) >> 1;
-					va = (V[0] + V[1] + 1) >> 1;
-				} else {
-					ua = (ul + 2 * U[0] + U[1] + 2) >> 2;
-					va = (vl + 2 * V[0] + V[1] + 2) >> 2;
-				}
-				const int ub = (U[1] + 2 * U[2] + U[3] + 2) >> 2, vb = (V[1] + 2 * V[2] + V[3] + 2) >> 2;
-				reinterpret_cast<uint16_t *>(urow)[step * 32 + lane] = (uint16_t)(ua | (ub << 8));
-				reinterpret_cast<uint16_t *>(vrow)[step * 32 + lane] = (uint16_t)(va | (vb << 8));
+				edge = __shfl_sync(0xffffffffu, uv[3], 31);
+				uint32_t fa = ((left + 2u * uv[0] + uv[1] + 0x00020002u) >> 2) & 0x00ff00ffu;
+				if (step == 0 && lane == 0) fa = ((uv[0] + uv[1] + 0x00010001u) >> 1) & 0x00ff00ffu;
+				const uint32_t fb = ((uv[1] + 2u * uv[2] + uv[3] + 0x00020002u) >> 2) & 0x00ff00ffu;
+				reinterpret_cast<uint16_t *>(urow)[step * 32 + lane] = (uint16_t)__byte_perm(fa, fb, 0x0040);
+				reinterpret_cast<uint16_t *>(vrow)[step * 32 + lane] = (uint16_t)__byte_perm(fa, fb, 0x0062);
 			}
 		}
 		__syncthreads();
@@ -402,21 +413,26 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 				}
 				if (warp == 15 && lane == 31) S.strip_carry[(i + 1) & 1] = cin;
 				const int knext = __shfl_down_sync(0xffffffffu, K[0], 1);
-				const int my_last_flag = pair_flag(K[15], knext);
-				int a = __shfl_up_sync(0xffffffffu, my_last_flag, 1);
+				// pair rule through its tables: interval of each value, then one entry per pair
+				int cat[17];
+#pragma unroll
+				for (int t = 1; t < 17; t++) {
+					const int kv = t < 16 ? K[t] : knext;
+					cat[t] = S.pcat[max(min(kv, 255), -255) + 256];
+				}
+				uint32_t ent[8];
+#pragma unroll
+				for (int p = 0; p < 8; p++) ent[p] = S.plut[cat[1 + 2 * p] * PAIR_CATS + cat[2 + 2 * p]];
+				if (lane == 31) ent[7] = 0x92u;   // there is no pair (511, 512)
+				int a = __shfl_up_sync(0xffffffffu, (int)(ent[7] >> 9), 1);
 				if (lane == 0) a = flag;
-				if (warp == 15 && lane == 31) S.strip_flag[(i + 1) & 1] = pair_flag(K[13], K[14]);
+				if (warp == 15 && lane == 31) S.strip_flag[(i + 1) & 1] = (int)(ent[6] >> 9);
 				int d[17];
-				d[0] = 0;
 #pragma unroll
 				for (int p = 0; p < 8; p++) {
-					const int res = K[1 + 2 * p], cnt = p < 7 ? K[2 + 2 * p] : knext;
-					int d0 = 0, d1 = 0;
-					const bool live = !(p == 7 && lane == 31);
-					if (live && (nhw_iabs(res) > 10 || nhw_iabs(cnt) > 10)) pair_nudge(res, cnt, a, d0, d1);
-					d[1 + 2 * p] = d0;
-					d[2 + 2 * p] = d1;
-					a = pair_flag(res, cnt);
+					d[1 + 2 * p] = (int)((ent[p] >> (3 * a)) & 7u) - 2;
+					d[2 + 2 * p] = (int)((ent[p] >> 6) & 7u) - 2;
+					a = (int)(ent[p] >> 9);
 				}
 				const int dprev = __shfl_up_sync(0xffffffffu, d[16], 1);
 				d[0] = lane ? dprev : 0;
@@ -426,10 +442,10 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 			} else {
 				unpack16(reinterpret_cast<const uint4 *>(S.yring[r % RING])[lane], x);
 			}
-			row_pass_regs(x, lane, S.rring[r % RING]);
+			row_pass_regs(x, lane, S.rring[r % RING], r % RING < 19);
 			if (i == 0 && warp == 0) {   // row 0 is outside the sharpening window
 				unpack16(reinterpret_cast<const uint4 *>(S.yring[0])[lane], x);
-				row_pass_regs(x, lane, S.rring[0]);
+				row_pass_regs(x, lane, S.rring[0], true);
 			}
 		}
 		__syncthreads();
@@ -438,13 +454,11 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 		{
 			const int k = tid, e0 = 8 * i;
 			int col[19];
+			const int16_t *win = &S.rring[(16 * i + RING - 2) % RING][k];   // rows 16i-2 .. 16i+16, never wraps
 #pragma unroll
-			for (int j = 0; j < 19; j++) {
-				int y = 16 * i - 2 + j;
-				if (y < 0) y = -y;
-				if (y > 511) y = 510;
-				col[j] = S.rring[y % RING][k];
-			}
+			for (int j = 0; j < 19; j++) col[j] = win[j * 512];
+			if (i == 0) { col[0] = col[4]; col[1] = col[3]; }   // rows -2, -1 mirror rows 2, 1
+			if (i == 31) col[18] = col[16];                     // row 512 mirrors row 510
 			int lo[8], hi[8];
 			const bool fine = k < 256;
 			col_pass8(col, e0, fine, i == 31, v_rem, lo, hi);
@@ -595,6 +609,16 @@ void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_
 	if (!attr) {
 		cudaFuncSetAttribute(k_front_luma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem));
 		attr = true;
+	}
+	static bool tables[64] = {false};
+	if (!tables[c->device & 63]) {
+		static uint8_t cat[512];
+		static uint16_t lut[PAIR_CATS * PAIR_CATS];
+		pair_build_tables(cat, lut);
+		cudaMemcpyToSymbolAsync(g_pair_cat, cat, sizeof(cat), 0, cudaMemcpyHostToDevice, c->stream);
+		cudaMemcpyToSymbolAsync(g_pair_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, c->stream);
+		cudaStreamSynchronize(c->stream);
+		tables[c->device & 63] = true;
 	}
 	const ColorParams p = color_params(quality);
 	NHW_LAUNCH_L(c, "k_front_luma", k_front_luma, n, FT, sizeof(FrontSmem), rgb, y_proc, ypstride, y_ll1, ylstride, uv_bytes,

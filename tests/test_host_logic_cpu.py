@@ -1,0 +1,14 @@
+"""CPU checks of closed forms / tables the CUDA kernels use in place of the reference's branchy rules
+(tests/hostcheck/check_tables.cpp compiles the shared headers with g++ and compares both forms)."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_tables_match_branchy_rules(tmp_path):
+    exe = str(tmp_path / "check_tables")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "hostcheck", "check_tables.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "sround mismatches 0" in out.stdout and "pair table mismatches 0" in out.stdout
