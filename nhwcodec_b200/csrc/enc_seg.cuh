@@ -14,41 +14,76 @@
 
 #define SEG_THREADS 256
 
+// Zero runs are measured on a bitmap of the stream (bit set = byte is not the zero symbol 128)
+// instead of byte by byte: the streams are mostly zeros and a run of a thousand zeros is 32 words.
+struct NzBits {
+	const uint32_t *w;      // bit k of word j describes stream byte p1 + 32*j + k
+	int p1, n;              // first stream position covered, number of bits (multiple of 32)
+};
+
+NHW_HD int nhw_ctz(uint32_t m)
+{
+#ifdef __CUDA_ARCH__
+	return __ffs((int)m) - 1;
+#else
+	return __builtin_ctz(m);
+#endif
+}
+NHW_HD int nhw_clz(uint32_t m)
+{
+#ifdef __CUDA_ARCH__
+	return __clz((int)m);
+#else
+	return __builtin_clz(m);
+#endif
+}
+
+// nonzero mask of 4 stream bytes packed in a word -> 4 bits
+NHW_HD uint32_t nz_mask4(uint32_t w)
+{
+	const uint32_t x = w ^ 0x80808080u;
+	const uint32_t t = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) >> 7;   // 0x01 per nonzero byte
+	return ((t * 0x00204081u) >> 21) & 15u;
+}
+
+// first position >= i (i >= p1) holding a non-zero byte, `end` if there is none before it
+NHW_HD int nz_next(const NzBits &b, int i, int end)
+{
+	const int k = i - b.p1, nw = b.n >> 5;
+	if (k >= b.n) return end;
+	int wi = k >> 5;
+	uint32_t m = b.w[wi] & (0xffffffffu << (k & 31));
+	while (!m) {
+		if (++wi >= nw) return end;
+		m = b.w[wi];
+	}
+	const int r = b.p1 + (wi << 5) + nhw_ctz(m);
+	return r < end ? r : end;
+}
+
+// last position <= i holding a non-zero byte, p1 - 1 if there is none
+NHW_HD int nz_prev(const NzBits &b, int i)
+{
+	const int k = i - b.p1;
+	if (k < 0) return b.p1 - 1;
+	int wi = k >> 5;
+	uint32_t m = b.w[wi] & (0xffffffffu >> (31 - (k & 31)));
+	while (!m) {
+		if (--wi < 0) return b.p1 - 1;
+		m = b.w[wi];
+	}
+	return b.p1 + (wi << 5) + 31 - nhw_clz(m);
+}
+
 struct SegStream {
 	const uint8_t *s;       // whole scan buffer (im.scan)
 	int p1, p2;             // [p1, p2) is the stream
 	int S;                  // segment size, (p2-p1)/SEG_THREADS
-	const uint16_t *first_nz;   // per segment: offset of its first non-128 byte, S if none
+	NzBits nz;              // non-zero bitmap of [p1, p2)
 };
 
-NHW_HD int seg_first_nz(const uint8_t *s, int start, int S)
-{
-	int k = 0;
-	while (k < S && s[start + k] == 128) k++;
-	return k;
-}
-
 // number of consecutive 128s starting at i (s[i]==128), never past p2
-NHW_HD int seg_run_len(const SegStream &st, int i)
-{
-	int seg = (i - st.p1) / st.S;
-	const int seg_end = st.p1 + (seg + 1) * st.S;
-	int k = i;
-	while (k < seg_end && st.s[k] == 128) k++;
-	if (k < seg_end) return k - i;
-	seg++;
-	while (seg < SEG_THREADS && st.first_nz[seg] == st.S) seg++;
-	if (seg == SEG_THREADS) return st.p2 - i;
-	return st.p1 + seg * st.S + st.first_nz[seg] - i;
-}
-
-// number of consecutive 128s ending at i (s[i]==128), walking backwards, capped at `cap`
-NHW_HD int seg_run_len_back(const uint8_t *s, int i, int lo, int cap)
-{
-	int n = 0;
-	while (i - n >= lo && n < cap && s[i - n] == 128) n++;
-	return n;
-}
+NHW_HD int seg_run_len(const SegStream &st, int i) { return nz_next(st.nz, i, st.p2) - i; }
 
 // =====================================================================================
 // peephole
@@ -80,7 +115,7 @@ NHW_HD void peep_merge_chain(uint8_t *s, int i, int N)
 // result byte returned; sel1/sel2 tell which select counter to bump.
 // B: isolated / paired +-8 bytes lose their code and keep only a sign bit (153/155, 157/159).
 // C: a 153/155 that ends a zero run too long for one run code goes back to a coded byte.
-NHW_HD int peep_select_byte(const uint8_t *d, int i, int N, int &sel1, int &sel2)
+NHW_HD int peep_select_byte(const uint8_t *d, const NzBits &nz, int i, int N, int &sel1, int &sel2)
 {
 	sel1 = sel2 = 0;
 	int v = d[i];
@@ -111,8 +146,7 @@ NHW_HD int peep_select_byte(const uint8_t *d, int i, int N, int &sel1, int &sel2
 	sel1 = 1;
 	int out = v == 136 ? 153 : 155;
 	// pass C: zero run [p, i) of length L ends right before me
-	const int cap = 1 << 30;
-	const int L = seg_run_len_back(d, i - 1, 0, cap);
+	const int L = i - 1 - nz_prev(nz, i - 1);
 	if (L >= 253) {
 		const int p = i - L;
 		int m = 0, i_last = 0;

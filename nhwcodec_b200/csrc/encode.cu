@@ -376,8 +376,19 @@ __global__ void __launch_bounds__(512) k_offset_quant(EncBatch b, int m1)
 
 // ---- peephole passes over the luma scan, one CTA per image (enc_seg.cuh)
 #define PEEP_THREADS 512
+// non-zero bitmap of `count` stream bytes starting at s (16-byte aligned, count % 32 == 0) into shared memory
+__device__ __forceinline__ void build_nz_bitmap(const uint8_t *s, int count, uint32_t *bits, int tid, int nthreads)
+{
+	for (int w = tid; w < count / 32; w += nthreads) {
+		const uint4 a = reinterpret_cast<const uint4 *>(s)[2 * w], b = reinterpret_cast<const uint4 *>(s)[2 * w + 1];
+		bits[w] = nz_mask4(a.x) | (nz_mask4(a.y) << 4) | (nz_mask4(a.z) << 8) | (nz_mask4(a.w) << 12) | (nz_mask4(b.x) << 16) |
+		          (nz_mask4(b.y) << 20) | (nz_mask4(b.z) << 24) | (nz_mask4(b.w) << 28);
+	}
+}
+
 __global__ void __launch_bounds__(PEEP_THREADS) k_peephole(EncBatch b)
 {
+	extern __shared__ __align__(16) uint32_t nzbits[];   // 262144 bits
 	__shared__ int n_heads, sel1, sel2;
 	const EncImg im = make_img(b, blockIdx.x, 0);
 	uint8_t *s = im.scan;
@@ -398,11 +409,14 @@ __global__ void __launch_bounds__(PEEP_THREADS) k_peephole(EncBatch b)
 	__syncthreads();
 	if (threadIdx.x < 4) { s[threadIdx.x] = 128; s[N - 4 + threadIdx.x] = 128; }
 	__syncthreads();
+	build_nz_bitmap(s, N, nzbits, threadIdx.x, PEEP_THREADS);
+	__syncthreads();
+	const NzBits nz{nzbits, 0, N};
 	// passes B + C: every output byte from the pass-A stream
 	int a1 = 0, a2 = 0;
 	for (int i = threadIdx.x; i < N; i += PEEP_THREADS) {
 		int x1, x2;
-		out[i] = (uint8_t)peep_select_byte(s, i, N, x1, x2);
+		out[i] = (uint8_t)peep_select_byte(s, nz, i, N, x1, x2);
 		a1 += x1;
 		a2 += x2;
 	}
@@ -430,7 +444,7 @@ __device__ __forceinline__ void block_excl_scan3(int *a, int *b, int *c, int t) 
 
 __global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
 {
-	__shared__ uint16_t fnz[SEG_THREADS];
+	extern __shared__ __align__(16) uint32_t nzbits[];   // 262144 bits (luma part), reused for the chroma part
 	__shared__ int hist_sym[256], hist_run[256];
 	__shared__ int sbits[SEG_THREADS + 1], sn1[SEG_THREADS + 1], sn2[SEG_THREADS + 1];
 	__shared__ uint32_t s_weight[354];
@@ -453,9 +467,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
 		hist_sym[t] = 0;
 		hist_run[t] = 0;
 		__syncthreads();
-		fnz[t] = (uint16_t)seg_first_nz(s, p1 + t * S, S);
+		build_nz_bitmap(s + p1, p2 - p1, nzbits, t, SEG_THREADS);
 		__syncthreads();
-		SegStream ss{s, p1, p2, S, fnz};
+		SegStream ss{s, p1, p2, S, NzBits{nzbits, p1, p2 - p1}};
 		seg_stats(ss, t, [&](bool run, int idx) { atomicAdd(run ? &hist_run[idx] : &hist_sym[idx], 1); });
 		__syncthreads();
 		st.rle_buf[t] = hist_sym[t];
@@ -797,7 +811,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_rows(c, "y_offset_pairs57", b, n, 256, [=] __device__(const EncImg &im, int r) { y_offset_pairs57_row(im, r); });
 	NHW_LAUNCH_L(c, "y_offset_quant", k_offset_quant, n, 512, 0, b, ratio);
 	run_rows(c, "y_scan", b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
-	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 0, b);
+	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 262144 / 8, b);
 
 	// ---- chroma, U and V planes side by side (nhw_encoder.c:2255-2868)
 	run_plane_rows(c, "c_recons1", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
@@ -825,7 +839,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
 	run_image(c, "c_ll_code", b, n, [=] __device__(const EncImg &im, int) { ll_dpcm_chroma_image(im); });
-	NHW_LAUNCH_L(c, "entropy_pack", k_entropy, n, SEG_THREADS, 0, b);
+	NHW_LAUNCH_L(c, "entropy_pack", k_entropy, n, SEG_THREADS, 262144 / 8, b);
 	NHW_LAUNCH(c, k_write_stream, (n + 31) / 32, 32, 0, b, n, out_dev, len_dev, status_dev);
 }
 

@@ -151,10 +151,17 @@ void host_peephole(const EncImg &im)
 	s[0] = s[1] = s[2] = s[3] = 128;
 	s[N - 4] = s[N - 3] = s[N - 2] = s[N - 1] = 128;
 	std::vector<uint8_t> out(N);
+	std::vector<uint32_t> bits(N / 32, 0);
+	for (int i = 0; i < N; i++) if (s[i] != 128) bits[i >> 5] |= 1u << (i & 31);
+	for (int i = 0; i < N; i += 4) {
+		uint32_t w; memcpy(&w, s + i, 4);
+		if (nz_mask4(w) != ((bits[i >> 5] >> (i & 31)) & 15u)) abort();
+	}
+	const NzBits nz{bits.data(), 0, N};
 	int sel1 = 0, sel2 = 0;
 	for (int i = N - 1; i >= 0; i--) {
 		int a, b;
-		out[i] = (uint8_t)peep_select_byte(s, i, N, a, b);
+		out[i] = (uint8_t)peep_select_byte(s, nz, i, N, a, b);
 		sel1 += a;
 		sel2 += b;
 	}
@@ -173,9 +180,9 @@ int host_entropy(const EncImg &im, int part, int &word0)
 	uint8_t saved = 0;
 	if (!part) { saved = s[262144]; s[262144] = 3; } else s[393215] = s[393214];
 	const int S = (p2 - p1) / SEG_THREADS;
-	std::vector<uint16_t> fnz(SEG_THREADS);
-	for (int t = 0; t < SEG_THREADS; t++) fnz[t] = (uint16_t)seg_first_nz(s, p1 + t * S, S);
-	SegStream ss{s, p1, p2, S, fnz.data()};
+	std::vector<uint32_t> nzb((p2 - p1) / 32, 0);
+	for (int i = p1; i < p2; i++) if (s[i] != 128) nzb[(i - p1) >> 5] |= 1u << ((i - p1) & 31);
+	SegStream ss{s, p1, p2, S, NzBits{nzb.data(), p1, p2 - p1}};
 	for (int i = 0; i < 256; i++) { st.rle_buf[i] = 0; st.rle_128[i] = 0; }
 	for (int t = SEG_THREADS - 1; t >= 0; t--)
 		seg_stats(ss, t, [&](bool run, int idx) { if (run) st.rle_128[idx]++; else st.rle_buf[idx]++; });
