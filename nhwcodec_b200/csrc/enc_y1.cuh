@@ -265,12 +265,15 @@ NHW_HD int e6d_soften(int a)
 	return a < -11 ? a + 7 : a < -7 ? a + 4 : a < -5 ? a + 2 : a + 1;
 }
 
-NHW_HD void y_e6d_correct_row(const EncImg &im, int r)
+// P, J, L point at column 0 of the row; P[-1], P[256], L[-1], L[256] are the flat neighbours the
+// reference reads at the row ends.  J may alias L (J[j] is written after the last read of L[j]).
+NHW_HD void y_e6d_correct_cells(int16_t *P, int16_t *J, const int16_t *L)
 {
-	int16_t *P = im.proc + r * YW, *J = im.jpeg + r * YW;
-	const int16_t *L = im.ll1 + r * 256;
+	int prev = P[-1] - L[-1];       // left neighbour's difference AFTER its correction
+	int cur = P[0] - L[0];
 	for (int j = 0; j < 256; j++) {
-		int scan = P[j] - L[j];
+		const int nxt = P[j + 1] - L[j + 1];
+		const int scan = cur;
 		int d = 0;
 		if (scan > 11) d = -7;
 		else if (scan > 7) d = -4;
@@ -281,7 +284,7 @@ NHW_HD void y_e6d_correct_row(const EncImg &im, int r)
 		else if (scan < -5) d = 2;
 		else if (scan < -4) d = 1;
 		else if (nhw_iabs(scan) > 1) {
-			int a = e6d_soften(P[j + 1] - L[j + 1]) + (P[j - 1] - L[j - 1]);
+			int a = e6d_soften(nxt) + prev;
 			if (scan >= 4 && a >= 1) d = -1;
 			else if (scan <= -4 && a <= -1) d = 1;
 			else if (scan == 3 && a >= 0) d = -1;
@@ -295,7 +298,15 @@ NHW_HD void y_e6d_correct_row(const EncImg &im, int r)
 				else if (a <= -4) d = 1;
 			}
 		}
-		J[j] = (int16_t)(L[j] + d);
+		const int l = L[j];
+		J[j] = (int16_t)(l + d);
 		P[j] = (int16_t)(P[j] + d);
+		prev = scan + d;
+		cur = nxt;
 	}
+}
+
+NHW_HD void y_e6d_correct_row(const EncImg &im, int r)
+{
+	y_e6d_correct_cells(im.proc + r * YW, im.jpeg + r * YW, im.ll1 + r * 256);
 }

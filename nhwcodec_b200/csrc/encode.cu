@@ -13,6 +13,7 @@
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
 #include "enc_seg.cuh"
+#include "enc_point.cuh"
 #include "enc_batch.cuh"
 #include "../../include/nhw_cuda.h"
 
@@ -353,25 +354,122 @@ __global__ void __launch_bounds__(256) k_e18_lists(EncBatch b, int q)
 	}
 }
 
-// ---- offsetUV to bytes, one thread per row of one chroma plane
-__global__ void __launch_bounds__(256) k_c_offset_quant(EncBatch b, int m2)
+// ---- E6d: LL1 correction, sequential along a row.  One warp per 32 rows; the rows are staged in
+// shared memory at an odd word stride so that "thread = row" walks are bank-conflict free and all
+// global traffic is coalesced.
+#define E6D_STRIDE 262   // int16 cells per staged row: 2 left (cell -1 used), 256, 4 right (cell 256 used)
+__global__ void __launch_bounds__(32) k_e6d_correct(EncBatch b)
 {
-	const EncImg im = make_img(b, blockIdx.x >> 1, blockIdx.x & 1);
-	const int r = threadIdx.x;
-	const int next0 = r < 255 ? (int)im.cproc[(r + 1) * CW] : 0;
-	__syncthreads();
-	c_offset_quant_row(im, m2, r, next0);
+	__shared__ __align__(16) int16_t sP[32 * E6D_STRIDE];
+	__shared__ __align__(16) int16_t sL[32 * E6D_STRIDE];
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	const int r0 = blockIdx.x * 32, lane = threadIdx.x;
+	for (int rr = 0; rr < 32; rr++) {
+		const int16_t *gp = im.proc + (r0 + rr) * YW, *gl = im.ll1 + (r0 + rr) * 256;
+		uint32_t *dp = reinterpret_cast<uint32_t *>(sP + rr * E6D_STRIDE + 2), *dl = reinterpret_cast<uint32_t *>(sL + rr * E6D_STRIDE + 2);
+		for (int k = lane; k < 128; k += 32) {
+			dp[k] = reinterpret_cast<const uint32_t *>(gp)[k];
+			dl[k] = reinterpret_cast<const uint32_t *>(gl)[k];
+		}
+		if (lane == 0) { sP[rr * E6D_STRIDE + 1] = gp[-1]; sL[rr * E6D_STRIDE + 1] = gl[-1]; }
+		if (lane == 1) { sP[rr * E6D_STRIDE + 258] = gp[256]; sL[rr * E6D_STRIDE + 258] = gl[256]; }
+	}
+	__syncwarp();
+	y_e6d_correct_cells(sP + lane * E6D_STRIDE + 2, sL + lane * E6D_STRIDE + 2, sL + lane * E6D_STRIDE + 2);
+	__syncwarp();
+	for (int rr = 0; rr < 32; rr++) {
+		int16_t *gp = im.proc + (r0 + rr) * YW, *gj = im.jpeg + (r0 + rr) * YW;
+		const uint32_t *dp = reinterpret_cast<const uint32_t *>(sP + rr * E6D_STRIDE + 2), *dl = reinterpret_cast<const uint32_t *>(sL + rr * E6D_STRIDE + 2);
+		for (int k = lane; k < 128; k += 32) {
+			reinterpret_cast<uint32_t *>(gp)[k] = dp[k];
+			reinterpret_cast<uint32_t *>(gj)[k] = dl[k];
+		}
+	}
 }
 
-// ---- offsetY to bytes, one thread per row; the look-ahead cell of the next row is sampled
-// before any row is rewritten
-__global__ void __launch_bounds__(512) k_offset_quant(EncBatch b, int m1)
+// ---- offsetY loop 4 + serpentine scan, pointwise (enc_point.cuh): 16 rows per CTA, 8 cells per thread
+// and step; the bytes go through shared memory so that they leave in 64-byte runs of the scan order.
+__global__ void __launch_bounds__(256) k_y_quant_scan(EncBatch b, int m1)
 {
-	const EncImg im = make_img(b, blockIdx.x, 0);
-	const int r = threadIdx.x;
-	const int next0 = r < 511 ? (int)im.proc[(r + 1) * YW] : 0;
+	__shared__ __align__(16) uint8_t sout[128 * 64];
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	const int band = blockIdx.x, tid = threadIdx.x;
+	const int16_t *P = im.proc;
+	for (int q = tid; q < 16 * 64; q += 256) {
+		const int rr = q >> 6, c = (q & 63) * 8, row = band * 16 + rr, i = row * YW + c;
+		const uint4 w = *reinterpret_cast<const uint4 *>(P + i);
+		int o[10];
+		o[0] = c ? (int)P[i - 1] : 0;
+		o[1] = (int16_t)(w.x & 0xffff); o[2] = (int16_t)(w.x >> 16);
+		o[3] = (int16_t)(w.y & 0xffff); o[4] = (int16_t)(w.y >> 16);
+		o[5] = (int16_t)(w.z & 0xffff); o[6] = (int16_t)(w.z >> 16);
+		o[7] = (int16_t)(w.w & 0xffff); o[8] = (int16_t)(w.w >> 16);
+		o[9] = i + 8 < 512 * 512 ? (int)P[i + 8] : 0;
+		uint32_t by[8];
+#pragma unroll
+		for (int t = 0; t < 8; t++) by[t] = (uint32_t)y_quant_byte(o[t], o[t + 1], o[t + 2], c + t >= 1, c + t < 511, m1);
+		uint32_t lo, hi;
+		if (rr & 1) { lo = by[3] | (by[2] << 8) | (by[1] << 16) | (by[0] << 24); hi = by[7] | (by[6] << 8) | (by[5] << 16) | (by[4] << 24); }
+		else { lo = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24); hi = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24); }
+		const int strip = c >> 2, off = (rr >> 1) * 8 + (rr & 1) * 4;
+		*reinterpret_cast<uint32_t *>(sout + strip * 64 + off) = lo;
+		*reinterpret_cast<uint32_t *>(sout + (strip + 1) * 64 + off) = hi;
+	}
 	__syncthreads();
-	y_offset_quant_row(im, m1, r, next0);
+	for (int idx = tid; idx < 512; idx += 256) {
+		const int strip = idx >> 2, part = idx & 3;
+		*reinterpret_cast<uint4 *>(im.scan + strip * 2048 + band * 64 + part * 16) = *reinterpret_cast<const uint4 *>(sout + strip * 64 + part * 16);
+	}
+}
+
+// ---- offsetUV + interleaved chroma scan, pointwise: both planes of 16 rows per CTA
+__global__ void __launch_bounds__(256) k_c_quant_scan(EncBatch b, int m2)
+{
+	__shared__ __align__(16) uint8_t sout[32 * 256];
+	const EncImg imu = make_img(b, blockIdx.y, 0), imv = make_img(b, blockIdx.y, 1);
+	const int band = blockIdx.x, tid = threadIdx.x;
+	for (int q = tid; q < 16 * 32; q += 256) {
+		const int rr = q >> 5, c = (q & 31) * 8, row = band * 16 + rr, i = row * CW + c;
+		uint32_t by[2][8];
+#pragma unroll
+		for (int v = 0; v < 2; v++) {
+			const int16_t *P = v ? imv.cproc : imu.cproc;
+			const uint4 w = *reinterpret_cast<const uint4 *>(P + i);
+			int o[9];
+			o[0] = (int16_t)(w.x & 0xffff); o[1] = (int16_t)(w.x >> 16);
+			o[2] = (int16_t)(w.y & 0xffff); o[3] = (int16_t)(w.y >> 16);
+			o[4] = (int16_t)(w.z & 0xffff); o[5] = (int16_t)(w.z >> 16);
+			o[6] = (int16_t)(w.w & 0xffff); o[7] = (int16_t)(w.w >> 16);
+			o[8] = i + 8 < 65536 ? (int)P[i + 8] : 0;
+#pragma unroll
+			for (int t = 0; t < 8; t++) {
+				int run = 0;
+				bool pre = false;
+				const int col = c + t;
+				if (c_pairable(o[t])) {
+					while (run < col && c_pairable(P[i + t - 1 - run])) run++;
+				} else if (o[t] == 7) {
+					while (run < col && P[i + t - 1 - run] == 7) run++;
+					pre = run < col && c_bumps_next(P[i + t - 1 - run]);
+				}
+				by[v][t] = (uint32_t)c_quant_byte(o[t], o[t + 1], run, pre, col < 255, m2);
+			}
+		}
+		uint32_t wv[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int t0 = (rr & 1) ? 7 - 2 * k : 2 * k, t1 = (rr & 1) ? 6 - 2 * k : 2 * k + 1;
+			wv[k] = by[0][t0] | (by[1][t0] << 8) | (by[0][t1] << 16) | (by[1][t1] << 24);
+		}
+		const int strip = c >> 3;
+		*reinterpret_cast<uint4 *>(sout + strip * 256 + (rr >> 1) * 32 + (rr & 1) * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+	}
+	__syncthreads();
+	for (int idx = tid; idx < 512; idx += 256) {
+		const int strip = idx >> 4, part = idx & 15;
+		*reinterpret_cast<uint4 *>(imu.scan + 262144 + strip * 4096 + band * 256 + part * 16) =
+		    *reinterpret_cast<const uint4 *>(sout + strip * 256 + part * 16);
+	}
 }
 
 // ---- peephole passes over the luma scan, one CTA per image (enc_seg.cuh)
@@ -762,7 +860,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_rows(c, "y_recons1_quant", b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 1); });
 	idwt_luma256(c, b, n);
 	run_rows(c, "y_e6c_apply", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6c_apply_row(im, r); });
-	run_rows(c, "y_e6d_correct", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6d_correct_row(im, r); });
+	NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(8, n), 32, 0, b);
 	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
 
 	// ---- LL2 coding (nhw_encoder.c:623-757)
@@ -809,8 +907,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_wavefront(c, "y_offset_patterns", b, n, wf_offset_patterns_geom(),
 	              [=] __device__(const EncImg &im, int r, int j) { return wf_offset_patterns_cell(im, r, j); });
 	run_rows(c, "y_offset_pairs57", b, n, 256, [=] __device__(const EncImg &im, int r) { y_offset_pairs57_row(im, r); });
-	NHW_LAUNCH_L(c, "y_offset_quant", k_offset_quant, n, 512, 0, b, ratio);
-	run_rows(c, "y_scan", b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
+	NHW_LAUNCH_L(c, "y_quant_scan", k_y_quant_scan, dim3(32, n), 256, 0, b, ratio);
 	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 262144 / 8, b);
 
 	// ---- chroma, U and V planes side by side (nhw_encoder.c:2255-2868)
@@ -834,8 +931,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		if (v) im.hdr->exw_v_len = e; else im.hdr->exw_u_len = e;
 		if (q > 15) c_ll_bit1_plane(im, v);
 	});
-	NHW_LAUNCH_L(c, "c_offset_quant", k_c_offset_quant, 2 * n, 256, 0, b, ratio);
-	run_plane_rows(c, "c_scan", b, n, 32, [=] __device__(const EncImg &im, int s, int v) { c_scan_strip(im, s, v); });
+	NHW_LAUNCH_L(c, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);
 
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
 	run_image(c, "c_ll_code", b, n, [=] __device__(const EncImg &im, int) { ll_dpcm_chroma_image(im); });

@@ -14,6 +14,7 @@
 
 #include "../../nhwcodec_b200/csrc/dec_stages.cuh"
 #include "../../nhwcodec_b200/csrc/dec_parse.h"
+#include "../../nhwcodec_b200/csrc/enc_point.cuh"
 
 namespace {
 
@@ -458,13 +459,20 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	for (int r = 511; r >= 0; r--) y_offset_mult8_row(im, r);
 	host_wavefront(wf_offset_patterns_geom(), [&](int r, int j) { return wf_offset_patterns_cell(im, r, j); });
 	for (int r = 255; r >= 0; r--) y_offset_pairs57_row(im, r);
-	{
+	if (getenv("HE_ROWFORM")) {
 		std::vector<int> next0(512);
 		for (int r = 0; r < 512; r++) next0[r] = r < 511 ? im.proc[(r + 1) * 512] : 0;
 		for (int r = 511; r >= 0; r--) y_offset_quant_row(im, ratio, r, next0[r]);
+		T("y_e21_proc", im.proc, 512 * 512 * 2);
+		for (int s = 127; s >= 0; s--) y_scan_strip(im, s);
+	} else {   // pointwise form (enc_point.cuh), as the fused quantise+scan kernel runs it
+		const int16_t *P = im.proc;
+		for (int i = 512 * 512 - 1; i >= 0; i--) {
+			const int row = i >> 9, col = i & 511;
+			const int op1 = i + 1 < 512 * 512 ? P[i + 1] : 0;
+			im.scan[y_scan_pos(row, col)] = (uint8_t)y_quant_byte(col ? P[i - 1] : 0, P[i], op1, col >= 1, col < 511, ratio);
+		}
 	}
-	T("y_e21_proc", im.proc, 512 * 512 * 2);
-	for (int s = 127; s >= 0; s--) y_scan_strip(im, s);
 	T("y_e23_scan", im.scan, 262144);
 	if (getenv("HE_SERIAL")) y_peephole_image(im); else host_peephole(im);
 	T("y_e24_scan", im.scan, 262144);
@@ -502,13 +510,27 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		int e = c_ll_to_bytes_image(im, v);
 		if (v) h->exw_v_len = e; else h->exw_u_len = e;
 		if (q > 15) c_ll_bit1_plane(im, v);
-		{
+		if (getenv("HE_ROWFORM")) {
 			std::vector<int> next0(256);
 			for (int r = 0; r < 256; r++) next0[r] = r < 255 ? im.cproc[(r + 1) * 256] : 0;
 			for (int r = 255; r >= 0; r--) c_offset_quant_row(im, ratio, r, next0[r]);
+			TN("quant_proc", im.cproc, 65536 * 2);
+			for (int s = 31; s >= 0; s--) c_scan_strip(im, s, v);
+		} else {
+			const int16_t *P = im.cproc;
+			for (int i = 65535; i >= 0; i--) {
+				const int row = i >> 8, col = i & 255;
+				int run = 0;
+				bool pre = false;
+				if (c_pairable(P[i])) { while (run < col && c_pairable(P[i - 1 - run])) run++; }
+				else if (P[i] == 7) {
+					while (run < col && P[i - 1 - run] == 7) run++;
+					pre = run < col && c_bumps_next(P[i - 1 - run]);
+				}
+				const int op1 = i + 1 < 65536 ? P[i + 1] : 0;
+				im.scan[c_scan_pos(row, col, v)] = (uint8_t)c_quant_byte(P[i], op1, run, pre, col < 255, ratio);
+			}
 		}
-		TN("quant_proc", im.cproc, 65536 * 2);
-		for (int s = 31; s >= 0; s--) c_scan_strip(im, s, v);
 	}
 	T("uv_scan", im.scan + 262144, 131072);
 	ll_dpcm_chroma_image(im);
