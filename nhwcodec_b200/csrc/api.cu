@@ -130,6 +130,11 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	c->prof = new nhw::ProfState();
 	const size_t B = (size_t)max_batch;
 	bool ok = check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	ok = ok && check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	for (int k = 0; k < 2 && ok; k++) {
+		ok = ok && check(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming), "cudaEventCreate");
+		ok = ok && check(cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming), "cudaEventCreate");
+	}
 	// every workspace array is zero-filled once: guard bands and never-written borders must
 	// read as 0 (canonical oracle semantics)
 	ok = ok && dev_alloc0(&c->rgb, B * NHW_RGB_BYTES);
@@ -169,6 +174,11 @@ void nhw_destroy(nhw_ctx *c)
 	if (c->offs_host) cudaFreeHost(c->offs_host);
 	if (c->status_host) cudaFreeHost(c->status_host);
 	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	for (int k = 0; k < 2; k++) {
+		if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
+		if (c->ev_consumed[k]) cudaEventDestroy(c->ev_consumed[k]);
+	}
 	if (c->prof) {
 		nhw::ProfState *p = static_cast<nhw::ProfState *>(c->prof);
 		nhw::prof_resolve(c);
@@ -330,13 +340,31 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 	if (!c || !rgb || !out || !offsets || n <= 0) return NHW_ERR_ARG;
 	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q21 are)", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
+	// Software pipeline over sub-chunks: while the kernels of sub-chunk k run on `stream`, the pixels of
+	// sub-chunk k+1 travel host->device on `copy_stream` into the other half of the staging buffer.
+	// (sub-chunks stay large: several stages still run one thread per image and cost the same for 512 images as for 2048)
+	const int sub = c->max_batch >= 2 ? c->max_batch / 2 : 1;
+	const bool overlap = c->max_batch >= 2 * sub;
+	const int nsub = (n + sub - 1) / sub;
+	auto stage = [&](int k) { return c->rgb + (size_t)(overlap ? (k & 1) : 0) * sub * NHW_RGB_BYTES; };
+	auto count = [&](int k) { return n - k * sub < sub ? n - k * sub : sub; };
+	auto upload = [&](int k) {
+		cudaStream_t s = overlap ? c->copy_stream : c->stream;
+		if (overlap && k >= 2) cudaStreamWaitEvent(s, c->ev_consumed[k & 1], 0);
+		bool ok = check(cudaMemcpyAsync(stage(k), rgb + (size_t)k * sub * NHW_RGB_BYTES, (size_t)count(k) * NHW_RGB_BYTES,
+		                                cudaMemcpyHostToDevice, s), "H2D pixels");
+		if (overlap) cudaEventRecord(c->ev_copied[k & 1], s);
+		return ok;
+	};
 	uint64_t pos = 0;
 	offsets[0] = 0;
-	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
-		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
-		if (!check(cudaMemcpyAsync(c->rgb, rgb + (size_t)i0 * NHW_RGB_BYTES, (size_t)m * NHW_RGB_BYTES,
-		                           cudaMemcpyHostToDevice, c->stream), "H2D pixels")) return NHW_ERR_CUDA;
-		nhw::encode_chunk(c, c->rgb, m, quality, c->out_dev, c->len_dev, c->status_dev);
+	if (!upload(0)) return NHW_ERR_CUDA;
+	for (int k = 0; k < nsub; k++) {
+		const int i0 = k * sub, m = count(k);
+		if (overlap && k + 1 < nsub && !upload(k + 1)) return NHW_ERR_CUDA;
+		if (overlap) cudaStreamWaitEvent(c->stream, c->ev_copied[k & 1], 0);
+		nhw::encode_chunk(c, stage(k), m, quality, c->out_dev, c->len_dev, c->status_dev);
+		if (overlap) cudaEventRecord(c->ev_consumed[k & 1], c->stream);
 		nhw::pack_streams(c, m);
 		cudaMemcpyAsync(c->offs_host, c->offs_dev, (size_t)(m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
 		cudaMemcpyAsync(c->status_host, c->status_dev, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
@@ -344,12 +372,17 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 		if (rc) return rc;
 		const uint64_t total = c->offs_host[m];
 		if (pos + total > out_cap) { nhw::set_error("output buffer too small"); return NHW_ERR_ARG; }
-		if (total && !check(cudaMemcpy(out + pos, c->pack_dev, total, cudaMemcpyDeviceToHost), "D2H streams")) return NHW_ERR_CUDA;
+		if (total) {
+			if (!check(cudaMemcpyAsync(out + pos, c->pack_dev, total, cudaMemcpyDeviceToHost, c->stream), "D2H streams")) return NHW_ERR_CUDA;
+			rc = finish(c, "nhw_encode_batch");
+			if (rc) return rc;
+		}
 		for (int i = 0; i < m; i++) {
 			offsets[i0 + i + 1] = pos + c->offs_host[i + 1];
 			if (status) status[i0 + i] = c->status_host[i];
 		}
 		pos += total;
+		if (!overlap && k + 1 < nsub && !upload(k + 1)) return NHW_ERR_CUDA;
 	}
 	return NHW_OK;
 }

@@ -12,6 +12,8 @@ struct nhw_ctx {
 	int device;
 	int max_batch;
 	cudaStream_t stream;
+	cudaStream_t copy_stream;   // host<->device copies that overlap the kernels of `stream`
+	cudaEvent_t ev_copied[2], ev_consumed[2];
 	uint64_t launches;
 	char dbg_label[64];  // debug: stop issuing kernels after the dbg_count-th launch of this label
 	int dbg_count, dbg_seen, dbg_stopped;
