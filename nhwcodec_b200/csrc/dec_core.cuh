@@ -35,32 +35,71 @@ struct DecImg {
 	int32_t *list_len;                // 8 lengths + [8] = stale `count`, [9] = edge-flag count
 	uint16_t *flags;                  // edge-flag positions
 	uint16_t *book;                   // rank -> (run<<8 | byte)
+	const uint16_t *lut;              // primary table of the static prefix code (dec_build_lut)
 	uint8_t *yuv;                     // Y, U, V u8 planes 512x512 each
 };
 
 NHW_HD int nhw_extra_value(int word) { return word >= 0 && word < 110 ? (int)nhw_extra_table[word] : 0; }
 
-// ---- bit reader over the packed 32-bit words (stored little-endian, consumed MSB first)
+// ---- bit reader over the packed 32-bit words (stored little-endian, consumed MSB first).
+// The stream may start at any byte address: words are fetched with aligned 32-bit loads and
+// re-aligned with a funnel shift; a 64-bit buffer holds the next bits MSB first.
 struct BitReader {
-	const uint8_t *b;
-	long pos;
-	NHW_HD uint32_t word(long i) const
+	const uint32_t *ap;      // aligned pointer at or below the first stream byte
+	int sh;                  // 8 * (first byte address & 3)
+	long widx;               // next aligned word to fetch
+	uint32_t carry;          // ap[widx], already fetched
+	unsigned long long buf;  // unread bits, MSB first
+	int nb;                  // valid bits in buf
+	long pos;                // bits consumed so far
+	NHW_HD void init(const uint8_t *b)
 	{
-		const uint8_t *p = b + 4 * i;
-		return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+		const uintptr_t a = (uintptr_t)b;
+		ap = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+		sh = (int)(a & 3) * 8;
+		widx = 0;
+		carry = ap[0];
+		buf = 0;
+		nb = 0;
+		pos = 0;
+		fill();
+		fill();
 	}
-	NHW_HD uint32_t peek(int n) const   // next n (<=24) bits, MSB first
+	NHW_HD void fill()       // append the next stream word (nb <= 32 on entry)
 	{
-		const long w = pos >> 5;
-		const int sh = (int)(pos & 31);
-		unsigned long long v = ((unsigned long long)word(w) << 32) | word(w + 1);
-		return (uint32_t)((v << sh) >> (64 - n));
+		const uint32_t nxt = ap[++widx];
+		const uint32_t w = sh ? ((carry >> sh) | (nxt << (32 - sh))) : carry;
+		carry = nxt;
+		buf |= (unsigned long long)w << (32 - nb);
+		nb += 32;
 	}
-	NHW_HD void skip(int n) { pos += n; }
+	NHW_HD uint32_t peek(int n) const { return (uint32_t)(buf >> (64 - n)); }   // next n (<= 32) bits
+	NHW_HD void skip(int n)
+	{
+		buf <<= n;
+		nb -= n;
+		pos += n;
+		if (nb <= 32) fill();
+	}
 };
 
+// Primary decode table of the static prefix code: entry for the next 12 bits = (length << 10) | rank for
+// every code of at most 12 bits, 0 where a longer code (13..20 bits, ranks NHW_LONG_FIRST..) starts.
+#define NHW_LUT_BITS 12
+#define NHW_LONG_FIRST 98
+inline void dec_build_lut(uint16_t *lut /* 4096 */)
+{
+	for (int i = 0; i < (1 << NHW_LUT_BITS); i++) lut[i] = 0;
+	for (int r = 0; r < NHW_CODE_DEPTH; r++) {
+		const int len = h_nhw_code_len[r];
+		if (len > NHW_LUT_BITS) continue;
+		const uint32_t first = h_nhw_code_bits[r] << (NHW_LUT_BITS - len);
+		for (uint32_t k = 0; k < (1u << (NHW_LUT_BITS - len)); k++) lut[first + k] = (uint16_t)((len << 10) | r);
+	}
+}
+
 // rank of the next code (static prefix code).  Returns -1 if nothing matches.
-NHW_HD int dec_next_rank(BitReader &br, bool zone)
+NHW_HD int dec_next_rank(BitReader &br, bool zone, const uint16_t *lut)
 {
 	const uint32_t v = br.peek(20);
 	if (zone && (v >> 11) == 1) {   // 000000001 + 6 bits
@@ -68,8 +107,13 @@ NHW_HD int dec_next_rank(BitReader &br, bool zone)
 		br.skip(15);
 		return r;
 	}
-	// codes are listed by non-decreasing length: scan lengths, compare within the length's ranks
-	for (int r = 0; r < NHW_CODE_DEPTH; r++) {
+	const int ent = lut[v >> (20 - NHW_LUT_BITS)];
+	if (ent) {
+		const int r = ent & 1023;
+		br.skip(ent >> 10);
+		return (zone && r >= 110) ? r + 64 : r;
+	}
+	for (int r = NHW_LONG_FIRST; r < NHW_CODE_DEPTH; r++) {
 		const int len = nhw_code_len[r];
 		if ((v >> (20 - len)) == nhw_code_bits[r]) {
 			br.skip(len);
@@ -114,63 +158,70 @@ NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
 	const DecDesc *d = im.d;
 	const uint8_t *sel1 = im.blob + d->off_sel1, *sel2 = im.blob + d->off_sel2;
 	const bool zone = d->byte0 < 4;
-	BitReader br{im.blob + d->off_words, 0};
+	BitReader br;
+	br.init(im.blob + d->off_words);
 	const long nbits = (long)d->size_data1 * 32;
 	const int p1 = 262144;
 	int e = 0, mem = 0, mem2 = 0, ac1 = 0, run_over = -257, t = 0, t2 = 0;
 	auto bit1 = [&](int k) { return (sel1[k >> 3] >> (7 - (k & 7))) & 1; };
 	auto bit2 = [&](int k) { return (sel2[k >> 3] >> (7 - (k & 7))) & 1; };
-	auto z = [&](int k) { return k >= 0 ? im3[k] == 0 : true; };   // reads below 0 see the zero guard
+	// The plane starts zeroed and is written at increasing positions only, so "is cell e-k still
+	// zero" is answered from a shift register of the last 32 positions instead of reading it back:
+	// bit j of hist = a non-zero value was stored at position e-1-j.
+	uint32_t hist = 0;
+	auto z = [&](int k) { return k >= 0 ? !((hist >> (e - 1 - k)) & 1u) : true; };   // k in [e-5, e-1]; below 0: zero guard
+	auto put = [&](int v) { im3[e++] = (int16_t)v; hist = (hist << 1) | (v != 0 ? 1u : 0u); };
+	auto advance = [&](int n) { e += n; hist = n >= 32 ? 0u : hist << n; };
 	while (br.pos < nbits + 64) {
-		const int dec = dec_next_rank(br, zone);
+		const int dec = dec_next_rank(br, zone, im.lut);
 		if (dec < 0) return NHW_ERR_CODEBOOK_DEV;
 		const int sym = im.book[dec];
 		const int word = sym & 0xff, run = sym >> 8;
 		if (word == 0x80) {
 			mem++;
 			if (mem2 == 1) {
-				if (e >= 5 && z(e - 2) && z(e - 3) && z(e - 4) && z(e - 5)) { im3[e++] = bit2(t2++) ? 11 : -11; }
-				else if (run >= 4 && z(e - 2)) { im3[e++] = bit2(t2++) ? 11 : -11; }
+				if (e >= 5 && z(e - 2) && z(e - 3) && z(e - 4) && z(e - 5)) { put(bit2(t2++) ? 11 : -11); }
+				else if (run >= 4 && z(e - 2)) { put(bit2(t2++) ? 11 : -11); }
 				mem2 = 0;
 			} else if (mem == 2 && !ac1) {
 				if (e >= 4 && z(e - 1) && z(e - 2) && z(e - 3) && z(e - 4) && (e + run - 257) >= run_over) {
-					im3[e++] = bit1(t++) ? -11 : 11;
+					put(bit1(t++) ? -11 : 11);
 					mem = 1;
 				} else if (run >= 4 && e > 0 && z(e - 1) && !ac1 && (e + run - 257) >= run_over) {
-					im3[e++] = bit1(t++) ? -11 : 11;
+					put(bit1(t++) ? -11 : 11);
 					mem = 1;
 				}
 			} else if (run >= 4 && e > 0 && z(e - 1) && !ac1 && (e + run - 257) >= run_over) {
-				im3[e++] = bit1(t++) ? -11 : 11;
+				put(bit1(t++) ? -11 : 11);
 				mem = 1;
 			}
 			if (run == 254) { ac1 = 1; mem = 0; run_over = e; }
 			else ac1 = 0;
-			e += run;
+			advance(run);
 		} else {
 			mem = 0; mem2 = 0; ac1 = 0;
 			bool done = true;
-			if (word == 136) { im3[e++] = 11; mem2 = 1; }
-			else if (word == 120) { im3[e++] = -11; mem2 = 1; }
+			if (word == 136) { put(11); mem2 = 1; }
+			else if (word == 120) { put(-11); mem2 = 1; }
 			else if (word >= 132 && word <= 135) {
-				im3[e] = (int16_t)(word < 134 ? 11 : -11);
-				e += 4;
-				im3[e++] = (int16_t)((word & 1) ? -11 : 11);
+				put(word < 134 ? 11 : -11);
+				advance(3);
+				put((word & 1) ? -11 : 11);
 			}
-			else if (word == 127) im3[e++] = 1008;
-			else if (word == 129) im3[e++] = 1009;
-			else if (word == 125) im3[e++] = 1006;
-			else if (word == 126) im3[e++] = 1007;
-			else if (word == 121) im3[e++] = 1010;
-			else if (word == 122) im3[e++] = 1011;
-			else if (word == 124) im3[e++] = 11;
-			else if (word == 123) im3[e++] = -11;
+			else if (word == 127) put(1008);
+			else if (word == 129) put(1009);
+			else if (word == 125) put(1006);
+			else if (word == 126) put(1007);
+			else if (word == 121) put(1010);
+			else if (word == 122) put(1011);
+			else if (word == 124) put(11);
+			else if (word == 123) put(-11);
 			else done = false;
 			if (!done) {
 				const int x = word < 110 ? nhw_extra_value(word) : 0;
-				if (x > 0) im3[e++] = (int16_t)(123 + (x << 3));
-				else if (x < 0) im3[e++] = (int16_t)((x << 3) - 123);
-				else im3[e++] = (int16_t)(word > 0x80 ? word - 125 : word - 131);
+				if (x > 0) put(123 + (x << 3));
+				else if (x < 0) put((x << 3) - 123);
+				else put(word > 0x80 ? word - 125 : word - 131);
 			}
 		}
 		if (e >= p1 - 1) return 0;
@@ -182,12 +233,13 @@ NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
 NHW_HDN int dec_prefix_chroma(const DecImg &im, int16_t *im3 /* 131072, zeroed */)
 {
 	const DecDesc *d = im.d;
-	BitReader br{im.blob + d->off_words + 4 * (size_t)d->size_data1, 0};
+	BitReader br;
+	br.init(im.blob + d->off_words + 4 * (size_t)d->size_data1);
 	const long nbits = (long)(d->size_data2 - d->size_data1) * 32;
 	const int p1 = 131071;
 	int e = 0;
 	while (br.pos < nbits + 64) {
-		const int dec = dec_next_rank(br, false);
+		const int dec = dec_next_rank(br, false, im.lut);
 		if (dec < 0) return NHW_ERR_CODEBOOK_DEV;
 		const int sym = im.book[dec];
 		const int word = sym & 0xff;

@@ -1,0 +1,70 @@
+// dec_par.cuh -- parallel forms of the decoder's raster-order stages (same approach as
+// enc_par.cuh: wavefront cells with the smallest skew the dependency footprint allows, and
+// pointwise forms where the raster order turns out not to matter).
+//
+//   D8   shrink isolated coefficients     decoder/nhw_decoder.c:685-711   wavefront, skew 2
+//   D11  edge flags (+16000 in place)     decoder/nhw_decoder.c:789-825   wavefront over pairs, skew 2
+//   D16  chroma sharpen                   decoder/nhw_decoder.c:1085-1109 wavefront, skew 2
+//   D16  chroma 2x upsample               decoder/nhw_decoder.c:1137-1181 pointwise
+// In all three wavefront stages a cell reads its 8 neighbours in place: the row above and the left
+// neighbour already edited, the right neighbour and the row below not yet; a row may therefore run
+// ahead of the row below by two cells (two pairs for D11) and no more.
+#pragma once
+#include "dec_stages.cuh"
+
+// D8: cell (r, j), 1 <= r, j <= 254, of the level-2 region of J (stride 512)
+NHW_HD WfGeom dwf_shrink_geom() { return WfGeom{1, 254, 1, 254, 2}; }
+NHW_HD int dwf_shrink_cell(int16_t *J, int r, int j)
+{
+	const int s = r * YW + j;
+	if (nhw_iabs(J[s]) <= 8) return 1;
+	if (nhw_iabs(J[s - YW - 1]) > 8 || nhw_iabs(J[s - YW]) > 8 || nhw_iabs(J[s - YW + 1]) > 8 ||
+	    nhw_iabs(J[s - 1]) > 8 || nhw_iabs(J[s + 1]) > 8 || nhw_iabs(J[s + YW - 1]) > 8 ||
+	    nhw_iabs(J[s + YW]) > 8 || nhw_iabs(J[s + YW + 1]) > 8)
+		return 1;
+	if (r >= 128 || j >= 128) J[s] += J[s] > 0 ? -1 : 1;
+	return 1;
+}
+
+// D11: pair p (columns 1+2p, 2+2p), 0 <= p <= 126, rows 1..254 of the reconstructed LL1 (stride 512)
+NHW_HD WfGeom dwf_edge_geom() { return WfGeom{1, 254, 0, 127, 2}; }
+NHW_HD int dwf_edge_cell(int16_t *P, int r, int p)
+{
+	const int s = r * YW + 1 + 2 * p;
+	const int res = dec_lap8(P, s, YW);
+	const int cnt = dec_lap8(P, s + 1, YW);
+	if (res > 41 && res < 108 && cnt < 16) P[s] += 16000;
+	else if (res < -41 && res > -108 && cnt > -16) P[s] += 16000;
+	else if (cnt > 41 && cnt < 108 && res < 16) P[s + 1] += 16000;
+	else if (cnt < -41 && cnt > -108 && res > -16) P[s + 1] += 16000;
+	return 1;
+}
+
+// D16: chroma sharpen cell (r, j), 1 <= r, j <= 254 (stride 256)
+NHW_HD WfGeom dwf_sharpen_geom() { return WfGeom{1, 254, 1, 254, 2}; }
+NHW_HD int dwf_sharpen_cell(int16_t *P, int thr, int r, int j)
+{
+	const int s = r * CW + j;
+	const int res = dec_lap8(P, s, CW);
+	if (nhw_iabs(res) > thr) {
+		if (res > 0) P[s] += res > 160 ? 3 : 2;
+		else P[s] -= res < -160 ? 3 : 2;
+	}
+	return 1;
+}
+
+// D16: the 2x2 output cells of chroma cell (r, c) from the un-clipped sharpened plane
+// (clip, then rows, then columns; the last row / column is repeated)
+NHW_HD void dec_c_upsample_cell(const int16_t *P, uint8_t *out /* 512x512 */, int r, int c)
+{
+	const int c1 = c < 255 ? c + 1 : 255, r1 = r < 255 ? r + 1 : 255;
+	const int a00 = dec_clip8(P[r * CW + c]), a01 = dec_clip8(P[r * CW + c1]);
+	const int a10 = dec_clip8(P[r1 * CW + c]), a11 = dec_clip8(P[r1 * CW + c1]);
+	const int b0 = r < 255 ? (a00 + a10 + 1) >> 1 : a00;      // odd output row
+	const int b1 = r < 255 ? (a01 + a11 + 1) >> 1 : a01;
+	uint8_t *o = out + (2 * r) * 512 + 2 * c;
+	o[0] = (uint8_t)a00;
+	o[1] = (uint8_t)(c < 255 ? (a00 + a01 + 1) >> 1 : a00);
+	o[512] = (uint8_t)b0;
+	o[513] = (uint8_t)(c < 255 ? (b0 + b1 + 1) >> 1 : b0);
+}

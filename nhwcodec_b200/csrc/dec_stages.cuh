@@ -101,12 +101,11 @@ NHW_HDN void dec_y_markers_image(const DecImg &im)
 }
 
 // ---- D5-D7: LL2 fill, res4 parity restore, exw overrides (nhw_decoder.c:609-658)
-NHW_HDN int dec_y_ll_image(const DecImg &im)
+// res4 parity restore + exw overrides; returns where the chroma exw entries start
+NHW_HDN int dec_y_ll_overrides(const DecImg &im)
 {
 	int16_t *J = im.jpeg;
 	const DecDesc *d = im.d;
-	for (int r = 0; r < 128; r++)
-		for (int j = 0; j < 128; j++) J[r * YW + j] = im.res_comp[r * 128 + j];
 	if (d->quality > 17) {
 		const uint8_t *r4 = im.blob + d->off_res4;
 		int count = 0;
@@ -128,6 +127,13 @@ NHW_HDN int dec_y_ll_image(const DecImg &im)
 		J[(x[i] << 9) + col] = (int16_t)val;
 	}
 	return i;   // exw1: where the chroma entries start (after the 0,0 separator)
+}
+
+NHW_HDN int dec_y_ll_image(const DecImg &im)
+{
+	for (int r = 0; r < 128; r++)
+		for (int j = 0; j < 128; j++) im.jpeg[r * YW + j] = im.res_comp[r * 128 + j];
+	return dec_y_ll_overrides(im);
 }
 
 // ---- D8: shrink isolated coefficients of the level-2 bands, in place (nhw_decoder.c:685-711)

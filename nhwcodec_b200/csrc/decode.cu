@@ -9,7 +9,7 @@
 
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
-#include "dec_stages.cuh"
+#include "dec_par.cuh"
 #include "../../include/nhw_cuda.h"
 
 namespace {
@@ -36,7 +36,10 @@ struct DecBatch {
 	uint8_t *bytes;
 	uint8_t *yuv;                 // n x 3 x 262144
 	int32_t *status;
+	const uint16_t *lut;          // primary prefix-code table (device memory)
 };
+
+__device__ uint16_t g_dec_lut[1 << NHW_LUT_BITS];
 
 __device__ __forceinline__ DecImg make_dec(const DecBatch &b, int i, int comp)
 {
@@ -58,6 +61,7 @@ __device__ __forceinline__ DecImg make_dec(const DecBatch &b, int i, int comp)
 	im.flags = reinterpret_cast<uint16_t *>(bytes + DOFF_FLAGS);
 	for (int k = 0; k < 8; k++) im.list[k] = reinterpret_cast<uint16_t *>(bytes + DOFF_LISTS) + (size_t)k * 65536;
 	im.yuv = b.yuv + (size_t)i * 786432;
+	im.lut = b.lut;
 	return im;
 }
 
@@ -66,6 +70,21 @@ __global__ void kd_image(DecBatch b, int n, F f)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n && b.status[i] == 0) f(make_dec(b, i, 0), i);
+}
+// same, with the prefix-code table staged in shared memory (the bit-serial decoders hit it once per code)
+template <typename F>
+__global__ void __launch_bounds__(32) kd_image_lut(DecBatch b, int n, F f)
+{
+	__shared__ uint16_t slut[1 << NHW_LUT_BITS];
+	for (int k = threadIdx.x; k < (1 << NHW_LUT_BITS) / 8; k += 32)
+		reinterpret_cast<uint4 *>(slut)[k] = reinterpret_cast<const uint4 *>(b.lut)[k];
+	__syncwarp();
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && b.status[i] == 0) {
+		DecImg im = make_dec(b, i, 0);
+		im.lut = slut;
+		f(im, i);
+	}
 }
 template <typename F>
 __global__ void kd_plane(DecBatch b, int n2, F f)
@@ -87,9 +106,119 @@ __global__ void kd_plane_rows(DecBatch b, int rows, F f)   // grid (ceil(rows/64
 }
 
 template <typename F> void d_image(nhw_ctx *c, const char *l, const DecBatch &b, int n, F f) { NHW_LAUNCH_L(c, l, kd_image, (n + 31) / 32, 32, 0, b, n, f); }
+template <typename F> void d_image_lut(nhw_ctx *c, const char *l, const DecBatch &b, int n, F f) { NHW_LAUNCH_L(c, l, kd_image_lut, (n + 31) / 32, 32, 0, b, n, f); }
 template <typename F> void d_plane(nhw_ctx *c, const char *l, const DecBatch &b, int n, F f) { NHW_LAUNCH_L(c, l, kd_plane, (2 * n + 31) / 32, 32, 0, b, 2 * n, f); }
 template <typename F> void d_rows(nhw_ctx *c, const char *l, const DecBatch &b, int n, int rows, F f) { NHW_LAUNCH_L(c, l, kd_rows, dim3((rows + 63) / 64, n), 64, 0, b, rows, f); }
 template <typename F> void d_plane_rows(nhw_ctx *c, const char *l, const DecBatch &b, int n, int rows, F f) { NHW_LAUNCH_L(c, l, kd_plane_rows, dim3((rows + 63) / 64, 2 * n), 64, 0, b, rows, f); }
+
+// ---- wavefront executor (dec_par.cuh): one CTA per plane, thread = row of the stage's region
+template <typename Cell>
+__global__ void __launch_bounds__(256) kd_wavefront(DecBatch b, WfGeom g, int planes_per_image, Cell cell)
+{
+	const int img = blockIdx.x / planes_per_image;
+	if (b.status[img] != 0) return;
+	const DecImg im = make_dec(b, img, blockIdx.x % planes_per_image);
+	const int ri = threadIdx.x;
+	const int steps = g.cols + g.skew * (g.rows - 1);
+	int next = 0;
+	for (int t = 0; t < steps; t++) {
+		const int c = t - g.skew * ri;
+		if (ri < g.rows && c >= 0 && c < g.cols && c == next) next = c + cell(im, g.r0 + ri, g.c0 + c);
+		__syncthreads();
+	}
+}
+template <typename Cell>
+void d_wavefront(nhw_ctx *c, const char *l, const DecBatch &b, int n, int ppi, WfGeom g, Cell cell)
+{
+	NHW_LAUNCH_L(c, l, kd_wavefront, n * ppi, 256, 0, b, g, ppi, cell);
+}
+
+// ---- D5-D7: LL2 fill in parallel, then the two short override lists
+__global__ void __launch_bounds__(256) kd_y_ll(DecBatch b)
+{
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.x, 0);
+	for (int i = threadIdx.x; i < 16384; i += 256) im.jpeg[(i >> 7) * YW + (i & 127)] = im.res_comp[i];
+	__syncthreads();
+	if (threadIdx.x == 0) im.list_len[10] = dec_y_ll_overrides(im);
+}
+
+// 16-bit add on a cell other threads may be adding to as well
+__device__ __forceinline__ void atomic_add_s16(int16_t *p, int v)
+{
+	uint32_t *w = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+	const bool hi = (reinterpret_cast<uintptr_t>(p) & 2) != 0;
+	uint32_t old = *w, assumed;
+	do {
+		assumed = old;
+		const uint32_t cur = hi ? assumed >> 16 : assumed & 0xffffu;
+		const uint32_t nv = (cur + (uint32_t)v) & 0xffffu;
+		old = atomicCAS(w, assumed, hi ? (assumed & 0xffffu) | (nv << 16) : (assumed & 0xffff0000u) | nv);
+	} while (old != assumed);
+}
+
+// ---- D10: residual add-backs (nhw_decoder.c:721-787): commutative += / -= at listed positions
+__global__ void __launch_bounds__(256) kd_addbacks(DecBatch b)
+{
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.x, 0);
+	int16_t *P = im.proc;
+	const int q = im.d->quality, t = threadIdx.x;
+	auto at = [](uint16_t v) { return ((v & 65280) << 1) + (v & 255); };
+	if (q >= 21) {
+		for (int i = t; i < im.list_len[2]; i += 256) atomic_add_s16(P + at(im.list[2][i]), -3);
+		for (int i = t; i < im.list_len[3]; i += 256) atomic_add_s16(P + at(im.list[3][i]), 3);
+	}
+	if (q > 12) {
+		const int e = q >= 18 ? 5 : q >= 15 ? 7 : 9;
+		for (int i = t; i < im.list_len[0]; i += 256) atomic_add_s16(P + at(im.list[0][i]), -e);
+		for (int i = t; i < im.list_len[1]; i += 256) atomic_add_s16(P + at(im.list[1][i]), e);
+	}
+	if (q >= 19) {
+		for (int i = t; i < im.list_len[5]; i += 256) { const int a = at(im.list[5][i]); atomic_add_s16(P + a, -4); atomic_add_s16(P + a + YW, -3); }
+		for (int i = t; i < im.list_len[4]; i += 256) { const int a = at(im.list[4][i]); atomic_add_s16(P + a, 4); atomic_add_s16(P + a + YW, 3); }
+		for (int i = t; i < im.list_len[6]; i += 256) { const int a = at(im.list[6][i]); atomic_add_s16(P + a, 2); atomic_add_s16(P + a + YW, 2); atomic_add_s16(P + a + 2 * YW, 2); }
+		for (int i = t; i < im.list_len[7]; i += 256) { const int a = at(im.list[7][i]); atomic_add_s16(P + a, -2); atomic_add_s16(P + a + YW, -2); atomic_add_s16(P + a + 2 * YW, -2); }
+	}
+}
+
+// ---- D12: flagged positions in raster order, flags removed (nhw_decoder.c:827-839); thread = row
+__global__ void __launch_bounds__(256) kd_edge_compact(DecBatch b)
+{
+	__shared__ int cnt[257];
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.x, 0);
+	const int r = threadIdx.x;
+	int16_t *row = im.proc + r * YW;
+	int n = 0;
+	if (r >= 1 && r < 255)
+		for (int j = 0; j < 256; j += 2) {
+			const uint32_t w = *reinterpret_cast<const uint32_t *>(row + j);
+			n += ((int16_t)(w & 0xffff) > 10000) + ((int16_t)(w >> 16) > 10000);
+		}
+	cnt[r] = n;
+	__syncthreads();
+	if (r == 0) {
+		int run = 0;
+		for (int k = 0; k < 256; k++) { const int v = cnt[k]; cnt[k] = run; run += v; }
+		im.list_len[9] = run;
+	}
+	__syncthreads();
+	if (n) {
+		int o = cnt[r];
+		for (int j = 0; j < 256; j++)
+			if (row[j] > 10000) { im.flags[o++] = (uint16_t)((r << 8) + j); row[j] -= 16000; }
+	}
+}
+
+// ---- D16: 2x chroma upsample (clip fused), one thread per chroma cell
+__global__ void __launch_bounds__(256) kd_upsample_uv(DecBatch b)
+{
+	const int img = blockIdx.y >> 1, v = blockIdx.y & 1;
+	if (b.status[img] != 0) return;
+	const DecImg im = make_dec(b, img, v);
+	dec_c_upsample_cell(im.cproc, im.yuv + (size_t)(1 + v) * 262144, blockIdx.x, threadIdx.x);
+}
 
 // ---- inverse filter passes (upfilter53I + III / VI, decoder/filters.c:143-194)
 // rows: every row k of the band plane -> 2M outputs, optionally normalised
@@ -167,6 +296,19 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	b.uvcoef = c->y_aux2 + NHW_GUARD_S;
 	b.c_proc = c->c_proc + NHW_GUARD_S; b.c_jpeg = c->c_jpeg + NHW_GUARD_S; b.c_aux = c->c_aux + NHW_GUARD_S;
 	b.bytes = c->enc_bytes; b.yuv = c->dec_yuv;
+	{
+		static bool tables[64] = {false};
+		if (!tables[c->device & 63]) {
+			static uint16_t lut[1 << NHW_LUT_BITS];
+			dec_build_lut(lut);
+			cudaMemcpyToSymbolAsync(g_dec_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, c->stream);
+			cudaStreamSynchronize(c->stream);
+			tables[c->device & 63] = true;
+		}
+		void *p = nullptr;
+		cudaGetSymbolAddress(&p, g_dec_lut);
+		b.lut = static_cast<const uint16_t *>(p);
+	}
 	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT;
 
 	// coefficient planes start at zero: zero runs are skipped, not written (decoder/nhw_decoder.c:2029)
@@ -174,7 +316,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH(c, kd_zero, dim3(131072 * 2 / 16 / 256, n), 256, 0, b.uvcoef, YS, (size_t)(131072 * 2 / 16));
 
 	// ---- luma
-	d_image(c, "d_ll_prefix_y", b, n, [=] __device__(const DecImg &im, int i) {
+	d_image_lut(c, "d_ll_prefix_y", b, n, [=] __device__(const DecImg &im, int i) {
 		dec_ll_dpcm(im);
 		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 2048;
 		dec_build_book(im.blob + im.d->off_tree1, im.d->size_tree1, 3, -1, im.book, btmp);
@@ -185,16 +327,13 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	d_image(c, "d_lists", b, n, [=] __device__(const DecImg &im, int) {
 		dec_lists_image(im, reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(im.flags) + 131072));
 	});
-	d_image(c, "d_markers_ll_shrink", b, n, [=] __device__(const DecImg &im, int) {
-		dec_y_markers_image(im);
-		im.list_len[10] = dec_y_ll_image(im);
-		dec_y_shrink_image(im);
-	});
+	d_image(c, "d_markers_y", b, n, [=] __device__(const DecImg &im, int) { dec_y_markers_image(im); });
+	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
+	d_wavefront(c, "d_shrink_y", b, n, 1, dwf_shrink_geom(), [=] __device__(const DecImg &im, int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
 	idwt_rows_cols(c, n, b.y_jpeg, b.y_aux, b.y_proc, YS, 256, 512);
-	d_image(c, "d_addbacks_flags", b, n, [=] __device__(const DecImg &im, int) {
-		dec_y_addbacks_image(im);
-		dec_y_edge_flags_image(im);
-	});
+	NHW_LAUNCH_L(c, "d_addbacks", kd_addbacks, n, 256, 0, b);
+	d_wavefront(c, "d_edge_flags", b, n, 1, dwf_edge_geom(), [=] __device__(const DecImg &im, int r, int p) { return dwf_edge_cell(im.proc, r, p); });
+	NHW_LAUNCH_L(c, "d_edge_compact", kd_edge_compact, n, 256, 0, b);
 	NHW_LAUNCH(c, kd_transpose, dim3(8, 8, n), 256, 0, b.y_proc, b.y_jpeg, YS, YS, 512);
 	NHW_LAUNCH_L(c, "d_inv_rows512", (kd_inv_rows<256, false>), dim3(512 / 8, n), 256, 0, b.y_jpeg, b.y_proc, YS, YS, 512);
 	NHW_LAUNCH(c, kd_transpose, dim3(16, 16, n), 256, 0, b.y_proc, b.y_jpeg, YS, YS, 512);
@@ -203,7 +342,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH(c, kd_clip_y, dim3(262144 / 256, n), 256, 0, b);
 
 	// ---- chroma
-	d_image(c, "d_prefix_uv", b, n, [=] __device__(const DecImg &im, int i) {
+	d_image_lut(c, "d_prefix_uv", b, n, [=] __device__(const DecImg &im, int i) {
 		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 2048;
 		for (int k = 0; k < 1024; k++) im.book[k] = 0;
 		dec_build_book(im.blob + im.d->off_tree2, im.d->size_tree2, 128, im.d->tree_end, im.book, btmp);
@@ -222,10 +361,10 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	d_plane(c, "d_markers_uv", b, n, [=] __device__(const DecImg &im, int) { dec_c_markers_image(im); });
 	NHW_LAUNCH(c, kd_transpose, dim3(4, 4, 2 * n), 256, 0, b.c_proc, b.c_jpeg, CS, CS, 256);
 	idwt_rows_cols(c, 2 * n, b.c_jpeg, b.c_aux, b.c_proc, CS, 256, 256);
-	d_plane(c, "d_sharpen_uv", b, n, [=] __device__(const DecImg &im, int) { dec_c_sharpen_image(im); });
-	d_plane_rows(c, "d_upsample_uv", b, n, 512, [=] __device__(const DecImg &im, int y, int v) {
-		dec_c_upsample_row(im.cproc, im.yuv + (size_t)(1 + v) * 262144, y);
+	d_wavefront(c, "d_sharpen_uv", b, n, 2, dwf_sharpen_geom(), [=] __device__(const DecImg &im, int r, int j) {
+		return dwf_sharpen_cell(im.cproc, im.d->quality <= 14 ? 35 : 60, r, j);
 	});
+	NHW_LAUNCH_L(c, "d_upsample_uv", kd_upsample_uv, dim3(256, 2 * n), 256, 0, b);
 
 	// ---- colour
 	NHW_LAUNCH(c, kd_color, dim3(262144 / 256, n), 256, 0, b, rgb_dev);

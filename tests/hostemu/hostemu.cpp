@@ -12,7 +12,7 @@
 #include <string.h>
 #include <vector>
 
-#include "../../nhwcodec_b200/csrc/dec_stages.cuh"
+#include "../../nhwcodec_b200/csrc/dec_par.cuh"
 #include "../../nhwcodec_b200/csrc/dec_parse.h"
 #include "../../nhwcodec_b200/csrc/enc_point.cuh"
 
@@ -331,6 +331,9 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	im.res_comp = res_comp.data();
 	for (int k = 0; k < 8; k++) im.list[k] = lists.data() + k * 65536;
 	im.list_len = list_len; im.flags = flags.data(); im.book = book.data(); im.yuv = yuv.data();
+	std::vector<uint16_t> lut(4096);
+	dec_build_lut(lut.data());
+	im.lut = lut.data();
 
 	dec_ll_dpcm(im);
 	dec_build_book(blob + d.off_tree1, d.size_tree1, 3, -1, im.book, btmp.data());
@@ -340,10 +343,21 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	dec_lists_image(im, ltmp.data());
 	dec_y_markers_image(im);
 	int exw = dec_y_ll_image(im);
-	dec_y_shrink_image(im);
+	if (getenv("HE_SERIAL")) dec_y_shrink_image(im);
+	else host_wavefront(dwf_shrink_geom(), [&](int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
 	inv_level(im.jpeg, im.proc, 512, 256, tmp);                 // LL1 reconstruction, natural orientation
 	dec_y_addbacks_image(im);
-	dec_y_edge_flags_image(im);
+	if (getenv("HE_SERIAL")) dec_y_edge_flags_image(im);
+	else {
+		host_wavefront(dwf_edge_geom(), [&](int r, int p) { return dwf_edge_cell(im.proc, r, p); });
+		int n = 0;
+		for (int r = 1; r < 255; r++)
+			for (int j = 0; j < 256; j++) {
+				const int s = r * 512 + j;
+				if (im.proc[s] > 10000) { im.flags[n++] = (uint16_t)((r << 8) + j); im.proc[s] -= 16000; }
+			}
+		im.list_len[9] = n;
+	}
 	transpose_sq(im.proc, im.jpeg, 512, 256);
 	inv_rows(im.jpeg, 512, im.proc, 512, 512, 256, false);      // wavelet_synthesis2: first half
 	transpose_sq(im.proc, im.jpeg, 512, 512);
@@ -362,8 +376,14 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 		dec_c_markers_image(im);
 		transpose_sq(im.cproc, im.cjpeg, 256, 128);
 		inv_level(im.cjpeg, im.cproc, 256, 256, tmp);
-		dec_c_sharpen_image(im);
-		for (int y = 511; y >= 0; y--) dec_c_upsample_row(im.cproc, im.yuv + (1 + v) * 262144, y);
+		if (getenv("HE_SERIAL")) {
+			dec_c_sharpen_image(im);
+			for (int y = 511; y >= 0; y--) dec_c_upsample_row(im.cproc, im.yuv + (1 + v) * 262144, y);
+		} else {
+			const int thr = d.quality <= 14 ? 35 : 60;
+			host_wavefront(dwf_sharpen_geom(), [&](int r, int j) { return dwf_sharpen_cell(im.cproc, thr, r, j); });
+			for (int i = 65535; i >= 0; i--) dec_c_upsample_cell(im.cproc, im.yuv + (1 + v) * 262144, i >> 8, i & 255);
+		}
 	}
 	DecColor col;
 	col.mode = d.quality >= 20 ? 0 : d.quality >= 18 ? 1 : 2;

@@ -47,6 +47,27 @@ def host_encode(y_pre, u8, v8, q, want_taps=True):
     return (out[:n].tobytes() if n > 0 else n), taps, order
 
 
+def host_decode(stream):
+    """host-compiled decoder stage functions, run in the kernels' order -> 786432 pixel bytes"""
+    L = lib()
+    L.he_decode.restype = ctypes.c_int
+    L.he_decode.argtypes = [ctypes.c_char_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p]
+    rgb = np.zeros(786432, dtype=np.uint8)
+    yuv = np.zeros(786432, dtype=np.uint8)
+    rc = L.he_decode(stream, len(stream), rgb.ctypes.data, yuv.ctypes.data)
+    return rc, rgb, yuv
+
+
+def compare_decode(pix, q, verbose=True):
+    stream = refbind.ref_encode(pix, q)
+    want = refbind.ref_decode(stream)
+    rc, rgb, _ = host_decode(stream)
+    ok = rc == 0 and np.array_equal(rgb, np.asarray(want).reshape(-1))
+    if verbose:
+        print("decode:", "BIT-EXACT" if ok else "DIFFERENT (rc=%d)" % rc)
+    return ok
+
+
 def compare(pix, q, verbose=True):
     ref_stream, rt = refbind.ref_encode_taps(pix, q)
     y_pre = rt["y_pre"].view(np.int16)
@@ -93,4 +114,7 @@ if __name__ == "__main__":
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     q = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     pix = {"natural": synth.natural, "noise": synth.noise, "textured": synth.textured}[kind](seed)
-    compare(pix, q)
+    if os.environ.get("HE_DECODE"):
+        compare_decode(pix, q)
+    else:
+        compare(pix, q)
