@@ -83,18 +83,31 @@ struct BitReader {
 	}
 };
 
-// Primary decode table of the static prefix code: entry for the next 12 bits = (length << 10) | rank for
-// every code of at most 12 bits, 0 where a longer code (13..20 bits, ranks NHW_LONG_FIRST..) starts.
+// Decode tables of the static prefix code, two levels.  Level 1 is indexed by the next 12 bits:
+// (length << 10) | rank for every code of at most 12 bits; 0x8000 | k where longer codes (13..20
+// bits, ranks NHW_LONG_FIRST..) start, k selecting a 256-entry level-2 table indexed by the 8 bits
+// that follow; 0 = no code.  Level-2 entries have the same (length << 10) | rank form.
 #define NHW_LUT_BITS 12
 #define NHW_LONG_FIRST 98
-inline void dec_build_lut(uint16_t *lut /* 4096 */)
+#define NHW_LUT2_TABLES 8
+#define NHW_LUT_WORDS ((1 << NHW_LUT_BITS) + NHW_LUT2_TABLES * 256)
+inline void dec_build_lut(uint16_t *lut /* NHW_LUT_WORDS */)
 {
-	for (int i = 0; i < (1 << NHW_LUT_BITS); i++) lut[i] = 0;
+	for (int i = 0; i < NHW_LUT_WORDS; i++) lut[i] = 0;
+	int ntab = 0;
 	for (int r = 0; r < NHW_CODE_DEPTH; r++) {
 		const int len = h_nhw_code_len[r];
-		if (len > NHW_LUT_BITS) continue;
-		const uint32_t first = h_nhw_code_bits[r] << (NHW_LUT_BITS - len);
-		for (uint32_t k = 0; k < (1u << (NHW_LUT_BITS - len)); k++) lut[first + k] = (uint16_t)((len << 10) | r);
+		const uint32_t code = h_nhw_code_bits[r];
+		if (len <= NHW_LUT_BITS) {
+			const uint32_t first = code << (NHW_LUT_BITS - len);
+			for (uint32_t k = 0; k < (1u << (NHW_LUT_BITS - len)); k++) lut[first + k] = (uint16_t)((len << 10) | r);
+		} else {
+			const uint32_t p = code >> (len - NHW_LUT_BITS);
+			if (!lut[p]) lut[p] = (uint16_t)(0x8000 | ntab++);
+			uint16_t *sub = lut + (1 << NHW_LUT_BITS) + (lut[p] & 255) * 256;
+			const uint32_t rest = (code << (20 - len)) & 255u;   // the code's bits 13..20, left aligned
+			for (uint32_t k = 0; k < (1u << (20 - len)); k++) sub[rest + k] = (uint16_t)((len << 10) | r);
+		}
 	}
 }
 
@@ -107,20 +120,12 @@ NHW_HD int dec_next_rank(BitReader &br, bool zone, const uint16_t *lut)
 		br.skip(15);
 		return r;
 	}
-	const int ent = lut[v >> (20 - NHW_LUT_BITS)];
-	if (ent) {
-		const int r = ent & 1023;
-		br.skip(ent >> 10);
-		return (zone && r >= 110) ? r + 64 : r;
-	}
-	for (int r = NHW_LONG_FIRST; r < NHW_CODE_DEPTH; r++) {
-		const int len = nhw_code_len[r];
-		if ((v >> (20 - len)) == nhw_code_bits[r]) {
-			br.skip(len);
-			return (zone && r >= 110) ? r + 64 : r;
-		}
-	}
-	return -1;
+	int ent = lut[v >> (20 - NHW_LUT_BITS)];
+	if (ent & 0x8000) ent = lut[(1 << NHW_LUT_BITS) + ((ent & 255) << 8) + (v & 255u)];
+	if (!ent) return -1;
+	const int r = ent & 1023;
+	br.skip(ent >> 10);
+	return (zone && r >= 110) ? r + 64 : r;
 }
 
 // ---- codebook: un-RLE, re-interleave, build rank -> symbol table (compress_pixel.c:92-118, 455-478)
@@ -268,8 +273,22 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 	uint8_t *o = im.res_comp;
 	const int q = d->quality, mode = d->byte0 & 3;
 	int j = 1, i = 1, a = 0;
-	o[0] = ch[0];
-	auto rel = [&](int delta) { o[j] = (uint8_t)(o[j - 1] + delta); j++; };
+	// `last` mirrors o[j-1] (without the chroma LSBs added on the way out, see below), so that the
+	// recurrence runs in registers instead of through memory
+	uint8_t last = ch[0];
+	o[0] = last;
+	const uint8_t *ub = im.blob + d->off_u64, *vb = im.blob + d->off_v64;
+	auto emit = [&](int v) {
+		last = (uint8_t)v;
+		uint8_t w = last;
+		if (j >= 16384 && q > 15) {   // res_U_64 / res_V_64 LSB planes (nhw_decoder.c:1983-2026)
+			const int k = (j - 16384) & 4095;
+			const uint8_t *pl = j < 20480 ? ub : vb;
+			w = (uint8_t)(w + (((pl[k >> 3] >> (7 - (k & 7))) & 1) << 1));
+		}
+		o[j++] = w;
+	};
+	auto rel = [&](int delta) { emit(last + delta); };
 	auto triple = [&](int c0, int c1) {   // 3 deltas packed in two bytes (marker 64)
 		rel((((c0 >> 1) & 31) << 1) - 32);
 		rel(((((c0 & 1) << 3) | (c1 >> 5)) << 1) - 16);
@@ -278,13 +297,13 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 	for (; j < 16384; i++) {
 		const int c = ch[i];
 		if (c >= 128) {
-			if (q > 15) o[j++] = hr[a++];
-			o[j++] = (uint8_t)((c - 128) << 1);
+			if (q > 15) emit(hr[a++]);
+			emit((c - 128) << 1);
 		} else if (mode == 0) {
 			if (c < 16) {
 				const int run = (c >> 3) & 1;
-				const uint8_t v = o[j - 1];
-				for (int e = 0; e < run + 2; e++) o[j++] = v;
+				const uint8_t v = last;
+				for (int e = 0; e < run + 2; e++) emit(v);
 				const int k = c & 7;
 				if (k == 1) rel(2);
 				else if (k == 2) { rel(2); rel(-2); }
@@ -304,8 +323,8 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 		} else if (mode == 1) {
 			if (c < 32) {
 				const int run = (c >> 2) & 7;
-				const uint8_t v = o[j - 1];
-				for (int e = 0; e < run + 2; e++) o[j++] = v;
+				const uint8_t v = last;
+				for (int e = 0; e < run + 2; e++) emit(v);
 				const int k = c & 3;
 				if (k == 1) rel(2);
 				else if (k == 2) rel(-2);
@@ -318,13 +337,14 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 		} else {
 			if (c < 64) {
 				const int run = c & 63;
-				const uint8_t v = o[j - 1];
-				for (int e = 0; e < run + 2; e++) o[j++] = v;
+				const uint8_t v = last;
+				for (int e = 0; e < run + 2; e++) emit(v);
 			} else { i++; triple(c - 64, ch[i]); }
 		}
 	}
-	o[16384] = ch[i++];
-	for (j = 16385; j < 24576; i++) {
+	j = 16384;
+	emit(ch[i++]);
+	for (; j < 24576; i++) {
 		const int c = ch[i];
 		if (c >= 192) {
 			const int x = c - 192, k = x >> 2;
@@ -334,15 +354,15 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 			rel(d1);
 			const int m = x & 3;
 			rel(m == 0 ? 0 : m == 1 ? 4 : m == 2 ? -4 : 8);
-		} else if (c >= 128) o[j++] = (uint8_t)((c - 128) << 2);
+		} else if (c >= 128) emit((c - 128) << 2);
 		else if (c >= 64) {
 			int run = (c >> 3) & 7;
-			const uint8_t v = o[j - 1];
+			const uint8_t v = last;
 			if (run == 7) {
 				run = (c & 7) + 7;
-				for (int e = 0; e < run + 2; e++) o[j++] = v;
+				for (int e = 0; e < run + 2; e++) emit(v);
 			} else {
-				for (int e = 0; e < run + 2; e++) o[j++] = v;
+				for (int e = 0; e < run + 2; e++) emit(v);
 				const int k = c & 7;
 				if (k == 1) rel(4);
 				else if (k == 2) { rel(4); rel(-4); }
@@ -355,13 +375,6 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 		} else {
 			rel(((c >> 3) << 2) - 16);
 			rel(((c & 7) << 2) - 16);
-		}
-	}
-	if (q > 15) {
-		const uint8_t *u = im.blob + d->off_u64, *v = im.blob + d->off_v64;
-		for (int k = 0; k < 4096; k++) {
-			o[16384 + k] = (uint8_t)(o[16384 + k] + (((u[k >> 3] >> (7 - (k & 7))) & 1) << 1));
-			o[20480 + k] = (uint8_t)(o[20480 + k] + (((v[k >> 3] >> (7 - (k & 7))) & 1) << 1));
 		}
 	}
 }

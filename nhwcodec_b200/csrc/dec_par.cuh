@@ -68,3 +68,64 @@ NHW_HD void dec_c_upsample_cell(const int16_t *P, uint8_t *out /* 512x512 */, in
 	o[512] = (uint8_t)b0;
 	o[513] = (uint8_t)(c < 255 ? (b0 + b1 + 1) >> 1 : b0);
 }
+
+// ---- D4 in parallel form ---------------------------------------------------------------------
+// dec_y_markers_image walks the band plane in three sweeps (rows 0..255; rows 256..511 left half;
+// rows 256..511 right half).  Marker codes (> 1000) are sparse and only WRITE constants, so they are
+// collected in sweep order and applied one after the other (a marker overwritten before its turn
+// is no longer one: re-checked when applied).  The right-half sweep also nudges |v| in 9..15 by one
+// when at least two of its 4-neighbours are small, in place; a nudged cell stays >= 9 in magnitude,
+// so the only things a cell's test can see change are marker writes.  For the cell at s, in sweep
+// order: the left and upper neighbours have had ALL their writers' turns (writers sit at most one
+// cell to the right), the right and lower neighbours none -- so the test reads the plane after the
+// markers (J) for the former and a snapshot taken before them (S) for the latter.
+// W: cells of the right half written by a right-half marker.  A: cells holding an applied 1008/1009.
+NHW_HD void dec_marker_apply(int16_t *J, int s, bool lower, uint32_t *W, uint32_t *A)
+{
+	const int v = J[s];
+	if (v <= 1000) return;
+	const int j = s & 511;
+	auto mark = [&](int t) {   // t in the right half of the lower rows
+		if (W && (t & 511) >= 256 && (t >> 9) >= 256 && (t >> 9) < 512) {
+			const int k = (((t >> 9) - 256) << 8) + ((t & 511) - 256);
+			W[k >> 5] |= 1u << (k & 31);
+		}
+	};
+	if (!lower) {
+		if (v == 1008) { J[s - 1] = 5; J[s + 1] = 5; J[s] = (int16_t)(j < 256 ? 5 : 6); }
+		else if (v == 1009) { J[s - 1] = -5; J[s + 1] = -5; J[s] = (int16_t)(j < 256 ? -6 : -7); }
+		else if (v == 1010) { J[s] = 5; J[s + 1] = 5; J[s + YW] = 5; J[s + YW + 1] = 5; }
+		else if (v == 1011) { J[s] = -5; J[s + 1] = -5; J[s + YW] = -5; J[s + YW + 1] = -5; }
+		else if (v == 1006) { J[s] = -6; J[s + 1] = -6; }
+		else if (v == 1007) { J[s] = 6; J[s + 1] = 6; }
+		return;
+	}
+	if (v == 1008 || v == 1009) {
+		const int sg = v == 1008 ? 1 : -1;
+		J[s - 1] = (int16_t)(5 * sg); J[s] = (int16_t)(v == 1008 ? 6 : -7); J[s + 1] = (int16_t)(5 * sg);
+		mark(s - 1); mark(s); if (j < 511) mark(s + 1);
+		if (A && j >= 256) {
+			const int k = (((s >> 9) - 256) << 8) + (j - 256);
+			A[k >> 5] |= 1u << (k & 31);
+		}
+	} else if (v == 1006 || v == 1007) {
+		const int16_t w = (int16_t)(v == 1006 ? -7 : 7);
+		if (j < 256) { J[s] = w; J[s + 1] = w; mark(s + 1); }
+		else { J[s - 256] = w; J[s - 768] = w; J[s] = 0; mark(s); }
+	}
+}
+
+// the nudge rule of the right-half sweep for cell s = (r, j), 256 <= r, 256 < j < 511.
+// S = snapshot of the plane before the right-half markers, J = plane after them.
+NHW_HD bool dec_dense_qualifies(const int16_t *S, const uint32_t *A, int s)
+{
+	const int k = (((s >> 9) - 256) << 8) + ((s & 511) - 256);
+	if ((A[(k - 1) >> 5] >> ((k - 1) & 31)) & 1u) return false;   // an applied 1008/1009 on the left rewrote this cell first
+	const int v = S[s];
+	return v <= 1000 && nhw_iabs(v) > 8 && nhw_iabs(v) < 16;
+}
+NHW_HD int dec_dense_count(const int16_t *J, const int16_t *S, int s)
+{
+	const int below = (s >> 9) < 511 ? (int)S[s + YW] : 0;   // past the last row: the zero guard
+	return (nhw_iabs(J[s - 1]) < 8) + (nhw_iabs(S[s + 1]) < 8) + (nhw_iabs(J[s - YW]) < 8) + (nhw_iabs(below) < 8);
+}

@@ -39,7 +39,7 @@ struct DecBatch {
 	const uint16_t *lut;          // primary prefix-code table (device memory)
 };
 
-__device__ uint16_t g_dec_lut[1 << NHW_LUT_BITS];
+__device__ uint16_t g_dec_lut[NHW_LUT_WORDS];
 
 __device__ __forceinline__ DecImg make_dec(const DecBatch &b, int i, int comp)
 {
@@ -75,8 +75,8 @@ __global__ void kd_image(DecBatch b, int n, F f)
 template <typename F>
 __global__ void __launch_bounds__(32) kd_image_lut(DecBatch b, int n, F f)
 {
-	__shared__ uint16_t slut[1 << NHW_LUT_BITS];
-	for (int k = threadIdx.x; k < (1 << NHW_LUT_BITS) / 8; k += 32)
+	__shared__ __align__(16) uint16_t slut[NHW_LUT_WORDS];
+	for (int k = threadIdx.x; k < NHW_LUT_WORDS / 8; k += 32)
 		reinterpret_cast<uint4 *>(slut)[k] = reinterpret_cast<const uint4 *>(b.lut)[k];
 	__syncwarp();
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,6 +131,86 @@ template <typename Cell>
 void d_wavefront(nhw_ctx *c, const char *l, const DecBatch &b, int n, int ppi, WfGeom g, Cell cell)
 {
 	NHW_LAUNCH_L(c, l, kd_wavefront, n * ppi, 256, 0, b, g, ppi, cell);
+}
+
+// ---- D4: marker expansion + right-half nudges in parallel form (dec_par.cuh).  One CTA per image.
+// Sweep rows ("slots"): 0..255 = rows 0..255 (all 512 columns), 256..511 = rows 256..511 left half,
+// 512..767 = rows 256..511 right half.  Candidates are compacted in sweep order (count, prefix, write),
+// one thread applies them; the snapshot and the candidate list live in the scratch plane (im.aux).
+#define MK_CAP 32768
+__global__ void __launch_bounds__(256) kd_y_markers(DecBatch b)
+{
+	__shared__ int cnt[768 + 1];
+	__shared__ uint32_t W[2048], A[2048];
+	__shared__ int first_q, fallback;
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.x, 0);
+	int16_t *J = im.jpeg, *S = im.aux;
+	int *cand = reinterpret_cast<int *>(im.aux);   // rows 0..127 of the scratch plane (the snapshot uses rows >= 255)
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	auto slot_cells = [&](int slot, int &base, int &n) {
+		if (slot < 256) { base = slot * YW; n = 512; }
+		else if (slot < 512) { base = slot * YW; n = 256; }
+		else { base = (slot - 256) * YW + 256; n = 256; }
+	};
+	for (int k = tid; k < 2048; k += 256) { W[k] = 0; A[k] = 0; }
+	if (tid == 0) { first_q = 1 << 30; fallback = 0; }
+	for (int slot = warp; slot < 768; slot += 8) {
+		int base, n, c = 0;
+		slot_cells(slot, base, n);
+		for (int j = lane; j < n; j += 32) c += __popc(__ballot_sync(0xffffffffu, J[base + j] > 1000));
+		if (lane == 0) cnt[slot] = c;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		int run = 0;
+		for (int k = 0; k < 768; k++) { const int v = cnt[k]; cnt[k] = run; run += v; }
+		cnt[768] = run;
+		if (run > MK_CAP) { fallback = 1; dec_y_markers_image(im); }   // never seen; keeps the stage total
+	}
+	__syncthreads();
+	if (fallback) return;
+	for (int slot = warp; slot < 768; slot += 8) {
+		int base, n, o = cnt[slot];
+		slot_cells(slot, base, n);
+		for (int j = lane; j < n; j += 32) {
+			const bool m = J[base + j] > 1000;
+			const uint32_t bal = __ballot_sync(0xffffffffu, m);
+			if (m) cand[o + __popc(bal & ((1u << lane) - 1u))] = base + j;
+			o += __popc(bal);
+		}
+	}
+	__syncthreads();
+	const int n12 = cnt[512], n3 = cnt[768];
+	if (tid == 0) {
+		const int n1 = cnt[256];
+		for (int k = 0; k < n1; k++) dec_marker_apply(J, cand[k], false, nullptr, nullptr);
+		for (int k = n1; k < n12; k++) dec_marker_apply(J, cand[k], true, nullptr, nullptr);
+	}
+	__syncthreads();
+	// snapshot of rows 255..511, columns 256..511, before the right-half markers
+	for (int idx = tid; idx < 257 * 32; idx += 256) {
+		const int r = 255 + (idx >> 5), c8 = (idx & 31) * 8;
+		*reinterpret_cast<uint4 *>(S + r * YW + 256 + c8) = *reinterpret_cast<const uint4 *>(J + r * YW + 256 + c8);
+	}
+	__syncthreads();
+	if (tid == 0)
+		for (int k = n12; k < n3; k++) dec_marker_apply(J, cand[k], true, W, A);
+	__syncthreads();
+	for (int r = 256 + warp; r < 512; r += 8)
+		for (int j = 257 + lane; j < 511; j += 32) {
+			const int s = r * YW + j;
+			if (dec_dense_qualifies(S, A, s)) atomicMin(&first_q, s);
+		}
+	__syncthreads();
+	const int first = first_q, stale = im.list_len[8];
+	for (int r = 256 + warp; r < 512; r += 8)
+		for (int j = 257 + lane; j < 511; j += 32) {
+			const int s = r * YW + j, k = ((r - 256) << 8) + (j - 256);
+			if (!dec_dense_qualifies(S, A, s)) continue;
+			const int c = dec_dense_count(J, S, s) + (s == first ? stale : 0);
+			if (c >= 2 && !((W[k >> 5] >> (k & 31)) & 1u)) J[s] += S[s] > 0 ? 1 : -1;
+		}
 }
 
 // ---- D5-D7: LL2 fill in parallel, then the two short override lists
@@ -299,7 +379,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	{
 		static bool tables[64] = {false};
 		if (!tables[c->device & 63]) {
-			static uint16_t lut[1 << NHW_LUT_BITS];
+			static uint16_t lut[NHW_LUT_WORDS];
 			dec_build_lut(lut);
 			cudaMemcpyToSymbolAsync(g_dec_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, c->stream);
 			cudaStreamSynchronize(c->stream);
@@ -327,7 +407,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	d_image(c, "d_lists", b, n, [=] __device__(const DecImg &im, int) {
 		dec_lists_image(im, reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(im.flags) + 131072));
 	});
-	d_image(c, "d_markers_y", b, n, [=] __device__(const DecImg &im, int) { dec_y_markers_image(im); });
+	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
 	d_wavefront(c, "d_shrink_y", b, n, 1, dwf_shrink_geom(), [=] __device__(const DecImg &im, int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
 	idwt_rows_cols(c, n, b.y_jpeg, b.y_aux, b.y_proc, YS, 256, 512);

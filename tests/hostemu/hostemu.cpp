@@ -331,7 +331,7 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	im.res_comp = res_comp.data();
 	for (int k = 0; k < 8; k++) im.list[k] = lists.data() + k * 65536;
 	im.list_len = list_len; im.flags = flags.data(); im.book = book.data(); im.yuv = yuv.data();
-	std::vector<uint16_t> lut(4096);
+	std::vector<uint16_t> lut(NHW_LUT_WORDS);
 	dec_build_lut(lut.data());
 	im.lut = lut.data();
 
@@ -341,7 +341,30 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	if (rc) return rc;
 	for (int s = 127; s >= 0; s--) dec_y_descan_strip(im.proc, im.jpeg, s);
 	dec_lists_image(im, ltmp.data());
-	dec_y_markers_image(im);
+	if (getenv("HE_SERIAL")) dec_y_markers_image(im);
+	else {   // parallel form (dec_par.cuh), phases in the kernel's order
+		int16_t *J = im.jpeg;
+		std::vector<int> c1, c2, c3;
+		for (int r = 0; r < 256; r++) for (int j = 0; j < 512; j++) if (J[r * 512 + j] > 1000) c1.push_back(r * 512 + j);
+		for (int r = 256; r < 512; r++) for (int j = 0; j < 256; j++) if (J[r * 512 + j] > 1000) c2.push_back(r * 512 + j);
+		for (int r = 256; r < 512; r++) for (int j = 256; j < 512; j++) if (J[r * 512 + j] > 1000) c3.push_back(r * 512 + j);
+		for (int s : c1) dec_marker_apply(J, s, false, nullptr, nullptr);
+		for (int s : c2) dec_marker_apply(J, s, true, nullptr, nullptr);
+		std::vector<int16_t> S(J, J + 512 * 512);
+		std::vector<uint32_t> W(2048, 0), A(2048, 0);
+		for (int s : c3) dec_marker_apply(J, s, true, W.data(), A.data());
+		int first = 1 << 30;
+		for (int r = 511; r >= 256; r--) for (int j = 510; j > 256; j--) {
+			const int s = r * 512 + j;
+			if (dec_dense_qualifies(S.data(), A.data(), s) && s < first) first = s;
+		}
+		for (int r = 511; r >= 256; r--) for (int j = 510; j > 256; j--) {
+			const int s = r * 512 + j, k = ((r - 256) << 8) + (j - 256);
+			if (!dec_dense_qualifies(S.data(), A.data(), s)) continue;
+			const int cnt = dec_dense_count(J, S.data(), s) + (s == first ? im.list_len[8] : 0);
+			if (cnt >= 2 && !((W[k >> 5] >> (k & 31)) & 1u)) J[s] += S[s] > 0 ? 1 : -1;
+		}
+	}
 	int exw = dec_y_ll_image(im);
 	if (getenv("HE_SERIAL")) dec_y_shrink_image(im);
 	else host_wavefront(dwf_shrink_geom(), [&](int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
