@@ -39,27 +39,22 @@ UNIT = "MPix/s"
 # Algorithmic (compulsory) bytes per image of each kernel label, DESIGN.md section 5.
 # planes: Y int16 512x512 = 524288 B, LL1 int16 256x256 = 131072 B, chroma int16 256x256 = 131072 B.
 ALG_BYTES = {
-    "k_colorspace": 786432 + 524288 + 131072,          # RGB in; Y int16 + U,V u8 out
-    "k_pre_energy": 524288 + 524288,                   # Y in, energy plane out
-    "k_pre_apply": 524288 + 524288,
-    "k_pre_nudge": 524288 + 524288 + 524288,           # kernel plane in, Y in/out
-    "k_pre_chain": 2048 + 512,
-    "k_dwt_rows<512>": 2 * 524288,
-    "k_dwt_cols_t<512>": 2 * 524288,
-    "k_dwt_level_smem<256>": 131072 + 131072 + 131072,  # LL in, P2 out, LL1 copy out
-    "k_dwt_rows<256>": 2 * 2 * 131072,
-    "k_dwt_cols_t<256>": 2 * 2 * 131072,
-    "k_dwt_level_smem<128>": 2 * 3 * 32768,
+    # fused front end: pixels in; three level-1 luma bands + LL1 (`res256`) + 4:2:0 chroma bytes out
+    "k_front_luma": 786432 + 393216 + 131072 + 131072,
+    "k_dwt_level<256>": 131072 + 131072,                # luma level 2: LL1 in, four level-2 bands out
+    "k_dwt_level<256,u8>": 2 * (65536 + 98304 + 32768), # chroma level 1 of both planes: bytes in, 3 bands + LL out
+    "k_dwt_level<128>": 2 * (32768 + 32768),            # chroma level 2 of both planes
     "k_idwt_rows<256>": 2 * 131072,
     "k_idwt_cols_t<256>": 2 * 131072,
     "k_idwt_rows<128>": 2 * 2 * 32768,
     "k_idwt_cols_t<128>": 2 * 2 * 32768,
-    "y_offset_quant": 2 * 524288,                      # plane in, bytes-in-int16 out (in place)
+    "y_quant_scan": 524288 + 262144,                   # coefficient plane in, scan bytes out
+    "c_quant_scan": 2 * 131072 + 131072,
+    "y_e6d_correct": 2 * 131072 + 2 * 131072,          # trial reconstruction + LL1 in, both corrected out
     "y_offset_pairs": 2 * 524288 * 3 // 4,
     "y_offset_patterns": 2 * 131072,
     "y_e20_cleanup": 2 * 524288 * 3 // 4,
     "y_peephole": 2 * 262144,
-    "y_scan": 524288 + 262144,
     "entropy_pack": 2 * 393216,                        # two passes over the byte stream (+ output, added at run time)
     "y_e16_residual": 2 * 131072 + 131072,
     "y_e16b_classify": 2 * 131072 + 131072,
@@ -69,6 +64,13 @@ ALG_BYTES = {
     "y_recons0_shrink": 2 * 131072,
     "y_ll2_code": 32768 + 3 * 16384,
     "c_ll_quant": 2 * 2 * 131072,
+}
+
+
+# DRAM bytes per image (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture / images in that
+# launch) of the kernels profiled this round, and the capture they come from (profiles/).
+NCU_TRAFFIC = {
+    "k_front_luma": (1734549, "profiles/r01b_ncu_summary.md (batch 1024)"),
 }
 
 
@@ -374,20 +376,30 @@ def run_ours(args):
                             "alg_bytes_per_image": b_img, "GBps": round(gbs, 2) if gbs else None,
                             "frac": round(gbs / peak, 5) if gbs else None})
         dom = kernels[0] if kernels else None
-        front = [k for k in kernels if k["kernel"] in ("k_colorspace", "k_pre_energy", "k_pre_chain", "k_pre_apply",
-                                                         "k_pre_nudge", "k_dwt_rows<512>", "k_dwt_cols_t<512>",
-                                                         "k_dwt_level_smem<256>")]
-        front_ms = sum(k["ms_per_step"] for k in front)
+        # the front end = k_front_luma + ONE of the k_dwt_level<256> launches (the other is the closed loop's) +
+        # the chroma levels; k_dwt_level<128> likewise runs twice per step, once here
+        by = {k["kernel"]: k for k in kernels}
+        front_ms = 0.0
+        for name, part in (("k_front_luma", 1.0), ("k_dwt_level<256>", 0.5), ("k_dwt_level<256,u8>", 1.0), ("k_dwt_level<128>", 0.5)):
+            if name in by:
+                front_ms += by[name]["ms_per_step"] * part
         roofline = None
         if dom:
             roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                        "frac": dom["frac"], "traffic": None, "peak_source": peak_src, "share_of_step": dom["share"]}
+                        "frac": dom["frac"], "traffic": NCU_TRAFFIC.get(dom["kernel"], (None,))[0] and int(NCU_TRAFFIC[dom["kernel"]][0] * B),
+                        "traffic_source": NCU_TRAFFIC.get(dom["kernel"], (None, None))[1],
+                        "peak_source": peak_src, "share_of_step": dom["share"]}
         frontend = None
         if front_ms > 0:
             gbs = 1572864 * B / (front_ms / 1e3) / 1e9
-            frontend = {"what": "colour + pre-sharpen + 2-level luma DWT (the north-star 'fused colorspace+DWT' work, "
-                                "8 kernels in this round)", "ms_per_step": round(front_ms, 4),
-                        "alg_bytes_per_image": 1572864, "GBps": round(gbs, 2), "frac": round(gbs / peak, 5)}
+            fl = by.get("k_front_luma")
+            frontend = {"what": "the north-star 'fused colorspace+DWT' work: k_front_luma (colour + 4:2:0 + pre-sharpen + level-1 "
+                                "luma DWT in one pass) + luma level 2 + chroma levels 1-2 (k_dwt_level)",
+                        "ms_per_step": round(front_ms, 4), "alg_bytes_per_image": 1572864, "GBps": round(gbs, 2),
+                        "frac": round(gbs / peak, 5),
+                        "k_front_luma": None if not fl else {"ms_per_step": fl["ms_per_step"], "GBps": fl["GBps"], "frac": fl["frac"],
+                                                             "traffic": int(NCU_TRAFFIC["k_front_luma"][0] * B),
+                                                             "traffic_source": NCU_TRAFFIC["k_front_luma"][1]}}
 
         # ---------------- CPU baseline: the compiled reference on the host cores ----------------
         cpu = None
@@ -406,7 +418,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int16 (+f64 colour)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16 (integer colour; f64 on exact ties)", "data": "synthetic",
             "config": {"workload": "batch %d synthetic 512x512 RGB encode -q%d per GPU (BASELINE.json configs[1])" % (B, q),
                        "quality": q, "batch_per_gpu": B, "generator": ["natural-like", "uniform-noise", "textured"][args.kind],
                        "mean_stream_bytes": round(mean_stream, 1), "bit_exact": "verified by tests/test_encode_gpu.py",

@@ -269,7 +269,7 @@ static int finish(nhw_ctx *c, const char *what)
 	return NHW_OK;
 }
 
-static bool quality_supported(int q) { return q >= 17 && q <= 21; }
+static bool quality_supported(int q) { return q >= 17 && q <= 23; }
 
 int nhw_stage_colorspace_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quality, int pre,
                                 int16_t *y, uint8_t *u, uint8_t *v)
@@ -306,7 +306,7 @@ int nhw_stage_frontend_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int qua
 		int16_t *cl = c_ll1 ? c_ll1 + (size_t)i0 * 2 * 16384 : c->c_ll1 + NHW_GUARD_S;
 		nhw::front_fused(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, yp, y_proc ? (size_t)NHW_YPLANE : YS, yl,
 		                 y_ll1 ? (size_t)NHW_CPLANE : CS, c->c_u8, cp, c_proc ? (size_t)NHW_CPLANE : CS, cl,
-		                 c_ll1 ? (size_t)16384 : QS);
+		                 c_ll1 ? (size_t)16384 : QS, c->y_aux2 + NHW_GUARD_S, YS);
 	}
 	return finish(c, "nhw_stage_frontend_device");
 }
@@ -323,7 +323,7 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
                             uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev)
 {
 	if (!c || !rgb_dev || !out_dev || n <= 0) return NHW_ERR_ARG;
-	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q21 are)", quality); return NHW_ERR_QUALITY; }
+	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q23 are)", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
@@ -338,7 +338,7 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
                      uint8_t *out, size_t out_cap, uint64_t *offsets, int32_t *status)
 {
 	if (!c || !rgb || !out || !offsets || n <= 0) return NHW_ERR_ARG;
-	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q21 are)", quality); return NHW_ERR_QUALITY; }
+	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q23 are)", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
 	// Software pipeline over sub-chunks: while the kernels of sub-chunk k run on `stream`, the pixels of
 	// sub-chunk k+1 travel host->device on `copy_stream` into the other half of the staging buffer.

@@ -18,9 +18,11 @@ struct DecDesc {   // one per image, filled on the host from the .nhw header (SU
 	int32_t size_tree1, size_tree2, size_data1, size_data2, tree_end, exw_Y_end;
 	int32_t res1_len, res1_bit_len, res3_len, res3_bit_len, res4_len, res5_len, res5_bit_len;
 	int32_t select1, select2, highres_comp_len, end_ch_res;
+	int32_t res6_len, res6_bit_len, char_res1_len, qsetting3_len;   // q22/q23
 	uint32_t off_tree1, off_tree2, off_exw, off_res1, off_res1_bit, off_res1_word, off_res4, off_res3, off_res3_bit,
 	    off_res3_word, off_res5, off_res5_bit, off_res5_word, off_sel1, off_sel2, off_u64, off_v64, off_highres,
 	    off_ch_res, off_words;
+	uint32_t off_res6, off_res6_bit, off_res6_word, off_char_res1, off_qsetting3;
 	uint32_t blob_len;
 };
 
@@ -32,7 +34,8 @@ struct DecImg {
 	int16_t *cproc, *cjpeg, *caux;    // chroma planes of one component (256x256)
 	uint8_t *res_comp;                // 24577 LL bytes
 	uint16_t *list[8];                // expanded position lists (res1 -,+ ; res5 -,+ ; res3 x4)
-	int32_t *list_len;                // 8 lengths + [8] = stale `count`, [9] = edge-flag count
+	int32_t *list_len;                // 8 lengths + [8] = stale `count`, [9] = edge-flag count, [10] = exw split, [11],[12] = hq lists
+	uint32_t *hq_list[2];             // q22/q23: res6 positions, -32 then +32 (flat indices into the half-synthesised plane)
 	uint16_t *flags;                  // edge-flag positions
 	uint16_t *book;                   // rank -> (run<<8 | byte)
 	const uint16_t *lut;              // primary table of the static prefix code (dec_build_lut)
@@ -382,15 +385,17 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 // ---- position list expansion (nhw_decoder.c:93-183 and its res5/res3 twins).
 // in: packed list (pair-delta bytes >=128, 127 = row step), LSB plane.  out: col + (row<<8).
 // Returns the number of entries; cap = 8*bit_len like the reference's calloc.
-NHW_HDN int dec_expand_list(const uint8_t *res, int len, const uint8_t *bits, int bit_len, uint16_t *out)
+#define NHW_CAP_HQ_LIST 32768
+template <typename T>
+NHW_HDN int dec_expand_list(const uint8_t *res, int len, const uint8_t *bits, int bit_len, T *out, int cap_limit = 1 << 30)
 {
-	const int cap = bit_len << 3;
+	const int cap = (bit_len << 3) < cap_limit ? (bit_len << 3) : cap_limit;
 	for (int i = 0; i < cap; i++) out[i] = 0;
 	int stage = 0, count;
 	auto last = [&]() { return stage > 0 ? (int)out[stage - 1] : 0; };   // [-1] reads the zero guard
 	int prev = res[0];                       // value of res[i-1] as the reference leaves it behind
 	if (res[0] == 127) count = 1;
-	else { out[stage++] = (uint16_t)(res[0] << 1); count = 0; }
+	else { out[stage++] = (T)(res[0] << 1); count = 0; }
 	for (int i = 1; i < len; i++) {
 		int cur = res[i];
 		if (cur >= 128) {
@@ -398,18 +403,18 @@ NHW_HDN int dec_expand_list(const uint8_t *res, int len, const uint8_t *bits, in
 			if (prev != 127) {
 				int j = (last() & 255) + (e << 1);
 				if (j >= 254) { count++; cur = 127; }
-				else out[stage++] = (uint16_t)(j + (count << 8));
+				else if (stage < cap) out[stage++] = (T)(j + (count << 8));
 				j += scan << 1;
 				if (j >= 254) { count++; cur = 127; }
-				else out[stage++] = (uint16_t)(j + (count << 8));
+				else if (stage < cap) out[stage++] = (T)(j + (count << 8));
 			} else { cur = 127; count += 2; }
 		} else if (cur == 127) count++;
 		else {
 			if ((cur << 1) < (last() & 255) && prev != 127) count++;
-			out[stage++] = (uint16_t)((cur << 1) + (count << 8));
+			if (stage < cap) out[stage++] = (T)((cur << 1) + (count << 8));
 		}
 		prev = cur;
 	}
-	for (int i = 0; i < cap; i++) out[i] = (uint16_t)(out[i] + ((bits[i >> 3] >> (7 - (i & 7))) & 1));
+	for (int i = 0; i < cap; i++) out[i] = (T)(out[i] + ((bits[i >> 3] >> (7 - (i & 7))) & 1));
 	return stage;
 }

@@ -26,7 +26,8 @@ static inline int nhw_parse_header(const uint8_t *p, size_t len, DecDesc *d)
 	if (q > 17) d->res4_len = u16();
 	if (q > 12) d->res1_bit_len = u16();
 	if (q >= 21) { d->res5_len = u16(); d->res5_bit_len = u16(); }
-	if (q > 21) return -3;                             // res6 / char_res1 side channels: not built
+	if (q > 21) { d->res6_len = u32(); d->res6_bit_len = u16(); d->char_res1_len = u16(); }
+	if (q > 22) d->qsetting3_len = u16();
 	d->select1 = u16(); d->select2 = u16();
 	if (q > 15) d->highres_comp_len = u16();
 	d->end_ch_res = u16();
@@ -38,6 +39,11 @@ static inline int nhw_parse_header(const uint8_t *p, size_t len, DecDesc *d)
 	if (q > 17) take(d->off_res4, d->res4_len);
 	if (q >= 19) { take(d->off_res3, d->res3_len); take(d->off_res3_bit, d->res3_bit_len); take(d->off_res3_word, 2 * (size_t)d->res3_bit_len); }
 	if (q >= 21) { take(d->off_res5, d->res5_len); take(d->off_res5_bit, d->res5_bit_len); take(d->off_res5_word, d->res5_bit_len); }
+	if (q > 21) {
+		take(d->off_res6, (size_t)(uint32_t)d->res6_len); take(d->off_res6_bit, d->res6_bit_len); take(d->off_res6_word, d->res6_bit_len);
+		take(d->off_char_res1, 2 * (size_t)d->char_res1_len);
+	}
+	if (q > 22) take(d->off_qsetting3, 4 * (size_t)d->qsetting3_len);
 	take(d->off_sel1, d->select1);
 	take(d->off_sel2, d->select2);
 	if (q > 15) { take(d->off_u64, 512); take(d->off_v64, 512); take(d->off_highres, d->highres_comp_len); }
@@ -45,6 +51,7 @@ static inline int nhw_parse_header(const uint8_t *p, size_t len, DecDesc *d)
 	take(d->off_words, 4 * (size_t)d->size_data2);
 	d->blob_len = (uint32_t)len;
 	if (pos > len || d->size_data1 <= 0 || d->size_data2 < d->size_data1) return -7;
-	if (q < 17) return -3;
+	if (q < 17 || q > 23) return -3;
+	if (q > 21 && (d->res6_bit_len << 3) > NHW_CAP_HQ_LIST) return -5;   // more res6 entries than the decode workspace holds
 	return 0;
 }

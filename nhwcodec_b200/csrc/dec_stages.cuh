@@ -58,6 +58,57 @@ NHW_HDN void dec_lists_image(const DecImg &im, uint16_t *tmp /* 65536 */)
 	im.list_len[8] = stale;
 }
 
+// ---- q22/q23: expand + split the res6 list (nhw_decoder.c:282-388); positions are flat indices
+// (half-row * 256 + column) into the plane after the first half of the level-1 synthesis
+NHW_HDN void dec_hq_lists_image(const DecImg &im, uint32_t *tmp /* NHW_CAP_HQ_LIST */)
+{
+	const DecDesc *d = im.d;
+	im.list_len[11] = im.list_len[12] = 0;
+	if (d->quality <= 21) return;
+	dec_expand_list(im.blob + d->off_res6, d->res6_len, im.blob + d->off_res6_bit, d->res6_bit_len, tmp, NHW_CAP_HQ_LIST);
+	const uint8_t *word = im.blob + d->off_res6_word;
+	int nm = 0, np = 0, c = 0;
+	for (int i = 0; i < d->res6_bit_len - 1; i++)
+		for (int b = 7; b >= 0; b--) {
+			if ((word[i] >> b) & 1) im.hq_list[0][nm++] = tmp[c++];
+			else im.hq_list[1][np++] = tmp[c++];
+		}
+	im.list_len[11] = nm;
+	im.list_len[12] = np;
+}
+
+// q22/q23 add-backs inside wavelet_synthesis2 (decoder/wavelet_filterbank.c:296-348), entry k of the
+// concatenation [-32 list | +32 list | char_res1 | high_qsetting3]: target cell and amount
+NHW_HD bool dec_hq_addback(const DecImg &im, int k, int &pos, int &amount)
+{
+	const DecDesc *d = im.d;
+	const int n0 = im.list_len[11], n1 = im.list_len[12];
+	if (k < n0) { pos = (int)im.hq_list[0][k]; amount = -32; return true; }
+	k -= n0;
+	if (k < n1) { pos = (int)im.hq_list[1][k]; amount = 32; return true; }
+	k -= n1;
+	if (k < d->char_res1_len) {
+		const uint8_t *p = im.blob + d->off_char_res1 + 2 * k;
+		const int v = p[0] | (p[1] << 8), m = v & 3;
+		pos = ((v - m) << 1) + (m < 2 ? 254 : 255);
+		amount = (m & 1) ? -32 : 32;
+		return true;
+	}
+	k -= d->char_res1_len;
+	if (d->quality > 22 && k < d->qsetting3_len) {
+		const uint8_t *p = im.blob + d->off_qsetting3 + 4 * k;
+		const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+		pos = (int)(v >> 1);
+		amount = (v & 1) ? -56 : 56;
+		return true;
+	}
+	return false;
+}
+NHW_HD int dec_hq_addback_count(const DecImg &im)
+{
+	return im.d->quality > 21 ? im.list_len[11] + im.list_len[12] + im.d->char_res1_len + (im.d->quality > 22 ? im.d->qsetting3_len : 0) : 0;
+}
+
 // ---- D4: marker expansion, in place and in raster order (nhw_decoder.c:493-607)
 NHW_HDN void dec_y_markers_image(const DecImg &im)
 {

@@ -23,7 +23,8 @@ enum : int {
 	DOFF_FLAGS = DOFF_LISTLEN + 256,
 	DOFF_LTMP = DOFF_FLAGS + 131072,
 	DOFF_LISTS = DOFF_LTMP + 131072 + 256,        // 8 lists x 65536 entries
-	DOFF_END = DOFF_LISTS + 8 * 131072,
+	DOFF_HQ = DOFF_LISTS + 8 * 131072,             // q22/q23: two res6 position lists, NHW_CAP_HQ_LIST x u32 each
+	DOFF_END = DOFF_HQ + 2 * 4 * NHW_CAP_HQ_LIST,
 };
 static_assert(DOFF_END <= ENC_BYTES_SLOT, "decode scratch must fit the per-image byte slot");
 
@@ -60,6 +61,8 @@ __device__ __forceinline__ DecImg make_dec(const DecBatch &b, int i, int comp)
 	im.list_len = reinterpret_cast<int32_t *>(bytes + DOFF_LISTLEN);
 	im.flags = reinterpret_cast<uint16_t *>(bytes + DOFF_FLAGS);
 	for (int k = 0; k < 8; k++) im.list[k] = reinterpret_cast<uint16_t *>(bytes + DOFF_LISTS) + (size_t)k * 65536;
+	im.hq_list[0] = reinterpret_cast<uint32_t *>(bytes + DOFF_HQ);
+	im.hq_list[1] = im.hq_list[0] + NHW_CAP_HQ_LIST;
 	im.yuv = b.yuv + (size_t)i * 786432;
 	im.lut = b.lut;
 	return im;
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(256) kd_y_markers(DecBatch b)
 	if (tid == 0)
 		for (int k = n12; k < n3; k++) dec_marker_apply(J, cand[k], true, W, A);
 	__syncthreads();
+	if (im.d->quality >= 23) return;   // the nudge rule is off at q23 (nhw_decoder.c:588)
 	for (int r = 256 + warp; r < 512; r += 8)
 		for (int j = 257 + lane; j < 511; j += 32) {
 			const int s = r * YW + j;
@@ -223,20 +227,6 @@ __global__ void __launch_bounds__(256) kd_y_ll(DecBatch b)
 	if (threadIdx.x == 0) im.list_len[10] = dec_y_ll_overrides(im);
 }
 
-// 16-bit add on a cell other threads may be adding to as well
-__device__ __forceinline__ void atomic_add_s16(int16_t *p, int v)
-{
-	uint32_t *w = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-	const bool hi = (reinterpret_cast<uintptr_t>(p) & 2) != 0;
-	uint32_t old = *w, assumed;
-	do {
-		assumed = old;
-		const uint32_t cur = hi ? assumed >> 16 : assumed & 0xffffu;
-		const uint32_t nv = (cur + (uint32_t)v) & 0xffffu;
-		old = atomicCAS(w, assumed, hi ? (assumed & 0xffffu) | (nv << 16) : (assumed & 0xffff0000u) | nv);
-	} while (old != assumed);
-}
-
 // ---- D10: residual add-backs (nhw_decoder.c:721-787): commutative += / -= at listed positions
 __global__ void __launch_bounds__(256) kd_addbacks(DecBatch b)
 {
@@ -259,6 +249,18 @@ __global__ void __launch_bounds__(256) kd_addbacks(DecBatch b)
 		for (int i = t; i < im.list_len[4]; i += 256) { const int a = at(im.list[4][i]); atomic_add_s16(P + a, 4); atomic_add_s16(P + a + YW, 3); }
 		for (int i = t; i < im.list_len[6]; i += 256) { const int a = at(im.list[6][i]); atomic_add_s16(P + a, 2); atomic_add_s16(P + a + YW, 2); atomic_add_s16(P + a + 2 * YW, 2); }
 		for (int i = t; i < im.list_len[7]; i += 256) { const int a = at(im.list[7][i]); atomic_add_s16(P + a, -2); atomic_add_s16(P + a + YW, -2); atomic_add_s16(P + a + 2 * YW, -2); }
+	}
+}
+
+// ---- q22/q23 corrections between the two halves of the level-1 synthesis (dec_hq_addback)
+__global__ void __launch_bounds__(256) kd_hq_addbacks(DecBatch b)
+{
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.x, 0);
+	const int n = dec_hq_addback_count(im);
+	for (int k = threadIdx.x; k < n; k += 256) {
+		int pos, amount;
+		if (dec_hq_addback(im, k, pos, amount) && pos >= 0 && pos < 512 * 512) atomic_add_s16(im.proc + pos, amount);
 	}
 }
 
@@ -406,6 +408,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	d_rows(c, "d_descan_y", b, n, 128, [=] __device__(const DecImg &im, int s) { dec_y_descan_strip(im.proc, im.jpeg, s); });
 	d_image(c, "d_lists", b, n, [=] __device__(const DecImg &im, int) {
 		dec_lists_image(im, reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(im.flags) + 131072));
+		dec_hq_lists_image(im, reinterpret_cast<uint32_t *>(im.aux));
 	});
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
@@ -416,6 +419,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH_L(c, "d_edge_compact", kd_edge_compact, n, 256, 0, b);
 	NHW_LAUNCH(c, kd_transpose, dim3(8, 8, n), 256, 0, b.y_proc, b.y_jpeg, YS, YS, 512);
 	NHW_LAUNCH_L(c, "d_inv_rows512", (kd_inv_rows<256, false>), dim3(512 / 8, n), 256, 0, b.y_jpeg, b.y_proc, YS, YS, 512);
+	NHW_LAUNCH_L(c, "d_hq_addbacks", kd_hq_addbacks, n, 256, 0, b);   // no-op below q22
 	NHW_LAUNCH(c, kd_transpose, dim3(16, 16, n), 256, 0, b.y_proc, b.y_jpeg, YS, YS, 512);
 	d_image(c, "d_smooth_flags", b, n, [=] __device__(const DecImg &im, int) { dec_y_smooth_flags_image(im); });
 	NHW_LAUNCH_L(c, "d_inv_rows512n", (kd_inv_rows<256, true>), dim3(512 / 8, n), 256, 0, b.y_jpeg, b.y_proc, YS, YS, 512);

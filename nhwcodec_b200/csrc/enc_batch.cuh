@@ -7,6 +7,7 @@
 
 struct EncBatch {
 	int16_t *y_proc, *y_jpeg, *y_aux, *y_ll1, *y_ll2s;
+	int16_t *y_hq;           // q22/q23: kept first pass (256x512) + LL1 copy (256x256) + rebuilt LH1 (256x256), one plane slot
 	int16_t *c_proc, *c_jpeg, *c_aux, *c_ll1, *c_ll2s;
 	uint8_t *bytes;
 	EncHdr *hdr;
@@ -35,7 +36,12 @@ enum : int {
 	OFF_RES5 = ENC_NEXT(OFF_RES4, 8192),
 	OFF_RES5_BIT = ENC_NEXT(OFF_RES5, 65600),
 	OFF_RES5_WORD = ENC_NEXT(OFF_RES5_BIT, 8224),
-	OFF_TMP1 = ENC_NEXT(OFF_RES5_WORD, 8224),
+	OFF_RES6 = ENC_NEXT(OFF_RES5_WORD, 8224),
+	OFF_RES6_BIT = ENC_NEXT(OFF_RES6, 65600),
+	OFF_RES6_WORD = ENC_NEXT(OFF_RES6_BIT, 8224),
+	OFF_CHARRES1 = ENC_NEXT(OFF_RES6_WORD, 8224),
+	OFF_QSET3 = ENC_NEXT(OFF_CHARRES1, 512),
+	OFF_TMP1 = ENC_NEXT(OFF_QSET3, 65536),
 	OFF_TMP2 = ENC_NEXT(OFF_TMP1, 65600),
 	OFF_TMP3 = ENC_NEXT(OFF_TMP2, 65600),
 	OFF_HRMEM = ENC_NEXT(OFF_TMP3, 65600),

@@ -71,6 +71,11 @@ struct EncImg {
 	uint8_t *res3, *res3_bit, *res3_word;
 	uint8_t *res4;
 	uint8_t *res5, *res5_bit, *res5_word;
+	uint8_t *res6, *res6_bit, *res6_word;   // q22/q23 side channel (enc_hq.cuh)
+	uint16_t *char_res1;
+	uint32_t *qsetting3;
+	int16_t *hq_qs, *hq_fo, *hq_band;       // kept first pass (256x512), LL1 copy (256x256), rebuilt LH1 (256x256)
+	uint8_t *hq_tag;                        // 256x512 comparison tags
 	uint8_t *tmp1, *tmp2, *tmp3;   // list scratch (highres / ch_comp / scan_run)
 	uint16_t *highres_mem;
 	uint8_t *highres_word;

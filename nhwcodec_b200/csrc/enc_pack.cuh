@@ -266,6 +266,12 @@ NHW_HDN int write_stream_image(const EncImg &im, uint8_t *out)
 	if (q > 17) putn(p, im.res4, h->res4_len);
 	if (q >= 19) { putn(p, im.res3, h->res3_len); putn(p, im.res3_bit, h->res3_bit_len); putn(p, im.res3_word, h->res3_word_len); }
 	if (q >= 21) { putn(p, im.res5, h->res5_len); putn(p, im.res5_bit, h->res5_bit_len); putn(p, im.res5_word, h->res5_word_len); }
+	if (q > 21) {
+		putn(p, im.res6, h->res6_len); putn(p, im.res6_bit, h->res6_bit_len); putn(p, im.res6_word, h->res6_word_len);
+		for (int i = 0; i < h->char_res1_len; i++) put16(p, im.char_res1[i]);
+	}
+	if (q > 22)
+		for (int i = 0; i < h->qsetting3_len; i++) put32(p, im.qsetting3[i]);
 	putn(p, im.sel1, h->select1);
 	putn(p, im.sel2, h->select2);
 	if (q > 15) {

@@ -11,7 +11,7 @@
 // The same functions are run in the same schedule by tests/hostemu (sequentially, rows of a
 // step in reverse order) to check the analysis against the reference taps.
 #pragma once
-#include "enc_pack.cuh"
+#include "enc_hq.cuh"
 
 // ---- wavefront geometry of each stage -------------------------------------------------------
 struct WfGeom { int r0, rows, c0, cols, skew; };

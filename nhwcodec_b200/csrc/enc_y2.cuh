@@ -299,7 +299,8 @@ NHW_HDN void y_e18_finish_list_image(const EncImg &im, int which, int count, int
 	uint8_t *out, *out_bit, *out_word;
 	if (which == 1) { out = im.res1; out_bit = im.res1_bit; out_word = im.res1_word; }
 	else if (which == 3) { out = im.res3; out_bit = im.res3_bit; out_word = im.res3_word; }
-	else { out = im.res5; out_bit = im.res5_bit; out_word = im.res5_word; }
+	else if (which == 5) { out = im.res5; out_bit = im.res5_bit; out_word = im.res5_word; }
+	else { out = im.res6; out_bit = im.res6_bit; out_word = im.res6_word; }
 	for (int i = 0; i < 8; i++) wrd[e + i] = 0;   // the reference reads up to 7 entries past the end
 	// drop end-of-row markers the decoder can infer from a decreasing position
 	for (int i = 0; i < count; i++) cpy[i] = pos[i];
@@ -346,7 +347,8 @@ NHW_HDN void y_e18_finish_list_image(const EncImg &im, int which, int count, int
 	}
 	if (which == 1) { h->res1_len = olen; h->res1_bit_len = bit_len; h->res1_word_len = wbytes; }
 	else if (which == 3) { h->res3_len = olen; h->res3_bit_len = bit_len; h->res3_word_len = wbytes; }
-	else { h->res5_len = olen; h->res5_bit_len = bit_len; h->res5_word_len = wbytes; }
+	else if (which == 5) { h->res5_len = olen; h->res5_bit_len = bit_len; h->res5_word_len = wbytes; }
+	else { h->res6_len = olen; h->res6_bit_len = bit_len; h->res6_word_len = wbytes; }
 }
 
 // ---- E19 (nhw_encoder.c:1893-1910): restore the level-2 region from the resIII snapshot,

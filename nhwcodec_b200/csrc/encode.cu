@@ -49,6 +49,15 @@ __device__ __forceinline__ EncImg make_img(const EncBatch &b, int i, int comp)
 	im.res5 = bytes + OFF_RES5;
 	im.res5_bit = bytes + OFF_RES5_BIT;
 	im.res5_word = bytes + OFF_RES5_WORD;
+	im.res6 = bytes + OFF_RES6;
+	im.res6_bit = bytes + OFF_RES6_BIT;
+	im.res6_word = bytes + OFF_RES6_WORD;
+	im.char_res1 = reinterpret_cast<uint16_t *>(bytes + OFF_CHARRES1);
+	im.qsetting3 = reinterpret_cast<uint32_t *>(bytes + OFF_QSET3);
+	im.hq_qs = b.y_hq + (size_t)i * NHW_Y_SLOT;
+	im.hq_fo = im.hq_qs + 131072;
+	im.hq_band = im.hq_qs + 196608;
+	im.hq_tag = reinterpret_cast<uint8_t *>(im.jpeg);   // im_jpeg is dead once the second reconstruction is done
 	im.tmp1 = bytes + OFF_TMP1;
 	im.tmp2 = bytes + OFF_TMP2;
 	im.tmp3 = bytes + OFF_TMP3;
@@ -472,6 +481,100 @@ __global__ void __launch_bounds__(256) k_c_quant_scan(EncBatch b, int m2)
 	}
 }
 
+// ---- q22/q23 side channel (enc_hq.cuh) -------------------------------------------------------
+// LL1 copy: fo[r][j] = reconstruction[j][r] (the reference copies its transposed work plane)
+__global__ void __launch_bounds__(256) k_hq_first_order(EncBatch b)
+{
+	__shared__ int16_t tile[32][33];
+	const EncImg im = make_img(b, blockIdx.z, 0);
+	const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	for (int r = ty; r < 32; r += 8) tile[r][tx] = im.proc[(y0 + r) * YW + x0 + tx];
+	__syncthreads();
+	for (int r = ty; r < 32; r += 8) im.hq_fo[(x0 + r) * 256 + y0 + tx] = tile[tx][r];
+}
+
+// E17: residual codes of LL1 cell (r, j) adjust up to three consecutive cells of the copy
+__global__ void __launch_bounds__(256) k_hq_e17(EncBatch b)
+{
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	const int r = blockIdx.x, j = threadIdx.x;
+	if (j >= 254) return;
+	int d[3];
+	if (!hq_e17_delta(im.ll1[r * 256 + j], d)) return;
+	for (int k = 0; k < 3; k++)
+		if (d[k]) atomic_add_s16(im.hq_fo + j * 256 + r + k, d[k]);
+}
+
+// LH1 rebuilt from the scan bytes, then half synthesis + comparison of row blockIdx.x
+__global__ void __launch_bounds__(256) k_hq_band(EncBatch b)
+{
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	const int c = blockIdx.x * 256 + threadIdx.x;
+	auto byte_at = [&](int cc) { return (int)im.scan[y_scan_pos(cc >> 8, 256 + (cc & 255))]; };
+	im.hq_band[c] = (int16_t)hq_band_cell(byte_at, c);
+}
+
+__global__ void __launch_bounds__(256) k_hq_tags(EncBatch b, int q)
+{
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	hq_tag_pair(im, q, blockIdx.x, threadIdx.x);
+}
+
+// lists: rows counted and written in parallel (thread = row), the short tail by one thread
+__global__ void __launch_bounds__(256) k_hq_lists(EncBatch b, int q)
+{
+	__shared__ int np[257], nw[257], nc[257], n3[257];
+	__shared__ int bad;
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	EncHdr *h = im.hdr;
+	const int r = threadIdx.x;
+	const uint8_t *tag = im.hq_tag + r * 512;
+	{
+		int w;
+		np[r] = hq_collect_row(im, r, nullptr, nullptr, w);
+		nw[r] = w;
+		int c1 = 0, c3 = 0;
+		for (int k = 0; k < 2; k++) c1 += (tag[254 + k] == 1 || tag[254 + k] == 2);
+		if (q > 22)
+			for (int j = 0; j < 512; j++) c3 += (tag[j] >= 3);
+		nc[r] = c1;
+		n3[r] = c3;
+	}
+	__syncthreads();
+	if (r < 4) {
+		int *v = r == 0 ? np : r == 1 ? nw : r == 2 ? nc : n3;
+		int run = 0;
+		for (int k = 0; k < 256; k++) { const int x = v[k]; v[k] = run; run += x; }
+		v[256] = run;
+	}
+	__syncthreads();
+	if (r == 0) bad = (np[256] + 16 > NHW_CAP_LIST || nc[256] > NHW_CAP_CHAR_RES1 || n3[256] > NHW_CAP_QSETTING3) ? 1 : 0;
+	__syncthreads();
+	if (bad) { if (r == 0 && h->status == 0) h->status = NHW_ERR_OVERFLOW_DEV; return; }
+	{
+		int w;
+		hq_collect_row(im, r, im.tmp1 + np[r], im.tmp3 + nw[r], w);
+		int o = nc[r];
+		for (int k = 0; k < 2; k++) {
+			const int g = tag[254 + k];
+			if (g == 1 || g == 2) im.char_res1[o++] = (uint16_t)(r * 256 + 2 * k + (g - 1));
+		}
+		if (q > 22) {
+			int o3 = n3[r];
+			for (int j = 0; j < 512; j++) {
+				const int g = tag[j];
+				if (g >= 3) im.qsetting3[o3++] = (uint32_t)((r * 512 + j) << 1) + (g == 4 ? 1u : 0u);
+			}
+		}
+	}
+	__syncthreads();
+	if (r == 0) {
+		h->char_res1_len = nc[256];
+		h->qsetting3_len = n3[256];
+		y_e18_finish_list_image(im, 6, np[256], nw[256]);
+	}
+}
+
 // ---- peephole passes over the luma scan, one CTA per image (enc_seg.cuh)
 #define PEEP_THREADS 512
 // non-zero bitmap of `count` stream bytes starting at s (16-byte aligned, count % 32 == 0) into shared memory
@@ -789,6 +892,7 @@ EncBatch enc_batch_of(nhw_ctx *c)
 	b.y_aux = c->y_aux + NHW_GUARD_S;
 	b.y_ll1 = c->y_ll1 + NHW_GUARD_S;
 	b.y_ll2s = c->y_ll2save + NHW_GUARD_S;
+	b.y_hq = c->y_aux2 + NHW_GUARD_S;
 	b.c_proc = c->c_proc + NHW_GUARD_S;
 	b.c_jpeg = c->c_jpeg + NHW_GUARD_S;
 	b.c_aux = c->c_aux + NHW_GUARD_S;
@@ -849,7 +953,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_image(c, "init_hdr", b, n, [=] __device__(const EncImg &im, int) { im.hdr->quality = q; });
 
 	// ---- front end: colour, 4:2:0, pre-sharpening, two analysis levels (front.cu)
-	front_fused(c, rgb, n, q, b.y_proc, YS, b.y_ll1, CS, c->c_u8, b.c_proc, CS, b.c_ll1, QS);
+	front_fused(c, rgb, n, q, b.y_proc, YS, b.y_ll1, CS, c->c_u8, b.c_proc, CS, b.c_ll1, QS, b.y_hq, YS);
 
 	// ---- luma closed loop (nhw_encoder.c:141-283)
 	run_rows(c, "y_e6a_tag", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });
@@ -885,6 +989,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_wavefront(c, "y_recons0_shrink", b, n, wf_shrink_geom(),
 	              [=] __device__(const EncImg &im, int r, int j) { return wf_shrink_cell(im, r, j); });
 	idwt_luma256(c, b, n);
+	if (q > 21) NHW_LAUNCH_L(c, "y_hq_first_order", k_hq_first_order, dim3(8, 8, n), 256, 0, b);
 
 	// ---- level-1 thresholds, pattern tags, residual side channels (nhw_encoder.c:783-1887)
 	run_rows(c, "y_e14_e15_tags", b, n, 512, [=] __device__(const EncImg &im, int r) {
@@ -896,6 +1001,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		run_rows(c, "y_e16b_classify", b, n, 256, [=] __device__(const EncImg &im, int j) { int w1 = 0, w3 = 0, w5 = 0; y_e16b_classify_col(im, q, j, w1, w3, w5); });
 	else
 		NHW_LAUNCH_L(c, "y_e16b_classify", k_e16b_classify, n, 256, 0, b, q);
+	if (q > 21) NHW_LAUNCH_L(c, "y_hq_e17", k_hq_e17, dim3(256, n), 256, 0, b);
 	NHW_LAUNCH_L(c, "y_e18_lists", k_e18_lists, n, 256, 0, b, q);
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
@@ -908,6 +1014,11 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	              [=] __device__(const EncImg &im, int r, int j) { return wf_offset_patterns_cell(im, r, j); });
 	run_rows(c, "y_offset_pairs57", b, n, 256, [=] __device__(const EncImg &im, int r) { y_offset_pairs57_row(im, r); });
 	NHW_LAUNCH_L(c, "y_quant_scan", k_y_quant_scan, dim3(32, n), 256, 0, b, ratio);
+	if (q > 21) {   // res6 / char_res1 / high_qsetting3 from the quantised LH1 bytes, before the peephole edits them
+		NHW_LAUNCH_L(c, "y_hq_band", k_hq_band, dim3(256, n), 256, 0, b);
+		NHW_LAUNCH_L(c, "y_hq_tags", k_hq_tags, dim3(256, n), 256, 0, b, q);
+		NHW_LAUNCH_L(c, "y_hq_lists", k_hq_lists, n, 256, 0, b, q);
+	}
 	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 262144 / 8, b);
 
 	// ---- chroma, U and V planes side by side (nhw_encoder.c:2255-2868)

@@ -207,7 +207,8 @@ __device__ __forceinline__ void col_pass8(const int (&col)[19], int e0, bool fin
 // =====================================================================================
 __global__ void __launch_bounds__(FT, 2)
 k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t pstride, int16_t *__restrict__ ll1,
-             size_t lstride, uint8_t *__restrict__ uv, size_t uvstride, ColorParams cp, int pre)
+             size_t lstride, uint8_t *__restrict__ uv, size_t uvstride, ColorParams cp, int pre,
+             int16_t *__restrict__ kept, size_t kstride)
 {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	FrontSmem &S = *reinterpret_cast<FrontSmem *>(smem_raw);
@@ -461,6 +462,13 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 			if (i == 31) col[18] = col[16];                     // row 512 mirrors row 510
 			int lo[8], hi[8];
 			const bool fine = k < 256;
+			if (kept && fine) {
+				// q22/q23: the low half of the first pass is kept, transposed, for the res6 side channel
+				// (im_quality_setting, encoder/wavelet_filterbank.c:107-112): rows 16i .. 16i+15 of column k
+				uint4 *dst = reinterpret_cast<uint4 *>(kept + (size_t)img * kstride + k * 512 + 16 * i);
+				dst[0] = make_uint4(pack2(col[2], col[3]), pack2(col[4], col[5]), pack2(col[6], col[7]), pack2(col[8], col[9]));
+				dst[1] = make_uint4(pack2(col[10], col[11]), pack2(col[12], col[13]), pack2(col[14], col[15]), pack2(col[16], col[17]));
+			}
 			col_pass8(col, e0, fine, i == 31, v_rem, lo, hi);
 			const uint4 H = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
 			*reinterpret_cast<uint4 *>(P + k * 512 + 256 + e0) = H;
@@ -603,7 +611,8 @@ ColorParams color_params(int quality);
 // The whole front end of n images: rgb -> luma coefficient planes (both levels) + `res256`,
 // chroma coefficient planes (both levels) + chroma `res256`.  uv_bytes: scratch, 2*65536 B / image.
 void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_proc, size_t ypstride, int16_t *y_ll1,
-                 size_t ylstride, uint8_t *uv_bytes, int16_t *c_proc, size_t cpstride, int16_t *c_ll1, size_t clstride)
+                 size_t ylstride, uint8_t *uv_bytes, int16_t *c_proc, size_t cpstride, int16_t *c_ll1, size_t clstride,
+                 int16_t *kept, size_t kstride)
 {
 	static bool attr = false;
 	if (!attr) {
@@ -622,7 +631,7 @@ void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_
 	}
 	const ColorParams p = color_params(quality);
 	NHW_LAUNCH_L(c, "k_front_luma", k_front_luma, n, FT, sizeof(FrontSmem), rgb, y_proc, ypstride, y_ll1, ylstride, uv_bytes,
-	             (size_t)2 * NHW_CPLANE, p, quality < 22 ? 1 : 0);
+	             (size_t)2 * NHW_CPLANE, p, quality < 22 ? 1 : 0, quality > 21 ? kept : (int16_t *)nullptr, kstride);
 	launch_level<256, int16_t, 1024>(c, "k_dwt_level<256>", n, y_ll1, ylstride, 256, y_proc, ypstride, 512, nullptr, 0);
 	launch_level<256, uint8_t, 1024>(c, "k_dwt_level<256,u8>", 2 * n, uv_bytes, (size_t)NHW_CPLANE, 256, c_proc, cpstride, 256,
 	                                 c_ll1, clstride);

@@ -26,3 +26,17 @@ struct nhw_ctx;
 	} while (0)
 #define NHW_LAUNCH(ctx, kernel, grid, block, smem, ...) NHW_LAUNCH_L(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 
+
+// 16-bit add on a cell other threads may be adding to as well (CAS on the containing word)
+__device__ __forceinline__ void atomic_add_s16(int16_t *p, int v)
+{
+	uint32_t *w = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+	const bool hi = (reinterpret_cast<uintptr_t>(p) & 2) != 0;
+	uint32_t old = *w, assumed;
+	do {
+		assumed = old;
+		const uint32_t cur = hi ? assumed >> 16 : assumed & 0xffffu;
+		const uint32_t nv = (cur + (uint32_t)v) & 0xffffu;
+		old = atomicCAS(w, assumed, hi ? (assumed & 0xffffu) | (nv << 16) : (assumed & 0xffff0000u) | nv);
+	} while (old != assumed);
+}

@@ -33,10 +33,14 @@ for s in $ENC_SRCS; do
 	$CC $CFLAGS -I"$REF/encoder" -c "$REF/encoder/$s" -o "$TMP/enc_${s%.c}.o"
 	objs="$objs $TMP/enc_${s%.c}.o"
 done
+# the q22/q23 side channel is computed inside wavelet_filterbank.c: the canonical library gets a tapped copy of it too
+python3 "$HERE/make_tapped.py" "$REF/encoder/wavelet_filterbank.c" "$HERE/taps_enc.txt" "$TMP/enc_wfb_tapped.c"
+$CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$TMP/enc_wfb_tapped.c" -o "$TMP/enc_wavelet_filterbank_tapped.o"
+tobjs="${objs/$TMP\/enc_wavelet_filterbank.o/$TMP/enc_wavelet_filterbank_tapped.o}"
 $CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$TMP/enc_tapped.c" -o "$TMP/enc_nhw_encoder.o"
 $CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$HERE/ref_enc_glue.c" -o "$TMP/enc_glue.o"
 $CC $CFLAGS -c "$HERE/zguard.c" -o "$TMP/zguard.o"
-$CC -shared -o "$OUT/libnhwref_enc.so" $objs "$TMP/enc_nhw_encoder.o" "$TMP/enc_glue.o" "$TMP/zguard.o" \
+$CC -shared -o "$OUT/libnhwref_enc.so" $tobjs "$TMP/enc_nhw_encoder.o" "$TMP/enc_glue.o" "$TMP/zguard.o" \
 	$WRAP -Wl,-Bsymbolic -lm -lpthread
 # timing build: the same reference objects on the STOCK allocator (only exit() is trapped), so the
 # CPU baseline is not slowed down by the canonicalising allocator.  Never used for parity.

@@ -66,6 +66,15 @@ Work *make_work()
 	im.res5 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
 	im.res5_bit = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
 	im.res5_word = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
+	im.res6 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
+	im.res6_bit = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
+	im.res6_word = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
+	im.char_res1 = carve<uint16_t>(w->mem, off, NHW_CAP_CHAR_RES1, NHW_GUARD_B);
+	im.qsetting3 = carve<uint32_t>(w->mem, off, NHW_CAP_QSETTING3, NHW_GUARD_B);
+	im.hq_qs = carve<int16_t>(w->mem, off, 256 * 512, NHW_GUARD_B);
+	im.hq_fo = carve<int16_t>(w->mem, off, 256 * 256, NHW_GUARD_B);
+	im.hq_band = carve<int16_t>(w->mem, off, 256 * 256, NHW_GUARD_B);
+	im.hq_tag = carve<uint8_t>(w->mem, off, 256 * 512, NHW_GUARD_B);
 	im.tmp1 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
 	im.tmp2 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
 	im.tmp3 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
@@ -341,6 +350,9 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	if (rc) return rc;
 	for (int s = 127; s >= 0; s--) dec_y_descan_strip(im.proc, im.jpeg, s);
 	dec_lists_image(im, ltmp.data());
+	std::vector<uint32_t> hq0(NHW_CAP_HQ_LIST), hq1(NHW_CAP_HQ_LIST), hqtmp(NHW_CAP_HQ_LIST + 64);
+	im.hq_list[0] = hq0.data(); im.hq_list[1] = hq1.data();
+	dec_hq_lists_image(im, hqtmp.data());
 	if (getenv("HE_SERIAL")) dec_y_markers_image(im);
 	else {   // parallel form (dec_par.cuh), phases in the kernel's order
 		int16_t *J = im.jpeg;
@@ -354,10 +366,12 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 		std::vector<uint32_t> W(2048, 0), A(2048, 0);
 		for (int s : c3) dec_marker_apply(J, s, true, W.data(), A.data());
 		int first = 1 << 30;
+		if (d.quality < 23)
 		for (int r = 511; r >= 256; r--) for (int j = 510; j > 256; j--) {
 			const int s = r * 512 + j;
 			if (dec_dense_qualifies(S.data(), A.data(), s) && s < first) first = s;
 		}
+		if (d.quality < 23)
 		for (int r = 511; r >= 256; r--) for (int j = 510; j > 256; j--) {
 			const int s = r * 512 + j, k = ((r - 256) << 8) + (j - 256);
 			if (!dec_dense_qualifies(S.data(), A.data(), s)) continue;
@@ -383,6 +397,10 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	}
 	transpose_sq(im.proc, im.jpeg, 512, 256);
 	inv_rows(im.jpeg, 512, im.proc, 512, 512, 256, false);      // wavelet_synthesis2: first half
+	for (int k = dec_hq_addback_count(im) - 1; k >= 0; k--) {
+		int pos, amount;
+		if (dec_hq_addback(im, k, pos, amount)) im.proc[pos] = (int16_t)(im.proc[pos] + amount);
+	}
 	transpose_sq(im.proc, im.jpeg, 512, 512);
 	dec_y_smooth_flags_image(im);
 	inv_rows(im.jpeg, 512, im.proc, 512, 512, 256, true);       // wavelet_synthesis(...,3): second half
@@ -437,11 +455,14 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	const int ratio = 8;
 	std::vector<int16_t> tmp;
 	auto T = [&](const char *name, const void *p, size_t n) { if (tap) tap(name, p, n); };
-	if (q < 17 || q > 21) return -3;
+	if (q < 17 || q > 23) return -3;
 
 	// ---------------- luma ----------------
 	memcpy(im.jpeg, y_pre, 512 * 512 * 2);
 	fwd_level(im.jpeg, 512, false, im.proc, 512, 512, tmp);
+	if (q > 21)   // kept first pass, low half, transposed (tmp = R[y][k] after fwd_level)
+		for (int k = 0; k < 256; k++)
+			for (int y = 0; y < 512; y++) im.hq_qs[k * 512 + y] = tmp[y * 512 + k];
 	for (int m = 0; m < 256; m++)
 		for (int k = 0; k < 256; k++) im.ll1[m * 256 + k] = im.proc[k * 512 + m];
 	fwd_level(im.proc, 512, true, im.proc, 512, 256, tmp);
@@ -481,6 +502,11 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	T("y_rec0_jpeg", im.jpeg, 512 * 512 * 2);
 	inv_level(im.jpeg, im.proc, 512, 256, tmp);
 	T("y_syn0_proc", im.proc, 512 * 512 * 2);
+	if (q > 21) {
+		for (int r = 0; r < 256; r++)
+			for (int j = 0; j < 256; j++) im.hq_fo[r * 256 + j] = im.proc[j * 512 + r];   // the reference copies its transposed work plane
+		T("y_hq_fo0", im.hq_fo, 65536 * 2);
+	}
 	for (int r = 511; r >= 256; r--) y_e14_threshold_row(im, q, ratio, r);
 	T("y_e14_proc", im.proc, 512 * 512 * 2);
 	for (int r = 510; r >= 1; r--) y_e15_tags_row(im, r);
@@ -491,6 +517,7 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	y_e16b_classify_image(im, q);
 	T("y_e16b_proc", im.proc, 512 * 512 * 2);
 	T("y_e16b_ll1", im.ll1, 65536 * 2);
+	if (q > 21) { hq_e17_image(im); T("y_hq_fo1", im.hq_fo, 65536 * 2); }
 	y_e18_pack_list_image(im, 1);
 	if (q >= 19) y_e18_pack_list_image(im, 3);
 	if (q >= 21) y_e18_pack_list_image(im, 5);
@@ -517,6 +544,14 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		}
 	}
 	T("y_e23_scan", im.scan, 262144);
+	if (q > 21) {
+		auto byte_at = [&](int c) { return (int)im.scan[y_scan_pos(c >> 8, 256 + (c & 255))]; };
+		for (int c = 65535; c >= 0; c--) im.hq_band[c] = (int16_t)hq_band_cell(byte_at, c);
+		T("y_hq_band", im.hq_band, 65536 * 2);
+		for (int r = 255; r >= 0; r--) hq_tag_row(im, q, r);
+		int rc = hq_lists_image(im, q);
+		if (rc) return rc;
+	}
 	if (getenv("HE_SERIAL")) y_peephole_image(im); else host_peephole(im);
 	T("y_e24_scan", im.scan, 262144);
 

@@ -14,7 +14,7 @@ def _mixed(n, seed0):
     return np.stack([fs[i % 3](seed0 + i) for i in range(n)])
 
 
-@pytest.mark.parametrize("q", [20, 17, 18, 19, 21])
+@pytest.mark.parametrize("q", [20, 17, 18, 19, 21, 22, 23])
 def test_decode_bit_exact(codec, ref, q):
     imgs = _mixed(6, 9100 + q)
     streams = [ref.ref_encode(imgs[i], q) for i in range(imgs.shape[0])]
@@ -31,13 +31,26 @@ def test_round_trip_own_streams_and_chunking(codec, ref):
     reference decoder on the same streams; mixed qualities in one decode batch."""
     imgs = _mixed(20, 9300)
     s20, st = codec.encode(imgs, 20)
-    s18, st2 = codec.encode(imgs, 18)
+    s18, st2 = codec.encode(imgs, 23)
     assert (st == 0).all() and (st2 == 0).all()
     streams = s20 + s18
     rgb, status = codec.decode(streams)
     assert (status == 0).all()
     for i in (0, 1, 2, 19, 20, 21, 39):
         assert np.array_equal(rgb[i], ref.ref_decode(streams[i])), i
+
+
+@pytest.mark.parametrize("q", [17, 20, 22, 23])
+def test_decode_known_answer(codec, ref, q):
+    """md5 of the BMP nhw-dec writes for the formula-defined image"""
+    import hashlib
+    from test_oracle_cpu import KAT, smooth_pixels
+    stream = ref.ref_encode(smooth_pixels(), q)
+    rgb, status = codec.decode([stream])
+    assert status[0] == 0
+    hdr = bytes([66, 77, 54, 0, 12, 0, 0, 0, 0, 0, 54, 0, 0, 0, 40, 0, 0, 0, 0, 2, 0, 0, 0, 2, 0, 0, 1, 0, 24, 0,
+                 0, 0, 0, 0, 0, 0, 12, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    assert hashlib.md5(hdr + rgb[0].tobytes()).hexdigest() == KAT[q][2]
 
 
 def test_decode_rejects_garbage(codec):

@@ -13,7 +13,7 @@ def _mixed(n, seed0):
     return np.stack([fs[i % 3](seed0 + i) for i in range(n)])
 
 
-@pytest.mark.parametrize("q", [20, 17, 18, 19, 21])
+@pytest.mark.parametrize("q", [20, 17, 18, 19, 21, 22, 23])
 def test_encode_bit_exact(codec, ref, q):
     imgs = _mixed(6, 7000 + q)
     streams, status = codec.encode(imgs, q)
@@ -48,14 +48,15 @@ def test_encode_chunking_and_device_api(codec, ref):
         assert streams[i] == ref.ref_encode(imgs[i], 20), i
 
 
-def test_smooth_known_answer(codec):
-    """md5 of the canonical .nhw of the formula-defined image at q20"""
+@pytest.mark.parametrize("q", [17, 20, 21, 22, 23])
+def test_smooth_known_answer(codec, q):
+    """size and md5 of the canonical .nhw of the formula-defined image"""
     import hashlib
-    from test_oracle_cpu import smooth_pixels
-    streams, status = codec.encode(smooth_pixels()[None, :], 20)
+    from test_oracle_cpu import KAT, smooth_pixels
+    streams, status = codec.encode(smooth_pixels()[None, :], q)
     assert status[0] == 0
-    assert len(streams[0]) == 24412
-    assert hashlib.md5(streams[0]).hexdigest() == "9ea5053bd20fc35758652b0a0aa47b8d"
+    assert len(streams[0]) == KAT[q][0]
+    assert hashlib.md5(streams[0]).hexdigest() == KAT[q][1]
 
 
 def test_unsupported_quality_is_an_error(codec):
