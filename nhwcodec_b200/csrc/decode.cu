@@ -18,8 +18,8 @@ namespace {
 enum : int {
 	DOFF_RESCOMP = 4096,
 	DOFF_BOOK = DOFF_RESCOMP + 24640,
-	DOFF_BTMP = DOFF_BOOK + 2048,
-	DOFF_LISTLEN = DOFF_BTMP + 2048,
+	DOFF_BTMP = DOFF_BOOK + 4096,                  // two books (luma, chroma) of 1024 entries
+	DOFF_LISTLEN = DOFF_BTMP + 4096,               // and their two scratch areas
 	DOFF_FLAGS = DOFF_LISTLEN + 256,
 	DOFF_LTMP = DOFF_FLAGS + 131072,
 	DOFF_LISTS = DOFF_LTMP + 131072 + 256,        // 8 lists x 65536 entries
@@ -89,6 +89,60 @@ __global__ void __launch_bounds__(32) kd_image_lut(DecBatch b, int n, F f)
 		f(im, i);
 	}
 }
+// ---- the decoder's serial front: four independent single-thread jobs per image run side by side
+// (threadIdx.y = job) instead of one after the other: luma prefix decode, chroma prefix decode, LL byte
+// DPCM, side-channel list expansion.  32 images per CTA; the prefix-code table is staged in shared memory.
+__global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n)
+{
+	__shared__ __align__(16) uint16_t slut[NHW_LUT_WORDS];
+	const int tid = threadIdx.y * 32 + threadIdx.x;
+	for (int k = tid; k < NHW_LUT_WORDS / 8; k += 128) reinterpret_cast<uint4 *>(slut)[k] = reinterpret_cast<const uint4 *>(b.lut)[k];
+	__syncthreads();
+	const int i = blockIdx.x * 32 + threadIdx.x, job = threadIdx.y;
+	if (i >= n || b.status[i] != 0) return;
+	DecImg im = make_dec(b, i, 0);
+	im.lut = slut;
+	if (job == 0) {
+		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 4096;
+		dec_build_book(im.blob + im.d->off_tree1, im.d->size_tree1, 3, -1, im.book, btmp);
+		const int rc = dec_prefix_luma(im, im.proc);
+		if (rc) b.status[i] = rc;
+	} else if (job == 1) {
+		im.book += 1024;
+		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 4096;
+		for (int k = 0; k < 1024; k++) im.book[k] = 0;
+		dec_build_book(im.blob + im.d->off_tree2, im.d->size_tree2, 128, im.d->tree_end, im.book, btmp);
+		const int rc = dec_prefix_chroma(im, im.uvcoef);
+		if (rc) b.status[i] = rc;
+	} else if (job == 2) {
+		dec_ll_dpcm(im);
+	} else {
+		dec_lists_image(im, reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(im.flags) + 131072));
+		dec_hq_lists_image(im, reinterpret_cast<uint32_t *>(im.aux));
+	}
+}
+
+// ---- chroma markers 5003..5006 (dec_c_markers_image): every marker only ADDS to cells of the reconstructed
+// LL and clears itself, so cells are independent given atomic adds.  One thread per band cell.
+__global__ void __launch_bounds__(256) kd_c_markers(DecBatch b)
+{
+	const int img = blockIdx.y >> 1;
+	if (b.status[img] != 0) return;
+	const DecImg im = make_dec(b, img, blockIdx.y & 1);
+	const int r = blockIdx.x, j = threadIdx.x;
+	if (r < 128 && j < 128) return;
+	int16_t *P = im.cproc, *J = im.cjpeg;
+	const int s = r * CW + j, v = J[s];
+	if (v <= 5000) return;
+	int t = s;
+	if (r < 128) t -= 128;
+	else t -= 32768 + (j < 128 ? 0 : 128);
+	if (v == 5005) { atomic_add_s16(P + t, -4); atomic_add_s16(P + t + 1, -4); J[s] = 0; }
+	else if (v == 5006) { atomic_add_s16(P + t, 4); atomic_add_s16(P + t + 1, 4); J[s] = 0; }
+	else if (v == 5003) { atomic_add_s16(P + t, -6); J[s] = 0; }
+	else if (v == 5004) { atomic_add_s16(P + t, 6); J[s] = 0; }
+}
+
 template <typename F>
 __global__ void kd_plane(DecBatch b, int n2, F f)
 {
@@ -398,18 +452,8 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH(c, kd_zero, dim3(131072 * 2 / 16 / 256, n), 256, 0, b.uvcoef, YS, (size_t)(131072 * 2 / 16));
 
 	// ---- luma
-	d_image_lut(c, "d_ll_prefix_y", b, n, [=] __device__(const DecImg &im, int i) {
-		dec_ll_dpcm(im);
-		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 2048;
-		dec_build_book(im.blob + im.d->off_tree1, im.d->size_tree1, 3, -1, im.book, btmp);
-		int rc = dec_prefix_luma(im, im.proc);
-		if (rc) b.status[i] = rc;
-	});
+	NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + 31) / 32, dim3(32, 4), 0, b, n);
 	d_rows(c, "d_descan_y", b, n, 128, [=] __device__(const DecImg &im, int s) { dec_y_descan_strip(im.proc, im.jpeg, s); });
-	d_image(c, "d_lists", b, n, [=] __device__(const DecImg &im, int) {
-		dec_lists_image(im, reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(im.flags) + 131072));
-		dec_hq_lists_image(im, reinterpret_cast<uint32_t *>(im.aux));
-	});
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
 	d_wavefront(c, "d_shrink_y", b, n, 1, dwf_shrink_geom(), [=] __device__(const DecImg &im, int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
@@ -426,13 +470,6 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH(c, kd_clip_y, dim3(262144 / 256, n), 256, 0, b);
 
 	// ---- chroma
-	d_image_lut(c, "d_prefix_uv", b, n, [=] __device__(const DecImg &im, int i) {
-		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 2048;
-		for (int k = 0; k < 1024; k++) im.book[k] = 0;
-		dec_build_book(im.blob + im.d->off_tree2, im.d->size_tree2, 128, im.d->tree_end, im.book, btmp);
-		int rc = dec_prefix_chroma(im, im.uvcoef);
-		if (rc) b.status[i] = rc;
-	});
 	d_plane_rows(c, "d_descan_uv", b, n, 32, [=] __device__(const DecImg &im, int s, int v) { dec_c_descan_strip(im.uvcoef, im.cjpeg, s, v); });
 	d_image(c, "d_ll_uv", b, n, [=] __device__(const DecImg &im0, int i) {
 		int exw = im0.list_len[10];
@@ -442,7 +479,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 		}
 	});
 	idwt_rows_cols(c, 2 * n, b.c_jpeg, b.c_aux, b.c_proc, CS, 128, 256);
-	d_plane(c, "d_markers_uv", b, n, [=] __device__(const DecImg &im, int) { dec_c_markers_image(im); });
+	NHW_LAUNCH_L(c, "d_markers_uv", kd_c_markers, dim3(256, 2 * n), 256, 0, b);
 	NHW_LAUNCH(c, kd_transpose, dim3(4, 4, 2 * n), 256, 0, b.c_proc, b.c_jpeg, CS, CS, 256);
 	idwt_rows_cols(c, 2 * n, b.c_jpeg, b.c_aux, b.c_proc, CS, 256, 256);
 	d_wavefront(c, "d_sharpen_uv", b, n, 2, dwf_sharpen_geom(), [=] __device__(const DecImg &im, int r, int j) {

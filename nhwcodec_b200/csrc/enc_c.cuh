@@ -245,13 +245,11 @@ NHW_HD void c_scan_strip(const EncImg &im, int strip /* 0..31 */, int is_v)
 
 // ---- highres_compression (compress_pixel.c:878-1022): both chroma LL planes, appended to
 // the luma LL code.  in: tree1[16384..24575]; io: im.llcode (highres_comp) from y_res_comp on.
-NHW_HDN void ll_dpcm_chroma_image(const EncImg &im)
+// Core: x = the LL bytes indexed as in tree1 (x[16384..24575] valid and already masked with 252, readable up
+// to x[24575 + 20]); out[j0..] receives the code; returns the end index.
+NHW_HDN int ll_dpcm_chroma_core(const uint8_t *x, uint8_t *out, int j0)
 {
-	uint8_t *x = im.tree1;
-	uint8_t *out = im.llcode;
-	EncHdr *h = im.hdr;
-	for (int i = 16384; i < 24576; i++) x[i] &= 252;
-	int j = h->y_res_comp;
+	int j = j0;
 	out[j++] = x[16384];
 	int a = 0, res = 0;
 	for (int i = 16385; i < 24576; i++) {
@@ -309,5 +307,11 @@ NHW_HDN void ll_dpcm_chroma_image(const EncImg &im)
 			else { out[j++] = (uint8_t)((scan << 1) + (count >> 2)); i++; }
 		} else out[j++] = (uint8_t)(128 + (x[i] >> 2));
 	}
-	h->end_ch_res = j;
+	return j;
+}
+
+NHW_HDN void ll_dpcm_chroma_image(const EncImg &im)
+{
+	for (int i = 16384; i < 24576; i++) im.tree1[i] &= 252;
+	im.hdr->end_ch_res = ll_dpcm_chroma_core(im.tree1, im.llcode, im.hdr->y_res_comp);
 }

@@ -230,11 +230,15 @@ NHW_HD void put16(uint8_t *&p, int v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >>
 NHW_HD void put32(uint8_t *&p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); p += 4; }
 NHW_HD void putn(uint8_t *&p, const uint8_t *src, int n) { for (int i = 0; i < n; i++) p[i] = src[i]; p += n; }
 
-NHW_HDN int write_stream_image(const EncImg &im, uint8_t *out)
+// The container as an ordered list of byte ranges: `hdr` receives the header fields (<= 64 bytes, returned
+// length), section(src, n) is called for every section in file order.  Multi-byte section elements
+// (char_res1, high_qsetting3, the code words) are little-endian in memory already.
+template <typename Section>
+NHW_HD int stream_layout(const EncImg &im, uint8_t *hdr, Section section)
 {
 	const EncHdr *h = im.hdr;
 	const int q = h->quality;
-	uint8_t *p = out;
+	uint8_t *p = hdr;
 	const int exw_end = h->exw_y_len + 2 + h->exw_u_len + 2 + h->exw_v_len;
 	*p++ = (uint8_t)(h->res_low + h->wavelet_type);
 	*p++ = (uint8_t)q;
@@ -255,30 +259,42 @@ NHW_HDN int write_stream_image(const EncImg &im, uint8_t *out)
 	put16(p, h->select2);
 	if (q > 15) put16(p, h->highres_comp_len);
 	put16(p, h->end_ch_res);
-	putn(p, im.codebook1, h->size_tree1);
-	putn(p, im.codebook2, h->size_tree2);
-	putn(p, im.exw, h->exw_y_len);
-	*p++ = 0; *p++ = 0;
-	putn(p, im.tmp3, h->exw_u_len);
-	*p++ = 0; *p++ = 0;
-	putn(p, im.tmp3 + 16384, h->exw_v_len);
-	if (q > 12) { putn(p, im.res1, h->res1_len); putn(p, im.res1_bit, h->res1_bit_len); putn(p, im.res1_word, h->res1_word_len); }
-	if (q > 17) putn(p, im.res4, h->res4_len);
-	if (q >= 19) { putn(p, im.res3, h->res3_len); putn(p, im.res3_bit, h->res3_bit_len); putn(p, im.res3_word, h->res3_word_len); }
-	if (q >= 21) { putn(p, im.res5, h->res5_len); putn(p, im.res5_bit, h->res5_bit_len); putn(p, im.res5_word, h->res5_word_len); }
+	const int hdr_len = (int)(p - hdr);
+	section(hdr, hdr_len);
+	section(im.codebook1, h->size_tree1);
+	section(im.codebook2, h->size_tree2);
+	section(im.exw, h->exw_y_len);
+	section(nullptr, 2);                       // 0,0 separator
+	section(im.tmp3, h->exw_u_len);
+	section(nullptr, 2);
+	section(im.tmp3 + 16384, h->exw_v_len);
+	if (q > 12) { section(im.res1, h->res1_len); section(im.res1_bit, h->res1_bit_len); section(im.res1_word, h->res1_word_len); }
+	if (q > 17) section(im.res4, h->res4_len);
+	if (q >= 19) { section(im.res3, h->res3_len); section(im.res3_bit, h->res3_bit_len); section(im.res3_word, h->res3_word_len); }
+	if (q >= 21) { section(im.res5, h->res5_len); section(im.res5_bit, h->res5_bit_len); section(im.res5_word, h->res5_word_len); }
 	if (q > 21) {
-		putn(p, im.res6, h->res6_len); putn(p, im.res6_bit, h->res6_bit_len); putn(p, im.res6_word, h->res6_word_len);
-		for (int i = 0; i < h->char_res1_len; i++) put16(p, im.char_res1[i]);
+		section(im.res6, h->res6_len); section(im.res6_bit, h->res6_bit_len); section(im.res6_word, h->res6_word_len);
+		section(reinterpret_cast<const uint8_t *>(im.char_res1), 2 * h->char_res1_len);
 	}
-	if (q > 22)
-		for (int i = 0; i < h->qsetting3_len; i++) put32(p, im.qsetting3[i]);
-	putn(p, im.sel1, h->select1);
-	putn(p, im.sel2, h->select2);
+	if (q > 22) section(reinterpret_cast<const uint8_t *>(im.qsetting3), 4 * h->qsetting3_len);
+	section(im.sel1, h->select1);
+	section(im.sel2, h->select2);
 	if (q > 15) {
-		putn(p, im.res_uv64, 1024);
-		putn(p, im.highres_word, h->highres_comp_len);
+		section(im.res_uv64, 1024);
+		section(im.highres_word, h->highres_comp_len);
 	}
-	putn(p, im.llcode, h->end_ch_res);
-	for (int i = 0; i < h->size_data2; i++) put32(p, im.words[i]);
+	section(im.llcode, h->end_ch_res);
+	section(reinterpret_cast<const uint8_t *>(im.words), 4 * h->size_data2);
+	return hdr_len;
+}
+
+NHW_HDN int write_stream_image(const EncImg &im, uint8_t *out)
+{
+	uint8_t hdr[64];
+	uint8_t *p = out;
+	stream_layout(im, hdr, [&](const uint8_t *src, int n) {
+		for (int i = 0; i < n; i++) p[i] = src ? src[i] : (uint8_t)0;
+		p += n;
+	});
 	return (int)(p - out);
 }

@@ -828,17 +828,58 @@ __global__ void k_zero_bytes(uint8_t *base, size_t slot, size_t off, size_t coun
 	if (i * 16 < count) reinterpret_cast<uint4 *>(base + (size_t)blockIdx.y * slot + off)[i] = make_uint4(0, 0, 0, 0);
 }
 
-// final: container bytes
-__global__ void k_write_stream(EncBatch b, int n, uint8_t *out, uint32_t *len, int32_t *status)
+// ---- chroma LL code: a serial coder (each step looks a few bytes ahead and skips a variable distance), run by
+// one thread per image out of shared memory; the warp stages the 8192 input bytes and the output.
+#define CLL_PAD 32
+__global__ void __launch_bounds__(32) k_c_ll_code(EncBatch b)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	EncImg im = make_img(b, i, 0);
-	int st = im.hdr->status;
-	int L = 0;
-	if (st == 0) L = write_stream_image(im, out + (size_t)i * NHW_MAX_STREAM_BYTES);
-	if (len) len[i] = (uint32_t)L;
-	if (status) status[i] = st;
+	__shared__ __align__(16) uint8_t sx[8192 + CLL_PAD];
+	__shared__ __align__(16) uint8_t so[8192 + 16];
+	__shared__ int jend;
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int lane = threadIdx.x;
+	for (int k = lane; k < (8192 + CLL_PAD) / 4; k += 32) {
+		uint32_t w = reinterpret_cast<const uint32_t *>(im.tree1 + 16384)[k];
+		if (k < 2048) w &= 0xfcfcfcfcu;   // x[i] &= 252 (compress_pixel.c:886)
+		reinterpret_cast<uint32_t *>(sx)[k] = w;
+	}
+	__syncwarp();
+	if (lane == 0) jend = ll_dpcm_chroma_core(sx - 16384, so, 0);
+	__syncwarp();
+	const int j0 = im.hdr->y_res_comp, cnt = jend;
+	for (int k = lane; k < cnt; k += 32) im.llcode[j0 + k] = so[k];
+	for (int k = lane; k < 2048; k += 32) reinterpret_cast<uint32_t *>(im.tree1 + 16384)[k] = reinterpret_cast<const uint32_t *>(sx)[k];
+	if (lane == 0) im.hdr->end_ch_res = j0 + cnt;
+}
+
+// final: container bytes.  One CTA per image: thread 0 lays the sections out (enc_pack.cuh), all threads copy.
+#define WS_MAX_SECTIONS 40
+__global__ void __launch_bounds__(256) k_write_stream(EncBatch b, int n, uint8_t *out, uint32_t *len, int32_t *status)
+{
+	__shared__ const uint8_t *src[WS_MAX_SECTIONS];
+	__shared__ int off[WS_MAX_SECTIONS + 1];
+	__shared__ uint8_t hdr[64];
+	__shared__ int nsec, st;
+	const int i = blockIdx.x;
+	const EncImg im = make_img(b, i, 0);
+	if (threadIdx.x == 0) {
+		st = im.hdr->status;
+		nsec = 0;
+		off[0] = 0;
+		if (st == 0)
+			stream_layout(im, hdr, [&](const uint8_t *s, int cnt) {
+				if (nsec < WS_MAX_SECTIONS) { src[nsec] = s; off[nsec + 1] = off[nsec] + cnt; nsec++; }
+			});
+		if (len) len[i] = (uint32_t)off[nsec];
+		if (status) status[i] = st;
+	}
+	__syncthreads();
+	uint8_t *dst = out + (size_t)i * NHW_MAX_STREAM_BYTES;
+	for (int k = 0; k < nsec; k++) {
+		const uint8_t *s = src[k];
+		const int o = off[k], cnt = off[k + 1] - o;
+		for (int t = threadIdx.x; t < cnt; t += 256) dst[o + t] = s ? s[t] : (uint8_t)0;
+	}
 }
 
 // exclusive prefix of the stream lengths (one CTA, n <= a few thousand) ...
@@ -1045,9 +1086,9 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH_L(c, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);
 
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
-	run_image(c, "c_ll_code", b, n, [=] __device__(const EncImg &im, int) { ll_dpcm_chroma_image(im); });
+	NHW_LAUNCH_L(c, "c_ll_code", k_c_ll_code, n, 32, 0, b);
 	NHW_LAUNCH_L(c, "entropy_pack", k_entropy, n, SEG_THREADS, 262144 / 8, b);
-	NHW_LAUNCH(c, k_write_stream, (n + 31) / 32, 32, 0, b, n, out_dev, len_dev, status_dev);
+	NHW_LAUNCH(c, k_write_stream, n, 256, 0, b, n, out_dev, len_dev, status_dev);
 }
 
 void pack_streams(nhw_ctx *c, int n)
