@@ -3,6 +3,7 @@
 // without a usable CUDA device nhw_create() fails and every other call needs a context.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <new>
@@ -129,12 +130,13 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	c->max_batch = max_batch;
 	c->prof = new nhw::ProfState();
 	const size_t B = (size_t)max_batch;
-	bool ok = check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-	ok = ok && check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-	for (int k = 0; k < 2 && ok; k++) {
-		ok = ok && check(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming), "cudaEventCreate");
-		ok = ok && check(cudaEventCreateWithFlags(&c->ev_consumed[k], cudaEventDisableTiming), "cudaEventCreate");
+	bool ok = true;
+	for (int k = 0; k < NHW_LANES && ok; k++) {
+		ok = ok && check(cudaStreamCreateWithFlags(&c->lanes[k], cudaStreamNonBlocking), "cudaStreamCreate");
+		ok = ok && check(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming), "cudaEventCreate");
 	}
+	ok = ok && check(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+	c->stream = c->lanes[0];
 	// every workspace array is zero-filled once: guard bands and never-written borders must
 	// read as 0 (canonical oracle semantics)
 	ok = ok && dev_alloc0(&c->rgb, B * NHW_RGB_BYTES);
@@ -148,11 +150,11 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	ok = ok && dev_alloc0(&c->rowmap, B * 512) && dev_alloc0(&c->rowcarry, B * 512);
 	ok = ok && dev_alloc0(&c->enc_bytes, B * (size_t)ENC_BYTES_SLOT) && dev_alloc0(&c->enc_hdr, B);
 	ok = ok && dev_alloc0(&c->out_dev, B * (size_t)NHW_MAX_STREAM_BYTES) && dev_alloc0(&c->pack_dev, B * (size_t)NHW_MAX_STREAM_BYTES);
-	ok = ok && dev_alloc0(&c->len_dev, B) && dev_alloc0(&c->status_dev, B) && dev_alloc0(&c->offs_dev, B + 1);
+	ok = ok && dev_alloc0(&c->len_dev, B) && dev_alloc0(&c->status_dev, B) && dev_alloc0(&c->offs_dev, B + 1 + NHW_LANES);
 	ok = ok && dev_alloc0(&c->dec_yuv, B * (size_t)NHW_RGB_BYTES);
 	ok = ok && check(cudaMalloc(&c->dec_desc_dev, B * sizeof(DecDesc)), "cudaMalloc");
 	ok = ok && check(cudaMallocHost(&c->dec_desc_host, B * sizeof(DecDesc)), "cudaMallocHost");
-	ok = ok && check(cudaMallocHost((void **)&c->offs_host, (B + 1) * sizeof(uint64_t)), "cudaMallocHost");
+	ok = ok && check(cudaMallocHost((void **)&c->offs_host, (B + 1 + NHW_LANES) * sizeof(uint64_t)), "cudaMallocHost");
 	ok = ok && check(cudaMallocHost((void **)&c->status_host, B * sizeof(int32_t)), "cudaMallocHost");
 	if (!ok || !check(cudaDeviceSynchronize(), "nhw_create sync")) { nhw_destroy(c); return NHW_ERR_CUDA; }
 	*out = c;
@@ -173,12 +175,11 @@ void nhw_destroy(nhw_ctx *c)
 	if (c->dec_desc_host) cudaFreeHost(c->dec_desc_host);
 	if (c->offs_host) cudaFreeHost(c->offs_host);
 	if (c->status_host) cudaFreeHost(c->status_host);
-	if (c->stream) cudaStreamDestroy(c->stream);
-	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-	for (int k = 0; k < 2; k++) {
-		if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
-		if (c->ev_consumed[k]) cudaEventDestroy(c->ev_consumed[k]);
+	for (int k = 0; k < NHW_LANES; k++) {
+		if (c->lanes[k]) cudaStreamDestroy(c->lanes[k]);
+		if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
 	}
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->prof) {
 		nhw::ProfState *p = static_cast<nhw::ProfState *>(c->prof);
 		nhw::prof_resolve(c);
@@ -269,6 +270,78 @@ static int finish(nhw_ctx *c, const char *what)
 	return NHW_OK;
 }
 
+// ---- lanes: sub-chunks side by side on their own streams and workspace slices --------------------
+struct LanePlan {
+	int lanes;           // sub-chunks in this wave
+	int slot;            // workspace images per lane
+	int first[NHW_LANES + 1];   // image range of each lane inside the wave
+};
+
+// Split the next `m` images (m <= max_batch) over the lanes.  Per-kernel profiling and the debug stop are
+// defined on one stream, so they run single-lane.
+static int env_lanes(const char *name, int dflt)
+{
+	const char *e = getenv(name);
+	const int v = e ? atoi(e) : dflt;
+	return v < 1 ? 1 : v > NHW_LANES ? NHW_LANES : v;
+}
+
+static LanePlan plan_lanes(const nhw_ctx *c, int m, int max_lanes)
+{
+	LanePlan p;
+	const int want = (c->profile || c->dbg_label[0] || c->max_batch < 2 * NHW_LANES) ? 1 : max_lanes;
+	p.slot = want == 1 ? c->max_batch : c->max_batch / want;
+	int lanes = want;
+	if (lanes > 1 && m < 2 * lanes) lanes = m >= 2 ? 2 : 1;
+	if (lanes == 1) p.slot = c->max_batch;
+	p.lanes = lanes;
+	for (int l = 0; l <= lanes; l++) p.first[l] = (int)((long long)m * l / lanes);
+	return p;
+}
+
+// A shallow copy of the context whose stream is lane l's and whose workspace pointers start at image `slot0`.
+static nhw_ctx lane_view(const nhw_ctx *c, int l, int slot0)
+{
+	nhw_ctx v = *c;
+	const size_t s = (size_t)slot0;
+	v.stream = c->lanes[l];
+	v.launches = 0;
+	v.rgb += s * NHW_RGB_BYTES;
+	v.y_jpeg += s * NHW_Y_SLOT; v.y_proc += s * NHW_Y_SLOT; v.y_aux += s * NHW_Y_SLOT; v.y_aux2 += s * NHW_Y_SLOT;
+	v.y_ll1 += s * NHW_C_SLOT; v.y_ll2save += s * NHW_C_SLOT;
+	v.c_u8 += s * 2 * NHW_CPLANE;
+	v.c_jpeg += s * 2 * NHW_C_SLOT; v.c_proc += s * 2 * NHW_C_SLOT; v.c_aux += s * 2 * NHW_C_SLOT;
+	v.c_ll1 += s * 2 * NHW_Q_SLOT; v.c_ll2save += s * 2 * NHW_Q_SLOT;
+	v.rowmap += s * 512; v.rowcarry += s * 512;
+	v.enc_bytes += s * (size_t)ENC_BYTES_SLOT; v.enc_hdr += s;
+	v.out_dev += s * (size_t)NHW_MAX_STREAM_BYTES; v.pack_dev += s * (size_t)NHW_MAX_STREAM_BYTES;
+	v.len_dev += s; v.status_dev += s; v.offs_dev += s + l; v.offs_host += s + l; v.status_host += s;
+	v.dec_yuv += s * (size_t)NHW_RGB_BYTES;
+	v.dec_desc_dev = static_cast<DecDesc *>(c->dec_desc_dev) + s;
+	v.dec_desc_host = static_cast<DecDesc *>(c->dec_desc_host) + s;
+	return v;
+}
+
+static void lanes_fork(nhw_ctx *c, int lanes)
+{
+	if (lanes <= 1) return;
+	cudaEventRecord(c->ev_fork, c->lanes[0]);
+	for (int l = 1; l < lanes; l++) cudaStreamWaitEvent(c->lanes[l], c->ev_fork, 0);
+}
+static void lanes_join(nhw_ctx *c, int lanes)
+{
+	for (int l = 1; l < lanes; l++) {
+		cudaEventRecord(c->ev_join[l], c->lanes[l]);
+		cudaStreamWaitEvent(c->lanes[0], c->ev_join[l], 0);
+	}
+}
+static void lane_done(nhw_ctx *c, nhw_ctx &v)
+{
+	c->launches += v.launches;
+	c->dbg_seen = v.dbg_seen;
+	c->dbg_stopped = v.dbg_stopped;
+}
+
 static bool quality_supported(int q) { return q >= 17 && q <= 23; }
 
 int nhw_stage_colorspace_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quality, int pre,
@@ -327,9 +400,19 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
-		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
-		nhw::encode_chunk(c, rgb_dev + (size_t)i0 * NHW_RGB_BYTES, m, quality, out_dev + (size_t)i0 * NHW_MAX_STREAM_BYTES,
-		                  len_dev ? len_dev + i0 : nullptr, status_dev ? status_dev + i0 : nullptr);
+		const int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
+		// device-resident input: the kernels of one chunk already fill the GPU and share L2 better on one stream
+		const LanePlan p = plan_lanes(c, m, env_lanes("NHW_LANES_DEVICE", 1));
+		lanes_fork(c, p.lanes);
+		for (int l = 0; l < p.lanes; l++) {
+			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
+			if (cnt <= 0) continue;
+			nhw_ctx v = lane_view(c, l, l * p.slot);
+			nhw::encode_chunk(&v, rgb_dev + (size_t)a * NHW_RGB_BYTES, cnt, quality, out_dev + (size_t)a * NHW_MAX_STREAM_BYTES,
+			                  len_dev ? len_dev + a : nullptr, status_dev ? status_dev + a : nullptr);
+			lane_done(c, v);
+		}
+		lanes_join(c, p.lanes);
 	}
 	return finish(c, "nhw_encode_batch_device");
 }
@@ -340,49 +423,42 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 	if (!c || !rgb || !out || !offsets || n <= 0) return NHW_ERR_ARG;
 	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q23 are)", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
-	// Software pipeline over sub-chunks: while the kernels of sub-chunk k run on `stream`, the pixels of
-	// sub-chunk k+1 travel host->device on `copy_stream` into the other half of the staging buffer.
-	// (sub-chunks stay large: several stages still run one thread per image and cost the same for 512 images as for 2048)
-	const int sub = c->max_batch >= 2 ? c->max_batch / 2 : 1;
-	const bool overlap = c->max_batch >= 2 * sub;
-	const int nsub = (n + sub - 1) / sub;
-	auto stage = [&](int k) { return c->rgb + (size_t)(overlap ? (k & 1) : 0) * sub * NHW_RGB_BYTES; };
-	auto count = [&](int k) { return n - k * sub < sub ? n - k * sub : sub; };
-	auto upload = [&](int k) {
-		cudaStream_t s = overlap ? c->copy_stream : c->stream;
-		if (overlap && k >= 2) cudaStreamWaitEvent(s, c->ev_consumed[k & 1], 0);
-		bool ok = check(cudaMemcpyAsync(stage(k), rgb + (size_t)k * sub * NHW_RGB_BYTES, (size_t)count(k) * NHW_RGB_BYTES,
-		                                cudaMemcpyHostToDevice, s), "H2D pixels");
-		if (overlap) cudaEventRecord(c->ev_copied[k & 1], s);
-		return ok;
-	};
+	// Waves of up to NHW_LANES sub-chunks: each lane uploads its pixels, encodes and packs on its own stream, so
+	// the uploads of some lanes overlap the kernels of others; the streams' bytes come back in image order.
 	uint64_t pos = 0;
 	offsets[0] = 0;
-	if (!upload(0)) return NHW_ERR_CUDA;
-	for (int k = 0; k < nsub; k++) {
-		const int i0 = k * sub, m = count(k);
-		if (overlap && k + 1 < nsub && !upload(k + 1)) return NHW_ERR_CUDA;
-		if (overlap) cudaStreamWaitEvent(c->stream, c->ev_copied[k & 1], 0);
-		nhw::encode_chunk(c, stage(k), m, quality, c->out_dev, c->len_dev, c->status_dev);
-		if (overlap) cudaEventRecord(c->ev_consumed[k & 1], c->stream);
-		nhw::pack_streams(c, m);
-		cudaMemcpyAsync(c->offs_host, c->offs_dev, (size_t)(m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
-		cudaMemcpyAsync(c->status_host, c->status_dev, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-		int rc = finish(c, "nhw_encode_batch");
-		if (rc) return rc;
-		const uint64_t total = c->offs_host[m];
-		if (pos + total > out_cap) { nhw::set_error("output buffer too small"); return NHW_ERR_ARG; }
-		if (total) {
-			if (!check(cudaMemcpyAsync(out + pos, c->pack_dev, total, cudaMemcpyDeviceToHost, c->stream), "D2H streams")) return NHW_ERR_CUDA;
-			rc = finish(c, "nhw_encode_batch");
-			if (rc) return rc;
+	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
+		const int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
+		const LanePlan p = plan_lanes(c, m, env_lanes("NHW_LANES_ENCODE", NHW_LANES));
+		nhw_ctx v[NHW_LANES];
+		lanes_fork(c, p.lanes);
+		for (int l = 0; l < p.lanes; l++) {
+			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
+			v[l] = lane_view(c, l, l * p.slot);
+			if (cnt <= 0) continue;
+			if (!check(cudaMemcpyAsync(v[l].rgb, rgb + (size_t)a * NHW_RGB_BYTES, (size_t)cnt * NHW_RGB_BYTES,
+			                           cudaMemcpyHostToDevice, v[l].stream), "H2D pixels")) return NHW_ERR_CUDA;
+			nhw::encode_chunk(&v[l], v[l].rgb, cnt, quality, v[l].out_dev, v[l].len_dev, v[l].status_dev);
+			nhw::pack_streams(&v[l], cnt);
+			cudaMemcpyAsync(v[l].offs_host, v[l].offs_dev, (size_t)(cnt + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, v[l].stream);
+			cudaMemcpyAsync(v[l].status_host, v[l].status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v[l].stream);
+			lane_done(c, v[l]);
 		}
-		for (int i = 0; i < m; i++) {
-			offsets[i0 + i + 1] = pos + c->offs_host[i + 1];
-			if (status) status[i0 + i] = c->status_host[i];
+		for (int l = 0; l < p.lanes; l++) {
+			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
+			if (cnt <= 0) continue;
+			if (!check(cudaGetLastError(), "nhw_encode_batch") || !check(cudaStreamSynchronize(v[l].stream), "nhw_encode_batch")) return NHW_ERR_CUDA;
+			const uint64_t total = v[l].offs_host[cnt];
+			if (pos + total > out_cap) { nhw::set_error("output buffer too small"); return NHW_ERR_ARG; }
+			if (total && !check(cudaMemcpyAsync(out + pos, v[l].pack_dev, total, cudaMemcpyDeviceToHost, v[l].stream), "D2H streams")) return NHW_ERR_CUDA;
+			for (int i = 0; i < cnt; i++) {
+				offsets[a + i + 1] = pos + v[l].offs_host[i + 1];
+				if (status) status[a + i] = v[l].status_host[i];
+			}
+			pos += total;
 		}
-		pos += total;
-		if (!overlap && k + 1 < nsub && !upload(k + 1)) return NHW_ERR_CUDA;
+		for (int l = 0; l < p.lanes; l++)
+			if (!check(cudaStreamSynchronize(c->lanes[l]), "nhw_encode_batch")) return NHW_ERR_CUDA;
 	}
 	return NHW_OK;
 }
@@ -393,31 +469,43 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 	if (!c || !in || !offsets || (!rgb && !yuv) || n <= 0) return NHW_ERR_ARG;
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
-	DecDesc *desc = static_cast<DecDesc *>(c->dec_desc_host);
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
 		const int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
-		const uint64_t base = offsets[i0], total = offsets[i0 + m] - base;
-		if (total + 64 > (uint64_t)c->max_batch * NHW_MAX_STREAM_BYTES) { nhw::set_error("input chunk too large"); return NHW_ERR_ARG; }
-		for (int i = 0; i < m; i++) {
-			const uint64_t o = offsets[i0 + i] - base, len = offsets[i0 + i + 1] - offsets[i0 + i];
-			c->offs_host[i] = o;
-			c->status_host[i] = nhw_parse_header(in + base + o, (size_t)len, &desc[i]);
-			if (quality) quality[i0 + i] = desc[i].quality;
+		const LanePlan p = plan_lanes(c, m, env_lanes("NHW_LANES_DECODE", NHW_LANES));
+		nhw_ctx v[NHW_LANES];
+		lanes_fork(c, p.lanes);
+		for (int l = 0; l < p.lanes; l++) {
+			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
+			v[l] = lane_view(c, l, l * p.slot);
+			if (cnt <= 0) continue;
+			nhw_ctx &w = v[l];
+			DecDesc *desc = static_cast<DecDesc *>(w.dec_desc_host);
+			const uint64_t base = offsets[a], total = offsets[a + cnt] - base;
+			if (total + 64 > (uint64_t)p.slot * NHW_MAX_STREAM_BYTES) { nhw::set_error("input chunk too large"); return NHW_ERR_ARG; }
+			for (int i = 0; i < cnt; i++) {
+				const uint64_t o = offsets[a + i] - base, len = offsets[a + i + 1] - offsets[a + i];
+				w.offs_host[i] = o;
+				w.status_host[i] = nhw_parse_header(in + base + o, (size_t)len, &desc[i]);
+				if (quality) quality[a + i] = desc[i].quality;
+			}
+			bool ok = check(cudaMemcpyAsync(w.pack_dev, in + base, total, cudaMemcpyHostToDevice, w.stream), "H2D streams");
+			// the bit reader may look a few words past the last code: keep that tail defined
+			ok = ok && check(cudaMemsetAsync(w.pack_dev + total, 0, 64, w.stream), "memset tail");
+			ok = ok && check(cudaMemcpyAsync(w.dec_desc_dev, desc, (size_t)cnt * sizeof(DecDesc), cudaMemcpyHostToDevice, w.stream), "H2D desc");
+			ok = ok && check(cudaMemcpyAsync(w.offs_dev, w.offs_host, (size_t)cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, w.stream), "H2D offs");
+			ok = ok && check(cudaMemcpyAsync(w.status_dev, w.status_host, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, w.stream), "H2D status");
+			if (!ok) return NHW_ERR_CUDA;
+			nhw::decode_chunk(&w, w.pack_dev, w.offs_dev, static_cast<const DecDesc *>(w.dec_desc_dev), w.status_dev, cnt, w.rgb);
+			if (rgb) cudaMemcpyAsync(rgb + (size_t)a * NHW_RGB_BYTES, w.rgb, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);
+			if (yuv) cudaMemcpyAsync(yuv + (size_t)a * NHW_RGB_BYTES, w.dec_yuv, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);
+			cudaMemcpyAsync(w.status_host, w.status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, w.stream);
+			lane_done(c, w);
 		}
-		bool ok = check(cudaMemcpyAsync(c->pack_dev, in + base, total, cudaMemcpyHostToDevice, c->stream), "H2D streams");
-		// the bit reader may look a few words past the last code: keep that tail defined
-		ok = ok && check(cudaMemsetAsync(c->pack_dev + total, 0, 64, c->stream), "memset tail");
-		ok = ok && check(cudaMemcpyAsync(c->dec_desc_dev, desc, (size_t)m * sizeof(DecDesc), cudaMemcpyHostToDevice, c->stream), "H2D desc");
-		ok = ok && check(cudaMemcpyAsync(c->offs_dev, c->offs_host, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream), "H2D offs");
-		ok = ok && check(cudaMemcpyAsync(c->status_dev, c->status_host, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream), "H2D status");
-		if (!ok) return NHW_ERR_CUDA;
-		nhw::decode_chunk(c, c->pack_dev, c->offs_dev, static_cast<const DecDesc *>(c->dec_desc_dev), c->status_dev, m, c->rgb);
-		if (rgb) cudaMemcpyAsync(rgb + (size_t)i0 * NHW_RGB_BYTES, c->rgb, (size_t)m * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, c->stream);
-		if (yuv) cudaMemcpyAsync(yuv + (size_t)i0 * NHW_RGB_BYTES, c->dec_yuv, (size_t)m * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, c->stream);
-		cudaMemcpyAsync(c->status_host, c->status_dev, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-		int rc = finish(c, "nhw_decode_batch");
-		if (rc) return rc;
-		for (int i = 0; status && i < m; i++) status[i0 + i] = c->status_host[i];
+		for (int l = 0; l < p.lanes; l++) {
+			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
+			if (!check(cudaGetLastError(), "nhw_decode_batch") || !check(cudaStreamSynchronize(c->lanes[l]), "nhw_decode_batch")) return NHW_ERR_CUDA;
+			for (int i = 0; status && i < cnt; i++) status[a + i] = v[l].status_host[i];
+		}
 	}
 	return NHW_OK;
 }

@@ -1,5 +1,6 @@
 // nhw_ctx.h -- host-side context of libnhw_cuda (internal; the public face is include/nhw_cuda.h)
 #pragma once
+#define NHW_LANES 4
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -11,9 +12,12 @@ struct DecDesc;
 struct nhw_ctx {
 	int device;
 	int max_batch;
-	cudaStream_t stream;
-	cudaStream_t copy_stream;   // host<->device copies that overlap the kernels of `stream`
-	cudaEvent_t ev_copied[2], ev_consumed[2];
+	cudaStream_t stream;        // the stream kernels are issued on (lanes[0] for the context itself)
+	// A batch is cut into up to NHW_LANES sub-chunks that run side by side, each on its own stream and on its
+	// own slice of every workspace array (api.cu: lane_view): the many latency-bound stages of one sub-chunk
+	// overlap the others', and host<->device copies overlap kernels.
+	cudaStream_t lanes[4];
+	cudaEvent_t ev_fork, ev_join[4];
 	uint64_t launches;
 	char dbg_label[64];  // debug: stop issuing kernels after the dbg_count-th launch of this label
 	int dbg_count, dbg_seen, dbg_stopped;
