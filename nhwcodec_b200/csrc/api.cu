@@ -136,6 +136,7 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 		ok = ok && check(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming), "cudaEventCreate");
 	}
 	ok = ok && check(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+
 	c->stream = c->lanes[0];
 	// every workspace array is zero-filled once: guard bands and never-written borders must
 	// read as 0 (canonical oracle semantics)
@@ -180,6 +181,7 @@ void nhw_destroy(nhw_ctx *c)
 		if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
 	}
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+
 	if (c->prof) {
 		nhw::ProfState *p = static_cast<nhw::ProfState *>(c->prof);
 		nhw::prof_resolve(c);

@@ -26,7 +26,8 @@ enum : int {
 	OFF_CHRES = ENC_NEXT(OFF_TREE1, NHW_CAP_TREE1),
 	OFF_LLCODE = ENC_NEXT(OFF_CHRES, 16384),
 	OFF_EXW = ENC_NEXT(OFF_LLCODE, 49152),
-	OFF_RES1 = ENC_NEXT(OFF_EXW, 49152),
+	OFF_EXWUV = ENC_NEXT(OFF_EXW, 49152),
+	OFF_RES1 = ENC_NEXT(OFF_EXWUV, 32768),
 	OFF_RES1_BIT = ENC_NEXT(OFF_RES1, 65600),
 	OFF_RES1_WORD = ENC_NEXT(OFF_RES1_BIT, 8224),
 	OFF_RES3 = ENC_NEXT(OFF_RES1_WORD, 8224),

@@ -110,13 +110,13 @@ NHW_HD void c_residual_tags_row(const EncImg &im, int q, int r /* 0..127 */)
 }
 
 // ---- chroma LL (64x64) -> tree1 bytes + exw escapes (nhw_encoder.c:2482-2515, 2781-2813).
-// exw entries go to a per-component list (im.tmp3 for U, im.tmp3+16384 for V) that the
+// exw entries go to a per-component list (im.exw_uv for U, im.exw_uv+16384 for V) that the
 // container writer splices after the luma list with the two-zero separators.
 NHW_HDN int c_ll_to_bytes_image(const EncImg &im, int is_v)
 {
 	int16_t *P = im.cproc;
 	uint8_t *t = im.tree1;
-	uint8_t *exw = im.tmp3 + (is_v ? 16384 : 0);
+	uint8_t *exw = im.exw_uv + (is_v ? 16384 : 0);
 	int a = is_v ? 20480 : 16384, e = 0;
 	for (int r = 0; r < 64; r++) {
 		for (int j = 0; j < 64; j++) {

@@ -66,7 +66,8 @@ struct EncImg {
 	uint8_t *tree1;      // LL bytes: Y 16384 + U 4096 + V 4096 (+1)
 	uint8_t *ch_res;     // un-truncated LL2 bytes (E11), 16384
 	uint8_t *llcode;     // LL code: luma part then chroma part (the file's ch_res section)
-	uint8_t *exw;        // exw_Y
+	uint8_t *exw;        // exw_Y (luma part)
+	uint8_t *exw_uv;     // exw_Y entries of U (first 16384 bytes) and V (next 16384), spliced in by the writer
 	uint8_t *res1, *res1_bit, *res1_word;
 	uint8_t *res3, *res3_bit, *res3_word;
 	uint8_t *res4;

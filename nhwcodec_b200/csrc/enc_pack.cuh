@@ -265,9 +265,9 @@ NHW_HD int stream_layout(const EncImg &im, uint8_t *hdr, Section section)
 	section(im.codebook2, h->size_tree2);
 	section(im.exw, h->exw_y_len);
 	section(nullptr, 2);                       // 0,0 separator
-	section(im.tmp3, h->exw_u_len);
+	section(im.exw_uv, h->exw_u_len);
 	section(nullptr, 2);
-	section(im.tmp3 + 16384, h->exw_v_len);
+	section(im.exw_uv + 16384, h->exw_v_len);
 	if (q > 12) { section(im.res1, h->res1_len); section(im.res1_bit, h->res1_bit_len); section(im.res1_word, h->res1_word_len); }
 	if (q > 17) section(im.res4, h->res4_len);
 	if (q >= 19) { section(im.res3, h->res3_len); section(im.res3_bit, h->res3_bit_len); section(im.res3_word, h->res3_word_len); }

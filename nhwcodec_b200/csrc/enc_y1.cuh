@@ -265,6 +265,54 @@ NHW_HD int e6d_soften(int a)
 	return a < -11 ? a + 7 : a < -7 ? a + 4 : a < -5 ? a + 2 : a + 1;
 }
 
+// One step of E6d: the correction of a cell from its own difference `scan`, the right neighbour's (original)
+// difference `nxt` and the left neighbour's difference AFTER its correction `prev`.  Only |scan| in 2..4 looks
+// at the neighbours at all.
+NHW_HD bool e6d_needs_neighbours(int scan) { const int a = nhw_iabs(scan); return a >= 2 && a <= 4; }
+NHW_HD int e6d_delta(int scan, int nxt, int prev)
+{
+	if (scan > 11) return -7;
+	if (scan > 7) return -4;
+	if (scan > 5) return -2;
+	if (scan > 4) return -1;
+	if (scan < -11) return 7;
+	if (scan < -7) return 4;
+	if (scan < -5) return 2;
+	if (scan < -4) return 1;
+	if (nhw_iabs(scan) <= 1) return 0;
+	const int a = e6d_soften(nxt) + prev;
+	if (scan >= 4 && a >= 1) return -1;
+	if (scan <= -4 && a <= -1) return 1;
+	if (scan == 3 && a >= 0) return -1;
+	if (scan == -3 && a <= 0) return 1;
+	if (nhw_iabs(a) >= 3) {
+		if (scan > 0 && a > 0) return -1;
+		if (scan < 0 && a < 0) return 1;
+		if (a >= 5) return -2;
+		if (a <= -5) return 2;
+		if (a >= 4) return -1;
+		if (a <= -4) return 1;
+	}
+	return 0;
+}
+
+// Correction of cell j from the row's differences sc[-1 .. 256] (sc[j] = P[j] - L[j] before the pass).  The
+// left-to-right dependency only runs through unbroken stretches of cells with |difference| in 2..4, so a cell
+// finds the start of its stretch and replays it: cells are independent of each other.
+NHW_HD int e6d_delta_at(const int16_t *sc, int j)
+{
+	if (!e6d_needs_neighbours(sc[j])) return e6d_delta(sc[j], 0, 0);
+	int start = j;
+	while (start > 0 && e6d_needs_neighbours(sc[start - 1])) start--;
+	int prev = start > 0 ? sc[start - 1] + e6d_delta(sc[start - 1], 0, 0) : sc[-1];
+	int d = 0;
+	for (int t = start; t <= j; t++) {
+		d = e6d_delta(sc[t], sc[t + 1], prev);
+		prev = sc[t] + d;
+	}
+	return d;
+}
+
 // P, J, L point at column 0 of the row; P[-1], P[256], L[-1], L[256] are the flat neighbours the
 // reference reads at the row ends.  J may alias L (J[j] is written after the last read of L[j]).
 NHW_HD void y_e6d_correct_cells(int16_t *P, int16_t *J, const int16_t *L)
@@ -274,30 +322,7 @@ NHW_HD void y_e6d_correct_cells(int16_t *P, int16_t *J, const int16_t *L)
 	for (int j = 0; j < 256; j++) {
 		const int nxt = P[j + 1] - L[j + 1];
 		const int scan = cur;
-		int d = 0;
-		if (scan > 11) d = -7;
-		else if (scan > 7) d = -4;
-		else if (scan > 5) d = -2;
-		else if (scan > 4) d = -1;
-		else if (scan < -11) d = 7;
-		else if (scan < -7) d = 4;
-		else if (scan < -5) d = 2;
-		else if (scan < -4) d = 1;
-		else if (nhw_iabs(scan) > 1) {
-			int a = e6d_soften(nxt) + prev;
-			if (scan >= 4 && a >= 1) d = -1;
-			else if (scan <= -4 && a <= -1) d = 1;
-			else if (scan == 3 && a >= 0) d = -1;
-			else if (scan == -3 && a <= 0) d = 1;
-			else if (nhw_iabs(a) >= 3) {
-				if (scan > 0 && a > 0) d = -1;
-				else if (scan < 0 && a < 0) d = 1;
-				else if (a >= 5) d = -2;
-				else if (a <= -5) d = 2;
-				else if (a >= 4) d = -1;
-				else if (a <= -4) d = 1;
-			}
-		}
+		const int d = e6d_delta(scan, nxt, prev);
 		const int l = L[j];
 		J[j] = (int16_t)(l + d);
 		P[j] = (int16_t)(P[j] + d);

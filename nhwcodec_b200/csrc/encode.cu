@@ -39,6 +39,7 @@ __device__ __forceinline__ EncImg make_img(const EncBatch &b, int i, int comp)
 	im.ch_res = bytes + OFF_CHRES;
 	im.llcode = bytes + OFF_LLCODE;
 	im.exw = bytes + OFF_EXW;
+	im.exw_uv = bytes + OFF_EXWUV;
 	im.res1 = bytes + OFF_RES1;
 	im.res1_bit = bytes + OFF_RES1_BIT;
 	im.res1_word = bytes + OFF_RES1_WORD;
@@ -363,37 +364,39 @@ __global__ void __launch_bounds__(256) k_e18_lists(EncBatch b, int q)
 	}
 }
 
-// ---- E6d: LL1 correction, sequential along a row.  One warp per 32 rows; the rows are staged in
-// shared memory at an odd word stride so that "thread = row" walks are bank-conflict free and all
-// global traffic is coalesced.
-#define E6D_STRIDE 262   // int16 cells per staged row: 2 left (cell -1 used), 256, 4 right (cell 256 used)
-__global__ void __launch_bounds__(32) k_e6d_correct(EncBatch b)
+// ---- E6d: LL1 correction (enc_y1.cuh: e6d_delta_at), one thread per cell; 8 rows per CTA
+__global__ void __launch_bounds__(256) k_e6d_correct(EncBatch b)
 {
-	__shared__ __align__(16) int16_t sP[32 * E6D_STRIDE];
-	__shared__ __align__(16) int16_t sL[32 * E6D_STRIDE];
+	__shared__ int16_t sc[8][264];   // differences of a row, columns -1 .. 256 at index 1 .. 258
 	const EncImg im = make_img(b, blockIdx.y, 0);
-	const int r0 = blockIdx.x * 32, lane = threadIdx.x;
-	for (int rr = 0; rr < 32; rr++) {
-		const int16_t *gp = im.proc + (r0 + rr) * YW, *gl = im.ll1 + (r0 + rr) * 256;
-		uint32_t *dp = reinterpret_cast<uint32_t *>(sP + rr * E6D_STRIDE + 2), *dl = reinterpret_cast<uint32_t *>(sL + rr * E6D_STRIDE + 2);
-		for (int k = lane; k < 128; k += 32) {
-			dp[k] = reinterpret_cast<const uint32_t *>(gp)[k];
-			dl[k] = reinterpret_cast<const uint32_t *>(gl)[k];
-		}
-		if (lane == 0) { sP[rr * E6D_STRIDE + 1] = gp[-1]; sL[rr * E6D_STRIDE + 1] = gl[-1]; }
-		if (lane == 1) { sP[rr * E6D_STRIDE + 258] = gp[256]; sL[rr * E6D_STRIDE + 258] = gl[256]; }
+	const int j = threadIdx.x;
+	for (int k = 0; k < 8; k++) {
+		const int r = blockIdx.x * 8 + k;
+		const int16_t *P = im.proc + r * YW, *L = im.ll1 + r * 256;
+		sc[k][j + 2] = (int16_t)(P[j] - L[j]);
+		if (j == 0) sc[k][1] = (int16_t)(P[-1] - L[-1]);
+		if (j == 255) sc[k][258] = (int16_t)(P[256] - L[256]);
 	}
-	__syncwarp();
-	y_e6d_correct_cells(sP + lane * E6D_STRIDE + 2, sL + lane * E6D_STRIDE + 2, sL + lane * E6D_STRIDE + 2);
-	__syncwarp();
-	for (int rr = 0; rr < 32; rr++) {
-		int16_t *gp = im.proc + (r0 + rr) * YW, *gj = im.jpeg + (r0 + rr) * YW;
-		const uint32_t *dp = reinterpret_cast<const uint32_t *>(sP + rr * E6D_STRIDE + 2), *dl = reinterpret_cast<const uint32_t *>(sL + rr * E6D_STRIDE + 2);
-		for (int k = lane; k < 128; k += 32) {
-			reinterpret_cast<uint32_t *>(gp)[k] = dp[k];
-			reinterpret_cast<uint32_t *>(gj)[k] = dl[k];
-		}
+	__syncthreads();
+	for (int k = 0; k < 8; k++) {
+		const int r = blockIdx.x * 8 + k;
+		int16_t *P = im.proc + r * YW, *J = im.jpeg + r * YW;
+		const int16_t *L = im.ll1 + r * 256;
+		const int d = e6d_delta_at(&sc[k][2], j);
+		J[j] = (int16_t)(L[j] + d);
+		P[j] = (int16_t)(P[j] + d);
 	}
+}
+
+// ---- E19: restore the level-2 region from the resIII snapshot (y_e19_restore_row), one thread per cell pair
+__global__ void __launch_bounds__(128) k_e19_restore(EncBatch b)
+{
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	const int r = blockIdx.x, j = threadIdx.x * 2;
+	const uint32_t w = *reinterpret_cast<const uint32_t *>(im.ll2s + r * 256 + j);
+	int v0 = (int16_t)(w & 0xffff), v1 = (int16_t)(w >> 16);
+	if (r < 128 && j < 128) { if (v0 <= 8000) v0 = 0; if (v1 <= 8000) v1 = 0; }
+	*reinterpret_cast<uint32_t *>(im.proc + r * YW + j) = (uint32_t)(uint16_t)v0 | ((uint32_t)(uint16_t)v1 << 16);
 }
 
 // ---- offsetY loop 4 + serpentine scan, pointwise (enc_point.cuh): 16 rows per CTA, 8 cells per thread
@@ -1005,7 +1008,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	run_rows(c, "y_recons1_quant", b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 1); });
 	idwt_luma256(c, b, n);
 	run_rows(c, "y_e6c_apply", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6c_apply_row(im, r); });
-	NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(8, n), 32, 0, b);
+	NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(32, n), 256, 0, b);
 	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
 
 	// ---- LL2 coding (nhw_encoder.c:623-757)
@@ -1046,7 +1049,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH_L(c, "y_e18_lists", k_e18_lists, n, 256, 0, b, q);
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
-	run_rows(c, "y_e19_restore", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e19_restore_row(im, r); });
+	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(256, n), 128, 0, b);
 	for (int pass = 0; pass < 3; pass++)
 		run_wavefront(c, "y_e20_cleanup", b, n, wf_e20_geom(pass),
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_e20_cell(im, q, ratio, pass, r, j); });

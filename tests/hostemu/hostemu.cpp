@@ -56,6 +56,7 @@ Work *make_work()
 	im.ch_res = carve<uint8_t>(w->mem, off, 16384, NHW_GUARD_B);
 	im.llcode = carve<uint8_t>(w->mem, off, 49152, NHW_GUARD_B);
 	im.exw = carve<uint8_t>(w->mem, off, 3 * 16384, NHW_GUARD_B);
+	im.exw_uv = carve<uint8_t>(w->mem, off, 2 * 16384, NHW_GUARD_B);
 	im.res1 = carve<uint8_t>(w->mem, off, NHW_CAP_LIST, NHW_GUARD_B);
 	im.res1_bit = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
 	im.res1_word = carve<uint8_t>(w->mem, off, NHW_CAP_LIST / 8 + 16, NHW_GUARD_B);
@@ -480,7 +481,20 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	for (int r = 255; r >= 0; r--) y_e6c_apply_row(im, r);
 	T("y_e6c_proc", im.proc, 512 * 512 * 2);
 	T("y_e6c_ll1", im.ll1, 65536 * 2);
-	for (int r = 255; r >= 0; r--) y_e6d_correct_row(im, r);
+	if (getenv("HE_SERIAL")) { for (int r = 255; r >= 0; r--) y_e6d_correct_row(im, r); }
+	else {   // cell-parallel form: every cell from the row's original differences
+		std::vector<int16_t> sc(264);
+		for (int r = 255; r >= 0; r--) {
+			int16_t *P = im.proc + r * 512, *J = im.jpeg + r * 512;
+			const int16_t *L = im.ll1 + r * 256;
+			for (int j = -1; j <= 256; j++) sc[j + 2] = (int16_t)(P[j] - L[j]);
+			for (int j = 255; j >= 0; j--) {
+				const int d = e6d_delta_at(&sc[2], j);
+				J[j] = (int16_t)(L[j] + d);
+				P[j] = (int16_t)(P[j] + d);
+			}
+		}
+	}
 	T("y_e6d_jpeg", im.jpeg, 512 * 512 * 2);
 	fwd_level(im.jpeg, 512, false, im.proc, 512, 256, tmp);
 	T("y_dwt2b_proc", im.proc, 512 * 512 * 2);
