@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(128) k_recons_ll2_wave(EncBatch b, int q, int 
 
 // LL2 -> bytes + DPCM coding in parallel form (enc_ll_par.cuh), one CTA of 128 threads per image.
 // shared memory: band copy (later: output offsets), sample values (later: step links), res4 rows.
-#define LL2_CODE_SMEM (LL2_SMEM_BYTES + 16384 * 2 + 128 * 32 + 128 * 4 + 64)
+#define LL2_CODE_SMEM (LL2_SMEM_BYTES + 16384 * 2 + 128 * 32 + 128 * 4 + 64)   // band (later: bytes + chain marks), samples (later: steps), res4 rows, counters
 __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 {
 	extern __shared__ __align__(16) int16_t sP[];
@@ -267,14 +267,24 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 			__syncthreads();
 		}
 	}
-	for (int a = t; a < 16384; a += 128)
-		if (!ll2_is_escape(V[a], a)) ll2_bytes_store(im, a, V[a]);
+	// ---- bytes.  A cell whose value does not fit a byte ("escape") repeats the byte on its left and goes to
+	// the exw_Y list; lists are in raster order: each thread owns 128 consecutive cells, counts, CTA scan, writes.
+	uint8_t *sx = reinterpret_cast<uint8_t *>(sP);            // the band copy is dead: tree1 bytes [0, 16384 + 128)
+	uint8_t *vis = sx + 16384 + 256;                          // chain marks, one byte per position
+	int *tot = cnt + 2;                                       // [0] escapes, [1] code bytes, [2] raw samples
+	__shared__ int seg_cnt[3][129];
+	__shared__ int seg_exit[128], seg_merge[128];
+	{
+		int ne = 0;
+		for (int a = 128 * t; a < 128 * t + 128; a++) ne += ll2_is_escape(V[a], a) ? 1 : 0;
+		seg_cnt[0][t] = ne;
+	}
 	__syncthreads();
 	if (t == 0) {
-		int e = 0;
-		for (int a = 1; a < 16384; a++)
-			if (ll2_is_escape(V[a], a)) ll2_bytes_escape(im, a, V[a], e);
-		h->exw_y_len = e;
+		int run = 0;
+		for (int k = 0; k < 128; k++) { const int v = seg_cnt[0][k]; seg_cnt[0][k] = run; run += v; }
+		tot[0] = run;
+		h->exw_y_len = 3 * run;
 		if (q > 17) {
 			int n = 0;
 			for (int r = 0; r < 128; r++)
@@ -283,10 +293,38 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 		}
 	}
 	__syncthreads();
-	// ---- DPCM coder over the 16384 bytes just written (tree1)
-	const uint8_t *x = im.tree1;
-	uint16_t *info = reinterpret_cast<uint16_t *>(V);      // step link of every position
-	uint16_t *offs = reinterpret_cast<uint16_t *>(sP);     // output offset of the visited ones
+	{
+		int e = 3 * seg_cnt[0][t];
+		for (int a = 128 * t; a < 128 * t + 128; a++) {
+			int v = V[a];
+			if (ll2_is_escape(v, a)) {
+				im.exw[e++] = (uint8_t)(a >> 7);
+				if (v > 255) { im.exw[e++] = (uint8_t)((a & 127) + 128); const int y = v - 255; im.exw[e++] = (uint8_t)(y > 255 ? 255 : y); }
+				else { im.exw[e++] = (uint8_t)(a & 127); im.exw[e++] = (uint8_t)(v < -255 ? 255 : -v); }
+				int p = a - 1;
+				while (ll2_is_escape(V[p], p)) p--;               // position 0 never is one
+				v = V[p];
+				v = v > 255 ? 255 : v < 0 ? 0 : v;
+				sx[a] = (uint8_t)(v & 254);
+				im.tree1[a] = sx[a];
+				im.ch_res[a] = sx[a];
+			} else {
+				v = v > 255 ? 255 : v < 0 ? 0 : v;
+				sx[a] = (uint8_t)(v & 254);
+				im.tree1[a] = sx[a];
+				im.ch_res[a] = (uint8_t)v;
+			}
+		}
+		if (t == 0) for (int k = 0; k < 256; k++) sx[16384 + k] = 0;   // tree1[16384..] is still zero while luma is coded
+	}
+	__syncthreads();
+	// ---- DPCM coder over the 16384 bytes (enc_ll_par.cuh).  Every position gets its step (where the coder would
+	// go next from there, how many bytes it emits); the positions the coder really visits are the orbit of 1.
+	// Each thread walks the orbit of its segment's first position (speculation), one thread then stitches the
+	// segments together: the true chain enters a segment somewhere, runs until it meets the speculative
+	// chain (from there on they coincide) or leaves the segment.  Offsets are a CTA scan over the segments.
+	const uint8_t *x = sx;
+	uint16_t *info = reinterpret_cast<uint16_t *>(V);      // (next - i) << 2 | (nbytes - 1) << 1 | raw
 	{
 		int a8 = 0, y16 = 0;
 		for (int i = t + 1; i < 16384; i += 128)
@@ -297,35 +335,66 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 	__syncthreads();
 	const int mode = cnt[1] > 299 ? 2 : (cnt[0] + cnt[1] > 179 ? 1 : 0);
 	for (int i = t; i < 16384; i += 128) {
-		offs[i] = 0xFFFF;
+		vis[i] = 0;
 		if (i >= 1) {
 			const LlStep s = ll_dpcm_step(x, i, mode, q);
 			info[i] = (uint16_t)(((s.next - i) << 2) | ((s.nbytes - 1) << 1) | s.raw);
 		}
 	}
 	__syncthreads();
-	if (t == 0) {
-		int off = 1, nmem = 0;
-		for (int i = 1; i < 16384;) {
-			const int inf = info[i];
-			offs[i] = (uint16_t)off;
-			off += 1 + ((inf >> 1) & 1);
-			if (inf & 1) { im.highres_word[nmem] = im.ch_res[i]; im.highres_mem[nmem++] = (uint16_t)i; }
-			i += inf >> 2;
-		}
-		im.llcode[0] = x[0];
-		h->highres_comp_len = nmem;
-		h->highres_mem_len = nmem;
-		h->res_low = mode;
-		h->y_res_comp = off;
+	{
+		int i = t ? 128 * t : 1;
+		const int end = 128 * t + 128;
+		while (i < end) { vis[i] = 1; i += info[i] >> 2; }
+		seg_exit[t] = i;
 	}
 	__syncthreads();
-	for (int i = t + 1; i < 16384; i += 128) {
-		const int off = offs[i];
-		if (off == 0xFFFF) continue;
-		const LlStep s = ll_dpcm_step(x, i, mode, q);
-		im.llcode[off] = s.b[0];
-		if (s.nbytes == 2) im.llcode[off + 1] = s.b[1];
+	if (t == 0) {
+		int p = seg_exit[0];
+		seg_merge[0] = 0;
+		for (int k = 1; k < 128; k++) {
+			const int end = 128 * k + 128;
+			int i = p;
+			while (i < end && vis[i] != 1) { vis[i] = 2; i += info[i] >> 2; }
+			if (i < end) { seg_merge[k] = i; p = seg_exit[k]; }     // met the speculative chain: it is the true one from here
+			else { seg_merge[k] = end; p = i; }                     // never met it inside this segment
+		}
+	}
+	__syncthreads();
+	{
+		const int m = seg_merge[t];
+		int nb = 0, nr = 0;
+		for (int i = 128 * t; i < 128 * t + 128; i++) {
+			if (i < m && vis[i] == 1) vis[i] = 0;
+			if (vis[i]) { const int inf = info[i]; nb += 1 + ((inf >> 1) & 1); nr += inf & 1; }
+		}
+		seg_cnt[1][t] = nb;
+		seg_cnt[2][t] = nr;
+	}
+	__syncthreads();
+	if (t < 2) {
+		int *v = seg_cnt[1 + t];
+		int run = 0;
+		for (int k = 0; k < 128; k++) { const int c = v[k]; v[k] = run; run += c; }
+		tot[1 + t] = run;
+	}
+	__syncthreads();
+	{
+		int off = 1 + seg_cnt[1][t], nm = seg_cnt[2][t];
+		for (int i = 128 * t; i < 128 * t + 128; i++) {
+			if (!vis[i]) continue;
+			const LlStep s = ll_dpcm_step(x, i, mode, q);
+			im.llcode[off++] = s.b[0];
+			if (s.nbytes == 2) im.llcode[off++] = s.b[1];
+			if (s.raw) { im.highres_word[nm] = im.ch_res[i]; im.highres_mem[nm++] = (uint16_t)i; }
+		}
+	}
+	if (t == 0) {
+		im.llcode[0] = x[0];
+		h->highres_comp_len = tot[2];
+		h->highres_mem_len = tot[2];
+		h->res_low = mode;
+		h->y_res_comp = 1 + tot[1];
 	}
 }
 
