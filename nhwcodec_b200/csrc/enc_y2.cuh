@@ -393,6 +393,75 @@ NHW_HD void e20_cell(int16_t *P, int a, int j, int jmax, int lo, int yw, int yw2
 	}
 }
 
+// ---- E20 without the wavefront.  The neighbour test of the rule above (|n| + 2 >= 8) has the same outcome on a
+// neighbour before and after that neighbour's own turn, except that an already visited neighbour (left, above)
+// with |n| < lo has been zeroed: "visited and |n| >= lo, or not visited and |n| >= 6".  So the count is a function
+// of the plane as it was before the pass; what remains sequential is only the one-cell look-ahead nudge along a
+// row (P[a+1]--, P[a+1]++, P[a+1] = -8), and a cell can only receive one if its value is > 7, == -7 or < -14.
+// The final value of a cell is found by replaying its row from the start of its unbroken stretch of such cells.
+// P = the plane BEFORE the pass (read only); regions of the three passes never read each other's cells.
+struct E20Pass { int r0, r1, j0, j1, jmax, lo, yw, yw2, pass; };   // rows [r0, r1), columns [j0, j1)
+NHW_HD E20Pass e20_pass(int q, int ratio, int pass)
+{
+	E20Pass g;
+	g.pass = pass;
+	if (pass == 0) { g.r0 = 1; g.r1 = 255; g.j0 = 257; g.j1 = 511; g.jmax = 510; g.lo = ratio - 2; if (q > 22) { g.yw = 8; g.yw2 = 4; } else { g.yw = 9; g.yw2 = 9; } }
+	else if (pass == 1) { g.r0 = 256; g.r1 = 511; g.j0 = 1; g.j1 = 256; g.jmax = 254; g.lo = ratio - 2; if (q > 22) { g.yw = 8; g.yw2 = 4; } else if (q > 17) { g.yw = 8; g.yw2 = 9; } else { g.yw = 9; g.yw2 = 9; } }
+	else { g.r0 = 256; g.r1 = 511; g.j0 = 257; g.j1 = 511; g.jmax = 510; g.lo = ratio - 1; g.yw = q > 22 ? 8 : 11; g.yw2 = g.yw; }
+	return g;
+}
+NHW_HD bool e20_can_receive(int v) { return v > 7 || v == -7 || v < -14; }
+// one cell's turn: v = its value when its turn comes (original + what the left neighbour did to it); returns its
+// final value and, in `give`, what it does to the cell on its right (0 none, -1, +1, or 100 = "becomes -8")
+NHW_HD int e20_turn(const int16_t *P, const E20Pass &g, int r, int j, int v, int &give)
+{
+	const int a = r * YW + j;
+	if (nhw_iabs(v) >= g.lo) {
+		if (nhw_iabs(v) < g.yw2) {
+			int cnt = 0;
+			if (nhw_iabs(P[a - 1]) >= (j > g.j0 ? g.lo : 6)) cnt++;     // visited neighbours survive only from lo up
+			if (nhw_iabs(P[a + 1]) >= 6) cnt++;
+			if (nhw_iabs(P[a - YW]) >= (r > g.r0 ? g.lo : 6)) cnt++;
+			if (nhw_iabs(P[a + YW]) >= 6) cnt++;
+			if (cnt < 3 && v < g.yw && v > -g.yw) {
+				if (g.pass == 0) { if (v < -6) v = -7; else if (v > 6) v = 7; }
+				else v = v < 0 ? -7 : 7;
+			} else if (g.pass == 1 && cnt == 0 && nhw_iabs(v) < g.yw2) v = v < 0 ? -7 : 7;
+		}
+	} else v = 0;
+	give = 0;
+	if (nhw_iabs(v) > 6) {
+		const int e = v, n1 = P[a + 1];
+		if (e >= 8 && (e & 7) < 2) {
+			if (n1 > 7 && n1 < 10000) give = -1;
+		} else if (e == -7 && n1 == 8) v = -8;
+		else if (e == 8 && n1 == -7) give = 100;
+		else if (e < -7 && ((-e) & 7) < 2) {
+			if (n1 < -14 && n1 < 10000) {
+				if (((-n1) & 7) == 7) give = 1;
+				else if (((-n1) & 7) < 2 && j < g.jmax && P[a + 2] <= 0) give = 1;
+			}
+		}
+	}
+	return v;
+}
+// j in [j0, j1]: column j1 is outside the region (it has no turn) but still receives from the last cell of the row
+NHW_HD int e20_final_cell(const int16_t *P, const E20Pass &g, int r, int j)
+{
+	int start = j;
+	while (start > g.j0 && e20_can_receive(P[r * YW + start])) start--;
+	// `start` receives nothing (it cannot, or it is the first cell of the row): replay start .. j
+	int give = 0, v = 0;
+	for (int x = start; x <= j; x++) {
+		int in = P[r * YW + x];
+		if (give == 100) in = -8;
+		else in += give;
+		if (x == g.j1) return in;
+		v = e20_turn(P, g, r, x, in, give);
+	}
+	return v;
+}
+
 NHW_HDN void y_e20_cleanup_image(const EncImg &im, int q, int ratio)
 {
 	int16_t *P = im.proc;

@@ -457,6 +457,37 @@ __global__ void __launch_bounds__(256) k_e6d_correct(EncBatch b)
 	}
 }
 
+// ---- E20: clean-up of the three level-1 bands, cell-parallel (enc_y2.cuh: e20_final_cell).  Finals are computed
+// from the plane as it is (read only) into the scratch plane, a second launch copies them back.
+// blockIdx.x enumerates (pass, row): 254 rows of pass 0, then 255 of pass 1, then 255 of pass 2.
+__device__ __forceinline__ bool e20_block(int bx, int q, int ratio, E20Pass &g, int &r)
+{
+	int pass = bx < 254 ? 0 : bx < 509 ? 1 : 2;
+	g = e20_pass(q, ratio, pass);
+	r = g.r0 + (pass == 0 ? bx : pass == 1 ? bx - 254 : bx - 509);
+	return r < g.r1;
+}
+__global__ void __launch_bounds__(256) k_e20_cells(EncBatch b, int q, int ratio)
+{
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	E20Pass g;
+	int r;
+	if (!e20_block(blockIdx.x, q, ratio, g, r)) return;
+	const int j = g.j0 + threadIdx.x;
+	if (j > g.j1) return;
+	im.aux[r * YW + j] = (int16_t)e20_final_cell(im.proc, g, r, j);
+}
+__global__ void __launch_bounds__(256) k_e20_commit(EncBatch b, int q, int ratio)
+{
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	E20Pass g;
+	int r;
+	if (!e20_block(blockIdx.x, q, ratio, g, r)) return;
+	const int j = g.j0 + threadIdx.x;
+	if (j > g.j1) return;
+	im.proc[r * YW + j] = im.aux[r * YW + j];
+}
+
 // ---- E19: restore the level-2 region from the resIII snapshot (y_e19_restore_row), one thread per cell pair
 __global__ void __launch_bounds__(128) k_e19_restore(EncBatch b)
 {
@@ -1119,9 +1150,8 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
 	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(256, n), 128, 0, b);
-	for (int pass = 0; pass < 3; pass++)
-		run_wavefront(c, "y_e20_cleanup", b, n, wf_e20_geom(pass),
-		              [=] __device__(const EncImg &im, int r, int j) { return wf_e20_cell(im, q, ratio, pass, r, j); });
+	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_cells, dim3(764, n), 256, 0, b, q, ratio);
+	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_commit, dim3(764, n), 256, 0, b, q, ratio);
 	run_rows(c, "y_offset_mult8", b, n, 512, [=] __device__(const EncImg &im, int r) { y_offset_mult8_row(im, r); });
 	run_wavefront(c, "y_offset_patterns", b, n, wf_offset_patterns_geom(),
 	              [=] __device__(const EncImg &im, int r, int j) { return wf_offset_patterns_cell(im, r, j); });

@@ -537,8 +537,18 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	if (q >= 21) y_e18_pack_list_image(im, 5);
 	T("y_e18_ll1", im.ll1, 65536 * 2);
 	for (int r = 255; r >= 0; r--) y_e19_restore_row(im, r);
-	for (int pass = 0; pass < 3; pass++)
-		host_wavefront(wf_e20_geom(pass), [&](int r, int j) { return wf_e20_cell(im, q, ratio, pass, r, j); });
+	if (getenv("HE_WAVEFRONT")) {
+		for (int pass = 0; pass < 3; pass++)
+			host_wavefront(wf_e20_geom(pass), [&](int r, int j) { return wf_e20_cell(im, q, ratio, pass, r, j); });
+	} else {   // cell-parallel form: every final value from the plane as it was before the stage
+		std::vector<int16_t> before(im.proc - 4096, im.proc + 512 * 512 + 4096);
+		const int16_t *B = before.data() + 4096;
+		for (int pass = 2; pass >= 0; pass--) {
+			const E20Pass g = e20_pass(q, ratio, pass);
+			for (int r = g.r1 - 1; r >= g.r0; r--)
+				for (int j = g.j1; j >= g.j0; j--) im.proc[r * 512 + j] = (int16_t)e20_final_cell(B, g, r, j);
+		}
+	}
 	T("y_e20_proc", im.proc, 512 * 512 * 2);
 	for (int r = 511; r >= 0; r--) y_offset_mult8_row(im, r);
 	host_wavefront(wf_offset_patterns_geom(), [&](int r, int j) { return wf_offset_patterns_cell(im, r, j); });
