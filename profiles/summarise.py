@@ -35,13 +35,13 @@ if os.path.exists(launches):
         a[1] += ns
     total = sum(v[1] for v in agg.values())
     out.append("## Launch list (ncu --metrics gpu__time_duration.sum --clock-control none), %d launches, %.2f ms total\n" % (len(rows), total / 1e6))
-    out.append("bench.py --batch 256 --steps 1 --warmup 3 (4 device-API steps + 2 host-API steps + synth). Cold-cache, serialised: compare shares.\n")
+    out.append("bench.py --batch 256 --steps 1 --warmup 3 (device-API steps, one profiled pass, host-API encode and decode steps, synth). Cold-cache, serialised: compare shares.\n")
     out.append("| kernel block x grid | launches | total ms | share |\n|---|---|---|---|")
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append("| `%s` | %d | %.3f | %.1f%% |" % (k, n, ns / 1e6, 100 * ns / total))
     out.append("")
 
-WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
