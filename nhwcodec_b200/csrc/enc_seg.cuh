@@ -18,7 +18,8 @@
 // instead of byte by byte: the streams are mostly zeros and a run of a thousand zeros is 32 words.
 struct NzBits {
 	const uint32_t *w;      // bit k of word j describes stream byte p1 + 32*j + k
-	int p1, n;              // first stream position covered, number of bits (multiple of 32)
+	int p1, n;              // first stream position covered, number of bits (multiple of 1024)
+	const uint32_t *sum;    // second level: bit k of word j = "w[32*j + k] != 0" (n / 1024 words), or NULL
 };
 
 NHW_HD int nhw_ctz(uint32_t m)
@@ -53,6 +54,19 @@ NHW_HD int nz_next(const NzBits &b, int i, int end)
 	if (k >= b.n) return end;
 	int wi = k >> 5;
 	uint32_t m = b.w[wi] & (0xffffffffu << (k & 31));
+	if (!m && b.sum) {
+		// hop over all-zero words through the summary level
+		if (++wi >= nw) return end;
+		int si = wi >> 5;
+		const int ns = nw >> 5;
+		uint32_t ms = b.sum[si] & (0xffffffffu << (wi & 31));
+		while (!ms) {
+			if (++si >= ns) return end;
+			ms = b.sum[si];
+		}
+		wi = (si << 5) + nhw_ctz(ms);
+		m = b.w[wi];
+	}
 	while (!m) {
 		if (++wi >= nw) return end;
 		m = b.w[wi];
@@ -68,6 +82,17 @@ NHW_HD int nz_prev(const NzBits &b, int i)
 	if (k < 0) return b.p1 - 1;
 	int wi = k >> 5;
 	uint32_t m = b.w[wi] & (0xffffffffu >> (31 - (k & 31)));
+	if (!m && b.sum) {
+		if (--wi < 0) return b.p1 - 1;
+		int si = wi >> 5;
+		uint32_t ms = b.sum[si] & (0xffffffffu >> (31 - (wi & 31)));
+		while (!ms) {
+			if (--si < 0) return b.p1 - 1;
+			ms = b.sum[si];
+		}
+		wi = (si << 5) + 31 - nhw_clz(ms);
+		m = b.w[wi];
+	}
 	while (!m) {
 		if (--wi < 0) return b.p1 - 1;
 		m = b.w[wi];

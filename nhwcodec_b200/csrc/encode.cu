@@ -681,12 +681,19 @@ __global__ void __launch_bounds__(256) k_hq_lists(EncBatch b, int q)
 // ---- peephole passes over the luma scan, one CTA per image (enc_seg.cuh)
 #define PEEP_THREADS 512
 // non-zero bitmap of `count` stream bytes starting at s (16-byte aligned, count % 32 == 0) into shared memory
-__device__ __forceinline__ void build_nz_bitmap(const uint8_t *s, int count, uint32_t *bits, int tid, int nthreads)
+// (count % 1024 == 0; `sum` = the second level, count / 1024 words, needs a barrier of its own: callers sync after)
+__device__ __forceinline__ void build_nz_bitmap(const uint8_t *s, int count, uint32_t *bits, uint32_t *sum, int tid, int nthreads)
 {
 	for (int w = tid; w < count / 32; w += nthreads) {
 		const uint4 a = reinterpret_cast<const uint4 *>(s)[2 * w], b = reinterpret_cast<const uint4 *>(s)[2 * w + 1];
 		bits[w] = nz_mask4(a.x) | (nz_mask4(a.y) << 4) | (nz_mask4(a.z) << 8) | (nz_mask4(a.w) << 12) | (nz_mask4(b.x) << 16) |
 		          (nz_mask4(b.y) << 20) | (nz_mask4(b.z) << 24) | (nz_mask4(b.w) << 28);
+	}
+	__syncthreads();
+	for (int j = tid; j < count / 1024; j += nthreads) {
+		uint32_t m = 0;
+		for (int k = 0; k < 32; k++) m |= (bits[32 * j + k] != 0 ? 1u : 0u) << k;
+		sum[j] = m;
 	}
 }
 
@@ -713,9 +720,10 @@ __global__ void __launch_bounds__(PEEP_THREADS) k_peephole(EncBatch b)
 	__syncthreads();
 	if (threadIdx.x < 4) { s[threadIdx.x] = 128; s[N - 4 + threadIdx.x] = 128; }
 	__syncthreads();
-	build_nz_bitmap(s, N, nzbits, threadIdx.x, PEEP_THREADS);
+	__shared__ uint32_t nzsum[256];
+	build_nz_bitmap(s, N, nzbits, nzsum, threadIdx.x, PEEP_THREADS);
 	__syncthreads();
-	const NzBits nz{nzbits, 0, N};
+	const NzBits nz{nzbits, 0, N, nzsum};
 	// passes B + C: every output byte from the pass-A stream
 	int a1 = 0, a2 = 0;
 	for (int i = threadIdx.x; i < N; i += PEEP_THREADS) {
@@ -749,6 +757,7 @@ __device__ __forceinline__ void block_excl_scan3(int *a, int *b, int *c, int t) 
 __global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
 {
 	extern __shared__ __align__(16) uint32_t nzbits[];   // 262144 bits (luma part), reused for the chroma part
+	__shared__ uint32_t nzsum[256];
 	__shared__ int hist_sym[256], hist_run[256];
 	__shared__ int sbits[SEG_THREADS + 1], sn1[SEG_THREADS + 1], sn2[SEG_THREADS + 1];
 	__shared__ uint32_t s_weight[354];
@@ -771,9 +780,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
 		hist_sym[t] = 0;
 		hist_run[t] = 0;
 		__syncthreads();
-		build_nz_bitmap(s + p1, p2 - p1, nzbits, t, SEG_THREADS);
+		build_nz_bitmap(s + p1, p2 - p1, nzbits, nzsum, t, SEG_THREADS);
 		__syncthreads();
-		SegStream ss{s, p1, p2, S, NzBits{nzbits, p1, p2 - p1}};
+		SegStream ss{s, p1, p2, S, NzBits{nzbits, p1, p2 - p1, nzsum}};
 		seg_stats(ss, t, [&](bool run, int idx) { atomicAdd(run ? &hist_run[idx] : &hist_sym[idx], 1); });
 		__syncthreads();
 		st.rle_buf[t] = hist_sym[t];

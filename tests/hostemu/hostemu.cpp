@@ -168,7 +168,7 @@ void host_peephole(const EncImg &im)
 		uint32_t w; memcpy(&w, s + i, 4);
 		if (nz_mask4(w) != ((bits[i >> 5] >> (i & 31)) & 15u)) abort();
 	}
-	const NzBits nz{bits.data(), 0, N};
+	const NzBits nz{bits.data(), 0, N, nullptr};
 	int sel1 = 0, sel2 = 0;
 	for (int i = N - 1; i >= 0; i--) {
 		int a, b;
@@ -193,7 +193,9 @@ int host_entropy(const EncImg &im, int part, int &word0)
 	const int S = (p2 - p1) / SEG_THREADS;
 	std::vector<uint32_t> nzb((p2 - p1) / 32, 0);
 	for (int i = p1; i < p2; i++) if (s[i] != 128) nzb[(i - p1) >> 5] |= 1u << ((i - p1) & 31);
-	SegStream ss{s, p1, p2, S, NzBits{nzb.data(), p1, p2 - p1}};
+	std::vector<uint32_t> nzs((p2 - p1) / 1024, 0);
+	for (size_t j = 0; j < nzs.size(); j++) for (int k = 0; k < 32; k++) if (nzb[32 * j + k]) nzs[j] |= 1u << k;
+	SegStream ss{s, p1, p2, S, NzBits{nzb.data(), p1, p2 - p1, nzs.data()}};
 	for (int i = 0; i < 256; i++) { st.rle_buf[i] = 0; st.rle_128[i] = 0; }
 	for (int t = SEG_THREADS - 1; t >= 0; t--)
 		seg_stats(ss, t, [&](bool run, int idx) { if (run) st.rle_128[idx]++; else st.rle_buf[idx]++; });
