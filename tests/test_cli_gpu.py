@@ -41,6 +41,30 @@ def test_cli_known_answer(smooth_bmp, exe, tmp_path):
     assert r3.returncode == 0
 
 
+@pytest.mark.parametrize("exe", ["cli/nhw-enc", "oracle/_ref/nhw-enc-dropin"])
+@pytest.mark.parametrize("q", [17, 23])
+def test_cli_other_qualities(smooth_bmp, exe, q, tmp_path):
+    """-q17 (scaled colour path, no res3/res5) and -q23 (res6 / char_res1 / high_qsetting3 sections) through both
+    CLIs, then back through both decoder CLIs: SURVEY.md Appendix E hashes"""
+    from test_oracle_cpu import KAT
+    path = os.path.join(ROOT, exe)
+    if not os.path.exists(path):
+        pytest.skip(exe + " not built")
+    out = str(tmp_path / "out.nhw")
+    r = subprocess.run([path, "-q%d" % q, smooth_bmp, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    data = open(out, "rb").read()
+    assert (len(data), hashlib.md5(data).hexdigest()) == (KAT[q][0], KAT[q][1])
+    for dec in ("cli/nhw-dec", "oracle/_ref/nhw-dec-dropin"):
+        dpath = os.path.join(ROOT, dec)
+        if not os.path.exists(dpath):
+            continue
+        bmp = str(tmp_path / "back.bmp")
+        r = subprocess.run([dpath, out, bmp], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert hashlib.md5(open(bmp, "rb").read()).hexdigest() == KAT[q][2], dec
+
+
 def test_cli_rejects_bad_input(tmp_path):
     import torch
     if not torch.cuda.is_available():
