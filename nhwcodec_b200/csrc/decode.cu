@@ -318,6 +318,33 @@ __global__ void __launch_bounds__(256) kd_hq_addbacks(DecBatch b)
 	}
 }
 
+// ---- D2: inverse scans as gathers.  Luma: cell (row, col) = coef[y_scan_pos(row, col)] (enc_point.cuh); one
+// thread per 4 cells = one 8-byte run of the scan.  Chroma: one thread per (row, 8-column strip) = 16 interleaved
+// coefficients of which this plane takes every other one.
+__global__ void __launch_bounds__(128) kd_descan_y(DecBatch b)
+{
+	if (b.status[blockIdx.y] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.y, 0);
+	const int row = blockIdx.x, strip = threadIdx.x;
+	const uint2 v = *reinterpret_cast<const uint2 *>(im.proc + strip * 2048 + (row >> 1) * 8 + (row & 1) * 4);
+	uint2 o = v;
+	if (row & 1) {   // second row of a step is stored reversed
+		o.x = (v.y >> 16) | (v.y << 16);
+		o.y = (v.x >> 16) | (v.x << 16);
+	}
+	*reinterpret_cast<uint2 *>(im.jpeg + row * YW + strip * 4) = o;
+}
+__global__ void __launch_bounds__(64) kd_descan_uv(DecBatch b)
+{
+	const int img = blockIdx.y;
+	if (b.status[img] != 0) return;
+	const int row = blockIdx.x, strip = threadIdx.x & 31, v = threadIdx.x >> 5;
+	const DecImg im = make_dec(b, img, v);
+	const int16_t *s = im.uvcoef + v + strip * 4096 + (row >> 1) * 32 + (row & 1) * 16;
+	int16_t *dst = im.cjpeg + row * CW + strip * 8;
+	for (int t = 0; t < 8; t++) dst[(row & 1) ? 7 - t : t] = s[2 * t];
+}
+
 // ---- D12: flagged positions in raster order, flags removed (nhw_decoder.c:827-839); thread = row
 __global__ void __launch_bounds__(256) kd_edge_compact(DecBatch b)
 {
@@ -453,7 +480,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 
 	// ---- luma
 	NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + 31) / 32, dim3(32, 4), 0, b, n);
-	d_rows(c, "d_descan_y", b, n, 128, [=] __device__(const DecImg &im, int s) { dec_y_descan_strip(im.proc, im.jpeg, s); });
+	NHW_LAUNCH_L(c, "d_descan_y", kd_descan_y, dim3(512, n), 128, 0, b);
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
 	d_wavefront(c, "d_shrink_y", b, n, 1, dwf_shrink_geom(), [=] __device__(const DecImg &im, int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
@@ -470,7 +497,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH(c, kd_clip_y, dim3(262144 / 256, n), 256, 0, b);
 
 	// ---- chroma
-	d_plane_rows(c, "d_descan_uv", b, n, 32, [=] __device__(const DecImg &im, int s, int v) { dec_c_descan_strip(im.uvcoef, im.cjpeg, s, v); });
+	NHW_LAUNCH_L(c, "d_descan_uv", kd_descan_uv, dim3(256, n), 64, 0, b);
 	d_image(c, "d_ll_uv", b, n, [=] __device__(const DecImg &im0, int i) {
 		int exw = im0.list_len[10];
 		for (int v = 0; v < 2; v++) {

@@ -90,18 +90,42 @@ __global__ void k_plane(EncBatch b, int n2, F f)   // thread per chroma plane (2
 	if (p < n2) f(make_img(b, p >> 1, p & 1), p & 1);
 }
 
+// "thread = row" stages walk rows that lie 512 B or 1 KB apart, so every load of a warp touches 32 lines and the
+// rest of each line is only used if it is still in L1 when the thread gets there.  The grid is therefore kept at
+// ROWS_CTAS_PER_SM resident CTAs per SM (persistent, looping over the work) so that the lines a warp has in
+// flight stay in L1 instead of being evicted by thousands of other row walkers.
+#define ROWS_CTAS_PER_SM 24
 template <typename F>
-__global__ void k_rows(EncBatch b, int rows, F f)   // grid (ceil(rows/64), n)
+__global__ void __launch_bounds__(64) k_rows(EncBatch b, int rows, int n, F f)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r < rows) f(make_img(b, blockIdx.y, 0), r);
+	const int nblk = (rows + 63) >> 6;
+	for (int item = blockIdx.x; item < n * nblk; item += gridDim.x) {
+		const int img = item / nblk, r = (item % nblk) * 64 + threadIdx.x;
+		if (r < rows) f(make_img(b, img, 0), r);
+	}
 }
 
 template <typename F>
-__global__ void k_plane_rows(EncBatch b, int rows, F f)   // grid (ceil(rows/64), 2n)
+__global__ void __launch_bounds__(64) k_plane_rows(EncBatch b, int rows, int n2, F f)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r < rows) f(make_img(b, blockIdx.y >> 1, blockIdx.y & 1), r, blockIdx.y & 1);
+	const int nblk = (rows + 63) >> 6;
+	for (int item = blockIdx.x; item < n2 * nblk; item += gridDim.x) {
+		const int pl = item / nblk, r = (item % nblk) * 64 + threadIdx.x;
+		if (r < rows) f(make_img(b, pl >> 1, pl & 1), r, pl & 1);
+	}
+}
+
+static int rows_grid_cap()
+{
+	static int cap = 0;
+	if (!cap) {
+		int dev = 0, sms = 148;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		const char *e = getenv("NHW_ROWS_CTAS_PER_SM");
+		cap = sms * (e ? atoi(e) : ROWS_CTAS_PER_SM);
+	}
+	return cap;
 }
 
 template <typename F>
@@ -117,12 +141,14 @@ void run_plane(nhw_ctx *c, const char *label, const EncBatch &b, int n, F f)
 template <typename F>
 void run_rows(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, F f)
 {
-	NHW_LAUNCH_L(c, label, k_rows, dim3((rows + 63) / 64, n), 64, 0, b, rows, f);
+	const int work = ((rows + 63) / 64) * n, cap = rows_grid_cap();
+	NHW_LAUNCH_L(c, label, k_rows, work < cap ? work : cap, 64, 0, b, rows, n, f);
 }
 template <typename F>
 void run_plane_rows(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, F f)
 {
-	NHW_LAUNCH_L(c, label, k_plane_rows, dim3((rows + 63) / 64, 2 * n), 64, 0, b, rows, f);
+	const int work = ((rows + 63) / 64) * 2 * n, cap = rows_grid_cap();
+	NHW_LAUNCH_L(c, label, k_plane_rows, work < cap ? work : cap, 64, 0, b, rows, 2 * n, f);
 }
 
 // ---- wavefront executor: one CTA per image, thread = row of the stage's region; see enc_par.cuh
