@@ -186,7 +186,7 @@ def run_reference(args):
     cores = host_cores()
     distinct = 8
     images = np.stack([synth.natural(1000 + i) for i in range(distinct)])
-    per_step = max(2 * cores, 8)
+    per_step = 16 * cores      # ~0.5 s of CPU work per step: long enough that thread start-up does not matter
     from oracle import refbind
     L = refbind.enc_stock_lib()
 
