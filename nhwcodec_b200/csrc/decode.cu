@@ -91,14 +91,20 @@ __global__ void __launch_bounds__(32) kd_image_lut(DecBatch b, int n, F f)
 }
 // ---- the decoder's serial front: four independent single-thread jobs per image run side by side
 // (threadIdx.y = job) instead of one after the other: luma prefix decode, chroma prefix decode, LL byte
-// DPCM, side-channel list expansion.  32 images per CTA; the prefix-code table is staged in shared memory.
-__global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n)
+// DPCM, side-channel list expansion.  The jobs are branchy bit-serial parsers: lanes of a warp working on
+// different streams diverge at almost every step and the warp pays for every path taken, so a warp only
+// carries DSF_STREAMS streams (one active lane in every 32 / DSF_STREAMS); the many more warps this makes
+// also hide each other's latency.  The prefix-code table is staged in shared memory.
+#define DSF_STREAMS 4
+__global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n, int spw)
 {
 	__shared__ __align__(16) uint16_t slut[NHW_LUT_WORDS];
 	const int tid = threadIdx.y * 32 + threadIdx.x;
 	for (int k = tid; k < NHW_LUT_WORDS / 8; k += 128) reinterpret_cast<uint4 *>(slut)[k] = reinterpret_cast<const uint4 *>(b.lut)[k];
 	__syncthreads();
-	const int i = blockIdx.x * 32 + threadIdx.x, job = threadIdx.y;
+	const int group = 32 / spw;
+	if (threadIdx.x % group) return;
+	const int i = blockIdx.x * spw + threadIdx.x / group, job = threadIdx.y;
 	if (i >= n || b.status[i] != 0) return;
 	DecImg im = make_dec(b, i, 0);
 	im.lut = slut;
@@ -479,7 +485,11 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH(c, kd_zero, dim3(131072 * 2 / 16 / 256, n), 256, 0, b.uvcoef, YS, (size_t)(131072 * 2 / 16));
 
 	// ---- luma
-	NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + 31) / 32, dim3(32, 4), 0, b, n);
+	{
+		const char *e = getenv("NHW_DSF_STREAMS");
+		const int spw = e ? atoi(e) : DSF_STREAMS;
+		NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + spw - 1) / spw, dim3(32, 4), 0, b, n, spw);
+	}
 	NHW_LAUNCH_L(c, "d_descan_y", kd_descan_y, dim3(512, n), 128, 0, b);
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
