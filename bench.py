@@ -434,8 +434,8 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": B * PIX_BYTES,
                     "d2h_bytes_per_step": d2h + 8 * (B + 1) + 4 * B, "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "kernel_table": "per-kernel ms from a separate serialised pass (CUDA events around every launch); the timed "
-                            "region runs %d sub-chunks side by side" % 4,
+            "kernel_table": "per-kernel ms from a separate serialised pass (CUDA events around every launch); in the timed "
+                            "regions the host-buffer calls run 4 (encode) / 8 (decode) sub-chunks on 4 streams",
             "clocks": clocks,
             "roofline": roofline,
             "frontend": frontend,

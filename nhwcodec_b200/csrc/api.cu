@@ -136,6 +136,8 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 		ok = ok && check(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming), "cudaEventCreate");
 	}
 	ok = ok && check(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+	ok = ok && check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	for (int k = 0; k < NHW_MAX_SUB && ok; k++) ok = ok && check(cudaEventCreateWithFlags(&c->ev_sub[k], cudaEventDisableTiming), "cudaEventCreate");
 
 	c->stream = c->lanes[0];
 	// every workspace array is zero-filled once: guard bands and never-written borders must
@@ -151,11 +153,11 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	ok = ok && dev_alloc0(&c->rowmap, B * 512) && dev_alloc0(&c->rowcarry, B * 512);
 	ok = ok && dev_alloc0(&c->enc_bytes, B * (size_t)ENC_BYTES_SLOT) && dev_alloc0(&c->enc_hdr, B);
 	ok = ok && dev_alloc0(&c->out_dev, B * (size_t)NHW_MAX_STREAM_BYTES) && dev_alloc0(&c->pack_dev, B * (size_t)NHW_MAX_STREAM_BYTES);
-	ok = ok && dev_alloc0(&c->len_dev, B) && dev_alloc0(&c->status_dev, B) && dev_alloc0(&c->offs_dev, B + 1 + NHW_LANES);
+	ok = ok && dev_alloc0(&c->len_dev, B) && dev_alloc0(&c->status_dev, B) && dev_alloc0(&c->offs_dev, B + 1 + NHW_MAX_SUB);
 	ok = ok && dev_alloc0(&c->dec_yuv, B * (size_t)NHW_RGB_BYTES);
 	ok = ok && check(cudaMalloc(&c->dec_desc_dev, B * sizeof(DecDesc)), "cudaMalloc");
 	ok = ok && check(cudaMallocHost(&c->dec_desc_host, B * sizeof(DecDesc)), "cudaMallocHost");
-	ok = ok && check(cudaMallocHost((void **)&c->offs_host, (B + 1 + NHW_LANES) * sizeof(uint64_t)), "cudaMallocHost");
+	ok = ok && check(cudaMallocHost((void **)&c->offs_host, (B + 1 + NHW_MAX_SUB) * sizeof(uint64_t)), "cudaMallocHost");
 	ok = ok && check(cudaMallocHost((void **)&c->status_host, B * sizeof(int32_t)), "cudaMallocHost");
 	if (!ok || !check(cudaDeviceSynchronize(), "nhw_create sync")) { nhw_destroy(c); return NHW_ERR_CUDA; }
 	*out = c;
@@ -181,6 +183,8 @@ void nhw_destroy(nhw_ctx *c)
 		if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
 	}
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	for (int k = 0; k < NHW_MAX_SUB; k++) if (c->ev_sub[k]) cudaEventDestroy(c->ev_sub[k]);
 
 	if (c->prof) {
 		nhw::ProfState *p = static_cast<nhw::ProfState *>(c->prof);
@@ -274,38 +278,42 @@ static int finish(nhw_ctx *c, const char *what)
 
 // ---- lanes: sub-chunks side by side on their own streams and workspace slices --------------------
 struct LanePlan {
-	int lanes;           // sub-chunks in this wave
-	int slot;            // workspace images per lane
-	int first[NHW_LANES + 1];   // image range of each lane inside the wave
+	int count;           // images this wave takes (<= subs * slot <= max_batch)
+	int subs;            // sub-chunks in this wave (each on its own workspace slice)
+	int streams;         // streams they are dealt to, round robin
+	int slot;            // workspace images per sub-chunk
+	int first[NHW_MAX_SUB + 1];   // image range of each sub-chunk inside the wave
 };
 
-// Split the next `m` images (m <= max_batch) over the lanes.  Per-kernel profiling and the debug stop are
-// defined on one stream, so they run single-lane.
-static int env_lanes(const char *name, int dflt)
+static int env_int(const char *name, int dflt, int lo, int hi)
 {
 	const char *e = getenv(name);
 	const int v = e ? atoi(e) : dflt;
-	return v < 1 ? 1 : v > NHW_LANES ? NHW_LANES : v;
+	return v < lo ? lo : v > hi ? hi : v;
 }
 
-static LanePlan plan_lanes(const nhw_ctx *c, int m, int max_lanes)
+// Split the next `m` images (m <= max_batch) into sub-chunks.  Per-kernel profiling and the debug stop are
+// defined on one stream, so they run as one sub-chunk.
+static LanePlan plan_lanes(const nhw_ctx *c, int m, int want_subs, int want_streams)
 {
 	LanePlan p;
-	const int want = (c->profile || c->dbg_label[0] || c->max_batch < 2 * NHW_LANES) ? 1 : max_lanes;
-	p.slot = want == 1 ? c->max_batch : c->max_batch / want;
-	int lanes = want;
-	if (lanes > 1 && m < 2 * lanes) lanes = m >= 2 ? 2 : 1;
-	if (lanes == 1) p.slot = c->max_batch;
-	p.lanes = lanes;
-	for (int l = 0; l <= lanes; l++) p.first[l] = (int)((long long)m * l / lanes);
+	int subs = (c->profile || c->dbg_label[0] || c->max_batch < 2 * NHW_MAX_SUB) ? 1 : want_subs;
+	if (subs > 1 && m < 2 * subs) subs = m >= 2 ? 2 : 1;
+	p.slot = c->max_batch / subs;
+	if (m > subs * p.slot) m = subs * p.slot;      // max_batch not a multiple of subs: the rest goes to the next wave
+	p.count = m;
+	p.subs = subs;
+	p.streams = want_streams < subs ? want_streams : subs;
+	for (int k = 0; k <= subs; k++) p.first[k] = (int)((long long)m * k / subs);   // consecutive differences <= ceil(m / subs) <= slot
 	return p;
 }
 
 // A shallow copy of the context whose stream is lane l's and whose workspace pointers start at image `slot0`.
-static nhw_ctx lane_view(const nhw_ctx *c, int l, int slot0)
+static nhw_ctx lane_view(const nhw_ctx *c, int l, int slot0, int sub = -1)
 {
 	nhw_ctx v = *c;
 	const size_t s = (size_t)slot0;
+	if (sub < 0) sub = l;
 	v.stream = c->lanes[l];
 	v.launches = 0;
 	v.rgb += s * NHW_RGB_BYTES;
@@ -317,7 +325,7 @@ static nhw_ctx lane_view(const nhw_ctx *c, int l, int slot0)
 	v.rowmap += s * 512; v.rowcarry += s * 512;
 	v.enc_bytes += s * (size_t)ENC_BYTES_SLOT; v.enc_hdr += s;
 	v.out_dev += s * (size_t)NHW_MAX_STREAM_BYTES; v.pack_dev += s * (size_t)NHW_MAX_STREAM_BYTES;
-	v.len_dev += s; v.status_dev += s; v.offs_dev += s + l; v.offs_host += s + l; v.status_host += s;
+	v.len_dev += s; v.status_dev += s; v.offs_dev += s + sub; v.offs_host += s + sub; v.status_host += s;
 	v.dec_yuv += s * (size_t)NHW_RGB_BYTES;
 	v.dec_desc_dev = static_cast<DecDesc *>(c->dec_desc_dev) + s;
 	v.dec_desc_host = static_cast<DecDesc *>(c->dec_desc_host) + s;
@@ -401,12 +409,13 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
 	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q23 are)", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
-	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
-		const int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
+	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
 		// device-resident input: the kernels of one chunk already fill the GPU and share L2 better on one stream
-		const LanePlan p = plan_lanes(c, m, env_lanes("NHW_LANES_DEVICE", 1));
-		lanes_fork(c, p.lanes);
-		for (int l = 0; l < p.lanes; l++) {
+		const int dl = env_int("NHW_LANES_DEVICE", 1, 1, NHW_LANES);
+		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, dl, dl);
+		step = p.count;
+		lanes_fork(c, p.streams);
+		for (int l = 0; l < p.subs; l++) {
 			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
 			if (cnt <= 0) continue;
 			nhw_ctx v = lane_view(c, l, l * p.slot);
@@ -414,7 +423,7 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
 			                  len_dev ? len_dev + a : nullptr, status_dev ? status_dev + a : nullptr);
 			lane_done(c, v);
 		}
-		lanes_join(c, p.lanes);
+		lanes_join(c, p.streams);
 	}
 	return finish(c, "nhw_encode_batch_device");
 }
@@ -425,41 +434,45 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 	if (!c || !rgb || !out || !offsets || n <= 0) return NHW_ERR_ARG;
 	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q23 are)", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
-	// Waves of up to NHW_LANES sub-chunks: each lane uploads its pixels, encodes and packs on its own stream, so
-	// the uploads of some lanes overlap the kernels of others; the streams' bytes come back in image order.
+	// Waves of sub-chunks dealt round robin to a few streams: a sub-chunk uploads its pixels, encodes and packs
+	// on its stream, so uploads overlap the kernels of the other streams; finished sub-chunks come back on the
+	// copy stream, in image order.
 	uint64_t pos = 0;
 	offsets[0] = 0;
-	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
-		const int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
-		const LanePlan p = plan_lanes(c, m, env_lanes("NHW_LANES_ENCODE", NHW_LANES));
-		nhw_ctx v[NHW_LANES];
-		lanes_fork(c, p.lanes);
-		for (int l = 0; l < p.lanes; l++) {
-			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
-			v[l] = lane_view(c, l, l * p.slot);
+	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
+		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, env_int("NHW_SUBS_ENCODE", 4, 1, NHW_MAX_SUB),
+		                              env_int("NHW_LANES_ENCODE", 4, 1, NHW_LANES));
+		step = p.count;
+		nhw_ctx v[NHW_MAX_SUB];
+		lanes_fork(c, p.streams);
+		for (int k = 0; k < p.subs; k++) {
+			const int a = i0 + p.first[k], cnt = p.first[k + 1] - p.first[k];
+			v[k] = lane_view(c, k % p.streams, k * p.slot, k);
 			if (cnt <= 0) continue;
-			if (!check(cudaMemcpyAsync(v[l].rgb, rgb + (size_t)a * NHW_RGB_BYTES, (size_t)cnt * NHW_RGB_BYTES,
-			                           cudaMemcpyHostToDevice, v[l].stream), "H2D pixels")) return NHW_ERR_CUDA;
-			nhw::encode_chunk(&v[l], v[l].rgb, cnt, quality, v[l].out_dev, v[l].len_dev, v[l].status_dev);
-			nhw::pack_streams(&v[l], cnt);
-			cudaMemcpyAsync(v[l].offs_host, v[l].offs_dev, (size_t)(cnt + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, v[l].stream);
-			cudaMemcpyAsync(v[l].status_host, v[l].status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v[l].stream);
-			lane_done(c, v[l]);
+			if (!check(cudaMemcpyAsync(v[k].rgb, rgb + (size_t)a * NHW_RGB_BYTES, (size_t)cnt * NHW_RGB_BYTES,
+			                           cudaMemcpyHostToDevice, v[k].stream), "H2D pixels")) return NHW_ERR_CUDA;
+			nhw::encode_chunk(&v[k], v[k].rgb, cnt, quality, v[k].out_dev, v[k].len_dev, v[k].status_dev);
+			nhw::pack_streams(&v[k], cnt);
+			cudaMemcpyAsync(v[k].offs_host, v[k].offs_dev, (size_t)(cnt + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, v[k].stream);
+			cudaMemcpyAsync(v[k].status_host, v[k].status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v[k].stream);
+			cudaEventRecord(c->ev_sub[k], v[k].stream);
+			lane_done(c, v[k]);
 		}
-		for (int l = 0; l < p.lanes; l++) {
-			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
+		for (int k = 0; k < p.subs; k++) {
+			const int a = i0 + p.first[k], cnt = p.first[k + 1] - p.first[k];
 			if (cnt <= 0) continue;
-			if (!check(cudaGetLastError(), "nhw_encode_batch") || !check(cudaStreamSynchronize(v[l].stream), "nhw_encode_batch")) return NHW_ERR_CUDA;
-			const uint64_t total = v[l].offs_host[cnt];
+			if (!check(cudaGetLastError(), "nhw_encode_batch") || !check(cudaEventSynchronize(c->ev_sub[k]), "nhw_encode_batch")) return NHW_ERR_CUDA;
+			const uint64_t total = v[k].offs_host[cnt];
 			if (pos + total > out_cap) { nhw::set_error("output buffer too small"); return NHW_ERR_ARG; }
-			if (total && !check(cudaMemcpyAsync(out + pos, v[l].pack_dev, total, cudaMemcpyDeviceToHost, v[l].stream), "D2H streams")) return NHW_ERR_CUDA;
+			if (total && !check(cudaMemcpyAsync(out + pos, v[k].pack_dev, total, cudaMemcpyDeviceToHost, c->copy_stream), "D2H streams")) return NHW_ERR_CUDA;
 			for (int i = 0; i < cnt; i++) {
-				offsets[a + i + 1] = pos + v[l].offs_host[i + 1];
-				if (status) status[a + i] = v[l].status_host[i];
+				offsets[a + i + 1] = pos + v[k].offs_host[i + 1];
+				if (status) status[a + i] = v[k].status_host[i];
 			}
 			pos += total;
 		}
-		for (int l = 0; l < p.lanes; l++)
+		if (!check(cudaStreamSynchronize(c->copy_stream), "nhw_encode_batch")) return NHW_ERR_CUDA;
+		for (int l = 0; l < p.streams; l++)
 			if (!check(cudaStreamSynchronize(c->lanes[l]), "nhw_encode_batch")) return NHW_ERR_CUDA;
 	}
 	return NHW_OK;
@@ -471,14 +484,15 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 	if (!c || !in || !offsets || (!rgb && !yuv) || n <= 0) return NHW_ERR_ARG;
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
-	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
-		const int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
-		const LanePlan p = plan_lanes(c, m, env_lanes("NHW_LANES_DECODE", NHW_LANES));
-		nhw_ctx v[NHW_LANES];
-		lanes_fork(c, p.lanes);
-		for (int l = 0; l < p.lanes; l++) {
+	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
+		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, env_int("NHW_SUBS_DECODE", 8, 1, NHW_MAX_SUB),
+		                              env_int("NHW_LANES_DECODE", 4, 1, NHW_LANES));
+		step = p.count;
+		nhw_ctx v[NHW_MAX_SUB];
+		lanes_fork(c, p.streams);
+		for (int l = 0; l < p.subs; l++) {
 			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
-			v[l] = lane_view(c, l, l * p.slot);
+			v[l] = lane_view(c, l % p.streams, l * p.slot, l);
 			if (cnt <= 0) continue;
 			nhw_ctx &w = v[l];
 			DecDesc *desc = static_cast<DecDesc *>(w.dec_desc_host);
@@ -503,9 +517,10 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 			cudaMemcpyAsync(w.status_host, w.status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, w.stream);
 			lane_done(c, w);
 		}
-		for (int l = 0; l < p.lanes; l++) {
-			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
+		for (int l = 0; l < p.streams; l++)
 			if (!check(cudaGetLastError(), "nhw_decode_batch") || !check(cudaStreamSynchronize(c->lanes[l]), "nhw_decode_batch")) return NHW_ERR_CUDA;
+		for (int l = 0; l < p.subs; l++) {
+			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
 			for (int i = 0; status && i < cnt; i++) status[a + i] = v[l].status_host[i];
 		}
 	}

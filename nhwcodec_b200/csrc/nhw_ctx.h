@@ -1,6 +1,7 @@
 // nhw_ctx.h -- host-side context of libnhw_cuda (internal; the public face is include/nhw_cuda.h)
 #pragma once
 #define NHW_LANES 4
+#define NHW_MAX_SUB 8
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -17,7 +18,8 @@ struct nhw_ctx {
 	// own slice of every workspace array (api.cu: lane_view): the many latency-bound stages of one sub-chunk
 	// overlap the others', and host<->device copies overlap kernels.
 	cudaStream_t lanes[4];
-	cudaEvent_t ev_fork, ev_join[4];
+	cudaStream_t copy_stream;   // device->host copies of finished sub-chunks
+	cudaEvent_t ev_fork, ev_join[4], ev_sub[8];
 	uint64_t launches;
 	char dbg_label[64];  // debug: stop issuing kernels after the dbg_count-th launch of this label
 	int dbg_count, dbg_seen, dbg_stopped;
