@@ -279,6 +279,24 @@ NHW_HD int y_e18_collect_row(const EncImg &im, int which, int row, uint8_t *pos,
 
 NHW_HDN void y_e18_finish_list_image(const EncImg &im, int which, int count, int e);
 
+// The three collection passes as one function of the cell's value before the stage: list 1 rewrites some of
+// its codes into codes of lists 3 and 5, which then collect them (q >= 19 / q >= 21).  member bit k = the cell is
+// an entry of list 1 / 3 / 5 (k = 0 / 1 / 2), w[k] its word value; returns the cell's value after all passes.
+NHW_HD int y_e18_classify(int v, int q, int &member, int (&w)[3])
+{
+	member = 0;
+	w[0] = w[1] = w[2] = 0;
+	if (v == 141) { member |= 1; w[0] = 1; v = 0; }
+	else if (v == 140) { member |= 1; w[0] = 0; v = 0; }
+	else if (v == 126) { member |= 1; w[0] = 0; v = 122; }
+	else if (v == 125) { member |= 1; w[0] = 1; v = 121; }
+	else if (v == 148) { member |= 1; w[0] = 1; v = 144; }
+	else if (v == 149) { member |= 1; w[0] = 0; v = 145; }
+	if (q >= 19 && v >= 121 && v <= 124) { member |= 2; w[1] = v == 121 ? 1 : v == 122 ? 0 : v == 123 ? 2 : 3; v = 0; }
+	if (q >= 21 && (v == 144 || v == 145)) { member |= 4; w[2] = v == 144 ? 1 : 0; v = 0; }
+	return v;
+}
+
 NHW_HDN void y_e18_pack_list_image(const EncImg &im, int which)
 {
 	uint8_t *pos = im.tmp1, *wrd = im.tmp3;

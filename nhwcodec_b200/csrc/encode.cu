@@ -435,28 +435,104 @@ void run_ll2_staged(nhw_ctx *c, const char *label, const EncBatch &b, int n, siz
 
 // ---- res1/res3/res5 side-channel lists: rows collected in parallel (count, CTA prefix, write),
 // the short list post-processing by one thread
+// One coalesced sweep over LL1 collects all three lists (y_e18_classify): warp = row, lane = 8 columns; rows are
+// counted, a CTA prefix gives every row its place in each list, a second sweep writes entries and the rewritten
+// cells.  The serial tails of the lists (pruning, packing) are 3 x n independent single-thread jobs: they run in
+// their own launch, one job per warp, so that thousands of them are resident at once (k_e18_tails).
+#define E18_PART 21800        // scratch entries per list; longer lists (never seen) take the one-list-at-a-time path
 __global__ void __launch_bounds__(256) k_e18_lists(EncBatch b, int q)
 {
-	__shared__ int cnt[257];
+	__shared__ int cnt[3][257];
+	__shared__ int too_long;
 	const EncImg im = make_img(b, blockIdx.x, 0);
-	const int row = threadIdx.x;
-	for (int which = 1; which <= 5; which += 2) {
-		if ((which == 3 && q < 19) || (which == 5 && q < 21)) continue;
-		const int n = y_e18_collect_row(im, which, row, nullptr, nullptr);
-		cnt[row] = n;
-		__syncthreads();
-		if (row == 0) {
-			int run = 0;
-			for (int r = 0; r < 256; r++) { const int v = cnt[r]; cnt[r] = run; run += v; }
-			cnt[256] = run;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	auto sweep = [&](bool write) {
+		for (int row = warp; row < 256; row += 8) {
+			int16_t *L = im.ll1 + row * 256;
+			const uint4 raw = reinterpret_cast<const uint4 *>(L)[lane];
+			const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
+			int v[8], mem[8], w[8][3], n[3] = {0, 0, 0};
+#pragma unroll
+			for (int t = 0; t < 8; t++) {
+				const int orig = (int16_t)(wv[t >> 1] >> ((t & 1) * 16));
+				const int j = 8 * lane + t;
+				if (j < 254) v[t] = y_e18_classify(orig, q, mem[t], w[t]);
+				else { v[t] = write ? 0 : orig; mem[t] = 0; }       // the stage clears columns 254, 255
+				for (int k = 0; k < 3; k++) n[k] += (mem[t] >> k) & 1;
+			}
+			int off[3];
+			for (int k = 0; k < 3; k++) {
+				int inc = n[k];
+				for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+				off[k] = inc - n[k];
+				if (!write && lane == 31) cnt[k][row] = inc;
+			}
+			if (write) {
+				for (int k = 0; k < 3; k++) {
+					const int e0 = cnt[k][row];
+					uint8_t *pos = im.tmp1 + k * E18_PART + e0 + row, *wrd = im.tmp3 + k * E18_PART + e0;
+					int o = off[k];
+#pragma unroll
+					for (int t = 0; t < 8; t++)
+						if ((mem[t] >> k) & 1) { pos[o] = (uint8_t)(8 * lane + t); wrd[o] = (uint8_t)w[t][k]; o++; }
+					if (lane == 31) pos[o] = 254;     // end-of-row marker after the row's last entry
+				}
+				reinterpret_cast<uint4 *>(L)[lane] =
+				    make_uint4((uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16), (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16),
+				               (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16), (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16));
+			}
 		}
-		__syncthreads();
-		const int e0 = cnt[row];
-		y_e18_collect_row(im, which, row, im.tmp1 + e0 + row, im.tmp3 + e0);
-		__syncthreads();
-		if (row == 0) y_e18_finish_list_image(im, which, cnt[256] + 256, cnt[256]);
-		__syncthreads();
+	};
+	sweep(false);
+	__syncthreads();
+	if (threadIdx.x < 3) {
+		int *c = cnt[threadIdx.x];
+		int run = 0;
+		for (int r = 0; r < 256; r++) { const int x = c[r]; c[r] = run; run += x; }
+		c[256] = run;
 	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		too_long = (cnt[0][256] + 300 > E18_PART || cnt[1][256] + 300 > E18_PART || cnt[2][256] + 300 > E18_PART) ? 1 : 0;
+		for (int k = 0; k < 3; k++) im.hdr->pad[k] = too_long ? -1 : cnt[k][256];   // entries per list, for k_e18_tails
+	}
+	__syncthreads();
+	if (too_long) {
+		// one list at a time with the whole scratch (the original schedule); thread = row
+		const int row = threadIdx.x;
+		for (int which = 1; which <= 5; which += 2) {
+			if ((which == 3 && q < 19) || (which == 5 && q < 21)) continue;
+			__syncthreads();
+			cnt[0][row] = y_e18_collect_row(im, which, row, nullptr, nullptr);
+			__syncthreads();
+			if (row == 0) {
+				int run = 0;
+				for (int r = 0; r < 256; r++) { const int x = cnt[0][r]; cnt[0][r] = run; run += x; }
+				cnt[0][256] = run;
+			}
+			__syncthreads();
+			const int e0 = cnt[0][row];
+			y_e18_collect_row(im, which, row, im.tmp1 + e0 + row, im.tmp3 + e0);
+			__syncthreads();
+			if (row == 0) y_e18_finish_list_image(im, which, cnt[0][256] + 256, cnt[0][256]);
+		}
+		return;
+	}
+	sweep(true);
+}
+
+// list tails: block (k, image), one thread
+__global__ void __launch_bounds__(32) k_e18_tails(EncBatch b, int q)
+{
+	if (threadIdx.x) return;
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	const int k = blockIdx.x, which = 1 + 2 * k, e = im.hdr->pad[k];
+	if (e < 0 || (which == 3 && q < 19) || (which == 5 && q < 21)) return;
+	EncImg lm = im;
+	lm.tmp1 = im.tmp1 + k * E18_PART;
+	lm.tmp2 = im.tmp2 + k * E18_PART;
+	lm.tmp3 = im.tmp3 + k * E18_PART;
+	y_e18_finish_list_image(lm, which, e + 256, e);
 }
 
 // ---- E6d: LL1 correction (enc_y1.cuh: e6d_delta_at), one thread per cell; 8 rows per CTA
@@ -1182,6 +1258,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		NHW_LAUNCH_L(c, "y_e16b_classify", k_e16b_classify, n, 256, 0, b, q);
 	if (q > 21) NHW_LAUNCH_L(c, "y_hq_e17", k_hq_e17, dim3(256, n), 256, 0, b);
 	NHW_LAUNCH_L(c, "y_e18_lists", k_e18_lists, n, 256, 0, b, q);
+	NHW_LAUNCH_L(c, "y_e18_tails", k_e18_tails, dim3(3, n), 32, 0, b, q);
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
 	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(256, n), 128, 0, b);
