@@ -100,13 +100,14 @@ NHW_HDN int pack_alphabet(PackState &st, int part, int &select, int &k, int &b)
 }
 
 // Codebook section of the container for one stream (compress_pixel.c:400-461)
-NHW_HDN void pack_codebook(const EncImg &im, const PackState &st, int part, int k)
+// scratch: 2 x 1024 bytes (the raw list, then its de-interleaved copy); NULL = use the image's list scratch
+NHW_HDN void pack_codebook(const EncImg &im, const PackState &st, int part, int k, uint8_t *scratch = nullptr)
 {
 	EncHdr *h = im.hdr;
 	// ---- codebook: ranked symbol list, de-interleaved (even then odd positions), runs of the
 	// marker byte compressed (compress_pixel.c:400-461)
 	const int marker = part ? 128 : 3;
-	uint8_t *raw = im.tmp3 + 40000, *de = im.tmp3 + 41000;   // raw list, then its de-interleaved copy
+	uint8_t *raw = scratch ? scratch : im.tmp3 + 40000, *de = raw + 1000;
 	int n = 0;
 	for (int i = 0; i < k; i++) {
 		if ((st.sym[i] >> 8) == 1) raw[n++] = (uint8_t)(part ? ((st.sym[i] & 0xff) | 1) : (st.sym[i] & 0xff));

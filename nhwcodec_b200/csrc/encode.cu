@@ -792,10 +792,10 @@ __device__ __forceinline__ void build_nz_bitmap(const uint8_t *s, int count, uin
 		          (nz_mask4(b.y) << 20) | (nz_mask4(b.z) << 24) | (nz_mask4(b.w) << 28);
 	}
 	__syncthreads();
-	for (int j = tid; j < count / 1024; j += nthreads) {
-		uint32_t m = 0;
-		for (int k = 0; k < 32; k++) m |= (bits[32 * j + k] != 0 ? 1u : 0u) << k;
-		sum[j] = m;
+	// summary word j = ballot of "bits[32 j + lane] != 0" (one conflict-free load per warp and word)
+	for (int j = tid >> 5; j < count / 1024; j += nthreads >> 5) {
+		const uint32_t m = __ballot_sync(0xffffffffu, bits[32 * j + (tid & 31)] != 0);
+		if ((tid & 31) == 0) sum[j] = m;
 	}
 }
 
@@ -866,7 +866,8 @@ __global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
 	__shared__ uint16_t s_sym[354];
 	__shared__ int s_select, s_k, s_b, s_rc, s_bad, s_word0;
 	const EncImg im = make_img(b, blockIdx.x, 0);
-	PackState &st = *static_cast<PackState *>(im.pack_scratch);
+	__shared__ PackState st;                       // histograms / alphabet: the serial sections run on shared memory
+	__shared__ uint8_t book_scratch[2048];
 	uint8_t *s = im.scan;
 	EncHdr *h = im.hdr;
 	const int t = threadIdx.x;
@@ -969,7 +970,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
 				s[262144] = saved;
 			} else h->size_data2 = word0 + nwords;
 			s_word0 = word0 + nwords;
-			pack_codebook(im, st, part, k);
+			pack_codebook(im, st, part, k, book_scratch);
 		}
 		__syncthreads();
 	}
