@@ -1,0 +1,371 @@
+// enc_cells.cuh -- cell-parallel forms of luma stages the reference writes as in-place row loops.  One call handles
+// a GROUP of 8 consecutive cells of a row (one 16-byte load / store); every value is computed from the plane as it
+// was BEFORE the stage (the executor loads, synchronises, then stores; rows never straddle two CTAs), so groups are
+// independent.  For each stage the comment states why the row loop reduces to this.  tests/hostemu runs the same
+// functions against the reference's taps.
+#pragma once
+#include "enc_point.cuh"
+
+NHW_HD void ld8(const int16_t *p, int *v)
+{
+#ifdef __CUDA_ARCH__
+	const uint4 w = *reinterpret_cast<const uint4 *>(p);
+	v[0] = (int16_t)(w.x & 0xffff); v[1] = (int16_t)(w.x >> 16);
+	v[2] = (int16_t)(w.y & 0xffff); v[3] = (int16_t)(w.y >> 16);
+	v[4] = (int16_t)(w.z & 0xffff); v[5] = (int16_t)(w.z >> 16);
+	v[6] = (int16_t)(w.w & 0xffff); v[7] = (int16_t)(w.w >> 16);
+#else
+	for (int k = 0; k < 8; k++) v[k] = p[k];
+#endif
+}
+NHW_HD void st8(int16_t *p, const int *v)
+{
+#ifdef __CUDA_ARCH__
+	uint4 w;
+	w.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+	w.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
+	w.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
+	w.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+	*reinterpret_cast<uint4 *>(p) = w;
+#else
+	for (int k = 0; k < 8; k++) p[k] = (int16_t)v[k];
+#endif
+}
+
+// ---- E6a (nhw_encoder.c:144-177; row form y_e6a_tag_row): reads the level-2 detail cell and two diagonal
+// neighbours, adds a tag to the LL1 copy.  Pointwise as written.  Returns whether L changed.
+NHW_HD bool y_e6a_tag_cells(const int16_t *P /* plane */, int16_t *Lrow /* ll1 row r */, int r, int g)
+{
+	const int j0 = g * 8;
+	if (r < 128 && j0 < 128) return false;
+	int v[8], add[8];
+	ld8(P + r * YW + j0, v);
+	bool any = false;
+	for (int k = 0; k < 8; k++) {
+		const int scan = r * YW + j0 + k, st = v[k];
+		int a = 0;
+		if (st < -7) {
+			const int low = (-st) & 7;
+			if (low == 7 || low == 0) a = 16000;
+		} else if (st < -4) a = 12000;
+		else if (st >= 0) {
+			if (st >= 2 && st < 5) {
+				if (scan >= YW + 1 && scan < 2 * 65536 - YW - 1) {
+					if (P[scan - (YW + 1)] != 0 || P[scan + (YW + 1)] != 0) a = 12000;
+				}
+			} else if ((st & 7) == 0 || (st & 7) == 1) a = 12000;
+			else if (st > 4 && st <= 7) a = 16000;
+		}
+		add[k] = a;
+		any |= a != 0;
+	}
+	if (!any) return false;
+	int l[8];
+	ld8(Lrow + j0, l);
+	for (int k = 0; k < 8; k++) l[k] += add[k];
+	st8(Lrow + j0, l);
+	return true;
+}
+
+// ---- E6c (nhw_encoder.c:183-216; row form y_e6c_apply_row): un-tag LL1, push +-1 into the trial reconstruction
+// at the transposed position.  Every target is written by exactly one source cell.
+NHW_HD void y_e6c_apply_cells(int16_t *P, int16_t *Lrow, int r, int g)
+{
+	const int j0 = g * 8;
+	int l[8];
+	ld8(Lrow + j0, l);
+	bool any = false;
+	for (int k = 0; k < 8; k++) {
+		const int j = j0 + k;
+		int d;
+		if (l[k] > 14000) { l[k] -= 16000; d = 1; }
+		else if (l[k] > 10000) { l[k] -= 12000; d = -1; }
+		else continue;
+		any = true;
+		if (r < 128 && j >= 128) P[2 * r + ((j - 128) << 10) + YW] += d;
+		else if (r >= 128 && j < 128) P[2 * (r - 128) + (j << 10) + 1] += d;
+		else if (r >= 128 && j >= 128) P[2 * (r - 128) + ((j - 128) << 10) + YW + 1] += d;
+	}
+	if (any) st8(Lrow + j0, l);
+}
+
+// ---- offsetY loop 1 (image_processing.c:194-237; row form y_offset_mult8_row).  A turn at cell i (columns
+// c0(r) .. 510) fires when P[i] and P[i+1] are both positive multiples of 8; it decrements P[i] (when P[i] > 15
+// and P[i-1] <= 0) or else P[i+1] (when P[i+1] > 15 and P[i+2] <= 0, column < 510).  A decremented cell is still
+// positive, a cell <= 0 is never touched, and a turn that decrements its right neighbour needs P[i+2] <= 0 -- which
+// makes the neighbour's own turn fail whether or not it was decremented; so every condition has the same outcome on
+// the values before the stage.  o[0..7] = the final values of the group; returns false when nothing changed.
+NHW_HD bool offset_mult8_fires(int a, int b) { return a > 7 && b > 7 && !(a & 7) && !(b & 7); }
+NHW_HD bool y_offset_mult8_cells(const int16_t *P, int r, int g, int *o)
+{
+	const int c = g * 8, c0 = r < 256 ? 256 : 0;
+	if (c < c0) return false;
+	int w[12];   // columns c-2 .. c+9
+	const int16_t *R = P + r * YW;
+	w[0] = R[c - 2]; w[1] = R[c - 1];
+	ld8(R + c, w + 2);
+	w[10] = R[c + 8]; w[11] = R[c + 9];
+	bool any = false;
+	for (int k = 0; k < 8; k++) {
+		const int col = c + k;
+		const int *v = w + 2 + k;   // v[0] = this cell
+		int dec = 0;
+		// its own turn
+		if (col < 511 && offset_mult8_fires(v[0], v[1]) && v[0] > 15 && v[-1] <= 0) dec = 1;
+		// the turn of the cell on its left
+		else if (col - 1 >= c0 && col - 1 < 510 && offset_mult8_fires(v[-1], v[0]) && v[0] > 15 && v[1] <= 0 &&
+		         !(v[-1] > 15 && v[-2] <= 0))
+			dec = 1;
+		o[k] = v[0] - dec;
+		any |= dec != 0;
+	}
+	return any;
+}
+
+// ---- offsetY like-signed 5..7 pairs (image_processing.c:291-311; row form y_offset_pairs57_row), rows 0..255,
+// columns 0..255.  The loop pairs cells of the same class greedily from the left and tags the first of each pair;
+// the tag is behind the cursor, so a cell is tagged iff its right neighbour is of its class and it sits at an even
+// offset in its run of that class (runs start at column 0 of a row at the earliest).
+NHW_HD int pairs57_class(int v) { return (v >= 5 && v <= 7) ? 1 : (v <= -5 && v >= -7) ? 2 : 0; }
+NHW_HD bool y_offset_pairs57_cells(const int16_t *P, int r, int g, int *o)
+{
+	const int c = g * 8;
+	const int16_t *R = P + r * YW;
+	int v[9];
+	ld8(R + c, v);
+	v[8] = c + 8 < 256 ? (int)R[c + 8] : 0;
+	int any_cls = 0;
+	for (int k = 0; k < 8; k++) any_cls |= pairs57_class(v[k]);
+	if (!any_cls) return false;
+	// offset parity of the first cell in its run
+	int cls = pairs57_class(v[0]), par = 0;
+	if (cls) { int s = c; while (s > 0 && pairs57_class(R[s - 1]) == cls) { s--; par ^= 1; } }
+	bool any = false;
+	for (int k = 0; k < 8; k++) {
+		const int cl = pairs57_class(v[k]);
+		if (k) { if (cl && cl == cls) par ^= 1; else par = 0; }
+		cls = cl;
+		o[k] = v[k];
+		if (cl && !par && c + k < 255 && pairs57_class(v[k + 1]) == cl) { o[k] = cl == 1 ? 10300 : 10204; any = true; }
+	}
+	return any;
+}
+
+// ---- E6d (nhw_encoder.c:218-279), 8 cells: like e6d_delta_at, but the stretch before the group is replayed once
+// and the group is then walked left to right.  sc = the row's differences (sc[-1] .. sc[256]).
+NHW_HD void e6d_delta_cells(const int16_t *sc, int j0, const int *own /* sc[j0 .. j0+7] */, int *d)
+{
+	int prev;
+	if (e6d_needs_neighbours(own[0])) {
+		int start = j0;
+		while (start > 0 && e6d_needs_neighbours(sc[start - 1])) start--;
+		prev = start > 0 ? sc[start - 1] + e6d_delta(sc[start - 1], 0, 0) : sc[-1];
+		for (int t = start; t < j0; t++) prev = sc[t] + e6d_delta(sc[t], sc[t + 1], prev);
+	} else prev = 0;   // not read
+	for (int k = 0; k < 8; k++) {
+		const int s = own[k];
+		d[k] = e6d_delta(s, k < 7 ? own[k + 1] : (int)sc[j0 + 8], prev);
+		prev = s + d[k];
+	}
+}
+
+// ---- offsetY_recons256: like-signed 5..7 pairs (second call only; row form y_recons_tag57_row) followed by the
+// dead-zone quantise + dequantise of a detail row into im_jpeg (row form y_recons_quant_row).
+// Pair tags: same greedy pairing as above, the value a cell has after that loop is a function of its run parity.
+NHW_HD int recons_tag57_at(const int16_t *R /* row */, int j, int jr0)
+{
+	const int v = R[j], cl = pairs57_class(v);
+	if (!cl || j >= 255 || pairs57_class(R[j + 1]) != cl) return v;
+	int par = 0;
+	for (int s = j; s > jr0 && pairs57_class(R[s - 1]) == cl; s--) par ^= 1;
+	return par ? v : (cl == 1 ? 15700 : 15800);
+}
+// The quantiser walks a row with a cursor that jumps over 1 or 2 cells after a pattern tag, and a visited cell may
+// rewrite the NEXT cell (-7 -> -8, 7 -> 8) before that cell's turn.  Two facts bound the history a cell depends on:
+//   * a cell is visited whenever the two cells before it hold no tag (whatever skipped them ends before it);
+//   * a rewritten cell only ever passes on one more rewrite (a 7 turned 8 can turn the next -7 into -8; a -8 does
+//     nothing), so an unknown state dies out within two cells.
+// So the cursor is re-started behind six tag-free cells (or at the start of the row) and the loop is replayed from
+// there on private state; only im_jpeg is written (the in-place edits of the band are dead: both callers rebuild
+// the region afterwards).  o[k] / bit k of the result = value / "written" for the 8 cells of the group.
+#define RQ_NONE 0x40000000
+NHW_HD int rq_val(const int16_t *R, int j, int jr0, int part) { return part ? (int)R[j] : recons_tag57_at(R, j, jr0); }
+NHW_HD int y_recons_quant_cells(const int16_t *R /* band row, before the stage */, int r, int g, int m1, int part, int *o)
+{
+	const int c = g * 8, jr0 = r < 128 ? 128 : 0;
+	if (c < jr0) return 0;
+	int st = c, clean = 0;
+	while (st > jr0) {
+		st--;
+		clean = rq_val(R, st, jr0, part) > 15000 ? 0 : clean + 1;
+		if (clean == 6) { st += 2; break; }
+	}
+	int mask = 0, pend = RQ_NONE;
+	for (int j = st; j < c + 8;) {
+		int a = pend != RQ_NONE ? pend : rq_val(R, j, jr0, part);
+		pend = RQ_NONE;
+		int out = RQ_NONE, out_next = RQ_NONE, step = 1;
+		if (a > 15000) {
+			if (a == 15300) { out = 5; step = 3; }
+			else if (a == 15400) { out = -5; step = 3; }
+			else if (a == 15500) { out = 5; step = 2; }
+			else if (a == 15600) { out = -5; step = 2; }
+			else if (a == 15700) { out = 6; out_next = 6; step = 2; }
+			else if (a == 15800) { out = -6; out_next = -6; step = 2; }
+		} else {
+			const int nx = j < 255 ? rq_val(R, j + 1, jr0, part) : RQ_NONE;
+			if (a < -12 && ((-a) & 7) == 6) { if (nx == -7) pend = -8; }
+			if (a < 0) {
+				if (a == -7 && nx == 8) a = -8;
+				a = -a;
+				if ((a & 7) < 7) a &= 65528;
+				a = -a;
+			} else if (a == 8 && nx == -7) pend = -8;
+			else if (a > 12 && !part && (a & 7) >= 6) { if (nx == 7) pend = 8; }
+			if (a < m1 && a > -m1) out = 0;
+			else {
+				a += 128;
+				if (a < 0) a = -((-a) & 65528);
+				else a &= 65528;
+				out = a > 128 ? a - 125 : a - 131;
+			}
+		}
+		if (j >= c && out != RQ_NONE) { o[j - c] = out; mask |= 1 << (j - c); }
+		if (j + 1 >= c && j + 1 < c + 8 && out_next != RQ_NONE) { o[j + 1 - c] = out_next; mask |= 1 << (j + 1 - c); }
+		j += step;
+	}
+	return mask;
+}
+
+// ---- E14 + E15 (nhw_encoder.c:783-803, 970-1074; row forms y_e14_threshold_row, y_e15_tags_row).
+// E14 is pointwise.  E15 visits every cell of a band row in order, reads (left, self, right) and may rewrite all
+// three; but a cell whose value lies outside +-4..+-8 neither triggers a rule nor is ever rewritten, so the loop is
+// replayed on private state from the nearest such cell on the left (or from the start of the band row), one turn
+// past the group (that turn may still rewrite the group's last cell).
+NHW_HD int e14_value(int v, int q, int ratio, int r, int j)
+{
+	if (r >= 256 && q < 20 && q > 15) {
+		const int a = nhw_iabs(v);
+		if (a >= ratio && (j < 256 ? a < 9 : a <= 14)) return v > 0 ? 7 : -7;
+	}
+	return v;
+}
+NHW_HD bool e15_active(int v) { const int a = nhw_iabs(v); return a >= 4 && a <= 8; }
+NHW_HD bool y_e14_e15_cells(const int16_t *R /* row r */, int r, int g, int q, int ratio, int *o)
+{
+	const int c = g * 8;
+	int raw[8];
+	ld8(R + c, raw);
+	bool changed = false, any_active = false;
+	for (int k = 0; k < 8; k++) {
+		o[k] = e14_value(raw[k], q, ratio, r, c + k);
+		changed |= o[k] != raw[k];
+		any_active |= e15_active(o[k]);
+	}
+	int j0, j1;
+	bool band_a;
+	if (r >= 1 && r <= 254) { j0 = 257; j1 = 511; band_a = true; }
+	else if (r >= 257 && r <= 510) { j0 = 1; j1 = 255; band_a = false; }
+	else return changed;
+	if (c + 7 < j0 - 1 || c > j1) return changed;
+	// a rewrite of a group cell needs that cell, or (for the +-9 pair rule) nothing else, to be active
+	if (!any_active) return changed;
+	int s = c > j0 ? c : j0;
+	while (s > j0 && e15_active(e14_value(R[s - 1], q, ratio, r, s - 1))) s--;
+	int prev = e14_value(R[s - 1], q, ratio, r, s - 1), cur = e14_value(R[s], q, ratio, r, s);
+	const int last = c + 8 < j1 - 1 ? c + 8 : j1 - 1;
+	for (int j = s; j <= last; j++) {
+		const int nx = e14_value(R[j + 1], q, ratio, r, j + 1);
+		int nx_new = nx;
+		const int v = cur;
+		if (v > 4 && v < 8) {
+			if (in4to7(prev) && in4to7(nx)) { cur = 12700; prev = 10100; nx_new = 10100; }
+		} else if (v < -4 && v > -8) {
+			if (in_m7to_m4(prev) && in_m7to_m4(nx)) { cur = 12900; prev = 10100; nx_new = 10100; }
+		} else if (v == 8) {
+			if ((prev & 65534) == 6 || (nx & 65534) == 6) cur = 10;
+			else if (band_a && nx == 8) { cur = 9; nx_new = 9; }
+		} else if (v == -8) {
+			if (((-prev) & 65534) == 6 || ((-nx) & 65534) == 6) cur = -9;
+			else if (band_a && nx == -8) { cur = -9; nx_new = -9; }
+		}
+		if (j - 1 >= c && j - 1 < c + 8 && o[j - 1 - c] != prev) { o[j - 1 - c] = prev; changed = true; }
+		if (j >= c && j < c + 8 && o[j - c] != cur) { o[j - c] = cur; changed = true; }
+		if (j + 1 >= c && j + 1 < c + 8 && o[j + 1 - c] != nx_new) { o[j + 1 - c] = nx_new; changed = true; }
+		prev = cur;
+		cur = nx_new;
+	}
+	return changed;
+}
+
+// ---- chroma: offsetUV_recons256 (row forms c_recons_ll_row + c_recons_quant_row), one group of a 128-column row of
+// the level-2 region.  The band is only read.  The one sequential element (second call: greedy pairing of
+// neighbouring -7/-8 cells into -11,-11) is the parity of a cell's offset in its run of such cells.
+NHW_HD int c_recons_quant_value(int a, int nx, int m1)
+{
+	if (a < 0) {
+		a = -a;
+		if (nx < 0 && nx > -8) { if ((a & 7) < 6) a &= 65528; }
+		else if ((a & 7) < 7) a &= 65528;
+		a = -a;
+	}
+	if (a < m1 && a > -m1) return 0;
+	a += 128;
+	if (a < 0) a = -((-a) & 65528);
+	else a &= 65528;
+	return a > 128 ? a - 125 : a - 131;
+}
+NHW_HD void c_recons_cells(const int16_t *R /* cproc row r */, int r, int g, int m1, int comp, int *o)
+{
+	const int c = g * 8;
+	int v[9];
+	ld8(R + c, v);
+	v[8] = R[c + 8];
+	if (r < 64 && c < 64) {   // LL
+		for (int k = 0; k < 8; k++) {
+			if (comp) o[k] = (r == 0) == ((k & 1) == 1) ? (int)(int16_t)(v[k] & 65534) : v[k];
+			else o[k] = (v[k] > 0 && v[k] < 256) ? (v[k] & 65534) : v[k];
+		}
+		return;
+	}
+	const int jr0 = r < 64 ? 64 : 0;
+	int par = 0;
+	bool prev_pairable = false;
+	if (!comp && c_pairable(v[0])) {
+		for (int s = c; s > jr0 && c_pairable(R[s - 1]); s--) par ^= 1;
+		prev_pairable = true;   // only its parity is used below
+	}
+	for (int k = 0; k < 8; k++) {
+		const int j = c + k;
+		if (!comp && c_pairable(v[k])) {
+			if (k) par = prev_pairable ? par ^ 1 : 0;
+			prev_pairable = true;
+			if (par || (j < 127 && c_pairable(v[k + 1]))) { o[k] = -11; continue; }
+		} else prev_pairable = false;
+		o[k] = c_recons_quant_value(v[k], v[k + 1], m1);
+	}
+}
+
+// ---- chroma LL1 correction (row form c_correct_row): pointwise
+NHW_HD void c_correct_cells(const int16_t *P /* cproc row */, const int16_t *L /* cll1 row */, int g, int is_v, int *o)
+{
+	const int c = g * 8;
+	int p[9], l[9];
+	ld8(P + c, p); p[8] = P[c + 8];
+	ld8(L + c, l); l[8] = L[c + 8];
+	for (int k = 0; k < 8; k++) {
+		const int scan = p[k] - l[k], nx = p[k + 1] - l[k + 1];
+		int d = 0;
+		if (scan > 10) d = -6;
+		else if (scan > 7) d = -3;
+		else if (scan > 4) d = -2;
+		else if (scan > 3) d = -1;
+		else if (scan > 2 && (is_v ? nx > 0 : nx >= 0)) d = -1;
+		else if (scan < -10) d = 6;
+		else if (scan < -7) d = 3;
+		else if (scan < -4) d = 2;
+		else if (scan < -3) d = 1;
+		else if (scan < -2 && (is_v ? nx < 0 : nx <= 0)) d = 1;
+		o[k] = l[k] + d;
+	}
+}

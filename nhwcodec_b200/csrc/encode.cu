@@ -13,7 +13,7 @@
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
 #include "enc_seg.cuh"
-#include "enc_point.cuh"
+#include "enc_cells.cuh"
 #include "enc_batch.cuh"
 #include "../../include/nhw_cuda.h"
 
@@ -126,6 +126,58 @@ static int rows_grid_cap()
 		cap = sms * (e ? atoi(e) : ROWS_CTAS_PER_SM);
 	}
 	return cap;
+}
+
+// ---- cell-group executors (enc_cells.cuh): one thread per group of 8 cells, 256 threads = whole rows of a CTA.
+// k_groups: f does its own loads and stores (stages that never read what they write).
+// k_groups_inplace: f only reads and returns the group's final values; the CTA synchronises, then stores, so a
+// group never sees another group's result (rows never straddle CTAs, and these stages only look along their row).
+template <typename F>
+__global__ void __launch_bounds__(256) k_groups(EncBatch b, int gshift, F f)
+{
+	const int idx = blockIdx.x * 256 + threadIdx.x;
+	f(make_img(b, blockIdx.y, 0), idx >> gshift, idx & ((1 << gshift) - 1));
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_groups_inplace(EncBatch b, int gshift, F f)
+{
+	const int idx = blockIdx.x * 256 + threadIdx.x;
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	const int r = idx >> gshift, g = idx & ((1 << gshift) - 1);
+	int o[8];
+	const bool changed = f(im, r, g, o);
+	__syncthreads();
+	if (changed) st8(im.proc + r * YW + g * 8, o);
+}
+// dead-zone quantiser of the level-2 detail bands into im_jpeg (enc_cells.cuh: y_recons_quant_cells); the band is only read
+__device__ __forceinline__ void recons_quant_group(const EncImg &im, int r, int g, int m1, int part)
+{
+	int o[8];
+	const int mask = y_recons_quant_cells(im.proc + r * YW, r, g, m1, part, o);
+	int16_t *J = im.jpeg + r * YW + g * 8;
+	if (mask == 0xff) st8(J, o);
+	else for (int x = 0; x < 8; x++) if (mask >> x & 1) J[x] = (int16_t)o[x];
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_plane_groups(EncBatch b, int gshift, F f)
+{
+	const int idx = blockIdx.x * 256 + threadIdx.x;
+	f(make_img(b, blockIdx.y >> 1, blockIdx.y & 1), idx >> gshift, idx & ((1 << gshift) - 1), (int)(blockIdx.y & 1));
+}
+template <typename F>
+void run_plane_groups(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, int gshift, F f)
+{
+	NHW_LAUNCH_L(c, label, k_plane_groups, dim3((rows << gshift) / 256, 2 * n), 256, 0, b, gshift, f);
+}
+template <typename F>
+void run_groups(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, int gshift, F f)
+{
+	NHW_LAUNCH_L(c, label, k_groups, dim3((rows << gshift) / 256, n), 256, 0, b, gshift, f);
+}
+template <typename F>
+void run_groups_inplace(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, int gshift, F f)
+{
+	NHW_LAUNCH_L(c, label, k_groups_inplace, dim3((rows << gshift) / 256, n), 256, 0, b, gshift, f);
 }
 
 template <typename F>
@@ -535,59 +587,88 @@ __global__ void __launch_bounds__(32) k_e18_tails(EncBatch b, int q)
 	y_e18_finish_list_image(lm, which, e + 256, e);
 }
 
-// ---- E6d: LL1 correction (enc_y1.cuh: e6d_delta_at), one thread per cell; 8 rows per CTA
+// ---- E6d: LL1 correction (enc_cells.cuh: e6d_delta_cells), one thread per 8 cells; 8 rows per CTA
 __global__ void __launch_bounds__(256) k_e6d_correct(EncBatch b)
 {
-	__shared__ int16_t sc[8][264];   // differences of a row, columns -1 .. 256 at index 1 .. 258
+	__shared__ __align__(16) int16_t sc[8][272];   // differences of a row, columns -1 .. 256 at index 7 .. 264
 	const EncImg im = make_img(b, blockIdx.y, 0);
-	const int j = threadIdx.x;
-	for (int k = 0; k < 8; k++) {
-		const int r = blockIdx.x * 8 + k;
-		const int16_t *P = im.proc + r * YW, *L = im.ll1 + r * 256;
-		sc[k][j + 2] = (int16_t)(P[j] - L[j]);
-		if (j == 0) sc[k][1] = (int16_t)(P[-1] - L[-1]);
-		if (j == 255) sc[k][258] = (int16_t)(P[256] - L[256]);
-	}
+	const int k = threadIdx.x >> 5, g = threadIdx.x & 31, j0 = g * 8;
+	const int r = blockIdx.x * 8 + k;
+	int16_t *P = im.proc + r * YW, *J = im.jpeg + r * YW;
+	const int16_t *L = im.ll1 + r * 256;
+	int p[8], l[8], d[8], own[8];
+	ld8(P + j0, p);
+	ld8(L + j0, l);
+	#pragma unroll
+	for (int x = 0; x < 8; x++) own[x] = (int16_t)(p[x] - l[x]);
+	st8(&sc[k][8 + j0], own);
+	if (g == 0) sc[k][7] = (int16_t)(P[-1] - L[-1]);
+	if (g == 31) sc[k][264] = (int16_t)(P[256] - L[256]);
 	__syncthreads();
-	for (int k = 0; k < 8; k++) {
-		const int r = blockIdx.x * 8 + k;
-		int16_t *P = im.proc + r * YW, *J = im.jpeg + r * YW;
-		const int16_t *L = im.ll1 + r * 256;
-		const int d = e6d_delta_at(&sc[k][2], j);
-		J[j] = (int16_t)(L[j] + d);
-		P[j] = (int16_t)(P[j] + d);
-	}
+	e6d_delta_cells(&sc[k][8], j0, own, d);
+	#pragma unroll
+	for (int x = 0; x < 8; x++) { l[x] += d[x]; p[x] += d[x]; }
+	st8(J + j0, l);
+	st8(P + j0, p);
 }
 
-// ---- E20: clean-up of the three level-1 bands, cell-parallel (enc_y2.cuh: e20_final_cell).  Finals are computed
-// from the plane as it is (read only) into the scratch plane, a second launch copies them back.
-// blockIdx.x enumerates (pass, row): 254 rows of pass 0, then 255 of pass 1, then 255 of pass 2.
-__device__ __forceinline__ bool e20_block(int bx, int q, int ratio, E20Pass &g, int &r)
+// ---- E20: clean-up of the three level-1 bands, cell-parallel (enc_y2.cuh: e20_final_cell).  One CTA per (image,
+// pass) walks its region top-down in bands of 8 rows staged in shared memory: every final value is computed from
+// the rows as they were before the stage (the row above a band is kept from the previous band, the row below has
+// not been touched yet), then the band is written back in place.  Column 256 of rows 256..510 is written by pass 1
+// (it receives from column 255) and only read by pass 2, whose test on it has the same outcome either way: each
+// pass stores only its own columns.
+#define E20_ROWS 8
+#define E20_TS 264   // 256 columns + column 256 for pass 1 (+ pad to keep rows 16-byte aligned)
+__global__ void __launch_bounds__(256) k_e20_bands(EncBatch b, int q, int ratio)
 {
-	int pass = bx < 254 ? 0 : bx < 509 ? 1 : 2;
-	g = e20_pass(q, ratio, pass);
-	r = g.r0 + (pass == 0 ? bx : pass == 1 ? bx - 254 : bx - 509);
-	return r < g.r1;
-}
-__global__ void __launch_bounds__(256) k_e20_cells(EncBatch b, int q, int ratio)
-{
+	__shared__ __align__(16) int16_t tile[E20_ROWS + 2][E20_TS];
+	__shared__ __align__(16) int16_t outv[E20_ROWS][256];
+	__shared__ int16_t out_edge[E20_ROWS];   // pass 1: column 256
 	const EncImg im = make_img(b, blockIdx.y, 0);
-	E20Pass g;
-	int r;
-	if (!e20_block(blockIdx.x, q, ratio, g, r)) return;
-	const int j = g.j0 + threadIdx.x;
-	if (j > g.j1) return;
-	im.aux[r * YW + j] = (int16_t)e20_final_cell(im.proc, g, r, j);
-}
-__global__ void __launch_bounds__(256) k_e20_commit(EncBatch b, int q, int ratio)
-{
-	const EncImg im = make_img(b, blockIdx.y, 0);
-	E20Pass g;
-	int r;
-	if (!e20_block(blockIdx.x, q, ratio, g, r)) return;
-	const int j = g.j0 + threadIdx.x;
-	if (j > g.j1) return;
-	im.proc[r * YW + j] = im.aux[r * YW + j];
+	const E20Pass g = e20_pass(q, ratio, blockIdx.x);
+	const int cb = g.pass == 1 ? 0 : 256, tid = threadIdx.x;
+	int16_t *P = im.proc;
+	// row above the first band
+	tile[0][tid] = P[(g.r0 - 1) * YW + cb + tid];
+	if (g.pass == 1 && tid == 0) tile[0][256] = P[(g.r0 - 1) * YW + 256];
+	for (int r0 = g.r0; r0 < g.r1; r0 += E20_ROWS) {
+		{   // rows r0 .. r0+8 (the last one is the row below the band), 32 x 16 bytes each
+			const int k = tid >> 5, c = (tid & 31) * 8, r = r0 + k;
+			if (r <= 511) *reinterpret_cast<uint4 *>(&tile[1 + k][c]) = *reinterpret_cast<const uint4 *>(P + r * YW + cb + c);
+			if (tid < 32) {
+				const int r2 = r0 + E20_ROWS;
+				if (r2 <= 511) *reinterpret_cast<uint4 *>(&tile[1 + E20_ROWS][c]) = *reinterpret_cast<const uint4 *>(P + r2 * YW + cb + c);
+			} else if (g.pass == 1 && tid < 32 + E20_ROWS + 1) {
+				const int r2 = r0 + tid - 32;
+				if (r2 <= 511) tile[1 + tid - 32][256] = P[r2 * YW + 256];
+			}
+		}
+		__syncthreads();
+		#pragma unroll
+		for (int k = 0; k < E20_ROWS; k++) {
+			const int r = r0 + k;
+			if (r >= g.r1) break;
+			const int16_t *row = &tile[1 + k][0] - cb;
+			const int j = cb + tid;
+			if (j >= g.j0 && j <= g.j1) outv[k][tid] = (int16_t)e20_final_cell(row, E20_TS, g, r, j);
+			else if (g.pass == 1 && tid == 0) out_edge[k] = (int16_t)e20_final_cell(row, E20_TS, g, r, 256);
+		}
+		__syncthreads();
+		// keep the last row of the band as it was, then write the band back
+		tile[0][tid] = tile[E20_ROWS][tid];
+		if (g.pass == 1 && tid == 0) tile[0][256] = tile[E20_ROWS][256];
+		{
+			const int k = tid >> 5, c = (tid & 31) * 8, r = r0 + k;
+			if (r < g.r1) {
+				if (c == 0) {   // the first column of the block is not this pass's to write
+					for (int x = 1; x < 8; x++) P[r * YW + cb + x] = outv[k][x];
+				} else *reinterpret_cast<uint4 *>(P + r * YW + cb + c) = *reinterpret_cast<const uint4 *>(&outv[k][c]);
+			}
+			if (g.pass == 1 && tid < E20_ROWS && r0 + tid < g.r1) P[(r0 + tid) * YW + 256] = out_edge[tid];
+		}
+		__syncthreads();
+	}
 }
 
 // ---- E19: restore the level-2 region from the resIII snapshot (y_e19_restore_row), one thread per cell pair
@@ -1212,14 +1293,14 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	front_fused(c, rgb, n, q, b.y_proc, YS, b.y_ll1, CS, c->c_u8, b.c_proc, CS, b.c_ll1, QS, b.y_hq, YS);
 
 	// ---- luma closed loop (nhw_encoder.c:141-283)
-	run_rows(c, "y_e6a_tag", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6a_tag_row(im, r); });
+	run_groups(c, "y_e6a_tag", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { y_e6a_tag_cells(im.proc, im.ll1 + r * 256, r, g); });
 	NHW_LAUNCH_L(c, "y_recons1_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 1);
 	for (int reg = 0; reg < 2; reg++)
 		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
-	run_rows(c, "y_recons1_quant", b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 1); });
+	run_groups(c, "y_recons1_quant", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { recons_quant_group(im, r, g, ratio, 1); });
 	idwt_luma256(c, b, n);
-	run_rows(c, "y_e6c_apply", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e6c_apply_row(im, r); });
+	run_groups(c, "y_e6c_apply", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { y_e6c_apply_cells(im.proc, im.ll1 + r * 256, r, g); });
 	NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(32, n), 256, 0, b);
 	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
 
@@ -1238,20 +1319,14 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	for (int reg = 0; reg < 2; reg++)
 		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
-	run_rows(c, "y_recons0_quant", b, n, 256, [=] __device__(const EncImg &im, int r) {
-		y_recons_tag57_row(im, r);
-		y_recons_quant_row(im, r, ratio, 0);
-	});
+	run_groups(c, "y_recons0_quant", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { recons_quant_group(im, r, g, ratio, 0); });
 	run_wavefront(c, "y_recons0_shrink", b, n, wf_shrink_geom(),
 	              [=] __device__(const EncImg &im, int r, int j) { return wf_shrink_cell(im, r, j); });
 	idwt_luma256(c, b, n);
 	if (q > 21) NHW_LAUNCH_L(c, "y_hq_first_order", k_hq_first_order, dim3(8, 8, n), 256, 0, b);
 
 	// ---- level-1 thresholds, pattern tags, residual side channels (nhw_encoder.c:783-1887)
-	run_rows(c, "y_e14_e15_tags", b, n, 512, [=] __device__(const EncImg &im, int r) {
-		if (r >= 256) y_e14_threshold_row(im, q, ratio, r);
-		y_e15_tags_row(im, r);
-	});
+	run_groups_inplace(c, "y_e14_e15_tags", b, n, 512, 6, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_e14_e15_cells(im.proc + r * YW, r, g, q, ratio, o); });
 	NHW_LAUNCH_L(c, "y_e16_residual", k_e16_residual, n, 256, 0, b, q);
 	if (getenv("NHW_E16B_ROWS"))
 		run_rows(c, "y_e16b_classify", b, n, 256, [=] __device__(const EncImg &im, int j) { int w1 = 0, w3 = 0, w5 = 0; y_e16b_classify_col(im, q, j, w1, w3, w5); });
@@ -1263,12 +1338,11 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
 	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(256, n), 128, 0, b);
-	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_cells, dim3(764, n), 256, 0, b, q, ratio);
-	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_commit, dim3(764, n), 256, 0, b, q, ratio);
-	run_rows(c, "y_offset_mult8", b, n, 512, [=] __device__(const EncImg &im, int r) { y_offset_mult8_row(im, r); });
+	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_bands, dim3(3, n), 256, 0, b, q, ratio);
+	run_groups_inplace(c, "y_offset_mult8", b, n, 512, 6, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_offset_mult8_cells(im.proc, r, g, o); });
 	run_wavefront(c, "y_offset_patterns", b, n, wf_offset_patterns_geom(),
 	              [=] __device__(const EncImg &im, int r, int j) { return wf_offset_patterns_cell(im, r, j); });
-	run_rows(c, "y_offset_pairs57", b, n, 256, [=] __device__(const EncImg &im, int r) { y_offset_pairs57_row(im, r); });
+	run_groups_inplace(c, "y_offset_pairs57", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_offset_pairs57_cells(im.proc, r, g, o); });
 	NHW_LAUNCH_L(c, "y_quant_scan", k_y_quant_scan, dim3(32, n), 256, 0, b, ratio);
 	if (q > 21) {   // res6 / char_res1 / high_qsetting3 from the quantised LH1 bytes, before the peephole edits them
 		NHW_LAUNCH_L(c, "y_hq_band", k_hq_band, dim3(256, n), 256, 0, b);
@@ -1278,17 +1352,23 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 262144 / 8, b);
 
 	// ---- chroma, U and V planes side by side (nhw_encoder.c:2255-2868)
-	run_plane_rows(c, "c_recons1", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
-		if (r < 64) c_recons_ll_row(im, r, 1);
-		c_recons_quant_row(im, r, ratio, 1);
+	run_plane_groups(c, "c_recons1", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int) {
+		int o[8];
+		c_recons_cells(im.cproc + r * CW, r, g, ratio, 1, o);
+		st8(im.cjpeg + r * CW + g * 8, o);
 	});
 	idwt_chroma128(c, b, n);
-	run_plane_rows(c, "c_correct", b, n, 128, [=] __device__(const EncImg &im, int r, int v) { c_correct_row(im, r, v); });
+	run_plane_groups(c, "c_correct", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int v) {
+		int o[8];
+		c_correct_cells(im.cproc + r * CW, im.cll1 + r * 128, g, v, o);
+		st8(im.cjpeg + r * CW + g * 8, o);
+	});
 	dwt_level_from_jpeg(c, 2 * n, b.c_jpeg, CS, b.c_proc, CS, 128, 256);
 	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_proc, CS, 256, b.c_ll2s, QS, 128, 128);
-	run_plane_rows(c, "c_recons0", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
-		if (r < 64) c_recons_ll_row(im, r, 0);
-		c_recons_quant_row(im, r, ratio, 0);
+	run_plane_groups(c, "c_recons0", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int) {
+		int o[8];
+		c_recons_cells(im.cproc + r * CW, r, g, ratio, 0, o);
+		st8(im.cjpeg + r * CW + g * 8, o);
 	});
 	idwt_chroma128(c, b, n);
 	run_plane_rows(c, "c_residual_tags", b, n, 128, [=] __device__(const EncImg &im, int r, int) { c_residual_tags_row(im, q, r); });

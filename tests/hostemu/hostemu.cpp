@@ -14,7 +14,7 @@
 
 #include "../../nhwcodec_b200/csrc/dec_par.cuh"
 #include "../../nhwcodec_b200/csrc/dec_parse.h"
-#include "../../nhwcodec_b200/csrc/enc_point.cuh"
+#include "../../nhwcodec_b200/csrc/enc_cells.cuh"
 
 namespace {
 
@@ -236,6 +236,40 @@ int host_entropy(const EncImg &im, int part, int &word0)
 	pack_codebook(im, st, part, k);
 	if (!part) s[262144] = saved;
 	return 0;
+}
+
+// the k_groups_inplace schedule: every group computed from the plane as it was before the stage
+template <typename F>
+static void host_groups_inplace(const EncImg &im, int rows, int gpr, F f)
+{
+	std::vector<int16_t> before(im.proc - 4096, im.proc + 512 * 512 + 4096);
+	const int16_t *B = before.data() + 4096;
+	for (int r = rows - 1; r >= 0; r--)
+		for (int g = gpr - 1; g >= 0; g--) {
+			int o[8];
+			if (f(B, r, g, o)) for (int x = 0; x < 8; x++) im.proc[r * 512 + g * 8 + x] = (int16_t)o[x];
+		}
+}
+
+// the cell form of the dead-zone quantiser: the band is read only, im_jpeg gets the written cells
+static void host_recons_quant_cells(const EncImg &im, int m1, int part)
+{
+	for (int r = 255; r >= 0; r--)
+		for (int g = 31; g >= 0; g--) {
+			int o[8];
+			const int mask = y_recons_quant_cells(im.proc + r * 512, r, g, m1, part, o);
+			for (int x = 0; x < 8; x++) if (mask >> x & 1) im.jpeg[r * 512 + g * 8 + x] = (int16_t)o[x];
+		}
+}
+
+static void host_c_recons_cells(const EncImg &im, int m1, int comp)
+{
+	for (int r = 127; r >= 0; r--)
+		for (int g = 15; g >= 0; g--) {
+			int o[8];
+			c_recons_cells(im.cproc + r * 256, r, g, m1, comp, o);
+			for (int x = 0; x < 8; x++) im.cjpeg[r * 256 + g * 8 + x] = (int16_t)o[x];
+		}
 }
 
 // the CUDA wavefront schedule, run sequentially: step t lets row ri handle column t - skew*ri;
@@ -471,16 +505,19 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	fwd_level(im.proc, 512, true, im.proc, 512, 256, tmp);
 	T("y_dwt2_proc", im.proc, 512 * 512 * 2);
 	T("y_ll1", im.ll1, 65536 * 2);
-	for (int r = 255; r >= 0; r--) y_e6a_tag_row(im, r);
+	if (getenv("HE_ROWFORM")) { for (int r = 255; r >= 0; r--) y_e6a_tag_row(im, r); }
+	else for (int r = 255; r >= 0; r--) for (int g = 31; g >= 0; g--) y_e6a_tag_cells(im.proc, im.ll1 + r * 256, r, g);
 	T("y_e6a_ll1", im.ll1, 65536 * 2);
 	host_recons_ll2(im, q, 1);
 	for (int reg = 0; reg < 2; reg++)
 		host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
-	for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 1);
+	if (getenv("HE_ROWFORM")) { for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 1); }
+	else host_recons_quant_cells(im, ratio, 1);
 	T("y_rec1_jpeg", im.jpeg, 512 * 512 * 2);
 	inv_level(im.jpeg, im.proc, 512, 256, tmp);
 	T("y_syn1_proc", im.proc, 512 * 512 * 2);
-	for (int r = 255; r >= 0; r--) y_e6c_apply_row(im, r);
+	if (getenv("HE_ROWFORM")) { for (int r = 255; r >= 0; r--) y_e6c_apply_row(im, r); }
+	else for (int r = 255; r >= 0; r--) for (int g = 31; g >= 0; g--) y_e6c_apply_cells(im.proc, im.ll1 + r * 256, r, g);
 	T("y_e6c_proc", im.proc, 512 * 512 * 2);
 	T("y_e6c_ll1", im.ll1, 65536 * 2);
 	if (getenv("HE_SERIAL")) { for (int r = 255; r >= 0; r--) y_e6d_correct_row(im, r); }
@@ -490,10 +527,19 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 			int16_t *P = im.proc + r * 512, *J = im.jpeg + r * 512;
 			const int16_t *L = im.ll1 + r * 256;
 			for (int j = -1; j <= 256; j++) sc[j + 2] = (int16_t)(P[j] - L[j]);
-			for (int j = 255; j >= 0; j--) {
-				const int d = e6d_delta_at(&sc[2], j);
-				J[j] = (int16_t)(L[j] + d);
-				P[j] = (int16_t)(P[j] + d);
+			if (getenv("HE_E6D_CELL")) {
+				for (int j = 255; j >= 0; j--) {
+					const int d = e6d_delta_at(&sc[2], j);
+					J[j] = (int16_t)(L[j] + d);
+					P[j] = (int16_t)(P[j] + d);
+				}
+			} else {
+				for (int g = 31; g >= 0; g--) {
+					int own[8], d[8];
+					for (int x = 0; x < 8; x++) own[x] = sc[2 + g * 8 + x];
+					e6d_delta_cells(&sc[2], g * 8, own, d);
+					for (int x = 0; x < 8; x++) { J[g * 8 + x] = (int16_t)(L[g * 8 + x] + d[x]); P[g * 8 + x] = (int16_t)(P[g * 8 + x] + d[x]); }
+				}
 			}
 		}
 	}
@@ -512,8 +558,10 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	host_recons_ll2(im, q, 0);
 	for (int reg = 0; reg < 2; reg++)
 		host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
-	for (int r = 255; r >= 0; r--) y_recons_tag57_row(im, r);
-	for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 0);
+	if (getenv("HE_ROWFORM")) {
+		for (int r = 255; r >= 0; r--) y_recons_tag57_row(im, r);
+		for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 0);
+	} else host_recons_quant_cells(im, ratio, 0);
 	host_wavefront(wf_shrink_geom(), [&](int r, int j) { return wf_shrink_cell(im, r, j); });
 	T("y_rec0_jpeg", im.jpeg, 512 * 512 * 2);
 	inv_level(im.jpeg, im.proc, 512, 256, tmp);
@@ -523,9 +571,11 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 			for (int j = 0; j < 256; j++) im.hq_fo[r * 256 + j] = im.proc[j * 512 + r];   // the reference copies its transposed work plane
 		T("y_hq_fo0", im.hq_fo, 65536 * 2);
 	}
-	for (int r = 511; r >= 256; r--) y_e14_threshold_row(im, q, ratio, r);
-	T("y_e14_proc", im.proc, 512 * 512 * 2);
-	for (int r = 510; r >= 1; r--) y_e15_tags_row(im, r);
+	if (getenv("HE_ROWFORM")) {
+		for (int r = 511; r >= 256; r--) y_e14_threshold_row(im, q, ratio, r);
+		T("y_e14_proc", im.proc, 512 * 512 * 2);
+		for (int r = 510; r >= 1; r--) y_e15_tags_row(im, r);
+	} else host_groups_inplace(im, 512, 64, [&](const int16_t *B, int r, int g, int *o) { return y_e14_e15_cells(B + r * 512, r, g, q, ratio, o); });
 	T("y_e15_proc", im.proc, 512 * 512 * 2);
 	host_e16(im, q);
 	T("y_e16_proc", im.proc, 512 * 512 * 2);
@@ -548,13 +598,15 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		for (int pass = 2; pass >= 0; pass--) {
 			const E20Pass g = e20_pass(q, ratio, pass);
 			for (int r = g.r1 - 1; r >= g.r0; r--)
-				for (int j = g.j1; j >= g.j0; j--) im.proc[r * 512 + j] = (int16_t)e20_final_cell(B, g, r, j);
+				for (int j = g.j1; j >= g.j0; j--) im.proc[r * 512 + j] = (int16_t)e20_final_cell(B + r * 512, 512, g, r, j);
 		}
 	}
 	T("y_e20_proc", im.proc, 512 * 512 * 2);
-	for (int r = 511; r >= 0; r--) y_offset_mult8_row(im, r);
+	if (getenv("HE_ROWFORM")) { for (int r = 511; r >= 0; r--) y_offset_mult8_row(im, r); }
+	else host_groups_inplace(im, 512, 64, [&](const int16_t *B, int r, int g, int *o) { return y_offset_mult8_cells(B, r, g, o); });
 	host_wavefront(wf_offset_patterns_geom(), [&](int r, int j) { return wf_offset_patterns_cell(im, r, j); });
-	for (int r = 255; r >= 0; r--) y_offset_pairs57_row(im, r);
+	if (getenv("HE_ROWFORM")) { for (int r = 255; r >= 0; r--) y_offset_pairs57_row(im, r); }
+	else host_groups_inplace(im, 256, 32, [&](const int16_t *B, int r, int g, int *o) { return y_offset_pairs57_cells(B, r, g, o); });
 	if (getenv("HE_ROWFORM")) {
 		std::vector<int> next0(512);
 		for (int r = 0; r < 512; r++) next0[r] = r < 511 ? im.proc[(r + 1) * 512] : 0;
@@ -594,18 +646,27 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		fwd_level(im.cproc, 256, true, im.cproc, 256, 128, tmp);
 		TN("dwt2_proc", im.cproc, 65536 * 2);
 		TN("ll1", im.cll1, 16384 * 2);
-		for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 1);
-		for (int r = 127; r >= 0; r--) c_recons_quant_row(im, r, ratio, 1);
+		if (getenv("HE_ROWFORM")) {
+			for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 1);
+			for (int r = 127; r >= 0; r--) c_recons_quant_row(im, r, ratio, 1);
+		} else host_c_recons_cells(im, ratio, 1);
 		TN("rec1_jpeg", im.cjpeg, 65536 * 2);
 		inv_level(im.cjpeg, im.cproc, 256, 128, tmp);
 		TN("syn1_proc", im.cproc, 65536 * 2);
-		for (int r = 127; r >= 0; r--) c_correct_row(im, r, v);
+		if (getenv("HE_ROWFORM")) { for (int r = 127; r >= 0; r--) c_correct_row(im, r, v); }
+		else for (int r = 127; r >= 0; r--) for (int g = 15; g >= 0; g--) {
+			int o[8];
+			c_correct_cells(im.cproc + r * 256, im.cll1 + r * 128, g, v, o);
+			for (int x = 0; x < 8; x++) im.cjpeg[r * 256 + g * 8 + x] = (int16_t)o[x];
+		}
 		TN("corr_jpeg", im.cjpeg, 65536 * 2);
 		fwd_level(im.cjpeg, 256, false, im.cproc, 256, 128, tmp);
 		TN("dwt2b_proc", im.cproc, 65536 * 2);
 		copy_region(im.cll2s, 128, im.cproc, 256, 128);
-		for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 0);
-		for (int r = 127; r >= 0; r--) c_recons_quant_row(im, r, ratio, 0);
+		if (getenv("HE_ROWFORM")) {
+			for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 0);
+			for (int r = 127; r >= 0; r--) c_recons_quant_row(im, r, ratio, 0);
+		} else host_c_recons_cells(im, ratio, 0);
 		inv_level(im.cjpeg, im.cproc, 256, 128, tmp);
 		TN("syn0_proc", im.cproc, 65536 * 2);
 		for (int r = 127; r >= 0; r--) c_residual_tags_row(im, q, r);
