@@ -11,6 +11,7 @@
 // ahead of the row below by two cells (two pairs for D11) and no more.
 #pragma once
 #include "dec_stages.cuh"
+#include "cells8.cuh"
 
 // D8: cell (r, j), 1 <= r, j <= 254, of the level-2 region of J (stride 512)
 NHW_HD WfGeom dwf_shrink_geom() { return WfGeom{1, 254, 1, 254, 2}; }

@@ -196,6 +196,16 @@ void d_wavefront(nhw_ctx *c, const char *l, const DecBatch &b, int n, int ppi, W
 	NHW_LAUNCH_L(c, l, kd_wavefront, n * ppi, 256, 0, b, g, ppi, cell);
 }
 
+// ---- D8: isolated-coefficient shrink of the level-2 region, order-free form (cells8.cuh: shrink_cells8)
+__global__ void __launch_bounds__(256) kd_shrink_y(DecBatch b)
+{
+	if (b.status[blockIdx.y] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.y, 0);
+	const int idx = blockIdx.x * 256 + threadIdx.x, r = idx >> 5, g = idx & 31;
+	int o[8];
+	if (shrink_cells8(im.jpeg, r, g, 9, o)) st8(im.jpeg + r * YW + g * 8, o);
+}
+
 // ---- D4: marker expansion + right-half nudges in parallel form (dec_par.cuh).  One CTA per image.
 // Sweep rows ("slots"): 0..255 = rows 0..255 (all 512 columns), 256..511 = rows 256..511 left half,
 // 512..767 = rows 256..511 right half.  Candidates are compacted in sweep order (count, prefix, write),
@@ -493,7 +503,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH_L(c, "d_descan_y", kd_descan_y, dim3(512, n), 128, 0, b);
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
-	d_wavefront(c, "d_shrink_y", b, n, 1, dwf_shrink_geom(), [=] __device__(const DecImg &im, int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
+	NHW_LAUNCH_L(c, "d_shrink_y", kd_shrink_y, dim3(32, n), 256, 0, b);
 	idwt_rows_cols(c, n, b.y_jpeg, b.y_aux, b.y_proc, YS, 256, 512);
 	NHW_LAUNCH_L(c, "d_addbacks", kd_addbacks, n, 256, 0, b);
 	d_wavefront(c, "d_edge_flags", b, n, 1, dwf_edge_geom(), [=] __device__(const DecImg &im, int r, int p) { return dwf_edge_cell(im.proc, r, p); });

@@ -5,32 +5,7 @@
 // functions against the reference's taps.
 #pragma once
 #include "enc_point.cuh"
-
-NHW_HD void ld8(const int16_t *p, int *v)
-{
-#ifdef __CUDA_ARCH__
-	const uint4 w = *reinterpret_cast<const uint4 *>(p);
-	v[0] = (int16_t)(w.x & 0xffff); v[1] = (int16_t)(w.x >> 16);
-	v[2] = (int16_t)(w.y & 0xffff); v[3] = (int16_t)(w.y >> 16);
-	v[4] = (int16_t)(w.z & 0xffff); v[5] = (int16_t)(w.z >> 16);
-	v[6] = (int16_t)(w.w & 0xffff); v[7] = (int16_t)(w.w >> 16);
-#else
-	for (int k = 0; k < 8; k++) v[k] = p[k];
-#endif
-}
-NHW_HD void st8(int16_t *p, const int *v)
-{
-#ifdef __CUDA_ARCH__
-	uint4 w;
-	w.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
-	w.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
-	w.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
-	w.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
-	*reinterpret_cast<uint4 *>(p) = w;
-#else
-	for (int k = 0; k < 8; k++) p[k] = (int16_t)v[k];
-#endif
-}
+#include "cells8.cuh"
 
 // ---- E6a (nhw_encoder.c:144-177; row form y_e6a_tag_row): reads the level-2 detail cell and two diagonal
 // neighbours, adds a tag to the LL1 copy.  Pointwise as written.  Returns whether L changed.
@@ -184,55 +159,86 @@ NHW_HD int recons_tag57_at(const int16_t *R /* row */, int j, int jr0)
 // rewrite the NEXT cell (-7 -> -8, 7 -> 8) before that cell's turn.  Two facts bound the history a cell depends on:
 //   * a cell is visited whenever the two cells before it hold no tag (whatever skipped them ends before it);
 //   * a rewritten cell only ever passes on one more rewrite (a 7 turned 8 can turn the next -7 into -8; a -8 does
-//     nothing), so an unknown state dies out within two cells.
-// So the cursor is re-started behind six tag-free cells (or at the start of the row) and the loop is replayed from
-// there on private state; only im_jpeg is written (the in-place edits of the band are dead: both callers rebuild
-// the region afterwards).  o[k] / bit k of the result = value / "written" for the 8 cells of the group.
+//     nothing), and a cell that rewrites a 7 is > 12, i.e. not rewritten itself.
+// So behind four tag-free cells k..k+3 the loop can be re-started at k+2 and is exact from k+4 on; it is replayed
+// from there (or from the start of the row) on private state up to the group, then run over the group.  Only
+// im_jpeg is written (the in-place edits of the band are dead: both callers rebuild the region afterwards).
+// o[k] / bit k of the result = value / "written" for the 8 cells of the group.
 #define RQ_NONE 0x40000000
 NHW_HD int rq_val(const int16_t *R, int j, int jr0, int part) { return part ? (int)R[j] : recons_tag57_at(R, j, jr0); }
+// one turn: a = the cell (with a pending rewrite applied), nx = the next cell or RQ_NONE at the end of the row.
+// Returns the cursor step; out / out_next = values for im_jpeg (RQ_NONE: not written), pend = rewrite of the next cell
+NHW_HD int rq_turn(int a, int nx, int m1, int part, int &out, int &out_next, int &pend)
+{
+	out = RQ_NONE; out_next = RQ_NONE; pend = RQ_NONE;
+	if (a > 15000) {
+		if (a == 15300) { out = 5; return 3; }
+		if (a == 15400) { out = -5; return 3; }
+		if (a == 15500) { out = 5; return 2; }
+		if (a == 15600) { out = -5; return 2; }
+		if (a == 15700) { out = 6; out_next = 6; return 2; }
+		if (a == 15800) { out = -6; out_next = -6; return 2; }
+		return 1;
+	}
+	if (a < -12 && ((-a) & 7) == 6) { if (nx == -7) pend = -8; }
+	if (a < 0) {
+		if (a == -7 && nx == 8) a = -8;
+		a = -a;
+		if ((a & 7) < 7) a &= 65528;
+		a = -a;
+	} else if (a == 8 && nx == -7) pend = -8;
+	else if (a > 12 && !part && (a & 7) >= 6) { if (nx == 7) pend = 8; }
+	if (a < m1 && a > -m1) out = 0;
+	else {
+		a += 128;
+		if (a < 0) a = -((-a) & 65528);
+		else a &= 65528;
+		out = a > 128 ? a - 125 : a - 131;
+	}
+	return 1;
+}
 NHW_HD int y_recons_quant_cells(const int16_t *R /* band row, before the stage */, int r, int g, int m1, int part, int *o)
 {
 	const int c = g * 8, jr0 = r < 128 ? 128 : 0;
 	if (c < jr0) return 0;
-	int st = c, clean = 0;
-	while (st > jr0) {
-		st--;
-		clean = rq_val(R, st, jr0, part) > 15000 ? 0 : clean + 1;
-		if (clean == 6) { st += 2; break; }
-	}
-	int mask = 0, pend = RQ_NONE;
-	for (int j = st; j < c + 8;) {
-		int a = pend != RQ_NONE ? pend : rq_val(R, j, jr0, part);
-		pend = RQ_NONE;
-		int out = RQ_NONE, out_next = RQ_NONE, step = 1;
-		if (a > 15000) {
-			if (a == 15300) { out = 5; step = 3; }
-			else if (a == 15400) { out = -5; step = 3; }
-			else if (a == 15500) { out = 5; step = 2; }
-			else if (a == 15600) { out = -5; step = 2; }
-			else if (a == 15700) { out = 6; out_next = 6; step = 2; }
-			else if (a == 15800) { out = -6; out_next = -6; step = 2; }
-		} else {
-			const int nx = j < 255 ? rq_val(R, j + 1, jr0, part) : RQ_NONE;
-			if (a < -12 && ((-a) & 7) == 6) { if (nx == -7) pend = -8; }
-			if (a < 0) {
-				if (a == -7 && nx == 8) a = -8;
-				a = -a;
-				if ((a & 7) < 7) a &= 65528;
-				a = -a;
-			} else if (a == 8 && nx == -7) pend = -8;
-			else if (a > 12 && !part && (a & 7) >= 6) { if (nx == 7) pend = 8; }
-			if (a < m1 && a > -m1) out = 0;
-			else {
-				a += 128;
-				if (a < 0) a = -((-a) & 65528);
-				else a &= 65528;
-				out = a > 128 ? a - 125 : a - 131;
-			}
+	// the group's cells (and the two after it) as this call sees them
+	int v[10], T[9];
+	ld8(R + c, v);
+	v[8] = R[c + 8]; v[9] = R[c + 9];
+	if (part) { for (int k = 0; k < 9; k++) T[k] = v[k]; }
+	else {
+		int cls_prev = 0, par = 0;
+		const int cl0 = pairs57_class(v[0]);
+		if (cl0) for (int s = c; s > jr0 && pairs57_class(R[s - 1]) == cl0; s--) par ^= 1;
+		for (int k = 0; k < 9; k++) {
+			const int cl = pairs57_class(v[k]);
+			if (k) par = (cl && cl == cls_prev) ? par ^ 1 : 0;
+			cls_prev = cl;
+			T[k] = (cl && c + k < 255 && pairs57_class(v[k + 1]) == cl && !par) ? (cl == 1 ? 15700 : 15800) : v[k];
 		}
-		if (j >= c && out != RQ_NONE) { o[j - c] = out; mask |= 1 << (j - c); }
-		if (j + 1 >= c && j + 1 < c + 8 && out_next != RQ_NONE) { o[j + 1 - c] = out_next; mask |= 1 << (j + 1 - c); }
+	}
+	// replay up to the group
+	int j = c, clean = 0;
+	while (j > jr0) {
+		j--;
+		clean = rq_val(R, j, jr0, part) > 15000 ? 0 : clean + 1;
+		if (clean == 4) { j += 2; break; }
+	}
+	int mask = 0, pend = RQ_NONE, out, out_next;
+	while (j < c) {
+		const int a = pend != RQ_NONE ? pend : rq_val(R, j, jr0, part);
+		const int nx = j + 1 < c ? rq_val(R, j + 1, jr0, part) : T[0];
+		const int step = rq_turn(a, nx, m1, part, out, out_next, pend);
+		if (j + 1 == c && out_next != RQ_NONE) { o[0] = out_next; mask |= 1; }
 		j += step;
+	}
+	for (int k = 0; k < 8; k++) {
+		if (j != c + k) continue;
+		const int a = pend != RQ_NONE ? pend : T[k];
+		const int nx = c + k < 255 ? T[k + 1] : RQ_NONE;
+		j += rq_turn(a, nx, m1, part, out, out_next, pend);
+		if (out != RQ_NONE) { o[k] = out; mask |= 1 << k; }
+		if (k < 7 && out_next != RQ_NONE) { o[k + 1] = out_next; mask |= 2 << k; }
 	}
 	return mask;
 }
@@ -251,50 +257,59 @@ NHW_HD int e14_value(int v, int q, int ratio, int r, int j)
 	return v;
 }
 NHW_HD bool e15_active(int v) { const int a = nhw_iabs(v); return a >= 4 && a <= 8; }
+NHW_HD void e15_turn(int &prev, int &cur, int &nx, bool band_a)
+{
+	const int v = cur;
+	if (v > 4 && v < 8) {
+		if (in4to7(prev) && in4to7(nx)) { cur = 12700; prev = 10100; nx = 10100; }
+	} else if (v < -4 && v > -8) {
+		if (in_m7to_m4(prev) && in_m7to_m4(nx)) { cur = 12900; prev = 10100; nx = 10100; }
+	} else if (v == 8) {
+		if ((prev & 65534) == 6 || (nx & 65534) == 6) cur = 10;
+		else if (band_a && nx == 8) { cur = 9; nx = 9; }
+	} else if (v == -8) {
+		if (((-prev) & 65534) == 6 || ((-nx) & 65534) == 6) cur = -9;
+		else if (band_a && nx == -8) { cur = -9; nx = -9; }
+	}
+}
 NHW_HD bool y_e14_e15_cells(const int16_t *R /* row r */, int r, int g, int q, int ratio, int *o)
 {
 	const int c = g * 8;
-	int raw[8];
+	int raw[8], w[11];   // w[i] = current value of column c - 1 + i
 	ld8(R + c, raw);
 	bool changed = false, any_active = false;
 	for (int k = 0; k < 8; k++) {
-		o[k] = e14_value(raw[k], q, ratio, r, c + k);
-		changed |= o[k] != raw[k];
-		any_active |= e15_active(o[k]);
+		w[k + 1] = e14_value(raw[k], q, ratio, r, c + k);
+		any_active |= e15_active(w[k + 1]);
 	}
-	int j0, j1;
-	bool band_a;
+	int j0 = 0, j1 = 0;
+	bool band_a = false;
 	if (r >= 1 && r <= 254) { j0 = 257; j1 = 511; band_a = true; }
-	else if (r >= 257 && r <= 510) { j0 = 1; j1 = 255; band_a = false; }
-	else return changed;
-	if (c + 7 < j0 - 1 || c > j1) return changed;
-	// a rewrite of a group cell needs that cell, or (for the +-9 pair rule) nothing else, to be active
-	if (!any_active) return changed;
-	int s = c > j0 ? c : j0;
-	while (s > j0 && e15_active(e14_value(R[s - 1], q, ratio, r, s - 1))) s--;
-	int prev = e14_value(R[s - 1], q, ratio, r, s - 1), cur = e14_value(R[s], q, ratio, r, s);
-	const int last = c + 8 < j1 - 1 ? c + 8 : j1 - 1;
-	for (int j = s; j <= last; j++) {
-		const int nx = e14_value(R[j + 1], q, ratio, r, j + 1);
-		int nx_new = nx;
-		const int v = cur;
-		if (v > 4 && v < 8) {
-			if (in4to7(prev) && in4to7(nx)) { cur = 12700; prev = 10100; nx_new = 10100; }
-		} else if (v < -4 && v > -8) {
-			if (in_m7to_m4(prev) && in_m7to_m4(nx)) { cur = 12900; prev = 10100; nx_new = 10100; }
-		} else if (v == 8) {
-			if ((prev & 65534) == 6 || (nx & 65534) == 6) cur = 10;
-			else if (band_a && nx == 8) { cur = 9; nx_new = 9; }
-		} else if (v == -8) {
-			if (((-prev) & 65534) == 6 || ((-nx) & 65534) == 6) cur = -9;
-			else if (band_a && nx == -8) { cur = -9; nx_new = -9; }
+	else if (r >= 257 && r <= 510) { j0 = 1; j1 = 255; }
+	// a cell that gets rewritten is itself in +-4..+-8
+	if (any_active && j1 && c + 7 >= j0 - 1 && c <= j1) {
+		w[0] = c > 0 ? e14_value(R[c - 1], q, ratio, r, c - 1) : 0;
+		w[9] = e14_value(R[c + 8], q, ratio, r, c + 8);
+		w[10] = e14_value(R[c + 9], q, ratio, r, c + 9);
+		if (c > j0 && e15_active(w[0])) {   // replay the turns between the last inactive cell and the group
+			int s = c - 1;
+			while (s > j0 && e15_active(e14_value(R[s - 1], q, ratio, r, s - 1))) s--;
+			int prev = e14_value(R[s - 1], q, ratio, r, s - 1), cur = e14_value(R[s], q, ratio, r, s);
+			for (int j = s; j < c; j++) {
+				int nx = j + 1 < c ? e14_value(R[j + 1], q, ratio, r, j + 1) : w[1];
+				e15_turn(prev, cur, nx, band_a);
+				prev = cur;
+				cur = nx;
+			}
+			w[0] = prev;
+			w[1] = cur;
 		}
-		if (j - 1 >= c && j - 1 < c + 8 && o[j - 1 - c] != prev) { o[j - 1 - c] = prev; changed = true; }
-		if (j >= c && j < c + 8 && o[j - c] != cur) { o[j - c] = cur; changed = true; }
-		if (j + 1 >= c && j + 1 < c + 8 && o[j + 1 - c] != nx_new) { o[j + 1 - c] = nx_new; changed = true; }
-		prev = cur;
-		cur = nx_new;
+		for (int k = 0; k <= 8; k++) {
+			const int j = c + k;
+			if (j >= j0 && j < j1) e15_turn(w[k], w[k + 1], w[k + 2], band_a);
+		}
 	}
+	for (int k = 0; k < 8; k++) { o[k] = w[k + 1]; changed |= o[k] != raw[k]; }
 	return changed;
 }
 
@@ -369,3 +384,27 @@ NHW_HD void c_correct_cells(const int16_t *P /* cproc row */, const int16_t *L /
 		o[k] = l[k] + d;
 	}
 }
+
+// ---- E20 (enc_y2.cuh: e20_final_cell states the rule), 8 cells of a row: what the cells on the left pass into the
+// group is replayed once, then the group is walked left to right.  row / up / dn point at column 0 of the row, the
+// row above and the row below as they were before the stage; columns outside [j0, j1] keep their value.
+NHW_HD void e20_cells8(const int16_t *up, const int16_t *row, const int16_t *dn, const E20Pass &g, int r, int c, int *o)
+{
+	int m[11], u[8], d[8];   // m[i] = column c - 1 + i
+	ld8(row + c, m + 1);
+	ld8(up + c, u);
+	ld8(dn + c, d);
+	m[0] = row[c - 1]; m[9] = row[c + 8]; m[10] = row[c + 9];
+	int give = e20_give_into(row, (int)(dn - row), g, r, c);
+	for (int k = 0; k < 8; k++) {
+		const int j = c + k;
+		int in = m[k + 1];
+		if (j < g.j0 || j > g.j1) { o[k] = in; give = 0; continue; }
+		if (give == 100) in = -8;
+		else in += give;
+		if (j == g.j1) { o[k] = in; give = 0; }
+		else o[k] = e20_turn_v(g, r, j, m[k], in, m[k + 2], m[k + 3], u[k], d[k], give);
+	}
+}
+// the cell just right of the group (only needed where that is column j1 = 256 of pass 1)
+NHW_HD int e20_edge_cell(const int16_t *row, int S, const E20Pass &g, int r) { return e20_final_cell(row, S, g, r, g.j1); }

@@ -431,16 +431,16 @@ NHW_HD E20Pass e20_pass(int q, int ratio, int pass)
 NHW_HD bool e20_can_receive(int v) { return v > 7 || v == -7 || v < -14; }
 // one cell's turn: v = its value when its turn comes (original + what the left neighbour did to it); returns its
 // final value and, in `give`, what it does to the cell on its right (0 none, -1, +1, or 100 = "becomes -8")
-// `row` points at column 0 of row r (of the plane, stride S = YW, or of a staged copy of it with its own stride)
-NHW_HD int e20_turn(const int16_t *row, int S, const E20Pass &g, int r, int j, int v, int &give)
+// the values version: left / n1 / n2 = the cells at j-1, j+1, j+2, up / dn = above and below, all as before the stage
+NHW_HD int e20_turn_v(const E20Pass &g, int r, int j, int left, int v, int n1, int n2, int up, int dn, int &give)
 {
 	if (nhw_iabs(v) >= g.lo) {
 		if (nhw_iabs(v) < g.yw2) {
 			int cnt = 0;
-			if (nhw_iabs(row[j - 1]) >= (j > g.j0 ? g.lo : 6)) cnt++;     // visited neighbours survive only from lo up
-			if (nhw_iabs(row[j + 1]) >= 6) cnt++;
-			if (nhw_iabs(row[j - S]) >= (r > g.r0 ? g.lo : 6)) cnt++;
-			if (nhw_iabs(row[j + S]) >= 6) cnt++;
+			if (nhw_iabs(left) >= (j > g.j0 ? g.lo : 6)) cnt++;     // visited neighbours survive only from lo up
+			if (nhw_iabs(n1) >= 6) cnt++;
+			if (nhw_iabs(up) >= (r > g.r0 ? g.lo : 6)) cnt++;
+			if (nhw_iabs(dn) >= 6) cnt++;
 			if (cnt < 3 && v < g.yw && v > -g.yw) {
 				if (g.pass == 0) { if (v < -6) v = -7; else if (v > 6) v = 7; }
 				else v = v < 0 ? -7 : 7;
@@ -449,7 +449,7 @@ NHW_HD int e20_turn(const int16_t *row, int S, const E20Pass &g, int r, int j, i
 	} else v = 0;
 	give = 0;
 	if (nhw_iabs(v) > 6) {
-		const int e = v, n1 = row[j + 1];
+		const int e = v;
 		if (e >= 8 && (e & 7) < 2) {
 			if (n1 > 7 && n1 < 10000) give = -1;
 		} else if (e == -7 && n1 == 8) v = -8;
@@ -457,11 +457,31 @@ NHW_HD int e20_turn(const int16_t *row, int S, const E20Pass &g, int r, int j, i
 		else if (e < -7 && ((-e) & 7) < 2) {
 			if (n1 < -14 && n1 < 10000) {
 				if (((-n1) & 7) == 7) give = 1;
-				else if (((-n1) & 7) < 2 && j < g.jmax && row[j + 2] <= 0) give = 1;
+				else if (((-n1) & 7) < 2 && j < g.jmax && n2 <= 0) give = 1;
 			}
 		}
 	}
 	return v;
+}
+// `row` points at column 0 of row r (of the plane, stride S = YW, or of a staged copy of it with its own stride)
+NHW_HD int e20_turn(const int16_t *row, int S, const E20Pass &g, int r, int j, int v, int &give)
+{
+	return e20_turn_v(g, r, j, row[j - 1], v, row[j + 1], row[j + 2], row[j - S], row[j + S], give);
+}
+// what the cells on the left of column c pass into it (0 none, -1, +1, 100 = "becomes -8")
+NHW_HD int e20_give_into(const int16_t *row, int S, const E20Pass &g, int r, int c)
+{
+	if (c <= g.j0 || !e20_can_receive(row[c])) return 0;
+	int start = c - 1;
+	while (start > g.j0 && e20_can_receive(row[start])) start--;
+	int give = 0;
+	for (int x = start; x < c; x++) {
+		int in = row[x];
+		if (give == 100) in = -8;
+		else in += give;
+		e20_turn(row, S, g, r, x, in, give);
+	}
+	return give;
 }
 // j in [j0, j1]: column j1 is outside the region (it has no turn) but still receives from the last cell of the row
 NHW_HD int e20_final_cell(const int16_t *row, int S, const E20Pass &g, int r, int j)

@@ -587,6 +587,36 @@ __global__ void __launch_bounds__(32) k_e18_tails(EncBatch b, int q)
 	y_e18_finish_list_image(lm, which, e + 256, e);
 }
 
+// ---- E6c (enc_cells.cuh: y_e6c_apply_cells states the rule): un-tag LL1, push +-1 into the trial reconstruction at
+// the transposed position.  A CTA takes a 32 x 32 tile of LL1: tags are read (and cleared) row-wise, the +-1 go
+// through shared memory and are applied column-wise, so that a warp's 32 targets lie in one 128-byte span.
+__global__ void __launch_bounds__(256) k_e6c_apply(EncBatch b)
+{
+	__shared__ int8_t dt[32][33];
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	const int r0 = (blockIdx.x >> 3) * 32, j0 = (blockIdx.x & 7) * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const int rr = ty + 8 * i;
+		int16_t *L = im.ll1 + (r0 + rr) * 256 + j0 + tx;
+		const int l = *L;
+		int d = 0;
+		if (l > 14000) { *L = (int16_t)(l - 16000); d = 1; }
+		else if (l > 10000) { *L = (int16_t)(l - 12000); d = -1; }
+		dt[rr][tx] = (int8_t)d;
+	}
+	__syncthreads();
+	int16_t *P = im.proc;
+	#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const int jj = ty + 8 * i, d = dt[tx][jj], r = r0 + tx, j = j0 + jj;
+		if (!d) continue;
+		if (r < 128 && j >= 128) P[2 * r + ((j - 128) << 10) + YW] += d;
+		else if (r >= 128 && j < 128) P[2 * (r - 128) + (j << 10) + 1] += d;
+		else if (r >= 128 && j >= 128) P[2 * (r - 128) + ((j - 128) << 10) + YW + 1] += d;
+	}
+}
+
 // ---- E6d: LL1 correction (enc_cells.cuh: e6d_delta_cells), one thread per 8 cells; 8 rows per CTA
 __global__ void __launch_bounds__(256) k_e6d_correct(EncBatch b)
 {
@@ -612,62 +642,53 @@ __global__ void __launch_bounds__(256) k_e6d_correct(EncBatch b)
 	st8(P + j0, p);
 }
 
-// ---- E20: clean-up of the three level-1 bands, cell-parallel (enc_y2.cuh: e20_final_cell).  One CTA per (image,
-// pass) walks its region top-down in bands of 8 rows staged in shared memory: every final value is computed from
-// the rows as they were before the stage (the row above a band is kept from the previous band, the row below has
-// not been touched yet), then the band is written back in place.  Column 256 of rows 256..510 is written by pass 1
-// (it receives from column 255) and only read by pass 2, whose test on it has the same outcome either way: each
-// pass stores only its own columns.
+// ---- E20: clean-up of the three level-1 bands (enc_cells.cuh: e20_cells8).  One CTA per (image, pass) walks its
+// region top-down in bands of 8 rows staged in shared memory (two buffers in turn); a thread owns 8 cells of a row.
+// Every final value is computed from the rows as they were before the stage: the row above a band is copied from
+// the previous band's buffer, the row below has not been touched yet; results go straight back to the plane.
+// Column 256 of rows 256..510 is written by pass 1 (it receives from column 255) and only read by pass 2, whose
+// test on it has the same outcome either way: each pass stores only its own columns.
 #define E20_ROWS 8
-#define E20_TS 264   // 256 columns + column 256 for pass 1 (+ pad to keep rows 16-byte aligned)
+#define E20_TS 272   // 256 columns, column 256 (pass 1) and the two look-ahead cells behind the last group
 __global__ void __launch_bounds__(256) k_e20_bands(EncBatch b, int q, int ratio)
 {
-	__shared__ __align__(16) int16_t tile[E20_ROWS + 2][E20_TS];
-	__shared__ __align__(16) int16_t outv[E20_ROWS][256];
-	__shared__ int16_t out_edge[E20_ROWS];   // pass 1: column 256
+	__shared__ __align__(16) int16_t tile[2][E20_ROWS + 2][E20_TS];
 	const EncImg im = make_img(b, blockIdx.y, 0);
 	const E20Pass g = e20_pass(q, ratio, blockIdx.x);
-	const int cb = g.pass == 1 ? 0 : 256, tid = threadIdx.x;
+	const int cb = g.pass == 1 ? 0 : 256, tid = threadIdx.x, k = tid >> 5, c = (tid & 31) * 8;
 	int16_t *P = im.proc;
-	// row above the first band
-	tile[0][tid] = P[(g.r0 - 1) * YW + cb + tid];
-	if (g.pass == 1 && tid == 0) tile[0][256] = P[(g.r0 - 1) * YW + 256];
-	for (int r0 = g.r0; r0 < g.r1; r0 += E20_ROWS) {
-		{   // rows r0 .. r0+8 (the last one is the row below the band), 32 x 16 bytes each
-			const int k = tid >> 5, c = (tid & 31) * 8, r = r0 + k;
-			if (r <= 511) *reinterpret_cast<uint4 *>(&tile[1 + k][c]) = *reinterpret_cast<const uint4 *>(P + r * YW + cb + c);
-			if (tid < 32) {
-				const int r2 = r0 + E20_ROWS;
-				if (r2 <= 511) *reinterpret_cast<uint4 *>(&tile[1 + E20_ROWS][c]) = *reinterpret_cast<const uint4 *>(P + r2 * YW + cb + c);
-			} else if (g.pass == 1 && tid < 32 + E20_ROWS + 1) {
-				const int r2 = r0 + tid - 32;
-				if (r2 <= 511) tile[1 + tid - 32][256] = P[r2 * YW + 256];
-			}
-		}
-		__syncthreads();
-		#pragma unroll
-		for (int k = 0; k < E20_ROWS; k++) {
+	int buf = 0;
+	for (int r0 = g.r0; r0 < g.r1; r0 += E20_ROWS, buf ^= 1) {
+		int16_t (*T)[E20_TS] = tile[buf];
+		{   // rows r0-1 .. r0+8; the cells right of column 255 of the block only matter for pass 1 (column 256)
 			const int r = r0 + k;
-			if (r >= g.r1) break;
-			const int16_t *row = &tile[1 + k][0] - cb;
-			const int j = cb + tid;
-			if (j >= g.j0 && j <= g.j1) outv[k][tid] = (int16_t)e20_final_cell(row, E20_TS, g, r, j);
-			else if (g.pass == 1 && tid == 0) out_edge[k] = (int16_t)e20_final_cell(row, E20_TS, g, r, 256);
-		}
-		__syncthreads();
-		// keep the last row of the band as it was, then write the band back
-		tile[0][tid] = tile[E20_ROWS][tid];
-		if (g.pass == 1 && tid == 0) tile[0][256] = tile[E20_ROWS][256];
-		{
-			const int k = tid >> 5, c = (tid & 31) * 8, r = r0 + k;
-			if (r < g.r1) {
-				if (c == 0) {   // the first column of the block is not this pass's to write
-					for (int x = 1; x < 8; x++) P[r * YW + cb + x] = outv[k][x];
-				} else *reinterpret_cast<uint4 *>(P + r * YW + cb + c) = *reinterpret_cast<const uint4 *>(&outv[k][c]);
+			if (r <= 511) *reinterpret_cast<uint4 *>(&T[1 + k][c]) = *reinterpret_cast<const uint4 *>(P + r * YW + cb + c);
+			if (k == 0) {
+				const int r2 = r0 + E20_ROWS;
+				if (r2 <= 511) *reinterpret_cast<uint4 *>(&T[1 + E20_ROWS][c]) = *reinterpret_cast<const uint4 *>(P + r2 * YW + cb + c);
+			} else if (k == 1) {
+				if (r0 == g.r0) *reinterpret_cast<uint4 *>(&T[0][c]) = *reinterpret_cast<const uint4 *>(P + (r0 - 1) * YW + cb + c);
+				else *reinterpret_cast<uint4 *>(&T[0][c]) = *reinterpret_cast<const uint4 *>(&tile[buf ^ 1][E20_ROWS][c]);
+			} else if (k == 2 && tid - 64 < E20_ROWS + 2) {
+				const int kk = tid - 64, r2 = r0 - 1 + kk;   // tile row kk
+				int e0 = 0, e1 = 0;
+				if (g.pass == 1 && r2 <= 511) { e0 = P[r2 * YW + 256]; e1 = P[r2 * YW + 257]; }
+				T[kk][256] = (int16_t)e0;
+				T[kk][257] = (int16_t)e1;
 			}
-			if (g.pass == 1 && tid < E20_ROWS && r0 + tid < g.r1) P[(r0 + tid) * YW + 256] = out_edge[tid];
 		}
 		__syncthreads();
+		const int r = r0 + k;
+		if (r < g.r1) {
+			const int16_t *row = &T[1 + k][0] - cb;
+			int o[8];
+			e20_cells8(row - E20_TS, row, row + E20_TS, g, r, cb + c, o);
+			int16_t *dst = P + r * YW + cb + c;
+			if (c == 0 && cb) { for (int x = 1; x < 8; x++) dst[x] = (int16_t)o[x]; }   // column 256 is not this pass's
+			else st8(dst, o);
+			if (g.pass == 1 && c == 248) P[r * YW + 256] = (int16_t)e20_edge_cell(row, E20_TS, g, r);
+		}
+		// the next band loads into the other buffer; this one is read again (its last row) during that load
 	}
 }
 
@@ -1300,7 +1321,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
 	run_groups(c, "y_recons1_quant", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { recons_quant_group(im, r, g, ratio, 1); });
 	idwt_luma256(c, b, n);
-	run_groups(c, "y_e6c_apply", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { y_e6c_apply_cells(im.proc, im.ll1 + r * 256, r, g); });
+	NHW_LAUNCH_L(c, "y_e6c_apply", k_e6c_apply, dim3(64, n), 256, 0, b);
 	NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(32, n), 256, 0, b);
 	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
 
@@ -1320,8 +1341,10 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
 		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
 	run_groups(c, "y_recons0_quant", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { recons_quant_group(im, r, g, ratio, 0); });
-	run_wavefront(c, "y_recons0_shrink", b, n, wf_shrink_geom(),
-	              [=] __device__(const EncImg &im, int r, int j) { return wf_shrink_cell(im, r, j); });
+	run_groups(c, "y_recons0_shrink", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) {
+		int o[8];
+		if (shrink_cells8(im.jpeg, r, g, 8, o)) st8(im.jpeg + r * YW + g * 8, o);
+	});
 	idwt_luma256(c, b, n);
 	if (q > 21) NHW_LAUNCH_L(c, "y_hq_first_order", k_hq_first_order, dim3(8, 8, n), 256, 0, b);
 

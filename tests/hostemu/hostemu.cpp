@@ -418,7 +418,13 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	}
 	int exw = dec_y_ll_image(im);
 	if (getenv("HE_SERIAL")) dec_y_shrink_image(im);
-	else host_wavefront(dwf_shrink_geom(), [&](int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
+	else if (getenv("HE_WAVEFRONT")) host_wavefront(dwf_shrink_geom(), [&](int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
+	else
+		for (int r = 255; r >= 0; r--)
+			for (int g = 31; g >= 0; g--) {
+				int o[8];
+				if (shrink_cells8(im.jpeg, r, g, 9, o)) for (int x = 0; x < 8; x++) im.jpeg[r * 512 + g * 8 + x] = (int16_t)o[x];
+			}
 	inv_level(im.jpeg, im.proc, 512, 256, tmp);                 // LL1 reconstruction, natural orientation
 	dec_y_addbacks_image(im);
 	if (getenv("HE_SERIAL")) dec_y_edge_flags_image(im);
@@ -562,7 +568,13 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		for (int r = 255; r >= 0; r--) y_recons_tag57_row(im, r);
 		for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 0);
 	} else host_recons_quant_cells(im, ratio, 0);
-	host_wavefront(wf_shrink_geom(), [&](int r, int j) { return wf_shrink_cell(im, r, j); });
+	if (getenv("HE_WAVEFRONT")) host_wavefront(wf_shrink_geom(), [&](int r, int j) { return wf_shrink_cell(im, r, j); });
+	else   // order-free form, run in place in the reverse of the reference's order
+		for (int r = 255; r >= 0; r--)
+			for (int g = 31; g >= 0; g--) {
+				int o[8];
+				if (shrink_cells8(im.jpeg, r, g, 8, o)) for (int x = 0; x < 8; x++) im.jpeg[r * 512 + g * 8 + x] = (int16_t)o[x];
+			}
 	T("y_rec0_jpeg", im.jpeg, 512 * 512 * 2);
 	inv_level(im.jpeg, im.proc, 512, 256, tmp);
 	T("y_syn0_proc", im.proc, 512 * 512 * 2);
@@ -597,8 +609,22 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		const int16_t *B = before.data() + 4096;
 		for (int pass = 2; pass >= 0; pass--) {
 			const E20Pass g = e20_pass(q, ratio, pass);
-			for (int r = g.r1 - 1; r >= g.r0; r--)
-				for (int j = g.j1; j >= g.j0; j--) im.proc[r * 512 + j] = (int16_t)e20_final_cell(B + r * 512, 512, g, r, j);
+			for (int r = g.r1 - 1; r >= g.r0; r--) {
+				if (getenv("HE_E20_CELL")) {
+					for (int j = g.j1; j >= g.j0; j--) im.proc[r * 512 + j] = (int16_t)e20_final_cell(B + r * 512, 512, g, r, j);
+					continue;
+				}
+				const int cb = pass == 1 ? 0 : 256;
+				if (pass == 1) im.proc[r * 512 + 256] = (int16_t)e20_edge_cell(B + r * 512, 512, g, r);
+				for (int gi = 31; gi >= 0; gi--) {
+					int o[8];
+					e20_cells8(B + (r - 1) * 512, B + r * 512, B + (r + 1) * 512, g, r, cb + gi * 8, o);
+					for (int x = 0; x < 8; x++) {
+						const int j = cb + gi * 8 + x;
+						if (j >= g.j0 && j <= g.j1) im.proc[r * 512 + j] = (int16_t)o[x];
+					}
+				}
+			}
 		}
 	}
 	T("y_e20_proc", im.proc, 512 * 512 * 2);
