@@ -13,7 +13,7 @@
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
 #include "enc_seg.cuh"
-#include "enc_cells.cuh"
+#include "enc_patterns.cuh"
 #include "enc_batch.cuh"
 #include "../../include/nhw_cuda.h"
 
@@ -585,6 +585,44 @@ __global__ void __launch_bounds__(32) k_e18_tails(EncBatch b, int q)
 	lm.tmp2 = im.tmp2 + k * E18_PART;
 	lm.tmp3 = im.tmp3 + k * E18_PART;
 	y_e18_finish_list_image(lm, which, e + 256, e);
+}
+
+// ---- pattern substitutions of the level-2 region on 256-bit row masks (enc_patterns.cuh).  One CTA per image:
+// class bits of rows 0..256 (a warp per row, a lane per 8 cells), every row solved by its own thread as if the row
+// above fired no block, one thread walks down the rows and redoes those below a row with blocks, then the fired
+// events are applied, one thread per 32 columns of a row.
+__global__ void __launch_bounds__(256) k_patterns(EncBatch b, int kind)
+{
+	__shared__ PatMasks m;
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	int16_t *P = im.proc, *J = im.jpeg;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	uint8_t *posb = reinterpret_cast<uint8_t *>(m.pos), *negb = reinterpret_cast<uint8_t *>(m.neg);
+	for (int r = warp; r < 257; r += 8) {
+		int v[8];
+		uint32_t p8, n8;
+		ld8(P + r * YW + lane * 8, v);
+		pat_class_bits8(v, p8, n8);
+		posb[r * 32 + lane] = (uint8_t)p8;
+		negb[r * 32 + lane] = (uint8_t)n8;
+	}
+	__syncthreads();
+	const int rows = pat_rows(kind);
+	if (tid < rows) {
+		const uint64_t zero[4] = {0, 0, 0, 0};
+		pat_solve_row(m, kind, tid, zero);
+	}
+	__syncthreads();
+	if (tid == 0) pat_fixup(m, kind);
+	__syncthreads();
+	const uint32_t *ft = reinterpret_cast<const uint32_t *>(m.ft), *fb = reinterpret_cast<const uint32_t *>(m.fb);
+	const uint32_t *pos = reinterpret_cast<const uint32_t *>(m.pos);
+	for (int item = tid; item < rows * 8; item += 256) {
+		const int r = item >> 3, w = item & 7;
+		const uint32_t p = pos[r * 8 + w];
+		for (uint32_t f = ft[r * 8 + w]; f; f &= f - 1) { const int bit = __ffs(f) - 1; pat_apply(P, J, kind, r, w * 32 + bit, true, p >> bit & 1); }
+		for (uint32_t f = fb[r * 8 + w]; f; f &= f - 1) { const int bit = __ffs(f) - 1; pat_apply(P, J, kind, r, w * 32 + bit, false, p >> bit & 1); }
+	}
 }
 
 // ---- E6c (enc_cells.cuh: y_e6c_apply_cells states the rule): un-tag LL1, push +-1 into the trial reconstruction at
@@ -1316,9 +1354,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	// ---- luma closed loop (nhw_encoder.c:141-283)
 	run_groups(c, "y_e6a_tag", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { y_e6a_tag_cells(im.proc, im.ll1 + r * 256, r, g); });
 	NHW_LAUNCH_L(c, "y_recons1_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 1);
-	for (int reg = 0; reg < 2; reg++)
-		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
-		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
+	NHW_LAUNCH_L(c, "y_recons_patterns", k_patterns, n, 256, 0, b, 0);
 	run_groups(c, "y_recons1_quant", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { recons_quant_group(im, r, g, ratio, 1); });
 	idwt_luma256(c, b, n);
 	NHW_LAUNCH_L(c, "y_e6c_apply", k_e6c_apply, dim3(64, n), 256, 0, b);
@@ -1337,9 +1373,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	// ---- second reconstruction = what the decoder will see as LL1 (nhw_encoder.c:759-781)
 	NHW_LAUNCH_L(c, "y_recons0_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 0);
-	for (int reg = 0; reg < 2; reg++)
-		run_wavefront(c, "y_recons_patterns", b, n, wf_recons_patterns_geom(reg),
-		              [=] __device__(const EncImg &im, int r, int j) { return wf_recons_patterns_cell(im, r, j); });
+	NHW_LAUNCH_L(c, "y_recons_patterns", k_patterns, n, 256, 0, b, 0);
 	run_groups(c, "y_recons0_quant", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { recons_quant_group(im, r, g, ratio, 0); });
 	run_groups(c, "y_recons0_shrink", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) {
 		int o[8];
@@ -1363,8 +1397,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(256, n), 128, 0, b);
 	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_bands, dim3(3, n), 256, 0, b, q, ratio);
 	run_groups_inplace(c, "y_offset_mult8", b, n, 512, 6, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_offset_mult8_cells(im.proc, r, g, o); });
-	run_wavefront(c, "y_offset_patterns", b, n, wf_offset_patterns_geom(),
-	              [=] __device__(const EncImg &im, int r, int j) { return wf_offset_patterns_cell(im, r, j); });
+	NHW_LAUNCH_L(c, "y_offset_patterns", k_patterns, n, 256, 0, b, 1);
 	run_groups_inplace(c, "y_offset_pairs57", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_offset_pairs57_cells(im.proc, r, g, o); });
 	NHW_LAUNCH_L(c, "y_quant_scan", k_y_quant_scan, dim3(32, n), 256, 0, b, ratio);
 	if (q > 21) {   // res6 / char_res1 / high_qsetting3 from the quantised LH1 bytes, before the peephole edits them

@@ -14,7 +14,7 @@
 
 #include "../../nhwcodec_b200/csrc/dec_par.cuh"
 #include "../../nhwcodec_b200/csrc/dec_parse.h"
-#include "../../nhwcodec_b200/csrc/enc_cells.cuh"
+#include "../../nhwcodec_b200/csrc/enc_patterns.cuh"
 
 namespace {
 
@@ -272,6 +272,31 @@ static void host_c_recons_cells(const EncImg &im, int m1, int comp)
 		}
 }
 
+// the k_patterns schedule (enc_patterns.cuh): class masks, rows solved independently, fix-up walk, parallel apply
+static void host_patterns(const EncImg &im, int kind)
+{
+	static PatMasks m;
+	memset(&m, 0, sizeof m);
+	for (int r = 0; r < 257; r++)
+		for (int g = 0; g < 32; g++) {
+			int v[8];
+			uint32_t p8, n8;
+			ld8(im.proc + r * 512 + g * 8, v);
+			pat_class_bits8(v, p8, n8);
+			((uint8_t *)m.pos[r])[g] = (uint8_t)p8;
+			((uint8_t *)m.neg[r])[g] = (uint8_t)n8;
+		}
+	const uint64_t zero[4] = {0, 0, 0, 0};
+	for (int r = pat_rows(kind) - 1; r >= 0; r--) pat_solve_row(m, kind, r, zero);
+	pat_fixup(m, kind);
+	if (getenv("HE_STATS")) { int nt = 0, nb = 0, nf = 0; uint64_t cl[4]; for (int r = 0; r < pat_rows(kind); r++) { for (int w = 0; w < 4; w++) { nt += __builtin_popcountll(m.ft[r][w]); nb += __builtin_popcountll(m.fb[r][w]); } if (r && pat_cleared_by(m, r - 1, cl)) nf++; } fprintf(stderr, "patterns kind %d: %d triples, %d blocks, %d rows redone\n", kind, nt, nb, nf); }
+	for (int r = pat_rows(kind) - 1; r >= 0; r--)
+		for (int j = 255; j >= 0; j--) {
+			const bool t = m.ft[r][j >> 6] >> (j & 63) & 1, bk = m.fb[r][j >> 6] >> (j & 63) & 1;
+			if (t || bk) pat_apply(im.proc, im.jpeg, kind, r, j, t, m.pos[r][j >> 6] >> (j & 63) & 1);
+		}
+}
+
 // the CUDA wavefront schedule, run sequentially: step t lets row ri handle column t - skew*ri;
 // rows of one step are visited bottom-up so that any same-step dependency shows up as a diff
 template <typename Cell>
@@ -515,8 +540,10 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	else for (int r = 255; r >= 0; r--) for (int g = 31; g >= 0; g--) y_e6a_tag_cells(im.proc, im.ll1 + r * 256, r, g);
 	T("y_e6a_ll1", im.ll1, 65536 * 2);
 	host_recons_ll2(im, q, 1);
-	for (int reg = 0; reg < 2; reg++)
-		host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
+	if (getenv("HE_WAVEFRONT")) {
+		for (int reg = 0; reg < 2; reg++)
+			host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
+	} else host_patterns(im, 0);
 	if (getenv("HE_ROWFORM")) { for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 1); }
 	else host_recons_quant_cells(im, ratio, 1);
 	T("y_rec1_jpeg", im.jpeg, 512 * 512 * 2);
@@ -562,8 +589,10 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	T("y_e12_chres", im.llcode, h->y_res_comp);
 	copy_region(im.proc, 512, im.ll2s, 256, 256);
 	host_recons_ll2(im, q, 0);
-	for (int reg = 0; reg < 2; reg++)
-		host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
+	if (getenv("HE_WAVEFRONT")) {
+		for (int reg = 0; reg < 2; reg++)
+			host_wavefront(wf_recons_patterns_geom(reg), [&](int r, int j) { return wf_recons_patterns_cell(im, r, j); });
+	} else host_patterns(im, 0);
 	if (getenv("HE_ROWFORM")) {
 		for (int r = 255; r >= 0; r--) y_recons_tag57_row(im, r);
 		for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 0);
@@ -630,7 +659,8 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	T("y_e20_proc", im.proc, 512 * 512 * 2);
 	if (getenv("HE_ROWFORM")) { for (int r = 511; r >= 0; r--) y_offset_mult8_row(im, r); }
 	else host_groups_inplace(im, 512, 64, [&](const int16_t *B, int r, int g, int *o) { return y_offset_mult8_cells(B, r, g, o); });
-	host_wavefront(wf_offset_patterns_geom(), [&](int r, int j) { return wf_offset_patterns_cell(im, r, j); });
+	if (getenv("HE_WAVEFRONT")) host_wavefront(wf_offset_patterns_geom(), [&](int r, int j) { return wf_offset_patterns_cell(im, r, j); });
+	else host_patterns(im, 1);
 	if (getenv("HE_ROWFORM")) { for (int r = 255; r >= 0; r--) y_offset_pairs57_row(im, r); }
 	else host_groups_inplace(im, 256, 32, [&](const int16_t *B, int r, int g, int *o) { return y_offset_pairs57_cells(B, r, g, o); });
 	if (getenv("HE_ROWFORM")) {

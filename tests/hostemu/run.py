@@ -17,7 +17,13 @@ TAPFN = ctypes.CFUNCTYPE(None, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t
 def lib():
     global _lib
     if _lib is None:
-        _lib = ctypes.CDLL(os.path.join(HERE, "libhostemu.so"))
+        so = os.path.join(HERE, "libhostemu.so")
+        csrc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "nhwcodec_b200", "csrc")
+        srcs = [os.path.join(HERE, "hostemu.cpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
+            import subprocess
+            subprocess.check_call(["bash", os.path.join(HERE, "build.sh")])   # a stale library would test nothing
+        _lib = ctypes.CDLL(so)
         _lib.he_new.restype = ctypes.c_void_p
         _lib.he_free.argtypes = [ctypes.c_void_p]
         _lib.he_encode.restype = ctypes.c_int
