@@ -13,7 +13,7 @@
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
 #include "enc_seg.cuh"
-#include "enc_patterns.cuh"
+#include "enc_ll2_masks.cuh"
 #include "enc_batch.cuh"
 #include "../../include/nhw_cuda.h"
 
@@ -287,18 +287,21 @@ __global__ void __launch_bounds__(128) k_recons_ll2_wave(EncBatch b, int q, int 
 		reinterpret_cast<uint32_t *>(sP + r * LL2_PS)[c] = reinterpret_cast<const uint32_t *>(im.proc + r * YW)[c];
 	}
 	__syncthreads();
+	// quad tagging (rows independent), masks of the tagged row, one thread solves the parity nudges on the masks
+	// (enc_ll2_masks.cuh), then every cell gets its final value and its im_jpeg sample
+	__shared__ Ll2Masks m;
 	if (q > 17) y_recons_ll2_tag_row(sP, LL2_PS, t, part);
-	__syncthreads();
-	const WfGeom g = wf_ll2_geom();
-	const int steps = g.cols + g.skew * (g.rows - 1);
-	int next = 0;
-	for (int s = 0; s < steps; s++) {
-		const int c = s - g.skew * t;
-		if (c >= 0 && c < g.cols && c == next) next = c + y_recons_ll2_cell(sP, LL2_PS, im.jpeg, q, part, t, c);
-		__syncthreads();
+	ll2_masks_row(sP + t * LL2_PS, m.odd[t], m.tag[t], m.d2inc[t]);
+	if (t < LL2M_ROWS - 128) {
+		m.odd[128 + t][0] = m.odd[128 + t][1] = m.odd[128 + t][2] = 0;
+		m.tag[128 + t][0] = m.tag[128 + t][1] = 0;
 	}
+	__syncthreads();
+	if (t == 0) ll2_nudge_solve(m, q, part == 1);
+	__syncthreads();
+	for (int r = 0; r < 128; r++)
+		ll2_recons_apply_cell(sP + r * LL2_PS + t, im.jpeg + r * YW + t, im.aux + r * 128 + t, (int)(m.d2inc[r][t >> 6] >> (t & 63) & 1), part);
 	if (!part) {
-		y_recons_ll2_tail_row(sP, LL2_PS, im.jpeg, im.aux, t);
 		__syncthreads();
 		if (q > 15) {
 			const int n = im.hdr->highres_mem_len;
@@ -336,14 +339,21 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 	__syncthreads();
 	n4[t] = q > 17 ? ll2_bytes_tag_row(sP, LL2_PS, t, r4 + t * 32) : 0;
 	__syncthreads();
-	{
-		const WfGeom g = wf_ll2_geom();
-		const int steps = g.cols + g.skew * (g.rows - 1);
-		for (int s = 0; s < steps; s++) {
-			const int c = s - g.skew * t;
-			if (c >= 0 && c < g.cols) ll2_bytes_cell(sP, LL2_PS, V, q, t, c);
-			__syncthreads();
+	{   // parity nudges on row masks (enc_ll2_masks.cuh); the masks borrow the sample array, which is filled last
+		Ll2Masks &m = *reinterpret_cast<Ll2Masks *>(V);
+		ll2_masks_row(sP + t * LL2_PS, m.odd[t], m.tag[t], m.d2inc[t]);
+		if (t < LL2M_ROWS - 128) {
+			m.odd[128 + t][0] = m.odd[128 + t][1] = m.odd[128 + t][2] = 0;
+			m.tag[128 + t][0] = m.tag[128 + t][1] = 0;
 		}
+		__syncthreads();
+		if (t == 0) ll2_nudge_solve(m, q, false);
+		__syncthreads();
+		uint64_t mine[2] = {0, 0};   // bit r = "cell (r, t) gets +1"
+		for (int r = 0; r < 128; r++) mine[r >> 6] |= (m.d2inc[r][t >> 6] >> (t & 63) & 1) << (r & 63);
+		__syncthreads();
+		for (int r = 0; r < 128; r++) V[r * 128 + t] = (int16_t)ll2_bytes_value(sP[r * LL2_PS + t], (int)(mine[r >> 6] >> (r & 63) & 1), q);
+		__syncthreads();
 	}
 	// ---- bytes.  A cell whose value does not fit a byte ("escape") repeats the byte on its left and goes to
 	// the exw_Y list; lists are in raster order: each thread owns 128 consecutive cells, counts, CTA scan, writes.

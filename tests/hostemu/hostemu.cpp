@@ -14,7 +14,7 @@
 
 #include "../../nhwcodec_b200/csrc/dec_par.cuh"
 #include "../../nhwcodec_b200/csrc/dec_parse.h"
-#include "../../nhwcodec_b200/csrc/enc_patterns.cuh"
+#include "../../nhwcodec_b200/csrc/enc_ll2_masks.cuh"
 
 namespace {
 
@@ -316,9 +316,46 @@ void host_recons_ll2(const EncImg &im, int q, int part)
 {
 	int16_t *P = im.proc, *J = im.jpeg;
 	if (q > 17) for (int r = 127; r >= 0; r--) y_recons_ll2_tag_row(P, 512, r, part);
+	if (!getenv("HE_WAVEFRONT")) {   // mask form (enc_ll2_masks.cuh), the schedule of k_recons_ll2
+		static Ll2Masks m;
+		if (getenv("HE_LL2_DEBUG")) {
+			std::vector<int16_t> cp(P - 4096, P + 512 * 512 + 4096), jj(512 * 512 + 8192);
+			int16_t *Q = cp.data() + 4096;
+			std::vector<int16_t> before(cp);
+			host_wavefront(wf_ll2_geom(), [&](int r, int j) { return y_recons_ll2_cell(Q, 512, jj.data() + 4096, q, part, r, j); });
+			memset(&m, 0, sizeof m);
+			for (int r = 127; r >= 0; r--) ll2_masks_row(P + r * 512, m.odd[r], m.tag[r], m.d2inc[r]);
+			ll2_nudge_solve(m, q, part == 1);
+			int shown = 0;
+			if (part) for (int r = 0; r < 128 && shown < 6; r++) for (int j = 0; j < 128 && shown < 6; j++) {
+				int16_t p2 = before[4096 + r * 512 + j], j2 = 0, t2 = 0;
+				ll2_recons_apply_cell(&p2, &j2, &t2, m.d2inc[r][j >> 6] >> (j & 63) & 1, part);
+				if (j2 != jj[4096 + r * 512 + j] || p2 != Q[r * 512 + j]) {
+					shown++;
+					fprintf(stderr, "ll2 part %d (r=%d,j=%d): J want %d got %d, P want %d got %d (before %d)\n", part, r, j, jj[4096 + r * 512 + j], j2, Q[r * 512 + j], p2, before[4096 + r * 512 + j]);
+				}
+			}
+			for (int r = 0; r < 128 && shown < 6; r++) for (int j = 0; j < 128 && shown < 6; j++) {
+				const int16_t *B = before.data() + 4096;
+				int want = Q[r * 512 + j] - B[r * 512 + j]; if (B[r * 512 + j] > 10000 && part) want += 16000;
+				int got = m.d2inc[r][j >> 6] >> (j & 63) & 1;
+				if (want != got) {
+					shown++;
+					fprintf(stderr, "ll2 part %d (r=%d,j=%d): want inc %d got %d\n", part, r, j, want, got);
+					for (int dr = -1; dr <= 3; dr++) { for (int dj = -3; dj <= 3; dj++) fprintf(stderr, "%6d", r + dr >= 0 ? B[(r + dr) * 512 + j + dj] : 0); fprintf(stderr, "\n"); }
+				}
+			}
+		}
+		memset(&m, 0, sizeof m);
+		for (int r = 127; r >= 0; r--) ll2_masks_row(P + r * 512, m.odd[r], m.tag[r], m.d2inc[r]);
+		ll2_nudge_solve(m, q, part == 1);
+		for (int r = 127; r >= 0; r--)
+			for (int j = 127; j >= 0; j--) ll2_recons_apply_cell(P + r * 512 + j, J + r * 512 + j, im.aux + r * 128 + j, m.d2inc[r][j >> 6] >> (j & 63) & 1, part);
+	} else {
 	host_wavefront(wf_ll2_geom(), [&](int r, int j) { return y_recons_ll2_cell(P, 512, J, q, part, r, j); });
+	if (!part) for (int r = 127; r >= 0; r--) y_recons_ll2_tail_row(P, 512, J, im.aux, r);
+	}
 	if (!part) {
-		for (int r = 127; r >= 0; r--) y_recons_ll2_tail_row(P, 512, J, im.aux, r);
 		if (q > 15)
 			for (int k = im.hdr->highres_mem_len - 1; k >= 0; k--) {
 				const int m = im.highres_mem[k];
@@ -335,6 +372,14 @@ void host_ll2_code(const EncImg &im, int q)
 	std::vector<uint8_t> r4(128 * 32);
 	std::vector<int> n4(128, 0);
 	if (q > 17) for (int r = 127; r >= 0; r--) n4[r] = ll2_bytes_tag_row(P, 512, r, &r4[r * 32]);
+	if (!getenv("HE_WAVEFRONT")) {
+		static Ll2Masks m;
+		memset(&m, 0, sizeof m);
+		for (int r = 127; r >= 0; r--) ll2_masks_row(P + r * 512, m.odd[r], m.tag[r], m.d2inc[r]);
+		ll2_nudge_solve(m, q, false);
+		for (int r = 127; r >= 0; r--)
+			for (int j = 127; j >= 0; j--) { V[r * 128 + j] = (int16_t)ll2_bytes_value(P[r * 512 + j], m.d2inc[r][j >> 6] >> (j & 63) & 1, q); P[r * 512 + j] = 0; }
+	} else
 	host_wavefront(wf_ll2_geom(), [&](int r, int j) { return ll2_bytes_cell(P, 512, V.data(), q, r, j); });
 	for (int a = 16383; a >= 0; a--)
 		if (!ll2_is_escape(V[a], a)) ll2_bytes_store(im, a, V[a]);
