@@ -337,6 +337,15 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps * PIX / float(tt.item()) / 1e6
+    # the same pinned pixels copied to the device with nothing else running: the PCIe floor of one e2e step
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rgb.copy_(rgb_host, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    rgb.copy_(rgb_host, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_alone_ms = ev0.elapsed_time(ev1)
 
     # ---------------- decode of the streams just produced (host API: .nhw bytes in, pixels out) ----------------
     dec = None
@@ -432,10 +441,12 @@ def run_ours(args):
                        "mean_stream_bytes": round(mean_stream, 1), "bit_exact": "verified by tests/test_encode_gpu.py",
                        "l2": "inputs (%.1f GB per step) exceed the 126 MB L2; no flush needed" % (B * PIX_BYTES / 1e9)},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": B * PIX_BYTES,
-                    "d2h_bytes_per_step": d2h + 8 * (B + 1) + 4 * B, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h + 8 * (B + 1) + 4 * B, "steps": e2e_steps,
+                    "ms_per_step": round(float(tt.item()) * 1e3 / e2e_steps, 3),
+                    "h2d_alone_ms": round(h2d_alone_ms, 3), "h2d_alone_GBps": round(B * PIX_BYTES / h2d_alone_ms / 1e6, 2)},
             "gpu_launches": int(launches),
             "kernel_table": "per-kernel ms from a separate serialised pass (CUDA events around every launch); in the timed "
-                            "regions the host-buffer calls run 4 (encode) / 8 (decode) sub-chunks on 4 streams",
+                            "regions the host-buffer calls run 8 (encode) / 8 (decode) sub-chunks on 4 streams",
             "clocks": clocks,
             "roofline": roofline,
             "frontend": frontend,

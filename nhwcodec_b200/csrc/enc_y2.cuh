@@ -61,20 +61,20 @@ NHW_HD void e16_band_fix_w2(int16_t *P, int stage, int left)
 	if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
 	else if (P[stage] == 7 || (P[stage] & 65534) == 8) { if (left >= -2) P[stage] += 3; }
 }
-NHW_HD void e16_band_fix_w3(int16_t *P, int16_t *L, int stage, int count, int q, int left)
+NHW_HD void e16_band_fix_w3(int16_t *P, int16_t *Lc /* the LL1 cell */, int stage, int q, int left)
 {
-	if (q >= 21) { L[count] = 14500; return; }
+	if (q >= 21) { *Lc = 14500; return; }
 	if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
 	else if (P[stage] >= 0 && ((P[stage] + 2) & 65532) == 8) { if (left >= -2) P[stage] = 10; }
 	else if (P[stage] > 14 && (P[stage] & 7) == 7) P[stage]++;
 }
-NHW_HD void e16_band_fix_w5(int16_t *P, int16_t *L, int stage, int count, int res, int q, int left)
+NHW_HD void e16_band_fix_w5(int16_t *P, int16_t *Lc /* the LL1 cell */, int stage, int res, int q, int left)
 {
-	L[count] = 14000;
+	*Lc = 14000;
 	if (res == -4) {
 		if (P[stage] == -7 || P[stage] == -8) { if (left < 2 && left > -8) P[stage] = -9; }
 	} else if (res < -6) {
-		if (res < -7 && q >= 21) L[count] = 14900;
+		if (res < -7 && q >= 21) *Lc = 14900;
 		else if (P[stage] < -14) { if (!((-P[stage]) & 7) || ((-P[stage]) & 7) == 7) P[stage]++; }
 		else if (P[stage] == 7 || P[stage] == 8) { if (left >= -1 && left < 8) P[stage] += 3; }
 	}
@@ -171,10 +171,122 @@ NHW_HDN void y_e16_residual_col(const EncImg &im, int q, int j, const int16_t *P
 				const int left = row == 0 ? Pn[stage - 1] : P[stage - 1];
 				if (go == W1) e16_band_fix_w1(P, stage, left);
 				else if (go == W2) e16_band_fix_w2(P, stage, left);
-				else if (go == W3) e16_band_fix_w3(P, L, stage, count, q, left);
-				else if (go == W5) e16_band_fix_w5(P, L, stage, count, res, q, left);
+				else if (go == W3) e16_band_fix_w3(P, L + count, stage, q, left);
+				else if (go == W5) e16_band_fix_w5(P, L + count, stage, res, q, left);
 			}
 		}
+	}
+}
+
+// The same walk with the four rows a step touches held in registers: the next rows are loaded ahead of time and a step no
+// longer waits for the previous step's stores to come back from memory (the column walk is a 255-step dependency
+// chain, one column per thread).
+NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t *Pn, const int16_t *Ln)
+{
+	int16_t *P = im.proc, *L = im.ll1;
+	const int rs = res_setting_of(q);
+	{
+		int scan = j, count = j;
+		// cells of rows row-1 .. row+2 of this column; o* = what memory holds for the ones not stored yet
+		int pm1 = 0, lm1 = 0, p0 = P[j], l0 = L[j], p1 = P[j + YW], l1 = L[j + 256], p2 = P[j + 2 * YW], l2 = L[j + 512];
+		int ol0 = l0, op1 = p1, ol1 = l1, op2 = p2;
+		int np = P[j + 3 * YW], nl = L[j + 768];   // next row to enter the window (reads past the band on the last rows)
+		for (int row = 0; row < 255; row++, scan += YW, count += 256) {
+			const int stage = (j << 9) + row + 256;
+			int res = p0 - l0;
+			int a = p1 - l1;
+			int b = p2 - l2;
+			enum { NONE, W1, W2, W3, W5 } go = NONE;
+			if (res == 2 && a == 2 && b >= 2) {
+				if (b < 5 || b > 6) { l0 = 12400; p1 -= 2; p2 -= 2; }
+			} else if (((res == 2 && a == 3) || (res == 3 && a == 2)) && b > 1 && b < 6) {
+				l0 = 12400; p1 -= 2; p2 -= 2;
+			} else if (res == 3 && a == 3) {
+				if (b > 0 && b < 6) { l0 = 12400; p1 -= 2; p2 -= 2; }
+				else if (q >= 19) { l0 = 12100; p1 = l1; }
+			} else if (a == -4 && (res == 2 || res == 3) && (b == 2 || b == 3)) {
+				if (res == 2 && b == 2) p1++;
+				else { l0 = 12400; p1 -= 2; p2 -= 2; }
+			} else if (res == 1 && a == 3 && b == 2) {
+				if (row > 0 && (pm1 - lm1) >= 0) { l0 = 12400; p1 -= 2; p2 -= 2; }
+			} else if ((res == 3 || res == 4 || res == 5 || res > 6) && (a == 3 || (a & 65534) == 4)) {
+				if (res > 6) { l0 = 12500; p1 = l1; }
+				else if (q >= 19) { l0 = 12100; p1 = l1; }
+				else if (q == 18) {
+					if (res < 5 && a == 5) l1 = 14100;
+					else if (res >= 5) l0 = 14100;
+					else if (res == 3 && a >= 4) l1 = 14100;
+					p1 = l1;
+				}
+			} else if ((res == 2 || res == 3) && (a == 2 || a == 3)) {
+				if (b == 0 || b == 1) {
+					int c1 = Pn[scan + 1] - Ln[count + 1];
+					if (c1 == 2 || c1 == 3) {
+						int c2 = Pn[scan + YW + 1] - Ln[count + 257];
+						if (c2 == 2 || c2 == 3) {
+							if ((Pn[scan + 2 * YW + 1] - Ln[count + 513]) > 0) { l0 = 12400; p1 -= 2; p2 -= 2; }
+						}
+					}
+				}
+			} else if (a == 4 && (res == -2 || res == -3) && (-b == 2 || -b == 3)) {
+				if (res == -2 && -b == 2) p1--;
+				else { l0 = 12300; p1 += 2; p2 += 2; }
+			} else if ((res == -3 || res == -4 || res == -5 || res < -7) && (a == -3 || a == -4 || a == -5)) {
+				if (res < -7) { l0 = 12600; p1 = l1; }
+				else if (q >= 19) { l0 = 12200; p1 = l1; }
+				else if (q == 18) {
+					if (res > -5 && a == -5) l1 = 14000;
+					else if (res <= -5) l0 = 14000;
+					else if (res == -3 && a <= -4) l1 = 14000;
+					p1 = l1;
+				}
+			} else if (a == -2 || a == -3) {
+				if (res == -2 || res == -3) {
+					if (-b > 0) { l0 = 12300; p1 += 2; p2 += 2; }
+					else if (res == -3 && q >= 21) l0 = 14500;
+					else if (b == 0) {
+						int c1 = Pn[scan + 1] - Ln[count + 1];
+						if (c1 == -2 || c1 == -3) {
+							int c2 = Pn[scan + YW + 1] - Ln[count + 257];
+							if (c2 == -2 || c2 == -3) {
+								if ((Pn[scan + 2 * YW + 1] - Ln[count + 513]) < 0) { l0 = 12300; p1 += 2; p2 += 2; }
+							}
+						}
+					} else if (res == -2) go = W2;
+					else go = W3;
+				} else if (res == -1 && a == -3 && b == -2) {
+					if (row > 0 && (pm1 - lm1) <= 0) { l0 = 12300; p1 += 2; p2 += 2; }
+				} else if (res == -1) {
+					if (-b == 3) { l0 = 12300; p1 += 2; p2 += 2; }
+					else go = W1;
+				} else if (res == -4) {
+					if (-b > 1 && -b < 4) { l0 = 12300; p1 += 2; p2 += 2; }
+					else go = W5;
+				}
+			} else if (res == 0 || res == -1) go = W1;
+			else if (res == -2) go = W2;
+			else if (res == -3) go = W3;
+			else if (res < -rs) go = W5;
+
+			if (go != NONE) {
+				const int left = row == 0 ? Pn[stage - 1] : P[stage - 1];
+				if (go == W1) e16_band_fix_w1(P, stage, left);
+				else if (go == W2) e16_band_fix_w2(P, stage, left);
+				else if (go == W3) { int16_t lc = (int16_t)l0; e16_band_fix_w3(P, &lc, stage, q, left); l0 = lc; }
+				else if (go == W5) { int16_t lc = (int16_t)l0; e16_band_fix_w5(P, &lc, stage, res, q, left); l0 = lc; }
+			}
+			// row `row` of LL1 and row+1 of the plane are final now
+			if (l0 != ol0) L[count] = (int16_t)l0;
+			if (p1 != op1) P[scan + YW] = (int16_t)p1;
+			pm1 = p0; lm1 = l0;
+			p0 = p1; l0 = l1; ol0 = ol1;
+			p1 = p2; op1 = op2; l1 = l2; ol1 = l2;
+			p2 = np; op2 = np; l2 = nl;
+			if (row < 253) { np = P[scan + 4 * YW]; nl = L[count + 1024]; }   // up to row 256
+		}
+		// the window still holds row 255 of LL1 (a q18 rule of the last step may have coded it) and row 256 of the plane
+		if (l0 != ol0) L[count] = (int16_t)l0;
+		if (p1 != op1) P[scan + YW] = (int16_t)p1;
 	}
 }
 

@@ -230,15 +230,17 @@ __global__ void __launch_bounds__(256) k_e16_residual(EncBatch b, int q)
 	const EncImg im = make_img(b, blockIdx.x, 0);
 	const int4 *ps = reinterpret_cast<const int4 *>(im.proc);
 	int4 *pd = reinterpret_cast<int4 *>(im.aux);
-	for (int i = threadIdx.x; i < E16_SNAP_P_CELLS / 8; i += 256) pd[i] = ps[i];
+	// neighbour columns are read as they were before the stage: left half of rows 0..257 (columns <= 255 are all a
+	// column walk looks at next to it) and the LL1 copy
+	for (int i = threadIdx.x; i < 258 * 32; i += 256) { const int k = (i >> 5) * 64 + (i & 31); pd[k] = ps[k]; }
 	const int4 *ls = reinterpret_cast<const int4 *>(im.ll1);
 	int4 *ld = reinterpret_cast<int4 *>(im.aux + E16_SNAP_L_OFF);
 	for (int i = threadIdx.x; i < E16_SNAP_L_CELLS / 8; i += 256) ld[i] = i < 65536 / 8 ? ls[i] : make_int4(0, 0, 0, 0);
 	__syncthreads();
 	const int j = threadIdx.x;
-	if (j < 255) y_e16_residual_col(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF);
+	if (j < 255) y_e16_residual_col_w(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF);
 	__syncthreads();
-	if (j == 255) y_e16_residual_col(im, q, 255, im.proc, im.ll1);
+	if (j == 255) y_e16_residual_col_w(im, q, 255, im.proc, im.ll1);
 }
 
 __global__ void __launch_bounds__(256) k_e16b_classify(EncBatch b, int q)
@@ -1379,7 +1381,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		if (!attr) { cudaFuncSetAttribute(k_ll2_code, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_CODE_SMEM); attr = true; }
 		NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
 	}
-	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_ll2s, CS, 256, b.y_proc, YS, 512, 256);
+	// (the coder works on a shared-memory copy of the band: the plane still holds what the snapshot holds)
 
 	// ---- second reconstruction = what the decoder will see as LL1 (nhw_encoder.c:759-781)
 	NHW_LAUNCH_L(c, "y_recons0_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 0);

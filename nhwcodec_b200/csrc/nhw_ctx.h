@@ -1,7 +1,7 @@
 // nhw_ctx.h -- host-side context of libnhw_cuda (internal; the public face is include/nhw_cuda.h)
 #pragma once
 #define NHW_LANES 4
-#define NHW_MAX_SUB 8
+#define NHW_MAX_SUB 16
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>

@@ -401,8 +401,14 @@ void host_e16(const EncImg &im, int q)
 	memcpy(im.aux, im.proc, E16_SNAP_P_CELLS * sizeof(int16_t));
 	memcpy(im.aux + E16_SNAP_L_OFF, im.ll1, 65536 * sizeof(int16_t));
 	memset(im.aux + E16_SNAP_L_OFF + 65536, 0, 1024 * sizeof(int16_t));
-	for (int jj = 254; jj >= 0; jj--) { int j = getenv("HE_TOPDOWN") ? 254 - jj : jj; y_e16_residual_col(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF); }
-	y_e16_residual_col(im, q, 255, im.proc, im.ll1);
+	const bool mem = getenv("HE_E16_MEM") != nullptr;   // the memory-resident walk instead of the register window
+	for (int jj = 254; jj >= 0; jj--) {
+		int j = getenv("HE_TOPDOWN") ? 254 - jj : jj;
+		if (mem) y_e16_residual_col(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF);
+		else y_e16_residual_col_w(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF);
+	}
+	if (mem) y_e16_residual_col(im, q, 255, im.proc, im.ll1);
+	else y_e16_residual_col_w(im, q, 255, im.proc, im.ll1);
 }
 
 }  // namespace
