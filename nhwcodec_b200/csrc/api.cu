@@ -137,7 +137,11 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	}
 	ok = ok && check(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
 	ok = ok && check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-	for (int k = 0; k < NHW_MAX_SUB && ok; k++) ok = ok && check(cudaEventCreateWithFlags(&c->ev_sub[k], cudaEventDisableTiming), "cudaEventCreate");
+	ok = ok && check(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	for (int k = 0; k < NHW_MAX_SUB && ok; k++) {
+		ok = ok && check(cudaEventCreateWithFlags(&c->ev_sub[k], cudaEventDisableTiming), "cudaEventCreate");
+		ok = ok && check(cudaEventCreateWithFlags(&c->ev_up[k], cudaEventDisableTiming), "cudaEventCreate");
+	}
 
 	c->stream = c->lanes[0];
 	// every workspace array is zero-filled once: guard bands and never-written borders must
@@ -184,7 +188,11 @@ void nhw_destroy(nhw_ctx *c)
 	}
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-	for (int k = 0; k < NHW_MAX_SUB; k++) if (c->ev_sub[k]) cudaEventDestroy(c->ev_sub[k]);
+	if (c->up_stream) cudaStreamDestroy(c->up_stream);
+	for (int k = 0; k < NHW_MAX_SUB; k++) {
+		if (c->ev_sub[k]) cudaEventDestroy(c->ev_sub[k]);
+		if (c->ev_up[k]) cudaEventDestroy(c->ev_up[k]);
+	}
 
 	if (c->prof) {
 		nhw::ProfState *p = static_cast<nhw::ProfState *>(c->prof);
@@ -445,12 +453,22 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 		step = p.count;
 		nhw_ctx v[NHW_MAX_SUB];
 		lanes_fork(c, p.streams);
+		// every sub-chunk has its own pixel slice: all uploads are queued back to back on their own stream, so the
+		// copy engine never waits for the kernels of an earlier sub-chunk that shares a stream with a later one
+		if (p.streams <= 1) cudaEventRecord(c->ev_fork, c->lanes[0]);
+		cudaStreamWaitEvent(c->up_stream, c->ev_fork, 0);
 		for (int k = 0; k < p.subs; k++) {
 			const int a = i0 + p.first[k], cnt = p.first[k + 1] - p.first[k];
 			v[k] = lane_view(c, k % p.streams, k * p.slot, k);
 			if (cnt <= 0) continue;
 			if (!check(cudaMemcpyAsync(v[k].rgb, rgb + (size_t)a * NHW_RGB_BYTES, (size_t)cnt * NHW_RGB_BYTES,
-			                           cudaMemcpyHostToDevice, v[k].stream), "H2D pixels")) return NHW_ERR_CUDA;
+			                           cudaMemcpyHostToDevice, c->up_stream), "H2D pixels")) return NHW_ERR_CUDA;
+			cudaEventRecord(c->ev_up[k], c->up_stream);
+		}
+		for (int k = 0; k < p.subs; k++) {
+			const int cnt = p.first[k + 1] - p.first[k];
+			if (cnt <= 0) continue;
+			cudaStreamWaitEvent(v[k].stream, c->ev_up[k], 0);
 			nhw::encode_chunk(&v[k], v[k].rgb, cnt, quality, v[k].out_dev, v[k].len_dev, v[k].status_dev);
 			nhw::pack_streams(&v[k], cnt);
 			cudaMemcpyAsync(v[k].offs_host, v[k].offs_dev, (size_t)(cnt + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, v[k].stream);

@@ -17,9 +17,10 @@ struct nhw_ctx {
 	// A batch is cut into up to NHW_LANES sub-chunks that run side by side, each on its own stream and on its
 	// own slice of every workspace array (api.cu: lane_view): the many latency-bound stages of one sub-chunk
 	// overlap the others', and host<->device copies overlap kernels.
-	cudaStream_t lanes[4];
+	cudaStream_t lanes[NHW_LANES];
 	cudaStream_t copy_stream;   // device->host copies of finished sub-chunks
-	cudaEvent_t ev_fork, ev_join[4], ev_sub[8];
+	cudaStream_t up_stream;     // host->device copies of the pixels, queued back to back ahead of the sub-chunks that use them
+	cudaEvent_t ev_fork, ev_join[NHW_LANES], ev_sub[NHW_MAX_SUB], ev_up[NHW_MAX_SUB];
 	uint64_t launches;
 	char dbg_label[64];  // debug: stop issuing kernels after the dbg_count-th launch of this label
 	int dbg_count, dbg_seen, dbg_stopped;
