@@ -178,10 +178,44 @@ NHW_HDN void y_e16_residual_col(const EncImg &im, int q, int j, const int16_t *P
 	}
 }
 
+// Which arm of the rule chain of y_e16_residual_col a step takes is a function of the three differences (and of the
+// quality through rs); the arms' own sub-conditions stay with the arms.  Evaluated once per (res, a, b) into a table
+// (2431 entries: differences beyond the thresholds the chain tests are clamped), a step then costs one look-up
+// instead of up to fourteen compound tests.
+NHW_HD int e16_arm(int res, int a, int b, int rs)
+{
+	if (res == 2 && a == 2 && b >= 2) return 0;
+	if (((res == 2 && a == 3) || (res == 3 && a == 2)) && b > 1 && b < 6) return 1;
+	if (res == 3 && a == 3) return 2;
+	if (a == -4 && (res == 2 || res == 3) && (b == 2 || b == 3)) return 3;
+	if (res == 1 && a == 3 && b == 2) return 4;
+	if ((res == 3 || res == 4 || res == 5 || res > 6) && (a == 3 || (a & 65534) == 4)) return 5;
+	if ((res == 2 || res == 3) && (a == 2 || a == 3)) return 6;
+	if (a == 4 && (res == -2 || res == -3) && (-b == 2 || -b == 3)) return 7;
+	if ((res == -3 || res == -4 || res == -5 || res < -7) && (a == -3 || a == -4 || a == -5)) return 8;
+	if (a == -2 || a == -3) return 9;
+	if (res == 0 || res == -1) return 10;
+	if (res == -2) return 11;
+	if (res == -3) return 12;
+	if (res < -rs) return 13;
+	return 14;
+}
+#define E16_LUT_SIZE (17 * 13 * 11)
+NHW_HD int e16_clamp(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+NHW_HD int e16_lut_index(int res, int a, int b)
+{
+	return ((e16_clamp(res, -9, 7) + 9) * 13 + (e16_clamp(a, -6, 6) + 6)) * 11 + (e16_clamp(b, -4, 6) + 4);
+}
+NHW_HD int e16_lut_entry(int idx, int rs)
+{
+	const int b = idx % 11 - 4, a = (idx / 11) % 13 - 6, res = idx / (11 * 13) - 9;
+	return e16_arm(res, a, b, rs);
+}
+
 // The same walk with the four rows a step touches held in registers: the next rows are loaded ahead of time and a step no
 // longer waits for the previous step's stores to come back from memory (the column walk is a 255-step dependency
 // chain, one column per thread).
-NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t *Pn, const int16_t *Ln)
+NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t *Pn, const int16_t *Ln, const uint8_t *lut = nullptr)
 {
 	int16_t *P = im.proc, *L = im.ll1;
 	const int rs = res_setting_of(q);
@@ -197,19 +231,20 @@ NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t 
 			int a = p1 - l1;
 			int b = p2 - l2;
 			enum { NONE, W1, W2, W3, W5 } go = NONE;
-			if (res == 2 && a == 2 && b >= 2) {
+			const int arm = lut ? lut[e16_lut_index(res, a, b)] : e16_arm(res, a, b, rs);
+			if (arm == 0) {
 				if (b < 5 || b > 6) { l0 = 12400; p1 -= 2; p2 -= 2; }
-			} else if (((res == 2 && a == 3) || (res == 3 && a == 2)) && b > 1 && b < 6) {
+			} else if (arm == 1) {
 				l0 = 12400; p1 -= 2; p2 -= 2;
-			} else if (res == 3 && a == 3) {
+			} else if (arm == 2) {
 				if (b > 0 && b < 6) { l0 = 12400; p1 -= 2; p2 -= 2; }
 				else if (q >= 19) { l0 = 12100; p1 = l1; }
-			} else if (a == -4 && (res == 2 || res == 3) && (b == 2 || b == 3)) {
+			} else if (arm == 3) {
 				if (res == 2 && b == 2) p1++;
 				else { l0 = 12400; p1 -= 2; p2 -= 2; }
-			} else if (res == 1 && a == 3 && b == 2) {
+			} else if (arm == 4) {
 				if (row > 0 && (pm1 - lm1) >= 0) { l0 = 12400; p1 -= 2; p2 -= 2; }
-			} else if ((res == 3 || res == 4 || res == 5 || res > 6) && (a == 3 || (a & 65534) == 4)) {
+			} else if (arm == 5) {
 				if (res > 6) { l0 = 12500; p1 = l1; }
 				else if (q >= 19) { l0 = 12100; p1 = l1; }
 				else if (q == 18) {
@@ -218,7 +253,7 @@ NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t 
 					else if (res == 3 && a >= 4) l1 = 14100;
 					p1 = l1;
 				}
-			} else if ((res == 2 || res == 3) && (a == 2 || a == 3)) {
+			} else if (arm == 6) {
 				if (b == 0 || b == 1) {
 					int c1 = Pn[scan + 1] - Ln[count + 1];
 					if (c1 == 2 || c1 == 3) {
@@ -228,10 +263,10 @@ NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t 
 						}
 					}
 				}
-			} else if (a == 4 && (res == -2 || res == -3) && (-b == 2 || -b == 3)) {
+			} else if (arm == 7) {
 				if (res == -2 && -b == 2) p1--;
 				else { l0 = 12300; p1 += 2; p2 += 2; }
-			} else if ((res == -3 || res == -4 || res == -5 || res < -7) && (a == -3 || a == -4 || a == -5)) {
+			} else if (arm == 8) {
 				if (res < -7) { l0 = 12600; p1 = l1; }
 				else if (q >= 19) { l0 = 12200; p1 = l1; }
 				else if (q == 18) {
@@ -240,7 +275,7 @@ NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t 
 					else if (res == -3 && a <= -4) l1 = 14000;
 					p1 = l1;
 				}
-			} else if (a == -2 || a == -3) {
+			} else if (arm == 9) {
 				if (res == -2 || res == -3) {
 					if (-b > 0) { l0 = 12300; p1 += 2; p2 += 2; }
 					else if (res == -3 && q >= 21) l0 = 14500;
@@ -263,10 +298,10 @@ NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t 
 					if (-b > 1 && -b < 4) { l0 = 12300; p1 += 2; p2 += 2; }
 					else go = W5;
 				}
-			} else if (res == 0 || res == -1) go = W1;
-			else if (res == -2) go = W2;
-			else if (res == -3) go = W3;
-			else if (res < -rs) go = W5;
+			} else if (arm == 10) go = W1;
+			else if (arm == 11) go = W2;
+			else if (arm == 12) go = W3;
+			else if (arm == 13) go = W5;
 
 			if (go != NONE) {
 				const int left = row == 0 ? Pn[stage - 1] : P[stage - 1];
@@ -347,10 +382,67 @@ NHW_HDN void y_e16b_classify_col(const EncImg &im, int q, int j, int &w1, int &w
 	}
 }
 
+NHW_HDN void y_e16b_classify_col_w(const EncImg &im, int q, int j, int &w1, int &w3, int &w5)
+{
+	int16_t *P = im.proc, *L = im.ll1;
+	const int rs = res_setting_of(q);
+	{
+		// the band cell of the previous row ("left"), this row's band cell, LL1 code and reconstruction sample are
+		// carried in registers and the next row's are loaded a step ahead: no step waits for its predecessor's stores
+		int left = P[(j << 9) + 255];
+		int npv = P[(j << 9) + 256], nl = L[j], np = P[j];
+		for (int row = 0; row < 256; row++) {
+			const int scan = row * YW + j, count = row * 256 + j;
+			const int stage = (j << 9) + row + 256;
+			int pv = npv, lc = nl;
+			const int p = np, opv = pv, olc = lc;
+			if (row < 255) { npv = P[stage + 1]; nl = L[count + 256]; np = P[scan + YW]; }
+			if (lc < 12000) {
+				int res = p - lc;
+				lc = 0;
+				if (res == 0 || res == 1) {
+					if (pv == -7 || pv == -8) { if (left < 2 && left > -8) pv = -9; }
+				} else if (res == 2) {
+					if (pv > 15 && !(pv & 7)) pv--;
+					else if (pv == -7 || pv == -8) { if (left <= 1) pv = -9; }
+					else if (pv == -6) { if (left <= -1 && left > -8) pv = -9; }
+				} else if (res == 3) {
+					if (q >= 21) { lc = 144; w5++; }
+					else if (pv > 15 && !(pv & 7)) pv--;
+					else if (pv <= 0 && (((-pv) + 2) & 65532) == 8) { if (left <= 2) pv = -10; }
+				} else if (res > rs) {
+					lc = 141; w1++;
+					if (res == 4) {
+						if (pv == 7 || (pv & 65534) == 8) { if (left >= 0 && left < 8) pv += 2; }
+					} else if (res > 6) {
+						if (res > 7 && q >= 21) { lc = 148; w5++; w1++; }
+						else if (pv > 15 && !(pv & 7)) pv--;
+						else if (pv == -6 || pv == -7 || pv == -8) { if (left < 0 && left > -8) pv = -9; }
+					}
+				}
+			} else {
+				// every code left by the column pass is a multiple of 100; the byte code is code/100
+				const int v = lc;
+				const bool w1c = v == 14000 || v == 14100, w3c = v == 12100 || v == 12200 || v == 12300 || v == 12400;
+				const bool w5c = v == 14500, w31 = v == 12500 || v == 12600, w51 = v == 14900;
+				if (w1c || w3c || w5c || w31 || w51) {
+					lc = v / 100;
+					w1 += (w1c || w31 || w51) ? 1 : 0;
+					w3 += (w3c || w31) ? 1 : 0;
+					w5 += (w5c || w51) ? 1 : 0;
+				}
+			}
+			if (pv != opv) P[stage] = (int16_t)pv;
+			if (lc != olc) L[count] = (int16_t)lc;
+			left = pv;
+		}
+	}
+}
+
 NHW_HDN void y_e16b_classify_image(const EncImg &im, int q)
 {
 	int w1 = 0, w3 = 0, w5 = 0;
-	for (int j = 0; j < 256; j++) y_e16b_classify_col(im, q, j, w1, w3, w5);
+	for (int j = 0; j < 256; j++) y_e16b_classify_col_w(im, q, j, w1, w3, w5);
 	im.hdr->res1_word_len = w1;
 	im.hdr->res3_word_len = w3;
 	im.hdr->res5_word_len = w5;

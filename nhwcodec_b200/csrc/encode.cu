@@ -227,6 +227,8 @@ void run_wavefront(nhw_ctx *c, const char *label, const EncBatch &b, int n, WfGe
 // ---- residual coding (E16): columns 0..254 concurrently against a snapshot, then column 255
 __global__ void __launch_bounds__(256) k_e16_residual(EncBatch b, int q)
 {
+	__shared__ uint8_t lut[E16_LUT_SIZE];   // arm of the rule chain per (res, a, b), enc_y2.cuh: e16_arm
+	for (int k = threadIdx.x; k < E16_LUT_SIZE; k += 256) lut[k] = (uint8_t)e16_lut_entry(k, res_setting_of(q));
 	const EncImg im = make_img(b, blockIdx.x, 0);
 	const int4 *ps = reinterpret_cast<const int4 *>(im.proc);
 	int4 *pd = reinterpret_cast<int4 *>(im.aux);
@@ -238,16 +240,16 @@ __global__ void __launch_bounds__(256) k_e16_residual(EncBatch b, int q)
 	for (int i = threadIdx.x; i < E16_SNAP_L_CELLS / 8; i += 256) ld[i] = i < 65536 / 8 ? ls[i] : make_int4(0, 0, 0, 0);
 	__syncthreads();
 	const int j = threadIdx.x;
-	if (j < 255) y_e16_residual_col_w(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF);
+	if (j < 255) y_e16_residual_col_w(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF, lut);
 	__syncthreads();
-	if (j == 255) y_e16_residual_col_w(im, q, 255, im.proc, im.ll1);
+	if (j == 255) y_e16_residual_col_w(im, q, 255, im.proc, im.ll1, lut);
 }
 
 __global__ void __launch_bounds__(256) k_e16b_classify(EncBatch b, int q)
 {
 	const EncImg im = make_img(b, blockIdx.x, 0);
 	int w1 = 0, w3 = 0, w5 = 0;   // the reference only uses these as malloc sizes
-	y_e16b_classify_col(im, q, threadIdx.x, w1, w3, w5);
+	y_e16b_classify_col_w(im, q, threadIdx.x, w1, w3, w5);
 }
 
 // ---- serial LL2 stages with the band staged in shared memory: one warp per image copies the
@@ -951,48 +953,79 @@ __device__ __forceinline__ void build_nz_bitmap(const uint8_t *s, int count, uin
 	}
 }
 
+// 4 bits: which of the 4 stream bytes in a word are the +-8 codes (136 / 120), the only bytes the passes look for
+__device__ __forceinline__ uint32_t pm8_mask4(uint32_t w)
+{
+	return (~nz_mask4(w ^ (0x88888888u ^ 0x80808080u)) | ~nz_mask4(w ^ (0x78787878u ^ 0x80808080u))) & 15u;
+}
+__device__ __forceinline__ uint32_t pm8_mask16(const uint4 &a) { return pm8_mask4(a.x) | (pm8_mask4(a.y) << 4) | (pm8_mask4(a.z) << 8) | (pm8_mask4(a.w) << 12); }
+
+// The stream is read 16 bytes at a time; only the +-8 codes can start a pair (pass A) or change (passes B, C), so a
+// vector without one is skipped.  Pass A never turns a zero into a non-zero or back (136/120 -> 132..135 / 201), so
+// the non-zero bitmap of the stream after pass A is built from the same loads as the search for chain heads.
 __global__ void __launch_bounds__(PEEP_THREADS) k_peephole(EncBatch b)
 {
 	extern __shared__ __align__(16) uint32_t nzbits[];   // 262144 bits
 	__shared__ int n_heads, sel1, sel2;
+	__shared__ uint32_t nzsum[256];
 	const EncImg im = make_img(b, blockIdx.x, 0);
 	uint8_t *s = im.scan;
 	const int N = 262144;
-	uint8_t *out = reinterpret_cast<uint8_t *>(im.aux);                 // 262144 result bytes
+	const int tid = threadIdx.x;
+	uint4 *s4 = reinterpret_cast<uint4 *>(s);
+	uint4 *out4 = reinterpret_cast<uint4 *>(im.aux);                    // changed vectors, at their own index
 	int *heads = reinterpret_cast<int *>(im.aux) + N / 4;               // chain heads after them
-	if (threadIdx.x == 0) { n_heads = 0; sel1 = 0; sel2 = 0; }
+	if (tid == 0) { n_heads = 0; sel1 = 0; sel2 = 0; }
 	__syncthreads();
-	// pass A, phase 1: chain heads on the un-edited stream
-	for (int i = threadIdx.x; i < N - 4; i += PEEP_THREADS) {
-		const int x = s[i];
-		if ((x == 136 || x == 120) && peep_pair_candidate(s, i, N) && !peep_pair_candidate(s, i - 4, N))
-			heads[atomicAdd(&n_heads, 1)] = i;
+	// pass A, phase 1: chain heads on the un-edited stream (+ the non-zero bitmap)
+	for (int w = tid; w < N / 32; w += PEEP_THREADS) {
+		const uint4 a = s4[2 * w], c = s4[2 * w + 1];
+		nzbits[w] = nz_mask4(a.x) | (nz_mask4(a.y) << 4) | (nz_mask4(a.z) << 8) | (nz_mask4(a.w) << 12) | (nz_mask4(c.x) << 16) |
+		            (nz_mask4(c.y) << 20) | (nz_mask4(c.z) << 24) | (nz_mask4(c.w) << 28);
+		for (uint32_t m = pm8_mask16(a) | (pm8_mask16(c) << 16); m; m &= m - 1) {
+			const int i = 32 * w + __ffs(m) - 1;
+			if (i < N - 4 && peep_pair_candidate(s, i, N) && !peep_pair_candidate(s, i - 4, N)) heads[atomicAdd(&n_heads, 1)] = i;
+		}
 	}
 	__syncthreads();
 	// pass A, phase 2: merge along each chain (chains are disjoint)
-	for (int k = threadIdx.x; k < n_heads; k += PEEP_THREADS) peep_merge_chain(s, heads[k], N);
+	for (int k = tid; k < n_heads; k += PEEP_THREADS) peep_merge_chain(s, heads[k], N);
 	__syncthreads();
-	if (threadIdx.x < 4) { s[threadIdx.x] = 128; s[N - 4 + threadIdx.x] = 128; }
+	if (tid < 4) { s[tid] = 128; s[N - 4 + tid] = 128; }
+	if (tid == 0) { nzbits[0] &= ~15u; nzbits[N / 32 - 1] &= ~(15u << 28); }
 	__syncthreads();
-	__shared__ uint32_t nzsum[256];
-	build_nz_bitmap(s, N, nzbits, nzsum, threadIdx.x, PEEP_THREADS);
+	for (int j = tid >> 5; j < N / 1024; j += PEEP_THREADS >> 5) {   // second level of the bitmap
+		const uint32_t m = __ballot_sync(0xffffffffu, nzbits[32 * j + (tid & 31)] != 0);
+		if ((tid & 31) == 0) nzsum[j] = m;
+	}
 	__syncthreads();
 	const NzBits nz{nzbits, 0, N, nzsum};
-	// passes B + C: every output byte from the pass-A stream
+	// passes B + C: every byte that changes, from the pass-A stream; changed vectors are parked and written back
+	// once everybody has read
 	int a1 = 0, a2 = 0;
-	for (int i = threadIdx.x; i < N; i += PEEP_THREADS) {
-		int x1, x2;
-		out[i] = (uint8_t)peep_select_byte(s, nz, i, N, x1, x2);
-		a1 += x1;
-		a2 += x2;
+	uint32_t changed = 0;   // N / 16 / PEEP_THREADS = 32 vectors per thread
+	for (int w = tid, it = 0; w < N / 16; w += PEEP_THREADS, it++) {
+		uint4 a = s4[w];
+		uint32_t m = pm8_mask16(a);
+		if (!m) continue;
+		uint32_t v[4] = {a.x, a.y, a.z, a.w};
+		bool ch = false;
+		for (; m; m &= m - 1) {
+			const int k = __ffs(m) - 1, i = 16 * w + k;
+			int x1, x2;
+			const uint32_t old = (v[k >> 2] >> (8 * (k & 3))) & 255u, nw = (uint32_t)peep_select_byte(s, nz, i, N, x1, x2);
+			a1 += x1;
+			a2 += x2;
+			if (nw != old) { v[k >> 2] ^= (old ^ nw) << (8 * (k & 3)); ch = true; }
+		}
+		if (ch) { out4[w] = make_uint4(v[0], v[1], v[2], v[3]); changed |= 1u << it; }
 	}
 	if (a1) atomicAdd(&sel1, a1);
 	if (a2) atomicAdd(&sel2, a2);
 	__syncthreads();
-	const uint4 *o4 = reinterpret_cast<const uint4 *>(out);
-	uint4 *s4 = reinterpret_cast<uint4 *>(s);
-	for (int i = threadIdx.x; i < N / 16; i += PEEP_THREADS) s4[i] = o4[i];
-	if (threadIdx.x == 0) { im.hdr->select1 = sel1; im.hdr->select2 = sel2; }
+	for (int w = tid, it = 0; changed; w += PEEP_THREADS, it++)
+		if (changed >> it & 1u) { s4[w] = out4[w]; changed &= ~(1u << it); }
+	if (tid == 0) { im.hdr->select1 = sel1; im.hdr->select2 = sel2; }
 }
 
 // ---- entropy stage, one CTA per image, one thread per stream segment (enc_seg.cuh)

@@ -402,13 +402,16 @@ void host_e16(const EncImg &im, int q)
 	memcpy(im.aux + E16_SNAP_L_OFF, im.ll1, 65536 * sizeof(int16_t));
 	memset(im.aux + E16_SNAP_L_OFF + 65536, 0, 1024 * sizeof(int16_t));
 	const bool mem = getenv("HE_E16_MEM") != nullptr;   // the memory-resident walk instead of the register window
+	std::vector<uint8_t> lutv(E16_LUT_SIZE);
+	for (int k = 0; k < E16_LUT_SIZE; k++) lutv[k] = (uint8_t)e16_lut_entry(k, res_setting_of(q));
+	const uint8_t *lut = getenv("HE_E16_NOLUT") ? nullptr : lutv.data();
 	for (int jj = 254; jj >= 0; jj--) {
 		int j = getenv("HE_TOPDOWN") ? 254 - jj : jj;
 		if (mem) y_e16_residual_col(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF);
-		else y_e16_residual_col_w(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF);
+		else y_e16_residual_col_w(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF, lut);
 	}
 	if (mem) y_e16_residual_col(im, q, 255, im.proc, im.ll1);
-	else y_e16_residual_col_w(im, q, 255, im.proc, im.ll1);
+	else y_e16_residual_col_w(im, q, 255, im.proc, im.ll1, lut);
 }
 
 }  // namespace
