@@ -639,6 +639,68 @@ __global__ void __launch_bounds__(256) k_patterns(EncBatch b, int kind)
 	}
 }
 
+// ---- chroma LL (64 x 64) -> tree1 bytes + exw escapes + bit-1 planes (enc_c.cuh: c_ll_to_bytes_image,
+// c_ll_bit1_plane), one warp per plane, two planes (U, V) per CTA.  A sample that does not fit a byte repeats the
+// byte on its left (through any run of such samples) and goes to the escape list in raster order: a lane owns 128
+// consecutive samples, counts its escapes, the warp scans, lanes write.  The band is zeroed on the way.
+__global__ void __launch_bounds__(64) k_c_ll_quant(EncBatch b, int q)
+{
+	__shared__ __align__(16) int16_t sv[2][4096];
+	__shared__ __align__(16) uint8_t sb[2][4096], sf[2][4096];
+	const int v = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const EncImg im = make_img(b, blockIdx.x, v);
+	int16_t *P = im.cproc;
+	int16_t *V = sv[v];
+	uint8_t *B = sb[v];
+	for (int r = 0; r < 64; r++) {   // a row of 64 samples = 32 words
+		uint32_t *row = reinterpret_cast<uint32_t *>(P + r * CW);
+		reinterpret_cast<uint32_t *>(V + r * 64)[lane] = row[lane];
+		row[lane] = 0;
+	}
+	__syncwarp();
+	const int a0 = lane * 128;
+	int ne = 0;
+	for (int a = a0; a < a0 + 128; a++) {
+		int x = V[a];
+		const bool esc = (x > 255 || x < 0) && a > 0;
+		ne += esc ? 1 : 0;
+		x = x > 255 ? 255 : x < 0 ? 0 : x;
+		B[a] = (uint8_t)(x & 254);
+	}
+	int off = ne;
+	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += o; }
+	const int total = __shfl_sync(0xffffffffu, off, 31);
+	off -= ne;
+	__syncwarp();
+	uint8_t *exw = im.exw_uv + (v ? 16384 : 0) + 3 * off;
+	uint8_t *F = sf[v];
+	for (int a = a0; a < a0 + 128; a++) {
+		const int x = V[a];
+		uint8_t byte = B[a];
+		if ((x > 255 || x < 0) && a > 0) {
+			*exw++ = (uint8_t)(a >> 6);
+			if (x > 255) { *exw++ = (uint8_t)((a & 63) + 128); const int y = x - 255; *exw++ = (uint8_t)(y > 255 ? 255 : y); }
+			else { *exw++ = (uint8_t)(a & 63); *exw++ = (uint8_t)(x < -255 ? 255 : -x); }
+			int p = a - 1;
+			while (p > 0 && (V[p] > 255 || V[p] < 0)) p--;     // sample 0 never is an escape
+			byte = B[p];
+		}
+		F[a] = byte;
+	}
+	__syncwarp();
+	uint32_t *t = reinterpret_cast<uint32_t *>(im.tree1 + (v ? 20480 : 16384));
+	for (int k = lane; k < 1024; k += 32) t[k] = reinterpret_cast<const uint32_t *>(F)[k];
+	if (q > 15) {   // bit 1 of 8 consecutive bytes, MSB first (res_U_64 / res_V_64)
+		uint8_t *o = im.res_uv64 + (v ? 512 : 0);
+		for (int k = lane; k < 512; k += 32) {
+			int pk = 0;
+			for (int i = 0; i < 8; i++) pk |= ((F[8 * k + i] >> 1) & 1) << (7 - i);
+			o[k] = (uint8_t)pk;
+		}
+	}
+	if (lane == 0) { if (v) im.hdr->exw_v_len = 3 * total; else im.hdr->exw_u_len = 3 * total; }
+}
+
 // ---- E6c (enc_cells.cuh: y_e6c_apply_cells states the rule): un-tag LL1, push +-1 into the trial reconstruction at
 // the transposed position.  A CTA takes a 32 x 32 tile of LL1: tags are read (and cleared) row-wise, the +-1 go
 // through shared memory and are applied column-wise, so that a warp's 32 targets lie in one 128-byte span.
@@ -1474,11 +1536,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	idwt_chroma128(c, b, n);
 	run_plane_rows(c, "c_residual_tags", b, n, 128, [=] __device__(const EncImg &im, int r, int) { c_residual_tags_row(im, q, r); });
 	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_ll2s, QS, 128, b.c_proc, CS, 256, 128);
-	run_plane(c, "c_ll_quant", b, n, [=] __device__(const EncImg &im, int v) {
-		int e = c_ll_to_bytes_image(im, v);
-		if (v) im.hdr->exw_v_len = e; else im.hdr->exw_u_len = e;
-		if (q > 15) c_ll_bit1_plane(im, v);
-	});
+	NHW_LAUNCH_L(c, "c_ll_quant", k_c_ll_quant, n, 64, 0, b, q);
 	NHW_LAUNCH_L(c, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);
 
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
