@@ -51,7 +51,8 @@ ALG_BYTES = {
     "y_quant_scan": 524288 + 262144,                   # coefficient plane in, scan bytes out
     "c_quant_scan": 2 * 131072 + 131072,
     "y_e6d_correct": 2 * 131072 + 2 * 131072,          # trial reconstruction + LL1 in, both corrected out
-    "y_offset_pairs": 2 * 524288 * 3 // 4,
+    "y_offset_mult8": 2 * 524288 * 3 // 4,             # the three level-1 bands in and out
+    "y_e14_e15_tags": 2 * 524288 * 3 // 4,
     "y_offset_patterns": 2 * 131072,
     "y_e20_cleanup": 2 * 524288 * 3 // 4,
     "y_peephole": 2 * 262144,
@@ -59,8 +60,10 @@ ALG_BYTES = {
     "y_e16_residual": 2 * 131072 + 131072,
     "y_e16b_classify": 2 * 131072 + 131072,
     "y_e18_lists": 3 * 131072,
-    "y_recons1_serial": 2 * 131072,
-    "y_recons0_serial": 2 * 131072,
+    "y_recons_patterns": 2 * 2 * 131072,               # two calls: level-2 region in, tags + im_jpeg samples out
+    "y_recons0_quant": 2 * 98304,                      # level-2 detail bands in, im_jpeg out
+    "y_recons1_quant": 2 * 98304,
+    "y_e6a_tag": 98304 + 131072,
     "y_recons0_shrink": 2 * 131072,
     "y_ll2_code": 32768 + 3 * 16384,
     "c_ll_quant": 2 * 2 * 131072,

@@ -10,10 +10,8 @@ rm -f gpurun_out/prof_*.ncu-rep gpurun_out/launches.csv
 # 1) every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 # 2) full captures (with source) of single launches of the kernels we report on
-ncu --set full --clock-control none --import-source on -k regex:k_front_luma -s 1 -c 1 -o gpurun_out/prof_front_luma -f $B2 > gpurun_out/ncu_full1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_dwt_level -s 4 -c 3 -o gpurun_out/prof_dwt_level -f $B2 > gpurun_out/ncu_full2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_entropy -c 1 -o gpurun_out/prof_entropy -f $B2 > gpurun_out/ncu_full3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_ll2_code -c 1 -o gpurun_out/prof_ll2_code -f $B2 > gpurun_out/ncu_full4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_y_quant_scan -c 1 -o gpurun_out/prof_quant_scan -f $B2 > gpurun_out/ncu_full5.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:kd_serial_front -c 1 -o gpurun_out/prof_dec_front -f $B2 > gpurun_out/ncu_full6.log 2>&1
+for k in k_front_luma k_entropy k_ll2_code k_y_quant_scan k_patterns k_e20_bands k_e16_residual k_peephole kd_serial_front; do
+	ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o gpurun_out/prof_$k -f $B2 > gpurun_out/ncu_full_$k.log 2>&1
+done
+ncu --set full --clock-control none --import-source on -k regex:k_dwt_level -s 4 -c 3 -o gpurun_out/prof_k_dwt_level -f $B2 > gpurun_out/ncu_full_dwt.log 2>&1
 ls -la gpurun_out
