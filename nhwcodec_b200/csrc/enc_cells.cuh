@@ -291,6 +291,21 @@ NHW_HD bool y_e14_e15_cells(const int16_t *R /* row r */, int r, int g, int q, i
 		w[0] = c > 0 ? e14_value(R[c - 1], q, ratio, r, c - 1) : 0;
 		w[9] = e14_value(R[c + 8], q, ratio, r, c + 8);
 		w[10] = e14_value(R[c + 9], q, ratio, r, c + 9);
+		// Rewrites only ever take cells out of the classes the rules test, so a turn that cannot fire on the values
+		// before the stage cannot fire at all: the group can only change through the turns at columns c-1 .. c+8,
+		// and those need three like-signed 4..7 cells in a row or a +-8 in the middle.
+		{
+			const int wm = c > 1 ? e14_value(R[c - 2], q, ratio, r, c - 2) : 0;
+			uint32_t pos = 0, neg = 0, mid = 0;   // bit i = column c - 2 + i
+			for (int i = 0; i < 12; i++) {
+				const int v = i == 0 ? wm : w[i - 1];
+				if (in4to7(v)) pos |= 1u << i;
+				if (in_m7to_m4(v)) neg |= 1u << i;
+				if (v == 8 || v == -8) mid |= 1u << i;
+			}
+			const uint32_t can = ((pos & (pos << 1) & (pos >> 1)) | (neg & (neg << 1) & (neg >> 1)) | mid) & 0x7feu;   // turns c-1 .. c+8
+			if (!can) { for (int k = 0; k < 8; k++) { o[k] = w[k + 1]; changed |= o[k] != raw[k]; } return changed; }
+		}
 		if (c > j0 && e15_active(w[0])) {   // replay the turns between the last inactive cell and the group
 			int s = c - 1;
 			while (s > j0 && e15_active(e14_value(R[s - 1], q, ratio, r, s - 1))) s--;
@@ -408,3 +423,68 @@ NHW_HD void e20_cells8(const int16_t *up, const int16_t *row, const int16_t *dn,
 }
 // the cell just right of the group (only needed where that is column j1 = 256 of pass 1)
 NHW_HD int e20_edge_cell(const int16_t *row, int S, const E20Pass &g, int r) { return e20_final_cell(row, S, g, r, g.j1); }
+
+// ---- chroma residual tags (nhw_encoder.c:2372-2424; row form c_residual_tags_row), q >= 18.  A visited cell whose
+// residual and the next one are both medium and like-signed drops a pair tag (12400 / 12600) into the first free of
+// its three band cells and the cursor skips the next cell; otherwise a large residual drops 12900 / 13000.  The band
+// cells of a sample are its own, so whether the pair rule fires is a function of the data before the stage, and
+// "fire, then skip one" picks every other cell of a run of such cells: the parity of the offset in the run.
+// One coupling: the residual that follows column 127 is read at column 128, which is the first band cell of the
+// row's column 0 -- that cell's turn is replayed where it matters.
+NHW_HD bool c_tag_free(const int16_t *P, int scan)
+{
+	return nhw_iabs(P[scan + 128]) < 8 || nhw_iabs(P[scan + 32768]) < 8 || nhw_iabs(P[scan + 32768 + 128]) < 8;
+}
+NHW_HD bool c_tag_pair_fires(int d, int n) { return (d > 3 && d < 7 && n > 2 && n < 7) || (d < -3 && d > -7 && n < -2 && n > -8); }
+// the tag a visited cell drops when it does not fire the pair rule (0: none)
+NHW_HD int c_tag_single(int d, int n, int res_uv)
+{
+	if (nhw_iabs(d) <= res_uv) return 0;
+	if (d > 0) return 12900;
+	if (d == -5) return n < 0 ? 13000 : 0;
+	return 13000;
+}
+// residual of column j of row r, j <= 128; column 128 = the first band cell of column 0 after that cell's turn
+NHW_HD int c_tag_diff(const int16_t *P, const int16_t *L, int r, int j, int res_uv)
+{
+	const int scan = r * CW + j, count = r * 128 + j;
+	if (j < 128) return P[scan] - L[count];
+	int v = P[scan];
+	if (v < 12000 && nhw_iabs(v) < 8) {   // still free: does column 0 (always visited) drop a tag here?
+		const int d0 = P[r * CW] - L[r * 128], n0 = P[r * CW + 1] - L[r * 128 + 1];
+		if (c_tag_pair_fires(d0, n0)) v = d0 > 0 ? 12400 : 12600;
+		else { const int t = c_tag_single(d0, n0, res_uv); if (t) v = t; }
+	}
+	return v - L[count];
+}
+// tags[k] = what cell 8g+k drops (0: nothing); the plane is only read: the caller drops the tags once every group of
+// the row has decided (a dropped tag makes a band cell look taken)
+NHW_HD void c_residual_tags_cells(const int16_t *P, const int16_t *L, int q, int r, int g, int *tags)
+{
+	for (int k = 0; k < 8; k++) tags[k] = 0;
+	if (q < 18) return;
+	const int res_uv = q > 17 ? 4 : 5, c = g * 8;
+	int d[10];
+	for (int k = 0; k < 9; k++) d[k] = c + k <= 128 ? c_tag_diff(P, L, r, c + k, res_uv) : 0;
+	// is the first cell of the group skipped?  Count the cells right before it that fire in a row.
+	bool skip = false;
+	{
+		int k = c - 1, cnt = 0, dn = d[0];
+		while (k >= 0) {
+			const int dk = P[r * CW + k] - L[r * 128 + k];
+			if (!(c_tag_pair_fires(dk, dn) && c_tag_free(P, r * CW + k))) break;
+			cnt++;
+			dn = dk;
+			k--;
+		}
+		skip = (cnt & 1) != 0;
+	}
+	for (int k = 0; k < 8; k++) {
+		const int j = c + k, scan = r * CW + j;
+		if (skip) { skip = false; continue; }
+		int tag;
+		if (c_tag_pair_fires(d[k], d[k + 1]) && c_tag_free(P, scan)) { tag = d[k] > 0 ? 12400 : 12600; skip = true; }
+		else tag = c_tag_single(d[k], d[k + 1], res_uv);
+		tags[k] = tag;
+	}
+}

@@ -639,6 +639,18 @@ __global__ void __launch_bounds__(256) k_patterns(EncBatch b, int kind)
 	}
 }
 
+// ---- chroma residual tags (enc_cells.cuh: c_residual_tags_cells): 16 rows of a plane per CTA, a thread decides for 8
+// cells on the plane as it is, the tags are dropped after the barrier
+__global__ void __launch_bounds__(256) k_c_residual_tags(EncBatch b, int q)
+{
+	const EncImg im = make_img(b, blockIdx.y >> 1, blockIdx.y & 1);
+	const int idx = blockIdx.x * 256 + threadIdx.x, r = idx >> 4, g = idx & 15;
+	int tags[8];
+	c_residual_tags_cells(im.cproc, im.cll1, q, r, g, tags);
+	__syncthreads();
+	for (int k = 0; k < 8; k++) if (tags[k]) c_drop_tag(im.cproc, r * CW + g * 8 + k, tags[k]);
+}
+
 // ---- chroma LL (64 x 64) -> tree1 bytes + exw escapes + bit-1 planes (enc_c.cuh: c_ll_to_bytes_image,
 // c_ll_bit1_plane), one warp per plane, two planes (U, V) per CTA.  A sample that does not fit a byte repeats the
 // byte on its left (through any run of such samples) and goes to the escape list in raster order: a lane owns 128
@@ -1534,7 +1546,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		st8(im.cjpeg + r * CW + g * 8, o);
 	});
 	idwt_chroma128(c, b, n);
-	run_plane_rows(c, "c_residual_tags", b, n, 128, [=] __device__(const EncImg &im, int r, int) { c_residual_tags_row(im, q, r); });
+	NHW_LAUNCH_L(c, "c_residual_tags", k_c_residual_tags, dim3(8, 2 * n), 256, 0, b, q);
 	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_ll2s, QS, 128, b.c_proc, CS, 256, 128);
 	NHW_LAUNCH_L(c, "c_ll_quant", k_c_ll_quant, n, 64, 0, b, q);
 	NHW_LAUNCH_L(c, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);

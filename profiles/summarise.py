@@ -35,7 +35,24 @@ if os.path.exists(launches):
         a[1] += ns
     total = sum(v[1] for v in agg.values())
     out.append("## Launch list (ncu --metrics gpu__time_duration.sum --clock-control none), %d launches, %.2f ms total\n" % (len(rows), total / 1e6))
-    out.append("bench.py --batch 256 --steps 1 --warmup 3 (device-API steps, one profiled pass, host-API encode and decode steps, synth). Cold-cache, serialised: compare shares.\n")
+    out.append("bench.py --steps 2 --warmup 3 --no-cpu-baseline: the bench workload (batch 4096): device-API steps, one profiled pass, host-API encode and decode steps in 512-image sub-chunks, synth. Cold-cache, serialised: compare shares.\n")
+    # the device-API encode steps alone (grids over 4096 images / 8192 planes): the shares bench.py's kernel table must agree with
+    dev = collections.OrderedDict()
+    for r in rows:
+        g = [int(x) for x in re.findall(r"\d+", r[8])]
+        nm = short(r[4])
+        if not (4096 in g or 8192 in g) or nm.startswith("void at::") or nm.startswith("kd_") or nm in ("k_synth",):
+            continue
+        a = dev.setdefault(nm, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[14])
+    dtot = sum(v[1] for v in dev.values())
+    if dtot:
+        out.append("### Device-API encode steps only (grids over 4096 images), share of the step\n")
+        out.append("| kernel | launches | total ms | share |\n|---|---|---|---|")
+        for k, (n, ns) in sorted(dev.items(), key=lambda kv: -kv[1][1])[:25]:
+            out.append("| `%s` | %d | %.3f | %.1f%% |" % (k, n, ns / 1e6, 100 * ns / dtot))
+        out.append("")
     out.append("| kernel block x grid | launches | total ms | share |\n|---|---|---|---|")
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append("| `%s` | %d | %.3f | %.1f%% |" % (k, n, ns / 1e6, 100 * ns / total))

@@ -779,7 +779,12 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		} else host_c_recons_cells(im, ratio, 0);
 		inv_level(im.cjpeg, im.cproc, 256, 128, tmp);
 		TN("syn0_proc", im.cproc, 65536 * 2);
-		for (int r = 127; r >= 0; r--) c_residual_tags_row(im, q, r);
+		if (getenv("HE_ROWFORM")) { for (int r = 127; r >= 0; r--) c_residual_tags_row(im, q, r); }
+		else {
+			std::vector<int> tg(128 * 128, 0);
+			for (int r = 127; r >= 0; r--) for (int g = 15; g >= 0; g--) c_residual_tags_cells(im.cproc, im.cll1, q, r, g, &tg[r * 128 + g * 8]);
+			for (int r = 127; r >= 0; r--) for (int j = 127; j >= 0; j--) if (tg[r * 128 + j]) c_drop_tag(im.cproc, r * 256 + j, tg[r * 128 + j]);
+		}
 		copy_region(im.cproc, 256, im.cll2s, 128, 128);
 		TN("tags_proc", im.cproc, 65536 * 2);
 		int e = c_ll_to_bytes_image(im, v);
