@@ -132,22 +132,31 @@ static int rows_grid_cap()
 // k_groups: f does its own loads and stores (stages that never read what they write).
 // k_groups_inplace: f only reads and returns the group's final values; the CTA synchronises, then stores, so a
 // group never sees another group's result (rows never straddle CTAs, and these stages only look along their row).
+// A CTA takes GROUP_ITER consecutive blocks of 256 groups.  Measured: 4 blocks per CTA is slower for the stages with
+// data-dependent replays (level-2 quantiser 1.6 -> 2.7 ms) and no faster for the others, so it stays at 1.
+#define GROUP_ITER 1
 template <typename F>
 __global__ void __launch_bounds__(256) k_groups(EncBatch b, int gshift, F f)
 {
-	const int idx = blockIdx.x * 256 + threadIdx.x;
-	f(make_img(b, blockIdx.y, 0), idx >> gshift, idx & ((1 << gshift) - 1));
+	const EncImg im = make_img(b, blockIdx.y, 0);
+	#pragma unroll
+	for (int it = 0; it < GROUP_ITER; it++) {
+		const int idx = (blockIdx.x * GROUP_ITER + it) * 256 + threadIdx.x;
+		f(im, idx >> gshift, idx & ((1 << gshift) - 1));
+	}
 }
 template <typename F>
 __global__ void __launch_bounds__(256) k_groups_inplace(EncBatch b, int gshift, F f)
 {
-	const int idx = blockIdx.x * 256 + threadIdx.x;
 	const EncImg im = make_img(b, blockIdx.y, 0);
-	const int r = idx >> gshift, g = idx & ((1 << gshift) - 1);
-	int o[8];
-	const bool changed = f(im, r, g, o);
-	__syncthreads();
-	if (changed) st8(im.proc + r * YW + g * 8, o);
+	for (int it = 0; it < GROUP_ITER; it++) {
+		const int idx = (blockIdx.x * GROUP_ITER + it) * 256 + threadIdx.x;
+		const int r = idx >> gshift, g = idx & ((1 << gshift) - 1);
+		int o[8];
+		const bool changed = f(im, r, g, o);
+		__syncthreads();   // every group of these rows has read; the next iteration works on other rows
+		if (changed) st8(im.proc + r * YW + g * 8, o);
+	}
 }
 // dead-zone quantiser of the level-2 detail bands into im_jpeg (enc_cells.cuh: y_recons_quant_cells); the band is only read
 __device__ __forceinline__ void recons_quant_group(const EncImg &im, int r, int g, int m1, int part)
@@ -159,27 +168,31 @@ __device__ __forceinline__ void recons_quant_group(const EncImg &im, int r, int 
 	else for (int x = 0; x < 8; x++) if (mask >> x & 1) J[x] = (int16_t)o[x];
 }
 template <typename F>
-__global__ void __launch_bounds__(256) k_plane_groups(EncBatch b, int gshift, F f)
-{
-	const int idx = blockIdx.x * 256 + threadIdx.x;
-	f(make_img(b, blockIdx.y >> 1, blockIdx.y & 1), idx >> gshift, idx & ((1 << gshift) - 1), (int)(blockIdx.y & 1));
-}
-template <typename F>
-void run_plane_groups(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, int gshift, F f)
-{
-	NHW_LAUNCH_L(c, label, k_plane_groups, dim3((rows << gshift) / 256, 2 * n), 256, 0, b, gshift, f);
-}
-template <typename F>
 void run_groups(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, int gshift, F f)
 {
-	NHW_LAUNCH_L(c, label, k_groups, dim3((rows << gshift) / 256, n), 256, 0, b, gshift, f);
+	NHW_LAUNCH_L(c, label, k_groups, dim3((rows << gshift) / 256 / GROUP_ITER, n), 256, 0, b, gshift, f);
 }
 template <typename F>
 void run_groups_inplace(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, int gshift, F f)
 {
-	NHW_LAUNCH_L(c, label, k_groups_inplace, dim3((rows << gshift) / 256, n), 256, 0, b, gshift, f);
+	NHW_LAUNCH_L(c, label, k_groups_inplace, dim3((rows << gshift) / 256 / GROUP_ITER, n), 256, 0, b, gshift, f);
 }
 
+template <typename F>
+__global__ void __launch_bounds__(256) k_plane_groups(EncBatch b, int gshift, F f)
+{
+	const EncImg im = make_img(b, blockIdx.y >> 1, blockIdx.y & 1);
+	#pragma unroll
+	for (int it = 0; it < GROUP_ITER; it++) {
+		const int idx = (blockIdx.x * GROUP_ITER + it) * 256 + threadIdx.x;
+		f(im, idx >> gshift, idx & ((1 << gshift) - 1), (int)(blockIdx.y & 1));
+	}
+}
+template <typename F>
+void run_plane_groups(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, int gshift, F f)
+{
+	NHW_LAUNCH_L(c, label, k_plane_groups, dim3((rows << gshift) / 256 / GROUP_ITER, 2 * n), 256, 0, b, gshift, f);
+}
 template <typename F>
 void run_image(nhw_ctx *c, const char *label, const EncBatch &b, int n, F f)
 {
@@ -720,26 +733,30 @@ __global__ void __launch_bounds__(256) k_e6c_apply(EncBatch b)
 {
 	__shared__ int8_t dt[32][33];
 	const EncImg im = make_img(b, blockIdx.y, 0);
-	const int r0 = (blockIdx.x >> 3) * 32, j0 = (blockIdx.x & 7) * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-	#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const int rr = ty + 8 * i;
-		int16_t *L = im.ll1 + (r0 + rr) * 256 + j0 + tx;
-		const int l = *L;
-		int d = 0;
-		if (l > 14000) { *L = (int16_t)(l - 16000); d = 1; }
-		else if (l > 10000) { *L = (int16_t)(l - 12000); d = -1; }
-		dt[rr][tx] = (int8_t)d;
-	}
-	__syncthreads();
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 	int16_t *P = im.proc;
-	#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const int jj = ty + 8 * i, d = dt[tx][jj], r = r0 + tx, j = j0 + jj;
-		if (!d) continue;
-		if (r < 128 && j >= 128) P[2 * r + ((j - 128) << 10) + YW] += d;
-		else if (r >= 128 && j < 128) P[2 * (r - 128) + (j << 10) + 1] += d;
-		else if (r >= 128 && j >= 128) P[2 * (r - 128) + ((j - 128) << 10) + YW + 1] += d;
+	for (int tile = blockIdx.x * 4; tile < blockIdx.x * 4 + 4; tile++) {
+		const int r0 = (tile >> 3) * 32, j0 = (tile & 7) * 32;
+		#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const int rr = ty + 8 * i;
+			int16_t *L = im.ll1 + (r0 + rr) * 256 + j0 + tx;
+			const int l = *L;
+			int d = 0;
+			if (l > 14000) { *L = (int16_t)(l - 16000); d = 1; }
+			else if (l > 10000) { *L = (int16_t)(l - 12000); d = -1; }
+			dt[rr][tx] = (int8_t)d;
+		}
+		__syncthreads();
+		#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const int jj = ty + 8 * i, d = dt[tx][jj], r = r0 + tx, j = j0 + jj;
+			if (!d) continue;
+			if (r < 128 && j >= 128) P[2 * r + ((j - 128) << 10) + YW] += d;
+			else if (r >= 128 && j < 128) P[2 * (r - 128) + (j << 10) + 1] += d;
+			else if (r >= 128 && j >= 128) P[2 * (r - 128) + ((j - 128) << 10) + YW + 1] += d;
+		}
+		__syncthreads();
 	}
 }
 
@@ -818,15 +835,18 @@ __global__ void __launch_bounds__(256) k_e20_bands(EncBatch b, int q, int ratio)
 	}
 }
 
-// ---- E19: restore the level-2 region from the resIII snapshot (y_e19_restore_row), one thread per cell pair
-__global__ void __launch_bounds__(128) k_e19_restore(EncBatch b)
+// ---- E19: restore the level-2 region from the resIII snapshot (y_e19_restore_row), one thread per 8 cells, 32 rows per CTA
+__global__ void __launch_bounds__(256) k_e19_restore(EncBatch b)
 {
 	const EncImg im = make_img(b, blockIdx.y, 0);
-	const int r = blockIdx.x, j = threadIdx.x * 2;
-	const uint32_t w = *reinterpret_cast<const uint32_t *>(im.ll2s + r * 256 + j);
-	int v0 = (int16_t)(w & 0xffff), v1 = (int16_t)(w >> 16);
-	if (r < 128 && j < 128) { if (v0 <= 8000) v0 = 0; if (v1 <= 8000) v1 = 0; }
-	*reinterpret_cast<uint32_t *>(im.proc + r * YW + j) = (uint32_t)(uint16_t)v0 | ((uint32_t)(uint16_t)v1 << 16);
+	#pragma unroll
+	for (int it = 0; it < 4; it++) {
+		const int idx = (blockIdx.x * 4 + it) * 256 + threadIdx.x, r = idx >> 5, j = (idx & 31) * 8;
+		int v[8];
+		ld8(im.ll2s + r * 256 + j, v);
+		if (r < 128 && j < 128) { for (int k = 0; k < 8; k++) if (v[k] <= 8000) v[k] = 0; }
+		st8(im.proc + r * YW + j, v);
+	}
 }
 
 // ---- offsetY loop 4 + serpentine scan, pointwise (enc_point.cuh): 16 rows per CTA, 8 cells per thread
@@ -1476,7 +1496,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH_L(c, "y_recons_patterns", k_patterns, n, 256, 0, b, 0);
 	run_groups(c, "y_recons1_quant", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { recons_quant_group(im, r, g, ratio, 1); });
 	idwt_luma256(c, b, n);
-	NHW_LAUNCH_L(c, "y_e6c_apply", k_e6c_apply, dim3(64, n), 256, 0, b);
+	NHW_LAUNCH_L(c, "y_e6c_apply", k_e6c_apply, dim3(16, n), 256, 0, b);
 	NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(32, n), 256, 0, b);
 	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
 
@@ -1513,7 +1533,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH_L(c, "y_e18_tails", k_e18_tails, dim3(3, n), 32, 0, b, q);
 
 	// ---- clean-up, quantisation to bytes, scan, peephole (nhw_encoder.c:1893-2252)
-	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(256, n), 128, 0, b);
+	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(8, n), 256, 0, b);
 	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_bands, dim3(3, n), 256, 0, b, q, ratio);
 	run_groups_inplace(c, "y_offset_mult8", b, n, 512, 6, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_offset_mult8_cells(im.proc, r, g, o); });
 	NHW_LAUNCH_L(c, "y_offset_patterns", k_patterns, n, 256, 0, b, 1);
