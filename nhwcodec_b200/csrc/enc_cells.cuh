@@ -217,9 +217,12 @@ NHW_HD int y_recons_quant_cells(const int16_t *R /* band row, before the stage *
 			T[k] = (cl && c + k < 255 && pairs57_class(v[k + 1]) == cl && !par) ? (cl == 1 ? 15700 : 15800) : v[k];
 		}
 	}
-	// replay up to the group
+	// replay up to the group -- unless the two cells before it are plainly inert (|v| <= 4: no tag, no pair tag, no
+	// rewrite of their right neighbour, and a 7 -> 8 rewrite cannot reach them): then the cursor lands on the group's
+	// first cell with nothing pending
 	int j = c, clean = 0;
-	while (j > jr0) {
+	const bool inert = c - 2 >= jr0 && nhw_iabs(R[c - 1]) <= 4 && nhw_iabs(R[c - 2]) <= 4;
+	while (!inert && j > jr0) {
 		j--;
 		clean = rq_val(R, j, jr0, part) > 15000 ? 0 : clean + 1;
 		if (clean == 4) { j += 2; break; }
