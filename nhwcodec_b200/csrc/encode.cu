@@ -868,11 +868,17 @@ __global__ void __launch_bounds__(256) k_y_quant_scan(EncBatch b, int m1)
 		o[7] = (int16_t)(w.w & 0xffff); o[8] = (int16_t)(w.w >> 16);
 		o[9] = i + 8 < 512 * 512 ? (int)P[i + 8] : 0;
 		uint32_t by[8];
+		int big = 0;
+#pragma unroll
+		for (int t = 1; t <= 8; t++) big = max(big, nhw_iabs(o[t]));
+		uint32_t lo, hi;
+		if (big <= 6 && m1 > 6) { lo = 0x80808080u; hi = 0x80808080u; }   // |o| <= 6 quantises to "zero" whatever its neighbours are
+		else {
 #pragma unroll
 		for (int t = 0; t < 8; t++) by[t] = (uint32_t)y_quant_byte(o[t], o[t + 1], o[t + 2], c + t >= 1, c + t < 511, m1);
-		uint32_t lo, hi;
 		if (rr & 1) { lo = by[3] | (by[2] << 8) | (by[1] << 16) | (by[0] << 24); hi = by[7] | (by[6] << 8) | (by[5] << 16) | (by[4] << 24); }
 		else { lo = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24); hi = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24); }
+		}
 		const int strip = c >> 2, off = (rr >> 1) * 8 + (rr & 1) * 4;
 		*reinterpret_cast<uint32_t *>(sout + strip * 64 + off) = lo;
 		*reinterpret_cast<uint32_t *>(sout + (strip + 1) * 64 + off) = hi;
@@ -903,6 +909,14 @@ __global__ void __launch_bounds__(256) k_c_quant_scan(EncBatch b, int m2)
 			o[4] = (int16_t)(w.z & 0xffff); o[5] = (int16_t)(w.z >> 16);
 			o[6] = (int16_t)(w.w & 0xffff); o[7] = (int16_t)(w.w >> 16);
 			o[8] = i + 8 < 65536 ? (int)P[i + 8] : 0;
+			int big = 0;
+#pragma unroll
+			for (int t = 0; t < 8; t++) big = max(big, nhw_iabs(o[t]));
+			if (big <= 6 && m2 > 6) {   // |o| <= 6 quantises to "zero" whatever its neighbours are
+#pragma unroll
+				for (int t = 0; t < 8; t++) by[v][t] = 128u;
+				continue;
+			}
 #pragma unroll
 			for (int t = 0; t < 8; t++) {
 				int run = 0;
