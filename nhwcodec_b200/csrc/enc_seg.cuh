@@ -105,7 +105,9 @@ struct SegStream {
 	int p1, p2;             // [p1, p2) is the stream
 	int S;                  // segment size, (p2-p1)/SEG_THREADS
 	NzBits nz;              // non-zero bitmap of [p1, p2)
+	const int *bnd;         // optional: segment t = [bnd[t], bnd[t+1]) instead of equal sizes (work-balanced cut)
 };
+NHW_HD int seg_start(const SegStream &st, int t) { return st.bnd ? st.bnd[t] : st.p1 + t * st.S; }
 
 // number of consecutive 128s starting at i (s[i]==128), never past p2
 NHW_HD int seg_run_len(const SegStream &st, int i) { return nz_next(st.nz, i, st.p2) - i; }
@@ -188,7 +190,7 @@ NHW_HD int peep_select_byte(const uint8_t *d, const NzBits &nz, int i, int N, in
 // first position of segment t that starts a token owned by t
 NHW_HD int seg_first_token(const SegStream &st, int t)
 {
-	const int start = st.p1 + t * st.S;
+	const int start = seg_start(st, t);
 	int i = start;
 	for (int k = 1; k <= 4; k++)
 		if (i - k >= st.p1 && st.s[i - k] > 131 && st.s[i - k] < 136) { i = i - k + 5; break; }
@@ -201,7 +203,7 @@ NHW_HD int seg_first_token(const SegStream &st, int t)
 template <typename Add>
 NHW_HD void seg_stats(const SegStream &st, int t, Add add /* (is_run, index) */)
 {
-	const int start = st.p1 + t * st.S, end = start + st.S;
+	const int start = seg_start(st, t), end = seg_start(st, t + 1);
 	const int last = st.p2 - 1;   // the reference's loop never starts a token at the last byte
 	int i = start;
 	if (i < end && st.s[i] == 128 && i > st.p1 && st.s[i - 1] == 128) i += seg_run_len(st, i);
@@ -222,7 +224,7 @@ template <typename Emit, typename Bit1, typename Bit2>
 NHW_HD int seg_emit(const SegStream &st, int t, const int *sym_rank, const int *run_rank, int select, bool zone,
                     Emit emit, Bit1 bit1, Bit2 bit2)
 {
-	const int end = st.p1 + (t + 1) * st.S, last = st.p2 - 1;
+	const int end = seg_start(st, t + 1), last = st.p2 - 1;
 	int i = seg_first_token(st, t);
 	auto put = [&](int pos) -> int {
 		pos &= 0xffff;

@@ -1154,7 +1154,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
 	extern __shared__ __align__(16) uint32_t nzbits[];   // 262144 bits (luma part), reused for the chroma part
 	__shared__ uint32_t nzsum[256];
 	__shared__ int hist_sym[256], hist_run[256];
-	__shared__ int sbits[SEG_THREADS + 1], sn1[SEG_THREADS + 1], sn2[SEG_THREADS + 1];
+	__shared__ int sbits[SEG_THREADS + 1], sn1[SEG_THREADS + 1], sn2[SEG_THREADS + 1], bnd[SEG_THREADS + 1];
 	__shared__ uint32_t s_weight[354];
 	__shared__ uint16_t s_sym[354];
 	__shared__ int s_select, s_k, s_b, s_rc, s_bad, s_word0;
@@ -1178,7 +1178,41 @@ __global__ void __launch_bounds__(SEG_THREADS) k_entropy(EncBatch b)
 		__syncthreads();
 		build_nz_bitmap(s + p1, p2 - p1, nzbits, nzsum, t, SEG_THREADS);
 		__syncthreads();
-		SegStream ss{s, p1, p2, S, NzBits{nzbits, p1, p2 - p1, nzsum}};
+		// Work-balanced segments: thread t gets the stretch between the (t*T/256)-th and the ((t+1)*T/256)-th non-zero
+		// byte (T of them in the stream).  With equal-sized segments a warp waited for its busiest lane while the
+		// lanes over flat image areas had nothing to do (6 of 32 lanes active on average).
+		{
+			const int W = (p2 - p1) / 32 / SEG_THREADS;
+			int cnt = 0;
+			for (int k = 0; k < W; k++) cnt += __popc(nzbits[t * W + k]);
+			sbits[t] = cnt;
+			__syncthreads();
+			if (t == 0) {
+				int run = 0;
+				for (int k = 0; k < SEG_THREADS; k++) { const int x = sbits[k]; sbits[k] = run; run += x; }
+				sbits[SEG_THREADS] = run;
+			}
+			__syncthreads();
+			const int T = sbits[SEG_THREADS];
+			int pos = t ? p2 : p1;
+			if (t && T > 0) {
+				int rem = (int)((long long)t * T / SEG_THREADS);
+				int lo = 0, hi = SEG_THREADS - 1;            // last j with sbits[j] <= rem
+				while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sbits[mid] <= rem) lo = mid; else hi = mid - 1; }
+				rem -= sbits[lo];
+				for (int w = lo * W; w < (lo + 1) * W; w++) {
+					const uint32_t m = nzbits[w];
+					const int pc = __popc(m);
+					if (rem < pc) { pos = p1 + 32 * w + (int)__fns(m, 0, rem + 1); break; }
+					rem -= pc;
+				}
+			}
+			__syncthreads();
+			bnd[t] = pos;
+			if (t == 0) bnd[SEG_THREADS] = p2;
+			__syncthreads();
+		}
+		SegStream ss{s, p1, p2, S, NzBits{nzbits, p1, p2 - p1, nzsum}, bnd};
 		seg_stats(ss, t, [&](bool run, int idx) { atomicAdd(run ? &hist_run[idx] : &hist_sym[idx], 1); });
 		__syncthreads();
 		st.rle_buf[t] = hist_sym[t];

@@ -195,7 +195,16 @@ int host_entropy(const EncImg &im, int part, int &word0)
 	for (int i = p1; i < p2; i++) if (s[i] != 128) nzb[(i - p1) >> 5] |= 1u << ((i - p1) & 31);
 	std::vector<uint32_t> nzs((p2 - p1) / 1024, 0);
 	for (size_t j = 0; j < nzs.size(); j++) for (int k = 0; k < 32; k++) if (nzb[32 * j + k]) nzs[j] |= 1u << k;
-	SegStream ss{s, p1, p2, S, NzBits{nzb.data(), p1, p2 - p1, nzs.data()}};
+	// work-balanced segment cut of k_entropy: segment t starts at the (t*T/256)-th non-zero byte
+	std::vector<int> bnd(SEG_THREADS + 1, p2);
+	bnd[0] = p1;
+	if (!getenv("HE_EQUAL_SEGMENTS")) {
+		std::vector<int> nzpos;
+		for (int i = p1; i < p2; i++) if (s[i] != 128) nzpos.push_back(i);
+		const long long T = (long long)nzpos.size();
+		for (int t = 1; t < SEG_THREADS && T > 0; t++) bnd[t] = nzpos[(size_t)(t * T / SEG_THREADS)];
+	}
+	SegStream ss{s, p1, p2, S, NzBits{nzb.data(), p1, p2 - p1, nzs.data()}, getenv("HE_EQUAL_SEGMENTS") ? nullptr : bnd.data()};
 	for (int i = 0; i < 256; i++) { st.rle_buf[i] = 0; st.rle_128[i] = 0; }
 	for (int t = SEG_THREADS - 1; t >= 0; t--)
 		seg_stats(ss, t, [&](bool run, int idx) { if (run) st.rle_128[idx]++; else st.rle_buf[idx]++; });
