@@ -41,7 +41,7 @@ if os.path.exists(launches):
     for r in rows:
         g = [int(x) for x in re.findall(r"\d+", r[8])]
         nm = short(r[4])
-        if not (4096 in g or 8192 in g) or nm.startswith("void at::") or nm.startswith("kd_") or nm in ("k_synth",):
+        if not (4096 in g or 8192 in g) or nm.startswith("void at::") or "kd_" in nm or "decode_chunk" in nm or nm in ("k_synth",):
             continue
         a = dev.setdefault(nm, [0, 0.0])
         a[0] += 1

@@ -22,7 +22,8 @@ def he(ref):
     return he_run
 
 
-@pytest.mark.parametrize("kind,seed,q", [("natural", 1000, 20), ("noise", 5, 23), ("textured", 1002, 17)])
+@pytest.mark.parametrize("kind,seed,q", [("natural", 1000, 20), ("noise", 5, 23), ("textured", 1002, 17), ("natural", 7, 18),
+                                          ("textured", 11, 21), ("natural", 3, 22), ("noise", 9, 19)])
 def test_host_schedule_encode(he, kind, seed, q):
     pix = getattr(synth, kind)(seed)
     ok, first_bad, stream, ref_stream = he.compare(pix, q, verbose=False)
