@@ -73,7 +73,7 @@ ALG_BYTES = {
 # DRAM bytes per image (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture / images in that
 # launch) of the kernels profiled this round, and the capture they come from (profiles/).
 NCU_TRAFFIC = {
-    "k_front_luma": (1658785, "profiles/r01b_ncu_summary.md (942.5 MB read + 756.1 MB written per 1024 images)"),
+    "k_front_luma": (1666870, "profiles/r01c_ncu_summary.md (946.5 MB read + 760.4 MB written per 1024 images)"),
 }
 
 
@@ -98,7 +98,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -108,6 +108,10 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark(self):
+        """samples before this point (warm-up) are dropped unless the timed region turns out too short to hold two"""
+        self.first = len(self.lines)
 
     def stop(self):
         if not self.proc:
@@ -119,7 +123,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        first = getattr(self, "first", 0)
+        window = "timed region"
+        if len(self.lines) - first < 2:
+            first, window = 0, "warm-up + timed region (timed region shorter than two samples)"
+        self.window = window
+        for ln in self.lines[first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -132,7 +141,7 @@ class ClockSampler:
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": self.window, "reasons": sorted(reasons)}
 
 
 def peaks():
@@ -262,16 +271,17 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (value) ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()       # already streaming when the timed region starts; only its samples from then on are used
     for _ in range(args.warmup):
         codec.encode_device(rgb, q, out, lens, status)
     assert int((status != 0).sum().item()) == 0, "encode reported per-image errors"
     mean_stream = float(lens.float().mean().item())
-    sampler = ClockSampler(local)
     barrier()
     codec.profile(0)          # the timed region runs un-instrumented (sub-chunks side by side on the codec's lanes)
     launches0 = codec.launches
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):

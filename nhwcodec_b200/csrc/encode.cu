@@ -338,6 +338,10 @@ __global__ void __launch_bounds__(128) k_recons_ll2_wave(EncBatch b, int q, int 
 // LL2 -> bytes + DPCM coding in parallel form (enc_ll_par.cuh), one CTA of 128 threads per image.
 // shared memory: band copy (later: output offsets), sample values (later: step links), res4 rows.
 #define LL2_CODE_SMEM (LL2_SMEM_BYTES + 16384 * 2 + 128 * 32 + 128 * 4 + 64)   // band (later: bytes + chain marks), samples (later: steps), res4 rows, counters
+// chain marks and step links are walked one 128-position segment per thread: the segments are laid out 33 / 65 words
+// apart so that the lanes of a warp hit different shared-memory banks
+#define LL2_VI(i) ((i) + (((i) >> 7) << 2))
+#define LL2_II(i) ((i) + (((i) >> 7) << 1))
 __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 {
 	extern __shared__ __align__(16) int16_t sP[];
@@ -379,11 +383,20 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 	int *tot = cnt + 2;                                       // [0] escapes, [1] code bytes, [2] raw samples
 	__shared__ int seg_cnt[3][129];
 	__shared__ int seg_exit[128], seg_merge[128];
-	{
-		int ne = 0;
-		for (int a = 128 * t; a < 128 * t + 128; a++) ne += ll2_is_escape(V[a], a) ? 1 : 0;
-		seg_cnt[0][t] = ne;
+	// pass 1, thread = column: bytes of every cell (coalesced), escapes marked per row by warp ballots
+	__shared__ uint32_t escw[128][4];
+	for (int k = 0; k < 128; k++) {
+		const int a = 128 * k + t;
+		const int v = V[a];
+		const bool esc = ll2_is_escape(v, a);
+		const int cl = v > 255 ? 255 : v < 0 ? 0 : v;
+		sx[a] = (uint8_t)(cl & 254);
+		if (!esc) { im.tree1[a] = (uint8_t)(cl & 254); im.ch_res[a] = (uint8_t)cl; }
+		const uint32_t m = __ballot_sync(0xffffffffu, esc);
+		if ((t & 31) == 0) escw[k][t >> 5] = m;
 	}
+	__syncthreads();
+	seg_cnt[0][t] = __popc(escw[t][0]) + __popc(escw[t][1]) + __popc(escw[t][2]) + __popc(escw[t][3]);   // thread = row from here on
 	__syncthreads();
 	if (t == 0) {
 		int run = 0;
@@ -398,28 +411,23 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 		}
 	}
 	__syncthreads();
-	{
+	{   // pass 2: the escapes of row t in raster order
 		int e = 3 * seg_cnt[0][t];
-		for (int a = 128 * t; a < 128 * t + 128; a++) {
-			int v = V[a];
-			if (ll2_is_escape(v, a)) {
+		for (int w = 0; w < 4; w++)
+			for (uint32_t m = escw[t][w]; m; m &= m - 1) {
+				const int a = 128 * t + 32 * w + __ffs(m) - 1;
+				const int v = V[a];
 				im.exw[e++] = (uint8_t)(a >> 7);
 				if (v > 255) { im.exw[e++] = (uint8_t)((a & 127) + 128); const int y = v - 255; im.exw[e++] = (uint8_t)(y > 255 ? 255 : y); }
 				else { im.exw[e++] = (uint8_t)(a & 127); im.exw[e++] = (uint8_t)(v < -255 ? 255 : -v); }
 				int p = a - 1;
 				while (ll2_is_escape(V[p], p)) p--;               // position 0 never is one
-				v = V[p];
-				v = v > 255 ? 255 : v < 0 ? 0 : v;
-				sx[a] = (uint8_t)(v & 254);
-				im.tree1[a] = sx[a];
-				im.ch_res[a] = sx[a];
-			} else {
-				v = v > 255 ? 255 : v < 0 ? 0 : v;
-				sx[a] = (uint8_t)(v & 254);
-				im.tree1[a] = sx[a];
-				im.ch_res[a] = (uint8_t)v;
+				int u = V[p];
+				u = u > 255 ? 255 : u < 0 ? 0 : u;
+				sx[a] = (uint8_t)(u & 254);                        // (predecessors are looked up in V, not in sx)
+				im.tree1[a] = (uint8_t)(u & 254);
+				im.ch_res[a] = (uint8_t)(u & 254);
 			}
-		}
 		if (t == 0) for (int k = 0; k < 256; k++) sx[16384 + k] = 0;   // tree1[16384..] is still zero while luma is coded
 	}
 	__syncthreads();
@@ -440,17 +448,17 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 	__syncthreads();
 	const int mode = cnt[1] > 299 ? 2 : (cnt[0] + cnt[1] > 179 ? 1 : 0);
 	for (int i = t; i < 16384; i += 128) {
-		vis[i] = 0;
+		vis[LL2_VI(i)] = 0;
 		if (i >= 1) {
 			const LlStep s = ll_dpcm_step(x, i, mode, q);
-			info[i] = (uint16_t)(((s.next - i) << 2) | ((s.nbytes - 1) << 1) | s.raw);
+			info[LL2_II(i)] = (uint16_t)(((s.next - i) << 2) | ((s.nbytes - 1) << 1) | s.raw);
 		}
 	}
 	__syncthreads();
 	{
 		int i = t ? 128 * t : 1;
 		const int end = 128 * t + 128;
-		while (i < end) { vis[i] = 1; i += info[i] >> 2; }
+		while (i < end) { vis[LL2_VI(i)] = 1; i += info[LL2_II(i)] >> 2; }
 		seg_exit[t] = i;
 	}
 	__syncthreads();
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 		for (int k = 1; k < 128; k++) {
 			const int end = 128 * k + 128;
 			int i = p;
-			while (i < end && vis[i] != 1) { vis[i] = 2; i += info[i] >> 2; }
+			while (i < end && vis[LL2_VI(i)] != 1) { vis[LL2_VI(i)] = 2; i += info[LL2_II(i)] >> 2; }
 			if (i < end) { seg_merge[k] = i; p = seg_exit[k]; }     // met the speculative chain: it is the true one from here
 			else { seg_merge[k] = end; p = i; }                     // never met it inside this segment
 		}
@@ -470,8 +478,8 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 		const int m = seg_merge[t];
 		int nb = 0, nr = 0;
 		for (int i = 128 * t; i < 128 * t + 128; i++) {
-			if (i < m && vis[i] == 1) vis[i] = 0;
-			if (vis[i]) { const int inf = info[i]; nb += 1 + ((inf >> 1) & 1); nr += inf & 1; }
+			if (i < m && vis[LL2_VI(i)] == 1) vis[LL2_VI(i)] = 0;
+			if (vis[LL2_VI(i)]) { const int inf = info[LL2_II(i)]; nb += 1 + ((inf >> 1) & 1); nr += inf & 1; }
 		}
 		seg_cnt[1][t] = nb;
 		seg_cnt[2][t] = nr;
@@ -487,7 +495,7 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 	{
 		int off = 1 + seg_cnt[1][t], nm = seg_cnt[2][t];
 		for (int i = 128 * t; i < 128 * t + 128; i++) {
-			if (!vis[i]) continue;
+			if (!vis[LL2_VI(i)]) continue;
 			const LlStep s = ll_dpcm_step(x, i, mode, q);
 			im.llcode[off++] = s.b[0];
 			if (s.nbytes == 2) im.llcode[off++] = s.b[1];
