@@ -676,10 +676,13 @@ __global__ void __launch_bounds__(256) k_c_residual_tags(EncBatch b, int q)
 // c_ll_bit1_plane), one warp per plane, two planes (U, V) per CTA.  A sample that does not fit a byte repeats the
 // byte on its left (through any run of such samples) and goes to the escape list in raster order: a lane owns 128
 // consecutive samples, counts its escapes, the warp scans, lanes write.  The band is zeroed on the way.
+#define CLV(a) ((a) + (((a) >> 7) << 1))
+#define CLB(a) ((a) + (((a) >> 7) << 2))
 __global__ void __launch_bounds__(64) k_c_ll_quant(EncBatch b, int q)
 {
-	__shared__ __align__(16) int16_t sv[2][4096];
-	__shared__ __align__(16) uint8_t sb[2][4096], sf[2][4096];
+	// a lane walks 128 consecutive samples: lanes are laid out 65 / 33 words apart (bank-conflict-free)
+	__shared__ __align__(16) int16_t sv[2][4096 + 64];
+	__shared__ __align__(16) uint8_t sb[2][4096 + 128], sf[2][4096 + 128];
 	const int v = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const EncImg im = make_img(b, blockIdx.x, v);
 	int16_t *P = im.cproc;
@@ -687,18 +690,18 @@ __global__ void __launch_bounds__(64) k_c_ll_quant(EncBatch b, int q)
 	uint8_t *B = sb[v];
 	for (int r = 0; r < 64; r++) {   // a row of 64 samples = 32 words
 		uint32_t *row = reinterpret_cast<uint32_t *>(P + r * CW);
-		reinterpret_cast<uint32_t *>(V + r * 64)[lane] = row[lane];
+		{ const uint32_t w = row[lane]; const int a = r * 64 + 2 * lane; V[CLV(a)] = (int16_t)(w & 0xffff); V[CLV(a + 1)] = (int16_t)(w >> 16); }
 		row[lane] = 0;
 	}
 	__syncwarp();
 	const int a0 = lane * 128;
 	int ne = 0;
 	for (int a = a0; a < a0 + 128; a++) {
-		int x = V[a];
+		int x = V[CLV(a)];
 		const bool esc = (x > 255 || x < 0) && a > 0;
 		ne += esc ? 1 : 0;
 		x = x > 255 ? 255 : x < 0 ? 0 : x;
-		B[a] = (uint8_t)(x & 254);
+		B[CLB(a)] = (uint8_t)(x & 254);
 	}
 	int off = ne;
 	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += o; }
@@ -708,26 +711,26 @@ __global__ void __launch_bounds__(64) k_c_ll_quant(EncBatch b, int q)
 	uint8_t *exw = im.exw_uv + (v ? 16384 : 0) + 3 * off;
 	uint8_t *F = sf[v];
 	for (int a = a0; a < a0 + 128; a++) {
-		const int x = V[a];
-		uint8_t byte = B[a];
+		const int x = V[CLV(a)];
+		uint8_t byte = B[CLB(a)];
 		if ((x > 255 || x < 0) && a > 0) {
 			*exw++ = (uint8_t)(a >> 6);
 			if (x > 255) { *exw++ = (uint8_t)((a & 63) + 128); const int y = x - 255; *exw++ = (uint8_t)(y > 255 ? 255 : y); }
 			else { *exw++ = (uint8_t)(a & 63); *exw++ = (uint8_t)(x < -255 ? 255 : -x); }
 			int p = a - 1;
-			while (p > 0 && (V[p] > 255 || V[p] < 0)) p--;     // sample 0 never is an escape
-			byte = B[p];
+			while (p > 0 && (V[CLV(p)] > 255 || V[CLV(p)] < 0)) p--;     // sample 0 never is an escape
+			byte = B[CLB(p)];
 		}
-		F[a] = byte;
+		F[CLB(a)] = byte;
 	}
 	__syncwarp();
 	uint32_t *t = reinterpret_cast<uint32_t *>(im.tree1 + (v ? 20480 : 16384));
-	for (int k = lane; k < 1024; k += 32) t[k] = reinterpret_cast<const uint32_t *>(F)[k];
+	for (int k = lane; k < 1024; k += 32) t[k] = *reinterpret_cast<const uint32_t *>(F + CLB(4 * k));
 	if (q > 15) {   // bit 1 of 8 consecutive bytes, MSB first (res_U_64 / res_V_64)
 		uint8_t *o = im.res_uv64 + (v ? 512 : 0);
 		for (int k = lane; k < 512; k += 32) {
 			int pk = 0;
-			for (int i = 0; i < 8; i++) pk |= ((F[8 * k + i] >> 1) & 1) << (7 - i);
+			for (int i = 0; i < 8; i++) pk |= ((F[CLB(8 * k + i)] >> 1) & 1) << (7 - i);
 			o[k] = (uint8_t)pk;
 		}
 	}
@@ -859,9 +862,12 @@ __global__ void __launch_bounds__(256) k_e19_restore(EncBatch b)
 
 // ---- offsetY loop 4 + serpentine scan, pointwise (enc_point.cuh): 16 rows per CTA, 8 cells per thread
 // and step; the bytes go through shared memory so that they leave in 64-byte runs of the scan order.
+#define YQ_STRIP 68
 __global__ void __launch_bounds__(256) k_y_quant_scan(EncBatch b, int m1)
 {
-	__shared__ __align__(16) uint8_t sout[128 * 64];
+	// a strip's 64 bytes are 68 bytes apart: the lanes of a warp store to every other strip, which at 64 bytes apart
+	// was one bank for the whole warp (32-way conflict on both stores, 97 % of the store wavefronts)
+	__shared__ __align__(16) uint8_t sout[128 * YQ_STRIP];
 	const EncImg im = make_img(b, blockIdx.y, 0);
 	const int band = blockIdx.x, tid = threadIdx.x;
 	const int16_t *P = im.proc;
@@ -888,20 +894,22 @@ __global__ void __launch_bounds__(256) k_y_quant_scan(EncBatch b, int m1)
 		else { lo = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24); hi = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24); }
 		}
 		const int strip = c >> 2, off = (rr >> 1) * 8 + (rr & 1) * 4;
-		*reinterpret_cast<uint32_t *>(sout + strip * 64 + off) = lo;
-		*reinterpret_cast<uint32_t *>(sout + (strip + 1) * 64 + off) = hi;
+		*reinterpret_cast<uint32_t *>(sout + strip * YQ_STRIP + off) = lo;
+		*reinterpret_cast<uint32_t *>(sout + (strip + 1) * YQ_STRIP + off) = hi;
 	}
 	__syncthreads();
 	for (int idx = tid; idx < 512; idx += 256) {
 		const int strip = idx >> 2, part = idx & 3;
-		*reinterpret_cast<uint4 *>(im.scan + strip * 2048 + band * 64 + part * 16) = *reinterpret_cast<const uint4 *>(sout + strip * 64 + part * 16);
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(sout + strip * YQ_STRIP + part * 16);
+		*reinterpret_cast<uint4 *>(im.scan + strip * 2048 + band * 64 + part * 16) = make_uint4(src[0], src[1], src[2], src[3]);
 	}
 }
 
 // ---- offsetUV + interleaved chroma scan, pointwise: both planes of 16 rows per CTA
+#define CQ_STRIP 272
 __global__ void __launch_bounds__(256) k_c_quant_scan(EncBatch b, int m2)
 {
-	__shared__ __align__(16) uint8_t sout[32 * 256];
+	__shared__ __align__(16) uint8_t sout[32 * CQ_STRIP];   // strips 272 bytes apart: lane = strip, 16-byte stores
 	const EncImg imu = make_img(b, blockIdx.y, 0), imv = make_img(b, blockIdx.y, 1);
 	const int band = blockIdx.x, tid = threadIdx.x;
 	for (int q = tid; q < 16 * 32; q += 256) {
@@ -946,13 +954,13 @@ __global__ void __launch_bounds__(256) k_c_quant_scan(EncBatch b, int m2)
 			wv[k] = by[0][t0] | (by[1][t0] << 8) | (by[0][t1] << 16) | (by[1][t1] << 24);
 		}
 		const int strip = c >> 3;
-		*reinterpret_cast<uint4 *>(sout + strip * 256 + (rr >> 1) * 32 + (rr & 1) * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+		*reinterpret_cast<uint4 *>(sout + strip * CQ_STRIP + (rr >> 1) * 32 + (rr & 1) * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
 	}
 	__syncthreads();
 	for (int idx = tid; idx < 512; idx += 256) {
 		const int strip = idx >> 4, part = idx & 15;
 		*reinterpret_cast<uint4 *>(imu.scan + 262144 + strip * 4096 + band * 256 + part * 16) =
-		    *reinterpret_cast<const uint4 *>(sout + strip * 256 + part * 16);
+		    *reinterpret_cast<const uint4 *>(sout + strip * CQ_STRIP + part * 16);
 	}
 }
 
