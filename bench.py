@@ -459,7 +459,7 @@ def run_ours(args):
                     "h2d_alone_ms": round(h2d_alone_ms, 3), "h2d_alone_GBps": round(B * PIX_BYTES / h2d_alone_ms / 1e6, 2)},
             "gpu_launches": int(launches),
             "kernel_table": "per-kernel ms from a separate serialised pass (CUDA events around every launch); in the timed "
-                            "regions the host-buffer calls run 8 (encode) / 8 (decode) sub-chunks on 4 streams",
+                            "regions the host-buffer calls run 16 (encode) / 8 (decode) sub-chunks on 4 streams",
             "clocks": clocks,
             "roofline": roofline,
             "frontend": frontend,

@@ -448,7 +448,7 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 	uint64_t pos = 0;
 	offsets[0] = 0;
 	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
-		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, env_int("NHW_SUBS_ENCODE", 8, 1, NHW_MAX_SUB),
+		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, env_int("NHW_SUBS_ENCODE", 16, 1, NHW_MAX_SUB),
 		                              env_int("NHW_LANES_ENCODE", 4, 1, NHW_LANES));
 		step = p.count;
 		nhw_ctx v[NHW_MAX_SUB];
