@@ -527,7 +527,7 @@ void run_ll2_staged(nhw_ctx *c, const char *label, const EncBatch &b, int n, siz
 // cells.  The serial tails of the lists (pruning, packing) are 3 x n independent single-thread jobs: they run in
 // their own launch, one job per warp, so that thousands of them are resident at once (k_e18_tails).
 #define E18_PART 21800        // scratch entries per list; longer lists (never seen) take the one-list-at-a-time path
-__global__ void __launch_bounds__(256) k_e18_lists(EncBatch b, int q)
+__global__ void __launch_bounds__(256, 4) k_e18_lists(EncBatch b, int q)
 {
 	__shared__ int cnt[3][257];
 	__shared__ int too_long;
@@ -538,14 +538,18 @@ __global__ void __launch_bounds__(256) k_e18_lists(EncBatch b, int q)
 			int16_t *L = im.ll1 + row * 256;
 			const uint4 raw = reinterpret_cast<const uint4 *>(L)[lane];
 			const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
-			int v[8], mem[8], w[8][3], n[3] = {0, 0, 0};
+			int v[8], n[3] = {0, 0, 0};
+			uint32_t mw[8];   // membership bits (24..26) and the three word values (one byte each) of a cell
 #pragma unroll
 			for (int t = 0; t < 8; t++) {
 				const int orig = (int16_t)(wv[t >> 1] >> ((t & 1) * 16));
 				const int j = 8 * lane + t;
-				if (j < 254) v[t] = y_e18_classify(orig, q, mem[t], w[t]);
-				else { v[t] = write ? 0 : orig; mem[t] = 0; }       // the stage clears columns 254, 255
-				for (int k = 0; k < 3; k++) n[k] += (mem[t] >> k) & 1;
+				int mem = 0, w[3] = {0, 0, 0};
+				if (j < 254) v[t] = y_e18_classify(orig, q, mem, w);
+				else v[t] = write ? 0 : orig;                       // the stage clears columns 254, 255
+				mw[t] = ((uint32_t)mem << 24) | ((uint32_t)(w[0] & 255)) | ((uint32_t)(w[1] & 255) << 8) | ((uint32_t)(w[2] & 255) << 16);
+#pragma unroll
+				for (int k = 0; k < 3; k++) n[k] += (mem >> k) & 1;
 			}
 			int off[3];
 			for (int k = 0; k < 3; k++) {
@@ -561,7 +565,7 @@ __global__ void __launch_bounds__(256) k_e18_lists(EncBatch b, int q)
 					int o = off[k];
 #pragma unroll
 					for (int t = 0; t < 8; t++)
-						if ((mem[t] >> k) & 1) { pos[o] = (uint8_t)(8 * lane + t); wrd[o] = (uint8_t)w[t][k]; o++; }
+						if ((mw[t] >> (24 + k)) & 1u) { pos[o] = (uint8_t)(8 * lane + t); wrd[o] = (uint8_t)(mw[t] >> (8 * k)); o++; }
 					if (lane == 31) pos[o] = 254;     // end-of-row marker after the row's last entry
 				}
 				reinterpret_cast<uint4 *>(L)[lane] =
