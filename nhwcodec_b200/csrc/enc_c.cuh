@@ -247,65 +247,73 @@ NHW_HD void c_scan_strip(const EncImg &im, int strip /* 0..31 */, int is_v)
 // the luma LL code.  in: tree1[16384..24575]; io: im.llcode (highres_comp) from y_res_comp on.
 // Core: x = the LL bytes indexed as in tree1 (x[16384..24575] valid and already masked with 252, readable up
 // to x[24575 + 20]); out[j0..] receives the code; returns the end index.
+// One iteration of the coder's loop at position i: it emits exactly one byte and moves on by 1..17 positions, and it
+// carries no state from one iteration to the next -- a pure function of the position (the parallel form,
+// k_c_ll_code, evaluates it everywhere and then finds the positions the coder really visits).
+NHW_HD int c_ll_step(const uint8_t *x, int i, int &byte)
+{
+	int scan = x[i] - x[i - 1];
+	int count = x[i + 1] - x[i];
+	if (scan == 0 && count == 0) {
+		int a = 0, res = 0;
+		while (x[i + a + 2] == x[i + a + 1]) {
+			a++;
+			if (a < 7) continue;
+			res = 1;             // a==7 || res==1
+			if (a >= 14) break;
+		}
+		i += a + 1;
+		if (res == 1) byte = 64 + (7 << 3) + a - 7;
+		else {
+			i++;
+			int code = 64 + (a << 3);
+			int d = x[i] - x[i - 1], d2 = x[i + 1] - x[i];
+			if (d == 4) {
+				if (d2 == -4) {
+					if (x[i + 2] - x[i + 1] == 0) { code += 3; i += 2; }
+					else { code += 2; i++; }
+				} else code += 1;
+			} else if (d == -4) {
+				if (d2 == 4) {
+					if (x[i + 2] - x[i + 1] == 0) { code += 4; i += 2; }
+					else { code += 5; i++; }
+				} else code += 6;
+			} else if (d == 8) code += 7;
+			else i--;
+			byte = code;
+		}
+	} else if (nhw_iabs(scan) <= 4 && nhw_iabs(count) <= 4) {
+		int res = 0;
+		if (!scan && count == 4) res = 0;
+		else if (!scan && count == -4) res = 1;
+		else if (scan == 4 && !count) res = 2;
+		else if (scan == -4 && !count) res = 3;
+		else if (scan == 4 && count == 4) res = 4;
+		else if (scan == 4 && count == -4) res = 5;
+		else if (scan == -4 && count == 4) res = 6;
+		else if (scan == -4 && count == -4) res = 7;
+		int d3 = x[i + 2] - x[i + 1];
+		if (d3 == 0) { byte = 192 + (res << 2); i += 2; }
+		else if (d3 == 4) { byte = 192 + (res << 2) + 1; i += 2; }
+		else if (d3 == -4) { byte = 192 + (res << 2) + 2; i += 2; }
+		else if (d3 == 8) { byte = 192 + (res << 2) + 3; i += 2; }
+		else { byte = ((scan + 16) << 1) + ((count + 16) >> 2); i++; }
+	} else if (nhw_iabs(scan) <= 16 && nhw_iabs(count) <= 16) {
+		scan += 16; count += 16;
+		if (scan == 32 || count == 32) byte = 128 + (x[i] >> 2);
+		else { byte = (scan << 1) + (count >> 2); i++; }
+	} else byte = 128 + (x[i] >> 2);
+	byte &= 255;
+	return i + 1;
+}
 NHW_HDN int ll_dpcm_chroma_core(const uint8_t *x, uint8_t *out, int j0)
 {
 	int j = j0;
 	out[j++] = x[16384];
-	int a = 0, res = 0;
-	for (int i = 16385; i < 24576; i++) {
-		int scan = x[i] - x[i - 1];
-		int count = x[i + 1] - x[i];
-		if (scan == 0 && count == 0) {
-			while (x[i + a + 2] == x[i + a + 1]) {
-				a++;
-				if (a < 7) continue;
-				res = 1;             // a==7 || res==1
-				if (a >= 14) break;
-			}
-			i += a + 1;
-			if (res == 1) out[j] = (uint8_t)(64 + (7 << 3) + a - 7);
-			else {
-				i++;
-				int code = 64 + (a << 3);
-				int d = x[i] - x[i - 1], d2 = x[i + 1] - x[i];
-				if (d == 4) {
-					if (d2 == -4) {
-						if (x[i + 2] - x[i + 1] == 0) { code += 3; i += 2; }
-						else { code += 2; i++; }
-					} else code += 1;
-				} else if (d == -4) {
-					if (d2 == 4) {
-						if (x[i + 2] - x[i + 1] == 0) { code += 4; i += 2; }
-						else { code += 5; i++; }
-					} else code += 6;
-				} else if (d == 8) code += 7;
-				else i--;
-				out[j] = (uint8_t)code;
-			}
-			a = 0;
-			res = 0;
-			j++;
-		} else if (nhw_iabs(scan) <= 4 && nhw_iabs(count) <= 4) {
-			if (!scan && count == 4) res = 0;
-			else if (!scan && count == -4) res = 1;
-			else if (scan == 4 && !count) res = 2;
-			else if (scan == -4 && !count) res = 3;
-			else if (scan == 4 && count == 4) res = 4;
-			else if (scan == 4 && count == -4) res = 5;
-			else if (scan == -4 && count == 4) res = 6;
-			else if (scan == -4 && count == -4) res = 7;
-			int d3 = x[i + 2] - x[i + 1];
-			if (d3 == 0) { out[j++] = (uint8_t)(192 + (res << 2)); i += 2; }
-			else if (d3 == 4) { out[j++] = (uint8_t)(192 + (res << 2) + 1); i += 2; }
-			else if (d3 == -4) { out[j++] = (uint8_t)(192 + (res << 2) + 2); i += 2; }
-			else if (d3 == 8) { out[j++] = (uint8_t)(192 + (res << 2) + 3); i += 2; }
-			else { out[j++] = (uint8_t)(((scan + 16) << 1) + ((count + 16) >> 2)); i++; }
-			res = 0;
-		} else if (nhw_iabs(scan) <= 16 && nhw_iabs(count) <= 16) {
-			scan += 16; count += 16;
-			if (scan == 32 || count == 32) out[j++] = (uint8_t)(128 + (x[i] >> 2));
-			else { out[j++] = (uint8_t)((scan << 1) + (count >> 2)); i++; }
-		} else out[j++] = (uint8_t)(128 + (x[i] >> 2));
+	for (int i = 16385; i < 24576;) {
+		int byte;
+		i = c_ll_step(x, i, byte);
+		out[j++] = (uint8_t)byte;
 	}
 	return j;
 }

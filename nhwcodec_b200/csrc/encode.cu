@@ -1393,25 +1393,79 @@ __global__ void k_zero_bytes(uint8_t *base, size_t slot, size_t off, size_t coun
 // ---- chroma LL code: a serial coder (each step looks a few bytes ahead and skips a variable distance), run by
 // one thread per image out of shared memory; the warp stages the 8192 input bytes and the output.
 #define CLL_PAD 32
-__global__ void __launch_bounds__(32) k_c_ll_code(EncBatch b)
+// Parallel form of the chroma LL coder (enc_c.cuh: c_ll_step is a pure function of the position and emits one byte):
+// the step is evaluated at all 8191 positions, every thread walks the orbit of its 32-position segment's first
+// position (speculation), one thread stitches the segments (the true chain enters a segment somewhere and runs
+// until it meets the speculative one or leaves), a CTA scan of the visit counts gives the output offsets.
+// Per-position arrays are laid out 36 bytes per segment so that the lanes of a warp hit different banks.
+#define CLL_SW(i) ((i) + (((i) >> 5) << 2))
+__global__ void __launch_bounds__(256) k_c_ll_code(EncBatch b)
 {
 	__shared__ __align__(16) uint8_t sx[8192 + CLL_PAD];
-	__shared__ __align__(16) uint8_t so[8192 + 16];
-	__shared__ int jend;
+	__shared__ uint8_t snext[8192 + 1024], sbyte[8192 + 1024], vis[8192 + 1024];
+	__shared__ int seg_exit[256], seg_merge[256], seg_cnt[257];
 	const EncImg im = make_img(b, blockIdx.x, 0);
-	const int lane = threadIdx.x;
-	for (int k = lane; k < (8192 + CLL_PAD) / 4; k += 32) {
+	const int t = threadIdx.x;
+	for (int k = t; k < (8192 + CLL_PAD) / 4; k += 256) {
 		uint32_t w = reinterpret_cast<const uint32_t *>(im.tree1 + 16384)[k];
 		if (k < 2048) w &= 0xfcfcfcfcu;   // x[i] &= 252 (compress_pixel.c:886)
 		reinterpret_cast<uint32_t *>(sx)[k] = w;
 	}
-	__syncwarp();
-	if (lane == 0) jend = ll_dpcm_chroma_core(sx - 16384, so, 0);
-	__syncwarp();
-	const int j0 = im.hdr->y_res_comp, cnt = jend;
-	for (int k = lane; k < cnt; k += 32) im.llcode[j0 + k] = so[k];
-	for (int k = lane; k < 2048; k += 32) reinterpret_cast<uint32_t *>(im.tree1 + 16384)[k] = reinterpret_cast<const uint32_t *>(sx)[k];
-	if (lane == 0) im.hdr->end_ch_res = j0 + cnt;
+	__syncthreads();
+	const uint8_t *x = sx - 16384;        // indexed as in tree1
+	for (int p = t; p < 8192; p += 256) {
+		vis[CLL_SW(p)] = 0;
+		if (p >= 1) {
+			int byte;
+			const int nx = c_ll_step(x, 16384 + p, byte);
+			snext[CLL_SW(p)] = (uint8_t)(nx - (16384 + p));
+			sbyte[CLL_SW(p)] = (uint8_t)byte;
+		}
+	}
+	__syncthreads();
+	{
+		int p = t ? 32 * t : 1;
+		const int end = 32 * t + 32;
+		while (p < end) { vis[CLL_SW(p)] = 1; p += snext[CLL_SW(p)]; }
+		seg_exit[t] = p;
+	}
+	__syncthreads();
+	if (t == 0) {
+		int p = seg_exit[0];
+		seg_merge[0] = 0;
+		for (int k = 1; k < 256; k++) {
+			const int end = 32 * k + 32;
+			int i = p;
+			while (i < end && vis[CLL_SW(i)] != 1) { vis[CLL_SW(i)] = 2; i += snext[CLL_SW(i)]; }
+			if (i < end) { seg_merge[k] = i; p = seg_exit[k]; }     // met the speculative chain: it is the true one from here
+			else { seg_merge[k] = end; p = i; }                     // never met it inside this segment
+		}
+	}
+	__syncthreads();
+	{
+		const int m = seg_merge[t];
+		int n = 0;
+		for (int p = 32 * t; p < 32 * t + 32; p++) {
+			if (p < m && vis[CLL_SW(p)] == 1) vis[CLL_SW(p)] = 0;
+			n += vis[CLL_SW(p)] ? 1 : 0;
+		}
+		seg_cnt[t] = n;
+	}
+	__syncthreads();
+	if (t == 0) {
+		int run = 0;
+		for (int k = 0; k < 256; k++) { const int c = seg_cnt[k]; seg_cnt[k] = run; run += c; }
+		seg_cnt[256] = run;
+	}
+	__syncthreads();
+	const int j0 = im.hdr->y_res_comp, cnt = 1 + seg_cnt[256];
+	{
+		uint8_t *o = im.llcode + j0 + 1 + seg_cnt[t];
+		for (int p = 32 * t; p < 32 * t + 32; p++)
+			if (vis[CLL_SW(p)]) *o++ = sbyte[CLL_SW(p)];
+	}
+	if (t == 0) { im.llcode[j0] = sx[0]; im.hdr->end_ch_res = j0 + cnt; }
+	for (int k = t; k < 2048; k += 256) reinterpret_cast<uint32_t *>(im.tree1 + 16384)[k] = reinterpret_cast<const uint32_t *>(sx)[k];
 }
 
 // final: container bytes.  One CTA per image: thread 0 lays the sections out (enc_pack.cuh), all threads copy.
@@ -1640,7 +1694,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH_L(c, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);
 
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
-	NHW_LAUNCH_L(c, "c_ll_code", k_c_ll_code, n, 32, 0, b);
+	NHW_LAUNCH_L(c, "c_ll_code", k_c_ll_code, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "entropy_pack", k_entropy, n, SEG_THREADS, 262144 / 8, b);
 	NHW_LAUNCH(c, k_write_stream, n, 256, 0, b, n, out_dev, len_dev, status_dev);
 }
