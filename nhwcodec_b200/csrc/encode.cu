@@ -613,9 +613,108 @@ __global__ void __launch_bounds__(256, 4) k_e18_lists(EncBatch b, int q)
 }
 
 // list tails: block (k, image), one thread
+// The list tail (enc_y2.cuh: y_e18_finish_list_image states the steps) by one warp, 32 entries per step:
+//   marker pruning   : pointwise on the collected list -> ballot compaction
+//   LSB plane        : compaction of the real positions' low bits, then 8 per byte
+//   pair merging     : "merge with the next entry, then skip it" = every other cell of each run of mergeable cursors
+//                      (carry trick on the ballot word, the state carried across words is one bit)
+//   word plane       : pointwise
+__device__ __forceinline__ uint64_t alt64(uint64_t e)   // every other bit of each run of ones, from the run's lowest bit
+{
+	const uint64_t EVEN = 0x5555555555555555ull;
+	const uint64_t es = e & ~(e << 1) & EVEN, x = e + es;
+	return (e & ~x & EVEN) | (e & x & ~EVEN);
+}
+__device__ void e18_finish_list_warp(const EncImg &im, int which, int count, int e, int lane)
+{
+	EncHdr *h = im.hdr;
+	uint8_t *pos = im.tmp1, *A = im.tmp2, *wrd = im.tmp3;
+	uint8_t *out, *out_bit, *out_word;
+	if (which == 1) { out = im.res1; out_bit = im.res1_bit; out_word = im.res1_word; }
+	else if (which == 3) { out = im.res3; out_bit = im.res3_bit; out_word = im.res3_word; }
+	else { out = im.res5; out_bit = im.res5_bit; out_word = im.res5_word; }
+	const uint32_t lt = (1u << lane) - 1u;
+	if (lane < 8) wrd[e + lane] = 0;   // the reference reads up to 7 entries past the end
+	// ---- drop end-of-row markers the decoder can infer from a decreasing position: pos[0, count) -> A[0, len)
+	int len = 0;
+	for (int base = 0; base < count; base += 32) {
+		const int i = base + lane;
+		bool keep = false;
+		int v = 0;
+		if (i < count) {
+			v = pos[i];
+			keep = true;
+			if (i >= 1 && i <= count - 2 && v == 254) {
+				const int l = pos[i - 1], r = pos[i + 1];
+				if (l != 254 && r != 254 && l > r) keep = false;
+			}
+		}
+		const uint32_t m = __ballot_sync(0xffffffffu, keep);
+		if (keep) A[len + __popc(m & lt)] = (uint8_t)v;
+		len += __popc(m);
+	}
+	__syncwarp();
+	// ---- LSB plane of the real positions: compacted into pos[] (free now), then 8 per byte, MSB first
+	int np = 0;
+	for (int base = 0; base < len; base += 32) {
+		const int i = base + lane;
+		const int v = i < len ? (int)A[i] : 254;
+		const uint32_t m = __ballot_sync(0xffffffffu, v != 254);
+		if (v != 254) pos[np + __popc(m & lt)] = (uint8_t)(v & 1);
+		np += __popc(m);
+	}
+	if (lane < 8) pos[np + lane] = 0;
+	__syncwarp();
+	const int bit_len = (np >> 3) + 1;
+	for (int o = lane; o < bit_len; o += 32) {
+		int bb = 0;
+		for (int k = 0; k < 8; k++) bb |= (pos[8 * o + k] & 1) << (7 - k);
+		out_bit[o] = (uint8_t)bb;
+	}
+	// ---- halve the positions and merge (small delta, small delta) pairs into one byte >= 128; cursors 1 .. len-2
+	int olen = 1;
+	if (lane == 0) out[0] = (uint8_t)(A[0] >> 1);
+	uint32_t carry = 0;   // the cursor before this word merged (and swallows this word's first cursor)
+	for (int base = 1; base < len - 1; base += 32) {
+		const int i = base + lane;
+		const bool in = i < len - 1;
+		int cur = 0, d1 = -1, d2 = -1;
+		if (in) { cur = A[i] >> 1; d1 = cur - (A[i - 1] >> 1); d2 = (A[i + 1] >> 1) - cur; }
+		const bool mg = in && d1 >= 0 && d1 < 8 && d2 >= 0 && d2 < 16;
+		const uint32_t M = __ballot_sync(0xffffffffu, mg);
+		const uint64_t f64 = alt64(((uint64_t)M << 1) | carry);
+		const uint32_t F = (uint32_t)(f64 >> 1);                  // cursors that merge
+		const uint32_t skipped = (F << 1) | carry;                 // cursors swallowed by the merge before them
+		const uint32_t inm = __ballot_sync(0xffffffffu, in);
+		const uint32_t vis = inm & ~skipped;
+		if ((vis >> lane) & 1u) out[olen + __popc(vis & lt)] = (uint8_t)(((F >> lane) & 1u) ? 128 + (d1 << 4) + d2 : cur);
+		olen += __popc(vis);
+		carry = F >> 31;
+	}
+	// ---- word plane
+	const int groups = (e >> 3) + 1;
+	for (int g = lane; g < groups; g += 32) {
+		const uint8_t *w = wrd + 8 * g;
+		if (which == 3) {
+			out_word[2 * g] = (uint8_t)(((w[0] & 3) << 6) | ((w[1] & 3) << 4) | ((w[2] & 3) << 2) | (w[3] & 3));
+			out_word[2 * g + 1] = (uint8_t)(((w[4] & 3) << 6) | ((w[5] & 3) << 4) | ((w[6] & 3) << 2) | (w[7] & 3));
+		} else {
+			int bb = 0;
+			for (int k = 0; k < 8; k++) bb |= (w[k] & 1) << (7 - k);
+			out_word[g] = (uint8_t)bb;
+		}
+	}
+	if (lane == 0) {
+		const int wbytes = which == 3 ? 2 * groups : groups;
+		if (which == 1) { h->res1_len = olen; h->res1_bit_len = bit_len; h->res1_word_len = wbytes; }
+		else if (which == 3) { h->res3_len = olen; h->res3_bit_len = bit_len; h->res3_word_len = wbytes; }
+		else { h->res5_len = olen; h->res5_bit_len = bit_len; h->res5_word_len = wbytes; }
+	}
+}
+
+// list tails: block (k, image), one warp
 __global__ void __launch_bounds__(32) k_e18_tails(EncBatch b, int q)
 {
-	if (threadIdx.x) return;
 	const EncImg im = make_img(b, blockIdx.y, 0);
 	const int k = blockIdx.x, which = 1 + 2 * k, e = im.hdr->pad[k];
 	if (e < 0 || (which == 3 && q < 19) || (which == 5 && q < 21)) return;
@@ -623,7 +722,7 @@ __global__ void __launch_bounds__(32) k_e18_tails(EncBatch b, int q)
 	lm.tmp1 = im.tmp1 + k * E18_PART;
 	lm.tmp2 = im.tmp2 + k * E18_PART;
 	lm.tmp3 = im.tmp3 + k * E18_PART;
-	y_e18_finish_list_image(lm, which, e + 256, e);
+	e18_finish_list_warp(lm, which, e + 256, e, threadIdx.x);
 }
 
 // ---- pattern substitutions of the level-2 region on 256-bit row masks (enc_patterns.cuh).  One CTA per image:
