@@ -215,7 +215,19 @@ NHW_HD int e16_lut_entry(int idx, int rs)
 // The same walk with the four rows a step touches held in registers: the next rows are loaded ahead of time and a step no
 // longer waits for the previous step's stores to come back from memory (the column walk is a 255-step dependency
 // chain, one column per thread).
-NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t *Pn, const int16_t *Ln, const uint8_t *lut = nullptr)
+// LOCKSTEP (CUDA only): all columns of an image advance one row per barrier and column 255 runs E16_LAG rows behind.
+// Column 255 is the one column that reads live data of another column -- the LL1 codes of column 0 up to three rows
+// further down (its "next" cell in flat order) -- and in the reference it runs last; behind a lag of four rows it
+// sees exactly those final values, so it no longer needs a serial pass of its own after the other 255 columns.
+#define E16_LAG 4
+template <bool LOCKSTEP> NHW_HD void e16_lockstep()
+{
+#ifdef __CUDA_ARCH__
+	if (LOCKSTEP) __syncthreads();
+#endif
+}
+template <bool LOCKSTEP>
+NHW_HDN void y_e16_residual_col_t(const EncImg &im, int q, int j, const int16_t *Pn, const int16_t *Ln, const uint8_t *lut, int lag)
 {
 	int16_t *P = im.proc, *L = im.ll1;
 	const int rs = res_setting_of(q);
@@ -225,7 +237,10 @@ NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t 
 		int pm1 = 0, lm1 = 0, p0 = P[j], l0 = L[j], p1 = P[j + YW], l1 = L[j + 256], p2 = P[j + 2 * YW], l2 = L[j + 512];
 		int ol0 = l0, op1 = p1, ol1 = l1, op2 = p2;
 		int np = P[j + 3 * YW], nl = L[j + 768];   // next row to enter the window (reads past the band on the last rows)
-		for (int row = 0; row < 255; row++, scan += YW, count += 256) {
+		for (int it = 0; it < 255 + E16_LAG; it++) {
+			const int row = it - lag;
+			if (row >= 0 && row < 255) {
+			scan = row * YW + j; count = row * 256 + j;
 			const int stage = (j << 9) + row + 256;
 			int res = p0 - l0;
 			int a = p1 - l1;
@@ -318,11 +333,19 @@ NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t 
 			p1 = p2; op1 = op2; l1 = l2; ol1 = l2;
 			p2 = np; op2 = np; l2 = nl;
 			if (row < 253) { np = P[scan + 4 * YW]; nl = L[count + 1024]; }   // up to row 256
+			}
+			e16_lockstep<LOCKSTEP>();
 		}
+		scan = 255 * YW + j; count = 255 * 256 + j;
 		// the window still holds row 255 of LL1 (a q18 rule of the last step may have coded it) and row 256 of the plane
 		if (l0 != ol0) L[count] = (int16_t)l0;
 		if (p1 != op1) P[scan + YW] = (int16_t)p1;
 	}
+}
+
+NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t *Pn, const int16_t *Ln, const uint8_t *lut = nullptr)
+{
+	y_e16_residual_col_t<false>(im, q, j, Pn, Ln, lut, 0);
 }
 
 // serial form (reference order); the CUDA path runs columns 0..254 concurrently against a

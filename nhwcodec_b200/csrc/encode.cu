@@ -253,9 +253,9 @@ __global__ void __launch_bounds__(256) k_e16_residual(EncBatch b, int q)
 	for (int i = threadIdx.x; i < E16_SNAP_L_CELLS / 8; i += 256) ld[i] = i < 65536 / 8 ? ls[i] : make_int4(0, 0, 0, 0);
 	__syncthreads();
 	const int j = threadIdx.x;
-	if (j < 255) y_e16_residual_col_w(im, q, j, im.aux, im.aux + E16_SNAP_L_OFF, lut);
-	__syncthreads();
-	if (j == 255) y_e16_residual_col_w(im, q, 255, im.proc, im.ll1, lut);
+	// all 256 columns in lockstep, one row per barrier; column 255 (the one that reads live data: column 0's codes
+	// a few rows further down) runs E16_LAG rows behind instead of in a serial pass of its own
+	y_e16_residual_col_t<true>(im, q, j, j < 255 ? im.aux : im.proc, j < 255 ? im.aux + E16_SNAP_L_OFF : im.ll1, lut, j < 255 ? 0 : E16_LAG);
 }
 
 __global__ void __launch_bounds__(256) k_e16b_classify(EncBatch b, int q)
