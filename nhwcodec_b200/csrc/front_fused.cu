@@ -249,20 +249,17 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 			for (int step = 0; step < 4; step++) {
 				const uint32_t *w = reinterpret_cast<const uint32_t *>(line + step * 384 + lane * 12);
 				const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-				int c0[4], c1[4], c2[4];
-				c0[0] = w0 & 255u; c1[0] = (w0 >> 8) & 255u; c2[0] = (w0 >> 16) & 255u;
-				c0[1] = w0 >> 24; c1[1] = w1 & 255u; c2[1] = (w1 >> 8) & 255u;
-				c0[2] = (w1 >> 16) & 255u; c1[2] = w1 >> 24; c2[2] = w2 & 255u;
-				c0[3] = (w2 >> 8) & 255u; c1[3] = (w2 >> 16) & 255u; c2[3] = w2 >> 24;
+				// four pixels, each as c0 | c1 << 8 | c2 << 16
+				const uint32_t px[4] = {w0 & 0xffffffu, __funnelshift_r(w0, w1, 24) & 0xffffffu, __funnelshift_r(w1, w2, 16) & 0xffffffu, w2 >> 8};
 				int Y[4];
 				uint32_t uv[4];   // U | V << 16
 				if (cp.mode == 0) {
-					rgb4_to_ycc_q20(c0, c1, c2, Y, uv);
+					rgb4px_to_ycc_q20(px, Y, uv);
 				} else {
 #pragma unroll
 					for (int k = 0; k < 4; k++) {
 						int U, V;
-						rgb_to_ycc(c0[k], c1[k], c2[k], cp, Y[k], U, V);
+						rgb_to_ycc((int)(px[k] & 255u), (int)((px[k] >> 8) & 255u), (int)(px[k] >> 16), cp, Y[k], U, V);
 						uv[k] = (uint32_t)U | ((uint32_t)V << 16);
 					}
 				}
@@ -587,6 +584,12 @@ __global__ void k_color_check(ColorParams p, unsigned long long *bad)
 	rgb_to_ycc(c0, c1, c2, p, Y, U, V);
 	rgb_to_ycc_q20(c0, c1, c2, y, u, v);
 	if (Y != y || U != u || V != v) atomicAdd(bad, 1ull);
+	// the packed dp2a form the fused kernel uses (four pixels per call: this triple and three neighbours)
+	const uint32_t px[4] = {t, (t + 1u) & 0xffffffu, (t * 2654435761u) & 0xffffffu, (t ^ 0x5a5a5au) & 0xffffffu};
+	int Y4[4];
+	uint32_t uv4[4];
+	rgb4px_to_ycc_q20(px, Y4, uv4);
+	if (Y4[0] != Y || (int)(uv4[0] & 0xffffu) != U || (int)(uv4[0] >> 16) != V) atomicAdd(bad, 1ull);
 }
 
 template <int N, typename InT, int THREADS>
