@@ -138,6 +138,9 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	ok = ok && check(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
 	ok = ok && check(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
 	ok = ok && check(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	ok = ok && check(cudaStreamCreateWithFlags(&c->chroma_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	ok = ok && check(cudaEventCreateWithFlags(&c->ev_chroma0, cudaEventDisableTiming), "cudaEventCreate");
+	ok = ok && check(cudaEventCreateWithFlags(&c->ev_chroma1, cudaEventDisableTiming), "cudaEventCreate");
 	for (int k = 0; k < NHW_MAX_SUB && ok; k++) {
 		ok = ok && check(cudaEventCreateWithFlags(&c->ev_sub[k], cudaEventDisableTiming), "cudaEventCreate");
 		ok = ok && check(cudaEventCreateWithFlags(&c->ev_up[k], cudaEventDisableTiming), "cudaEventCreate");
@@ -189,6 +192,9 @@ void nhw_destroy(nhw_ctx *c)
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->up_stream) cudaStreamDestroy(c->up_stream);
+	if (c->chroma_stream) cudaStreamDestroy(c->chroma_stream);
+	if (c->ev_chroma0) cudaEventDestroy(c->ev_chroma0);
+	if (c->ev_chroma1) cudaEventDestroy(c->ev_chroma1);
 	for (int k = 0; k < NHW_MAX_SUB; k++) {
 		if (c->ev_sub[k]) cudaEventDestroy(c->ev_sub[k]);
 		if (c->ev_up[k]) cudaEventDestroy(c->ev_up[k]);
@@ -427,6 +433,7 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
 			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
 			if (cnt <= 0) continue;
 			nhw_ctx v = lane_view(c, l, l * p.slot);
+			v.chroma_side = (p.subs == 1 && !c->profile && !c->dbg_label[0] && env_int("NHW_CHROMA_STREAM", 1, 0, 1)) ? 1 : 0;
 			nhw::encode_chunk(&v, rgb_dev + (size_t)a * NHW_RGB_BYTES, cnt, quality, out_dev + (size_t)a * NHW_MAX_STREAM_BYTES,
 			                  len_dev ? len_dev + a : nullptr, status_dev ? status_dev + a : nullptr);
 			lane_done(c, v);

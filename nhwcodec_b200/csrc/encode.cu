@@ -1711,6 +1711,49 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	// ---- front end: colour, 4:2:0, pre-sharpening, two analysis levels (front.cu)
 	front_fused(c, rgb, n, q, b.y_proc, YS, b.y_ll1, CS, c->c_u8, b.c_proc, CS, b.c_ll1, QS, b.y_hq, YS);
 
+	// ---- chroma chain: independent of the luma chain from here to the entropy stage (own planes, own part of tree1,
+	// of the scan buffer and of the header); on its own stream when the chunk runs alone on the GPU
+	// (forked here, next to the short kernels of the luma closed loop: 43.9 -> 43.5 ms; forked before the LL2 coder it
+	// competes with the latency-bound kernels and the step gets slower: 45.6 ms)
+	nhw_ctx side = *c;
+	nhw_ctx *cs = c;
+	if (c->chroma_side && c->chroma_stream) {
+		side.stream = c->chroma_stream;
+		side.launches = 0;
+		cs = &side;
+		cudaEventRecord(c->ev_chroma0, c->stream);
+		cudaStreamWaitEvent(side.stream, c->ev_chroma0, 0);
+	}
+	// U and V planes side by side (nhw_encoder.c:2255-2868)
+	run_plane_groups(cs, "c_recons1", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int) {
+		int o[8];
+		c_recons_cells(im.cproc + r * CW, r, g, ratio, 1, o);
+		st8(im.cjpeg + r * CW + g * 8, o);
+	});
+	idwt_chroma128(cs, b, n);
+	run_plane_groups(cs, "c_correct", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int v) {
+		int o[8];
+		c_correct_cells(im.cproc + r * CW, im.cll1 + r * 128, g, v, o);
+		st8(im.cjpeg + r * CW + g * 8, o);
+	});
+	dwt_level_from_jpeg(cs, 2 * n, b.c_jpeg, CS, b.c_proc, CS, 128, 256);
+	NHW_LAUNCH(cs, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_proc, CS, 256, b.c_ll2s, QS, 128, 128);
+	run_plane_groups(cs, "c_recons0", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int) {
+		int o[8];
+		c_recons_cells(im.cproc + r * CW, r, g, ratio, 0, o);
+		st8(im.cjpeg + r * CW + g * 8, o);
+	});
+	idwt_chroma128(cs, b, n);
+	NHW_LAUNCH_L(cs, "c_residual_tags", k_c_residual_tags, dim3(8, 2 * n), 256, 0, b, q);
+	NHW_LAUNCH(cs, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_ll2s, QS, 128, b.c_proc, CS, 256, 128);
+	NHW_LAUNCH_L(cs, "c_ll_quant", k_c_ll_quant, n, 64, 0, b, q);
+	NHW_LAUNCH_L(cs, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);
+
+	if (cs != c) {
+		cudaEventRecord(c->ev_chroma1, side.stream);
+		c->launches += side.launches;
+	}
+
 	// ---- luma closed loop (nhw_encoder.c:141-283)
 	run_groups(c, "y_e6a_tag", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { y_e6a_tag_cells(im.proc, im.ll1 + r * 256, r, g); });
 	NHW_LAUNCH_L(c, "y_recons1_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 1);
@@ -1767,31 +1810,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	}
 	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 262144 / 8, b);
 
-	// ---- chroma, U and V planes side by side (nhw_encoder.c:2255-2868)
-	run_plane_groups(c, "c_recons1", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int) {
-		int o[8];
-		c_recons_cells(im.cproc + r * CW, r, g, ratio, 1, o);
-		st8(im.cjpeg + r * CW + g * 8, o);
-	});
-	idwt_chroma128(c, b, n);
-	run_plane_groups(c, "c_correct", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int v) {
-		int o[8];
-		c_correct_cells(im.cproc + r * CW, im.cll1 + r * 128, g, v, o);
-		st8(im.cjpeg + r * CW + g * 8, o);
-	});
-	dwt_level_from_jpeg(c, 2 * n, b.c_jpeg, CS, b.c_proc, CS, 128, 256);
-	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_proc, CS, 256, b.c_ll2s, QS, 128, 128);
-	run_plane_groups(c, "c_recons0", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int) {
-		int o[8];
-		c_recons_cells(im.cproc + r * CW, r, g, ratio, 0, o);
-		st8(im.cjpeg + r * CW + g * 8, o);
-	});
-	idwt_chroma128(c, b, n);
-	NHW_LAUNCH_L(c, "c_residual_tags", k_c_residual_tags, dim3(8, 2 * n), 256, 0, b, q);
-	NHW_LAUNCH(c, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_ll2s, QS, 128, b.c_proc, CS, 256, 128);
-	NHW_LAUNCH_L(c, "c_ll_quant", k_c_ll_quant, n, 64, 0, b, q);
-	NHW_LAUNCH_L(c, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);
-
+	if (cs != c) cudaStreamWaitEvent(c->stream, c->ev_chroma1, 0);   // the chroma chain joins here
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
 	NHW_LAUNCH_L(c, "c_ll_code", k_c_ll_code, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "entropy_pack", k_entropy, n, SEG_THREADS, 262144 / 8, b);

@@ -21,6 +21,11 @@ struct nhw_ctx {
 	cudaStream_t copy_stream;   // device->host copies of finished sub-chunks
 	cudaStream_t up_stream;     // host->device copies of the pixels, queued back to back ahead of the sub-chunks that use them
 	cudaEvent_t ev_fork, ev_join[NHW_LANES], ev_sub[NHW_MAX_SUB], ev_up[NHW_MAX_SUB];
+	// the chroma chain of a chunk runs next to the (latency-bound) luma chain on this stream when the chunk is
+	// encoded as one sub-chunk (device-resident input); NULL: everything on `stream`
+	cudaStream_t chroma_stream;
+	cudaEvent_t ev_chroma0, ev_chroma1;
+	int chroma_side;            // 1: encode_chunk may use chroma_stream for this call
 	uint64_t launches;
 	char dbg_label[64];  // debug: stop issuing kernels after the dbg_count-th launch of this label
 	int dbg_count, dbg_seen, dbg_stopped;
