@@ -1,4 +1,4 @@
-// dec_core.cuh -- decoder stage functions (host/device), q17..q21.
+// dec_core.cuh -- decoder stage functions (host/device), q17..q23.
 //
 //   dec_ll_dpcm          : LL byte decode of parse_file          decoder/nhw_decoder.c:1663-2026
 //   dec_prefix_luma/_chroma : retrieve_pixel_Y_comp / _UV_comp   decoder/compress_pixel.c:49-444, 446-641

@@ -1,5 +1,5 @@
 // dec_stages.cuh -- inline stages of decode_image (decoder/nhw_decoder.c:71-1474) and the colour
-// conversion of write_image_bmp (decoder/nhw_decoder_cli.c:108-291), q17..q21.
+// conversion of write_image_bmp (decoder/nhw_decoder_cli.c:108-291), q17..q23.
 // *_row / *_strip functions are independent per row/strip; *_image functions are raster-ordered.
 #pragma once
 #include "dec_core.cuh"

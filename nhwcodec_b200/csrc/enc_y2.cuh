@@ -1,7 +1,7 @@
 // enc_y2.cuh -- luma encoder stages after the LL2 coder (encoder/nhw_encoder.c:749-2252):
 // level-1 thresholds, pattern tags, residual side channels (res1/res3/res5), clean-up,
 // quantisation to bytes (offsetY, encoder/image_processing.c:185-521), serpentine scan and
-// the byte-stream peephole passes.  q17..q21 (q>=22 side channels res6 are not built yet).
+// the byte-stream peephole passes.  q17..q23 (the q>=22 side channels res6 / char_res1 / high_qsetting3 live in enc_hq.cuh).
 #pragma once
 #include "enc_ll.cuh"
 
