@@ -523,11 +523,13 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 			DecDesc *desc = static_cast<DecDesc *>(w.dec_desc_host);
 			const uint64_t base = offsets[a], total = offsets[a + cnt] - base;
 			if (total + 64 > (uint64_t)p.slot * NHW_MAX_STREAM_BYTES) { nhw::set_error("input chunk too large"); return NHW_ERR_ARG; }
+			bool any_lowq = false;   // q <= 16 streams take one extra (row-ordered) kernel
 			for (int i = 0; i < cnt; i++) {
 				const uint64_t o = offsets[a + i] - base, len = offsets[a + i + 1] - offsets[a + i];
 				w.offs_host[i] = o;
 				w.status_host[i] = nhw_parse_header(in + base + o, (size_t)len, &desc[i]);
 				if (quality) quality[a + i] = desc[i].quality;
+				any_lowq |= w.status_host[i] == 0 && desc[i].quality <= 16;
 			}
 			bool ok = check(cudaMemcpyAsync(w.pack_dev, in + base, total, cudaMemcpyHostToDevice, w.stream), "H2D streams");
 			// the bit reader may look a few words past the last code: keep that tail defined
@@ -536,7 +538,7 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 			ok = ok && check(cudaMemcpyAsync(w.offs_dev, w.offs_host, (size_t)cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, w.stream), "H2D offs");
 			ok = ok && check(cudaMemcpyAsync(w.status_dev, w.status_host, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, w.stream), "H2D status");
 			if (!ok) return NHW_ERR_CUDA;
-			nhw::decode_chunk(&w, w.pack_dev, w.offs_dev, static_cast<const DecDesc *>(w.dec_desc_dev), w.status_dev, cnt, w.rgb);
+			nhw::decode_chunk(&w, w.pack_dev, w.offs_dev, static_cast<const DecDesc *>(w.dec_desc_dev), w.status_dev, cnt, w.rgb, any_lowq);
 			if (rgb) cudaMemcpyAsync(rgb + (size_t)a * NHW_RGB_BYTES, w.rgb, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);
 			if (yuv) cudaMemcpyAsync(yuv + (size_t)a * NHW_RGB_BYTES, w.dec_yuv, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);
 			cudaMemcpyAsync(w.status_host, w.status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, w.stream);

@@ -171,8 +171,9 @@ NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
 	const long nbits = (long)d->size_data1 * 32;
 	const int p1 = 262144;
 	int e = 0, mem = 0, mem2 = 0, ac1 = 0, run_over = -257, t = 0, t2 = 0;
-	auto bit1 = [&](int k) { return (sel1[k >> 3] >> (7 - (k & 7))) & 1; };
-	auto bit2 = [&](int k) { return (sel2[k >> 3] >> (7 - (k & 7))) & 1; };
+	// select bits past the section the header declares read as 0 (a well-formed stream never gets there)
+	auto bit1 = [&](int k) { return (k >> 3) < d->select1 ? (sel1[k >> 3] >> (7 - (k & 7))) & 1 : 0; };
+	auto bit2 = [&](int k) { return (k >> 3) < d->select2 ? (sel2[k >> 3] >> (7 - (k & 7))) & 1 : 0; };
 	// The plane starts zeroed and is written at increasing positions only, so "is cell e-k still
 	// zero" is answered from a shift register of the last 32 positions instead of reading it back:
 	// bit j of hist = a non-zero value was stored at position e-1-j.
@@ -269,10 +270,12 @@ NHW_HDN int dec_prefix_chroma(const DecImg &im, int16_t *im3 /* 131072, zeroed *
 
 // ---- LL bytes (parse_file, nhw_decoder.c:1663-2026).  All arithmetic is modulo 256 like the
 // reference's unsigned char stores.
-NHW_HDN void dec_ll_dpcm(const DecImg &im)
+// Returns 0, or NHW_ERR_STREAM_DEV when the code runs past the section lengths the header declares.
+NHW_HDN int dec_ll_dpcm(const DecImg &im)
 {
 	const DecDesc *d = im.d;
 	const uint8_t *ch = im.blob + d->off_ch_res, *hr = im.blob + d->off_highres;
+	const int ch_len = d->end_ch_res, hr_len = d->highres_comp_len;
 	uint8_t *o = im.res_comp;
 	const int q = d->quality, mode = d->byte0 & 3;
 	int j = 1, i = 1, a = 0;
@@ -298,9 +301,10 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 		rel(((c1 & 31) << 1) - 32);
 	};
 	for (; j < 16384; i++) {
+		if (i + 1 >= ch_len) return NHW_ERR_STREAM_DEV;   // every code may take a second byte
 		const int c = ch[i];
 		if (c >= 128) {
-			if (q > 15) emit(hr[a++]);
+			if (q > 15) { if (a >= hr_len) return NHW_ERR_STREAM_DEV; emit(hr[a++]); }
 			emit((c - 128) << 1);
 		} else if (mode == 0) {
 			if (c < 16) {
@@ -346,8 +350,10 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 		}
 	}
 	j = 16384;
+	if (i >= ch_len) return NHW_ERR_STREAM_DEV;
 	emit(ch[i++]);
 	for (; j < 24576; i++) {
+		if (i >= ch_len) return NHW_ERR_STREAM_DEV;
 		const int c = ch[i];
 		if (c >= 192) {
 			const int x = c - 192, k = x >> 2;
@@ -380,6 +386,7 @@ NHW_HDN void dec_ll_dpcm(const DecImg &im)
 			rel(((c & 7) << 2) - 16);
 		}
 	}
+	return 0;
 }
 
 // ---- position list expansion (nhw_decoder.c:93-183 and its res5/res3 twins).

@@ -27,6 +27,19 @@ NHW_HD int dwf_shrink_cell(int16_t *J, int r, int j)
 	return 1;
 }
 
+// D8 at q <= 16: same rule with the diagonal threshold at 16.  Valid when rows above r are final and rows below
+// untouched; cells of row r may run in any order (see kd_shrink_y_lowq).
+NHW_HD void dec_shrink_lowq_cell(int16_t *J, int r, int j)
+{
+	const int s = r * YW + j;
+	if (nhw_iabs(J[s]) <= 8) return;
+	if (nhw_iabs(J[s - YW - 1]) > 16 || nhw_iabs(J[s - YW]) > 8 || nhw_iabs(J[s - YW + 1]) > 16 ||
+	    nhw_iabs(J[s - 1]) > 8 || nhw_iabs(J[s + 1]) > 8 || nhw_iabs(J[s + YW - 1]) > 16 ||
+	    nhw_iabs(J[s + YW]) > 8 || nhw_iabs(J[s + YW + 1]) > 16)
+		return;
+	if (r >= 128 || j >= 128) J[s] += J[s] > 0 ? -1 : 1;
+}
+
 // D11: pair p (columns 1+2p, 2+2p), 0 <= p <= 126, rows 1..254 of the reconstructed LL1 (stride 512)
 NHW_HD WfGeom dwf_edge_geom() { return WfGeom{1, 254, 0, 127, 2}; }
 NHW_HD int dwf_edge_cell(int16_t *P, int r, int p)

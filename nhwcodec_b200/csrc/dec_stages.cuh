@@ -19,11 +19,12 @@ NHW_HD void dec_y_descan_strip(const int16_t *coef, int16_t *J, int strip /* 0..
 
 // ---- D3: expand + split the side-channel lists (nhw_decoder.c:93-491).  list_len[8] receives
 // the value the reference's `count` variable is left with (it is read, stale, by D4).
-NHW_HDN void dec_lists_image(const DecImg &im, uint16_t *tmp /* 65536 */)
+#define DEC_LIST_CAP 65536   // entries per expanded list (and of `tmp`); nhw_parse_header rejects streams that need more
+NHW_HDN void dec_lists_image(const DecImg &im, uint16_t *tmp /* DEC_LIST_CAP */)
 {
 	const DecDesc *d = im.d;
 	const int q = d->quality;
-	int stale = 0;
+	int stale = 262144;   // q <= 12 expands no list: `count` still holds the de-scan loop's final value (nhw_decoder.c:71-91)
 	for (int k = 0; k < 8; k++) im.list_len[k] = 0;
 	for (int pass = 0; pass < 2; pass++) {   // res1 (q>12), then res5 (q>=21): one word bit per entry
 		if (pass == 0 ? !(q > 12) : !(q >= 21)) continue;
@@ -31,10 +32,10 @@ NHW_HDN void dec_lists_image(const DecImg &im, uint16_t *tmp /* 65536 */)
 		const uint8_t *bits = im.blob + (pass ? d->off_res5_bit : d->off_res1_bit);
 		const uint8_t *word = im.blob + (pass ? d->off_res5_word : d->off_res1_word);
 		const int len = pass ? d->res5_len : d->res1_len, bit_len = pass ? d->res5_bit_len : d->res1_bit_len;
-		dec_expand_list(res, len, bits, bit_len, tmp);
+		dec_expand_list(res, len, bits, bit_len, tmp, DEC_LIST_CAP);
 		uint16_t *minus = im.list[2 * pass], *plus = im.list[2 * pass + 1];
 		int nm = 0, np = 0, c = 0;
-		for (int i = 0; i < bit_len - 1; i++)
+		for (int i = 0; i < bit_len - 1 && c + 8 <= DEC_LIST_CAP; i++)   // the header check keeps 8*bit_len within the lists
 			for (int b = 7; b >= 0; b--) {
 				if ((word[i] >> b) & 1) minus[nm++] = tmp[c++];
 				else plus[np++] = tmp[c++];
@@ -44,10 +45,10 @@ NHW_HDN void dec_lists_image(const DecImg &im, uint16_t *tmp /* 65536 */)
 		stale = c;
 	}
 	if (q >= 19) {   // res3: two word bits per entry, four classes
-		dec_expand_list(im.blob + d->off_res3, d->res3_len, im.blob + d->off_res3_bit, d->res3_bit_len, tmp);
+		dec_expand_list(im.blob + d->off_res3, d->res3_len, im.blob + d->off_res3_bit, d->res3_bit_len, tmp, DEC_LIST_CAP);
 		const uint8_t *word = im.blob + d->off_res3_word;
 		int n[4] = {0, 0, 0, 0}, c = 0;
-		for (int i = 0; i < (d->res3_bit_len << 1) - 2; i++)
+		for (int i = 0; i < (d->res3_bit_len << 1) - 2 && c + 4 <= DEC_LIST_CAP; i++)
 			for (int b = 6; b >= 0; b -= 2) {
 				const int sel = (word[i] >> b) & 3;   // 0 -> nhwres4 (+4,+3), 1 -> nhwres3 (-4,-3), 2 -> +2 x3, 3 -> -2 x3
 				im.list[4 + sel][n[sel]++] = tmp[c++];
@@ -68,7 +69,7 @@ NHW_HDN void dec_hq_lists_image(const DecImg &im, uint32_t *tmp /* NHW_CAP_HQ_LI
 	dec_expand_list(im.blob + d->off_res6, d->res6_len, im.blob + d->off_res6_bit, d->res6_bit_len, tmp, NHW_CAP_HQ_LIST);
 	const uint8_t *word = im.blob + d->off_res6_word;
 	int nm = 0, np = 0, c = 0;
-	for (int i = 0; i < d->res6_bit_len - 1; i++)
+	for (int i = 0; i < d->res6_bit_len - 1 && c + 8 <= NHW_CAP_HQ_LIST; i++)
 		for (int b = 7; b >= 0; b--) {
 			if ((word[i] >> b) & 1) im.hq_list[0][nm++] = tmp[c++];
 			else im.hq_list[1][np++] = tmp[c++];
@@ -188,16 +189,18 @@ NHW_HDN int dec_y_ll_image(const DecImg &im)
 }
 
 // ---- D8: shrink isolated coefficients of the level-2 bands, in place (nhw_decoder.c:685-711)
+// q <= 16 tolerates diagonal neighbours up to 16 (nhw_decoder.c:660-684)
 NHW_HDN void dec_y_shrink_image(const DecImg &im)
 {
 	int16_t *J = im.jpeg;
+	const int dg = im.d->quality <= 16 ? 16 : 8;
 	for (int r = 1; r < 255; r++)
 		for (int j = 1; j < 255; j++) {
 			const int s = r * YW + j;
 			if (nhw_iabs(J[s]) <= 8) continue;
-			if (nhw_iabs(J[s - YW - 1]) > 8 || nhw_iabs(J[s - YW]) > 8 || nhw_iabs(J[s - YW + 1]) > 8 ||
-			    nhw_iabs(J[s - 1]) > 8 || nhw_iabs(J[s + 1]) > 8 || nhw_iabs(J[s + YW - 1]) > 8 ||
-			    nhw_iabs(J[s + YW]) > 8 || nhw_iabs(J[s + YW + 1]) > 8)
+			if (nhw_iabs(J[s - YW - 1]) > dg || nhw_iabs(J[s - YW]) > 8 || nhw_iabs(J[s - YW + 1]) > dg ||
+			    nhw_iabs(J[s - 1]) > 8 || nhw_iabs(J[s + 1]) > 8 || nhw_iabs(J[s + YW - 1]) > dg ||
+			    nhw_iabs(J[s + YW]) > 8 || nhw_iabs(J[s + YW + 1]) > dg)
 				continue;
 			if (r >= 128 || j >= 128) J[s] += J[s] > 0 ? -1 : 1;
 		}
@@ -360,8 +363,21 @@ NHW_HD void dec_c_upsample_row(const int16_t *P, uint8_t *out, int y /* 0..511 *
 }
 
 // ---- D17: YCbCr -> RGB (nhw_decoder_cli.c:139-229), IEEE-exact like the encoder's colour stage.
-// mode 0: q>=20   1: q18,19 (Y scaled in float first)   2: q17
+// mode 0: q>=20   1: q18,19 (Y scaled in float first)   2: q17   3: q<=16, float32 fixed-point form
 struct DecColor { int mode; float y_inv; };
+
+// the per-quality luma gain of write_image_bmp (nhw_decoder_cli.c:168-169,204,239-254); q0 has none (unsupported)
+NHW_HD DecColor dec_color_of(int quality)
+{
+	DecColor c;
+	c.mode = quality >= 20 ? 0 : quality >= 18 ? 1 : quality == 17 ? 2 : 3;
+	// (a table, not a switch: see DESIGN.md on sparse switches in device code)
+	const float gain[24] = {1.0f, 2.060881f, 1.985939f, 1.916257f, 1.820444f, 1.741126f, 1.665887f, 1.587597f, 1.521263f,
+	                        1.392014f, 1.281502f, 1.190611f, 1.177434f, 1.186945f, 1.138331f, 1.048174f, 1.012139f,
+	                        1.063830f, 1.075269f, 1.025641f, 1.0f, 1.0f, 1.0f, 1.0f};
+	c.y_inv = gain[quality < 0 ? 0 : quality > 23 ? 23 : quality];
+	return c;
+}
 
 #ifdef __CUDA_ARCH__
 #define NHW_DMUL(a, b) __dmul_rn((a), (b))
@@ -369,7 +385,13 @@ struct DecColor { int mode; float y_inv; };
 #define NHW_DSUB(a, b) __dsub_rn((a), (b))
 #define NHW_FMUL(a, b) __fmul_rn((a), (b))
 #define NHW_D2I(a) __double2int_rz(a)
+#define NHW_FADD(a, b) __fadd_rn((a), (b))
+#define NHW_I2F(a) __int2float_rn(a)
+#define NHW_F2I(a) __float2int_rz(a)
 #else
+#define NHW_FADD(a, b) ((a) + (b))
+#define NHW_I2F(a) ((float)(a))
+#define NHW_F2I(a) ((int)(a))
 #define NHW_DMUL(a, b) ((a) * (b))
 #define NHW_DADD(a, b) ((a) + (b))
 #define NHW_DSUB(a, b) ((a) - (b))
@@ -379,6 +401,18 @@ struct DecColor { int mode; float y_inv; };
 
 NHW_HD void dec_ycc_to_rgb(int y8, int u8, int v8, const DecColor &c, uint8_t *rgb)
 {
+	if (c.mode == 3) {
+		// q <= 16 (nhw_decoder_cli.c:256-276): integer matrix on un-centred U, V, one float32 multiply by the
+		// luma gain, +128.5f, truncate, >> 8.  -56992-128, 34784-128, -70688-128 are R/G/B_COMP (decoder/codec.h:96-98).
+		const int Y = y8 * 298;
+		const int r = NHW_F2I(NHW_FADD(NHW_FMUL(NHW_I2F(Y + 409 * v8 - 57120), c.y_inv), 128.5f)) >> 8;
+		const int g = NHW_F2I(NHW_FADD(NHW_FMUL(NHW_I2F(Y - 100 * u8 - 208 * v8 + 34656), c.y_inv), 128.5f)) >> 8;
+		const int b = NHW_F2I(NHW_FADD(NHW_FMUL(NHW_I2F(Y + 516 * u8 - 70816), c.y_inv), 128.5f)) >> 8;
+		rgb[0] = dec_clip8(r);
+		rgb[1] = dec_clip8(g);
+		rgb[2] = dec_clip8(b);
+		return;
+	}
 	const double U = (double)(u8 - 128), V = (double)(v8 - 128);
 	double Y = (double)y8;
 	if (c.mode == 1) Y = (double)NHW_FMUL((float)y8, c.y_inv);

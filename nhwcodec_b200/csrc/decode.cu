@@ -201,9 +201,26 @@ __global__ void __launch_bounds__(256) kd_shrink_y(DecBatch b)
 {
 	if (b.status[blockIdx.y] != 0) return;
 	const DecImg im = make_dec(b, blockIdx.y, 0);
+	if (im.d->quality <= 16) return;   // kd_shrink_y_lowq
 	const int idx = blockIdx.x * 256 + threadIdx.x, r = idx >> 5, g = idx & 31;
 	int o[8];
 	if (shrink_cells8(im.jpeg, r, g, 9, o)) st8(im.jpeg + r * YW + g * 8, o);
+}
+
+// q <= 16 (nhw_decoder.c:660-684): diagonal neighbours only block the shrink above 16, so a diagonal neighbour of
+// exactly +-17 that shrinks first changes the outcome: the rows above must be final, the rows below untouched (the
+// four orthogonal neighbours still cannot change while this cell is a candidate).  One CTA per image, thread =
+// column, one barrier per row.
+__global__ void __launch_bounds__(256) kd_shrink_y_lowq(DecBatch b)
+{
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.x, 0);
+	if (im.d->quality > 16) return;
+	const int j = threadIdx.x;
+	for (int r = 1; r < 255; r++) {
+		if (j >= 1 && j < 255) dec_shrink_lowq_cell(im.jpeg, r, j);
+		__syncthreads();
+	}
 }
 
 // ---- D4: marker expansion + right-half nudges in parallel form (dec_par.cuh).  One CTA per image.
@@ -450,9 +467,7 @@ __global__ void kd_color(DecBatch b, uint8_t *rgb)
 	uint8_t *o = rgb + (size_t)blockIdx.y * 786432 + 3 * (size_t)i;
 	if (b.status[blockIdx.y] != 0) { o[0] = o[1] = o[2] = 0; return; }
 	const int quality = b.desc[blockIdx.y].quality;   // each stream carries its own quality byte
-	DecColor col;
-	col.mode = quality >= 20 ? 0 : quality >= 18 ? 1 : 2;
-	col.y_inv = quality == 19 ? 1.025641f : quality == 18 ? 1.075269f : 1.063830f;
+	const DecColor col = dec_color_of(quality);
 	const uint8_t *yuv = b.yuv + (size_t)blockIdx.y * 786432;
 	dec_ycc_to_rgb(yuv[i], yuv[262144 + i], yuv[524288 + i], col, o);
 }
@@ -467,7 +482,7 @@ void idwt_rows_cols(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *tmp, i
 // Decode n <= max_batch streams.  blobs/offs/desc/status are device arrays for this chunk; rgb_dev
 // receives n x 786432 bytes.  All work is queued on c->stream.
 void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const DecDesc *desc, int32_t *status, int n,
-                  uint8_t *rgb_dev)
+                  uint8_t *rgb_dev, bool any_lowq)
 {
 	DecBatch b;
 	b.blobs = blobs; b.blob_off = offs; b.desc = desc; b.status = status;
@@ -504,6 +519,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_shrink_y", kd_shrink_y, dim3(32, n), 256, 0, b);
+	if (any_lowq) NHW_LAUNCH_L(c, "d_shrink_y_lowq", kd_shrink_y_lowq, n, 256, 0, b);
 	idwt_rows_cols(c, n, b.y_jpeg, b.y_aux, b.y_proc, YS, 256, 512);
 	NHW_LAUNCH_L(c, "d_addbacks", kd_addbacks, n, 256, 0, b);
 	d_wavefront(c, "d_edge_flags", b, n, 1, dwf_edge_geom(), [=] __device__(const DecImg &im, int r, int p) { return dwf_edge_cell(im.proc, r, p); });

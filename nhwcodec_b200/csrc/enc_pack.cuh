@@ -12,6 +12,7 @@
 
 #define NHW_ERR_CODEBOOK_DEV (-4)
 #define NHW_ERR_OVERFLOW_DEV (-5)
+#define NHW_ERR_STREAM_DEV (-7)
 #define NHW_WORDS_LIMIT (131072 - 4)   // ENC_WORDS_CAP minus slack, enc_batch.cuh
 
 struct PackState {

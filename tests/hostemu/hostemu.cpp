@@ -469,7 +469,8 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	dec_build_lut(lut.data());
 	im.lut = lut.data();
 
-	dec_ll_dpcm(im);
+	rc = dec_ll_dpcm(im);
+	if (rc) return rc;
 	dec_build_book(blob + d.off_tree1, d.size_tree1, 3, -1, im.book, btmp.data());
 	rc = dec_prefix_luma(im, im.proc);
 	if (rc) return rc;
@@ -506,6 +507,7 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	}
 	int exw = dec_y_ll_image(im);
 	if (getenv("HE_SERIAL")) dec_y_shrink_image(im);
+	else if (d.quality <= 16) { for (int r = 1; r < 255; r++) for (int j = 254; j >= 1; j--) dec_shrink_lowq_cell(im.jpeg, r, j); }
 	else if (getenv("HE_WAVEFRONT")) host_wavefront(dwf_shrink_geom(), [&](int r, int j) { return dwf_shrink_cell(im.jpeg, r, j); });
 	else
 		for (int r = 255; r >= 0; r--)
@@ -557,9 +559,7 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 			for (int i = 65535; i >= 0; i--) dec_c_upsample_cell(im.cproc, im.yuv + (1 + v) * 262144, i >> 8, i & 255);
 		}
 	}
-	DecColor col;
-	col.mode = d.quality >= 20 ? 0 : d.quality >= 18 ? 1 : 2;
-	col.y_inv = d.quality == 19 ? 1.025641f : d.quality == 18 ? 1.075269f : 1.063830f;
+	const DecColor col = dec_color_of(d.quality);
 	for (int i = 0; i < 262144; i++) dec_ycc_to_rgb(im.yuv[i], im.yuv[262144 + i], im.yuv[524288 + i], col, rgb + 3 * i);
 	if (yuv_out) memcpy(yuv_out, im.yuv, 3 * 262144);
 	return 0;
