@@ -2,19 +2,21 @@
 // skeleton on 256x256 planes, stride 256, with two small differences noted below), the chroma
 // quantisers offsetUV_recons256 / offsetUV (encoder/image_processing.c:3192-3353, 108-183)
 // and the chroma LL coder highres_compression (encoder/compress_pixel.c:878-1022).
-// q17..q23 (pre_processing_UV and the q<=16 thresholds are not built).
+// The q <= 16 additions (pre_processing_UV, thresholds, LL smoothing) are in enc_lowq.cuh.
 #pragma once
 #include "enc_y3.cuh"
 
 #define CW 256   // chroma row stride
 
 // ---- offsetUV_recons256: LL (64x64) part.  comp=1 first call, comp=0 second call.
-NHW_HD void c_recons_ll_row(const EncImg &im, int r /* 0..63 */, int comp)
+NHW_HD void c_recons_ll_row(const EncImg &im, int r /* 0..63 */, int comp, int q = 20)
 {
 	const int16_t *P = im.cproc + r * CW;
 	int16_t *J = im.cjpeg + r * CW;
-	if (comp) {
-		for (int j = 0; j < 64; j += 2) {   // q>15 branch
+	if (comp && q <= 15) {   // the decoder adds 1 to every chroma LL sample below q16 (nhw_decoder.c:953-962)
+		for (int j = 0; j < 64; j++) J[j] = (int16_t)((P[j] & 65532) + 1);
+	} else if (comp) {
+		for (int j = 0; j < 64; j += 2) {
 			if (r == 0) { J[j] = P[j]; J[j + 1] = (int16_t)(P[j + 1] & 65534); }
 			else { J[j] = (int16_t)(P[j] & 65534); J[j + 1] = P[j + 1]; }
 		}

@@ -6,7 +6,7 @@
 // Every function is either *_row (rows are independent: one thread per row) or *_image
 // (raster dependencies across rows: one thread per image).  Flat plane indices are kept
 // where the reference relies on them (neighbours that wrap to the adjacent row).
-// Supported quality range of this file: q17..q23 (the q<=16 branches are not built).
+// The *_row / *_image forms cover q1..q23; the cell-group forms in enc_cells.cuh are the q17..q23 fast path.
 #pragma once
 #include "dwt_core.cuh"
 
@@ -187,11 +187,37 @@ NHW_HD void y_recons_tag57_row(const EncImg &im, int r)
 	}
 }
 
+// The q <= 16 quantisers cut negative values of the form -(8k+7) on a cycle: of the cells of a row that hold -15
+// the first of every six is cut to -8 and the other five stay -15; of the cells holding -(8k+7) <= -23 the first of
+// every four is cut.  Everything else is cut (image_processing.c:357-410,
+// 2938-2990).  The two counters restart at the beginning of every row (of the region being walked).
+struct QuantCycle {
+	int n15, n23;
+	NHW_HD void reset() { n15 = 0; n23 = 0; }
+	// a = magnitude of a negative coefficient; returns the magnitude after the q <= 16 rounding rule
+	NHW_HD int cut(int a, int mask)
+	{
+		if (a == 15) {
+			const bool first = n15 == 0;
+			n15 = n15 == 5 ? 0 : n15 + 1;
+			return first ? (a & mask) : a;
+		}
+		if (a > 22 && (a & 7) == 7) {
+			const bool first = n23 == 0;
+			n23 = n23 == 3 ? 0 : n23 + 1;
+			return first ? (a & mask) : a;
+		}
+		return a & mask;
+	}
+};
+
 // ---- offsetY_recons256, dead-zone quantise + dequantise of one detail row into im_jpeg
-// (image_processing.c:2909-3133, q>16 branch)
-NHW_HD void y_recons_quant_row(const EncImg &im, int r, int m1, int part)
+// (image_processing.c:2909-3133)
+NHW_HD void y_recons_quant_row(const EncImg &im, int r, int m1, int part, int q = 20)
 {
 	int16_t *P = im.proc + r * YW, *J = im.jpeg + r * YW;
+	QuantCycle cyc;
+	cyc.reset();
 	for (int j = r < 128 ? 128 : 0; j < 256; j++) {
 		int a = P[j];
 		if (a > 15000) {
@@ -209,7 +235,8 @@ NHW_HD void y_recons_quant_row(const EncImg &im, int r, int m1, int part)
 		if (a < 0) {
 			if (a == -7 && j < 255 && P[j + 1] == 8) { P[j] = -8; a = -8; }
 			a = -a;
-			if ((a & 7) < 7) a &= 65528;
+			if (q <= 16) a = cyc.cut(a, 65528);
+			else if ((a & 7) < 7) a &= 65528;
 			a = -a;
 		} else if (a == 8 && j < 255 && P[j + 1] == -7) P[j + 1] = -8;
 		else if (a > 12 && !part && (a & 7) >= 6) {
@@ -225,16 +252,17 @@ NHW_HD void y_recons_quant_row(const EncImg &im, int r, int m1, int part)
 
 // ---- offsetY_recons256, second call only: shrink isolated reconstructed coefficients,
 // in place and in raster order (image_processing.c:3162-3187, q>16 branch)
-NHW_HDN void y_recons_shrink_image(const EncImg &im)
+NHW_HDN void y_recons_shrink_image(const EncImg &im, int q = 20)
 {
 	int16_t *J = im.jpeg;
+	const int dg = q <= 16 ? 16 : 8;   // q <= 16: diagonal neighbours only count from 16 up (image_processing.c:3137-3160)
 	for (int r = 1; r < 255; r++) {
 		int e = r * YW + 1;
 		for (int j = 1; j < 255; j++, e++) {
 			if (nhw_iabs(J[e]) < 8) continue;
-			if (nhw_iabs(J[e - YW - 1]) >= 8 || nhw_iabs(J[e - YW]) >= 8 || nhw_iabs(J[e - YW + 1]) >= 8 ||
-			    nhw_iabs(J[e - 1]) >= 8 || nhw_iabs(J[e + 1]) >= 8 || nhw_iabs(J[e + YW - 1]) >= 8 ||
-			    nhw_iabs(J[e + YW]) >= 8 || nhw_iabs(J[e + YW + 1]) >= 8)
+			if (nhw_iabs(J[e - YW - 1]) >= dg || nhw_iabs(J[e - YW]) >= 8 || nhw_iabs(J[e - YW + 1]) >= dg ||
+			    nhw_iabs(J[e - 1]) >= 8 || nhw_iabs(J[e + 1]) >= 8 || nhw_iabs(J[e + YW - 1]) >= dg ||
+			    nhw_iabs(J[e + YW]) >= 8 || nhw_iabs(J[e + YW + 1]) >= dg)
 				continue;
 			if (r >= 128 || j >= 128) J[e] += J[e] > 0 ? -1 : 1;
 		}

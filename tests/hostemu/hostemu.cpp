@@ -15,6 +15,7 @@
 #include "../../nhwcodec_b200/csrc/dec_par.cuh"
 #include "../../nhwcodec_b200/csrc/dec_parse.h"
 #include "../../nhwcodec_b200/csrc/enc_ll2_masks.cuh"
+#include "../../nhwcodec_b200/csrc/enc_lowq.cuh"
 
 namespace {
 
@@ -565,6 +566,74 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	return 0;
 }
 
+// ---- luma at q <= 16: the stage list of encode_image in its row / image forms (the forms the CUDA path runs for
+// these settings), rows visited bottom-up where they are independent units
+static int he_luma_lowq(const EncImg &im, int q, int ratio, std::vector<int16_t> &tmp, tap_fn tap)
+{
+	EncHdr *h = im.hdr;
+	auto T = [&](const char *name, const void *p, size_t n) { if (tap) tap(name, p, n); };
+	if (q > 6) {   // closed loop (nhw_encoder.c:141-283)
+		for (int r = 255; r >= 0; r--) y_e6a_tag_row(im, r);
+		T("y_e6a_ll1", im.ll1, 65536 * 2);
+		y_recons_ll2_image(im, q, 1);
+		for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 1, q);
+		T("y_rec1_jpeg", im.jpeg, 512 * 512 * 2);
+		inv_level(im.jpeg, im.proc, 512, 256, tmp);
+		T("y_syn1_proc", im.proc, 512 * 512 * 2);
+		for (int r = 255; r >= 0; r--) y_e6c_apply_row(im, r);
+		T("y_e6c_proc", im.proc, 512 * 512 * 2);
+		T("y_e6c_ll1", im.ll1, 65536 * 2);
+		for (int r = 255; r >= 0; r--) y_e6d_correct_row(im, r);
+		T("y_e6d_jpeg", im.jpeg, 512 * 512 * 2);
+		fwd_level(im.jpeg, 512, false, im.proc, 512, 256, tmp);
+		T("y_dwt2b_proc", im.proc, 512 * 512 * 2);
+	}
+	if (q <= 11) for (int r = 255; r >= 128; r--) y_e7_kill_row(im, q, ratio, r);
+	if (q < 13) y_e8_smooth_image(im, q);
+	T("y_e8_proc", im.proc, 512 * 512 * 2);
+	copy_region(im.ll2s, 256, im.proc, 512, 256);
+	y_ll2_to_bytes_image(im, q);
+	T("y_e11_tree1", im.tree1, 16384);
+	T("y_e11_chres", im.ch_res, 16384);
+	T("y_e11_exw", im.exw, h->exw_y_len);
+	ll_dpcm_luma_image(im, q);
+	T("y_e12_chres", im.llcode, h->y_res_comp);
+	copy_region(im.proc, 512, im.ll2s, 256, 256);
+	if (q > 12) {
+		y_recons_ll2_image(im, q, 0);
+		for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 0, q);
+		y_recons_shrink_image(im, q);
+		T("y_rec0_jpeg", im.jpeg, 512 * 512 * 2);
+		inv_level(im.jpeg, im.proc, 512, 256, tmp);
+		T("y_syn0_proc", im.proc, 512 * 512 * 2);
+	}
+	if (q == 16) { for (int r = 511; r >= 256; r--) y_e14_threshold_row(im, q, ratio, r); }
+	else y_e14_lowq_image(im, q, ratio);
+	T("y_e14_proc", im.proc, 512 * 512 * 2);
+	T("y_e15_proc", im.proc, 512 * 512 * 2);
+	if (q > 12) {
+		host_e16(im, q);
+		T("y_e16_proc", im.proc, 512 * 512 * 2);
+		T("y_e16_ll1", im.ll1, 65536 * 2);
+		y_e16b_classify_image(im, q);
+		T("y_e16b_proc", im.proc, 512 * 512 * 2);
+		T("y_e16b_ll1", im.ll1, 65536 * 2);
+		y_e18_pack_list_image(im, 1);
+		T("y_e18_ll1", im.ll1, 65536 * 2);
+	}
+	for (int r = 255; r >= 0; r--) y_e19_restore_row(im, r);
+	y_e20_cleanup_image(im, q, ratio);
+	T("y_e20_proc", im.proc, 512 * 512 * 2);
+	y_offset_pairs_image(im);
+	y_offset_quant_lowq_image(im, ratio);
+	T("y_e21_proc", im.proc, 512 * 512 * 2);
+	for (int s = 127; s >= 0; s--) y_scan_strip(im, s);
+	T("y_e23_scan", im.scan, 262144);
+	y_peephole_image(im);
+	T("y_e24_scan", im.scan, 262144);
+	return 0;
+}
+
 extern "C" {
 
 int he_decode(const uint8_t *blob, long len, uint8_t *rgb, uint8_t *yuv_out) { return host_decode(blob, (size_t)len, rgb, yuv_out); }
@@ -586,7 +655,7 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	const int ratio = 8;
 	std::vector<int16_t> tmp;
 	auto T = [&](const char *name, const void *p, size_t n) { if (tap) tap(name, p, n); };
-	if (q < 17 || q > 23) return -3;
+	if (q < 1 || q > 23) return -3;
 
 	// ---------------- luma ----------------
 	memcpy(im.jpeg, y_pre, 512 * 512 * 2);
@@ -599,6 +668,10 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	fwd_level(im.proc, 512, true, im.proc, 512, 256, tmp);
 	T("y_dwt2_proc", im.proc, 512 * 512 * 2);
 	T("y_ll1", im.ll1, 65536 * 2);
+	if (q <= 16) {
+		int rc = he_luma_lowq(im, q, ratio, tmp, tap);
+		if (rc) return rc;
+	} else {
 	if (getenv("HE_ROWFORM")) { for (int r = 255; r >= 0; r--) y_e6a_tag_row(im, r); }
 	else for (int r = 255; r >= 0; r--) for (int g = 31; g >= 0; g--) y_e6a_tag_cells(im.proc, im.ll1 + r * 256, r, g);
 	T("y_e6a_ll1", im.ll1, 65536 * 2);
@@ -751,6 +824,7 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 	}
 	if (getenv("HE_SERIAL")) y_peephole_image(im); else host_peephole(im);
 	T("y_e24_scan", im.scan, 262144);
+	}
 
 	// ---------------- chroma ----------------
 	for (int v = 0; v < 2; v++) {
@@ -758,15 +832,18 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		const char *pfx = v ? "v" : "u";
 		char name[64];
 		auto TN = [&](const char *sfx, const void *p, size_t n) { snprintf(name, sizeof name, "%s_%s", pfx, sfx); T(name, p, n); };
-		for (int i = 0; i < 65536; i++) im.cjpeg[i] = src[i];
+		if (q <= 14) { for (int i = 65535; i >= 0; i--) im.cjpeg[i] = (int16_t)c_pre_uv_cell(src, q, i >> 8, i & 255); }
+		else for (int i = 0; i < 65536; i++) im.cjpeg[i] = src[i];
 		fwd_level(im.cjpeg, 256, false, im.cproc, 256, 256, tmp);
+		TN("dwt1_proc", im.cproc, 65536 * 2);
 		for (int m = 0; m < 128; m++)
 			for (int k = 0; k < 128; k++) im.cll1[m * 128 + k] = im.cproc[k * 256 + m];
+		if (q <= 16) for (int i = 65535; i >= 0; i--) im.cproc[i] = (int16_t)c_threshold_cell(im.cproc[i], ratio, i >> 8, i & 255);
 		fwd_level(im.cproc, 256, true, im.cproc, 256, 128, tmp);
 		TN("dwt2_proc", im.cproc, 65536 * 2);
 		TN("ll1", im.cll1, 16384 * 2);
-		if (getenv("HE_ROWFORM")) {
-			for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 1);
+		if (getenv("HE_ROWFORM") || q <= 16) {
+			for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 1, q);
 			for (int r = 127; r >= 0; r--) c_recons_quant_row(im, r, ratio, 1);
 		} else host_c_recons_cells(im, ratio, 1);
 		TN("rec1_jpeg", im.cjpeg, 65536 * 2);
@@ -782,8 +859,8 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 		fwd_level(im.cjpeg, 256, false, im.cproc, 256, 128, tmp);
 		TN("dwt2b_proc", im.cproc, 65536 * 2);
 		copy_region(im.cll2s, 128, im.cproc, 256, 128);
-		if (getenv("HE_ROWFORM")) {
-			for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 0);
+		if (getenv("HE_ROWFORM") || q <= 16) {
+			for (int r = 63; r >= 0; r--) c_recons_ll_row(im, r, 0, q);
 			for (int r = 127; r >= 0; r--) c_recons_quant_row(im, r, ratio, 0);
 		} else host_c_recons_cells(im, ratio, 0);
 		inv_level(im.cjpeg, im.cproc, 256, 128, tmp);
@@ -795,6 +872,7 @@ int he_encode(void *hw, const int16_t *y_pre, const uint8_t *u8, const uint8_t *
 			for (int r = 127; r >= 0; r--) for (int j = 127; j >= 0; j--) if (tg[r * 128 + j]) c_drop_tag(im.cproc, r * 256 + j, tg[r * 128 + j]);
 		}
 		copy_region(im.cproc, 256, im.cll2s, 128, 128);
+		if (q <= 11) c_ll_smooth_image(im);
 		TN("tags_proc", im.cproc, 65536 * 2);
 		int e = c_ll_to_bytes_image(im, v);
 		if (v) h->exw_v_len = e; else h->exw_u_len = e;

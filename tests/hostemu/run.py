@@ -88,6 +88,13 @@ def compare(pix, q, verbose=True):
             w = 512 if a16.size == 262144 else 256 if a16.size == 65536 else 128
             # chroma planes: only rows/cols that exist; luma tap planes compare fully except
             # regions the reference leaves as stale scratch (handled per-name below)
+            if name.endswith("_jpeg"):
+                # im_jpeg outside the band being reconstructed is stale scratch of earlier transforms in the reference
+                # (nobody reads it): only the live N/2 x N/2 region is compared
+                m = np.zeros((w, w), bool)
+                m[: w // 2, : w // 2] = True
+                a16 = np.where(m.reshape(-1), a16, 0)
+                b16 = np.where(m.reshape(-1), b16, 0)
             same = np.array_equal(a16, b16)
             if not same:
                 d = np.flatnonzero(a16 != b16)
