@@ -16,6 +16,7 @@
 #include "../../nhwcodec_b200/csrc/dec_parse.h"
 #include "../../nhwcodec_b200/csrc/enc_ll2_masks.cuh"
 #include "../../nhwcodec_b200/csrc/enc_lowq.cuh"
+#include "../../nhwcodec_b200/csrc/pre_lowq.cuh"
 
 namespace {
 
@@ -637,6 +638,17 @@ static int he_luma_lowq(const EncImg &im, int q, int ratio, std::vector<int16_t>
 extern "C" {
 
 int he_decode(const uint8_t *blob, long len, uint8_t *rgb, uint8_t *yuv_out) { return host_decode(blob, (size_t)len, rgb, yuv_out); }
+
+// luma pre-sharpening at q <= 16, in place on a 512x512 plane
+void he_pre_lowq(int16_t *y, int q)
+{
+	std::vector<int16_t> o(512 * 512 + 8192, 0), k(512 * 512 + 8192, 0), yy(512 * 512 + 8192, 0);
+	std::vector<uint8_t> m(512 * 512 + 8192, 0);
+	memcpy(yy.data() + 4096, y, 512 * 512 * 2);
+	for (auto &v : k) v = 0x5555;   // the kernel plane is scratch: stale contents must not matter
+	pre_low_image(yy.data() + 4096, o.data() + 4096, k.data() + 4096, m.data() + 4096, q);
+	memcpy(y, yy.data() + 4096, 512 * 512 * 2);
+}
 
 void *he_new() { return make_work(); }
 void he_free(void *h) { delete static_cast<Work *>(h); }
