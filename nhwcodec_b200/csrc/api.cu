@@ -366,14 +366,13 @@ static void lane_done(nhw_ctx *c, nhw_ctx &v)
 	c->dbg_stopped = v.dbg_stopped;
 }
 
-static bool quality_supported(int q) { return q >= 17 && q <= 23; }
+static bool quality_supported(int q) { return q >= 1 && q <= 23; }   // q0 is accepted by the reference CLI but its tables are undefined
 
 int nhw_stage_colorspace_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quality, int pre,
                                 int16_t *y, uint8_t *u, uint8_t *v)
 {
 	if (!c || !rgb_dev || n <= 0) return NHW_ERR_ARG;
 	if (quality < 1 || quality > 23) return NHW_ERR_QUALITY;
-	if (pre && !(quality >= 17 && quality <= 23)) return NHW_ERR_QUALITY;
 	cudaSetDevice(c->device);
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
 		int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
@@ -391,7 +390,7 @@ int nhw_stage_frontend_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int qua
                               int16_t *y_proc, int16_t *y_ll1, int16_t *c_proc, int16_t *c_ll1)
 {
 	if (!c || !rgb_dev || n <= 0) return NHW_ERR_ARG;
-	if (!(quality >= 17 && quality <= 23)) return NHW_ERR_QUALITY;
+	if (quality < 1 || quality > 23) return NHW_ERR_QUALITY;
 	cudaSetDevice(c->device);
 	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT, QS = NHW_Q_SLOT;
 	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
@@ -420,7 +419,7 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
                             uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev)
 {
 	if (!c || !rgb_dev || !out_dev || n <= 0) return NHW_ERR_ARG;
-	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q23 are)", quality); return NHW_ERR_QUALITY; }
+	if (!quality_supported(quality)) { nhw::set_error("quality %d outside 1..23", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
 	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
@@ -447,7 +446,7 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
                      uint8_t *out, size_t out_cap, uint64_t *offsets, int32_t *status)
 {
 	if (!c || !rgb || !out || !offsets || n <= 0) return NHW_ERR_ARG;
-	if (!quality_supported(quality)) { nhw::set_error("quality %d not built yet (q17..q23 are)", quality); return NHW_ERR_QUALITY; }
+	if (!quality_supported(quality)) { nhw::set_error("quality %d outside 1..23", quality); return NHW_ERR_QUALITY; }
 	cudaSetDevice(c->device);
 	// Waves of sub-chunks dealt round robin to a few streams: a sub-chunk uploads its pixels, encodes and packs
 	// on its stream, so uploads overlap the kernels of the other streams; finished sub-chunks come back on the

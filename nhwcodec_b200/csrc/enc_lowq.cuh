@@ -203,6 +203,20 @@ NHW_HDN void y_e14_lowq_image(const EncImg &im, int q, int ratio)
 	}
 }
 
+// ---- offsetY_recons256's isolated-coefficient shrink at q <= 16 (image_processing.c:3137-3160): a diagonal neighbour
+// only blocks from 16 up.  A blocking diagonal neighbour of exactly +-16 may itself shrink first, so the rule needs
+// the rows above final and the rows below untouched; the four direct neighbours cannot change while this cell is a
+// candidate (they would need it to be below 8), so the cells of one row are independent.
+NHW_HD void y_recons_shrink_lowq_cell(int16_t *J, int r, int j)
+{
+	const int e = r * YW + j;
+	if (nhw_iabs(J[e]) < 8) return;
+	if (nhw_iabs(J[e - YW - 1]) >= 16 || nhw_iabs(J[e - YW]) >= 8 || nhw_iabs(J[e - YW + 1]) >= 16 || nhw_iabs(J[e - 1]) >= 8 ||
+	    nhw_iabs(J[e + 1]) >= 8 || nhw_iabs(J[e + YW - 1]) >= 16 || nhw_iabs(J[e + YW]) >= 8 || nhw_iabs(J[e + YW + 1]) >= 16)
+		return;
+	if (r >= 128 || j >= 128) J[e] += J[e] > 0 ? -1 : 1;
+}
+
 // ---- offsetY, the coefficient -> byte loop at q <= 16 (image_processing.c:312-519).  Differences from the q > 16
 // form (y_offset_quant_image): no pattern codes exist; negative values are cut on the QuantCycle (restarted per
 // row); and pairs of neighbouring large values whose magnitudes both end in 6/7 trade two units on a three-state

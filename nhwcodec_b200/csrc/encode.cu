@@ -14,6 +14,7 @@
 #include "nhw_dev.cuh"
 #include "enc_seg.cuh"
 #include "enc_ll2_masks.cuh"
+#include "enc_lowq.cuh"
 #include "enc_batch.cuh"
 #include "../../include/nhw_cuda.h"
 
@@ -1585,6 +1586,9 @@ __global__ void __launch_bounds__(256) k_write_stream(EncBatch b, int n, uint8_t
 			stream_layout(im, hdr, [&](const uint8_t *s, int cnt) {
 				if (nsec < WS_MAX_SECTIONS) { src[nsec] = s; off[nsec + 1] = off[nsec] + cnt; nsec++; }
 			});
+		// the output slot is NHW_MAX_STREAM_BYTES: a stream that would not fit (the section caps add up to more) is
+		// reported, not written
+		if (off[nsec] > (int)NHW_MAX_STREAM_BYTES) { st = NHW_ERR_OVERFLOW_DEV; nsec = 0; }
 		if (len) len[i] = (uint32_t)off[nsec];
 		if (status) status[i] = st;
 	}
@@ -1594,6 +1598,18 @@ __global__ void __launch_bounds__(256) k_write_stream(EncBatch b, int n, uint8_t
 		const uint8_t *s = src[k];
 		const int o = off[k], cnt = off[k + 1] - o;
 		for (int t = threadIdx.x; t < cnt; t += 256) dst[o + t] = s ? s[t] : (uint8_t)0;
+	}
+}
+
+// ---- isolated-coefficient shrink at q <= 16 (enc_lowq.cuh: y_recons_shrink_lowq_cell): one CTA per image, thread =
+// column, rows top to bottom with a barrier per row
+__global__ void __launch_bounds__(256) k_recons_shrink_lowq(EncBatch b)
+{
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int j = threadIdx.x;
+	for (int r = 1; r < 255; r++) {
+		if (j >= 1 && j < 255) y_recons_shrink_lowq_cell(im.jpeg, r, j);
+		__syncthreads();
 	}
 }
 
@@ -1639,6 +1655,12 @@ void idwt_attrs()
 }  // namespace
 
 namespace nhw {
+
+static void ll2_code_attr(nhw_ctx *)
+{
+	static bool attr = false;
+	if (!attr) { cudaFuncSetAttribute(k_ll2_code, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_CODE_SMEM); attr = true; }
+}
 
 EncBatch enc_batch_of(nhw_ctx *c)
 {
@@ -1693,6 +1715,48 @@ static void zero_bytes(nhw_ctx *c, const EncBatch &b, int n, size_t off, size_t 
 	NHW_LAUNCH(c, k_zero_bytes, dim3((unsigned)((units + 255) / 256), n), 256, 0, b.bytes, (size_t)ENC_BYTES_SLOT, off, count);
 }
 
+// ---- the luma chain at q <= 16 (nhw_encoder.c:141-2252 with the low-quality arms): the kernels that are written for
+// every quality are shared with the q17..q23 chain; the stages whose fast forms only cover q17..q23, and the stages
+// that exist only down here (enc_lowq.cuh), run in their row / image forms.
+static void encode_luma_lowq(nhw_ctx *c, const EncBatch &b, int n, int q, int ratio)
+{
+	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT;
+	if (q > 6) {   // closed loop
+		run_groups(c, "y_e6a_tag", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { y_e6a_tag_cells(im.proc, im.ll1 + r * 256, r, g); });
+		NHW_LAUNCH_L(c, "y_recons1_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 1);
+		run_rows(c, "y_recons1_quant_rows", b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 1, q); });
+		idwt_luma256(c, b, n);
+		NHW_LAUNCH_L(c, "y_e6c_apply", k_e6c_apply, dim3(16, n), 256, 0, b);
+		NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(32, n), 256, 0, b);
+		dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
+	}
+	if (q <= 11) run_rows(c, "y_e7_kill", b, n, 128, [=] __device__(const EncImg &im, int r) { y_e7_kill_row(im, q, ratio, 128 + r); });
+	if (q < 13) run_image(c, "y_e8_smooth", b, n, [=] __device__(const EncImg &im, int) { y_e8_smooth_image(im, q); });
+	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
+	ll2_code_attr(c);
+	NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
+	if (q > 12) {   // second reconstruction
+		NHW_LAUNCH_L(c, "y_recons0_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 0);
+		run_rows(c, "y_recons0_quant_rows", b, n, 256, [=] __device__(const EncImg &im, int r) { y_recons_quant_row(im, r, ratio, 0, q); });
+		NHW_LAUNCH_L(c, "y_recons0_shrink_lowq", k_recons_shrink_lowq, n, 256, 0, b);
+		idwt_luma256(c, b, n);
+	}
+	if (q == 16) run_rows(c, "y_e14_rows", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e14_threshold_row(im, q, ratio, 256 + r); });
+	else run_image(c, "y_e14_lowq", b, n, [=] __device__(const EncImg &im, int) { y_e14_lowq_image(im, q, ratio); });
+	if (q > 12) {
+		NHW_LAUNCH_L(c, "y_e16_residual", k_e16_residual, n, 256, 0, b, q);
+		NHW_LAUNCH_L(c, "y_e16b_classify", k_e16b_classify, n, 256, 0, b, q);
+		NHW_LAUNCH_L(c, "y_e18_lists", k_e18_lists, n, 256, 0, b, q);
+		NHW_LAUNCH_L(c, "y_e18_tails", k_e18_tails, dim3(3, n), 32, 0, b, q);
+	}
+	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(8, n), 256, 0, b);
+	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_bands, dim3(3, n), 256, 0, b, q, ratio);
+	run_groups_inplace(c, "y_offset_mult8", b, n, 512, 6, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_offset_mult8_cells(im.proc, r, g, o); });
+	run_image(c, "y_offset_quant_lowq", b, n, [=] __device__(const EncImg &im, int) { y_offset_quant_lowq_image(im, ratio); });
+	run_rows(c, "y_scan_strips", b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
+	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 262144 / 8, b);
+}
+
 // Encode n <= max_batch images whose pixels are in device memory.  out_dev: n slots of
 // NHW_MAX_STREAM_BYTES.  All work is queued on c->stream; the caller synchronises.
 void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev)
@@ -1725,6 +1789,13 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		cudaStreamWaitEvent(side.stream, c->ev_chroma0, 0);
 	}
 	// U and V planes side by side (nhw_encoder.c:2255-2868)
+	const bool lowq = q <= 16;   // row / image forms of the stages whose cell-group forms are q17..q23 only
+	if (lowq)
+		run_plane_rows(cs, "c_recons1_rows", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
+			if (r < 64) c_recons_ll_row(im, r, 1, q);
+			c_recons_quant_row(im, r, ratio, 1);
+		});
+	else
 	run_plane_groups(cs, "c_recons1", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int) {
 		int o[8];
 		c_recons_cells(im.cproc + r * CW, r, g, ratio, 1, o);
@@ -1738,14 +1809,21 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	});
 	dwt_level_from_jpeg(cs, 2 * n, b.c_jpeg, CS, b.c_proc, CS, 128, 256);
 	NHW_LAUNCH(cs, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_proc, CS, 256, b.c_ll2s, QS, 128, 128);
+	if (lowq)
+		run_plane_rows(cs, "c_recons0_rows", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
+			if (r < 64) c_recons_ll_row(im, r, 0, q);
+			c_recons_quant_row(im, r, ratio, 0);
+		});
+	else
 	run_plane_groups(cs, "c_recons0", b, n, 128, 4, [=] __device__(const EncImg &im, int r, int g, int) {
 		int o[8];
 		c_recons_cells(im.cproc + r * CW, r, g, ratio, 0, o);
 		st8(im.cjpeg + r * CW + g * 8, o);
 	});
 	idwt_chroma128(cs, b, n);
-	NHW_LAUNCH_L(cs, "c_residual_tags", k_c_residual_tags, dim3(8, 2 * n), 256, 0, b, q);
+	if (q >= 18) NHW_LAUNCH_L(cs, "c_residual_tags", k_c_residual_tags, dim3(8, 2 * n), 256, 0, b, q);
 	NHW_LAUNCH(cs, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_ll2s, QS, 128, b.c_proc, CS, 256, 128);
+	if (q <= 11) run_plane(cs, "c_ll_smooth", b, n, [=] __device__(const EncImg &im, int) { c_ll_smooth_image(im); });
 	NHW_LAUNCH_L(cs, "c_ll_quant", k_c_ll_quant, n, 64, 0, b, q);
 	NHW_LAUNCH_L(cs, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);
 
@@ -1754,6 +1832,8 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		c->launches += side.launches;
 	}
 
+	if (lowq) encode_luma_lowq(c, b, n, q, ratio);
+	else {
 	// ---- luma closed loop (nhw_encoder.c:141-283)
 	run_groups(c, "y_e6a_tag", b, n, 256, 5, [=] __device__(const EncImg &im, int r, int g) { y_e6a_tag_cells(im.proc, im.ll1 + r * 256, r, g); });
 	NHW_LAUNCH_L(c, "y_recons1_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 1);
@@ -1767,11 +1847,8 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	// ---- LL2 coding (nhw_encoder.c:623-757)
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
 	// LL2 -> bytes (wavefront) and the DPCM coder (step links + chain walk), see enc_ll_par.cuh
-	{
-		static bool attr = false;
-		if (!attr) { cudaFuncSetAttribute(k_ll2_code, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_CODE_SMEM); attr = true; }
-		NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
-	}
+	ll2_code_attr(c);
+	NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
 	// (the coder works on a shared-memory copy of the band: the plane still holds what the snapshot holds)
 
 	// ---- second reconstruction = what the decoder will see as LL1 (nhw_encoder.c:759-781)
@@ -1809,6 +1886,8 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		NHW_LAUNCH_L(c, "y_hq_lists", k_hq_lists, n, 256, 0, b, q);
 	}
 	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 262144 / 8, b);
+
+	}
 
 	if (cs != c) cudaStreamWaitEvent(c->stream, c->ev_chroma1, 0);   // the chroma chain joins here
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)

@@ -14,6 +14,8 @@
 #include "dwt_core.cuh"
 #include "color_core.cuh"
 #include "pre_core.cuh"
+#include "pre_lowq.cuh"
+#include "enc_lowq.cuh"
 
 namespace {
 
@@ -248,9 +250,63 @@ __global__ void __launch_bounds__(256) k_pre_nudge(const int16_t *__restrict__ k
 	if (d1) dst[1] = (int16_t)(dst[1] + d1);
 }
 
+// =====================================================================================
+// q <= 16
+// =====================================================================================
+// luma pre-sharpening state machine (pre_lowq.cuh): one walker per image.  The walks branch on data at every pair, so
+// a warp only carries PRE_LOW_WALKERS images (one active lane in every 32 / PRE_LOW_WALKERS): divergence costs a warp
+// every path its lanes take, and the many more warps hide each other's memory latency.
+#define PRE_LOW_WALKERS 4
+__global__ void __launch_bounds__(128) k_pre_lowq(int16_t *__restrict__ y, size_t ystride, int16_t *__restrict__ copy,
+                                                  int16_t *__restrict__ kern, int16_t *__restrict__ marks, size_t astride, int n, int q)
+{
+	const int group = 32 / PRE_LOW_WALKERS;
+	if (threadIdx.x % group) return;
+	const int img = (blockIdx.x * 128 + threadIdx.x) / group;
+	if (img >= n) return;
+	pre_low_image(y + (size_t)img * ystride, copy + (size_t)img * astride, kern + (size_t)img * astride,
+	              reinterpret_cast<uint8_t *>(marks + (size_t)img * astride), q);
+}
+
+// chroma pre-filter (pre_processing_UV, q <= 14): 4:2:0 bytes -> int16 plane with the +-1 / +-2 nudges applied
+__global__ void __launch_bounds__(256) k_c_pre_uv(const uint8_t *__restrict__ uv, int16_t *__restrict__ out, size_t oslot, int q)
+{
+	const uint8_t *src = uv + (size_t)blockIdx.y * NHW_CPLANE;
+	int16_t *dst = out + (size_t)blockIdx.y * oslot;
+	const int r = blockIdx.x, j = threadIdx.x;
+	dst[r * 256 + j] = (int16_t)c_pre_uv_cell(src, q, r, j);
+}
+
+// chroma level-1 band thresholds (q <= 16): in place on the coefficient plane, outside the level-2 region
+__global__ void __launch_bounds__(256) k_c_thresholds(int16_t *__restrict__ proc, size_t pslot, int ratio)
+{
+	int16_t *P = proc + (size_t)blockIdx.y * pslot;
+	const int r = blockIdx.x, j = threadIdx.x;
+	if (r < 128 && j < 128) return;
+	const int v = P[r * 256 + j], w = c_threshold_cell(v, ratio, r, j);
+	if (w != v) P[r * 256 + j] = (int16_t)w;
+}
+
 }  // namespace
 
 namespace nhw {
+
+void pre_processing_lowq(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystride)
+{
+	const int per_cta = 128 / (32 / PRE_LOW_WALKERS);
+	NHW_LAUNCH_L(c, "k_pre_lowq", k_pre_lowq, (n + per_cta - 1) / per_cta, 128, 0, y, ystride, c->y_proc + NHW_GUARD_S,
+	             c->y_aux + NHW_GUARD_S, c->y_aux2 + NHW_GUARD_S, (size_t)NHW_Y_SLOT, n, quality);
+}
+
+void chroma_pre_uv(nhw_ctx *c, int n_planes, int quality, const uint8_t *uv, int16_t *out, size_t oslot)
+{
+	NHW_LAUNCH_L(c, "k_c_pre_uv", k_c_pre_uv, dim3(256, n_planes), 256, 0, uv, out, oslot, quality);
+}
+
+void chroma_thresholds(nhw_ctx *c, int n_planes, int16_t *proc, size_t pslot, int ratio)
+{
+	NHW_LAUNCH_L(c, "k_c_thresholds", k_c_thresholds, dim3(256, n_planes), 256, 0, proc, pslot, ratio);
+}
 
 ColorParams color_params(int quality)
 {
@@ -274,7 +330,8 @@ void colorspace(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y, 
 
 void pre_processing(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystride)
 {
-	(void)quality;   // q17..q21 share one rule set; q>=22 never gets here; q<=16 is rejected upstream
+	if (quality <= 16) { pre_processing_lowq(c, n, quality, y, ystride); return; }
+	// q17..q21 share one rule set; q>=22 never gets here
 	dim3 grid((510 + PRE_WARPS - 1) / PRE_WARPS, n);
 	int16_t *energy = c->y_aux2 + NHW_GUARD_S, *kern = c->y_aux + NHW_GUARD_S;
 	NHW_LAUNCH(c, k_pre_energy, grid, 32 * PRE_WARPS, 0, y, energy, c->rowmap, ystride, (size_t)NHW_Y_SLOT);

@@ -174,6 +174,18 @@ __device__ __forceinline__ void unpack16(const uint4 &w, int (&x)[16])
 	}
 }
 
+// 16 consecutive int16 samples of a plane row (32-byte aligned)
+__device__ __forceinline__ void load16(const int16_t *p, int (&x)[16])
+{
+	const uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
+	const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		x[2 * k] = (int16_t)(w[k] & 0xffffu);
+		x[2 * k + 1] = (int16_t)(w[k] >> 16);
+	}
+}
+
 // 8 low + 8 high outputs of the vertical filter for one column: col[j] = R[2*e0 - 2 + j][k],
 // j = 0..18.  downfilter53VI (fine) / downfilter53, encoder/filters.c:203-287,55-114.
 __device__ __forceinline__ void col_pass8(const int (&col)[19], int e0, bool fine, bool last_group, int &rem,
@@ -205,28 +217,35 @@ __device__ __forceinline__ void col_pass8(const int (&col)[19], int e0, bool fin
 // =====================================================================================
 // k_front_luma
 // =====================================================================================
+// PLANE_IN (q <= 16): the luma plane already exists in memory as int16 (colour transform and the pre-sharpening state
+// machine ran as kernels of their own, front.cu), so stages C and E are skipped, stage A reads its row from `yplane`
+// and the chroma bytes are not touched.
+template <bool PLANE_IN>
 __global__ void __launch_bounds__(FT, 2)
-k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t pstride, int16_t *__restrict__ ll1,
-             size_t lstride, uint8_t *__restrict__ uv, size_t uvstride, ColorParams cp, int pre,
-             int16_t *__restrict__ kept, size_t kstride)
+k_front_luma(const uint8_t *__restrict__ rgb, const int16_t *__restrict__ yplane, size_t ystride, int16_t *__restrict__ proc,
+             size_t pstride, int16_t *__restrict__ ll1, size_t lstride, uint8_t *__restrict__ uv, size_t uvstride,
+             ColorParams cp, int pre, int16_t *__restrict__ kept, size_t kstride)
 {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	FrontSmem &S = *reinterpret_cast<FrontSmem *>(smem_raw);
 	const int img = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint8_t *src = rgb + (size_t)img * NHW_RGB_BYTES;
+	const uint8_t *src = PLANE_IN ? nullptr : rgb + (size_t)img * NHW_RGB_BYTES;
+	const int16_t *YP = PLANE_IN ? yplane + (size_t)img * ystride : nullptr;
 	int16_t *P = proc + (size_t)img * pstride;
 	int16_t *LL = ll1 + (size_t)img * lstride;
-	uint8_t *UV = uv + (size_t)img * uvstride;
+	uint8_t *UV = PLANE_IN ? nullptr : uv + (size_t)img * uvstride;
 
-	if (tid == 0) {
-		mbar_init(&S.mbar, 1);
-		S.strip_carry[0] = 0;
-		S.strip_flag[0] = 0;
+	if (!PLANE_IN) {
+		if (tid == 0) {
+			mbar_init(&S.mbar, 1);
+			S.strip_carry[0] = 0;
+			S.strip_flag[0] = 0;
+		}
+		S.pcat[tid] = g_pair_cat[tid];
+		if (tid < PAIR_CATS * PAIR_CATS) S.plut[tid] = g_pair_lut[tid];
+		__syncthreads();
+		if (tid == 0) bulk_load(S.rgb, src, RGB_ROWS * 1536, &S.mbar);
 	}
-	S.pcat[tid] = g_pair_cat[tid];
-	if (tid < PAIR_CATS * PAIR_CATS) S.plut[tid] = g_pair_lut[tid];
-	__syncthreads();
-	if (tid == 0) bulk_load(S.rgb, src, RGB_ROWS * 1536, &S.mbar);
 
 	int v_rem = 0;   // downfilter53VI's fed-forward remainder of this thread's column
 	// registers that live from stage E to stage A of a strip
@@ -239,6 +258,7 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 		const int y_hi = 16 * i + 18 < 512 ? 16 * i + 18 : 512;
 
 		// ------------------------------------------------------------------ C: colour
+		if (!PLANE_IN) {
 		mbar_wait(&S.mbar, (uint32_t)(i & 1));
 		for (int row = y_lo + warp; row < y_hi; row += 16) {
 			const uint8_t *line = S.rgb + (row - y_lo) * 1536;
@@ -284,10 +304,11 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 			const int n_hi = n_lo + 16 < 512 ? n_lo + 16 : 512;
 			bulk_load(S.rgb, src + (size_t)n_lo * 1536, (uint32_t)(n_hi - n_lo) * 1536u, &S.mbar);
 		}
+		}
 
 		// ------------------------------------------------------------------ E: energies, carry maps; chroma out
 		const int r = 16 * i + 1 + warp;
-		const bool sharpen = pre && r <= 510;
+		const bool sharpen = !PLANE_IN && pre && r <= 510;
 		if (sharpen) {
 			const uint8_t *up = S.yring[(r - 1) % RING], *mid = S.yring[r % RING], *dn = S.yring[(r + 1) % RING];
 			uint32_t wu[6], wm[6], wd[6];
@@ -350,7 +371,7 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 			}
 		}
 		// chroma rows whose three source rows are complete: vertical [1 2 1]/4 + 2:1 (colorspace.c:241-256)
-		{
+		if (!PLANE_IN) {
 			const int c_lo = i ? 8 * i + 1 : 0, c_hi = i < 31 ? 8 * i + 9 : 256;
 			for (int task = warp; task < 2 * (c_hi - c_lo); task += 16) {
 				const int plane = task & 1, cr = c_lo + (task >> 1);
@@ -378,7 +399,7 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 				reinterpret_cast<uint2 *>(UV + (size_t)plane * NHW_CPLANE + cr * 256)[lane] = o;
 			}
 		}
-		__syncthreads();
+		__syncthreads();   // (PLANE_IN: the one barrier that keeps the next stage A off the ring rows stage V is still reading)
 
 		// ------------------------------------------------------------------ A: apply carry, nudge, horizontal filter
 		if (r <= 511) {
@@ -437,12 +458,15 @@ k_front_luma(const uint8_t *__restrict__ rgb, int16_t *__restrict__ proc, size_t
 				unpack16(ymid, x);
 #pragma unroll
 				for (int t = 0; t < 16; t++) x[t] += d[t];
+			} else if (PLANE_IN) {
+				load16(YP + r * 512 + 16 * lane, x);
 			} else {
 				unpack16(reinterpret_cast<const uint4 *>(S.yring[r % RING])[lane], x);
 			}
 			row_pass_regs(x, lane, S.rring[r % RING], r % RING < 19);
 			if (i == 0 && warp == 0) {   // row 0 is outside the sharpening window
-				unpack16(reinterpret_cast<const uint4 *>(S.yring[0])[lane], x);
+				if (PLANE_IN) load16(YP + 16 * lane, x);
+				else unpack16(reinterpret_cast<const uint4 *>(S.yring[0])[lane], x);
 				row_pass_regs(x, lane, S.rring[0], true);
 			}
 		}
@@ -619,7 +643,8 @@ void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_
 {
 	static bool attr = false;
 	if (!attr) {
-		cudaFuncSetAttribute(k_front_luma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem));
+		cudaFuncSetAttribute(k_front_luma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem));
+		cudaFuncSetAttribute(k_front_luma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem));
 		attr = true;
 	}
 	static bool tables[64] = {false};
@@ -633,8 +658,33 @@ void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_
 		tables[c->device & 63] = true;
 	}
 	const ColorParams p = color_params(quality);
-	NHW_LAUNCH_L(c, "k_front_luma", k_front_luma, n, FT, sizeof(FrontSmem), rgb, y_proc, ypstride, y_ll1, ylstride, uv_bytes,
-	             (size_t)2 * NHW_CPLANE, p, quality < 22 ? 1 : 0, quality > 21 ? kept : (int16_t *)nullptr, kstride);
+	if (quality <= 16) {
+		// colour (integer form) -> luma plane + 4:2:0 bytes, the pre-sharpening state machine in place on the plane,
+		// then the same level-1 analysis fed from the plane.  The plane lives in the context's im_jpeg slots (the
+		// walkers use y_proc / y_aux / y_aux2 as scratch, all dead at this point).
+		int16_t *yplane = c->y_jpeg + NHW_GUARD_S;
+		const size_t ys = NHW_Y_SLOT;
+		colorspace(c, rgb, n, quality, yplane, ys, uv_bytes, uv_bytes + NHW_CPLANE, (size_t)2 * NHW_CPLANE);
+		pre_processing_lowq(c, n, quality, yplane, ys);
+		NHW_LAUNCH_L(c, "k_front_luma<plane>", k_front_luma<true>, n, FT, sizeof(FrontSmem), (const uint8_t *)nullptr, yplane, ys,
+		             y_proc, ypstride, y_ll1, ylstride, (uint8_t *)nullptr, (size_t)0, p, 0, (int16_t *)nullptr, kstride);
+		launch_level<256, int16_t, 1024>(c, "k_dwt_level<256>", n, y_ll1, ylstride, 256, y_proc, ypstride, 512, nullptr, 0);
+		if (quality <= 14) {
+			// pre_processing_UV: the filtered samples leave 0..255, so the planes go through int16 (chroma im_jpeg slots)
+			int16_t *cj = c->c_jpeg + NHW_GUARD_S;
+			chroma_pre_uv(c, 2 * n, quality, uv_bytes, cj, (size_t)NHW_C_SLOT);
+			launch_level<256, int16_t, 1024>(c, "k_dwt_level<256>", 2 * n, cj, (size_t)NHW_C_SLOT, 256, c_proc, cpstride, 256, c_ll1, clstride);
+		} else {
+			launch_level<256, uint8_t, 1024>(c, "k_dwt_level<256,u8>", 2 * n, uv_bytes, (size_t)NHW_CPLANE, 256, c_proc, cpstride, 256,
+			                                 c_ll1, clstride);
+		}
+		chroma_thresholds(c, 2 * n, c_proc, cpstride, 8);
+		launch_level<128, int16_t, 256>(c, "k_dwt_level<128>", 2 * n, c_ll1, clstride, 128, c_proc, cpstride, 256, nullptr, 0);
+		return;
+	}
+	NHW_LAUNCH_L(c, "k_front_luma", k_front_luma<false>, n, FT, sizeof(FrontSmem), rgb, (const int16_t *)nullptr, (size_t)0, y_proc,
+	             ypstride, y_ll1, ylstride, uv_bytes, (size_t)2 * NHW_CPLANE, p, quality < 22 ? 1 : 0,
+	             quality > 21 ? kept : (int16_t *)nullptr, kstride);
 	launch_level<256, int16_t, 1024>(c, "k_dwt_level<256>", n, y_ll1, ylstride, 256, y_proc, ypstride, 512, nullptr, 0);
 	launch_level<256, uint8_t, 1024>(c, "k_dwt_level<256,u8>", 2 * n, uv_bytes, (size_t)NHW_CPLANE, 256, c_proc, cpstride, 256,
 	                                 c_ll1, clstride);

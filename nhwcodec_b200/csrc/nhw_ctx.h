@@ -70,6 +70,9 @@ namespace nhw {
 void colorspace(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y, size_t ystride, uint8_t *u, uint8_t *v,
                 size_t cstride);
 void pre_processing(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystride);
+void pre_processing_lowq(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystride);   // y must not be y_proc / y_aux / y_aux2
+void chroma_pre_uv(nhw_ctx *c, int n_planes, int quality, const uint8_t *uv, int16_t *out, size_t oslot);
+void chroma_thresholds(nhw_ctx *c, int n_planes, int16_t *proc, size_t pslot, int ratio);
 // front_fused.cu
 void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_proc, size_t ypstride, int16_t *y_ll1,
                  size_t ylstride, uint8_t *uv_bytes, int16_t *c_proc, size_t cpstride, int16_t *c_ll1, size_t clstride,

@@ -603,7 +603,8 @@ static int he_luma_lowq(const EncImg &im, int q, int ratio, std::vector<int16_t>
 	if (q > 12) {
 		y_recons_ll2_image(im, q, 0);
 		for (int r = 255; r >= 0; r--) y_recons_quant_row(im, r, ratio, 0, q);
-		y_recons_shrink_image(im, q);
+		if (getenv("HE_SERIAL")) y_recons_shrink_image(im, q);
+		else for (int r = 1; r < 255; r++) for (int j = 254; j >= 1; j--) y_recons_shrink_lowq_cell(im.jpeg, r, j);
 		T("y_rec0_jpeg", im.jpeg, 512 * 512 * 2);
 		inv_level(im.jpeg, im.proc, 512, 256, tmp);
 		T("y_syn0_proc", im.proc, 512 * 512 * 2);

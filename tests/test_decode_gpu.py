@@ -14,7 +14,7 @@ def _mixed(n, seed0):
     return np.stack([fs[i % 3](seed0 + i) for i in range(n)])
 
 
-@pytest.mark.parametrize("q", [20, 17, 18, 19, 21, 22, 23])
+@pytest.mark.parametrize("q", list(range(1, 24)))
 def test_decode_bit_exact(codec, ref, q):
     imgs = _mixed(6, 9100 + q)
     streams = [ref.ref_encode(imgs[i], q) for i in range(imgs.shape[0])]
@@ -40,7 +40,7 @@ def test_round_trip_own_streams_and_chunking(codec, ref):
         assert np.array_equal(rgb[i], ref.ref_decode(streams[i])), i
 
 
-@pytest.mark.parametrize("q", [17, 20, 22, 23])
+@pytest.mark.parametrize("q", [1, 8, 12, 16, 17, 20, 22, 23])
 def test_decode_known_answer(codec, ref, q):
     """md5 of the BMP nhw-dec writes for the formula-defined image"""
     import hashlib
@@ -56,3 +56,34 @@ def test_decode_known_answer(codec, ref, q):
 def test_decode_rejects_garbage(codec):
     rgb, status = codec.decode([b"\x09" + b"\0" * 200, b"\0" * 10])
     assert (status != 0).all()
+
+
+def test_decode_mixed_low_and_high_quality_batch(codec, ref):
+    """streams of every quality in ONE decode batch (each carries its own quality byte)"""
+    imgs = _mixed(23, 9500)
+    streams = [ref.ref_encode(imgs[i], i + 1) for i in range(23)]
+    rgb, status = codec.decode(streams)
+    assert (status == 0).all(), status
+    for i, s in enumerate(streams):
+        assert np.array_equal(rgb[i], ref.ref_decode(s)), "q=%d" % (i + 1)
+
+
+def test_decode_hostile_headers(codec, ref):
+    """section lengths beyond the decode workspace, truncated streams, lying lengths: per-stream error status, the
+    good stream next to them still decodes (dec_parse.h)"""
+    import struct
+    img = _mixed(1, 9600)[0]
+    good = ref.ref_encode(img, 19)
+    bad = []
+    b = bytearray(good)
+    # q19 header: byte0,q, tree1(2) tree2(2) data1(4) data2(4) tree_end(2) exw(2) res1_len(2) res3_len(2) res3_bit_len(2) ...
+    struct.pack_into("<H", b, 24, 65535)          # res3_bit_len
+    bad.append(bytes(b) + b"\0" * 200000)
+    b = bytearray(good); struct.pack_into("<H", b, 14, 65535); bad.append(bytes(b))   # tree_end
+    bad.append(good[:36])                                                               # truncated after the header
+    bad.append(good[:20])                                                               # truncated inside the header
+    b = bytearray(good); b[1] = 23; bad.append(bytes(b[:37]))                           # quality byte lies about the header size
+    b = bytearray(good); b[1] = 0; bad.append(bytes(b))                                 # q0
+    rgb, status = codec.decode(bad + [good])
+    assert (status[:-1] != 0).all(), status
+    assert status[-1] == 0 and np.array_equal(rgb[-1], ref.ref_decode(good))

@@ -22,7 +22,7 @@ def test_synth_device_matches_host(codec):
             assert np.array_equal(got[i], f(4242 + i)), (kind, i)
 
 
-@pytest.mark.parametrize("q", [20, 23, 19, 18, 17])
+@pytest.mark.parametrize("q", [20, 23, 19, 18, 17, 16, 9, 1])
 def test_colorspace(codec, ref, q):
     import torch
     imgs = _imgs()
@@ -45,7 +45,7 @@ def test_color_fast_path_exhaustive(codec):
     assert codec.color_check() == 0
 
 
-@pytest.mark.parametrize("q", [20, 17, 21])
+@pytest.mark.parametrize("q", [20, 17, 21, 16, 14, 10, 7, 5, 1])
 def test_pre_processing(codec, ref, q):
     import torch
     imgs = _imgs()
@@ -61,7 +61,7 @@ def test_pre_processing(codec, ref, q):
         assert bad.size == 0, (q, i, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
 
 
-@pytest.mark.parametrize("q", [20, 22, 18])
+@pytest.mark.parametrize("q", [20, 22, 18, 16, 14, 13, 8, 2])
 def test_frontend_vs_taps(codec, ref, q):
     import torch
     imgs = _imgs()
