@@ -100,6 +100,13 @@ static void prof_resolve(nhw_ctx *c)
 
 }  // namespace nhw
 
+static int env_int(const char *name, int dflt, int lo, int hi)
+{
+	const char *e = getenv(name);
+	const int v = e ? atoi(e) : dflt;
+	return v < lo ? lo : v > hi ? hi : v;
+}
+
 template <typename T>
 static bool dev_alloc0(T **p, size_t count)
 {
@@ -147,6 +154,21 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	}
 
 	c->stream = c->lanes[0];
+	{
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+		NhwTuning &t = c->tune;
+		t.lanes_device = env_int("NHW_LANES_DEVICE", 1, 1, NHW_LANES);
+		t.chroma_stream = c->tune.chroma_stream;
+		t.subs_encode = c->tune.subs_encode;
+		t.lanes_encode = c->tune.lanes_encode;
+		t.subs_decode = c->tune.subs_decode;
+		t.lanes_decode = c->tune.lanes_decode;
+		t.dsf_streams = env_int("NHW_DSF_STREAMS", 4, 1, 32);
+		while (32 % t.dsf_streams) t.dsf_streams--;
+		t.rows_grid_cap = sms * env_int("NHW_ROWS_CTAS_PER_SM", 24, 1, 64);
+	}
+	ok = ok && nhw::front_device_init(c) && nhw::encode_device_init(c) && nhw::decode_device_init(c);
 	// every workspace array is zero-filled once: guard bands and never-written borders must
 	// read as 0 (canonical oracle semantics)
 	ok = ok && dev_alloc0(&c->rgb, B * NHW_RGB_BYTES);
@@ -299,13 +321,6 @@ struct LanePlan {
 	int first[NHW_MAX_SUB + 1];   // image range of each sub-chunk inside the wave
 };
 
-static int env_int(const char *name, int dflt, int lo, int hi)
-{
-	const char *e = getenv(name);
-	const int v = e ? atoi(e) : dflt;
-	return v < lo ? lo : v > hi ? hi : v;
-}
-
 // Split the next `m` images (m <= max_batch) into sub-chunks.  Per-kernel profiling and the debug stop are
 // defined on one stream, so they run as one sub-chunk.
 static LanePlan plan_lanes(const nhw_ctx *c, int m, int want_subs, int want_streams)
@@ -424,7 +439,7 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
 	c->dbg_seen = c->dbg_stopped = 0;
 	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
 		// device-resident input: the kernels of one chunk already fill the GPU and share L2 better on one stream
-		const int dl = env_int("NHW_LANES_DEVICE", 1, 1, NHW_LANES);
+		const int dl = c->tune.lanes_device;
 		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, dl, dl);
 		step = p.count;
 		lanes_fork(c, p.streams);
@@ -432,7 +447,7 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
 			const int a = i0 + p.first[l], cnt = p.first[l + 1] - p.first[l];
 			if (cnt <= 0) continue;
 			nhw_ctx v = lane_view(c, l, l * p.slot);
-			v.chroma_side = (p.subs == 1 && !c->profile && !c->dbg_label[0] && env_int("NHW_CHROMA_STREAM", 1, 0, 1)) ? 1 : 0;
+			v.chroma_side = (p.subs == 1 && !c->profile && !c->dbg_label[0] && c->tune.chroma_stream) ? 1 : 0;
 			nhw::encode_chunk(&v, rgb_dev + (size_t)a * NHW_RGB_BYTES, cnt, quality, out_dev + (size_t)a * NHW_MAX_STREAM_BYTES,
 			                  len_dev ? len_dev + a : nullptr, status_dev ? status_dev + a : nullptr);
 			lane_done(c, v);
@@ -454,8 +469,8 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 	uint64_t pos = 0;
 	offsets[0] = 0;
 	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
-		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, env_int("NHW_SUBS_ENCODE", 16, 1, NHW_MAX_SUB),
-		                              env_int("NHW_LANES_ENCODE", 4, 1, NHW_LANES));
+		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, c->tune.subs_encode,
+		                              c->tune.lanes_encode);
 		step = p.count;
 		nhw_ctx v[NHW_MAX_SUB];
 		lanes_fork(c, p.streams);
@@ -509,8 +524,8 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
 	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
-		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, env_int("NHW_SUBS_DECODE", 8, 1, NHW_MAX_SUB),
-		                              env_int("NHW_LANES_DECODE", 4, 1, NHW_LANES));
+		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, c->tune.subs_decode,
+		                              c->tune.lanes_decode);
 		step = p.count;
 		nhw_ctx v[NHW_MAX_SUB];
 		lanes_fork(c, p.streams);

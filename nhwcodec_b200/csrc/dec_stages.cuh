@@ -161,11 +161,14 @@ NHW_HDN int dec_y_ll_overrides(const DecImg &im)
 	if (d->quality > 17) {
 		const uint8_t *r4 = im.blob + d->off_res4;
 		int count = 0;
-		for (int i = 0; i < d->res4_len; i++) {
+		for (int i = 0; i < d->res4_len && count < 128; i++) {   // (a well-formed list names 128 rows; more is garbage)
 			if (r4[i] == 128) { count++; continue; }
-			const int e = (count << 9) + (r4[i] > 128 ? r4[i] - 129 : r4[i] - 1);
-			for (int k = 0; k < 4; k++)
-				if (!(J[e + k] & 1)) J[e + k]++;
+			const int col = r4[i] > 128 ? r4[i] - 129 : r4[i] - 1;
+			if (col >= 0 && col <= 124) {
+				const int e = (count << 9) + col;
+				for (int k = 0; k < 4; k++)
+					if (!(J[e + k] & 1)) J[e + k]++;
+			}
 			if (r4[i] > 128) count++;
 		}
 	}

@@ -476,6 +476,17 @@ __global__ void kd_color(DecBatch b, uint8_t *rgb)
 
 namespace nhw {
 
+bool decode_device_init(nhw_ctx *c)
+{
+	static uint16_t lut[NHW_LUT_WORDS];   // (filled with the same values by every caller)
+	dec_build_lut(lut);
+	void *p = nullptr;
+	if (!check(cudaMemcpyToSymbol(g_dec_lut, lut, sizeof(lut)), "prefix-code table") || !check(cudaGetSymbolAddress(&p, g_dec_lut), "prefix-code table"))
+		return false;
+	c->dec_lut = static_cast<const uint16_t *>(p);
+	return true;
+}
+
 // from encode.cu (same inverse kernels, natural-orientation output)
 void idwt_rows_cols(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *tmp, int16_t *out, size_t slot, int N, int stride);
 
@@ -490,19 +501,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	b.uvcoef = c->y_aux2 + NHW_GUARD_S;
 	b.c_proc = c->c_proc + NHW_GUARD_S; b.c_jpeg = c->c_jpeg + NHW_GUARD_S; b.c_aux = c->c_aux + NHW_GUARD_S;
 	b.bytes = c->enc_bytes; b.yuv = c->dec_yuv;
-	{
-		static bool tables[64] = {false};
-		if (!tables[c->device & 63]) {
-			static uint16_t lut[NHW_LUT_WORDS];
-			dec_build_lut(lut);
-			cudaMemcpyToSymbolAsync(g_dec_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, c->stream);
-			cudaStreamSynchronize(c->stream);
-			tables[c->device & 63] = true;
-		}
-		void *p = nullptr;
-		cudaGetSymbolAddress(&p, g_dec_lut);
-		b.lut = static_cast<const uint16_t *>(p);
-	}
+	b.lut = c->dec_lut;
 	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT;
 
 	// coefficient planes start at zero: zero runs are skipped, not written (decoder/nhw_decoder.c:2029)
@@ -511,8 +510,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 
 	// ---- luma
 	{
-		const char *e = getenv("NHW_DSF_STREAMS");
-		const int spw = e ? atoi(e) : DSF_STREAMS;
+		const int spw = c->tune.dsf_streams;
 		NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + spw - 1) / spw, dim3(32, 4), 0, b, n, spw);
 	}
 	NHW_LAUNCH_L(c, "d_descan_y", kd_descan_y, dim3(512, n), 128, 0, b);

@@ -116,19 +116,6 @@ __global__ void __launch_bounds__(64) k_plane_rows(EncBatch b, int rows, int n2,
 	}
 }
 
-static int rows_grid_cap()
-{
-	static int cap = 0;
-	if (!cap) {
-		int dev = 0, sms = 148;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		const char *e = getenv("NHW_ROWS_CTAS_PER_SM");
-		cap = sms * (e ? atoi(e) : ROWS_CTAS_PER_SM);
-	}
-	return cap;
-}
-
 // ---- cell-group executors (enc_cells.cuh): one thread per group of 8 cells, 256 threads = whole rows of a CTA.
 // k_groups: f does its own loads and stores (stages that never read what they write).
 // k_groups_inplace: f only reads and returns the group's final values; the CTA synchronises, then stores, so a
@@ -207,13 +194,13 @@ void run_plane(nhw_ctx *c, const char *label, const EncBatch &b, int n, F f)
 template <typename F>
 void run_rows(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, F f)
 {
-	const int work = ((rows + 63) / 64) * n, cap = rows_grid_cap();
+	const int work = ((rows + 63) / 64) * n, cap = c->tune.rows_grid_cap;
 	NHW_LAUNCH_L(c, label, k_rows, work < cap ? work : cap, 64, 0, b, rows, n, f);
 }
 template <typename F>
 void run_plane_rows(nhw_ctx *c, const char *label, const EncBatch &b, int n, int rows, F f)
 {
-	const int work = ((rows + 63) / 64) * 2 * n, cap = rows_grid_cap();
+	const int work = ((rows + 63) / 64) * 2 * n, cap = c->tune.rows_grid_cap;
 	NHW_LAUNCH_L(c, label, k_plane_rows, work < cap ? work : cap, 64, 0, b, rows, 2 * n, f);
 }
 
@@ -266,32 +253,9 @@ __global__ void __launch_bounds__(256) k_e16b_classify(EncBatch b, int q)
 	y_e16b_classify_col_w(im, q, threadIdx.x, w1, w3, w5);
 }
 
-// ---- serial LL2 stages with the band staged in shared memory: one warp per image copies the
-// band (128 rows x 132 columns, the 4 extra columns are look-ahead), lane 0 runs the stage at
-// shared-memory latency, the warp writes the 128x128 band back.  ~34-48 KB per image lets
-// several images share an SM, which is what these latency-bound stages need.
+// the LL2 band staged in shared memory: 128 rows x 132 columns (4 columns of look-ahead)
 #define LL2_PS 132
 #define LL2_SMEM_BYTES (128 * LL2_PS * 2)
-template <typename F>
-__global__ void __launch_bounds__(32) k_ll2_staged(EncBatch b, F f)
-{
-	extern __shared__ __align__(16) int16_t sP[];
-	const EncImg im = make_img(b, blockIdx.x, 0);
-	const int lane = threadIdx.x;
-	for (int r = 0; r < 128; r++) {
-		const uint32_t *src = reinterpret_cast<const uint32_t *>(im.proc + r * YW);
-		uint32_t *dst = reinterpret_cast<uint32_t *>(sP + r * LL2_PS);
-		for (int c = lane; c < LL2_PS / 2; c += 32) dst[c] = src[c];
-	}
-	__syncwarp();
-	if (lane == 0) f(im, sP);
-	__syncwarp();
-	for (int r = 0; r < 128; r++) {
-		uint32_t *dst = reinterpret_cast<uint32_t *>(im.proc + r * YW);
-		const uint32_t *src = reinterpret_cast<const uint32_t *>(sP + r * LL2_PS);
-		for (int c = lane; c < 64; c += 32) dst[c] = src[c];
-	}
-}
 
 // LL2 part of offsetY_recons256 in its parallel form (enc_par.cuh): band in shared memory,
 // thread = LL2 row; tagging rows -> wavefront (skew 3) -> second-call tail.
@@ -510,15 +474,6 @@ __global__ void __launch_bounds__(128) k_ll2_code(EncBatch b, int q)
 		h->res_low = mode;
 		h->y_res_comp = 1 + tot[1];
 	}
-}
-
-template <typename F>
-void run_ll2_staged(nhw_ctx *c, const char *label, const EncBatch &b, int n, size_t smem, F f)
-{
-	static bool attr = false;
-	(void)attr;
-	cudaFuncSetAttribute(k_ll2_staged<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	NHW_LAUNCH_L(c, label, k_ll2_staged, n, 32, smem, b, f);
 }
 
 // ---- res1/res3/res5 side-channel lists: rows collected in parallel (count, CTA prefix, write),
@@ -1643,23 +1598,19 @@ __global__ void k_pack_streams(const uint8_t *__restrict__ slots, const uint32_t
 	for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) dst[k] = src[k];
 }
 
-void idwt_attrs()
-{
-	static bool done = false;
-	if (done) return;
-	cudaFuncSetAttribute(k_idwt_cols_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * 2);
-	cudaFuncSetAttribute(k_idwt_cols_t<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 33 * 2);
-	done = true;
-}
 
 }  // namespace
 
 namespace nhw {
 
-static void ll2_code_attr(nhw_ctx *)
+bool encode_device_init(nhw_ctx *c)
 {
-	static bool attr = false;
-	if (!attr) { cudaFuncSetAttribute(k_ll2_code, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_CODE_SMEM); attr = true; }
+	(void)c;
+	bool ok = check(cudaFuncSetAttribute(k_ll2_code, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_CODE_SMEM), "attr k_ll2_code");
+	ok = ok && check(cudaFuncSetAttribute(k_recons_ll2_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_SMEM_BYTES), "attr k_recons_ll2_wave");
+	ok = ok && check(cudaFuncSetAttribute(k_idwt_cols_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * 2), "attr k_idwt_cols_t");
+	ok = ok && check(cudaFuncSetAttribute(k_idwt_cols_t<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 33 * 2), "attr k_idwt_cols_t");
+	return ok;
 }
 
 EncBatch enc_batch_of(nhw_ctx *c)
@@ -1684,7 +1635,6 @@ EncBatch enc_batch_of(nhw_ctx *c)
 // luma inverse level-2 transform: jpeg region (256x256) -> proc region, natural orientation
 static void idwt_luma256(nhw_ctx *c, const EncBatch &b, int n)
 {
-	idwt_attrs();
 	NHW_LAUNCH(c, k_idwt_rows<256>, dim3(256 / 8, n), 256, 0, b.y_jpeg, b.y_aux, (size_t)NHW_Y_SLOT, (size_t)NHW_Y_SLOT, 512);
 	NHW_LAUNCH(c, k_idwt_cols_t<256>, dim3(256 / 32, n), 256, 256 * 33 * 2, b.y_aux, b.y_proc, (size_t)NHW_Y_SLOT, (size_t)NHW_Y_SLOT, 512);
 }
@@ -1692,7 +1642,6 @@ static void idwt_luma256(nhw_ctx *c, const EncBatch &b, int n)
 // generic form used by the decoder: N x N bands at row stride `stride`, planes `slot` apart
 void idwt_rows_cols(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *tmp, int16_t *out, size_t slot, int N, int stride)
 {
-	idwt_attrs();
 	if (N == 256) {
 		NHW_LAUNCH(c, k_idwt_rows<256>, dim3(256 / 8, n_planes), 256, 0, in, tmp, slot, slot, stride);
 		NHW_LAUNCH(c, k_idwt_cols_t<256>, dim3(256 / 32, n_planes), 256, 256 * 33 * 2, tmp, out, slot, slot, stride);
@@ -1704,7 +1653,6 @@ void idwt_rows_cols(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *tmp, i
 
 static void idwt_chroma128(nhw_ctx *c, const EncBatch &b, int n)
 {
-	idwt_attrs();
 	NHW_LAUNCH(c, k_idwt_rows<128>, dim3(128 / 8, 2 * n), 256, 0, b.c_jpeg, b.c_aux, (size_t)NHW_C_SLOT, (size_t)NHW_C_SLOT, 256);
 	NHW_LAUNCH(c, k_idwt_cols_t<128>, dim3(128 / 32, 2 * n), 256, 128 * 33 * 2, b.c_aux, b.c_proc, (size_t)NHW_C_SLOT, (size_t)NHW_C_SLOT, 256);
 }
@@ -1733,7 +1681,6 @@ static void encode_luma_lowq(nhw_ctx *c, const EncBatch &b, int n, int q, int ra
 	if (q <= 11) run_rows(c, "y_e7_kill", b, n, 128, [=] __device__(const EncImg &im, int r) { y_e7_kill_row(im, q, ratio, 128 + r); });
 	if (q < 13) run_image(c, "y_e8_smooth", b, n, [=] __device__(const EncImg &im, int) { y_e8_smooth_image(im, q); });
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
-	ll2_code_attr(c);
 	NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
 	if (q > 12) {   // second reconstruction
 		NHW_LAUNCH_L(c, "y_recons0_ll2", k_recons_ll2_wave, n, 128, LL2_SMEM_BYTES, b, q, 0);
@@ -1779,14 +1726,13 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	// of the scan buffer and of the header); on its own stream when the chunk runs alone on the GPU
 	// (forked here, next to the short kernels of the luma closed loop: 43.9 -> 43.5 ms; forked before the LL2 coder it
 	// competes with the latency-bound kernels and the step gets slower: 45.6 ms)
-	nhw_ctx side = *c;
 	nhw_ctx *cs = c;
-	if (c->chroma_side && c->chroma_stream) {
-		side.stream = c->chroma_stream;
-		side.launches = 0;
-		cs = &side;
-		cudaEventRecord(c->ev_chroma0, c->stream);
-		cudaStreamWaitEvent(side.stream, c->ev_chroma0, 0);
+	const cudaStream_t main_stream = c->stream;
+	const bool side = c->chroma_side && c->chroma_stream;
+	if (side) {   // the launch macros issue on c->stream: point it at the side stream for the length of the chroma chain
+		cudaEventRecord(c->ev_chroma0, main_stream);
+		cudaStreamWaitEvent(c->chroma_stream, c->ev_chroma0, 0);
+		c->stream = c->chroma_stream;
 	}
 	// U and V planes side by side (nhw_encoder.c:2255-2868)
 	const bool lowq = q <= 16;   // row / image forms of the stages whose cell-group forms are q17..q23 only
@@ -1827,9 +1773,9 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH_L(cs, "c_ll_quant", k_c_ll_quant, n, 64, 0, b, q);
 	NHW_LAUNCH_L(cs, "c_quant_scan", k_c_quant_scan, dim3(16, n), 256, 0, b, ratio);
 
-	if (cs != c) {
-		cudaEventRecord(c->ev_chroma1, side.stream);
-		c->launches += side.launches;
+	if (side) {
+		cudaEventRecord(c->ev_chroma1, c->chroma_stream);
+		c->stream = main_stream;
 	}
 
 	if (lowq) encode_luma_lowq(c, b, n, q, ratio);
@@ -1847,7 +1793,6 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	// ---- LL2 coding (nhw_encoder.c:623-757)
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
 	// LL2 -> bytes (wavefront) and the DPCM coder (step links + chain walk), see enc_ll_par.cuh
-	ll2_code_attr(c);
 	NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
 	// (the coder works on a shared-memory copy of the band: the plane still holds what the snapshot holds)
 
@@ -1865,10 +1810,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	// ---- level-1 thresholds, pattern tags, residual side channels (nhw_encoder.c:783-1887)
 	run_groups_inplace(c, "y_e14_e15_tags", b, n, 512, 6, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_e14_e15_cells(im.proc + r * YW, r, g, q, ratio, o); });
 	NHW_LAUNCH_L(c, "y_e16_residual", k_e16_residual, n, 256, 0, b, q);
-	if (getenv("NHW_E16B_ROWS"))
-		run_rows(c, "y_e16b_classify", b, n, 256, [=] __device__(const EncImg &im, int j) { int w1 = 0, w3 = 0, w5 = 0; y_e16b_classify_col(im, q, j, w1, w3, w5); });
-	else
-		NHW_LAUNCH_L(c, "y_e16b_classify", k_e16b_classify, n, 256, 0, b, q);
+	NHW_LAUNCH_L(c, "y_e16b_classify", k_e16b_classify, n, 256, 0, b, q);
 	if (q > 21) NHW_LAUNCH_L(c, "y_hq_e17", k_hq_e17, dim3(256, n), 256, 0, b);
 	NHW_LAUNCH_L(c, "y_e18_lists", k_e18_lists, n, 256, 0, b, q);
 	NHW_LAUNCH_L(c, "y_e18_tails", k_e18_tails, dim3(3, n), 32, 0, b, q);
@@ -1889,7 +1831,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 
 	}
 
-	if (cs != c) cudaStreamWaitEvent(c->stream, c->ev_chroma1, 0);   // the chroma chain joins here
+	if (side) cudaStreamWaitEvent(c->stream, c->ev_chroma1, 0);   // the chroma chain joins here
 	// ---- LL code tail, entropy stage, container (compress_pixel.c:878-1022, 53-469)
 	NHW_LAUNCH_L(c, "c_ll_code", k_c_ll_code, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "entropy_pack", k_entropy, n, SEG_THREADS, 262144 / 8, b);

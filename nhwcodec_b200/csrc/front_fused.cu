@@ -620,11 +620,6 @@ template <int N, typename InT, int THREADS>
 void launch_level(nhw_ctx *c, const char *label, int n_planes, const InT *in, size_t in_slot, int in_stride, int16_t *out,
                   size_t out_slot, int out_stride, int16_t *ll, size_t ll_slot)
 {
-	static bool attr = false;
-	if (!attr) {
-		cudaFuncSetAttribute(k_dwt_level<N, InT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, N * N * 2);
-		attr = true;
-	}
 	NHW_LAUNCH_L(c, label, (k_dwt_level<N, InT, THREADS>), n_planes, THREADS, N * N * 2, in, in_slot, in_stride, out, out_slot,
 	             out_stride, ll, ll_slot);
 }
@@ -635,28 +630,28 @@ namespace nhw {
 
 ColorParams color_params(int quality);
 
+bool front_device_init(nhw_ctx *c)
+{
+	bool ok = check(cudaFuncSetAttribute(k_front_luma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)), "attr k_front_luma");
+	ok = ok && check(cudaFuncSetAttribute(k_front_luma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem)), "attr k_front_luma<plane>");
+	ok = ok && check(cudaFuncSetAttribute(k_dwt_level<256, int16_t, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 * 2), "attr k_dwt_level");
+	ok = ok && check(cudaFuncSetAttribute(k_dwt_level<256, uint8_t, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 * 2), "attr k_dwt_level");
+	ok = ok && check(cudaFuncSetAttribute(k_dwt_level<128, int16_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 2), "attr k_dwt_level");
+	uint8_t cat[512];
+	uint16_t lut[PAIR_CATS * PAIR_CATS];
+	pair_build_tables(cat, lut);
+	ok = ok && check(cudaMemcpyToSymbol(g_pair_cat, cat, sizeof(cat)), "pair tables");
+	ok = ok && check(cudaMemcpyToSymbol(g_pair_lut, lut, sizeof(lut)), "pair tables");
+	(void)c;
+	return ok;
+}
+
 // The whole front end of n images: rgb -> luma coefficient planes (both levels) + `res256`,
 // chroma coefficient planes (both levels) + chroma `res256`.  uv_bytes: scratch, 2*65536 B / image.
 void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_proc, size_t ypstride, int16_t *y_ll1,
                  size_t ylstride, uint8_t *uv_bytes, int16_t *c_proc, size_t cpstride, int16_t *c_ll1, size_t clstride,
                  int16_t *kept, size_t kstride)
 {
-	static bool attr = false;
-	if (!attr) {
-		cudaFuncSetAttribute(k_front_luma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem));
-		cudaFuncSetAttribute(k_front_luma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem));
-		attr = true;
-	}
-	static bool tables[64] = {false};
-	if (!tables[c->device & 63]) {
-		static uint8_t cat[512];
-		static uint16_t lut[PAIR_CATS * PAIR_CATS];
-		pair_build_tables(cat, lut);
-		cudaMemcpyToSymbolAsync(g_pair_cat, cat, sizeof(cat), 0, cudaMemcpyHostToDevice, c->stream);
-		cudaMemcpyToSymbolAsync(g_pair_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, c->stream);
-		cudaStreamSynchronize(c->stream);
-		tables[c->device & 63] = true;
-	}
 	const ColorParams p = color_params(quality);
 	if (quality <= 16) {
 		// colour (integer form) -> luma plane + 4:2:0 bytes, the pre-sharpening state machine in place on the plane,

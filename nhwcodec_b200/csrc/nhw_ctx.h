@@ -10,9 +10,21 @@
 
 struct DecDesc;
 
+// scheduling knobs, read from the environment ONCE in nhw_create (never on the call path)
+struct NhwTuning {
+	int lanes_device;      // NHW_LANES_DEVICE   sub-chunks of a device-resident encode call (1)
+	int chroma_stream;     // NHW_CHROMA_STREAM  chroma chain on a side stream (1)
+	int subs_encode, lanes_encode;   // NHW_SUBS_ENCODE (16), NHW_LANES_ENCODE (4): host-buffer encode waves
+	int subs_decode, lanes_decode;   // NHW_SUBS_DECODE (8), NHW_LANES_DECODE (4)
+	int dsf_streams;       // NHW_DSF_STREAMS    streams per warp in the decoder's serial front (4)
+	int rows_grid_cap;     // SM count x NHW_ROWS_CTAS_PER_SM (24): grid cap of the "thread = row" kernels
+};
+
 struct nhw_ctx {
 	int device;
 	int max_batch;
+	NhwTuning tune;
+	const uint16_t *dec_lut;    // the decoder's prefix-code table in this device's memory (decode.cu)
 	cudaStream_t stream;        // the stream kernels are issued on (lanes[0] for the context itself)
 	// A batch is cut into up to NHW_LANES sub-chunks that run side by side, each on its own stream and on its
 	// own slice of every workspace array (api.cu: lane_view): the many latency-bound stages of one sub-chunk
@@ -91,6 +103,13 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 
 // synth.cu
 void synth(nhw_ctx *c, uint8_t *rgb, int n, uint32_t seed0, int kind, const int16_t *sin_lut);
+
+// per-device set-up, called by nhw_create with the device current: opt-in to > 48 KB of dynamic shared memory for the
+// kernels that need it and upload of the constant tables.  Both are per-device state in CUDA; nothing here is
+// guarded by process-wide flags, so contexts on different GPUs (and from different threads) are independent.
+bool front_device_init(nhw_ctx *c);
+bool encode_device_init(nhw_ctx *c);
+bool decode_device_init(nhw_ctx *c);
 
 // api.cu: per-kernel timing with CUDA events recorded on c->stream around each launch
 bool dbg_skip(nhw_ctx *c, const char *label);

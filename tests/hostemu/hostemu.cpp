@@ -534,7 +534,7 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	inv_rows(im.jpeg, 512, im.proc, 512, 512, 256, false);      // wavelet_synthesis2: first half
 	for (int k = dec_hq_addback_count(im) - 1; k >= 0; k--) {
 		int pos, amount;
-		if (dec_hq_addback(im, k, pos, amount)) im.proc[pos] = (int16_t)(im.proc[pos] + amount);
+		if (dec_hq_addback(im, k, pos, amount) && pos >= 0 && pos < 512 * 512) im.proc[pos] = (int16_t)(im.proc[pos] + amount);
 	}
 	transpose_sq(im.proc, im.jpeg, 512, 512);
 	dec_y_smooth_flags_image(im);

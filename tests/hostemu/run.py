@@ -60,7 +60,9 @@ def host_decode(stream):
     L.he_decode.argtypes = [ctypes.c_char_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p]
     rgb = np.zeros(786432, dtype=np.uint8)
     yuv = np.zeros(786432, dtype=np.uint8)
-    rc = L.he_decode(stream, len(stream), rgb.ctypes.data, yuv.ctypes.data)
+    # like the device copy of a chunk (api.cu), the stream is followed by 64 defined bytes: the bit reader looks a few
+    # words past the last code
+    rc = L.he_decode(bytes(stream) + b"\0" * 64, len(stream), rgb.ctypes.data, yuv.ctypes.data)
     return rc, rgb, yuv
 
 

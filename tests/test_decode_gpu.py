@@ -77,8 +77,8 @@ def test_decode_hostile_headers(codec, ref):
     bad = []
     b = bytearray(good)
     # q19 header: byte0,q, tree1(2) tree2(2) data1(4) data2(4) tree_end(2) exw(2) res1_len(2) res3_len(2) res3_bit_len(2) ...
-    struct.pack_into("<H", b, 24, 65535)          # res3_bit_len
-    bad.append(bytes(b) + b"\0" * 200000)
+    struct.pack_into("<H", b, 22, 65535)          # res3_bit_len
+    bad.append(bytes(b) + b"\0" * 300000)
     b = bytearray(good); struct.pack_into("<H", b, 14, 65535); bad.append(bytes(b))   # tree_end
     bad.append(good[:36])                                                               # truncated after the header
     bad.append(good[:20])                                                               # truncated inside the header
