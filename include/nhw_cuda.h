@@ -74,6 +74,16 @@ int nhw_encode_batch_device(nhw_ctx *ctx, const uint8_t *rgb_dev, int n, int qua
 int nhw_decode_batch(nhw_ctx *ctx, const uint8_t *in, const uint64_t *offsets, int n,
                      uint8_t *rgb, int32_t *status);
 
+/* Same with every buffer resident in device memory (no host copies, no host synchronisation before the kernels:
+ * the .nhw headers are walked on the device).  Stream i occupies in_dev[i * stride, i * stride + len_dev[i]) -- with
+ * stride = NHW_MAX_STREAM_BYTES this is exactly what nhw_encode_batch_device leaves behind.  64 bytes past the end of
+ * the last stream must be readable (the bit reader looks ahead).  rgb_dev: n * NHW_PIX_BYTES.  status_dev: n entries. */
+int nhw_decode_batch_device(nhw_ctx *ctx, const uint8_t *in_dev, size_t stride, const uint32_t *len_dev, int n,
+                            uint8_t *rgb_dev, int32_t *status_dev);
+/* ... and for streams packed back to back: stream i is in_dev[offs_dev[i], offs_dev[i + 1]) (n + 1 offsets). */
+int nhw_decode_batch_packed_device(nhw_ctx *ctx, const uint8_t *in_dev, const uint64_t *offs_dev, int n,
+                                   uint8_t *rgb_dev, int32_t *status_dev);
+
 /* Same, but stops before the colour conversion: yuv receives, per image, the three 512x512
  * byte planes Y, U, V (786432 bytes) that decode_image leaves in im_bufferY/U/V for
  * write_image_bmp (decoder/nhw_decoder.c:877-891,1137-1181).  quality (n entries, may be NULL)

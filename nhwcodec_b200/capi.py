@@ -51,6 +51,10 @@ def load_library():
     L.nhw_encode_batch_device.restype = i32
     L.nhw_decode_batch.argtypes = [vp, vp, vp, i32, vp, vp]
     L.nhw_decode_batch.restype = i32
+    L.nhw_decode_batch_device.argtypes = [vp, vp, ctypes.c_size_t, vp, i32, vp, vp]
+    L.nhw_decode_batch_device.restype = i32
+    L.nhw_decode_batch_packed_device.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.nhw_decode_batch_packed_device.restype = i32
     L.nhw_decode_batch_planes.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.nhw_decode_batch_planes.restype = i32
     L.nhw_stage_frontend_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
@@ -192,6 +196,18 @@ class Codec:
         rc = self.lib.nhw_encode_batch_device(self.h, _ptr(rgb_t), n, int(quality), _ptr(out_t), _ptr(len_t),
                                               _ptr(status_t))
         self._check(rc, "nhw_encode_batch_device")
+
+    def decode_device(self, in_t, len_t, rgb_t, status_t, stride=MAX_STREAM_BYTES):
+        """streams in device memory, one per `stride`-byte slot (what encode_device writes) -> pixels in device memory"""
+        n = rgb_t.shape[0]
+        rc = self.lib.nhw_decode_batch_device(self.h, _ptr(in_t), int(stride), _ptr(len_t), n, _ptr(rgb_t), _ptr(status_t))
+        self._check(rc, "nhw_decode_batch_device")
+
+    def decode_packed_device(self, in_t, offs_t, rgb_t, status_t):
+        """streams packed back to back in device memory (offs_t: n + 1 uint64/int64 offsets; 64 readable bytes must follow)"""
+        n = rgb_t.shape[0]
+        rc = self.lib.nhw_decode_batch_packed_device(self.h, _ptr(in_t), _ptr(offs_t), n, _ptr(rgb_t), _ptr(status_t))
+        self._check(rc, "nhw_decode_batch_packed_device")
 
     def stage_frontend(self, rgb_t, quality, y_proc=None, y_ll1=None, c_proc=None, c_ll1=None):
         n = rgb_t.shape[0]

@@ -537,13 +537,14 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 			DecDesc *desc = static_cast<DecDesc *>(w.dec_desc_host);
 			const uint64_t base = offsets[a], total = offsets[a + cnt] - base;
 			if (total + 64 > (uint64_t)p.slot * NHW_MAX_STREAM_BYTES) { nhw::set_error("input chunk too large"); return NHW_ERR_ARG; }
-			bool any_lowq = false;   // q <= 16 streams take one extra (row-ordered) kernel
+			bool any_lowq = false, any_hq = false;   // q <= 16 and q >= 22 streams each take one extra kernel
 			for (int i = 0; i < cnt; i++) {
 				const uint64_t o = offsets[a + i] - base, len = offsets[a + i + 1] - offsets[a + i];
 				w.offs_host[i] = o;
 				w.status_host[i] = nhw_parse_header(in + base + o, (size_t)len, &desc[i]);
 				if (quality) quality[a + i] = desc[i].quality;
 				any_lowq |= w.status_host[i] == 0 && desc[i].quality <= 16;
+				any_hq |= w.status_host[i] == 0 && desc[i].quality >= 22;
 			}
 			bool ok = check(cudaMemcpyAsync(w.pack_dev, in + base, total, cudaMemcpyHostToDevice, w.stream), "H2D streams");
 			// the bit reader may look a few words past the last code: keep that tail defined
@@ -552,7 +553,7 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 			ok = ok && check(cudaMemcpyAsync(w.offs_dev, w.offs_host, (size_t)cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, w.stream), "H2D offs");
 			ok = ok && check(cudaMemcpyAsync(w.status_dev, w.status_host, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, w.stream), "H2D status");
 			if (!ok) return NHW_ERR_CUDA;
-			nhw::decode_chunk(&w, w.pack_dev, w.offs_dev, static_cast<const DecDesc *>(w.dec_desc_dev), w.status_dev, cnt, w.rgb, any_lowq);
+			nhw::decode_chunk(&w, w.pack_dev, w.offs_dev, static_cast<const DecDesc *>(w.dec_desc_dev), w.status_dev, cnt, w.rgb, any_lowq, any_hq, yuv != nullptr);
 			if (rgb) cudaMemcpyAsync(rgb + (size_t)a * NHW_RGB_BYTES, w.rgb, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);
 			if (yuv) cudaMemcpyAsync(yuv + (size_t)a * NHW_RGB_BYTES, w.dec_yuv, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);
 			cudaMemcpyAsync(w.status_host, w.status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, w.stream);
@@ -566,6 +567,35 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 		}
 	}
 	return NHW_OK;
+}
+
+static int decode_device_impl(nhw_ctx *c, const uint8_t *in_dev, size_t stride, const uint32_t *len_dev, const uint64_t *offs_dev,
+                              int n, uint8_t *rgb_dev, int32_t *status_dev)
+{
+	if (!c || !in_dev || !rgb_dev || n <= 0 || (!len_dev && !offs_dev)) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	c->dbg_seen = c->dbg_stopped = 0;
+	for (int i0 = 0; i0 < n; i0 += c->max_batch) {
+		const int m = n - i0 < c->max_batch ? n - i0 : c->max_batch;
+		nhw::decode_chunk_device(c, offs_dev ? in_dev : in_dev + (size_t)i0 * stride, stride, len_dev ? len_dev + i0 : nullptr,
+		                         offs_dev ? offs_dev + i0 : nullptr, m, rgb_dev + (size_t)i0 * NHW_RGB_BYTES,
+		                         status_dev ? status_dev + i0 : nullptr);
+	}
+	return finish(c, "nhw_decode_batch_device");
+}
+
+int nhw_decode_batch_device(nhw_ctx *c, const uint8_t *in_dev, size_t stride, const uint32_t *len_dev, int n, uint8_t *rgb_dev,
+                            int32_t *status_dev)
+{
+	if (!len_dev || stride == 0) return NHW_ERR_ARG;
+	return decode_device_impl(c, in_dev, stride, len_dev, nullptr, n, rgb_dev, status_dev);
+}
+
+int nhw_decode_batch_packed_device(nhw_ctx *c, const uint8_t *in_dev, const uint64_t *offs_dev, int n, uint8_t *rgb_dev,
+                                   int32_t *status_dev)
+{
+	if (!offs_dev) return NHW_ERR_ARG;
+	return decode_device_impl(c, in_dev, 0, nullptr, offs_dev, n, rgb_dev, status_dev);
 }
 
 int nhw_decode_batch(nhw_ctx *c, const uint8_t *in, const uint64_t *offsets, int n, uint8_t *rgb, int32_t *status)

@@ -1,6 +1,7 @@
 // dec_parse.h -- host-side header walk of one .nhw stream (decoder/nhw_decoder.c:1494-1661,
 // SURVEY.md Appendix A): fills the per-image descriptor the decode kernels work from.
-// Plain C++ (no CUDA), shared by api.cu and the host test harness.
+// Host/device: the host API walks headers on the host (api.cu), the device-resident API in a kernel (decode.cu:
+// kd_parse_headers); the host test harness compiles it with g++.
 //
 // The stream is untrusted: every length the device code later uses as a loop bound or an index
 // range is validated here against the capacity of the decode workspace (decode.cu: DOFF_*), and no
@@ -17,9 +18,9 @@
 #define NHW_DEC_LIST_ENTRIES 65536
 #define NHW_DEC_BOOK_BYTES 1000          // flat codebook bytes dec_build_book expands (its scratch is 1024)
 
-static inline int nhw_parse_header(const uint8_t *p, size_t len, DecDesc *d)
+NHW_HDN int nhw_parse_header(const uint8_t *p, size_t len, DecDesc *d)
 {
-	memset(d, 0, sizeof *d);
+	*d = DecDesc{};
 	if (len < 2) return -7;
 	size_t pos = 0;
 	bool trunc = false;

@@ -264,15 +264,16 @@ NHW_HDN void dec_y_edge_flags_image(const DecImg &im)
 }
 
 // ---- D14: conditional 5-tap smoothing at the flagged positions, list order (nhw_decoder.c:848-867)
-NHW_HDN void dec_y_smooth_flags_image(const DecImg &im)
+NHW_HDN void dec_y_smooth_flags_plane(const DecImg &im, int16_t *J /* the half-synthesised plane, transposed */)
 {
-	int16_t *J = im.jpeg;
 	for (int i = 0; i < im.list_len[9]; i++) {
 		const int s = ((im.flags[i] >> 8) << 10) + (im.flags[i] & 255);
 		const int res = dec_lap8(J, s, YW);
 		if (nhw_iabs(res) < 116) J[s] = (int16_t)(((J[s] << 2) + J[s - 1] + J[s + 1] + J[s - YW] + J[s + YW] + 4) >> 3);
 	}
 }
+
+NHW_HDN void dec_y_smooth_flags_image(const DecImg &im) { dec_y_smooth_flags_plane(im, im.jpeg); }
 
 NHW_HD uint8_t dec_clip8(int v) { return (uint8_t)((v >> 8) != 0 ? (v < 0 ? 0 : 255) : v); }
 

@@ -10,6 +10,7 @@
 #include "nhw_ctx.h"
 #include "nhw_dev.cuh"
 #include "dec_par.cuh"
+#include "dec_parse.h"
 #include "../../include/nhw_cuda.h"
 
 namespace {
@@ -340,6 +341,8 @@ __global__ void __launch_bounds__(256) kd_addbacks(DecBatch b)
 }
 
 // ---- q22/q23 corrections between the two halves of the level-1 synthesis (dec_hq_addback)
+// The positions index the half-synthesised plane row-major (row = band row k, column = output sample j); the plane
+// they are applied to is kd_inv_rows_t's output, which is that plane transposed.
 __global__ void __launch_bounds__(256) kd_hq_addbacks(DecBatch b)
 {
 	if (b.status[blockIdx.x] != 0) return;
@@ -347,7 +350,52 @@ __global__ void __launch_bounds__(256) kd_hq_addbacks(DecBatch b)
 	const int n = dec_hq_addback_count(im);
 	for (int k = threadIdx.x; k < n; k += 256) {
 		int pos, amount;
-		if (dec_hq_addback(im, k, pos, amount) && pos >= 0 && pos < 512 * 512) atomic_add_s16(im.proc + pos, amount);
+		if (dec_hq_addback(im, k, pos, amount) && pos >= 0 && pos < 512 * 512) atomic_add_s16(im.aux + ((pos & 511) << 9) + (pos >> 9), amount);
+	}
+}
+
+// ---- D13: first half of the level-1 luma synthesis (wavelet_synthesis2, decoder/wavelet_filterbank.c:237-295) with both
+// of its transposes folded in.  Band row k of the reference's transposed plane is: low = column k of the reconstructed
+// LL1 (k < 256; natural orientation in y_proc) or the band cells themselves (k >= 256), high = the band cells right of
+// it (y_jpeg).  upfilter53I + upfilter53III along the row give 512 samples, which the reference then transposes: the
+// output goes out transposed, O[j][k].  A CTA takes 32 band rows: the LL1 columns come in through a transposing
+// shared-memory tile (64-byte row segments), the results leave through another one (64-byte column segments).
+#define IRT_ROWS 32
+#define IRT_LS 258      // row strides of the two tiles, in int16: both are 1 (mod 32) in 32-bit words, so the transposing
+#define IRT_OS 514      // accesses (8 rows apart per lane group) fall into distinct banks
+#define IRT_SMEM ((IRT_ROWS * IRT_LS + IRT_ROWS * IRT_OS) * 2)
+__global__ void __launch_bounds__(256) kd_inv_rows_t(DecBatch b)
+{
+	extern __shared__ __align__(16) int16_t irt[];
+	int16_t *tl = irt, *to = irt + IRT_ROWS * IRT_LS;
+	const int img = blockIdx.y, k0 = blockIdx.x * IRT_ROWS, tid = threadIdx.x;
+	if (b.status[img] != 0) return;
+	const int16_t *P = b.y_proc + (size_t)img * NHW_Y_SLOT, *J = b.y_jpeg + (size_t)img * NHW_Y_SLOT;
+	int16_t *O = b.y_aux + (size_t)img * NHW_Y_SLOT;
+	if (k0 < 256) {
+		for (int idx = tid; idx < 256 * (IRT_ROWS / 8); idx += 256) {
+			const int t = idx / (IRT_ROWS / 8), c = idx % (IRT_ROWS / 8);
+			int v[8];
+			ld8(P + t * YW + k0 + 8 * c, v);
+#pragma unroll
+			for (int i = 0; i < 8; i++) tl[(8 * c + i) * IRT_LS + t] = (int16_t)v[i];
+		}
+		__syncthreads();
+	}
+	for (int kk = 0; kk < IRT_ROWS; kk++) {
+		const int16_t *row = J + (k0 + kk) * YW;
+		const int16_t *low = k0 < 256 ? tl + kk * IRT_LS : row;
+		int ev, od;
+		inverse_pair([&](int t) { return (int)low[t]; }, [&](int t) { return (int)row[256 + t]; }, tid, 256, false, ev, od);
+		*reinterpret_cast<uint32_t *>(to + kk * IRT_OS + 2 * tid) = (uint32_t)(uint16_t)ev | ((uint32_t)(uint16_t)od << 16);
+	}
+	__syncthreads();
+	for (int item = tid; item < 512 * (IRT_ROWS / 8); item += 256) {
+		const int j = item / (IRT_ROWS / 8), c = item % (IRT_ROWS / 8);
+		int v[8];
+#pragma unroll
+		for (int i = 0; i < 8; i++) v[i] = to[(8 * c + i) * IRT_OS + j];
+		st8(O + j * YW + k0 + 8 * c, v);
 	}
 }
 
@@ -407,33 +455,6 @@ __global__ void __launch_bounds__(256) kd_edge_compact(DecBatch b)
 	}
 }
 
-// ---- D16: 2x chroma upsample (clip fused), one thread per chroma cell
-__global__ void __launch_bounds__(256) kd_upsample_uv(DecBatch b)
-{
-	const int img = blockIdx.y >> 1, v = blockIdx.y & 1;
-	if (b.status[img] != 0) return;
-	const DecImg im = make_dec(b, img, v);
-	dec_c_upsample_cell(im.cproc, im.yuv + (size_t)(1 + v) * 262144, blockIdx.x, threadIdx.x);
-}
-
-// ---- inverse filter passes (upfilter53I + III / VI, decoder/filters.c:143-194)
-// rows: every row k of the band plane -> 2M outputs, optionally normalised
-template <int M, bool NORM>
-__global__ void __launch_bounds__(256) kd_inv_rows(const int16_t *in, int16_t *out, size_t in_slot, size_t out_slot, int stride)
-{
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int k = blockIdx.x * 8 + warp;
-	const int16_t *src = in + (size_t)blockIdx.y * in_slot + k * stride;
-	int16_t *dst = out + (size_t)blockIdx.y * out_slot + k * stride;
-	auto l = [&](int t) { return (int)src[t]; };
-	auto h = [&](int t) { return (int)src[M + t]; };
-	for (int t = lane; t < M; t += 32) {
-		int ev, od;
-		inverse_pair(l, h, t, M, NORM, ev, od);
-		*reinterpret_cast<uint32_t *>(dst + 2 * t) = (uint32_t)(uint16_t)ev | ((uint32_t)(uint16_t)od << 16);
-	}
-}
-
 // square transpose of the top-left N x N cells of a plane into another plane (32x32 tiles)
 __global__ void __launch_bounds__(256) kd_transpose(const int16_t *in, int16_t *out, size_t in_slot, size_t out_slot, int stride)
 {
@@ -453,23 +474,90 @@ __global__ void kd_zero(int16_t *p, size_t slot, size_t count16)   // count16 = 
 	if (i < count16) reinterpret_cast<uint4 *>(p + (size_t)blockIdx.y * slot)[i] = make_uint4(0, 0, 0, 0);
 }
 
-__global__ void kd_clip_y(DecBatch b)
+// ---- back end: second half of the level-1 luma synthesis + clip, chroma clip + 2x upsample, YCbCr -> RGB, in one pass
+// from the int16 planes to the BMP pixel bytes (the 6 B/pixel unit of SURVEY.md section 8(d): 786432 B of int16
+// coefficients in, 786432 B of pixels out per image).  Everything here is local to an output row: row y of the luma
+// plane comes from row y of the band plane (upfilter53I + upfilter53VI, decoder/filters.c:143-194), its chroma from
+// chroma rows y/2 and y/2 + 1 (decoder/nhw_decoder.c:1137-1181).  A CTA takes BE_ROWS output rows of one image: the
+// band rows and the clipped chroma rows are staged in shared memory with 16-byte loads, a thread computes two
+// neighbouring pixels of every row, the pixels leave through shared memory as one contiguous 16-byte-per-thread copy.
+#define BE_ROWS 16
+template <bool WRITE_YUV>
+__global__ void __launch_bounds__(256) kd_backend(DecBatch b, uint8_t *__restrict__ rgb)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b.status[blockIdx.y] != 0) return;
-	const int16_t *P = b.y_proc + (size_t)blockIdx.y * NHW_Y_SLOT;
-	b.yuv[(size_t)blockIdx.y * 786432 + i] = dec_clip8(P[i]);
+	__shared__ __align__(16) int16_t sy[BE_ROWS][512];
+	__shared__ __align__(16) uint8_t sc[2][BE_ROWS / 2 + 1][256];
+	__shared__ __align__(16) uint8_t so[BE_ROWS * 1536];
+	const int img = blockIdx.y, y0 = blockIdx.x * BE_ROWS, t = threadIdx.x;
+	uint4 *dst = reinterpret_cast<uint4 *>(rgb + (size_t)img * 786432 + (size_t)y0 * 1536);
+	if (b.status[img] != 0) {   // a refused stream decodes to black
+		for (int k = t; k < BE_ROWS * 96; k += 256) dst[k] = make_uint4(0, 0, 0, 0);
+		return;
+	}
+	const int16_t *J = b.y_aux + (size_t)img * NHW_Y_SLOT + y0 * YW;   // kd_inv_rows_t's output, after the flag smoothing
+	for (int k = t; k < BE_ROWS * 64; k += 256) reinterpret_cast<uint4 *>(&sy[0][0])[k] = reinterpret_cast<const uint4 *>(J)[k];
+	const int r0 = y0 >> 1;
+	for (int k = t; k < 2 * (BE_ROWS / 2 + 1) * 32; k += 256) {
+		const int v = k / ((BE_ROWS / 2 + 1) * 32), rem = k % ((BE_ROWS / 2 + 1) * 32), rr = rem >> 5, c8 = (rem & 31) * 8;
+		const int r = r0 + rr < 256 ? r0 + rr : 255;
+		const int16_t *P = b.c_proc + ((size_t)img * 2 + v) * NHW_C_SLOT + r * CW + c8;
+		int x[8];
+		ld8(P, x);
+		uint2 o;
+		o.x = (uint32_t)dec_clip8(x[0]) | ((uint32_t)dec_clip8(x[1]) << 8) | ((uint32_t)dec_clip8(x[2]) << 16) | ((uint32_t)dec_clip8(x[3]) << 24);
+		o.y = (uint32_t)dec_clip8(x[4]) | ((uint32_t)dec_clip8(x[5]) << 8) | ((uint32_t)dec_clip8(x[6]) << 16) | ((uint32_t)dec_clip8(x[7]) << 24);
+		*reinterpret_cast<uint2 *>(&sc[v][rr][c8]) = o;
+	}
+	__syncthreads();
+	const DecColor col = dec_color_of(b.desc[img].quality);
+	uint8_t *yuv = WRITE_YUV ? b.yuv + (size_t)img * 786432 : nullptr;
+	const int c1 = t < 255 ? t + 1 : 255;
+#pragma unroll 2
+	for (int rr = 0; rr < BE_ROWS; rr++) {
+		const int16_t *row = sy[rr];
+		int ev, od;
+		inverse_pair([&](int k) { return (int)row[k]; }, [&](int k) { return (int)row[256 + k]; }, t, 256, true, ev, od);
+		const int Y0 = dec_clip8(ev), Y1 = dec_clip8(od);
+		// chroma of pixels (2t, 2t+1) of output row y: dec_c_upsample_cell's rule on the clipped samples
+		const int y = y0 + rr, cr = (y >> 1) - r0;
+		int uvs[2][2];
+#pragma unroll
+		for (int v = 0; v < 2; v++) {
+			int a0 = sc[v][cr][t], a1 = sc[v][cr][c1];
+			if ((y & 1) && (y >> 1) < 255) {
+				a0 = (a0 + sc[v][cr + 1][t] + 1) >> 1;
+				a1 = (a1 + sc[v][cr + 1][c1] + 1) >> 1;
+			}
+			uvs[v][0] = a0;
+			uvs[v][1] = t < 255 ? (a0 + a1 + 1) >> 1 : a0;
+		}
+		uint8_t px[6];
+		dec_ycc_to_rgb(Y0, uvs[0][0], uvs[1][0], col, px);
+		dec_ycc_to_rgb(Y1, uvs[0][1], uvs[1][1], col, px + 3);
+		uint16_t *o = reinterpret_cast<uint16_t *>(so + rr * 1536 + 6 * t);
+		o[0] = (uint16_t)(px[0] | (px[1] << 8));
+		o[1] = (uint16_t)(px[2] | (px[3] << 8));
+		o[2] = (uint16_t)(px[4] | (px[5] << 8));
+		if (WRITE_YUV) {
+			*reinterpret_cast<uint16_t *>(yuv + y * 512 + 2 * t) = (uint16_t)(Y0 | (Y1 << 8));
+			*reinterpret_cast<uint16_t *>(yuv + 262144 + y * 512 + 2 * t) = (uint16_t)(uvs[0][0] | (uvs[0][1] << 8));
+			*reinterpret_cast<uint16_t *>(yuv + 524288 + y * 512 + 2 * t) = (uint16_t)(uvs[1][0] | (uvs[1][1] << 8));
+		}
+	}
+	__syncthreads();
+	for (int k = t; k < BE_ROWS * 96; k += 256) dst[k] = reinterpret_cast<const uint4 *>(so)[k];
 }
 
-__global__ void kd_color(DecBatch b, uint8_t *rgb)
+// ---- device-resident streams: header walk on the device (dec_parse.h), one thread per stream
+__global__ void kd_parse_headers(const uint8_t *in, size_t stride, const uint32_t *len, const uint64_t *offs, int n, DecDesc *desc,
+                                 uint64_t *off_out, int32_t *status)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	uint8_t *o = rgb + (size_t)blockIdx.y * 786432 + 3 * (size_t)i;
-	if (b.status[blockIdx.y] != 0) { o[0] = o[1] = o[2] = 0; return; }
-	const int quality = b.desc[blockIdx.y].quality;   // each stream carries its own quality byte
-	const DecColor col = dec_color_of(quality);
-	const uint8_t *yuv = b.yuv + (size_t)blockIdx.y * 786432;
-	dec_ycc_to_rgb(yuv[i], yuv[262144 + i], yuv[524288 + i], col, o);
+	if (i >= n) return;
+	const uint64_t o = offs ? offs[i] : (uint64_t)i * stride;
+	const uint64_t l = offs ? offs[i + 1] - offs[i] : (uint64_t)len[i];
+	off_out[i] = o;
+	status[i] = nhw_parse_header(in + o, (size_t)l, desc + i);
 }
 
 }  // namespace
@@ -484,7 +572,7 @@ bool decode_device_init(nhw_ctx *c)
 	if (!check(cudaMemcpyToSymbol(g_dec_lut, lut, sizeof(lut)), "prefix-code table") || !check(cudaGetSymbolAddress(&p, g_dec_lut), "prefix-code table"))
 		return false;
 	c->dec_lut = static_cast<const uint16_t *>(p);
-	return true;
+	return check(cudaFuncSetAttribute(kd_inv_rows_t, cudaFuncAttributeMaxDynamicSharedMemorySize, IRT_SMEM), "attr kd_inv_rows_t");
 }
 
 // from encode.cu (same inverse kernels, natural-orientation output)
@@ -493,7 +581,7 @@ void idwt_rows_cols(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *tmp, i
 // Decode n <= max_batch streams.  blobs/offs/desc/status are device arrays for this chunk; rgb_dev
 // receives n x 786432 bytes.  All work is queued on c->stream.
 void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const DecDesc *desc, int32_t *status, int n,
-                  uint8_t *rgb_dev, bool any_lowq)
+                  uint8_t *rgb_dev, bool any_lowq, bool any_hq, bool want_yuv)
 {
 	DecBatch b;
 	b.blobs = blobs; b.blob_off = offs; b.desc = desc; b.status = status;
@@ -522,13 +610,10 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH_L(c, "d_addbacks", kd_addbacks, n, 256, 0, b);
 	d_wavefront(c, "d_edge_flags", b, n, 1, dwf_edge_geom(), [=] __device__(const DecImg &im, int r, int p) { return dwf_edge_cell(im.proc, r, p); });
 	NHW_LAUNCH_L(c, "d_edge_compact", kd_edge_compact, n, 256, 0, b);
-	NHW_LAUNCH(c, kd_transpose, dim3(8, 8, n), 256, 0, b.y_proc, b.y_jpeg, YS, YS, 512);
-	NHW_LAUNCH_L(c, "d_inv_rows512", (kd_inv_rows<256, false>), dim3(512 / 8, n), 256, 0, b.y_jpeg, b.y_proc, YS, YS, 512);
-	NHW_LAUNCH_L(c, "d_hq_addbacks", kd_hq_addbacks, n, 256, 0, b);   // no-op below q22
-	NHW_LAUNCH(c, kd_transpose, dim3(16, 16, n), 256, 0, b.y_proc, b.y_jpeg, YS, YS, 512);
-	d_image(c, "d_smooth_flags", b, n, [=] __device__(const DecImg &im, int) { dec_y_smooth_flags_image(im); });
-	NHW_LAUNCH_L(c, "d_inv_rows512n", (kd_inv_rows<256, true>), dim3(512 / 8, n), 256, 0, b.y_jpeg, b.y_proc, YS, YS, 512);
-	NHW_LAUNCH(c, kd_clip_y, dim3(262144 / 256, n), 256, 0, b);
+	NHW_LAUNCH_L(c, "d_inv_rows_t", kd_inv_rows_t, dim3(512 / IRT_ROWS, n), 256, IRT_SMEM, b);   // -> y_aux
+	if (any_hq) NHW_LAUNCH_L(c, "d_hq_addbacks", kd_hq_addbacks, n, 256, 0, b);   // q22 / q23 streams only
+	d_image(c, "d_smooth_flags", b, n, [=] __device__(const DecImg &im, int) { dec_y_smooth_flags_plane(im, im.aux); });
+	// (the second half of the synthesis and the clip are part of the back-end kernel below)
 
 	// ---- chroma
 	NHW_LAUNCH_L(c, "d_descan_uv", kd_descan_uv, dim3(256, n), 64, 0, b);
@@ -546,10 +631,21 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	d_wavefront(c, "d_sharpen_uv", b, n, 2, dwf_sharpen_geom(), [=] __device__(const DecImg &im, int r, int j) {
 		return dwf_sharpen_cell(im.cproc, im.d->quality <= 14 ? 35 : 60, r, j);
 	});
-	NHW_LAUNCH_L(c, "d_upsample_uv", kd_upsample_uv, dim3(256, 2 * n), 256, 0, b);
 
-	// ---- colour
-	NHW_LAUNCH(c, kd_color, dim3(262144 / 256, n), 256, 0, b, rgb_dev);
+	// ---- back end: luma synthesis tail, chroma upsample, colour -> pixels (and the Y/U/V byte planes when asked for)
+	if (want_yuv) NHW_LAUNCH_L(c, "d_backend<yuv>", kd_backend<true>, dim3(512 / BE_ROWS, n), 256, 0, b, rgb_dev);
+	else NHW_LAUNCH_L(c, "d_backend", kd_backend<false>, dim3(512 / BE_ROWS, n), 256, 0, b, rgb_dev);
+}
+
+// streams resident in device memory: stream i at in + offs[i] (offs != NULL, n + 1 entries) or at in + i * stride with
+// length len[i].  Headers are walked on the device; everything is queued on c->stream.
+void decode_chunk_device(nhw_ctx *c, const uint8_t *in, size_t stride, const uint32_t *len, const uint64_t *offs, int n,
+                         uint8_t *rgb_dev, int32_t *status_dev)
+{
+	DecDesc *desc = static_cast<DecDesc *>(c->dec_desc_dev);
+	NHW_LAUNCH(c, kd_parse_headers, (n + 127) / 128, 128, 0, in, stride, len, offs, n, desc, c->offs_dev, c->status_dev);
+	decode_chunk(c, in, c->offs_dev, desc, c->status_dev, n, rgb_dev, true, true, false);
+	if (status_dev) cudaMemcpyAsync(status_dev, c->status_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream);
 }
 
 }  // namespace nhw

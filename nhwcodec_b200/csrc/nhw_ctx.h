@@ -99,7 +99,9 @@ void pack_streams(nhw_ctx *c, int n);   // out_dev slots + len_dev -> offs_dev, 
 
 // decode.cu
 void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const struct DecDesc *desc, int32_t *status, int n,
-                  uint8_t *rgb_dev, bool any_lowq);
+                  uint8_t *rgb_dev, bool any_lowq, bool any_hq, bool want_yuv);
+void decode_chunk_device(nhw_ctx *c, const uint8_t *in, size_t stride, const uint32_t *len, const uint64_t *offs, int n,
+                         uint8_t *rgb_dev, int32_t *status_dev);
 
 // synth.cu
 void synth(nhw_ctx *c, uint8_t *rgb, int n, uint32_t seed0, int kind, const int16_t *sin_lut);

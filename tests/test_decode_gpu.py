@@ -87,3 +87,58 @@ def test_decode_hostile_headers(codec, ref):
     rgb, status = codec.decode(bad + [good])
     assert (status[:-1] != 0).all(), status
     assert status[-1] == 0 and np.array_equal(rgb[-1], ref.ref_decode(good))
+
+
+def test_decode_device_api(codec, ref):
+    """device-resident decode (headers walked on the device): slots as written by the device encoder, and streams
+    packed back to back; more streams than max_batch (16), mixed qualities, one corrupt stream in the middle"""
+    import torch
+    imgs = _mixed(40, 9700)
+    t = torch.from_numpy(imgs).cuda()
+    slots = torch.zeros((40, 1 << 19), dtype=torch.uint8, device="cuda")
+    ln = torch.zeros(40, dtype=torch.int32, device="cuda")
+    st = torch.zeros(40, dtype=torch.int32, device="cuda")
+    codec.encode_device(t[:20], 20, slots[:20], ln[:20], st[:20])
+    codec.encode_device(t[20:], 7, slots[20:], ln[20:], st[20:])
+    assert int((st != 0).sum()) == 0
+    slots[13, 1] = 0                      # quality byte 0: refused
+    rgb = torch.empty((40, 786432), dtype=torch.uint8, device="cuda")
+    dst = torch.zeros(40, dtype=torch.int32, device="cuda")
+    codec.decode_device(slots, ln, rgb, dst)
+    dst_h = dst.cpu().numpy()
+    assert dst_h[13] != 0 and (np.delete(dst_h, 13) == 0).all(), dst_h
+    lens = ln.cpu().numpy()
+    got = rgb.cpu().numpy()
+    for i in (0, 1, 12, 14, 19, 20, 21, 39):
+        stream = slots[i, : int(lens[i])].cpu().numpy().tobytes()
+        assert np.array_equal(got[i], ref.ref_decode(stream)), i
+    assert not got[13].any()
+    # packed form
+    offs = np.concatenate([[0], np.cumsum(lens.astype(np.int64))])
+    packed = torch.zeros(int(offs[-1]) + 64, dtype=torch.uint8, device="cuda")
+    for i in range(40):
+        packed[int(offs[i]): int(offs[i + 1])] = slots[i, : int(lens[i])]
+    rgb2 = torch.empty_like(rgb)
+    dst2 = torch.zeros_like(dst)
+    codec.decode_packed_device(packed, torch.from_numpy(offs).cuda(), rgb2, dst2)
+    assert torch.equal(dst2, dst) and torch.equal(rgb2, rgb)
+
+
+def test_decode_planes_api(codec, ref):
+    """nhw_decode_batch_planes: the Y/U/V byte planes decode_image leaves for write_image_bmp"""
+    import ctypes
+    imgs = _mixed(5, 9800)
+    for q in (21, 12):
+        streams = [ref.ref_encode(imgs[i], q) for i in range(5)]
+        offs = np.zeros(6, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(s) for s in streams])
+        blob = np.frombuffer(b"".join(streams), dtype=np.uint8)
+        yuv = np.zeros((5, 786432), dtype=np.uint8)
+        qual = np.zeros(5, dtype=np.int32)
+        status = np.zeros(5, dtype=np.int32)
+        rc = codec.lib.nhw_decode_batch_planes(codec.h, blob.ctypes.data, offs.ctypes.data, 5, yuv.ctypes.data,
+                                               qual.ctypes.data, status.ctypes.data)
+        assert rc == 0 and (status == 0).all() and (qual == q).all()
+        for i in range(5):
+            _, planes = ref.ref_decode(streams[i], planes=True)
+            assert np.array_equal(yuv[i].reshape(3, 512, 512), planes), (q, i)
