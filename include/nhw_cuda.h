@@ -68,6 +68,18 @@ int nhw_encode_batch(nhw_ctx *ctx, const uint8_t *rgb, int n, int quality,
 int nhw_encode_batch_device(nhw_ctx *ctx, const uint8_t *rgb_dev, int n, int quality,
                             uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev);
 
+/* Pack the n stream slots nhw_encode_batch_device wrote (stride NHW_MAX_STREAM_BYTES) back to back into dense_dev:
+ * offs_dev receives n + 1 offsets (offs_dev[n] = total bytes; dense_dev must hold that many -- n * NHW_MAX_STREAM_BYTES
+ * always suffices).  This is the local half of the one exchange step of a multi-GPU encode (the stream gather). */
+int nhw_pack_batch_device(nhw_ctx *ctx, const uint8_t *slots_dev, const uint32_t *len_dev, int n, uint64_t *offs_dev,
+                          uint8_t *dense_dev);
+
+/* A 64-bit position-weighted checksum per item of a batch of byte strings in device memory (item i = data_dev +
+ * i * stride, length len_dev[i], or fixed_len when len_dev is NULL).  Lets sharded results (decoded pixels stay on
+ * their GPU) be compared between runs without moving them. */
+int nhw_digest_batch_device(nhw_ctx *ctx, const uint8_t *data_dev, size_t stride, const uint32_t *len_dev, uint32_t fixed_len,
+                            int n, uint64_t *digest_dev);
+
 /* ---- decode: replaces decode_image + write_image_bmp's pixel path
  * (decoder/nhw_decoder_cli.c:83-90) for n streams. ----
  * in/offsets : concatenated .nhw streams (host).   rgb : n * NHW_PIX_BYTES bytes out. */

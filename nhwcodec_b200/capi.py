@@ -51,6 +51,10 @@ def load_library():
     L.nhw_encode_batch_device.restype = i32
     L.nhw_decode_batch.argtypes = [vp, vp, vp, i32, vp, vp]
     L.nhw_decode_batch.restype = i32
+    L.nhw_pack_batch_device.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.nhw_pack_batch_device.restype = i32
+    L.nhw_digest_batch_device.argtypes = [vp, vp, ctypes.c_size_t, vp, u32, i32, vp]
+    L.nhw_digest_batch_device.restype = i32
     L.nhw_decode_batch_device.argtypes = [vp, vp, ctypes.c_size_t, vp, i32, vp, vp]
     L.nhw_decode_batch_device.restype = i32
     L.nhw_decode_batch_packed_device.argtypes = [vp, vp, vp, i32, vp, vp]
@@ -196,6 +200,17 @@ class Codec:
         rc = self.lib.nhw_encode_batch_device(self.h, _ptr(rgb_t), n, int(quality), _ptr(out_t), _ptr(len_t),
                                               _ptr(status_t))
         self._check(rc, "nhw_encode_batch_device")
+
+    def pack_device(self, slots_t, len_t, offs_t, dense_t):
+        """stream slots -> streams back to back (offs_t: n + 1 int64/uint64 on the device)"""
+        rc = self.lib.nhw_pack_batch_device(self.h, _ptr(slots_t), _ptr(len_t), int(len_t.numel()), _ptr(offs_t), _ptr(dense_t))
+        self._check(rc, "nhw_pack_batch_device")
+
+    def digest_device(self, data_t, out_t, len_t=None):
+        """one 64-bit checksum per row of data_t (2-D uint8, contiguous); len_t: optional per-row lengths"""
+        n, stride = data_t.shape[0], data_t.shape[1]
+        rc = self.lib.nhw_digest_batch_device(self.h, _ptr(data_t), int(stride), _ptr(len_t), int(stride), n, _ptr(out_t))
+        self._check(rc, "nhw_digest_batch_device")
 
     def decode_device(self, in_t, len_t, rgb_t, status_t, stride=MAX_STREAM_BYTES):
         """streams in device memory, one per `stride`-byte slot (what encode_device writes) -> pixels in device memory"""

@@ -457,6 +457,23 @@ int nhw_encode_batch_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quali
 	return finish(c, "nhw_encode_batch_device");
 }
 
+int nhw_pack_batch_device(nhw_ctx *c, const uint8_t *slots_dev, const uint32_t *len_dev, int n, uint64_t *offs_dev, uint8_t *dense_dev)
+{
+	if (!c || !slots_dev || !len_dev || !offs_dev || !dense_dev || n <= 0) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	nhw::pack_streams_to(c, slots_dev, len_dev, n, offs_dev, dense_dev);
+	return finish(c, "nhw_pack_batch_device");
+}
+
+int nhw_digest_batch_device(nhw_ctx *c, const uint8_t *data_dev, size_t stride, const uint32_t *len_dev, uint32_t fixed_len, int n,
+                            uint64_t *digest_dev)
+{
+	if (!c || !data_dev || !digest_dev || n <= 0) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	nhw::digest(c, data_dev, stride, len_dev, fixed_len, n, digest_dev);
+	return finish(c, "nhw_digest_batch_device");
+}
+
 int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
                      uint8_t *out, size_t out_cap, uint64_t *offsets, int32_t *status)
 {

@@ -1838,6 +1838,13 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	NHW_LAUNCH(c, k_write_stream, n, 256, 0, b, n, out_dev, len_dev, status_dev);
 }
 
+// caller-owned buffers (nhw_pack_batch_device): n may exceed max_batch -- the offsets kernel is one CTA over all n
+void pack_streams_to(nhw_ctx *c, const uint8_t *slots, const uint32_t *len, int n, uint64_t *offs, uint8_t *dense)
+{
+	NHW_LAUNCH(c, k_stream_offsets, 1, 1024, 0, len, offs, n);
+	NHW_LAUNCH(c, k_pack_streams, n, 256, 0, slots, len, offs, dense);
+}
+
 void pack_streams(nhw_ctx *c, int n)
 {
 	NHW_LAUNCH(c, k_stream_offsets, 1, 1024, 0, c->len_dev, c->offs_dev, n);

@@ -96,6 +96,7 @@ void dwt_level_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t j
 // encode.cu
 void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev);
 void pack_streams(nhw_ctx *c, int n);   // out_dev slots + len_dev -> offs_dev, pack_dev
+void pack_streams_to(nhw_ctx *c, const uint8_t *slots, const uint32_t *len, int n, uint64_t *offs, uint8_t *dense);
 
 // decode.cu
 void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const struct DecDesc *desc, int32_t *status, int n,
@@ -104,6 +105,7 @@ void decode_chunk_device(nhw_ctx *c, const uint8_t *in, size_t stride, const uin
                          uint8_t *rgb_dev, int32_t *status_dev);
 
 // synth.cu
+void digest(nhw_ctx *c, const uint8_t *data, size_t stride, const uint32_t *len, uint32_t fixed_len, int n, uint64_t *out);
 void synth(nhw_ctx *c, uint8_t *rgb, int n, uint32_t seed0, int kind, const int16_t *sin_lut);
 
 // per-device set-up, called by nhw_create with the device current: opt-in to > 48 KB of dynamic shared memory for the

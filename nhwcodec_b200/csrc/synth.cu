@@ -82,9 +82,45 @@ __global__ void __launch_bounds__(256) k_synth(uint8_t *__restrict__ rgb, uint32
 	}
 }
 
+// ---- per-item digest of a batch of byte strings (decoded images, .nhw streams): a position-weighted 64-bit sum,
+// sum over k of (byte[k] + 1) * w(k) mod 2^64 with w(k) = odd multiplier of (k + 1), so that any order of summation
+// gives the same value and the whole CTA can work on one item.  Used to compare runs (1 GPU vs N GPUs) without
+// moving the data; not a cryptographic hash.
+__global__ void __launch_bounds__(256) k_digest(const uint8_t *__restrict__ data, size_t stride, const uint32_t *__restrict__ len,
+                                                uint32_t fixed_len, unsigned long long *__restrict__ out)
+{
+	__shared__ unsigned long long part[256];
+	const int i = blockIdx.x;
+	const uint8_t *p = data + (size_t)i * stride;
+	const uint32_t L = len ? len[i] : fixed_len;
+	unsigned long long acc = 0;
+	const uint32_t words = (((uintptr_t)p & 3) == 0) ? L >> 2 : 0;   // aligned body as 32-bit words, the rest bytewise
+	for (uint32_t w = threadIdx.x; w < words; w += 256) {
+		const uint32_t v = reinterpret_cast<const uint32_t *>(p)[w];
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			const unsigned long long k = 4ull * w + b + 1ull;
+			acc += (unsigned long long)(((v >> (8 * b)) & 255u) + 1u) * (k * 0x9E3779B97F4A7C15ull | 1ull);
+		}
+	}
+	for (uint32_t k = 4 * words + threadIdx.x; k < L; k += 256) acc += (unsigned long long)(p[k] + 1u) * (((unsigned long long)k + 1ull) * 0x9E3779B97F4A7C15ull | 1ull);
+	part[threadIdx.x] = acc;
+	__syncthreads();
+	for (int s = 128; s > 0; s >>= 1) {
+		if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[i] = part[0] ^ ((unsigned long long)L << 40);
+}
+
 }  // namespace
 
 namespace nhw {
+void digest(nhw_ctx *c, const uint8_t *data, size_t stride, const uint32_t *len, uint32_t fixed_len, int n, uint64_t *out)
+{
+	NHW_LAUNCH(c, k_digest, n, 256, 0, data, stride, len, fixed_len, reinterpret_cast<unsigned long long *>(out));
+}
+
 void synth(nhw_ctx *c, uint8_t *rgb, int n, uint32_t seed0, int kind, const int16_t *sin_lut)
 {
 	NHW_LAUNCH(c, k_synth, dim3(64, n), 256, 0, rgb, seed0, kind, sin_lut);
