@@ -159,11 +159,11 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
 		NhwTuning &t = c->tune;
 		t.lanes_device = env_int("NHW_LANES_DEVICE", 1, 1, NHW_LANES);
-		t.chroma_stream = c->tune.chroma_stream;
-		t.subs_encode = c->tune.subs_encode;
-		t.lanes_encode = c->tune.lanes_encode;
-		t.subs_decode = c->tune.subs_decode;
-		t.lanes_decode = c->tune.lanes_decode;
+		t.chroma_stream = env_int("NHW_CHROMA_STREAM", 1, 0, 1);
+		t.subs_encode = env_int("NHW_SUBS_ENCODE", 16, 1, NHW_MAX_SUB);
+		t.lanes_encode = env_int("NHW_LANES_ENCODE", 4, 1, NHW_LANES);
+		t.subs_decode = env_int("NHW_SUBS_DECODE", 8, 1, NHW_MAX_SUB);
+		t.lanes_decode = env_int("NHW_LANES_DECODE", 4, 1, NHW_LANES);
 		t.dsf_streams = env_int("NHW_DSF_STREAMS", 4, 1, 32);
 		while (32 % t.dsf_streams) t.dsf_streams--;
 		t.rows_grid_cap = sms * env_int("NHW_ROWS_CTAS_PER_SM", 24, 1, 64);
