@@ -175,28 +175,6 @@ template <typename F> void d_plane(nhw_ctx *c, const char *l, const DecBatch &b,
 template <typename F> void d_rows(nhw_ctx *c, const char *l, const DecBatch &b, int n, int rows, F f) { NHW_LAUNCH_L(c, l, kd_rows, dim3((rows + 63) / 64, n), 64, 0, b, rows, f); }
 template <typename F> void d_plane_rows(nhw_ctx *c, const char *l, const DecBatch &b, int n, int rows, F f) { NHW_LAUNCH_L(c, l, kd_plane_rows, dim3((rows + 63) / 64, 2 * n), 64, 0, b, rows, f); }
 
-// ---- wavefront executor (dec_par.cuh): one CTA per plane, thread = row of the stage's region
-template <typename Cell>
-__global__ void __launch_bounds__(256) kd_wavefront(DecBatch b, WfGeom g, int planes_per_image, Cell cell)
-{
-	const int img = blockIdx.x / planes_per_image;
-	if (b.status[img] != 0) return;
-	const DecImg im = make_dec(b, img, blockIdx.x % planes_per_image);
-	const int ri = threadIdx.x;
-	const int steps = g.cols + g.skew * (g.rows - 1);
-	int next = 0;
-	for (int t = 0; t < steps; t++) {
-		const int c = t - g.skew * ri;
-		if (ri < g.rows && c >= 0 && c < g.cols && c == next) next = c + cell(im, g.r0 + ri, g.c0 + c);
-		__syncthreads();
-	}
-}
-template <typename Cell>
-void d_wavefront(nhw_ctx *c, const char *l, const DecBatch &b, int n, int ppi, WfGeom g, Cell cell)
-{
-	NHW_LAUNCH_L(c, l, kd_wavefront, n * ppi, 256, 0, b, g, ppi, cell);
-}
-
 // ---- D8: isolated-coefficient shrink of the level-2 region, order-free form (cells8.cuh: shrink_cells8)
 __global__ void __launch_bounds__(256) kd_shrink_y(DecBatch b)
 {
@@ -426,35 +404,6 @@ __global__ void __launch_bounds__(64) kd_descan_uv(DecBatch b)
 	for (int t = 0; t < 8; t++) dst[(row & 1) ? 7 - t : t] = s[2 * t];
 }
 
-// ---- D12: flagged positions in raster order, flags removed (nhw_decoder.c:827-839); thread = row
-__global__ void __launch_bounds__(256) kd_edge_compact(DecBatch b)
-{
-	__shared__ int cnt[257];
-	if (b.status[blockIdx.x] != 0) return;
-	const DecImg im = make_dec(b, blockIdx.x, 0);
-	const int r = threadIdx.x;
-	int16_t *row = im.proc + r * YW;
-	int n = 0;
-	if (r >= 1 && r < 255)
-		for (int j = 0; j < 256; j += 2) {
-			const uint32_t w = *reinterpret_cast<const uint32_t *>(row + j);
-			n += ((int16_t)(w & 0xffff) > 10000) + ((int16_t)(w >> 16) > 10000);
-		}
-	cnt[r] = n;
-	__syncthreads();
-	if (r == 0) {
-		int run = 0;
-		for (int k = 0; k < 256; k++) { const int v = cnt[k]; cnt[k] = run; run += v; }
-		im.list_len[9] = run;
-	}
-	__syncthreads();
-	if (n) {
-		int o = cnt[r];
-		for (int j = 0; j < 256; j++)
-			if (row[j] > 10000) { im.flags[o++] = (uint16_t)((r << 8) + j); row[j] -= 16000; }
-	}
-}
-
 // square transpose of the top-left N x N cells of a plane into another plane (32x32 tiles)
 __global__ void __launch_bounds__(256) kd_transpose(const int16_t *in, int16_t *out, size_t in_slot, size_t out_slot, int stride)
 {
@@ -472,6 +421,209 @@ __global__ void kd_zero(int16_t *p, size_t slot, size_t count16)   // count16 = 
 {
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < count16) reinterpret_cast<uint4 *>(p + (size_t)blockIdx.y * slot)[i] = make_uint4(0, 0, 0, 0);
+}
+
+// =====================================================================================
+// Row-sequential in-place stencils as "a row per warp step"
+// =====================================================================================
+// D11 (edge flags) and D16 (chroma sharpen) edit a plane in place in raster order: a cell's 8-neighbour Laplacian sees
+// the row above and its left neighbour AFTER their own turn, the right neighbour and the row below before.  Rows
+// therefore have to be final one after the other, but inside a row the only thing that travels from cell to cell is
+// what the left neighbour did to itself -- one of 5 values for the sharpen (0, +-2, +-3), one bit for the flags
+// (flagged or not).  So a cell is a map {what the left cell did} -> {what this cell does}, maps compose, and a warp
+// resolves a whole row with one scan of lane maps: a lane owns 8 consecutive columns, keeps the rows above / below
+// in registers (16-byte loads and stores, the plane is read once and written once), and evaluates its cells for
+// every incoming possibility only when one of them sits within reach of a threshold.  One warp per plane, no
+// barriers: 254 row steps of a few hundred instructions instead of 760 block-wide wavefront steps.
+
+// ---- D16: chroma sharpen (nhw_decoder.c:1085-1109; cell form dwf_sharpen_cell)
+__device__ __forceinline__ int sharpen_delta(int res, int thr)
+{
+	const int a = res < 0 ? -res : res;
+	const int d = a > thr ? (a > 160 ? 3 : 2) : 0;
+	return res < 0 ? -d : d;
+}
+__device__ __forceinline__ int sh_state(int d) { return d == 0 ? 2 : d < 0 ? (d == -3 ? 0 : 1) : (d == 2 ? 3 : 4); }   // -3,-2,0,2,3 -> 0..4
+__device__ __forceinline__ int sh_value(int st) { return st == 2 ? 0 : st < 2 ? st - 3 : st - 1; }
+// maps over the five states, 3 bits per entry; (first then second)[i] = second[first[i]]
+__device__ __forceinline__ uint32_t map5_then(uint32_t first, uint32_t second)
+{
+	uint32_t r = 0;
+#pragma unroll
+	for (int i = 0; i < 5; i++) r |= ((second >> (3 * ((first >> (3 * i)) & 7u))) & 7u) << (3 * i);
+	return r;
+}
+__device__ __forceinline__ void unpack8(const uint4 &w, int *v)
+{
+	v[0] = (int16_t)(w.x & 0xffff); v[1] = (int16_t)(w.x >> 16); v[2] = (int16_t)(w.y & 0xffff); v[3] = (int16_t)(w.y >> 16);
+	v[4] = (int16_t)(w.z & 0xffff); v[5] = (int16_t)(w.z >> 16); v[6] = (int16_t)(w.w & 0xffff); v[7] = (int16_t)(w.w >> 16);
+}
+__device__ __forceinline__ uint4 pack8(const int *v)
+{
+	return make_uint4((uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16), (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16),
+	                  (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16), (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16));
+}
+
+__global__ void __launch_bounds__(128) kd_sharpen_rows(DecBatch b, int n2)
+{
+	const int lane = threadIdx.x & 31, pl = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (pl >= n2 || b.status[pl >> 1] != 0) return;
+	int16_t *P = b.c_proc + (size_t)pl * NHW_C_SLOT;
+	const int thr = b.desc[pl >> 1].quality <= 14 ? 35 : 60;
+	// x[1..8] = the lane's columns 8*lane .. 8*lane+7; x[0], x[9] = the neighbours' edge columns
+	int up[10], cur[10], dn[10];
+	auto halo = [&](int *v) {
+		v[0] = __shfl_up_sync(0xffffffffu, v[8], 1);
+		v[9] = __shfl_down_sync(0xffffffffu, v[1], 1);
+	};
+	unpack8(reinterpret_cast<const uint4 *>(P)[lane], up + 1);
+	unpack8(reinterpret_cast<const uint4 *>(P + CW)[lane], cur + 1);
+	halo(up);
+	for (int r = 1; r < 255; r++) {
+		unpack8(reinterpret_cast<const uint4 *>(P + (r + 1) * CW)[lane], dn + 1);
+		halo(cur);
+		halo(dn);
+		// the Laplacian of every cell with its left neighbour as it was; what the left neighbour did is subtracted later
+		int base[9];
+		bool touchy = false;
+#pragma unroll
+		for (int k = 1; k <= 8; k++) {
+			base[k] = 8 * cur[k] - (up[k - 1] + up[k] + up[k + 1]) - cur[k - 1] - cur[k + 1] - (dn[k - 1] + dn[k] + dn[k + 1]);
+			const int a = base[k] < 0 ? -base[k] : base[k];
+			touchy |= (a >= thr - 2 && a <= thr + 3) || (a >= 158 && a <= 163);   // |left's step| <= 3 can change the outcome
+		}
+		// columns 0 and 255 are never edited: their "step" is 0 whatever comes in
+		const bool first_col = lane == 0, last_col = lane == 31;
+		int din = 0;
+		if (__any_sync(0xffffffffu, touchy)) {
+			uint32_t m;
+			if (touchy) {
+				m = 0;
+#pragma unroll
+				for (int h = 0; h < 5; h++) {
+					int x = sh_value(h);
+#pragma unroll
+					for (int k = 1; k <= 8; k++) {
+						const bool edit = !(first_col && k == 1) && !(last_col && k == 8);
+						x = edit ? sharpen_delta(base[k] - x, thr) : 0;
+					}
+					m |= (uint32_t)sh_state(x) << (3 * h);
+				}
+			} else {
+				const int x = last_col ? 0 : sharpen_delta(base[8], thr);   // (lane 0 has more than one cell: cell 8 is an edited one)
+				m = (uint32_t)sh_state(x) * 0x1249u;                         // the same state for all five entries
+			}
+#pragma unroll
+			for (int dlt = 1; dlt < 32; dlt <<= 1) {
+				const uint32_t o = __shfl_up_sync(0xffffffffu, m, dlt);
+				if (lane >= dlt) m = map5_then(o, m);
+			}
+			const uint32_t before = __shfl_up_sync(0xffffffffu, m, 1);
+			din = lane ? sh_value((int)((before >> 6) & 7u)) : 0;            // entry for "nothing came in" (state 2) at the row start
+		}
+		int x = din;
+#pragma unroll
+		for (int k = 1; k <= 8; k++) {
+			const bool edit = !(first_col && k == 1) && !(last_col && k == 8);
+			x = edit ? sharpen_delta(base[k] - x, thr) : 0;
+			cur[k] += x;
+		}
+		reinterpret_cast<uint4 *>(P + r * CW)[lane] = pack8(cur + 1);
+		halo(cur);
+#pragma unroll
+		for (int k = 0; k < 10; k++) { up[k] = cur[k]; cur[k] = dn[k]; }
+	}
+}
+
+// ---- D11 + D12: edge flags on the reconstructed LL1 and the list of flagged positions (nhw_decoder.c:789-839; cell
+// form dwf_edge_cell).  Pairs of columns (1+2p, 2+2p); a flagged cell carries +16000 while the pass runs, so the row
+// above is kept WITH its flags in registers while the plane itself is written back without them (the reference
+// removes them again right after, when it collects the list).  What travels along a row: whether the previous
+// pair flagged its second cell (the left neighbour of this pair's first cell).
+__global__ void __launch_bounds__(128) kd_edge_rows(DecBatch b, int n)
+{
+	const int lane = threadIdx.x & 31, img = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (img >= n || b.status[img] != 0) return;
+	const DecImg im = make_dec(b, img, 0);
+	int16_t *P = im.proc;
+	// x[1..8] = columns 8*lane .. 8*lane+7, x[0] = column 8*lane-1, x[9], x[10] = columns 8*lane+8, +9
+	int up[11], cur[11], dn[11];
+	auto halo = [&](int *v) {
+		v[0] = __shfl_up_sync(0xffffffffu, v[8], 1);
+		v[9] = __shfl_down_sync(0xffffffffu, v[1], 1);
+		v[10] = __shfl_down_sync(0xffffffffu, v[2], 1);
+		if (lane == 31) { v[9] = 0; v[10] = 0; }   // columns 256, 257: outside every stencil that is evaluated
+	};
+	unpack8(reinterpret_cast<const uint4 *>(P)[lane], up + 1);
+	unpack8(reinterpret_cast<const uint4 *>(P + YW)[lane], cur + 1);
+	halo(up);
+	int nflags = 0;
+	for (int r = 1; r < 255; r++) {
+		unpack8(reinterpret_cast<const uint4 *>(P + (r + 1) * YW)[lane], dn + 1);
+		halo(cur);
+		halo(dn);
+		auto lap = [&](int k) {
+			return 8 * cur[k] - cur[k - 1] - cur[k + 1] - (up[k - 1] + up[k] + up[k + 1]) - (dn[k - 1] + dn[k] + dn[k + 1]);
+		};
+		// the lane's four pairs start at x[2], x[4], x[6], x[8] (columns 8*lane+1, +3, +5, +7); the last pair of lane 31
+		// (columns 255, 256) does not exist
+		int res[4], cnt[4];
+#pragma unroll
+		for (int q = 0; q < 4; q++) { res[q] = lap(2 + 2 * q); cnt[q] = lap(3 + 2 * q); }
+		const int npairs = lane == 31 ? 3 : 4;
+		// outcome of a pair: 0 nothing, 1 first cell flagged, 2 second cell flagged; `in` = the previous pair flagged its
+		// second cell, which is this pair's first cell's left neighbour (-16000 in its Laplacian)
+		auto outcome = [&](int q, int in) {
+			const int rs = res[q] - (in ? 16000 : 0), ct = cnt[q];
+			if (rs > 41 && rs < 108 && ct < 16) return 1;
+			if (rs < -41 && rs > -108 && ct > -16) return 1;
+			if (ct > 41 && ct < 108 && rs < 16) return 2;
+			if (ct < -41 && ct > -108 && rs > -16) return 2;
+			return 0;
+		};
+		// lane map over the two incoming possibilities: bit i = "the lane's last pair flags its second cell" given in = i
+		uint32_t m = 0;
+#pragma unroll
+		for (int in = 0; in < 2; in++) {
+			int x = in;
+			for (int q = 0; q < npairs; q++) x = outcome(q, x) == 2 ? 1 : 0;
+			m |= (uint32_t)x << in;
+		}
+#pragma unroll
+		for (int dlt = 1; dlt < 32; dlt <<= 1) {
+			const uint32_t o = __shfl_up_sync(0xffffffffu, m, dlt);
+			if (lane >= dlt) m = ((m >> (o & 1u)) & 1u) | (((m >> ((o >> 1) & 1u)) & 1u) << 1);
+		}
+		const uint32_t before = __shfl_up_sync(0xffffffffu, m, 1);
+		int x = lane ? (int)(before & 1u) : 0;     // nothing is flagged left of column 1
+		const int carried = x;                      // the previous lane's last pair flagged this lane's column 8*lane
+		uint32_t fl = 0;                            // bit k-1 = x[k] flagged (own columns)
+		int spill = 0;
+		for (int q = 0; q < npairs; q++) {
+			const int o = outcome(q, x);
+			if (o == 1) fl |= 1u << (1 + 2 * q);
+			else if (o == 2) { if (q < 3) fl |= 1u << (2 + 2 * q); else spill = 1; }
+			x = o == 2 ? 1 : 0;
+		}
+		if (carried) fl |= 1u;
+		(void)spill;                                // (the next lane learns it through `carried`)
+		// D12: positions of the flagged cells in raster order
+		const int mine = __popc(fl);
+		int off = mine;
+#pragma unroll
+		for (int dlt = 1; dlt < 32; dlt <<= 1) { const int o = __shfl_up_sync(0xffffffffu, off, dlt); if (lane >= dlt) off += o; }
+		const int total = __shfl_sync(0xffffffffu, off, 31);
+		off += nflags - mine;
+		for (uint32_t f = fl; f; f &= f - 1) im.flags[off++] = (uint16_t)((r << 8) + 8 * lane + __ffs(f) - 1);
+		nflags += total;
+		// the row above the next row keeps its flags (register copy); the plane itself never shows them
+#pragma unroll
+		for (int k = 1; k <= 8; k++) up[k] = cur[k] + (((fl >> (k - 1)) & 1u) ? 16000 : 0);
+		halo(up);
+#pragma unroll
+		for (int k = 0; k < 11; k++) cur[k] = dn[k];
+	}
+	if (lane == 0) im.list_len[9] = nflags;
 }
 
 // ---- back end: second half of the level-1 luma synthesis + clip, chroma clip + 2x upsample, YCbCr -> RGB, in one pass
@@ -608,8 +760,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	if (any_lowq) NHW_LAUNCH_L(c, "d_shrink_y_lowq", kd_shrink_y_lowq, n, 256, 0, b);
 	idwt_rows_cols(c, n, b.y_jpeg, b.y_aux, b.y_proc, YS, 256, 512);
 	NHW_LAUNCH_L(c, "d_addbacks", kd_addbacks, n, 256, 0, b);
-	d_wavefront(c, "d_edge_flags", b, n, 1, dwf_edge_geom(), [=] __device__(const DecImg &im, int r, int p) { return dwf_edge_cell(im.proc, r, p); });
-	NHW_LAUNCH_L(c, "d_edge_compact", kd_edge_compact, n, 256, 0, b);
+	NHW_LAUNCH_L(c, "d_edge_rows", kd_edge_rows, (n + 3) / 4, 128, 0, b, n);   // D11 + D12
 	NHW_LAUNCH_L(c, "d_inv_rows_t", kd_inv_rows_t, dim3(512 / IRT_ROWS, n), 256, IRT_SMEM, b);   // -> y_aux
 	if (any_hq) NHW_LAUNCH_L(c, "d_hq_addbacks", kd_hq_addbacks, n, 256, 0, b);   // q22 / q23 streams only
 	d_image(c, "d_smooth_flags", b, n, [=] __device__(const DecImg &im, int) { dec_y_smooth_flags_plane(im, im.aux); });
@@ -628,9 +779,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH_L(c, "d_markers_uv", kd_c_markers, dim3(256, 2 * n), 256, 0, b);
 	NHW_LAUNCH(c, kd_transpose, dim3(4, 4, 2 * n), 256, 0, b.c_proc, b.c_jpeg, CS, CS, 256);
 	idwt_rows_cols(c, 2 * n, b.c_jpeg, b.c_aux, b.c_proc, CS, 256, 256);
-	d_wavefront(c, "d_sharpen_uv", b, n, 2, dwf_sharpen_geom(), [=] __device__(const DecImg &im, int r, int j) {
-		return dwf_sharpen_cell(im.cproc, im.d->quality <= 14 ? 35 : 60, r, j);
-	});
+	NHW_LAUNCH_L(c, "d_sharpen_rows", kd_sharpen_rows, (2 * n + 3) / 4, 128, 0, b, 2 * n);
 
 	// ---- back end: luma synthesis tail, chroma upsample, colour -> pixels (and the Y/U/V byte planes when asked for)
 	if (want_yuv) NHW_LAUNCH_L(c, "d_backend<yuv>", kd_backend<true>, dim3(512 / BE_ROWS, n), 256, 0, b, rgb_dev);

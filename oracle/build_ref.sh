@@ -42,13 +42,14 @@ $CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$HERE/ref_enc_glue.c" -o "$TMP/enc_gl
 $CC $CFLAGS -c "$HERE/zguard.c" -o "$TMP/zguard.o"
 $CC -shared -o "$OUT/libnhwref_enc.so" $tobjs "$TMP/enc_nhw_encoder.o" "$TMP/enc_glue.o" "$TMP/zguard.o" \
 	$WRAP -Wl,-Bsymbolic -lm -lpthread
-# timing build: the same reference objects on the STOCK allocator (only exit() is trapped), so the
-# CPU baseline is not slowed down by the canonicalising allocator.  Never used for parity.
+# timing build: the same reference objects with blocks padded but NOT zero-filled (zguard.c, NHW_NO_ZGUARD), so the
+# CPU baseline is not slowed down by the canonicalising allocator and cannot fault on the reference's out-of-bounds
+# reads.  Never used for parity.
 $CC $CFLAGS -I"$REF/encoder" -c "$REF/encoder/nhw_encoder.c" -o "$TMP/enc_nhw_encoder_plain.o"
 $CC $CFLAGS -DNHW_NO_ZGUARD -c "$HERE/zguard.c" -o "$TMP/zguard_exit_only.o"
 $CC $CFLAGS -I"$REF/encoder" -I"$HERE" -DNHW_NO_TAPS -c "$HERE/ref_enc_glue.c" -o "$TMP/enc_glue_plain.o"
 $CC -shared -o "$OUT/libnhwref_enc_stock.so" $objs "$TMP/enc_nhw_encoder_plain.o" "$TMP/enc_glue_plain.o" "$TMP/zguard_exit_only.o" \
-	-Wl,--wrap=exit -Wl,-Bsymbolic -lm -lpthread
+	$WRAP -Wl,-Bsymbolic -lm -lpthread
 
 # ---- decoder library ----
 if [ -f "$HERE/taps_dec.txt" ]; then

@@ -42,9 +42,30 @@ void __wrap_free(void *p)
 }
 
 #else
-/* timing build (libnhwref_enc_stock.so): stock allocator, the glue's __real_* names map to libc */
-void *__real_malloc(size_t n) { return malloc(n); }
-void __real_free(void *p) { free(p); }
+/* timing build (libnhwref_enc_stock.so): blocks are NOT zero-filled (malloc stays malloc, so the reference runs at
+ * its own speed), but every block is still padded by NHW_GUARD bytes on both sides: the reference's out-of-bounds
+ * reads then land in mapped memory.  Without the padding a read past a large (mmap'd) block can hit an unmapped
+ * page and kill the process -- seen once on a 32-thread baseline run.  Never used for parity. */
+void *__real_malloc(size_t);
+void *__real_calloc(size_t, size_t);
+void __real_free(void *);
+
+void *__wrap_malloc(size_t n)
+{
+	char *p = (char *)__real_malloc(n + 2 * NHW_GUARD);
+	return p ? p + NHW_GUARD : NULL;
+}
+
+void *__wrap_calloc(size_t a, size_t b)
+{
+	char *p = (char *)__real_calloc(1, a * b + 2 * NHW_GUARD);
+	return p ? p + NHW_GUARD : NULL;
+}
+
+void __wrap_free(void *p)
+{
+	if (p) __real_free((char *)p - NHW_GUARD);
+}
 #endif
 
 __thread jmp_buf nhwref_exit_jmp;
