@@ -36,6 +36,8 @@ struct DecImg {
 	uint16_t *list[8];                // expanded position lists (res1 -,+ ; res5 -,+ ; res3 x4)
 	int32_t *list_len;                // 8 lengths + [8] = stale `count`, [9] = edge-flag count, [10] = exw split, [11],[12] = hq lists
 	uint32_t *hq_list[2];             // q22/q23: res6 positions, -32 then +32 (flat indices into the half-synthesised plane)
+	uint32_t *mbits;                  // luma marker bitmap (512 rows x 16 words), written by the inverse scan
+	uint32_t *cmark;                  // chroma markers of this component: [0] = count, then (code << 24 | cell) entries
 	uint16_t *flags;                  // edge-flag positions
 	uint16_t *book;                   // rank -> (run<<8 | byte)
 	const uint16_t *lut;              // primary table of the static prefix code (dec_build_lut)

@@ -290,15 +290,11 @@ NHW_HD void dec_c_descan_strip(const int16_t *coef, int16_t *J, int strip /* 0..
 	}
 }
 
-// LL fill + exw overrides; exw_pos = index into the exw list (advanced past this component)
-NHW_HDN int dec_c_ll_image(const DecImg &im, int is_v, int exw_pos)
+// the exw escape entries of one chroma component; exw_pos = index into the exw list (returned advanced past them)
+NHW_HDN int dec_c_ll_overrides(const DecImg &im, int exw_pos)
 {
 	int16_t *J = im.cjpeg;
 	const DecDesc *d = im.d;
-	const uint8_t *src = im.res_comp + (is_v ? 20480 : 16384);
-	const int bias = d->quality > 15 ? 0 : 1;
-	for (int r = 0; r < 64; r++)
-		for (int j = 0; j < 64; j++) J[r * CW + j] = (int16_t)(src[r * 64 + j] + bias);
 	const uint8_t *x = im.blob + d->off_exw;
 	int i = exw_pos + 2;
 	for (; i < d->exw_Y_end; i += 3) {
@@ -309,6 +305,18 @@ NHW_HDN int dec_c_ll_image(const DecImg &im, int is_v, int exw_pos)
 		J[(x[i] << 8) + col] = (int16_t)val;
 	}
 	return i;
+}
+
+// LL fill + exw overrides; exw_pos = index into the exw list (advanced past this component)
+NHW_HDN int dec_c_ll_image(const DecImg &im, int is_v, int exw_pos)
+{
+	int16_t *J = im.cjpeg;
+	const DecDesc *d = im.d;
+	const uint8_t *src = im.res_comp + (is_v ? 20480 : 16384);
+	const int bias = d->quality > 15 ? 0 : 1;
+	for (int r = 0; r < 64; r++)
+		for (int j = 0; j < 64; j++) J[r * CW + j] = (int16_t)(src[r * 64 + j] + bias);
+	return dec_c_ll_overrides(im, exw_pos);
 }
 
 // markers 5003..5006 in the level-1 bands push +-6 / +-4,+-4 into the reconstructed LL

@@ -15,6 +15,8 @@
 
 namespace {
 
+#define DEC_CMARK_CAP 8191   // chroma markers per plane kept as a list; a plane with more falls back to a sweep
+
 // decode-time carve-up of the per-image byte slot (the encoder's layout is not live during decode)
 enum : int {
 	DOFF_RESCOMP = 4096,
@@ -25,7 +27,9 @@ enum : int {
 	DOFF_LTMP = DOFF_FLAGS + 131072,
 	DOFF_LISTS = DOFF_LTMP + 131072 + 256,        // 8 lists x 65536 entries
 	DOFF_HQ = DOFF_LISTS + 8 * 131072,             // q22/q23: two res6 position lists, NHW_CAP_HQ_LIST x u32 each
-	DOFF_END = DOFF_HQ + 2 * 4 * NHW_CAP_HQ_LIST,
+	DOFF_MBITS = DOFF_HQ + 2 * 4 * NHW_CAP_HQ_LIST,   // luma marker bitmap: 512 rows x 16 words (written by the inverse scan)
+	DOFF_CMARK = DOFF_MBITS + 512 * 64,             // chroma marker lists: 2 planes x (count + DEC_CMARK_CAP entries)
+	DOFF_END = DOFF_CMARK + 2 * 4 * (1 + DEC_CMARK_CAP),
 };
 static_assert(DOFF_END <= ENC_BYTES_SLOT, "decode scratch must fit the per-image byte slot");
 
@@ -42,6 +46,17 @@ struct DecBatch {
 };
 
 __device__ uint16_t g_dec_lut[NHW_LUT_WORDS];
+
+__device__ __forceinline__ void unpack8(const uint4 &w, int *v)
+{
+	v[0] = (int16_t)(w.x & 0xffff); v[1] = (int16_t)(w.x >> 16); v[2] = (int16_t)(w.y & 0xffff); v[3] = (int16_t)(w.y >> 16);
+	v[4] = (int16_t)(w.z & 0xffff); v[5] = (int16_t)(w.z >> 16); v[6] = (int16_t)(w.w & 0xffff); v[7] = (int16_t)(w.w >> 16);
+}
+__device__ __forceinline__ uint4 pack8(const int *v)
+{
+	return make_uint4((uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16), (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16),
+	                  (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16), (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16));
+}
 
 __device__ __forceinline__ DecImg make_dec(const DecBatch &b, int i, int comp)
 {
@@ -64,6 +79,8 @@ __device__ __forceinline__ DecImg make_dec(const DecBatch &b, int i, int comp)
 	for (int k = 0; k < 8; k++) im.list[k] = reinterpret_cast<uint16_t *>(bytes + DOFF_LISTS) + (size_t)k * 65536;
 	im.hq_list[0] = reinterpret_cast<uint32_t *>(bytes + DOFF_HQ);
 	im.hq_list[1] = im.hq_list[0] + NHW_CAP_HQ_LIST;
+	im.mbits = reinterpret_cast<uint32_t *>(bytes + DOFF_MBITS);
+	im.cmark = reinterpret_cast<uint32_t *>(bytes + DOFF_CMARK) + (size_t)comp * (1 + DEC_CMARK_CAP);
 	im.yuv = b.yuv + (size_t)i * 786432;
 	im.lut = b.lut;
 	return im;
@@ -129,25 +146,56 @@ __global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n, int sp
 	}
 }
 
-// ---- chroma markers 5003..5006 (dec_c_markers_image): every marker only ADDS to cells of the reconstructed
-// LL and clears itself, so cells are independent given atomic adds.  One thread per band cell.
-__global__ void __launch_bounds__(256) kd_c_markers(DecBatch b)
+// ---- chroma markers 5003..5006 (dec_c_markers_image): every marker only ADDS to cells of the reconstructed LL, so
+// they commute (atomic adds).  The inverse scan has already collected them (cmark list) and cleared their cells; a
+// plane with more markers than the list holds is swept instead.  One CTA per plane.
+__device__ __forceinline__ void c_marker_add(int16_t *P, int s, int code)
 {
-	const int img = blockIdx.y >> 1;
-	if (b.status[img] != 0) return;
-	const DecImg im = make_dec(b, img, blockIdx.y & 1);
-	const int r = blockIdx.x, j = threadIdx.x;
-	if (r < 128 && j < 128) return;
-	int16_t *P = im.cproc, *J = im.cjpeg;
-	const int s = r * CW + j, v = J[s];
-	if (v <= 5000) return;
+	const int r = s >> 8, j = s & 255;
 	int t = s;
 	if (r < 128) t -= 128;
 	else t -= 32768 + (j < 128 ? 0 : 128);
-	if (v == 5005) { atomic_add_s16(P + t, -4); atomic_add_s16(P + t + 1, -4); J[s] = 0; }
-	else if (v == 5006) { atomic_add_s16(P + t, 4); atomic_add_s16(P + t + 1, 4); J[s] = 0; }
-	else if (v == 5003) { atomic_add_s16(P + t, -6); J[s] = 0; }
-	else if (v == 5004) { atomic_add_s16(P + t, 6); J[s] = 0; }
+	if (code == 5) { atomic_add_s16(P + t, -4); atomic_add_s16(P + t + 1, -4); }
+	else if (code == 6) { atomic_add_s16(P + t, 4); atomic_add_s16(P + t + 1, 4); }
+	else if (code == 3) atomic_add_s16(P + t, -6);
+	else if (code == 4) atomic_add_s16(P + t, 6);
+}
+__global__ void __launch_bounds__(256) kd_c_markers(DecBatch b)
+{
+	const int img = blockIdx.x >> 1;
+	if (b.status[img] != 0) return;
+	const DecImg im = make_dec(b, img, blockIdx.x & 1);
+	const uint32_t n = im.cmark[0];
+	for (uint32_t k = threadIdx.x; k < n && k < DEC_CMARK_CAP; k += 256) {
+		const uint32_t e = im.cmark[1 + k];
+		c_marker_add(im.cproc, (int)(e & 0xffffffu), (int)(e >> 24));
+	}
+	if (n <= DEC_CMARK_CAP) return;
+	for (int s = threadIdx.x; s < 65536; s += 256) {   // the markers that did not fit stayed in the plane
+		if ((s >> 8) < 128 && (s & 255) < 128) continue;
+		const int v = im.cjpeg[s];
+		if (v > 5000) { c_marker_add(im.cproc, s, v - 5000); im.cjpeg[s] = 0; }
+	}
+}
+
+// ---- chroma LL fill + exw overrides (dec_c_ll_image), one CTA per image: the fills in parallel, the short override
+// lists (U then V, they share a cursor) by one thread
+__global__ void __launch_bounds__(256) kd_c_ll(DecBatch b)
+{
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im0 = make_dec(b, blockIdx.x, 0), im1 = make_dec(b, blockIdx.x, 1);
+	const int bias = im0.d->quality > 15 ? 0 : 1;
+	for (int i = threadIdx.x; i < 8192; i += 256) {
+		const DecImg &im = i < 4096 ? im0 : im1;
+		const int k = i & 4095;
+		im.cjpeg[(k >> 6) * CW + (k & 63)] = (int16_t)(im.res_comp[16384 + i] + bias);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int exw = im0.list_len[10];
+		exw = dec_c_ll_overrides(im0, exw);
+		dec_c_ll_overrides(im1, exw);
+	}
 }
 
 template <typename F>
@@ -216,38 +264,42 @@ __global__ void __launch_bounds__(256) kd_y_markers(DecBatch b)
 	const DecImg im = make_dec(b, blockIdx.x, 0);
 	int16_t *J = im.jpeg, *S = im.aux;
 	int *cand = reinterpret_cast<int *>(im.aux);   // rows 0..127 of the scratch plane (the snapshot uses rows >= 255)
+	const uint32_t *mb = im.mbits;                 // marker bitmap from the inverse scan: 16 words per row
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	auto slot_cells = [&](int slot, int &base, int &n) {
-		if (slot < 256) { base = slot * YW; n = 512; }
-		else if (slot < 512) { base = slot * YW; n = 256; }
-		else { base = (slot - 256) * YW + 256; n = 256; }
+	// slot -> (first bitmap word, words, first cell)
+	auto slot_words = [&](int slot, int &w0, int &nw, int &base) {
+		if (slot < 256) { w0 = slot * 16; nw = 16; base = slot * YW; }
+		else if (slot < 512) { w0 = slot * 16; nw = 8; base = slot * YW; }
+		else { w0 = (slot - 256) * 16 + 8; nw = 8; base = (slot - 256) * YW + 256; }
 	};
 	for (int k = tid; k < 2048; k += 256) { W[k] = 0; A[k] = 0; }
 	if (tid == 0) { first_q = 1 << 30; fallback = 0; }
-	for (int slot = warp; slot < 768; slot += 8) {
-		int base, n, c = 0;
-		slot_cells(slot, base, n);
-		for (int j = lane; j < n; j += 32) c += __popc(__ballot_sync(0xffffffffu, J[base + j] > 1000));
-		if (lane == 0) cnt[slot] = c;
+	for (int slot = tid; slot < 768; slot += 256) {
+		int w0, nw, base, c = 0;
+		slot_words(slot, w0, nw, base);
+		for (int k = 0; k < nw; k++) c += __popc(mb[w0 + k]);
+		cnt[slot] = c;
 	}
 	__syncthreads();
-	if (tid == 0) {
+	if (warp == 0) {   // exclusive prefix over the 768 slots: 24 per lane
 		int run = 0;
-		for (int k = 0; k < 768; k++) { const int v = cnt[k]; cnt[k] = run; run += v; }
-		cnt[768] = run;
-		if (run > MK_CAP) { fallback = 1; dec_y_markers_image(im); }   // never seen; keeps the stage total
+		for (int k = 0; k < 24; k++) run += cnt[lane * 24 + k];
+		int inc = run;
+		for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+		int acc = inc - run;
+		for (int k = 0; k < 24; k++) { const int v = cnt[lane * 24 + k]; cnt[lane * 24 + k] = acc; acc += v; }
+		if (lane == 31) {
+			cnt[768] = inc;
+			if (inc > MK_CAP) { fallback = 1; dec_y_markers_image(im); }   // never seen; keeps the stage total
+		}
 	}
 	__syncthreads();
 	if (fallback) return;
-	for (int slot = warp; slot < 768; slot += 8) {
-		int base, n, o = cnt[slot];
-		slot_cells(slot, base, n);
-		for (int j = lane; j < n; j += 32) {
-			const bool m = J[base + j] > 1000;
-			const uint32_t bal = __ballot_sync(0xffffffffu, m);
-			if (m) cand[o + __popc(bal & ((1u << lane) - 1u))] = base + j;
-			o += __popc(bal);
-		}
+	for (int slot = tid; slot < 768; slot += 256) {
+		int w0, nw, base, o = cnt[slot];
+		slot_words(slot, w0, nw, base);
+		for (int k = 0; k < nw; k++)
+			for (uint32_t m = mb[w0 + k]; m; m &= m - 1) cand[o++] = base + 32 * k + __ffs(m) - 1;
 	}
 	__syncthreads();
 	const int n12 = cnt[512], n3 = cnt[768];
@@ -257,6 +309,7 @@ __global__ void __launch_bounds__(256) kd_y_markers(DecBatch b)
 		for (int k = n1; k < n12; k++) dec_marker_apply(J, cand[k], true, nullptr, nullptr);
 	}
 	__syncthreads();
+	if (im.d->quality >= 23 && n3 == n12) return;   // no right-half markers and no nudges (the rule is off at q23)
 	// snapshot of rows 255..511, columns 256..511, before the right-half markers
 	for (int idx = tid; idx < 257 * 32; idx += 256) {
 		const int r = 255 + (idx >> 5), c8 = (idx & 31) * 8;
@@ -267,20 +320,24 @@ __global__ void __launch_bounds__(256) kd_y_markers(DecBatch b)
 		for (int k = n12; k < n3; k++) dec_marker_apply(J, cand[k], true, W, A);
 	__syncthreads();
 	if (im.d->quality >= 23) return;   // the nudge rule is off at q23 (nhw_decoder.c:588)
-	for (int r = 256 + warp; r < 512; r += 8)
-		for (int j = 257 + lane; j < 511; j += 32) {
-			const int s = r * YW + j;
-			if (dec_dense_qualifies(S, A, s)) atomicMin(&first_q, s);
-		}
-	__syncthreads();
-	const int first = first_q, stale = im.list_len[8];
+	// One pass: every qualifying cell is nudged on its own count.  The reference's count variable is stale at its first
+	// use, so the FIRST qualifying cell (raster order) gets that stale value on top: found with an atomic min here and
+	// looked at again by one thread afterwards (it can only turn a "no" into a "yes").
 	for (int r = 256 + warp; r < 512; r += 8)
 		for (int j = 257 + lane; j < 511; j += 32) {
 			const int s = r * YW + j, k = ((r - 256) << 8) + (j - 256);
 			if (!dec_dense_qualifies(S, A, s)) continue;
-			const int c = dec_dense_count(J, S, s) + (s == first ? stale : 0);
+			atomicMin(&first_q, s);
+			const int c = dec_dense_count(J, S, s);
 			if (c >= 2 && !((W[k >> 5] >> (k & 31)) & 1u)) J[s] += S[s] > 0 ? 1 : -1;
 		}
+	__syncthreads();
+	if (tid == 0 && first_q < (1 << 30)) {
+		// (a nudged cell keeps |v| >= 9, so the neighbours' "< 8" tests read the same before and after any nudge)
+		const int s = first_q, k = (((s >> 9) - 256) << 8) + ((s & 511) - 256);
+		const int c = dec_dense_count(J, S, s);
+		if (c < 2 && c + im.list_len[8] >= 2 && !((W[k >> 5] >> (k & 31)) & 1u)) J[s] += S[s] > 0 ? 1 : -1;
+	}
 }
 
 // ---- D5-D7: LL2 fill in parallel, then the two short override lists
@@ -291,6 +348,29 @@ __global__ void __launch_bounds__(256) kd_y_ll(DecBatch b)
 	for (int i = threadIdx.x; i < 16384; i += 256) im.jpeg[(i >> 7) * YW + (i & 127)] = im.res_comp[i];
 	__syncthreads();
 	if (threadIdx.x == 0) im.list_len[10] = dec_y_ll_overrides(im);
+}
+
+// ---- D14: conditional 5-tap smoothing at the flagged positions (dec_y_smooth_flags_plane).  The targets sit on even
+// rows of the half-synthesised plane, so the only neighbour of a target that can itself be a target is the one on its
+// left in the same row: a run of horizontally adjacent flags is a chain, everything else is independent.  One CTA
+// per image, a thread per run head.
+__global__ void __launch_bounds__(256) kd_smooth_flags(DecBatch b)
+{
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.x, 0);
+	int16_t *J = im.aux;
+	const int n = im.list_len[9];
+	for (int i = threadIdx.x; i < n; i += 256) {
+		const int f = im.flags[i];
+		if (i > 0 && im.flags[i - 1] == f - 1 && (f & 255) != 0) continue;   // not a run head
+		for (int k = i, g = f;;) {
+			const int s = ((g >> 8) << 10) + (g & 255);
+			const int res = dec_lap8(J, s, YW);
+			if (nhw_iabs(res) < 116) J[s] = (int16_t)(((J[s] << 2) + J[s - 1] + J[s + 1] + J[s - YW] + J[s + YW] + 4) >> 3);
+			if (++k >= n || im.flags[k] != g + 1 || ((g + 1) & 255) == 0) break;
+			g++;
+		}
+	}
 }
 
 // ---- D10: residual add-backs (nhw_decoder.c:721-787): commutative += / -= at listed positions
@@ -392,16 +472,49 @@ __global__ void __launch_bounds__(128) kd_descan_y(DecBatch b)
 		o.y = (v.x >> 16) | (v.x << 16);
 	}
 	*reinterpret_cast<uint2 *>(im.jpeg + row * YW + strip * 4) = o;
+	// which cells hold a marker code (> 1000): one bit per cell, 16 words per row, for kd_y_markers
+	const uint32_t nib = ((int16_t)(o.x & 0xffff) > 1000 ? 1u : 0u) | ((int16_t)(o.x >> 16) > 1000 ? 2u : 0u) |
+	                     ((int16_t)(o.y & 0xffff) > 1000 ? 4u : 0u) | ((int16_t)(o.y >> 16) > 1000 ? 8u : 0u);
+	const int lane = strip & 31;
+	const uint32_t word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
+	if ((lane & 7) == 0) im.mbits[row * 16 + (strip >> 3)] = word;
+	if (row == 0 && strip < 2) im.cmark[strip * (1 + DEC_CMARK_CAP)] = 0;   // the chroma marker lists start empty (kd_descan_uv)
 }
-__global__ void __launch_bounds__(64) kd_descan_uv(DecBatch b)
+// Chroma: the stream interleaves U and V, 8-column strips, two rows per step (the second one reversed): a thread takes
+// the 32 coefficients of one (strip, step) -- 64 contiguous bytes -- and writes the four 8-cell runs they hold (U and V,
+// two rows).  A warp = the 32 strips of one step: whole sectors in, whole 512-byte rows out.  Marker codes 5003..5006
+// outside the LL quadrant are not stored: they go to the component's marker list (applied after the level-2
+// synthesis by kd_c_markers) and the cell is cleared, which is what the reference leaves behind.
+__global__ void __launch_bounds__(256) kd_descan_uv(DecBatch b)
 {
 	const int img = blockIdx.y;
 	if (b.status[img] != 0) return;
-	const int row = blockIdx.x, strip = threadIdx.x & 31, v = threadIdx.x >> 5;
-	const DecImg im = make_dec(b, img, v);
-	const int16_t *s = im.uvcoef + v + strip * 4096 + (row >> 1) * 32 + (row & 1) * 16;
-	int16_t *dst = im.cjpeg + row * CW + strip * 8;
-	for (int t = 0; t < 8; t++) dst[(row & 1) ? 7 - t : t] = s[2 * t];
+	const int strip = threadIdx.x & 31, step = blockIdx.x * 8 + (threadIdx.x >> 5);   // step = row pair 0..127
+	const DecImg im0 = make_dec(b, img, 0), im1 = make_dec(b, img, 1);
+	const uint4 *src = reinterpret_cast<const uint4 *>(im0.uvcoef + strip * 4096 + step * 32);
+	int x[32];
+#pragma unroll
+	for (int k = 0; k < 4; k++) unpack8(src[k], x + 8 * k);
+#pragma unroll
+	for (int v = 0; v < 2; v++) {
+		const DecImg &im = v ? im1 : im0;
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			const int row = 2 * step + half;
+			int o[8];
+#pragma unroll
+			for (int t = 0; t < 8; t++) o[half ? 7 - t : t] = x[16 * half + 2 * t + v];
+			if (row >= 128 || strip >= 16) {
+#pragma unroll
+				for (int t = 0; t < 8; t++)
+					if (o[t] > 5000) {
+						const uint32_t at = atomicAdd(im.cmark, 1u);
+						if (at < DEC_CMARK_CAP) { im.cmark[1 + at] = ((uint32_t)(o[t] - 5000) << 24) | (uint32_t)(row * CW + strip * 8 + t); o[t] = 0; }
+					}
+			}
+			*reinterpret_cast<uint4 *>(im.cjpeg + row * CW + strip * 8) = pack8(o);
+		}
+	}
 }
 
 // square transpose of the top-left N x N cells of a plane into another plane (32x32 tiles)
@@ -453,17 +566,6 @@ __device__ __forceinline__ uint32_t map5_then(uint32_t first, uint32_t second)
 	for (int i = 0; i < 5; i++) r |= ((second >> (3 * ((first >> (3 * i)) & 7u))) & 7u) << (3 * i);
 	return r;
 }
-__device__ __forceinline__ void unpack8(const uint4 &w, int *v)
-{
-	v[0] = (int16_t)(w.x & 0xffff); v[1] = (int16_t)(w.x >> 16); v[2] = (int16_t)(w.y & 0xffff); v[3] = (int16_t)(w.y >> 16);
-	v[4] = (int16_t)(w.z & 0xffff); v[5] = (int16_t)(w.z >> 16); v[6] = (int16_t)(w.w & 0xffff); v[7] = (int16_t)(w.w >> 16);
-}
-__device__ __forceinline__ uint4 pack8(const int *v)
-{
-	return make_uint4((uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16), (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16),
-	                  (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16), (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16));
-}
-
 __global__ void __launch_bounds__(128) kd_sharpen_rows(DecBatch b, int n2)
 {
 	const int lane = threadIdx.x & 31, pl = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -763,20 +865,14 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	NHW_LAUNCH_L(c, "d_edge_rows", kd_edge_rows, (n + 3) / 4, 128, 0, b, n);   // D11 + D12
 	NHW_LAUNCH_L(c, "d_inv_rows_t", kd_inv_rows_t, dim3(512 / IRT_ROWS, n), 256, IRT_SMEM, b);   // -> y_aux
 	if (any_hq) NHW_LAUNCH_L(c, "d_hq_addbacks", kd_hq_addbacks, n, 256, 0, b);   // q22 / q23 streams only
-	d_image(c, "d_smooth_flags", b, n, [=] __device__(const DecImg &im, int) { dec_y_smooth_flags_plane(im, im.aux); });
+	NHW_LAUNCH_L(c, "d_smooth_flags", kd_smooth_flags, n, 256, 0, b);
 	// (the second half of the synthesis and the clip are part of the back-end kernel below)
 
 	// ---- chroma
-	NHW_LAUNCH_L(c, "d_descan_uv", kd_descan_uv, dim3(256, n), 64, 0, b);
-	d_image(c, "d_ll_uv", b, n, [=] __device__(const DecImg &im0, int i) {
-		int exw = im0.list_len[10];
-		for (int v = 0; v < 2; v++) {
-			DecImg im = make_dec(b, i, v);
-			exw = dec_c_ll_image(im, v, exw);
-		}
-	});
+	NHW_LAUNCH_L(c, "d_descan_uv", kd_descan_uv, dim3(16, n), 256, 0, b);
+	NHW_LAUNCH_L(c, "d_ll_uv", kd_c_ll, n, 256, 0, b);
 	idwt_rows_cols(c, 2 * n, b.c_jpeg, b.c_aux, b.c_proc, CS, 128, 256);
-	NHW_LAUNCH_L(c, "d_markers_uv", kd_c_markers, dim3(256, 2 * n), 256, 0, b);
+	NHW_LAUNCH_L(c, "d_markers_uv", kd_c_markers, 2 * n, 256, 0, b);
 	NHW_LAUNCH(c, kd_transpose, dim3(4, 4, 2 * n), 256, 0, b.c_proc, b.c_jpeg, CS, CS, 256);
 	idwt_rows_cols(c, 2 * n, b.c_jpeg, b.c_aux, b.c_proc, CS, 256, 256);
 	NHW_LAUNCH_L(c, "d_sharpen_rows", kd_sharpen_rows, (2 * n + 3) / 4, 128, 0, b, 2 * n);
