@@ -102,6 +102,14 @@ NHW_HDN int pack_alphabet(PackState &st, int part, int &select, int &k, int &b)
 
 // Codebook section of the container for one stream (compress_pixel.c:400-461)
 // scratch: 2 x 1024 bytes (the raw list, then its de-interleaved copy); NULL = use the image's list scratch
+// The reference de-interleaves into ONE 580-byte array (compress_pixel.c:58) that it fills for the luma book and then
+// again for the chroma book, and its run-length loop does not stop at the end of the list while it keeps seeing the
+// marker byte (:412-414, :446-448).  So when the chroma list ends on its marker (128), the run goes on into whatever
+// the LUMA list left behind at those positions -- a luma symbol byte 128 there makes the last run one longer (seen on
+// about 1 image in 4000).  `de` therefore persists from part 0 to part 1 (the caller passes the same scratch), is
+// cleared once per image, and the run loop reads on past n.  Beyond the luma list the array is never-written stack
+// memory in the reference; here it reads as 0, like every other such read.
+#define NHW_BOOK_ARRAY 580
 NHW_HDN void pack_codebook(const EncImg &im, const PackState &st, int part, int k, uint8_t *scratch = nullptr)
 {
 	EncHdr *h = im.hdr;
@@ -115,14 +123,14 @@ NHW_HDN void pack_codebook(const EncImg &im, const PackState &st, int part, int 
 		else { raw[n++] = (uint8_t)marker; raw[n++] = (uint8_t)(st.sym[i] >> 8); }
 	}
 	if (part) h->tree_end = n;
+	if (!part) for (int i = 0; i < NHW_BOOK_ARRAY + 4; i++) de[i] = 0;
 	int m = 0;
 	for (int i = 0; i < n; i += 2) de[m++] = raw[i];
 	for (int i = 1; i < n; i += 2) de[m++] = raw[i];
-	de[n] = 0;   // canonical: the byte after the list is not the marker
 	uint8_t *outb = part ? im.codebook2 : im.codebook1;
 	int o = 0, run = 0;
 	for (int i = 0; i < n; i++) {
-		while (i < n && de[i] == marker) { run++; i++; }
+		while (i < NHW_BOOK_ARRAY && de[i] == marker) { run++; i++; }
 		if (run > 0) { outb[o++] = (uint8_t)marker; outb[o++] = (uint8_t)run; run = 0; i--; }
 		else outb[o++] = de[i];
 	}
