@@ -62,27 +62,28 @@ NHW_HD void e8_silence_siblings(int16_t *P, int p)
 // `cursor` models the reference's `count` variable: it is assigned inside some branches only and read, stale, by
 // the q <= 11 tail of the third pass, so it is threaded through all four passes (65536 on entry: the value the
 // LL1 copy / correction loop leaves behind).
-NHW_HDN void y_e8_smooth_image(const EncImg &im, int q)
+// B = the LL2 band (128 x 128) at row stride BS -- the plane itself (BS = 512) or a staged copy; P = the plane, for
+// the descendants (flat plane indices).
+NHW_HDN void y_e8_smooth_band(int16_t *B, int BS, int16_t *P, int q)
 {
-	int16_t *P = im.proc;
 	const E8Thr t = e8_thresholds(q);
 	const bool deep = q <= 11;
 	int cursor = 65536;
 	// pass 1: five-sample windows along each LL2 row
 	for (int r = 0; r < 128; r++)
-		for (int j = 0, s = r * YW; j < 124; j++, s++) {
-			const int v0 = P[s], v1 = P[s + 1], v2 = P[s + 2], v3 = P[s + 3], v4 = P[s + 4];
+		for (int j = 0, s = r * YW, b = r * BS; j < 124; j++, s++, b++) {
+			const int v0 = B[b], v1 = B[b + 1], v2 = B[b + 2], v3 = B[b + 3], v4 = B[b + 4];
 			bool hit = false;
 			if (nhw_iabs(v4 - v0) < t.t1 && nhw_iabs(v4 - v3) < t.t1 && nhw_iabs(v1 - v0) < t.t1 && nhw_iabs(v3 - v1) < t.t1 &&
 			    nhw_iabs(v3 - v2) < t.t2 - 2) {
 				const int up = v3 - v1;             // slope across the middle sample
-				if (up > 5 && v2 >= v3) P[s + 2] = (int16_t)v3;
-				else if (-up > 5 && v2 <= v3) P[s + 2] = (int16_t)v3;
-				else if (-up > 5 && v2 >= v1) P[s + 2] = (int16_t)v1;
-				else if (up > 5 && v2 <= v1) P[s + 2] = (int16_t)v1;
+				if (up > 5 && v2 >= v3) B[b + 2] = (int16_t)v3;
+				else if (-up > 5 && v2 <= v3) B[b + 2] = (int16_t)v3;
+				else if (-up > 5 && v2 >= v1) B[b + 2] = (int16_t)v1;
+				else if (up > 5 && v2 <= v1) B[b + 2] = (int16_t)v1;
 				else if (v3 > v2 && v2 > v1) {}
 				else if (v1 > v2 && v2 > v3) {}
-				else P[s + 2] = (int16_t)((v3 + v1) >> 1);
+				else B[b + 2] = (int16_t)((v3 + v1) >> 1);
 				hit = true;
 			} else if (nhw_iabs(v4 - v0) < t.t2 + 1 && nhw_iabs(v4 - v3) < t.t2 + 1 && nhw_iabs(v1 - v0) < t.t2 + 1) {
 				if (nhw_iabs(v3 - v1) < t.t2 + 6 && nhw_iabs(v3 - v2) < t.t2 + 6)
@@ -91,28 +92,26 @@ NHW_HDN void y_e8_smooth_image(const EncImg &im, int q)
 			if (!hit) continue;
 			for (int k = 1; k < 4; k++) e8_silence_children(P, s + k, t.t6, t.t6 + 6, t.t5);
 			cursor = 4;
-			if (deep) {
+			if (deep)
 				for (int k = 1; k < 4; k++) e8_silence_siblings(P, s + k);
-				cursor = 4;
-			}
 		}
 	// passes 2 and 3: the centre of a plus-shaped neighbourhood becomes the rounded mean of its four arms
 	for (int pass = 0; pass < 2; pass++)
 		for (int r = 0; r < 126; r++)
-			for (int j = 0, s = r * YW; j < 126; j++, s++) {
-				const int up = P[s + 1], dn = P[s + 2 * YW + 1], lf = P[s + YW], rt = P[s + YW + 2], ce = P[s + YW + 1];
+			for (int j = 0, s = r * YW, b = r * BS; j < 126; j++, s++, b++) {
+				const int up = B[b + 1], dn = B[b + 2 * BS + 1], lf = B[b + BS], rt = B[b + BS + 2], ce = B[b + BS + 1];
 				bool outer, inner;
 				if (pass == 0) {
 					outer = nhw_iabs(up - dn) < t.t3 && nhw_iabs(lf - rt) < t.t3;
 					inner = outer && nhw_iabs(ce - lf) < t.t4 - 1 && nhw_iabs(up - ce) < t.t4;
 				} else {
-					outer = nhw_iabs(P[s + 2] - up) < t.t3 && nhw_iabs(up - P[s]) < t.t3 && nhw_iabs(P[s] - lf) < t.t3 &&
-					        nhw_iabs(P[s + 2] - rt) < t.t3;
+					outer = nhw_iabs(B[b + 2] - up) < t.t3 && nhw_iabs(up - B[b]) < t.t3 && nhw_iabs(B[b] - lf) < t.t3 &&
+					        nhw_iabs(B[b + 2] - rt) < t.t3;
 					inner = outer && nhw_iabs(dn - lf) < t.t3 && nhw_iabs(lf - ce) < t.t4;
 				}
 				if (inner) {
 					const int mean = (up + dn + lf + rt + (pass == 0 ? 2 : 1)) >> 2;
-					if (nhw_iabs(mean - lf) < 5 || nhw_iabs(mean - rt) < 5) P[s + YW + 1] = (int16_t)mean;
+					if (nhw_iabs(mean - lf) < 5 || nhw_iabs(mean - rt) < 5) B[b + BS + 1] = (int16_t)mean;
 					cursor = s + YW + 1;
 					e8_silence_children(P, cursor, t.t6, t.t6 + 6, 32);
 				}
@@ -124,14 +123,15 @@ NHW_HDN void y_e8_smooth_image(const EncImg &im, int q)
 	if (!deep) return;
 	// pass 4: three flat samples in a row
 	for (int r = 0; r < 128; r++)
-		for (int j = 0, s = r * YW; j < 126; j++, s++) {
-			const int v0 = P[s], v1 = P[s + 1], v2 = P[s + 2];
+		for (int j = 0, s = r * YW, b = r * BS; j < 126; j++, s++, b++) {
+			const int v0 = B[b], v1 = B[b + 1], v2 = B[b + 2];
 			if (nhw_iabs(v2 - v1) < t.t7 && nhw_iabs(v2 - v0) < t.t7 && nhw_iabs(v1 - v0) < t.t7) {
 				e8_silence_children(P, s + 1, t.t6, t.t6 + 6, 34);
 				e8_silence_siblings(P, s + 1);
 			}
 		}
 }
+NHW_HDN void y_e8_smooth_image(const EncImg &im, int q) { y_e8_smooth_band(im.proc, YW, im.proc, q); }
 
 // ---- E14 below q16.  q14/q15: pointwise.  q <= 13: thresholds chosen from a global count (q <= 12), then three
 // in-place walks that look at the parent sample in the level-2 snapshot (im.ll2s, flat index) and at both
@@ -277,6 +277,61 @@ NHW_HDN void y_offset_quant_lowq_image(const EncImg &im, int m1)
 		if (a < m1 && a > -m1) { P[i] = 128; continue; }
 		P[i] = (int16_t)((a + 128) & 248);
 	}
+}
+
+// Row form of the loop above.  R = the row before the stage (read only), W = where its bytes go (NULL: dry run),
+// next0 = the first cell of the next row before the stage (0 after the last row).  `trade` = the state of the
+// never-restarted cycle when the row starts; the state it leaves is returned.  spill != 0: the row's last cell traded
+// with the NEXT row's first cell (the reference's flat indexing lets it) -- the caller then has to take the image
+// through the serial form.  A row is walked once per possible incoming state (dry) to chain the rows, then once for real.
+NHW_HD int y_offset_quant_lowq_row(const int16_t *R, int16_t *W, int r, int m1, int next0, int trade, int &spill)
+{
+	QuantCycle cyc;
+	cyc.reset();
+	spill = 0;
+	int cur = R[0], prevq = 0;
+	for (int col = 0; col < 512; col++) {
+		const bool inrow = col < 511;
+		int nx = inrow ? (int)R[col + 1] : next0;   // the next cell as it stands; look-ahead rules of this cell rewrite it
+		int a = cur, outv = -1;
+		if (a > 10000) {
+			outv = a == 10100 ? 128 : a == 12700 ? 127 : a == 12900 ? 129 : a == 10204 ? 125 : a == 10300 ? 126 : a == 12100 ? 121 : a == 12200 ? 122 : -1;
+		}
+		if (outv < 0 && a > 127) { const int k = ((a & 0xfff8) - 128) >> 3; outv = NHW_EXTRA1(k > 18 ? 18 : k); }
+		else if (outv < 0 && a < -127) { const int k = (((-a) & 0xfff8) - 128) >> 3; outv = NHW_EXTRA2(k > 18 ? 18 : k); }
+		if (outv < 0) {
+			if (a < -12 && ((-a) & 7) == 6) { if (inrow && nx == -7) nx = -9; }
+			if (a < 0) {
+				if (a == -7 && nx == 8 && inrow) a = -8;
+				a = -a;
+				if (a > 14 && (a & 7) == 7 && nx > 0 && nx < 8) a -= 2;
+				a = -cyc.cut(a, 504);
+			} else if (a == 8 && nx == -7 && inrow) nx = -8;
+			else if (a > 12 && (a & 7) >= 6) { if (inrow && nx == 7) nx = 9; }
+			if (a >= 14 && nx >= 14 && (r >= 256 || col >= 256)) {
+				if (((a & 510) & 7) == 6 && ((nx & 510) & 7) == 6 && ((a & 1) || (nx & 1))) {
+					auto blocks = [](int v) { return (v < -2 && v > -8) || (v < -7 && ((-v) & 7) >= 6); };
+					bool bl = false, br = false;
+					if (col > 0 && col < 510) { bl = blocks(prevq); br = blocks(R[col + 2]); }
+					if (trade == 0) {
+						const bool same_step = (a & 504) == (nx & 504);
+						const bool first = same_step ? a >= nx : a <= nx;
+						int d = 0;
+						if (first) { if (!bl) { a += 2; d = -2; } }
+						else if (!br) d = 2;
+						nx += d;
+						if (!inrow) spill = d;
+					}
+					trade = trade == 2 ? 0 : trade + 1;
+				}
+			}
+			outv = (a < m1 && a > -m1) ? 128 : ((a + 128) & 248);
+		}
+		if (W) W[col] = (int16_t)outv;
+		prevq = outv;
+		cur = nx;
+	}
+	return trade;
 }
 
 // ---- chroma pre-filter (pre_processing_UV): 8-neighbour Laplacian of the un-filtered plane nudges the sample

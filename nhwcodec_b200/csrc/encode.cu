@@ -1556,6 +1556,21 @@ __global__ void __launch_bounds__(256) k_write_stream(EncBatch b, int n, uint8_t
 	}
 }
 
+// ---- E8 (q <= 12, enc_lowq.cuh: y_e8_smooth_band): a raster-serial walk over the 128 x 128 LL2 band, one WARP per
+// image: the band is staged in shared memory (coalesced), lane 0 walks it at shared-memory latency (the descendants it
+// silences are sparse writes to the plane), the warp writes the band back.
+__global__ void __launch_bounds__(32) k_e8_staged(EncBatch b, int q)
+{
+	__shared__ __align__(16) int16_t band[128 * 128];
+	const EncImg im = make_img(b, blockIdx.x, 0);
+	const int lane = threadIdx.x;
+	for (int k = lane; k < 128 * 16; k += 32) reinterpret_cast<uint4 *>(band)[k] = *reinterpret_cast<const uint4 *>(im.proc + (k >> 4) * YW + (k & 15) * 8);
+	__syncwarp();
+	if (lane == 0) y_e8_smooth_band(band, 128, im.proc, q);
+	__syncwarp();
+	for (int k = lane; k < 128 * 16; k += 32) *reinterpret_cast<uint4 *>(im.proc + (k >> 4) * YW + (k & 15) * 8) = reinterpret_cast<const uint4 *>(band)[k];
+}
+
 // ---- isolated-coefficient shrink at q <= 16 (enc_lowq.cuh: y_recons_shrink_lowq_cell): one CTA per image, thread =
 // column, rows top to bottom with a barrier per row
 __global__ void __launch_bounds__(256) k_recons_shrink_lowq(EncBatch b)
@@ -1679,7 +1694,7 @@ static void encode_luma_lowq(nhw_ctx *c, const EncBatch &b, int n, int q, int ra
 		dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
 	}
 	if (q <= 11) run_rows(c, "y_e7_kill", b, n, 128, [=] __device__(const EncImg &im, int r) { y_e7_kill_row(im, q, ratio, 128 + r); });
-	if (q < 13) run_image(c, "y_e8_smooth", b, n, [=] __device__(const EncImg &im, int) { y_e8_smooth_image(im, q); });
+	if (q < 13) NHW_LAUNCH_L(c, "y_e8_smooth", k_e8_staged, n, 32, 0, b, q);
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
 	NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
 	if (q > 12) {   // second reconstruction
@@ -1699,7 +1714,34 @@ static void encode_luma_lowq(nhw_ctx *c, const EncBatch &b, int n, int q, int ra
 	NHW_LAUNCH_L(c, "y_e19_restore", k_e19_restore, dim3(8, n), 256, 0, b);
 	NHW_LAUNCH_L(c, "y_e20_cleanup", k_e20_bands, dim3(3, n), 256, 0, b, q, ratio);
 	run_groups_inplace(c, "y_offset_mult8", b, n, 512, 6, [=] __device__(const EncImg &im, int r, int g, int *o) { return y_offset_mult8_cells(im.proc, r, g, o); });
-	run_image(c, "y_offset_quant_lowq", b, n, [=] __device__(const EncImg &im, int) { y_offset_quant_lowq_image(im, ratio); });
+	// offsetY's byte loop at q <= 16 (enc_lowq.cuh): rows are independent except for a three-state cycle that is never
+	// restarted.  Every row is walked dry for each state it could start in, one thread per image chains the rows, then
+	// the rows are walked for real.  Scratch (im.tmp1): next0[512] int16 | out-state / spill per (row, state) | in-state per row | flag
+	run_rows(c, "y_offq_dry", b, n, 512, [=] __device__(const EncImg &im, int r) {
+		int16_t *next0 = reinterpret_cast<int16_t *>(im.tmp1);
+		uint8_t *res = im.tmp1 + 1024;
+		const int nx = r < 511 ? im.proc[(r + 1) * YW] : 0;
+		next0[r] = (int16_t)nx;
+		for (int t = 0; t < 3; t++) {
+			int spill;
+			const int o = y_offset_quant_lowq_row(im.proc + r * YW, nullptr, r, ratio, nx, t, spill);
+			res[r * 3 + t] = (uint8_t)(o | (spill ? 4 : 0));
+		}
+	});
+	run_image(c, "y_offq_chain", b, n, [=] __device__(const EncImg &im, int) {
+		const uint8_t *res = im.tmp1 + 1024;
+		uint8_t *in_state = im.tmp1 + 4096;
+		int state = 0, spilled = 0;
+		for (int r = 0; r < 512; r++) { in_state[r] = (uint8_t)state; const int v = res[r * 3 + state]; spilled |= v & 4; state = v & 3; }
+		in_state[512] = (uint8_t)(spilled ? 1 : 0);   // a row traded with the next row's first cell: serial form for this image
+	});
+	run_rows(c, "y_offq_commit", b, n, 512, [=] __device__(const EncImg &im, int r) {
+		const uint8_t *in_state = im.tmp1 + 4096;
+		if (in_state[512]) return;
+		int spill;
+		y_offset_quant_lowq_row(im.proc + r * YW, im.proc + r * YW, r, ratio, reinterpret_cast<const int16_t *>(im.tmp1)[r], in_state[r], spill);
+	});
+	run_image(c, "y_offq_serial", b, n, [=] __device__(const EncImg &im, int) { if (im.tmp1[4096 + 512]) y_offset_quant_lowq_image(im, ratio); });
 	run_rows(c, "y_scan_strips", b, n, 128, [=] __device__(const EncImg &im, int s) { y_scan_strip(im, s); });
 	NHW_LAUNCH_L(c, "y_peephole", k_peephole, n, PEEP_THREADS, 262144 / 8, b);
 }

@@ -253,19 +253,112 @@ __global__ void __launch_bounds__(256) k_pre_nudge(const int16_t *__restrict__ k
 // =====================================================================================
 // q <= 16
 // =====================================================================================
-// luma pre-sharpening state machine (pre_lowq.cuh): one walker per image.  The walks branch on data at every pair, so
-// a warp only carries PRE_LOW_WALKERS images (one active lane in every 32 / PRE_LOW_WALKERS): divergence costs a warp
-// every path its lanes take, and the many more warps hide each other's memory latency.
-#define PRE_LOW_WALKERS 4
-__global__ void __launch_bounds__(128) k_pre_lowq(int16_t *__restrict__ y, size_t ystride, int16_t *__restrict__ copy,
-                                                  int16_t *__restrict__ kern, int16_t *__restrict__ marks, size_t astride, int n, int q)
+// luma pre-sharpening state machine (pre_lowq.cuh).  Walk A's kernel values are the q > 16 recurrence and come from the
+// scan kernels above (k_pre_energy / k_pre_chain / k_pre_apply); what is left is raster-serial per image and runs one
+// WARP per image: lane 0 walks, all lanes stage the rows it walks through shared memory (coalesced 16-byte loads and
+// stores), so the walker never waits for global memory, and the parts that are parallel inside an image (the q <= 14
+// smoothing of a row, walk D's rows) use all lanes.
+//   events : bitmap of the pixels walk A's marker rules have to look at (pre_low_is_event), one bit per pixel
+//   walk   : marker rules over the event pixels -> walk B row by row -> walk C on a two-row window -> walk D
+#define PLW_WARPS 4
+__global__ void __launch_bounds__(256) k_pre_low_events(const int16_t *__restrict__ kern, size_t kstride, uint32_t *__restrict__ bits,
+                                                        size_t bstride, int s2)
 {
-	const int group = 32 / PRE_LOW_WALKERS;
-	if (threadIdx.x % group) return;
-	const int img = (blockIdx.x * 128 + threadIdx.x) / group;
+	const int s = blockIdx.x * 256 + threadIdx.x, r = s >> 9, j = s & 511;
+	const bool ev = r >= 1 && r <= 510 && j >= 1 && j <= 510 && pre_low_is_event(kern[(size_t)blockIdx.y * kstride + s], s2);
+	const uint32_t m = __ballot_sync(0xffffffffu, ev);
+	if ((threadIdx.x & 31) == 0) bits[(size_t)blockIdx.y * bstride + (s >> 5)] = m;
+}
+
+__global__ void __launch_bounds__(32 * PLW_WARPS) k_pre_low_walk(int16_t *__restrict__ y, size_t ystride, const int16_t *__restrict__ copy,
+                                                                   int16_t *__restrict__ kern, int16_t *__restrict__ marks, size_t astride,
+                                                                   int n, int q)
+{
+	__shared__ __align__(16) int16_t sYa[PLW_WARPS][2 * PW], sKa[PLW_WARPS][2 * PW];
+	__shared__ __align__(16) uint8_t sMa[PLW_WARPS][2 * PW];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, img = blockIdx.x * PLW_WARPS + warp;
 	if (img >= n) return;
-	pre_low_image(y + (size_t)img * ystride, copy + (size_t)img * astride, kern + (size_t)img * astride,
-	              reinterpret_cast<uint8_t *>(marks + (size_t)img * astride), q);
+	int16_t *Y = y + (size_t)img * ystride, *K = kern + (size_t)img * astride;
+	const int16_t *O = copy + (size_t)img * astride;
+	uint8_t *M = reinterpret_cast<uint8_t *>(marks + (size_t)img * astride);
+	const uint32_t *bits = reinterpret_cast<const uint32_t *>(M + PW * PW);
+	int16_t *sY = sYa[warp], *sK = sKa[warp];
+	uint8_t *sM = sMa[warp];
+	const PreLowParams p = pre_low_params(q);
+	// rows move between the plane and the window as 32 lanes x 16 cells (int16: two 16-byte words, marks: one)
+	auto load_row16 = [&](int16_t *dst, const int16_t *src) {
+		reinterpret_cast<uint4 *>(dst)[2 * lane] = reinterpret_cast<const uint4 *>(src)[2 * lane];
+		reinterpret_cast<uint4 *>(dst)[2 * lane + 1] = reinterpret_cast<const uint4 *>(src)[2 * lane + 1];
+	};
+	auto load_row8 = [&](uint8_t *dst, const uint8_t *src) { reinterpret_cast<uint4 *>(dst)[lane] = reinterpret_cast<const uint4 *>(src)[lane]; };
+
+	// ---- walk A, marker rules: the event pixels in raster order
+	{
+		PreWalkA w = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+		for (int w0 = 0; w0 < PW * PW / 32; w0 += 32) {
+			const uint32_t mine = bits[w0 + lane];
+			uint32_t any = __ballot_sync(0xffffffffu, mine != 0);
+			while (any) {
+				const int src = __ffs(any) - 1;
+				any &= any - 1;
+				uint32_t m = __shfl_sync(0xffffffffu, mine, src);
+				if (lane == 0)
+					for (; m; m &= m - 1) {
+						const int s = 32 * (w0 + src) + __ffs(m) - 1;
+						pre_low_event(w, p, O, K, s, s & 511);
+					}
+			}
+		}
+		__syncwarp();
+	}
+	// ---- walk B, row by row through the window's second row
+	{
+		PairThrottle t;
+		t.init();
+		int a = 0;
+		for (int r = 1; r < 511; r++) {
+			load_row16(sY + PW, Y + r * PW);
+			load_row16(sK + PW, K + r * PW);
+			reinterpret_cast<uint4 *>(sM + PW)[lane] = make_uint4(0, 0, 0, 0);
+			__syncwarp();
+			if (p.smooth_on) {
+				for (int k = 0; k < 16; k++) {
+					const int j = 16 * lane + k;
+					int v;
+					if (j >= 1 && j <= 510 && pre_low_smooth_cell(O, r * PW + j, sK[PW + j], p, v)) sY[PW + j] = (int16_t)v;
+				}
+				__syncwarp();
+			}
+			if (lane == 0) pre_low_walk_b_row(t, a, p, r, sY + PW, sK + PW, sM + PW);
+			__syncwarp();
+			load_row16(Y + r * PW, sY + PW);
+			load_row16(K + r * PW, sK + PW);
+			load_row8(M + r * PW, sM + PW);
+			__syncwarp();
+		}
+	}
+	// ---- walk C on the two-row window (rows r - 1, r)
+	{
+		PreWalkC w = {0, 0, 0, 0, 0, 0};
+		for (int r = 1; r < 511; r++) {
+			for (int h = 0; h < 2; h++) {
+				load_row16(sY + h * PW, Y + (r - 1 + h) * PW);
+				load_row16(sK + h * PW, K + (r - 1 + h) * PW);
+				load_row8(sM + h * PW, M + (r - 1 + h) * PW);
+			}
+			__syncwarp();
+			if (lane == 0) pre_low_walk_c_row(w, p, r, sY, sK, sM);
+			__syncwarp();
+			for (int h = 0; h < 2; h++) {
+				load_row16(Y + (r - 1 + h) * PW, sY + h * PW);
+				load_row8(M + (r - 1 + h) * PW, sM + h * PW);
+			}
+			load_row16(K + r * PW, sK + PW);   // the row above is only read
+			__syncwarp();
+		}
+	}
+	// ---- walk D: rows are independent
+	for (int r = 1 + lane; r < 511; r += 32) pre_low_walk_d_row(Y, K, M, p, r);
 }
 
 // chroma pre-filter (pre_processing_UV, q <= 14): 4:2:0 bytes -> int16 plane with the +-1 / +-2 nudges applied
@@ -293,9 +386,24 @@ namespace nhw {
 
 void pre_processing_lowq(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystride)
 {
-	const int per_cta = 128 / (32 / PRE_LOW_WALKERS);
-	NHW_LAUNCH_L(c, "k_pre_lowq", k_pre_lowq, (n + per_cta - 1) / per_cta, 128, 0, y, ystride, c->y_proc + NHW_GUARD_S,
-	             c->y_aux + NHW_GUARD_S, c->y_aux2 + NHW_GUARD_S, (size_t)NHW_Y_SLOT, n, quality);
+	const size_t AS = NHW_Y_SLOT;
+	int16_t *copy = c->y_proc + NHW_GUARD_S, *kern = c->y_aux + NHW_GUARD_S, *scratch = c->y_aux2 + NHW_GUARD_S;
+	const PreLowParams p = pre_low_params(quality);
+	// plain kernel values (the remainder chain as a scan): scratch = signed energies, kern = values.  Rows 0 and 511 of
+	// the kernel plane are outside every walk's writes but inside their reads: zero.
+	dim3 grid((510 + PRE_WARPS - 1) / PRE_WARPS, n);
+	NHW_LAUNCH(c, k_pre_energy, grid, 32 * PRE_WARPS, 0, y, scratch, c->rowmap, ystride, AS);
+	NHW_LAUNCH(c, k_pre_chain, (n + 63) / 64, 64, 0, c->rowmap, c->rowcarry, n);
+	NHW_LAUNCH(c, k_pre_apply, grid, 32 * PRE_WARPS, 0, scratch, c->rowcarry, kern, AS);
+	cudaMemset2DAsync(kern, AS * 2, 0, PW * 2, n, c->stream);
+	cudaMemset2DAsync(kern + 511 * PW, AS * 2, 0, PW * 2, n, c->stream);
+	// the plane as it was (walk A's Laplacians and the smoothing read it while walk B rewrites the plane), the marks
+	cudaMemcpy2DAsync(copy, AS * 2, y, ystride * 2, (size_t)PW * PW * 2, n, cudaMemcpyDeviceToDevice, c->stream);
+	cudaMemset2DAsync(scratch, AS * 2, 0, PW * PW, n, c->stream);
+	uint32_t *bits = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(scratch) + PW * PW);
+	NHW_LAUNCH(c, k_pre_low_events, dim3(PW * PW / 256, n), 256, 0, kern, AS, bits, AS / 2, p.sharp2);
+	NHW_LAUNCH_L(c, "k_pre_low_walk", k_pre_low_walk, (n + PLW_WARPS - 1) / PLW_WARPS, 32 * PLW_WARPS, 0, y, ystride, copy, kern, scratch,
+	             AS, n, quality);
 }
 
 void chroma_pre_uv(nhw_ctx *c, int n_planes, int quality, const uint8_t *uv, int16_t *out, size_t oslot)

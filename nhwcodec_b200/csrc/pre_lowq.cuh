@@ -58,57 +58,85 @@ NHW_HD int pre_lap(const int16_t *O, int s, int &sad)
 	return d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;
 }
 
-NHW_HDN void pre_low_walk_a(const int16_t *O, int16_t *K, const PreLowParams &p)
+// Walk A in two parts.  (1) The plain kernel values: sign(lap) * ((15 |lap| + sad + carry) >> 4) with the carried
+// remainder -- the q > 16 recurrence, which the CUDA path evaluates as a scan (front.cu: k_pre_energy / k_pre_chain /
+// k_pre_apply); this serial form is the host harness's.  (2) The marker rules: they only look at a pixel whose plain
+// value satisfies pre_low_is_event, at its Laplacian, and at the left neighbour's CURRENT kernel value, and they never
+// touch the remainder chain -- so they run as a walk over those pixels only, in raster order (pre_low_event).
+NHW_HDN void pre_low_kernel_plane(const int16_t *O, int16_t *K)
 {
-	PreWalkA w = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-	const int s2 = p.sharp2, half = p.sharp >> 1;
+	int carry = 0;
 	for (int r = 1; r < 511; r++)
 		for (int j = 1, s = r * PW + 1; j < 511; j++, s++) {
 			int sad;
 			const int lap = pre_lap(O, s, sad);
-			if (lap == 0) { K[s] = 0; w.carry = 0; continue; }
-			const int mag = nhw_iabs(lap);
-			const int acc = 15 * mag + sad + ((w.carry + 2) >> 2);
-			w.carry = acc & 15;
-			int k = acc >> 4;                       // magnitude of the kernel value
-			const int left = j > 1 ? K[s - 1] : 0;
-			if (lap < 0) {
-				if (k == s2 && w.edge_bumps < 3) { k = s2 + 1; w.edge_bumps++; }
-				int out = -k;
-				if (mag <= s2 && k > s2 && k <= s2 + 20) {   // crossed the threshold through the carried remainder only
-					if (j > 1 && nhw_iabs(left) <= half) w.neg_phase = 0;
-					if (w.neg_phase == 0) { out = -20000; w.neg_phase = 1; }
-					else if (w.neg_skip == 0) { w.neg_phase = 0; w.neg_skip = 1; }
-					else if (w.neg_phase == 1) w.neg_phase = 2;
-					else { w.neg_phase = 0; w.neg_skip = w.neg_skip == 3 ? 0 : w.neg_skip + 1; }
-				}
-				K[s] = (int16_t)out;
-			} else {
-				int out = k;
-				if (mag <= s2 && k > s2 && k <= s2 + 20) {
-					auto toggle = [&]() {
-						if (!w.alt) { w.pos_phase = 0; if (!w.pos_skip) w.pos_skip = 1; w.alt = 1; }
-						else w.alt = 0;
-					};
-					if (j > 1) {
-						if (nhw_iabs(left) <= half) w.pos_phase = 0;
-						else if (nhw_iabs(left) > 10000 || left == s2 + 21) toggle();
-						else if (left == -(s2 + 21)) {
-							if (!w.alt2) w.alt2 = 1;
-							else { toggle(); w.alt2 = w.alt2 == 1 ? 2 : 0; }
-						} else if (left == s2 + 22) K[s - 1] = 7000;
-					}
-					if (w.pos_phase == 0) { out = 20000; w.pos_phase = 1; }
-					else if (w.pos_skip == 0) { w.pos_phase = 0; w.pos_skip = 1; }
-					else if (w.pos_phase == 1) w.pos_phase = 2;
-					else { w.pos_phase = 0; w.pos_skip = w.pos_skip == 3 ? 0 : w.pos_skip + 1; }
-				} else if (k == s2 + 21) {
-					if (w.first21 == 0) out = 7000;
-					w.first21++;
-				}
-				K[s] = (int16_t)out;
-			}
+			if (lap == 0) { K[s] = 0; carry = 0; continue; }
+			const int acc = 15 * nhw_iabs(lap) + sad + ((carry + 2) >> 2);
+			carry = acc & 15;
+			K[s] = (int16_t)(lap < 0 ? -(acc >> 4) : (acc >> 4));
 		}
+}
+
+NHW_HD bool pre_low_is_event(int kv, int s2)
+{
+	const int k = nhw_iabs(kv);
+	return (k > s2 && k <= s2 + 20) || kv == s2 + 21 || kv == -s2;
+}
+
+// pixel s (column j) holds the plain kernel value K[s] and pre_low_is_event says yes
+NHW_HD void pre_low_event(PreWalkA &w, const PreLowParams &p, const int16_t *O, int16_t *K, int s, int j)
+{
+	const int s2 = p.sharp2, half = p.sharp >> 1;
+	int sad;
+	const int lap = pre_lap(O, s, sad);
+	const int mag = nhw_iabs(lap);
+	int k = nhw_iabs(K[s]);
+	const int left = j > 1 ? K[s - 1] : 0;
+	if (lap < 0) {
+		if (k == s2 && w.edge_bumps < 3) { k = s2 + 1; w.edge_bumps++; }
+		int out = -k;
+		if (mag <= s2 && k > s2 && k <= s2 + 20) {   // crossed the threshold through the carried remainder only
+			if (j > 1 && nhw_iabs(left) <= half) w.neg_phase = 0;
+			if (w.neg_phase == 0) { out = -20000; w.neg_phase = 1; }
+			else if (w.neg_skip == 0) { w.neg_phase = 0; w.neg_skip = 1; }
+			else if (w.neg_phase == 1) w.neg_phase = 2;
+			else { w.neg_phase = 0; w.neg_skip = w.neg_skip == 3 ? 0 : w.neg_skip + 1; }
+		}
+		K[s] = (int16_t)out;
+	} else if (lap > 0) {
+		int out = k;
+		if (mag <= s2 && k > s2 && k <= s2 + 20) {
+			auto toggle = [&]() {
+				if (!w.alt) { w.pos_phase = 0; if (!w.pos_skip) w.pos_skip = 1; w.alt = 1; }
+				else w.alt = 0;
+			};
+			if (j > 1) {
+				if (nhw_iabs(left) <= half) w.pos_phase = 0;
+				else if (nhw_iabs(left) > 10000 || left == s2 + 21) toggle();
+				else if (left == -(s2 + 21)) {
+					if (!w.alt2) w.alt2 = 1;
+					else { toggle(); w.alt2 = w.alt2 == 1 ? 2 : 0; }
+				} else if (left == s2 + 22) K[s - 1] = 7000;
+			}
+			if (w.pos_phase == 0) { out = 20000; w.pos_phase = 1; }
+			else if (w.pos_skip == 0) { w.pos_phase = 0; w.pos_skip = 1; }
+			else if (w.pos_phase == 1) w.pos_phase = 2;
+			else { w.pos_phase = 0; w.pos_skip = w.pos_skip == 3 ? 0 : w.pos_skip + 1; }
+		} else if (k == s2 + 21) {
+			if (w.first21 == 0) out = 7000;
+			w.first21++;
+		}
+		K[s] = (int16_t)out;
+	}
+}
+
+NHW_HDN void pre_low_walk_a(const int16_t *O, int16_t *K, const PreLowParams &p)
+{
+	PreWalkA w = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	pre_low_kernel_plane(O, K);
+	for (int r = 1; r < 511; r++)
+		for (int j = 1, s = r * PW + 1; j < 511; j++, s++)
+			if (pre_low_is_event(K[s], p.sharp2)) pre_low_event(w, p, O, K, s, j);
 }
 
 // ---- walk B: the throttle ---------------------------------------------------------------------------------------
@@ -401,53 +429,67 @@ NHW_HD void throttle_pair(PairThrottle &t, const PreLowParams &p, int row, int &
 	if (n[1] > 15 && n[1] < 1000000) { n[1] = 0; n[4] = 0; n[29]++; }
 }
 
+// the q <= 14 smoothing of walk B for one pixel: O = the plane before the stage, kv = the pixel's kernel value after
+// walk A.  Pointwise (it reads O only), so it is applied to a whole row before the row's pairs are walked.
+NHW_HD bool pre_low_smooth_cell(const int16_t *O, int at, int kv, const PreLowParams &p, int &out)
+{
+	if (!(nhw_iabs(kv) > 4 && nhw_iabs(kv) < p.smooth_below)) return false;
+	const int up = O[at - PW], lf = O[at - 1], dn = O[at + PW], rt = O[at + 1];
+	if (!(nhw_iabs(up - lf) < 4 && nhw_iabs(lf - dn) < 4 && nhw_iabs(dn - rt) < 4 && nhw_iabs(rt - up) < 4)) return false;
+	out = ((O[at] << 2) + lf + rt + up + dn + 4) >> 3;
+	return true;
+}
+
+// One row of walk B.  Yr, Kr, Mr point at column 0 of the row (the plane itself or a staged copy); the row's smoothing
+// has been applied to Yr already.  `a` = the mid-range rule's one-pair memory, carried from row to row like the throttle.
+NHW_HD void pre_low_walk_b_row(PairThrottle &t, int &a, const PreLowParams &p, int r, int16_t *Yr, int16_t *Kr, uint8_t *Mr)
+{
+	const int sh = p.sharp;
+	for (int j = 1; j < 510; j += 2) {
+		// the pair is columns (j, j + 1)
+		int kA = Kr[j], kB = Kr[j + 1];
+		throttle_pair(t, p, r, kA, kB, Yr[j], Yr[j + 1], Kr[j], Kr[j + 1]);
+		// opposite-sign pair just above the threshold: push them apart, and remember which way (M)
+		if (nhw_iabs(kA) > sh && nhw_iabs(kA) <= sh + 20 && nhw_iabs(kB) > sh && nhw_iabs(kB) <= sh + 20) {
+			if (kA > 0 && kB < 0) { Yr[j]++; Yr[j + 1]--; Mr[j] = 2; Mr[j + 1] = 3; }
+			else if (kA < 0 && kB > 0) { Yr[j]--; Yr[j + 1]++; Mr[j] = 3; Mr[j + 1] = 2; }
+		}
+		if (p.midrange_on) {
+			// the 10..32 / >= 23 rule of the q > 16 path, without its 176 / 201 part
+			int d0 = 0, d1 = 0;
+			const int ar = nhw_iabs(kA), ac = nhw_iabs(kB);
+			if (ar > 10 && ar < 32 && ac >= 23) {
+				const int sg = kA > 0 ? 1 : -1;
+				if (ar < 16) { if (kB * sg > 0 && ac < 32 && ar > 11) d1 = sg; d0 = sg; }
+				else d0 = a ? sg : 2 * sg;
+				a = 0;
+			} else {
+				a = 0;
+				if (ac > 10 && ac < 32 && ar >= 23) {
+					const int sg = kB > 0 ? 1 : -1;
+					if (ac < 16) { if (kA * sg > 0 && ar < 32 && ac > 11) d0 = sg; d1 = sg; }
+					else { d1 = 2 * sg; a = 1; }
+				}
+			}
+			Yr[j] = (int16_t)(Yr[j] + d0);
+			Yr[j + 1] = (int16_t)(Yr[j + 1] + d1);
+		}
+	}
+}
+
 NHW_HDN void pre_low_walk_b(int16_t *Y, const int16_t *O, int16_t *K, uint8_t *M, const PreLowParams &p)
 {
 	PairThrottle t;
 	t.init();
-	int a = 0;   // the mid-range rule's one-pair memory (pre_core.cuh: pair_flag)
-	for (int r = 1; r < 511; r++)
-		for (int j = 1, s = r * PW + 2; j < 510; j += 2, s += 2) {
-			// the pair is (s - 1, s): columns j and j + 1
-			int kA = K[s - 1], kB = K[s];
-			if (p.smooth_on) {
-				for (int side = 0; side < 2; side++) {
-					const int at = s - 1 + side, kv = side ? kB : kA;
-					if (nhw_iabs(kv) > 4 && nhw_iabs(kv) < p.smooth_below) {
-						const int up = O[at - PW], lf = O[at - 1], dn = O[at + PW], rt = O[at + 1];
-						if (nhw_iabs(up - lf) < 4 && nhw_iabs(lf - dn) < 4 && nhw_iabs(dn - rt) < 4 && nhw_iabs(rt - up) < 4)
-							Y[at] = (int16_t)(((O[at] << 2) + lf + rt + up + dn + 4) >> 3);
-					}
-				}
+	int a = 0;
+	for (int r = 1; r < 511; r++) {
+		if (p.smooth_on)
+			for (int j = 1; j < 511; j++) {
+				int v;
+				if (pre_low_smooth_cell(O, r * PW + j, K[r * PW + j], p, v)) Y[r * PW + j] = (int16_t)v;
 			}
-			throttle_pair(t, p, r, kA, kB, Y[s - 1], Y[s], K[s - 1], K[s]);
-			// opposite-sign pair just above the threshold: push them apart, and remember which way (M)
-			const int sh = p.sharp;
-			if (nhw_iabs(kA) > sh && nhw_iabs(kA) <= sh + 20 && nhw_iabs(kB) > sh && nhw_iabs(kB) <= sh + 20) {
-				if (kA > 0 && kB < 0) { Y[s - 1]++; Y[s]--; M[s - 1] = 2; M[s] = 3; }
-				else if (kA < 0 && kB > 0) { Y[s - 1]--; Y[s]++; M[s - 1] = 3; M[s] = 2; }
-			}
-			if (p.midrange_on) {
-				// the 10..32 / >= 23 rule of the q > 16 path, without its 176 / 201 part
-				int d0 = 0, d1 = 0;
-				const int ar = nhw_iabs(kA), ac = nhw_iabs(kB);
-				if (ar > 10 && ar < 32 && ac >= 23) {
-					const int sg = kA > 0 ? 1 : -1;
-					if (ar < 16) { if (kB * sg > 0 && ac < 32 && ar > 11) d1 = sg; d0 = sg; }
-					else d0 = a ? sg : 2 * sg;
-					a = 0;
-				} else {
-					a = 0;
-					if (ac > 10 && ac < 32 && ar >= 23) {
-						const int sg = kB > 0 ? 1 : -1;
-						if (ac < 16) { if (kA * sg > 0 && ar < 32 && ac > 11) d0 = sg; d1 = sg; }
-						else { d1 = 2 * sg; a = 1; }
-					}
-				}
-				Y[s - 1] = (int16_t)(Y[s - 1] + d0);
-				Y[s] = (int16_t)(Y[s] + d1);
-			}
-		}
+		pre_low_walk_b_row(t, a, p, r, Y + r * PW, K + r * PW, M + r * PW);
+	}
 }
 
 // ---- walk C -----------------------------------------------------------------------------------------------------
@@ -465,73 +507,77 @@ NHW_HD void walk_c_resolve(int16_t &cell, int v, int &pos_cycle, int &neg_cycle,
 	} else if (v == 7000) cell = (int16_t)(s2 + 22);
 }
 
+// One row of walk C.  Y, K, M point at column 0 of row r - 1 of a window that holds rows r - 1 and r back to back
+// (the plane itself, or a staged copy of the two rows): every cell the row can touch lies in that window.
+NHW_HD void pre_low_walk_c_row(PreWalkC &w, const PreLowParams &p, int r, int16_t *Y, int16_t *K, uint8_t *M)
+{
+	const int sh = p.sharp, s2 = p.sharp2;
+	auto touch = [&](int at, int d) { Y[at] = (int16_t)(Y[at] + d); M[at] = 1; };
+	int misses = 0, back = 0, fresh = 0;     // per-row cursor state (e, t, f)
+	for (int j = 1, s = PW + 1; j < 509; j++, s++) {
+		int kA = K[s];
+		j++; s++;
+		int kB = K[s];
+		if (nhw_iabs(kA) > 6000) {
+			walk_c_resolve(K[s - 1], kA, w.pa, w.na, s2);
+			if (!w.gate) { walk_c_resolve(K[s], kB, w.pb, w.nb, s2); w.gate = 1; }
+			else w.gate = 0;
+			if (!w.skip_first) { w.skip_first = 1; continue; }
+			w.skip_first = 0;
+		} else if (nhw_iabs(kB) > 6000) {
+			walk_c_resolve(K[s], kB, w.pb, w.nb, s2);
+			continue;
+		}
+		// strong value next to a weak one (the stale kA / kB are used on purpose: a resolved marker still counts
+		// with its marker value here)
+		const bool strongA = nhw_iabs(kA) > sh + 20 && nhw_iabs(kB) > (sh >> 1) && nhw_iabs(kB) <= s2;
+		const bool strongB = !strongA && nhw_iabs(kB) > sh + 20 && nhw_iabs(kA) > (sh >> 1) && nhw_iabs(kA) <= s2;
+		if (strongA || strongB) {
+			const int big = strongA ? kA : kB, small = strongA ? kB : kA;
+			const int at_big = strongA ? s - 1 : s, at_small = strongA ? s : s - 1;
+			if (big != 0) {
+				const int sg = big > 0 ? 1 : -1;
+				touch(at_big, sg);
+				if (small * sg > 0) touch(at_small, 2 * sg);
+				if (r * PW + j >= 2 * PW + 2) {
+					// the two cells of the row above that sit over the pair
+					const int hi = s - PW, lo = s - PW - 1;
+					const int k_hi = K[hi], k_lo = K[lo];
+					if (strongA) {
+						if (k_hi * sg > 4) touch(hi, sg);
+						if (k_lo * sg > 4) touch(lo, sg);
+						if (k_hi * sg < -24 && !back) touch(hi, -sg);
+						if (k_lo * sg < -24 && !back) touch(lo, -sg);
+					} else {
+						if (k_lo * sg > 4) touch(lo, sg);
+						if (k_hi * sg > 4) touch(hi, sg);
+						if (k_lo * sg < -24 && !back) touch(lo, -sg);
+						if (k_hi * sg < -24 && !back) touch(hi, -sg);
+					}
+				}
+				misses = 0; fresh = 0;
+			}
+			if (back == 1) { j++; s++; back = 0; }
+			else if (back == 2) { j += 3; s += 3; back = 0; }
+		} else {
+			misses++;
+			if (!back) fresh++;
+			if (misses == 2) { j -= 3; s -= 3; misses = 0; back = 1; }
+			else if (back == 1) {
+				j++; s++; back = 0; misses = 0;
+				if (fresh == 4) {
+					if (nhw_iabs(K[s - 5]) <= s2 || nhw_iabs(K[s - 2]) <= s2) { j -= 5; s -= 5; back = 2; }
+					fresh = 0;
+				}
+			} else if (back == 2) { j += 3; s += 3; back = 0; misses = 0; fresh = 0; }
+		}
+	}
+}
+
 NHW_HDN void pre_low_walk_c(int16_t *Y, int16_t *K, uint8_t *M, const PreLowParams &p)
 {
 	PreWalkC w = {0, 0, 0, 0, 0, 0};
-	const int sh = p.sharp, s2 = p.sharp2;
-	auto touch = [&](int at, int d) { Y[at] = (int16_t)(Y[at] + d); M[at] = 1; };
-	for (int r = 1; r < 511; r++) {
-		int misses = 0, back = 0, fresh = 0;     // per-row cursor state (e, t, f)
-		for (int j = 1, s = r * PW + 1; j < 509; j++, s++) {
-			int kA = K[s];
-			j++; s++;
-			int kB = K[s];
-			if (nhw_iabs(kA) > 6000) {
-				walk_c_resolve(K[s - 1], kA, w.pa, w.na, s2);
-				if (!w.gate) { walk_c_resolve(K[s], kB, w.pb, w.nb, s2); w.gate = 1; }
-				else w.gate = 0;
-				if (!w.skip_first) { w.skip_first = 1; continue; }
-				w.skip_first = 0;
-			} else if (nhw_iabs(kB) > 6000) {
-				walk_c_resolve(K[s], kB, w.pb, w.nb, s2);
-				continue;
-			}
-			// strong value next to a weak one (the stale kA / kB are used on purpose: a resolved marker still counts
-			// with its marker value here)
-			const bool strongA = nhw_iabs(kA) > sh + 20 && nhw_iabs(kB) > (sh >> 1) && nhw_iabs(kB) <= s2;
-			const bool strongB = !strongA && nhw_iabs(kB) > sh + 20 && nhw_iabs(kA) > (sh >> 1) && nhw_iabs(kA) <= s2;
-			if (strongA || strongB) {
-				const int big = strongA ? kA : kB, small = strongA ? kB : kA;
-				const int at_big = strongA ? s - 1 : s, at_small = strongA ? s : s - 1;
-				if (big != 0) {
-					const int sg = big > 0 ? 1 : -1;
-					touch(at_big, sg);
-					if (small * sg > 0) touch(at_small, 2 * sg);
-					if (s >= 2 * PW + 2) {
-						// the two cells of the row above that sit over the pair (strongA: over the pair's right cell and
-						// its left neighbour; strongB the same two cells, visited left to right)
-						const int hi = s - PW, lo = s - PW - 1;
-						const int k_hi = K[hi], k_lo = K[lo];
-						if (strongA) {
-							if (k_hi * sg > 4) touch(hi, sg);
-							if (k_lo * sg > 4) touch(lo, sg);
-							if (k_hi * sg < -24 && !back) touch(hi, -sg);
-							if (k_lo * sg < -24 && !back) touch(lo, -sg);
-						} else {
-							if (k_lo * sg > 4) touch(lo, sg);
-							if (k_hi * sg > 4) touch(hi, sg);
-							if (k_lo * sg < -24 && !back) touch(lo, -sg);
-							if (k_hi * sg < -24 && !back) touch(hi, -sg);
-						}
-					}
-					misses = 0; fresh = 0;
-				}
-				if (back == 1) { j++; s++; back = 0; }
-				else if (back == 2) { j += 3; s += 3; back = 0; }
-			} else {
-				misses++;
-				if (!back) fresh++;
-				if (misses == 2) { j -= 3; s -= 3; misses = 0; back = 1; }
-				else if (back == 1) {
-					j++; s++; back = 0; misses = 0;
-					if (fresh == 4) {
-						if (nhw_iabs(K[s - 5]) <= s2 || nhw_iabs(K[s - 2]) <= s2) { j -= 5; s -= 5; back = 2; }
-						fresh = 0;
-					}
-				} else if (back == 2) { j += 3; s += 3; back = 0; misses = 0; fresh = 0; }
-			}
-		}
-	}
+	for (int r = 1; r < 511; r++) pre_low_walk_c_row(w, p, r, Y + (r - 1) * PW, K + (r - 1) * PW, M + (r - 1) * PW);
 }
 
 // ---- walk D -----------------------------------------------------------------------------------------------------

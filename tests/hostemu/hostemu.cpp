@@ -590,7 +590,15 @@ static int he_luma_lowq(const EncImg &im, int q, int ratio, std::vector<int16_t>
 		T("y_dwt2b_proc", im.proc, 512 * 512 * 2);
 	}
 	if (q <= 11) for (int r = 255; r >= 128; r--) y_e7_kill_row(im, q, ratio, r);
-	if (q < 13) y_e8_smooth_image(im, q);
+	if (q < 13) {
+		if (getenv("HE_SERIAL")) y_e8_smooth_image(im, q);
+		else {   // the band staged apart from the plane, as the CUDA kernel runs it
+			std::vector<int16_t> band(128 * 128);
+			for (int r = 0; r < 128; r++) memcpy(&band[r * 128], im.proc + r * 512, 256);
+			y_e8_smooth_band(band.data(), 128, im.proc, q);
+			for (int r = 0; r < 128; r++) memcpy(im.proc + r * 512, &band[r * 128], 256);
+		}
+	}
 	T("y_e8_proc", im.proc, 512 * 512 * 2);
 	copy_region(im.ll2s, 256, im.proc, 512, 256);
 	y_ll2_to_bytes_image(im, q);
@@ -627,7 +635,18 @@ static int he_luma_lowq(const EncImg &im, int q, int ratio, std::vector<int16_t>
 	y_e20_cleanup_image(im, q, ratio);
 	T("y_e20_proc", im.proc, 512 * 512 * 2);
 	y_offset_pairs_image(im);
-	y_offset_quant_lowq_image(im, ratio);
+	if (getenv("HE_SERIAL")) y_offset_quant_lowq_image(im, ratio);
+	else {   // the CUDA schedule: every row dry for the three incoming states, one chain walk, rows committed bottom-up
+		std::vector<int> next0(512), st_out(512 * 3), sp(512 * 3), in_state(512);
+		for (int r = 0; r < 512; r++) next0[r] = r < 511 ? im.proc[(r + 1) * 512] : 0;
+		for (int r = 511; r >= 0; r--)
+			for (int t = 0; t < 3; t++) st_out[r * 3 + t] = y_offset_quant_lowq_row(im.proc + r * 512, nullptr, r, ratio, next0[r], t, sp[r * 3 + t]);
+		int state = 0, spilled = 0;
+		for (int r = 0; r < 512; r++) { in_state[r] = state; spilled |= sp[r * 3 + state]; state = st_out[r * 3 + state]; }
+		if (spilled) y_offset_quant_lowq_image(im, ratio);
+		else
+			for (int r = 511; r >= 0; r--) { int dummy; y_offset_quant_lowq_row(im.proc + r * 512, im.proc + r * 512, r, ratio, next0[r], in_state[r], dummy); }
+	}
 	T("y_e21_proc", im.proc, 512 * 512 * 2);
 	for (int s = 127; s >= 0; s--) y_scan_strip(im, s);
 	T("y_e23_scan", im.scan, 262144);
