@@ -149,6 +149,9 @@ int nhw_debug_read(nhw_ctx *ctx, const char *what, int img, void *host, size_t b
  * fused front end and through the IEEE double/float form of encoder/colorspace.c:71-99;
  * returns the number of triples on which they differ (must be 0), or a negative error. */
 long nhw_debug_color_check(nhw_ctx *ctx);
+/* The same for the decoder's q >= 20 YCbCr -> RGB matrix (decoder/nhw_decoder_cli.c:148-150): all 2^24 (Y, U, V) triples
+ * through the integer form of the back-end kernel and through the IEEE double form; returns the number that differ. */
+long nhw_debug_dec_color_check(nhw_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,8 @@ def load_library():
     L.nhw_debug_read.restype = i32
     L.nhw_debug_color_check.argtypes = [vp]
     L.nhw_debug_color_check.restype = ctypes.c_long
+    L.nhw_debug_dec_color_check.argtypes = [vp]
+    L.nhw_debug_dec_color_check.restype = ctypes.c_long
     L.nhw_profile.argtypes = [vp, i32]
     L.nhw_profile.restype = i32
     L.nhw_profile_read.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
@@ -140,6 +142,10 @@ class Codec:
     def color_check(self):
         """mismatches between the integer and the IEEE colour transform over all 2^24 triples"""
         return int(self.lib.nhw_debug_color_check(self.h))
+
+    def dec_color_check(self):
+        """mismatches between the integer and the IEEE form of the decoder's q >= 20 colour matrix over all 2^24 triples"""
+        return int(self.lib.nhw_debug_dec_color_check(self.h))
 
     def profile(self, mode):
         """0 off, 1 on, 2 on + reset"""

@@ -276,6 +276,13 @@ long nhw_debug_color_check(nhw_ctx *c)
 	return nhw::color_fast_path_mismatches(c);
 }
 
+long nhw_debug_dec_color_check(nhw_ctx *c)
+{
+	if (!c) return NHW_ERR_ARG;
+	cudaSetDevice(c->device);
+	return nhw::dec_color_fast_path_mismatches(c);
+}
+
 int nhw_profile(nhw_ctx *c, int enable)
 {
 	if (!c) return NHW_ERR_ARG;

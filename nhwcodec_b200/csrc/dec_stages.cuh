@@ -411,7 +411,36 @@ NHW_HD DecColor dec_color_of(int quality)
 #define NHW_D2I(a) ((int)(a))
 #endif
 
+// ---- integer form of the q >= 20 matrix.  R, G, B are trunc(Y + k1 U' + k2 V' + 0.5) of values that lie exactly on
+// a 1e-3 (R, B) or 1e-5 (G) grid, and the double expression only leaves the exact value by ~1e-13: the truncation is
+// the integer quotient, except where the exact value IS an integer (B at U' = +-125, G on a few (U', V') pairs), where
+// the rounding of the partial products decides and the IEEE expression is evaluated.  Negative values clip to 0 either
+// way.  Checked against the IEEE form on all 2^24 (Y, U, V) triples (nhw_debug_dec_color_check, tests/test_decode_gpu.py).
+NHW_HD bool dec_ycc_to_rgb_q20_int(int y8, int u8, int v8, uint8_t *rgb)
+{
+	const int U = u8 - 128, V = v8 - 128;
+	const int tr = 1000 * y8 + 500 + 1402 * V;
+	const int tb = 1000 * y8 + 500 + 1772 * U;
+	const int tg = 100000 * y8 + 50000 - 34414 * U - 71414 * V;
+	if (U == 125 || U == -125) return false;
+	const uint32_t qg = tg > 0 ? (uint32_t)(((unsigned long long)(uint32_t)tg * 2814749768ull) >> 48) : 0u;
+	if (tg > 0 && qg * 100000u == (uint32_t)tg) return false;
+	const uint32_t qr = tr > 0 ? (uint32_t)(((unsigned long long)(uint32_t)tr * 0x10624dd3ull) >> 38) : 0u;
+	const uint32_t qb = tb > 0 ? (uint32_t)(((unsigned long long)(uint32_t)tb * 0x10624dd3ull) >> 38) : 0u;
+	rgb[0] = (uint8_t)(qr > 255u ? 255u : qr);
+	rgb[1] = (uint8_t)(qg > 255u ? 255u : qg);
+	rgb[2] = (uint8_t)(qb > 255u ? 255u : qb);
+	return true;
+}
+
+NHW_HD void dec_ycc_to_rgb_ieee(int y8, int u8, int v8, const DecColor &c, uint8_t *rgb);
 NHW_HD void dec_ycc_to_rgb(int y8, int u8, int v8, const DecColor &c, uint8_t *rgb)
+{
+	if (c.mode == 0 && dec_ycc_to_rgb_q20_int(y8, u8, v8, rgb)) return;
+	dec_ycc_to_rgb_ieee(y8, u8, v8, c, rgb);
+}
+
+NHW_HD void dec_ycc_to_rgb_ieee(int y8, int u8, int v8, const DecColor &c, uint8_t *rgb)
 {
 	if (c.mode == 3) {
 		// q <= 16 (nhw_decoder_cli.c:256-276): integer matrix on un-centred U, V, one float32 multiply by the

@@ -802,6 +802,18 @@ __global__ void __launch_bounds__(256) kd_backend(DecBatch b, uint8_t *__restric
 	for (int k = t; k < BE_ROWS * 96; k += 256) dst[k] = reinterpret_cast<const uint4 *>(so)[k];
 }
 
+// every (Y, U, V) triple through both forms of the q >= 20 decoder colour matrix; counts disagreements
+__global__ void kd_color_check(unsigned long long *bad)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = t & 255u, u = (t >> 8) & 255u, v = t >> 16;
+	const DecColor col = dec_color_of(20);
+	uint8_t a[3], b[3];
+	dec_ycc_to_rgb_ieee(y, u, v, col, a);
+	dec_ycc_to_rgb(y, u, v, col, b);
+	if (a[0] != b[0] || a[1] != b[1] || a[2] != b[2]) atomicAdd(bad, 1ull);
+}
+
 // ---- device-resident streams: header walk on the device (dec_parse.h), one thread per stream
 __global__ void kd_parse_headers(const uint8_t *in, size_t stride, const uint32_t *len, const uint64_t *offs, int n, DecDesc *desc,
                                  uint64_t *off_out, int32_t *status)
@@ -827,6 +839,18 @@ bool decode_device_init(nhw_ctx *c)
 		return false;
 	c->dec_lut = static_cast<const uint16_t *>(p);
 	return check(cudaFuncSetAttribute(kd_inv_rows_t, cudaFuncAttributeMaxDynamicSharedMemorySize, IRT_SMEM), "attr kd_inv_rows_t");
+}
+
+long dec_color_fast_path_mismatches(nhw_ctx *c)
+{
+	unsigned long long *bad = nullptr, host = ~0ull;
+	if (cudaMalloc(&bad, 8) != cudaSuccess) return -1;
+	cudaMemsetAsync(bad, 0, 8, c->stream);
+	kd_color_check<<<65536, 256, 0, c->stream>>>(bad);
+	cudaMemcpyAsync(&host, bad, 8, cudaMemcpyDeviceToHost, c->stream);
+	cudaStreamSynchronize(c->stream);
+	cudaFree(bad);
+	return (long)host;
 }
 
 // from encode.cu (same inverse kernels, natural-orientation output)

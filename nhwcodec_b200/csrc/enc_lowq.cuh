@@ -62,9 +62,17 @@ NHW_HD void e8_silence_siblings(int16_t *P, int p)
 // `cursor` models the reference's `count` variable: it is assigned inside some branches only and read, stale, by
 // the q <= 11 tail of the third pass, so it is threaded through all four passes (65536 on entry: the value the
 // LL1 copy / correction loop leaves behind).
-// B = the LL2 band (128 x 128) at row stride BS -- the plane itself (BS = 512) or a staged copy; P = the plane, for
-// the descendants (flat plane indices).
-NHW_HDN void y_e8_smooth_band(int16_t *B, int BS, int16_t *P, int q)
+// B = the LL2 band (128 x 128) at row stride BS -- the plane itself (BS = 512) or a staged copy.  The walk never reads
+// the cells it silences, and silencing is idempotent ("zero if below a threshold"; of two requests for the same cell
+// the larger threshold wins), so the requests go to a sink: E8Direct applies them to the plane at once (serial form),
+// the CUDA kernel records them and applies them with all its lanes after the walk (E8Deferred, encode.cu).
+struct E8Direct {
+	int16_t *P;
+	NHW_HD void children(int p, int a, int b, int c) const { e8_silence_children(P, p, a, b, c); }
+	NHW_HD void siblings(int p) const { e8_silence_siblings(P, p); }
+};
+template <typename Sink>
+NHW_HDN void y_e8_smooth_walk(int16_t *B, int BS, const Sink &P_, int q)
 {
 	const E8Thr t = e8_thresholds(q);
 	const bool deep = q <= 11;
@@ -90,10 +98,10 @@ NHW_HDN void y_e8_smooth_band(int16_t *B, int BS, int16_t *P, int q)
 					hit = (v3 >= v2 && v2 >= v1) || (v3 <= v2 && v2 <= v1);
 			}
 			if (!hit) continue;
-			for (int k = 1; k < 4; k++) e8_silence_children(P, s + k, t.t6, t.t6 + 6, t.t5);
+			for (int k = 1; k < 4; k++) P_.children(s + k, t.t6, t.t6 + 6, t.t5);
 			cursor = 4;
 			if (deep)
-				for (int k = 1; k < 4; k++) e8_silence_siblings(P, s + k);
+				for (int k = 1; k < 4; k++) P_.siblings(s + k);
 		}
 	// passes 2 and 3: the centre of a plus-shaped neighbourhood becomes the rounded mean of its four arms
 	for (int pass = 0; pass < 2; pass++)
@@ -113,12 +121,12 @@ NHW_HDN void y_e8_smooth_band(int16_t *B, int BS, int16_t *P, int q)
 					const int mean = (up + dn + lf + rt + (pass == 0 ? 2 : 1)) >> 2;
 					if (nhw_iabs(mean - lf) < 5 || nhw_iabs(mean - rt) < 5) B[b + BS + 1] = (int16_t)mean;
 					cursor = s + YW + 1;
-					e8_silence_children(P, cursor, t.t6, t.t6 + 6, 32);
+					P_.children(cursor, t.t6, t.t6 + 6, 32);
 				}
 				// pass 2 silences the siblings together with the children; pass 3 does it one test further out, with
 				// whatever the cursor holds
 				if (deep && (pass == 0 ? inner : outer))
-					for (int k = -1; k <= 1; k++) e8_silence_siblings(P, cursor + k);
+					for (int k = -1; k <= 1; k++) P_.siblings(cursor + k);
 			}
 	if (!deep) return;
 	// pass 4: three flat samples in a row
@@ -126,11 +134,12 @@ NHW_HDN void y_e8_smooth_band(int16_t *B, int BS, int16_t *P, int q)
 		for (int j = 0, s = r * YW, b = r * BS; j < 126; j++, s++, b++) {
 			const int v0 = B[b], v1 = B[b + 1], v2 = B[b + 2];
 			if (nhw_iabs(v2 - v1) < t.t7 && nhw_iabs(v2 - v0) < t.t7 && nhw_iabs(v1 - v0) < t.t7) {
-				e8_silence_children(P, s + 1, t.t6, t.t6 + 6, 34);
-				e8_silence_siblings(P, s + 1);
+				P_.children(s + 1, t.t6, t.t6 + 6, 34);
+				P_.siblings(s + 1);
 			}
 		}
 }
+NHW_HDN void y_e8_smooth_band(int16_t *B, int BS, int16_t *P, int q) { y_e8_smooth_walk(B, BS, E8Direct{P}, q); }
 NHW_HDN void y_e8_smooth_image(const EncImg &im, int q) { y_e8_smooth_band(im.proc, YW, im.proc, q); }
 
 // ---- E14 below q16.  q14/q15: pointwise.  q <= 13: thresholds chosen from a global count (q <= 12), then three

@@ -1556,17 +1556,42 @@ __global__ void __launch_bounds__(256) k_write_stream(EncBatch b, int n, uint8_t
 	}
 }
 
-// ---- E8 (q <= 12, enc_lowq.cuh: y_e8_smooth_band): a raster-serial walk over the 128 x 128 LL2 band, one WARP per
-// image: the band is staged in shared memory (coalesced), lane 0 walks it at shared-memory latency (the descendants it
-// silences are sparse writes to the plane), the warp writes the band back.
+// ---- E8 (q <= 12, enc_lowq.cuh: y_e8_smooth_walk): a raster-serial walk over the 128 x 128 LL2 band, one WARP per
+// image.  The band is staged in shared memory (coalesced) and lane 0 walks it at shared-memory latency; the cells the
+// walk silences (descendants in the level-1 bands, siblings in the level-2 bands) are never read by it, so the walk
+// only records the requests -- per LL2 cell the largest threshold asked for its diagonal-band children, per plane index
+// a sibling bit -- and the 32 lanes apply them afterwards.  The warp then writes the band back.
+struct E8Deferred {
+	uint8_t *child;      // [128 * 128] by LL2 cell: 0 none, else the threshold for the diagonal-band children
+	uint32_t *sib;       // bitmap over flat plane indices 0 .. 65536 + 63
+	__device__ void children(int p, int, int, int c) const
+	{
+		const int k = ((p >> 9) << 7) + (p & 127);
+		if (c > child[k]) child[k] = (uint8_t)c;
+	}
+	__device__ void siblings(int p) const { sib[p >> 5] |= 1u << (p & 31); }
+};
+#define E8_SMEM (128 * 128 * 2 + 128 * 128 + (65536 / 32 + 2) * 4)
 __global__ void __launch_bounds__(32) k_e8_staged(EncBatch b, int q)
 {
-	__shared__ __align__(16) int16_t band[128 * 128];
+	extern __shared__ __align__(16) uint8_t e8mem[];
+	int16_t *band = reinterpret_cast<int16_t *>(e8mem);
+	uint8_t *child = e8mem + 128 * 128 * 2;
+	uint32_t *sib = reinterpret_cast<uint32_t *>(child + 128 * 128);
 	const EncImg im = make_img(b, blockIdx.x, 0);
 	const int lane = threadIdx.x;
 	for (int k = lane; k < 128 * 16; k += 32) reinterpret_cast<uint4 *>(band)[k] = *reinterpret_cast<const uint4 *>(im.proc + (k >> 4) * YW + (k & 15) * 8);
+	for (int k = lane; k < 128 * 128 / 16; k += 32) reinterpret_cast<uint4 *>(child)[k] = make_uint4(0, 0, 0, 0);
+	for (int k = lane; k < 65536 / 32 + 2; k += 32) sib[k] = 0;
 	__syncwarp();
-	if (lane == 0) y_e8_smooth_band(band, 128, im.proc, q);
+	if (lane == 0) y_e8_smooth_walk(band, 128, E8Deferred{child, sib}, q);
+	__syncwarp();
+	const E8Thr t = e8_thresholds(q);
+	int16_t *P = im.proc;
+	for (int k = lane; k < 128 * 128; k += 32)
+		if (child[k]) e8_silence_children(P, ((k >> 7) << 9) + (k & 127), t.t6, t.t6 + 6, child[k]);
+	for (int w = lane; w < 65536 / 32 + 2; w += 32)
+		for (uint32_t m = sib[w]; m; m &= m - 1) e8_silence_siblings(P, 32 * w + __ffs(m) - 1);
 	__syncwarp();
 	for (int k = lane; k < 128 * 16; k += 32) *reinterpret_cast<uint4 *>(im.proc + (k >> 4) * YW + (k & 15) * 8) = reinterpret_cast<const uint4 *>(band)[k];
 }
@@ -1622,6 +1647,7 @@ bool encode_device_init(nhw_ctx *c)
 {
 	(void)c;
 	bool ok = check(cudaFuncSetAttribute(k_ll2_code, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_CODE_SMEM), "attr k_ll2_code");
+	ok = ok && check(cudaFuncSetAttribute(k_e8_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, E8_SMEM), "attr k_e8_staged");
 	ok = ok && check(cudaFuncSetAttribute(k_recons_ll2_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_SMEM_BYTES), "attr k_recons_ll2_wave");
 	ok = ok && check(cudaFuncSetAttribute(k_idwt_cols_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * 2), "attr k_idwt_cols_t");
 	ok = ok && check(cudaFuncSetAttribute(k_idwt_cols_t<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 33 * 2), "attr k_idwt_cols_t");
@@ -1694,7 +1720,7 @@ static void encode_luma_lowq(nhw_ctx *c, const EncBatch &b, int n, int q, int ra
 		dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
 	}
 	if (q <= 11) run_rows(c, "y_e7_kill", b, n, 128, [=] __device__(const EncImg &im, int r) { y_e7_kill_row(im, q, ratio, 128 + r); });
-	if (q < 13) NHW_LAUNCH_L(c, "y_e8_smooth", k_e8_staged, n, 32, 0, b, q);
+	if (q < 13) NHW_LAUNCH_L(c, "y_e8_smooth", k_e8_staged, n, 32, E8_SMEM, b, q);
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
 	NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);
 	if (q > 12) {   // second reconstruction

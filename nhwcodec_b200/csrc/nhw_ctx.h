@@ -90,6 +90,7 @@ void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_
                  size_t ylstride, uint8_t *uv_bytes, int16_t *c_proc, size_t cpstride, int16_t *c_ll1, size_t clstride,
                  int16_t *kept, size_t kstride);   // kept: q22/q23 only, 256x512 per image (may be NULL below q22)
 long color_fast_path_mismatches(nhw_ctx *c);
+long dec_color_fast_path_mismatches(nhw_ctx *c);   // decode.cu
 void dwt_level_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
                          int N, int row_stride);
 

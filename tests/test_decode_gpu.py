@@ -142,3 +142,9 @@ def test_decode_planes_api(codec, ref):
         for i in range(5):
             _, planes = ref.ref_decode(streams[i], planes=True)
             assert np.array_equal(yuv[i].reshape(3, 512, 512), planes), (q, i)
+
+
+def test_decoder_color_fast_path_exhaustive(codec):
+    """the back-end kernel's integer q >= 20 colour matrix == the IEEE double form of write_image_bmp on every one of
+    the 2^24 (Y, U, V) triples"""
+    assert codec.dec_color_check() == 0
