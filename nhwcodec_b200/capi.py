@@ -20,6 +20,8 @@ EXPORTS = [
     "nhw_encode_batch_device", "nhw_decode_batch", "nhw_decode_batch_planes", "nhw_stage_frontend_device",
     "nhw_stage_colorspace_device", "nhw_synth_batch_device", "nhw_launch_count",
     "nhw_stream", "nhw_profile", "nhw_profile_read", "nhw_debug_stop_after", "nhw_debug_read", "nhw_debug_color_check",
+    "nhw_decode_batch_device", "nhw_decode_batch_packed_device", "nhw_pack_batch_device", "nhw_digest_batch_device",
+    "nhw_debug_dec_color_check",
 ]
 
 _lib = None

@@ -181,6 +181,7 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 	ok = ok && dev_alloc0(&c->c_ll1, B * 2 * NHW_Q_SLOT) && dev_alloc0(&c->c_ll2save, B * 2 * NHW_Q_SLOT);
 	ok = ok && dev_alloc0(&c->rowmap, B * 512) && dev_alloc0(&c->rowcarry, B * 512);
 	ok = ok && dev_alloc0(&c->enc_bytes, B * (size_t)ENC_BYTES_SLOT) && dev_alloc0(&c->enc_hdr, B);
+	ok = ok && dev_alloc0(&c->dec_bytes, B * (size_t)NHW_DEC_BYTES_SLOT);
 	ok = ok && dev_alloc0(&c->out_dev, B * (size_t)NHW_MAX_STREAM_BYTES) && dev_alloc0(&c->pack_dev, B * (size_t)NHW_MAX_STREAM_BYTES);
 	ok = ok && dev_alloc0(&c->len_dev, B) && dev_alloc0(&c->status_dev, B) && dev_alloc0(&c->offs_dev, B + 1 + NHW_MAX_SUB);
 	ok = ok && dev_alloc0(&c->dec_yuv, B * (size_t)NHW_RGB_BYTES);
@@ -198,7 +199,7 @@ void nhw_destroy(nhw_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	void *ptrs[] = {c->rgb, c->y_jpeg, c->y_proc, c->y_aux, c->y_aux2, c->y_ll1, c->y_ll2save, c->c_u8, c->c_jpeg,
-	                c->c_proc, c->c_aux, c->c_ll1, c->c_ll2save, c->rowmap, c->rowcarry, c->enc_bytes, c->enc_hdr,
+	                c->c_proc, c->c_aux, c->c_ll1, c->c_ll2save, c->rowmap, c->rowcarry, c->enc_bytes, c->dec_bytes, c->enc_hdr,
 	                c->out_dev, c->pack_dev, c->len_dev, c->status_dev, c->offs_dev};
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
@@ -360,6 +361,7 @@ static nhw_ctx lane_view(const nhw_ctx *c, int l, int slot0, int sub = -1)
 	v.c_ll1 += s * 2 * NHW_Q_SLOT; v.c_ll2save += s * 2 * NHW_Q_SLOT;
 	v.rowmap += s * 512; v.rowcarry += s * 512;
 	v.enc_bytes += s * (size_t)ENC_BYTES_SLOT; v.enc_hdr += s;
+	v.dec_bytes += s * (size_t)NHW_DEC_BYTES_SLOT;
 	v.out_dev += s * (size_t)NHW_MAX_STREAM_BYTES; v.pack_dev += s * (size_t)NHW_MAX_STREAM_BYTES;
 	v.len_dev += s; v.status_dev += s; v.offs_dev += s + sub; v.offs_host += s + sub; v.status_host += s;
 	v.dec_yuv += s * (size_t)NHW_RGB_BYTES;

@@ -181,7 +181,8 @@ NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
 	// bit j of hist = a non-zero value was stored at position e-1-j.
 	uint32_t hist = 0;
 	auto z = [&](int k) { return k >= 0 ? !((hist >> (e - 1 - k)) & 1u) : true; };   // k in [e-5, e-1]; below 0: zero guard
-	auto put = [&](int v) { im3[e++] = (int16_t)v; hist = (hist << 1) | (v != 0 ? 1u : 0u); };
+	// (the last symbol may run a few cells past the plane: those stores are dropped, the plane's guard band stays zero)
+	auto put = [&](int v) { if (e < p1) im3[e] = (int16_t)v; e++; hist = (hist << 1) | (v != 0 ? 1u : 0u); };
 	auto advance = [&](int n) { e += n; hist = n >= 32 ? 0u : hist << n; };
 	while (br.pos < nbits + 64) {
 		const int dec = dec_next_rank(br, zone, im.lut);
@@ -257,13 +258,16 @@ NHW_HDN int dec_prefix_chroma(const DecImg &im, int16_t *im3 /* 131072, zeroed *
 		if (word == 0x80) e += sym >> 8;
 		else {
 			const int x = word < 110 ? nhw_extra_value(word) : 0;
-			if (word < 110 && x > 0) im3[e++] = (int16_t)(123 + (x << 3));
-			else if (word < 110 && x < 0) im3[e++] = (int16_t)((x << 3) - 123);
-			else if (word >= 110 && word == 124) im3[e++] = 5005;
-			else if (word >= 110 && word == 126) im3[e++] = 5006;
-			else if (word >= 110 && word == 122) im3[e++] = 5003;
-			else if (word >= 110 && word == 130) im3[e++] = 5004;
-			else im3[e++] = (int16_t)(word > 0x80 ? word - 125 : word - 131);
+			int v;
+			if (word < 110 && x > 0) v = 123 + (x << 3);
+			else if (word < 110 && x < 0) v = (x << 3) - 123;
+			else if (word >= 110 && word == 124) v = 5005;
+			else if (word >= 110 && word == 126) v = 5006;
+			else if (word >= 110 && word == 122) v = 5003;
+			else if (word >= 110 && word == 130) v = 5004;
+			else v = word > 0x80 ? word - 125 : word - 131;
+			if (e < 131072) im3[e] = (int16_t)v;   // (a run may carry e past the end: nothing is stored there)
+			e++;
 		}
 		if (e >= p1 - 1) return 0;
 	}

@@ -106,8 +106,8 @@ NHW_HD void dec_marker_apply(int16_t *J, int s, bool lower, uint32_t *W, uint32_
 		}
 	};
 	if (!lower) {
-		if (v == 1008) { J[s - 1] = 5; J[s + 1] = 5; J[s] = (int16_t)(j < 256 ? 5 : 6); }
-		else if (v == 1009) { J[s - 1] = -5; J[s + 1] = -5; J[s] = (int16_t)(j < 256 ? -6 : -7); }
+		if (v == 1008) { if (s > 0) J[s - 1] = 5; J[s + 1] = 5; J[s] = (int16_t)(j < 256 ? 5 : 6); }
+		else if (v == 1009) { if (s > 0) J[s - 1] = -5; J[s + 1] = -5; J[s] = (int16_t)(j < 256 ? -6 : -7); }
 		else if (v == 1010) { J[s] = 5; J[s + 1] = 5; J[s + YW] = 5; J[s + YW + 1] = 5; }
 		else if (v == 1011) { J[s] = -5; J[s + 1] = -5; J[s + YW] = -5; J[s + YW + 1] = -5; }
 		else if (v == 1006) { J[s] = -6; J[s + 1] = -6; }
@@ -116,7 +116,8 @@ NHW_HD void dec_marker_apply(int16_t *J, int s, bool lower, uint32_t *W, uint32_
 	}
 	if (v == 1008 || v == 1009) {
 		const int sg = v == 1008 ? 1 : -1;
-		J[s - 1] = (int16_t)(5 * sg); J[s] = (int16_t)(v == 1008 ? 6 : -7); J[s + 1] = (int16_t)(5 * sg);
+		// (at the plane's very last cell the reference writes one element past its buffer: dropped, the guard stays zero)
+		J[s - 1] = (int16_t)(5 * sg); J[s] = (int16_t)(v == 1008 ? 6 : -7); if (s + 1 < 512 * 512) J[s + 1] = (int16_t)(5 * sg);
 		mark(s - 1); mark(s); if (j < 511) mark(s + 1);
 		if (A && j >= 256) {
 			const int k = (((s >> 9) - 256) << 8) + (j - 256);

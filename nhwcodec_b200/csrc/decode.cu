@@ -31,7 +31,7 @@ enum : int {
 	DOFF_CMARK = DOFF_MBITS + 512 * 64,             // chroma marker lists: 2 planes x (count + DEC_CMARK_CAP entries)
 	DOFF_END = DOFF_CMARK + 2 * 4 * (1 + DEC_CMARK_CAP),
 };
-static_assert(DOFF_END <= ENC_BYTES_SLOT, "decode scratch must fit the per-image byte slot");
+static_assert(DOFF_END <= NHW_DEC_BYTES_SLOT, "decode scratch must fit the per-image decoder byte slot");
 
 struct DecBatch {
 	const uint8_t *blobs;         // dense concatenation of the chunk's streams
@@ -71,7 +71,7 @@ __device__ __forceinline__ DecImg make_dec(const DecBatch &b, int i, int comp)
 	im.cproc = b.c_proc + p * NHW_C_SLOT;
 	im.cjpeg = b.c_jpeg + p * NHW_C_SLOT;
 	im.caux = b.c_aux + p * NHW_C_SLOT;
-	uint8_t *bytes = b.bytes + (size_t)i * ENC_BYTES_SLOT;
+	uint8_t *bytes = b.bytes + (size_t)i * NHW_DEC_BYTES_SLOT;
 	im.res_comp = bytes + DOFF_RESCOMP;
 	im.book = reinterpret_cast<uint16_t *>(bytes + DOFF_BOOK);
 	im.list_len = reinterpret_cast<int32_t *>(bytes + DOFF_LISTLEN);
@@ -866,7 +866,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	b.y_proc = c->y_proc + NHW_GUARD_S; b.y_jpeg = c->y_jpeg + NHW_GUARD_S; b.y_aux = c->y_aux + NHW_GUARD_S;
 	b.uvcoef = c->y_aux2 + NHW_GUARD_S;
 	b.c_proc = c->c_proc + NHW_GUARD_S; b.c_jpeg = c->c_jpeg + NHW_GUARD_S; b.c_aux = c->c_aux + NHW_GUARD_S;
-	b.bytes = c->enc_bytes; b.yuv = c->dec_yuv;
+	b.bytes = c->dec_bytes; b.yuv = c->dec_yuv;
 	b.lut = c->dec_lut;
 	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT;
 

@@ -1,6 +1,7 @@
 // nhw_ctx.h -- host-side context of libnhw_cuda (internal; the public face is include/nhw_cuda.h)
 #pragma once
 #define NHW_LANES 4
+#define NHW_DEC_BYTES_SLOT (1728 * 1024)   // >= decode.cu's DOFF_END (static_assert there)
 #define NHW_MAX_SUB 16
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -62,6 +63,8 @@ struct nhw_ctx {
 	uint32_t *rowmap;    // pre-sharpen carry maps               512 u32
 	uint8_t *rowcarry;   // pre-sharpen carry-in class per row   512 u8
 	uint8_t *enc_bytes;  // byte-sized encoder state             ENC_BYTES_SLOT
+	uint8_t *dec_bytes;  // byte-sized decoder state             NHW_DEC_BYTES_SLOT (its own array: the encoder relies on the
+	                     // never-written gaps of enc_bytes reading as zero, so the decoder must not scribble there)
 	EncHdr *enc_hdr;
 
 	uint8_t *out_dev;    // staged output streams (host API only), NHW_MAX_STREAM_BYTES / image
