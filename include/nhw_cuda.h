@@ -125,6 +125,11 @@ int nhw_stage_colorspace_device(nhw_ctx *ctx, const uint8_t *rgb_dev, int n, int
 int nhw_synth_batch_device(nhw_ctx *ctx, uint8_t *rgb_dev, int n, uint32_t seed0, int kind,
                            const int16_t *sin_lut_dev);
 
+/* Page-locked ("pinned") host memory for the buffers handed to the host-buffer entry points: copies from and to pinned
+ * memory run at full PCIe speed and asynchronously; with pageable memory the calls still work, slower.  NULL on failure. */
+void *nhw_host_alloc(size_t bytes);
+void nhw_host_free(void *p);
+
 /* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
 uint64_t nhw_launch_count(const nhw_ctx *ctx);
 

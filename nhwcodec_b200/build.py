@@ -70,6 +70,12 @@ def build_host():
                            "-L" + HERE, "-lnhw_cuda", "-Wl,-rpath,$ORIGIN"])
     subprocess.check_call(["gcc", "-O2", "-Wall", os.path.join(cli, "nhw_dec_cli.c"), "-o", os.path.join(cli, "nhw-dec"),
                            "-L" + HERE, "-lnhw_cuda", "-Wl,-rpath,$ORIGIN/../nhwcodec_b200"])
+    # batch I/O front-end (image readers, tiling, the .nhwpack container, manifest jobs) and its CLI
+    batchio = os.path.join(HERE, "libnhw_batchio.so")
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-fvisibility=hidden", os.path.join(CSRC, "batchio.c"), "-o", batchio,
+                           "-L" + HERE, "-lnhw_cuda", "-lpthread", "-Wl,-rpath,$ORIGIN"])
+    subprocess.check_call(["gcc", "-O2", "-Wall", os.path.join(cli, "nhw_batch_cli.c"), "-o", os.path.join(cli, "nhw-batch"),
+                           "-L" + HERE, "-lnhw_batchio", "-lnhw_cuda", "-Wl,-rpath,$ORIGIN/../nhwcodec_b200"])
     # drop-in proof: the reference's OWN, unmodified CLI source compiled against its own header
     # and linked against our two libraries (only where the reference tree is present)
     ref_cli = "/root/reference/encoder/nhw_encoder_cli.c"

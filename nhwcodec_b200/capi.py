@@ -21,7 +21,7 @@ EXPORTS = [
     "nhw_stage_colorspace_device", "nhw_synth_batch_device", "nhw_launch_count",
     "nhw_stream", "nhw_profile", "nhw_profile_read", "nhw_debug_stop_after", "nhw_debug_read", "nhw_debug_color_check",
     "nhw_decode_batch_device", "nhw_decode_batch_packed_device", "nhw_pack_batch_device", "nhw_digest_batch_device",
-    "nhw_debug_dec_color_check",
+    "nhw_debug_dec_color_check", "nhw_host_alloc", "nhw_host_free",
 ]
 
 _lib = None

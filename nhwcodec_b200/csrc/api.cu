@@ -167,6 +167,7 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 		t.dsf_streams = env_int("NHW_DSF_STREAMS", 4, 1, 32);
 		while (32 % t.dsf_streams) t.dsf_streams--;
 		t.rows_grid_cap = sms * env_int("NHW_ROWS_CTAS_PER_SM", 24, 1, 64);
+		t.fetch_kernel = env_int("NHW_FETCH_KERNEL", 1, 0, 1);
 	}
 	ok = ok && nhw::front_device_init(c) && nhw::encode_device_init(c) && nhw::decode_device_init(c);
 	// every workspace array is zero-filled once: guard bands and never-written borders must
@@ -392,6 +393,18 @@ static void lane_done(nhw_ctx *c, nhw_ctx &v)
 
 static bool quality_supported(int q) { return q >= 1 && q <= 23; }   // q0 is accepted by the reference CLI but its tables are undefined
 
+void *nhw_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (!check(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost")) return nullptr;
+	return p;
+}
+
+void nhw_host_free(void *p)
+{
+	if (p) cudaFreeHost(p);
+}
+
 int nhw_stage_colorspace_device(nhw_ctx *c, const uint8_t *rgb_dev, int n, int quality, int pre,
                                 int16_t *y, uint8_t *u, uint8_t *v)
 {
@@ -483,6 +496,49 @@ int nhw_digest_batch_device(nhw_ctx *c, const uint8_t *data_dev, size_t stride, 
 	return finish(c, "nhw_digest_batch_device");
 }
 
+// ---- small host -> device transfers that must not queue behind another context's bulk uploads ----------------------
+// Copies of one direction are served in issue order by the copy engine: a decode call's 13 MB of stream bytes would wait
+// behind the gigabytes of pixel uploads an encode call on another context has already queued, and the two calls would
+// run back to back instead of side by side.  Pinned (mapped) host memory is fetched by a kernel instead -- SM loads over
+// PCIe do not pass through the copy queue; pageable memory keeps the cudaMemcpyAsync path.
+__global__ void __launch_bounds__(256) k_fetch(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, size_t bytes)
+{
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, T = (size_t)gridDim.x * blockDim.x;
+	if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+		const size_t n16 = bytes >> 4;
+		const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+		uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+		size_t i = t;
+		for (; i + 3 * T < n16; i += 4 * T) {   // four loads in flight per thread
+			const uint4 a = s4[i], b = s4[i + T], c = s4[i + 2 * T], d = s4[i + 3 * T];
+			d4[i] = a; d4[i + T] = b; d4[i + 2 * T] = c; d4[i + 3 * T] = d;
+		}
+		for (; i < n16; i += T) d4[i] = s4[i];
+		for (size_t j = (n16 << 4) + t; j < bytes; j += T) dst[j] = src[j];
+	} else {
+		for (size_t j = t; j < bytes; j += T) dst[j] = src[j];
+	}
+}
+
+// device-visible alias of a host pointer if the memory is pinned and mapped, else NULL
+static const uint8_t *mapped_alias(const void *host)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+	return static_cast<const uint8_t *>(at.devicePointer);
+}
+
+static bool fetch_to_device(nhw_ctx *w, void *dst, const void *host, const uint8_t *alias, size_t bytes, const char *what)
+{
+	if (!bytes) return true;
+	if (!alias) return check(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, w->stream), what);
+	const int blocks = bytes >= (8u << 20) ? 592 : bytes >= (64u << 10) ? 64 : 1;
+	k_fetch<<<blocks, 256, 0, w->stream>>>(static_cast<uint8_t *>(dst), alias, bytes);
+	w->launches++;
+	return check(cudaGetLastError(), what);
+}
+
 int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
                      uint8_t *out, size_t out_cap, uint64_t *offsets, int32_t *status)
 {
@@ -494,6 +550,7 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 	// copy stream, in image order.
 	uint64_t pos = 0;
 	offsets[0] = 0;
+	const uint8_t *out_alias = c->tune.fetch_kernel ? mapped_alias(out) : nullptr;
 	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
 		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, c->tune.subs_encode,
 		                              c->tune.lanes_encode);
@@ -518,8 +575,18 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 			cudaStreamWaitEvent(v[k].stream, c->ev_up[k], 0);
 			nhw::encode_chunk(&v[k], v[k].rgb, cnt, quality, v[k].out_dev, v[k].len_dev, v[k].status_dev);
 			nhw::pack_streams(&v[k], cnt);
-			cudaMemcpyAsync(v[k].offs_host, v[k].offs_dev, (size_t)(cnt + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, v[k].stream);
-			cudaMemcpyAsync(v[k].status_host, v[k].status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v[k].stream);
+			// the sub-chunk's offsets and status words go back by SM stores into the (mapped) staging arrays, not through the
+			// copy engine: behind another context's bulk downloads these few kilobytes would hold this lane up for milliseconds
+			if (c->tune.fetch_kernel) {
+				k_fetch<<<1, 256, 0, v[k].stream>>>(reinterpret_cast<uint8_t *>(v[k].offs_host), reinterpret_cast<const uint8_t *>(v[k].offs_dev),
+				                                    (size_t)(cnt + 1) * sizeof(uint64_t));
+				k_fetch<<<1, 256, 0, v[k].stream>>>(reinterpret_cast<uint8_t *>(v[k].status_host), reinterpret_cast<const uint8_t *>(v[k].status_dev),
+				                                    (size_t)cnt * sizeof(int32_t));
+				v[k].launches += 2;
+			} else {
+				cudaMemcpyAsync(v[k].offs_host, v[k].offs_dev, (size_t)(cnt + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, v[k].stream);
+				cudaMemcpyAsync(v[k].status_host, v[k].status_dev, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, v[k].stream);
+			}
 			cudaEventRecord(c->ev_sub[k], v[k].stream);
 			lane_done(c, v[k]);
 		}
@@ -529,7 +596,11 @@ int nhw_encode_batch(nhw_ctx *c, const uint8_t *rgb, int n, int quality,
 			if (!check(cudaGetLastError(), "nhw_encode_batch") || !check(cudaEventSynchronize(c->ev_sub[k]), "nhw_encode_batch")) return NHW_ERR_CUDA;
 			const uint64_t total = v[k].offs_host[cnt];
 			if (pos + total > out_cap) { nhw::set_error("output buffer too small"); return NHW_ERR_ARG; }
-			if (total && !check(cudaMemcpyAsync(out + pos, v[k].pack_dev, total, cudaMemcpyDeviceToHost, c->copy_stream), "D2H streams")) return NHW_ERR_CUDA;
+			if (total && out_alias) {   // pinned output buffer: SM stores again (see k_fetch), a few megabytes per sub-chunk
+				k_fetch<<<total >= (1u << 20) ? 128 : 8, 256, 0, c->copy_stream>>>(const_cast<uint8_t *>(out_alias) + pos, v[k].pack_dev, total);
+				c->launches++;
+				if (!check(cudaGetLastError(), "D2H streams")) return NHW_ERR_CUDA;
+			} else if (total && !check(cudaMemcpyAsync(out + pos, v[k].pack_dev, total, cudaMemcpyDeviceToHost, c->copy_stream), "D2H streams")) return NHW_ERR_CUDA;
 			for (int i = 0; i < cnt; i++) {
 				offsets[a + i + 1] = pos + v[k].offs_host[i + 1];
 				if (status) status[a + i] = v[k].status_host[i];
@@ -549,6 +620,9 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 	if (!c || !in || !offsets || (!rgb && !yuv) || n <= 0) return NHW_ERR_ARG;
 	cudaSetDevice(c->device);
 	c->dbg_seen = c->dbg_stopped = 0;
+	const uint8_t *in_alias = c->tune.fetch_kernel ? mapped_alias(in) : nullptr;
+	// the context's own staging arrays come from cudaMallocHost: mapped, and (unified addressing) at the same address
+	auto ctx_alias = [&](const void *p) { return in_alias ? static_cast<const uint8_t *>(p) : nullptr; };
 	for (int i0 = 0, step = 0; i0 < n; i0 += step) {
 		const LanePlan p = plan_lanes(c, n - i0 < c->max_batch ? n - i0 : c->max_batch, c->tune.subs_decode,
 		                              c->tune.lanes_decode);
@@ -562,22 +636,25 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 			nhw_ctx &w = v[l];
 			DecDesc *desc = static_cast<DecDesc *>(w.dec_desc_host);
 			const uint64_t base = offsets[a], total = offsets[a + cnt] - base;
-			if (total + 64 > (uint64_t)p.slot * NHW_MAX_STREAM_BYTES) { nhw::set_error("input chunk too large"); return NHW_ERR_ARG; }
+			const uint64_t mis = in_alias ? ((uintptr_t)(in + base) & 15) : 0;
+			if (total + mis + 64 > (uint64_t)p.slot * NHW_MAX_STREAM_BYTES) { nhw::set_error("input chunk too large"); return NHW_ERR_ARG; }
 			bool any_lowq = false, any_hq = false;   // q <= 16 and q >= 22 streams each take one extra kernel
 			for (int i = 0; i < cnt; i++) {
 				const uint64_t o = offsets[a + i] - base, len = offsets[a + i + 1] - offsets[a + i];
-				w.offs_host[i] = o;
+				w.offs_host[i] = o + mis;
 				w.status_host[i] = nhw_parse_header(in + base + o, (size_t)len, &desc[i]);
 				if (quality) quality[a + i] = desc[i].quality;
 				any_lowq |= w.status_host[i] == 0 && desc[i].quality <= 16;
 				any_hq |= w.status_host[i] == 0 && desc[i].quality >= 22;
 			}
-			bool ok = check(cudaMemcpyAsync(w.pack_dev, in + base, total, cudaMemcpyHostToDevice, w.stream), "H2D streams");
+			// (mis: the chunk lands at the same offset modulo 16 as it has in the caller's buffer, so the fetch kernel moves
+			// aligned 16-byte words; the per-stream offsets carry the shift)
+			bool ok = fetch_to_device(&w, w.pack_dev + mis, in + base, in_alias ? in_alias + base : nullptr, total, "H2D streams");
 			// the bit reader may look a few words past the last code: keep that tail defined
-			ok = ok && check(cudaMemsetAsync(w.pack_dev + total, 0, 64, w.stream), "memset tail");
-			ok = ok && check(cudaMemcpyAsync(w.dec_desc_dev, desc, (size_t)cnt * sizeof(DecDesc), cudaMemcpyHostToDevice, w.stream), "H2D desc");
-			ok = ok && check(cudaMemcpyAsync(w.offs_dev, w.offs_host, (size_t)cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, w.stream), "H2D offs");
-			ok = ok && check(cudaMemcpyAsync(w.status_dev, w.status_host, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, w.stream), "H2D status");
+			ok = ok && check(cudaMemsetAsync(w.pack_dev + mis + total, 0, 64, w.stream), "memset tail");
+			ok = ok && fetch_to_device(&w, w.dec_desc_dev, desc, ctx_alias(desc), (size_t)cnt * sizeof(DecDesc), "H2D desc");
+			ok = ok && fetch_to_device(&w, w.offs_dev, w.offs_host, ctx_alias(w.offs_host), (size_t)cnt * sizeof(uint64_t), "H2D offs");
+			ok = ok && fetch_to_device(&w, w.status_dev, w.status_host, ctx_alias(w.status_host), (size_t)cnt * sizeof(int32_t), "H2D status");
 			if (!ok) return NHW_ERR_CUDA;
 			nhw::decode_chunk(&w, w.pack_dev, w.offs_dev, static_cast<const DecDesc *>(w.dec_desc_dev), w.status_dev, cnt, w.rgb, any_lowq, any_hq, yuv != nullptr);
 			if (rgb) cudaMemcpyAsync(rgb + (size_t)a * NHW_RGB_BYTES, w.rgb, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);

@@ -19,6 +19,7 @@ struct NhwTuning {
 	int subs_decode, lanes_decode;   // NHW_SUBS_DECODE (8), NHW_LANES_DECODE (4)
 	int dsf_streams;       // NHW_DSF_STREAMS    streams per warp in the decoder's serial front (4)
 	int rows_grid_cap;     // SM count x NHW_ROWS_CTAS_PER_SM (24): grid cap of the "thread = row" kernels
+	int fetch_kernel;      // NHW_FETCH_KERNEL   decode: stream bytes in pinned host memory are fetched by a kernel, not the copy engine (1)
 };
 
 struct nhw_ctx {

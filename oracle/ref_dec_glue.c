@@ -59,6 +59,14 @@ static int tmp_path(char *path)
 	return 0;
 }
 
+/* Never-written stack memory reads as 0 in the canonical oracle (see ref_enc_glue.c: scrub_stack). */
+static void __attribute__((noinline)) scrub_stack(void)
+{
+	unsigned char pad[768 * 1024];
+	memset(pad, 0, sizeof pad);
+	__asm__ volatile("" : : "r"(pad) : "memory");
+}
+
 /* Decode a .nhw byte string to 786432 BMP pixel bytes (file order, header stripped).
  * planes (optional, 3*262144 bytes) receives the Y,U,V u8 planes decode_image leaves
  * for the writer (decoder/nhw_decoder.c:877-891,1137-1181). */
@@ -82,6 +90,7 @@ long nhwref_decode(const unsigned char *nhw, long len, unsigned char *out_pix, u
 		unlink(in_path);
 		return -(1000 + abs(nhwref_exit_code));
 	}
+	scrub_stack();
 	decode_image(&im, &dec, in_path);
 	unlink(in_path);
 	if (planes) {

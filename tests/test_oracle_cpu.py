@@ -155,3 +155,17 @@ def test_no_gpu_fails_loudly():
         pytest.skip("libnhw_cuda.so not built")
     with pytest.raises(capi.NhwError):
         capi.Codec(device=0, max_batch=1)
+
+
+def test_oracle_does_not_depend_on_call_history(ref):
+    """wavlts2packet reads one entry past its codebook list out of a never-written STACK array
+    (encoder/compress_pixel.c:58,412,446): in-process, what it finds is what earlier encodes left there.  The canonical
+    oracle clears the stack before every call (oracle/ref_enc_glue.c: scrub_stack); natural(1896) at q20 is an image whose
+    luma codebook ends in a marker run, i.e. one that such leftovers can lengthen."""
+    from nhwcodec_b200 import synth
+    x = synth.natural(1896)
+    first = ref.ref_encode(x, 20)
+    for other, q in ((synth.noise(7), 23), (synth.textured(1002), 9), (synth.natural(1768), 20), (synth.noise(8), 17)):
+        ref.ref_encode(other, q)
+        assert ref.ref_encode(x, 20) == first
+    assert first[320] == 0x1C          # the run is not lengthened: never-written memory reads as 0
