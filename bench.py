@@ -48,10 +48,10 @@ ALG_BYTES = {
     "k_dwt_level<256>": 131072 + 131072,                # one level-2 analysis: LL1 in, four level-2 bands out
     "k_dwt_level<256,u8>": 2 * (65536 + 98304 + 32768), # chroma level 1 of both planes: bytes in, 3 bands + LL out
     "k_dwt_level<128>": 2 * (32768 + 32768),            # chroma level 2 of both planes
-    "k_idwt_rows<256>": 2 * 131072,
-    "k_idwt_cols_t<256>": 2 * 131072,
-    "k_idwt_rows<128>": 2 * 2 * 32768,
-    "k_idwt_cols_t<128>": 2 * 2 * 32768,
+    # one synthesis level, band plane in + samples out.  <256> runs four times per round trip: three times on one luma
+    # plane per image (2 x encode, 1 x decode) and once on the two chroma planes (decode, level 1): 1.25 planes per launch
+    "k_idwt_level<256>": 2 * 131072 * 5 // 4,
+    "k_idwt_level<128>": 2 * 2 * 32768,               # chroma level 2, both planes
     "y_quant_scan": 524288 + 262144,                   # coefficient plane in, scan bytes out
     "c_quant_scan": 2 * 131072 + 131072,
     "y_e6d_correct": 2 * 131072 + 2 * 131072,          # trial reconstruction + LL1 in, both corrected out

@@ -1427,6 +1427,58 @@ __global__ void __launch_bounds__(256) k_idwt_cols_t(const int16_t *__restrict__
 	}
 }
 
+// Both passes of one synthesis level in ONE kernel, the band plane held in shared memory (the counterpart of k_dwt_level):
+// load the N x N band plane J(k, m) -> row pass in place (a warp per band row; a lane takes its inputs into registers
+// before any lane writes) -> column pass out of shared memory, normalised, written as natural image rows out(y, x).
+// The row pitch of N + 2 int16 (an odd number of 32-bit words) keeps the column pass's lanes on different banks.
+// Replaces k_idwt_rows + k_idwt_cols_t and the trip of the intermediate plane T through HBM.
+template <int N, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_idwt_level(const int16_t *__restrict__ in, int16_t *__restrict__ out,
+                                                        size_t in_stride, size_t out_stride, int row_stride)
+{
+	extern __shared__ __align__(16) int16_t band[];   // [N][N + 2]
+	constexpr int P = N + 2, M = N / 2, PER = M / 32;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int16_t *src = in + (size_t)blockIdx.x * in_stride;
+	int16_t *dst = out + (size_t)blockIdx.x * out_stride;
+	for (int idx = tid; idx < N * N / 8; idx += THREADS) {
+		const int k = idx / (N / 8), c = idx % (N / 8);
+		const uint4 v = *reinterpret_cast<const uint4 *>(src + (size_t)k * row_stride + c * 8);
+		uint32_t *d = reinterpret_cast<uint32_t *>(band + k * P + c * 8);   // rows are 4-byte aligned only
+		d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+	}
+	__syncthreads();
+	for (int k = warp; k < N; k += THREADS / 32) {
+		int16_t *row = band + k * P;
+		uint32_t o[PER];
+#pragma unroll
+		for (int u = 0; u < PER; u++) {
+			const int t = lane + 32 * u;
+			auto l = [&](int i) { return (int)row[i]; };
+			auto h = [&](int i) { return (int)row[M + i]; };
+			int ev, od;
+			inverse_pair(l, h, t, M, false, ev, od);
+			o[u] = (uint32_t)(uint16_t)ev | ((uint32_t)(uint16_t)od << 16);
+		}
+		__syncwarp();
+#pragma unroll
+		for (int u = 0; u < PER; u++) reinterpret_cast<uint32_t *>(row)[lane + 32 * u] = o[u];
+	}
+	__syncthreads();
+	for (int y = warp; y < N; y += THREADS / 32) {
+		auto l = [&](int i) { return (int)band[i * P + y]; };
+		auto h = [&](int i) { return (int)band[(M + i) * P + y]; };
+		int16_t *row = dst + (size_t)y * row_stride;
+#pragma unroll
+		for (int u = 0; u < PER; u++) {
+			const int t = lane + 32 * u;
+			int ev, od;
+			inverse_pair(l, h, t, M, true, ev, od);
+			*reinterpret_cast<uint32_t *>(row + 2 * t) = (uint32_t)(uint16_t)ev | ((uint32_t)(uint16_t)od << 16);
+		}
+	}
+}
+
 // copy an N x N region between planes of possibly different row strides (one thread per 2 cells)
 __global__ void k_copy_region(const int16_t *__restrict__ src, size_t src_slot, int src_stride,
                               int16_t *__restrict__ dst, size_t dst_slot, int dst_stride, int N)
@@ -1651,6 +1703,8 @@ bool encode_device_init(nhw_ctx *c)
 	ok = ok && check(cudaFuncSetAttribute(k_recons_ll2_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, LL2_SMEM_BYTES), "attr k_recons_ll2_wave");
 	ok = ok && check(cudaFuncSetAttribute(k_idwt_cols_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 33 * 2), "attr k_idwt_cols_t");
 	ok = ok && check(cudaFuncSetAttribute(k_idwt_cols_t<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 33 * 2), "attr k_idwt_cols_t");
+	ok = ok && check(cudaFuncSetAttribute(k_idwt_level<256, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 258 * 2), "attr k_idwt_level");
+	ok = ok && check(cudaFuncSetAttribute(k_idwt_level<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 130 * 2), "attr k_idwt_level");
 	return ok;
 }
 
@@ -1673,30 +1727,24 @@ EncBatch enc_batch_of(nhw_ctx *c)
 	return b;
 }
 
-// luma inverse level-2 transform: jpeg region (256x256) -> proc region, natural orientation
-static void idwt_luma256(nhw_ctx *c, const EncBatch &b, int n)
+// one synthesis level of n_planes N x N band planes (row stride `stride`, planes `slot` apart): in -> out
+static void idwt_level(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *out, size_t slot, int N, int stride)
 {
-	NHW_LAUNCH(c, k_idwt_rows<256>, dim3(256 / 8, n), 256, 0, b.y_jpeg, b.y_aux, (size_t)NHW_Y_SLOT, (size_t)NHW_Y_SLOT, 512);
-	NHW_LAUNCH(c, k_idwt_cols_t<256>, dim3(256 / 32, n), 256, 256 * 33 * 2, b.y_aux, b.y_proc, (size_t)NHW_Y_SLOT, (size_t)NHW_Y_SLOT, 512);
+	if (N == 256) NHW_LAUNCH_L(c, "k_idwt_level<256>", (k_idwt_level<256, 1024>), n_planes, 1024, 256 * 258 * 2, in, out, slot, slot, stride);
+	else NHW_LAUNCH_L(c, "k_idwt_level<128>", (k_idwt_level<128, 256>), n_planes, 256, 128 * 130 * 2, in, out, slot, slot, stride);
 }
 
-// generic form used by the decoder: N x N bands at row stride `stride`, planes `slot` apart
+// luma inverse level-2 transform: jpeg region (256x256) -> proc region, natural orientation
+static void idwt_luma256(nhw_ctx *c, const EncBatch &b, int n) { idwt_level(c, n, b.y_jpeg, b.y_proc, (size_t)NHW_Y_SLOT, 256, 512); }
+
+// generic form used by the decoder (tmp: unused since the two passes became one kernel)
 void idwt_rows_cols(nhw_ctx *c, int n_planes, const int16_t *in, int16_t *tmp, int16_t *out, size_t slot, int N, int stride)
 {
-	if (N == 256) {
-		NHW_LAUNCH(c, k_idwt_rows<256>, dim3(256 / 8, n_planes), 256, 0, in, tmp, slot, slot, stride);
-		NHW_LAUNCH(c, k_idwt_cols_t<256>, dim3(256 / 32, n_planes), 256, 256 * 33 * 2, tmp, out, slot, slot, stride);
-	} else {
-		NHW_LAUNCH(c, k_idwt_rows<128>, dim3(128 / 8, n_planes), 256, 0, in, tmp, slot, slot, stride);
-		NHW_LAUNCH(c, k_idwt_cols_t<128>, dim3(128 / 32, n_planes), 256, 128 * 33 * 2, tmp, out, slot, slot, stride);
-	}
+	(void)tmp;
+	idwt_level(c, n_planes, in, out, slot, N, stride);
 }
 
-static void idwt_chroma128(nhw_ctx *c, const EncBatch &b, int n)
-{
-	NHW_LAUNCH(c, k_idwt_rows<128>, dim3(128 / 8, 2 * n), 256, 0, b.c_jpeg, b.c_aux, (size_t)NHW_C_SLOT, (size_t)NHW_C_SLOT, 256);
-	NHW_LAUNCH(c, k_idwt_cols_t<128>, dim3(128 / 32, 2 * n), 256, 128 * 33 * 2, b.c_aux, b.c_proc, (size_t)NHW_C_SLOT, (size_t)NHW_C_SLOT, 256);
-}
+static void idwt_chroma128(nhw_ctx *c, const EncBatch &b, int n) { idwt_level(c, 2 * n, b.c_jpeg, b.c_proc, (size_t)NHW_C_SLOT, 128, 256); }
 
 static void zero_bytes(nhw_ctx *c, const EncBatch &b, int n, size_t off, size_t count)
 {
@@ -1717,7 +1765,7 @@ static void encode_luma_lowq(nhw_ctx *c, const EncBatch &b, int n, int q, int ra
 		idwt_luma256(c, b, n);
 		NHW_LAUNCH_L(c, "y_e6c_apply", k_e6c_apply, dim3(16, n), 256, 0, b);
 		NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(32, n), 256, 0, b);
-		dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
+		dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512, nullptr, 0);
 	}
 	if (q <= 11) run_rows(c, "y_e7_kill", b, n, 128, [=] __device__(const EncImg &im, int r) { y_e7_kill_row(im, q, ratio, 128 + r); });
 	if (q < 13) NHW_LAUNCH_L(c, "y_e8_smooth", k_e8_staged, n, 32, E8_SMEM, b, q);
@@ -1821,8 +1869,7 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 		c_correct_cells(im.cproc + r * CW, im.cll1 + r * 128, g, v, o);
 		st8(im.cjpeg + r * CW + g * 8, o);
 	});
-	dwt_level_from_jpeg(cs, 2 * n, b.c_jpeg, CS, b.c_proc, CS, 128, 256);
-	NHW_LAUNCH(cs, k_copy_region, dim3(128 * 64 / 256, 2 * n), 256, 0, b.c_proc, CS, 256, b.c_ll2s, QS, 128, 128);
+	dwt_level_from_jpeg(cs, 2 * n, b.c_jpeg, CS, b.c_proc, CS, 128, 256, b.c_ll2s, QS);   // (+ the level-2 snapshot)
 	if (lowq)
 		run_plane_rows(cs, "c_recons0_rows", b, n, 128, [=] __device__(const EncImg &im, int r, int) {
 			if (r < 64) c_recons_ll_row(im, r, 0, q);
@@ -1856,9 +1903,11 @@ void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev
 	idwt_luma256(c, b, n);
 	NHW_LAUNCH_L(c, "y_e6c_apply", k_e6c_apply, dim3(16, n), 256, 0, b);
 	NHW_LAUNCH_L(c, "y_e6d_correct", k_e6d_correct, dim3(32, n), 256, 0, b);
-	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512);
+	dwt_level_from_jpeg(c, n, b.y_jpeg, YS, b.y_proc, YS, 256, 512, nullptr, 0);
 
 	// ---- LL2 coding (nhw_encoder.c:623-757)
+	// (the `resIII` snapshot as a copy of its own: folded into the analysis kernel its second set of transposed 16-byte
+	// stores costs more than this coalesced copy -- 0.92 vs 0.49 + 0.30 ms; the 128 x 128 chroma snapshot is folded)
 	NHW_LAUNCH(c, k_copy_region, dim3(256 * 128 / 256, n), 256, 0, b.y_proc, YS, 512, b.y_ll2s, CS, 256, 256);
 	// LL2 -> bytes (wavefront) and the DPCM coder (step links + chain walk), see enc_ll_par.cuh
 	NHW_LAUNCH_L(c, "y_ll2_code", k_ll2_code, n, 128, LL2_CODE_SMEM, b, q);

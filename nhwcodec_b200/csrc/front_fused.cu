@@ -516,8 +516,11 @@ k_front_luma(const uint8_t *__restrict__ rgb, const int16_t *__restrict__ yplane
 template <int N, typename InT, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_dwt_level(const InT *__restrict__ in, size_t in_slot, int in_stride,
                                                        int16_t *__restrict__ out, size_t out_slot, int out_stride,
-                                                       int16_t *__restrict__ ll, size_t ll_slot)
+                                                       int16_t *__restrict__ ll, size_t ll_slot,
+                                                       int16_t *__restrict__ snap = nullptr, size_t snap_slot = 0)
 {
+	// snap (only with ll == NULL): a second, dense (row stride N) copy of the N x N output -- the closed loop's snapshot
+	// of the level-2 region (`resIII`, encoder/nhw_encoder.c:623-631), which used to be a copy kernel of its own
 	extern __shared__ __align__(16) int16_t band[];   // [N][N]
 	constexpr int H = N / 2;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -569,6 +572,7 @@ __global__ void __launch_bounds__(THREADS) k_dwt_level(const InT *__restrict__ i
 	__syncthreads();
 	// ---- vertical pass: task = (group of 8 outputs, column k); lanes run along k
 	int16_t *llp = ll ? ll + (size_t)blockIdx.x * ll_slot : nullptr;
+	int16_t *sn = snap ? snap + (size_t)blockIdx.x * snap_slot : nullptr;
 	for (int task = tid; task < N * (H / 8); task += THREADS) {
 		const int k = task % N, g = task / N, e0 = 8 * g;
 		const bool fine = k < H;
@@ -589,12 +593,14 @@ __global__ void __launch_bounds__(THREADS) k_dwt_level(const InT *__restrict__ i
 		col_pass8(col, e0, fine, e0 + 8 == H, rem, lo, hi);
 		const uint4 Hh = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
 		*reinterpret_cast<uint4 *>(dst + (size_t)k * out_stride + H + e0) = Hh;
+		if (sn) *reinterpret_cast<uint4 *>(sn + k * N + H + e0) = Hh;
 		if (fine && llp) {
 #pragma unroll
 			for (int s = 0; s < 8; s++) llp[(e0 + s) * H + k] = (int16_t)lo[s];
 		} else {
 			const uint4 L = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
 			*reinterpret_cast<uint4 *>(dst + (size_t)k * out_stride + e0) = L;
+			if (sn) *reinterpret_cast<uint4 *>(sn + k * N + e0) = L;
 		}
 	}
 }
@@ -618,10 +624,10 @@ __global__ void k_color_check(ColorParams p, unsigned long long *bad)
 
 template <int N, typename InT, int THREADS>
 void launch_level(nhw_ctx *c, const char *label, int n_planes, const InT *in, size_t in_slot, int in_stride, int16_t *out,
-                  size_t out_slot, int out_stride, int16_t *ll, size_t ll_slot)
+                  size_t out_slot, int out_stride, int16_t *ll, size_t ll_slot, int16_t *snap = nullptr, size_t snap_slot = 0)
 {
 	NHW_LAUNCH_L(c, label, (k_dwt_level<N, InT, THREADS>), n_planes, THREADS, N * N * 2, in, in_slot, in_stride, out, out_slot,
-	             out_stride, ll, ll_slot);
+	             out_stride, ll, ll_slot, snap, snap_slot);
 }
 
 }  // namespace
@@ -702,12 +708,12 @@ long color_fast_path_mismatches(nhw_ctx *c)
 // one more analysis level of a band held in `im_jpeg` orientation (closed loop,
 // encoder/nhw_encoder.c:281,2339)
 void dwt_level_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
-                         int N, int row_stride)
+                         int N, int row_stride, int16_t *snap, size_t snap_slot)
 {
 	if (N == 256)
-		launch_level<256, int16_t, 1024>(c, "k_dwt_level<256>", n_planes, jpeg, jstride, row_stride, proc, pstride, row_stride, nullptr, 0);
+		launch_level<256, int16_t, 1024>(c, "k_dwt_level<256>", n_planes, jpeg, jstride, row_stride, proc, pstride, row_stride, nullptr, 0, snap, snap_slot);
 	else
-		launch_level<128, int16_t, 256>(c, "k_dwt_level<128>", n_planes, jpeg, jstride, row_stride, proc, pstride, row_stride, nullptr, 0);
+		launch_level<128, int16_t, 256>(c, "k_dwt_level<128>", n_planes, jpeg, jstride, row_stride, proc, pstride, row_stride, nullptr, 0, snap, snap_slot);
 }
 
 }  // namespace nhw

@@ -96,7 +96,7 @@ void front_fused(nhw_ctx *c, const uint8_t *rgb, int n, int quality, int16_t *y_
 long color_fast_path_mismatches(nhw_ctx *c);
 long dec_color_fast_path_mismatches(nhw_ctx *c);   // decode.cu
 void dwt_level_from_jpeg(nhw_ctx *c, int n_planes, const int16_t *jpeg, size_t jstride, int16_t *proc, size_t pstride,
-                         int N, int row_stride);
+                         int N, int row_stride, int16_t *snap, size_t snap_slot);
 
 // encode.cu
 void encode_chunk(nhw_ctx *c, const uint8_t *rgb, int n, int q, uint8_t *out_dev, uint32_t *len_dev, int32_t *status_dev);
