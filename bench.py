@@ -520,9 +520,12 @@ def run_ours(args):
     if dist is not None:
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
+        # events on torch's current stream: the point-to-point operations are ordered against it (the pack kernel runs on the
+        # codec's stream inside a call that returns after it has finished)
+        g0.record()
         allb, alloffs = gather_step()
-        g1.record(stream)
+        g1.record()
+        torch.cuda.synchronize()
         barrier()
         tg = reduce_max(g0.elapsed_time(g1))
         total_bytes = int(alloffs[-1].item())

@@ -184,6 +184,9 @@ def config4(args):
     bytes_streams = 0
     checked = 0
     if dist is not None:
+        # NCCL sets its point-to-point connections up on first use (hundreds of milliseconds for seven peers): once, here
+        warm = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+        shard.gather_streams(warm, torch.full((4,), 1024, dtype=torch.int32, device="cuda"), 4 * world)
         dist.barrier()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()

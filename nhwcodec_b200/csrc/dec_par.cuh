@@ -13,8 +13,6 @@
 #include "dec_stages.cuh"
 #include "cells8.cuh"
 
-// D8: cell (r, j), 1 <= r, j <= 254, of the level-2 region of J (stride 512)
-NHW_HD WfGeom dwf_shrink_geom() { return WfGeom{1, 254, 1, 254, 2}; }
 NHW_HD int dwf_shrink_cell(int16_t *J, int r, int j)
 {
 	const int s = r * YW + j;
@@ -40,8 +38,6 @@ NHW_HD void dec_shrink_lowq_cell(int16_t *J, int r, int j)
 	if (r >= 128 || j >= 128) J[s] += J[s] > 0 ? -1 : 1;
 }
 
-// D11: pair p (columns 1+2p, 2+2p), 0 <= p <= 126, rows 1..254 of the reconstructed LL1 (stride 512)
-NHW_HD WfGeom dwf_edge_geom() { return WfGeom{1, 254, 0, 127, 2}; }
 NHW_HD int dwf_edge_cell(int16_t *P, int r, int p)
 {
 	const int s = r * YW + 1 + 2 * p;
@@ -54,8 +50,6 @@ NHW_HD int dwf_edge_cell(int16_t *P, int r, int p)
 	return 1;
 }
 
-// D16: chroma sharpen cell (r, j), 1 <= r, j <= 254 (stride 256)
-NHW_HD WfGeom dwf_sharpen_geom() { return WfGeom{1, 254, 1, 254, 2}; }
 NHW_HD int dwf_sharpen_cell(int16_t *P, int thr, int r, int j)
 {
 	const int s = r * CW + j;

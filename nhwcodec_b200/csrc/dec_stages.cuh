@@ -4,19 +4,6 @@
 #pragma once
 #include "dec_core.cuh"
 
-// ---- D2: inverse serpentine scan (nhw_decoder.c:71-91): coefficient stream -> transposed plane
-NHW_HD void dec_y_descan_strip(const int16_t *coef, int16_t *J, int strip /* 0..127 */)
-{
-	const int16_t *s = coef + strip * 2048;
-	int16_t *P = J + strip * 4;
-	for (int k = 0; k < 256; k++) {
-		int16_t *r0 = P + (2 * k) * YW, *r1 = r0 + YW;
-		r0[0] = s[0]; r0[1] = s[1]; r0[2] = s[2]; r0[3] = s[3];
-		r1[3] = s[4]; r1[2] = s[5]; r1[1] = s[6]; r1[0] = s[7];
-		s += 8;
-	}
-}
-
 // ---- D3: expand + split the side-channel lists (nhw_decoder.c:93-491).  list_len[8] receives
 // the value the reference's `count` variable is left with (it is read, stale, by D4).
 #define DEC_LIST_CAP 65536   // entries per expanded list (and of `tmp`); nhw_parse_header rejects streams that need more
@@ -184,83 +171,10 @@ NHW_HDN int dec_y_ll_overrides(const DecImg &im)
 	return i;   // exw1: where the chroma entries start (after the 0,0 separator)
 }
 
-NHW_HDN int dec_y_ll_image(const DecImg &im)
-{
-	for (int r = 0; r < 128; r++)
-		for (int j = 0; j < 128; j++) im.jpeg[r * YW + j] = im.res_comp[r * 128 + j];
-	return dec_y_ll_overrides(im);
-}
-
-// ---- D8: shrink isolated coefficients of the level-2 bands, in place (nhw_decoder.c:685-711)
-// q <= 16 tolerates diagonal neighbours up to 16 (nhw_decoder.c:660-684)
-NHW_HDN void dec_y_shrink_image(const DecImg &im)
-{
-	int16_t *J = im.jpeg;
-	const int dg = im.d->quality <= 16 ? 16 : 8;
-	for (int r = 1; r < 255; r++)
-		for (int j = 1; j < 255; j++) {
-			const int s = r * YW + j;
-			if (nhw_iabs(J[s]) <= 8) continue;
-			if (nhw_iabs(J[s - YW - 1]) > dg || nhw_iabs(J[s - YW]) > 8 || nhw_iabs(J[s - YW + 1]) > dg ||
-			    nhw_iabs(J[s - 1]) > 8 || nhw_iabs(J[s + 1]) > 8 || nhw_iabs(J[s + YW - 1]) > dg ||
-			    nhw_iabs(J[s + YW]) > 8 || nhw_iabs(J[s + YW + 1]) > dg)
-				continue;
-			if (r >= 128 || j >= 128) J[s] += J[s] > 0 ? -1 : 1;
-		}
-}
-
-// ---- D10: residual add-backs on the reconstructed LL1 (nhw_decoder.c:721-787)
-NHW_HDN void dec_y_addbacks_image(const DecImg &im)
-{
-	int16_t *P = im.proc;
-	const int q = im.d->quality;
-	auto at = [](uint16_t v) { return ((v & 65280) << 1) + (v & 255); };
-	if (q >= 21) {
-		for (int i = 0; i < im.list_len[2]; i++) P[at(im.list[2][i])] -= 3;
-		for (int i = 0; i < im.list_len[3]; i++) P[at(im.list[3][i])] += 3;
-	}
-	if (q > 12) {
-		const int e = q >= 18 ? 5 : q >= 15 ? 7 : 9;
-		for (int i = 0; i < im.list_len[0]; i++) P[at(im.list[0][i])] -= e;
-		for (int i = 0; i < im.list_len[1]; i++) P[at(im.list[1][i])] += e;
-	}
-	if (q >= 19) {
-		for (int i = 0; i < im.list_len[5]; i++) { const int a = at(im.list[5][i]); P[a] -= 4; P[a + YW] -= 3; }
-		for (int i = 0; i < im.list_len[4]; i++) { const int a = at(im.list[4][i]); P[a] += 4; P[a + YW] += 3; }
-		for (int i = 0; i < im.list_len[6]; i++) { const int a = at(im.list[6][i]); P[a] += 2; P[a + YW] += 2; P[a + 2 * YW] += 2; }
-		for (int i = 0; i < im.list_len[7]; i++) { const int a = at(im.list[7][i]); P[a] -= 2; P[a + YW] -= 2; P[a + 2 * YW] -= 2; }
-	}
-}
-
 NHW_HD int dec_lap8(const int16_t *P, int s, int stride)
 {
 	return (P[s] << 3) - P[s - 1] - P[s + 1] - P[s - stride] - P[s + stride] - P[s - stride - 1] - P[s + stride - 1] -
 	       P[s - stride + 1] - P[s + stride + 1];
-}
-
-// ---- D11+D12: edge flags on LL1 (flagged cells carry +16000 while the pass runs, so later
-// stencils see them), then the flag list in raster order (nhw_decoder.c:789-839)
-NHW_HDN void dec_y_edge_flags_image(const DecImg &im)
-{
-	int16_t *P = im.proc;
-	for (int r = 1; r < 255; r++)
-		for (int j = 1; j < 254; j++) {
-			int s = r * YW + j;
-			const int res = dec_lap8(P, s, YW);
-			j++; s++;
-			const int cnt = dec_lap8(P, s, YW);
-			if (res > 41 && res < 108 && cnt < 16) P[s - 1] += 16000;
-			else if (res < -41 && res > -108 && cnt > -16) P[s - 1] += 16000;
-			else if (cnt > 41 && cnt < 108 && res < 16) P[s] += 16000;
-			else if (cnt < -41 && cnt > -108 && res > -16) P[s] += 16000;
-		}
-	int n = 0;
-	for (int r = 1; r < 255; r++)
-		for (int j = 0; j < 256; j++) {
-			const int s = r * YW + j;
-			if (P[s] > 10000) { im.flags[n++] = (uint16_t)((r << 8) + j); P[s] -= 16000; }
-		}
-	im.list_len[9] = n;
 }
 
 // ---- D14: conditional 5-tap smoothing at the flagged positions, list order (nhw_decoder.c:848-867)
@@ -273,22 +187,7 @@ NHW_HDN void dec_y_smooth_flags_plane(const DecImg &im, int16_t *J /* the half-s
 	}
 }
 
-NHW_HDN void dec_y_smooth_flags_image(const DecImg &im) { dec_y_smooth_flags_plane(im, im.jpeg); }
-
 NHW_HD uint8_t dec_clip8(int v) { return (uint8_t)((v >> 8) != 0 ? (v < 0 ? 0 : 255) : v); }
-
-// ---- chroma (nhw_decoder.c:895-1183 / 1185-1474), one component
-NHW_HD void dec_c_descan_strip(const int16_t *coef, int16_t *J, int strip /* 0..31 */, int is_v)
-{
-	const int16_t *s = coef + is_v + strip * 4096;
-	int16_t *P = J + strip * 8;
-	for (int k = 0; k < 128; k++) {
-		int16_t *r0 = P + (2 * k) * CW, *r1 = r0 + CW;
-		for (int t = 0; t < 8; t++) r0[t] = s[2 * t];
-		for (int t = 0; t < 8; t++) r1[7 - t] = s[16 + 2 * t];
-		s += 32;
-	}
-}
 
 // the exw escape entries of one chroma component; exw_pos = index into the exw list (returned advanced past them)
 NHW_HDN int dec_c_ll_overrides(const DecImg &im, int exw_pos)
@@ -336,42 +235,6 @@ NHW_HDN void dec_c_markers_image(const DecImg &im)
 			else if (v == 5003) { P[t] -= 6; J[s] = 0; }
 			else if (v == 5004) { P[t] += 6; J[s] = 0; }
 		}
-}
-
-// in-place 8-neighbour sharpen, raster order (nhw_decoder.c:1085-1109), then clip to 0..255
-NHW_HDN void dec_c_sharpen_image(const DecImg &im)
-{
-	int16_t *P = im.cproc;
-	const int thr = im.d->quality <= 14 ? 35 : 60;
-	for (int r = 1; r < 255; r++)
-		for (int j = 1; j < 255; j++) {
-			const int s = r * CW + j;
-			const int res = dec_lap8(P, s, CW);
-			if (nhw_iabs(res) > thr) {
-				if (res > 0) P[s] += res > 160 ? 3 : 2;
-				else P[s] -= res < -160 ? 3 : 2;
-			}
-		}
-	for (int i = 0; i < 65536; i++)
-		if ((P[i] >> 8) != 0) P[i] = (int16_t)(P[i] < 0 ? 0 : 255);
-}
-
-// 2x upsample of the clipped 256x256 plane to 512x512 bytes: rows first, then columns, both
-// (a+b+1)>>1 with the last row/column repeated (nhw_decoder.c:1137-1181)
-NHW_HD void dec_c_upsample_row(const int16_t *P, uint8_t *out, int y /* 0..511 */)
-{
-	const int r = y >> 1;
-	auto v = [&](int c) -> int {
-		if ((y & 1) == 0 || r == 255) return P[r * CW + c];
-		return (P[r * CW + c] + P[(r + 1) * CW + c] + 1) >> 1;
-	};
-	uint8_t *o = out + y * 512;
-	for (int c = 0; c < 255; c++) {
-		const int a = (uint8_t)v(c), b = (uint8_t)v(c + 1);
-		o[2 * c] = (uint8_t)a;
-		o[2 * c + 1] = (uint8_t)((a + b + 1) >> 1);
-	}
-	o[510] = o[511] = (uint8_t)v(255);
 }
 
 // ---- D17: YCbCr -> RGB (nhw_decoder_cli.c:139-229), IEEE-exact like the encoder's colour stage.

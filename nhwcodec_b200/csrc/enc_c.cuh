@@ -156,95 +156,6 @@ NHW_HD void c_ll_bit1_plane(const EncImg &im, int is_v)
 	}
 }
 
-// ---- offsetUV (image_processing.c:108-183): chroma coefficient -> byte, flat raster order
-NHW_HDN void c_offset_quant_image(const EncImg &im, int m2)
-{
-	int16_t *P = im.cproc;
-	for (int i = 0; i < 65536; i++) {
-		int a = P[i];
-		if (a > 10000) {
-			int b = a == 12400 ? 124 : a == 12600 ? 126 : a == 12900 ? 122 : a == 13000 ? 130 : -1;
-			if (b >= 0) { P[i] = (int16_t)b; continue; }
-		}
-		if (a > 127) {
-			int k = ((a & 0xfff8) - 128) >> 3;
-			P[i] = NHW_EXTRA1(k > 18 ? 18 : k);
-			continue;
-		} else if (a < -127) {
-			int k = (((-a) & 0xfff8) - 128) >> 3;
-			P[i] = NHW_EXTRA2(k > 18 ? 18 : k);
-			continue;
-		}
-		bool neg = a < 0;
-		if (a == -7 || a == -8) {
-			if ((i & 255) < 255 && (P[i + 1] == -7 || P[i + 1] == -8)) { P[i] = 120; P[i + 1] = 120; i++; continue; }
-		}
-		if (neg) {
-			a = -a;
-			if (P[i + 1] < 0 && P[i + 1] > -8) { if ((a & 7) < 6) a &= 504; }
-			else if ((a & 7) < 7) a &= 504;
-			a = -a;
-		} else if (a > 6 && (a & 7) >= 6) {
-			if ((i & 255) < 255 && P[i + 1] == 7) P[i + 1] = 8;
-		}
-		if (a < m2 && a > -m2) { P[i] = 128; continue; }
-		P[i] = (int16_t)((a + 128) & 248);
-	}
-}
-
-// Row form of offsetUV.  The only cross-row access is the un-guarded look at P[i+1] from the last
-// column (image_processing.c:151-154): `next0` is the next row's first cell BEFORE it is quantised
-// (0 after the last row).
-NHW_HD void c_offset_quant_row(const EncImg &im, int m2, int r, int next0)
-{
-	int16_t *P = im.cproc + r * CW;
-	for (int c = 0; c < 256; c++) {
-		const bool inrow = c < 255;
-		int a = P[c];
-		if (a > 10000) {
-			int b = a == 12400 ? 124 : a == 12600 ? 126 : a == 12900 ? 122 : a == 13000 ? 130 : -1;
-			if (b >= 0) { P[c] = (int16_t)b; continue; }
-		}
-		if (a > 127) {
-			int k = ((a & 0xfff8) - 128) >> 3;
-			P[c] = NHW_EXTRA1(k > 18 ? 18 : k);
-			continue;
-		} else if (a < -127) {
-			int k = (((-a) & 0xfff8) - 128) >> 3;
-			P[c] = NHW_EXTRA2(k > 18 ? 18 : k);
-			continue;
-		}
-		const int nxt = inrow ? (int)P[c + 1] : next0;
-		const bool neg = a < 0;
-		if (a == -7 || a == -8) {
-			if (inrow && (nxt == -7 || nxt == -8)) { P[c] = 120; P[c + 1] = 120; c++; continue; }
-		}
-		if (neg) {
-			a = -a;
-			if (nxt < 0 && nxt > -8) { if ((a & 7) < 6) a &= 504; }
-			else if ((a & 7) < 7) a &= 504;
-			a = -a;
-		} else if (a > 6 && (a & 7) >= 6) {
-			if (inrow && nxt == 7) P[c + 1] = 8;
-		}
-		if (a < m2 && a > -m2) { P[c] = 128; continue; }
-		P[c] = (int16_t)((a + 128) & 248);
-	}
-}
-
-// ---- chroma scan: 8-column strips, two rows per step, U on even / V on odd bytes from 262144
-NHW_HD void c_scan_strip(const EncImg &im, int strip /* 0..31 */, int is_v)
-{
-	const int16_t *P = im.cproc + strip * 8;
-	uint8_t *s = im.scan + 262144 + is_v + strip * 4096;
-	for (int k = 0; k < 128; k++) {
-		const int16_t *r0 = P + (2 * k) * CW, *r1 = r0 + CW;
-		for (int t = 0; t < 8; t++) s[2 * t] = (uint8_t)r0[t];
-		for (int t = 0; t < 8; t++) s[16 + 2 * t] = (uint8_t)r1[7 - t];
-		s += 32;
-	}
-}
-
 // ---- highres_compression (compress_pixel.c:878-1022): both chroma LL planes, appended to
 // the luma LL code.  in: tree1[16384..24575]; io: im.llcode (highres_comp) from y_res_comp on.
 // Core: x = the LL bytes indexed as in tree1 (x[16384..24575] valid and already masked with 252, readable up

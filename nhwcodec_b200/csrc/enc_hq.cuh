@@ -40,16 +40,6 @@ NHW_HD int hq_e17_delta(int code, int (&d)[3])
 	return 1;
 }
 
-NHW_HDN void hq_e17_image(const EncImg &im)
-{
-	for (int r = 0; r < 256; r++)
-		for (int j = 0; j < 254; j++) {
-			int d[3];
-			if (!hq_e17_delta(im.ll1[r * 256 + j], d)) continue;
-			for (int k = 0; k < 3; k++) im.hq_fo[j * 256 + r + k] = (int16_t)(im.hq_fo[j * 256 + r + k] + d[k]);
-		}
-}
-
 // ---- LH1 from its bytes.  byte_at(c) = quantised byte of LH1 cell c = row*256 + col (the band is
 // rows 0..255, columns 256..511 of the coefficient plane).  The reference walks the cells in order,
 // a 127/129 byte ("three in a row") writes the cells left and right of it as well and skips the next
@@ -108,10 +98,6 @@ NHW_HD void hq_tag_pair(const EncImg &im, int q, int r, int t)   // outputs 2t, 
 		tag[2 * t + k] = (uint8_t)g;
 	}
 }
-NHW_HD void hq_tag_row(const EncImg &im, int q, int r)
-{
-	for (int t = 0; t < 256; t++) hq_tag_pair(im, q, r, t);
-}
 
 // positions + sign words of one row (two halves, each closed by the marker 254); returns entries written
 // to pos (markers included); nw = sign words written.  pos/wrd may be NULL to count only.
@@ -132,41 +118,4 @@ NHW_HD int hq_collect_row(const EncImg &im, int r, uint8_t *pos, uint8_t *wrd, i
 		}
 	}
 	return n;
-}
-
-// ---- everything after the tags, serially (the lists are short): char_res1, high_qsetting3, and the
-// res6 position list through the same pruning / packing as res1 (y_e18_finish_list_image, which = 6)
-NHW_HDN int hq_lists_image(const EncImg &im, int q)
-{
-	EncHdr *h = im.hdr;
-	int total = 0;
-	for (int r = 0; r < 256; r++) { int nw; total += hq_collect_row(im, r, nullptr, nullptr, nw); }
-	if (total + 16 > NHW_CAP_LIST) return NHW_ERR_OVERFLOW_DEV;
-	int count = 0, e = 0, res = 0;
-	for (int r = 0; r < 256; r++) {
-		int nw;
-		count += hq_collect_row(im, r, im.tmp1 + count, im.tmp3 + e, nw);
-		e += nw;
-		const uint8_t *tag = im.hq_tag + r * 512;
-		for (int k = 0; k < 2; k++) {
-			const int g = tag[254 + k];
-			if (g == 1 || g == 2) {
-				if (res >= NHW_CAP_CHAR_RES1) return NHW_ERR_OVERFLOW_DEV;
-				im.char_res1[res++] = (uint16_t)(r * 256 + 2 * k + (g - 1));
-			}
-		}
-	}
-	h->char_res1_len = res;
-	int n3 = 0;
-	if (q > 22)
-		for (int i = 0; i < 131072; i++) {
-			const int g = im.hq_tag[i];
-			if (g == 3 || g == 4) {
-				if (n3 >= NHW_CAP_QSETTING3) return NHW_ERR_OVERFLOW_DEV;
-				im.qsetting3[n3++] = (uint32_t)(i << 1) + (g == 4 ? 1u : 0u);
-			}
-		}
-	h->qsetting3_len = n3;
-	y_e18_finish_list_image(im, 6, count, e);
-	return 0;
 }

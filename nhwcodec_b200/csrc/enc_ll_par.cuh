@@ -45,31 +45,6 @@ NHW_HD int ll2_bytes_cell(int16_t *P, int PS, int16_t *V, int q, int r, int j)
 
 NHW_HD bool ll2_is_escape(int scan, int a) { return (scan > 255 || scan < 0) && a > 0; }
 
-// byte stores of one non-escape cell
-NHW_HD void ll2_bytes_store(const EncImg &im, int a, int scan)
-{
-	if (scan > 255) scan = 255;
-	else if (scan < 0) scan = 0;
-	im.ch_res[a] = (uint8_t)scan;
-	im.tree1[a] = (uint8_t)(scan & 254);
-}
-
-// escape cell a (visited in raster order): copies the previous byte, appends to exw_Y.  e = list length
-NHW_HD void ll2_bytes_escape(const EncImg &im, int a, int scan, int &e)
-{
-	im.exw[e++] = (uint8_t)(a >> 7);
-	if (scan > 255) {
-		im.exw[e++] = (uint8_t)((a & 127) + 128);
-		const int y = scan - 255;
-		im.exw[e++] = (uint8_t)(y > 255 ? 255 : y);
-	} else {
-		im.exw[e++] = (uint8_t)(a & 127);
-		im.exw[e++] = (uint8_t)(scan < -255 ? 255 : -scan);
-	}
-	im.tree1[a] = im.tree1[a - 1];
-	im.ch_res[a] = im.tree1[a - 1];
-}
-
 // ---- DPCM coder ------------------------------------------------------------------------------------
 // run statistics of one run of equal neighbours starting at i (x[i]==x[i-1], x[i-1]!=x[i-2] or i==1):
 // adds the run's contribution to (a8, y16) exactly like the reference's counting loop
@@ -167,30 +142,4 @@ NHW_HD LlStep ll_dpcm_step(const uint8_t *x, int i, int mode, int q)
 	s.next = i + 1;   // the for-loop's i++
 	(void)i0;
 	return s;
-}
-
-// serial reference of the whole coder built on the step function (host harness / fallback shape)
-NHW_HDN int ll_dpcm_luma_steps(const EncImg &im, const uint8_t *x, int q)
-{
-	EncHdr *h = im.hdr;
-	const int N = 16384;
-	int a8 = 0, y16 = 0;
-	for (int i = 1; i < N; i++)
-		if (x[i] == x[i - 1] && (i == 1 || x[i - 1] != x[i - 2])) ll_stats_run(x, i, N, a8, y16);
-	const int mode = y16 > 299 ? 2 : (a8 + y16 > 179 ? 1 : 0);
-	uint8_t *out = im.llcode;
-	out[0] = x[0];
-	int o = 1, nmem = 0;
-	for (int i = 1; i < N;) {
-		const LlStep s = ll_dpcm_step(x, i, mode, q);
-		out[o++] = s.b[0];
-		if (s.nbytes == 2) out[o++] = s.b[1];
-		if (s.raw) { im.highres_word[nmem] = im.ch_res[i]; im.highres_mem[nmem++] = (uint16_t)i; }
-		i = s.next;
-	}
-	h->highres_comp_len = nmem;
-	h->highres_mem_len = nmem;
-	h->res_low = mode;
-	h->y_res_comp = o;
-	return mode;
 }

@@ -238,7 +238,6 @@ NHW_HDN int packet_stream_image(const EncImg &im, int part, int &a)
 // ---- container.  Returns the stream length.
 NHW_HD void put16(uint8_t *&p, int v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p += 2; }
 NHW_HD void put32(uint8_t *&p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); p += 4; }
-NHW_HD void putn(uint8_t *&p, const uint8_t *src, int n) { for (int i = 0; i < n; i++) p[i] = src[i]; p += n; }
 
 // The container as an ordered list of byte ranges: `hdr` receives the header fields (<= 64 bytes, returned
 // length), section(src, n) is called for every section in file order.  Multi-byte section elements

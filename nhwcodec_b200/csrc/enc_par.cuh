@@ -16,20 +16,6 @@
 // ---- wavefront geometry of each stage -------------------------------------------------------
 struct WfGeom { int r0, rows, c0, cols, skew; };
 
-// offsetY_recons256 pattern substitution: region A then region B (image_processing.c:2759-2849).
-// cell (r,j) reads (r,j-1..j+1),(r+1,j-1..j); writes (r,j-1),(r,j),(r+1,j-1),(r+1,j): skew 3.
-NHW_HD WfGeom wf_recons_patterns_geom(int region) { return region == 0 ? WfGeom{0, 128, 129, 126, 3} : WfGeom{128, 127, 1, 254, 3}; }
-// returns the number of columns consumed (1 or 2)
-NHW_HD int wf_recons_patterns_cell(const EncImg &im, int r, int j)
-{
-	int a = r * YW + j, jj = j;
-	recons_pattern_cell(im.proc, im.jpeg, a, jj);
-	return jj - j + 1;
-}
-
-// offsetY_recons256 isolated-coefficient shrink (image_processing.c:3162-3187): reads all 8
-// neighbours, row above edited, row below not; writes (r,j): skew 2.
-NHW_HD WfGeom wf_shrink_geom() { return WfGeom{1, 254, 1, 254, 2}; }
 NHW_HD int wf_shrink_cell(const EncImg &im, int r, int j)
 {
 	int16_t *J = im.jpeg;
@@ -43,22 +29,6 @@ NHW_HD int wf_shrink_cell(const EncImg &im, int r, int j)
 	return 1;
 }
 
-// clean-up of the level-1 detail bands (nhw_encoder.c:1923-2098), three passes.
-// cell (r,j) reads (r-1,j) edited, (r+1,j) un-edited, (r,j-1..j+2); writes (r,j),(r,j+1): skew 2.
-NHW_HD WfGeom wf_e20_geom(int pass) { return pass == 0 ? WfGeom{1, 254, 257, 254, 2} : pass == 1 ? WfGeom{256, 255, 1, 255, 2} : WfGeom{256, 255, 257, 254, 2}; }
-NHW_HD int wf_e20_cell(const EncImg &im, int q, int ratio, int pass, int r, int j)
-{
-	int yw, yw2, lo, jmax;
-	if (pass == 0) { if (q > 22) { yw = 8; yw2 = 4; } else { yw = 9; yw2 = 9; } lo = ratio - 2; jmax = 510; }
-	else if (pass == 1) { if (q > 22) { yw = 8; yw2 = 4; } else if (q > 17) { yw = 8; yw2 = 9; } else { yw = 9; yw2 = 9; } lo = ratio - 2; jmax = 254; }
-	else { yw = q > 22 ? 8 : 11; yw2 = yw; lo = ratio - 1; jmax = 510; }
-	e20_cell(im.proc, r * YW + j, j, jmax, lo, yw, yw2, pass);
-	return 1;
-}
-
-// offsetY pattern marks in the level-2 region (image_processing.c:239-290): same footprint as
-// the recons patterns: skew 3.
-NHW_HD WfGeom wf_offset_patterns_geom() { return WfGeom{0, 256, 1, 254, 3}; }
 NHW_HD int wf_offset_patterns_cell(const EncImg &im, int r, int j)
 {
 	int16_t *P = im.proc;
@@ -116,63 +86,12 @@ NHW_HD void y_offset_mult8_row(const EncImg &im, int r /* 0..511 */)
 	}
 }
 
-// offsetY loop 4 (image_processing.c:312-519), one row.  `next0` is the NOT YET QUANTISED first
-// cell of the next row (0 after the last row): the one place the reference looks across the
-// row end without a bounds test.
-NHW_HD void y_offset_quant_row(const EncImg &im, int m1, int r, int next0)
-{
-	int16_t *P = im.proc + r * YW;
-	for (int c = 0; c < 512; c++) {
-		const bool inrow = c < 511;
-		const int nxt = inrow ? (int)P[c + 1] : next0;
-		int a = P[c];
-		if (a > 10000) {
-			int b = a == 10100 ? 128 : a == 12700 ? 127 : a == 12900 ? 129 : a == 10204 ? 125 : a == 10300 ? 126 :
-			        a == 12100 ? 121 : a == 12200 ? 122 : -1;
-			if (b >= 0) { P[c] = (int16_t)b; continue; }
-		}
-		if (a > 127) {
-			int k = ((a & 0xfff8) - 128) >> 3;
-			P[c] = NHW_EXTRA1(k > 18 ? 18 : k);
-			continue;
-		} else if (a < -127) {
-			int k = (((-a) & 0xfff8) - 128) >> 3;
-			P[c] = NHW_EXTRA2(k > 18 ? 18 : k);
-			continue;
-		}
-		if (a < -12 && ((-a) & 7) == 6) {
-			if (inrow && nxt == -7) P[c + 1] = -9;
-		}
-		if (a < 0) {
-			const int nx = inrow ? (int)P[c + 1] : next0;   // may just have become -9
-			if (a == -7 && nx == 8 && inrow) { P[c] = -8; a = -8; }
-			a = -a;
-			if (a > 14 && (a & 7) == 7 && nx > 0 && nx < 8) a -= 2;
-			if ((a & 7) < 7) a &= 504;
-			a = -a;
-		} else if (a == 8 && nxt == -7 && inrow) P[c + 1] = -8;
-		else if (a > 12 && (a & 7) >= 6) {
-			if (inrow && nxt == 7) P[c + 1] = 9;
-		}
-		if (a < m1 && a > -m1) { P[c] = 128; continue; }
-		P[c] = (int16_t)((a + 128) & 248);
-	}
-}
-
 // ---- residual coding with concurrent columns ---------------------------------------------------
 // snapshot layout inside the scratch plane: rows 0..257 of `proc` at the same flat indices,
 // then the 65536 LL1 cells followed by 1024 zeros (reads past the end must see 0).
 #define E16_SNAP_P_CELLS (258 * 512)
 #define E16_SNAP_L_OFF (260 * 512)
 #define E16_SNAP_L_CELLS (65536 + 1024)
-
-// ---- LL2 part of offsetY_recons256 (image_processing.c:2610-2737) in parallel form --------------
-// P = LL2 band at row stride PS (shared-memory copy), J = im_jpeg (stride 512).
-//   1. quad tagging: rows independent
-//   2. main loop: cell (r,j) reads (r,j..j+2),(r+1,j..j+2),(r+2,j),(r+3,j) and writes (r,j),(r,j+1),
-//      (r+1,j): the row above must be 3 columns ahead -> wavefront, skew 3
-//   3. second call only: un-tag + copy to jpeg (cells independent), then the highres_mem fix-ups
-NHW_HD WfGeom wf_ll2_geom() { return WfGeom{0, 128, 0, 128, 3}; }
 
 NHW_HD void y_recons_ll2_tag_row(int16_t *P, int PS, int r, int part)
 {
@@ -219,19 +138,4 @@ NHW_HD int y_recons_ll2_cell(int16_t *P, int PS, int16_t *J, int q, int part, in
 	ll2_parity_nudge(P, PS, a, r, j, P[a], q);
 	if (part) J[aj] = (P[a] > 0 && P[a] < 256) ? (int16_t)(P[a] & 65534) : P[a];
 	return 1;
-}
-
-NHW_HD void y_recons_ll2_tail_row(int16_t *P, int PS, int16_t *J, int16_t *tmp, int r)
-{
-	int a = r * PS, aj = r * YW, t = r * 128;
-	for (int j = 0; j < 128; j++, a++, aj++, t++) {
-		if (P[a] < 10000) {
-			tmp[t] = P[a];
-			J[aj] = (P[a] >= 0 && P[a] < 256) ? (int16_t)(P[a] & 65534) : P[a];
-		} else {
-			P[a] -= 16000;
-			tmp[t] = P[a];
-			J[aj] = P[a];
-		}
-	}
 }

@@ -91,10 +91,3 @@ NHW_HD int c_quant_byte(int o, int op1, int left_run, bool run_pre_bumps, bool i
 	if (a < m2 && a > -m2) return 128;
 	return (a + 128) & 248;
 }
-
-// position of chroma cell (row, col) of plane is_v in the scan buffer: 8-column strips, U on even bytes
-NHW_HD int c_scan_pos(int row, int col, int is_v)
-{
-	const int t = col & 7;
-	return 262144 + is_v + (col >> 3) * 4096 + (row >> 1) * 32 + ((row & 1) ? 16 + 2 * (7 - t) : 2 * t);
-}

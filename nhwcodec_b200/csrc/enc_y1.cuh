@@ -119,11 +119,6 @@ NHW_HDN void y_recons_ll2_core(int16_t *P, int PS, int16_t *J, int16_t *tmp, con
 	}
 }
 
-NHW_HDN void y_recons_ll2_image(const EncImg &im, int q, int part)
-{
-	y_recons_ll2_core(im.proc, YW, im.jpeg, im.aux, im.highres_mem, im.hdr->highres_mem_len, q, part);
-}
-
 // ---- offsetY_recons256, 3-in-a-row / vertical-pair substitutions in the level-2 detail
 // bands (image_processing.c:2757-2849).  Serial: writes into the next row.
 NHW_HD void recons_pattern_cell(int16_t *P, int16_t *J, int &a, int &j)
@@ -155,19 +150,6 @@ NHW_HD void recons_pattern_cell(int16_t *P, int16_t *J, int &a, int &j)
 				}
 			}
 		}
-	}
-}
-
-NHW_HDN void y_recons_patterns_image(const EncImg &im)
-{
-	int16_t *P = im.proc, *J = im.jpeg;
-	for (int r = 0; r < 128; r++) {
-		int a = r * YW + 129;
-		for (int j = 129; j < 255; j++, a++) recons_pattern_cell(P, J, a, j);
-	}
-	for (int r = 128; r < 255; r++) {
-		int a = r * YW + 1;
-		for (int j = 1; j < 255; j++, a++) recons_pattern_cell(P, J, a, j);
 	}
 }
 
@@ -247,25 +229,6 @@ NHW_HD void y_recons_quant_row(const EncImg &im, int r, int m1, int part, int q 
 		if (a < 0) a = -((-a) & 65528);
 		else a &= 65528;
 		J[j] = (int16_t)(a > 128 ? a - 125 : a - 131);
-	}
-}
-
-// ---- offsetY_recons256, second call only: shrink isolated reconstructed coefficients,
-// in place and in raster order (image_processing.c:3162-3187, q>16 branch)
-NHW_HDN void y_recons_shrink_image(const EncImg &im, int q = 20)
-{
-	int16_t *J = im.jpeg;
-	const int dg = q <= 16 ? 16 : 8;   // q <= 16: diagonal neighbours only count from 16 up (image_processing.c:3137-3160)
-	for (int r = 1; r < 255; r++) {
-		int e = r * YW + 1;
-		for (int j = 1; j < 255; j++, e++) {
-			if (nhw_iabs(J[e]) < 8) continue;
-			if (nhw_iabs(J[e - YW - 1]) >= dg || nhw_iabs(J[e - YW]) >= 8 || nhw_iabs(J[e - YW + 1]) >= dg ||
-			    nhw_iabs(J[e - 1]) >= 8 || nhw_iabs(J[e + 1]) >= 8 || nhw_iabs(J[e + YW - 1]) >= dg ||
-			    nhw_iabs(J[e + YW]) >= 8 || nhw_iabs(J[e + YW + 1]) >= dg)
-				continue;
-			if (r >= 128 || j >= 128) J[e] += J[e] > 0 ? -1 : 1;
-		}
 	}
 }
 
@@ -357,9 +320,4 @@ NHW_HD void y_e6d_correct_cells(int16_t *P, int16_t *J, const int16_t *L)
 		prev = scan + d;
 		cur = nxt;
 	}
-}
-
-NHW_HD void y_e6d_correct_row(const EncImg &im, int r)
-{
-	y_e6d_correct_cells(im.proc + r * YW, im.jpeg + r * YW, im.ll1 + r * 256);
 }

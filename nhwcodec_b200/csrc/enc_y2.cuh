@@ -343,68 +343,6 @@ NHW_HDN void y_e16_residual_col_t(const EncImg &im, int q, int j, const int16_t 
 	}
 }
 
-NHW_HDN void y_e16_residual_col_w(const EncImg &im, int q, int j, const int16_t *Pn, const int16_t *Ln, const uint8_t *lut = nullptr)
-{
-	y_e16_residual_col_t<false>(im, q, j, Pn, Ln, lut, 0);
-}
-
-// serial form (reference order); the CUDA path runs columns 0..254 concurrently against a
-// snapshot and column 255 afterwards (enc_par.cuh)
-NHW_HDN void y_e16_residual_image(const EncImg &im, int q)
-{
-	for (int j = 0; j < 256; j++) y_e16_residual_col(im, q, j, im.proc, im.ll1);
-}
-
-// ---- E16b (nhw_encoder.c:1327-1420): classify what is left, count the side-channel words
-// One column of the stage: cell (row,j) only touches its own LL1 code and band cell
-// P(j,256+row), and reads the band cell of (row-1,j): columns are independent.
-NHW_HDN void y_e16b_classify_col(const EncImg &im, int q, int j, int &w1, int &w3, int &w5)
-{
-	int16_t *P = im.proc, *L = im.ll1;
-	const int rs = res_setting_of(q);
-	{
-		for (int row = 0; row < 256; row++) {
-			const int scan = row * YW + j, count = row * 256 + j;
-			const int stage = (j << 9) + row + 256;
-			if (L[count] < 12000) {
-				int res = P[scan] - L[count];
-				L[count] = 0;
-				if (res == 0 || res == 1) {
-					if (P[stage] == -7 || P[stage] == -8) { if (P[stage - 1] < 2 && P[stage - 1] > -8) P[stage] = -9; }
-				} else if (res == 2) {
-					if (P[stage] > 15 && !(P[stage] & 7)) P[stage]--;
-					else if (P[stage] == -7 || P[stage] == -8) { if (P[stage - 1] <= 1) P[stage] = -9; }
-					else if (P[stage] == -6) { if (P[stage - 1] <= -1 && P[stage - 1] > -8) P[stage] = -9; }
-				} else if (res == 3) {
-					if (q >= 21) { L[count] = 144; w5++; }
-					else if (P[stage] > 15 && !(P[stage] & 7)) P[stage]--;
-					else if (P[stage] <= 0 && (((-P[stage]) + 2) & 65532) == 8) { if (P[stage - 1] <= 2) P[stage] = -10; }
-				} else if (res > rs) {
-					L[count] = 141; w1++;
-					if (res == 4) {
-						if (P[stage] == 7 || (P[stage] & 65534) == 8) { if (P[stage - 1] >= 0 && P[stage - 1] < 8) P[stage] += 2; }
-					} else if (res > 6) {
-						if (res > 7 && q >= 21) { L[count] = 148; w5++; w1++; }
-						else if (P[stage] > 15 && !(P[stage] & 7)) P[stage]--;
-						else if (P[stage] == -6 || P[stage] == -7 || P[stage] == -8) { if (P[stage - 1] < 0 && P[stage - 1] > -8) P[stage] = -9; }
-					}
-				}
-			} else {
-				// every code left by the column pass is a multiple of 100; the byte code is code/100
-				const int v = L[count];
-				const bool w1c = v == 14000 || v == 14100, w3c = v == 12100 || v == 12200 || v == 12300 || v == 12400;
-				const bool w5c = v == 14500, w31 = v == 12500 || v == 12600, w51 = v == 14900;
-				if (w1c || w3c || w5c || w31 || w51) {
-					L[count] = (int16_t)(v / 100);
-					w1 += (w1c || w31 || w51) ? 1 : 0;
-					w3 += (w3c || w31) ? 1 : 0;
-					w5 += (w5c || w51) ? 1 : 0;
-				}
-			}
-		}
-	}
-}
-
 NHW_HDN void y_e16b_classify_col_w(const EncImg &im, int q, int j, int &w1, int &w3, int &w5)
 {
 	int16_t *P = im.proc, *L = im.ll1;
@@ -462,15 +400,6 @@ NHW_HDN void y_e16b_classify_col_w(const EncImg &im, int q, int j, int &w1, int 
 	}
 }
 
-NHW_HDN void y_e16b_classify_image(const EncImg &im, int q)
-{
-	int w1 = 0, w3 = 0, w5 = 0;
-	for (int j = 0; j < 256; j++) y_e16b_classify_col_w(im, q, j, w1, w3, w5);
-	im.hdr->res1_word_len = w1;
-	im.hdr->res3_word_len = w3;
-	im.hdr->res5_word_len = w5;
-}
-
 // ---- E18 (nhw_encoder.c:1498-1887): turn the codes left in res256 into the res1/res3/res5
 // side channels: column positions per row (254 = end of row), pair-delta packed, with the
 // positions' LSBs and the 1- or 2-bit words in separate bit planes.
@@ -522,18 +451,6 @@ NHW_HD int y_e18_classify(int v, int q, int &member, int (&w)[3])
 	if (q >= 19 && v >= 121 && v <= 124) { member |= 2; w[1] = v == 121 ? 1 : v == 122 ? 0 : v == 123 ? 2 : 3; v = 0; }
 	if (q >= 21 && (v == 144 || v == 145)) { member |= 4; w[2] = v == 144 ? 1 : 0; v = 0; }
 	return v;
-}
-
-NHW_HDN void y_e18_pack_list_image(const EncImg &im, int which)
-{
-	uint8_t *pos = im.tmp1, *wrd = im.tmp3;
-	int count = 0, e = 0;
-	for (int row = 0; row < 256; row++) {
-		const int n = y_e18_collect_row(im, which, row, pos + count, wrd + e);
-		count += n + 1;
-		e += n;
-	}
-	y_e18_finish_list_image(im, which, count, e);
 }
 
 // Steps 2..6 on the collected lists: tmp1 = `count` positions, tmp3 = `e` word values.
@@ -725,19 +642,4 @@ NHW_HD int e20_final_cell(const int16_t *row, int S, const E20Pass &g, int r, in
 		v = e20_turn(row, S, g, r, x, in, give);
 	}
 	return v;
-}
-
-NHW_HDN void y_e20_cleanup_image(const EncImg &im, int q, int ratio)
-{
-	int16_t *P = im.proc;
-	int yw, yw2;
-	if (q > 22) { yw = 8; yw2 = 4; } else { yw = 9; yw2 = 9; }
-	for (int r = 1; r < 255; r++)
-		for (int j = 257; j < 511; j++) e20_cell(P, r * YW + j, j, 510, ratio - 2, yw, yw2, 0);
-	if (q > 22) { yw = 8; yw2 = 4; } else if (q > 17) { yw = 8; yw2 = 9; } else { yw = 9; yw2 = 9; }
-	for (int r = 256; r < 511; r++)
-		for (int j = 1; j < 256; j++) e20_cell(P, r * YW + j, j, 254, ratio - 2, yw, yw2, 1);
-	yw = q > 22 ? 8 : 11;
-	for (int r = 256; r < 511; r++)
-		for (int j = 257; j < 511; j++) e20_cell(P, r * YW + j, j, 510, ratio - 1, yw, yw, 2);
 }

@@ -23,65 +23,6 @@ static const uint8_t h_extra_words2[19] = NHW_EXTRA_WORDS2;
 #define NHW_EXTRA2(k) h_extra_words2[k]
 #endif
 
-// ---- offsetY loop 1 (image_processing.c:194-237): neighbouring multiples of 8 in the detail
-// bands; flat raster order (col 0 looks at the previous row's last, already-visited cell).
-NHW_HDN void y_offset_pairs_image(const EncImg &im)
-{
-	int16_t *P = im.proc;
-	for (int i = 0; i < 4 * 65536; i++) {
-		const int col = i & 511;
-		if (!(i >= 2 * 65536 || col >= 256)) continue;
-		if (!(P[i] > 7 && P[i + 1] > 7 && col < 511)) continue;
-		int a = P[i];
-		if ((a & 7) || (P[i + 1] & 7)) continue;
-		if (a > 15) {
-			if (i > 0) {
-				if (P[i - 1] <= 0) P[i]--;
-				else if (P[i + 1] > 15) {
-					if (col < 510 && P[i + 2] <= 0) P[i + 1]--;
-				}
-			}
-		} else if (P[i + 1] > 15) {
-			if (col < 510 && P[i + 2] <= 0) P[i + 1]--;
-		}
-	}
-}
-
-// ---- offsetY loops 2+3 (image_processing.c:239-311), q>16: patterns in the level-2 region
-NHW_HDN void y_offset_patterns_image(const EncImg &im)
-{
-	int16_t *P = im.proc;
-	for (int r = 0; r < 256; r++) {
-		int a = r * YW + 1;
-		for (int j = 1; j < 255; j++, a++) {
-			int v = P[a];
-			if (v > 3 && v < 8) {
-				if (in4to7(P[a - 1])) {
-					if (in4to7(P[a + 1])) { P[a] = 12700; P[a - 1] = 10100; j++; a++; }
-					else if (in4to7(P[a + YW - 1]) && in4to7(P[a + YW])) {
-						P[a - 1] = 12100; P[a] = 10100; P[a + YW - 1] = 10100; P[a + YW] = 10100; j++; a++;
-					}
-				}
-			} else if (v < -3 && v > -8) {
-				if (in_m7to_m4(P[a - 1])) {
-					if (in_m7to_m4(P[a + 1])) { P[a] = 12900; P[a - 1] = 10100; j++; a++; }
-					else if (in_m7to_m4(P[a + YW - 1]) && in_m7to_m4(P[a + YW])) {
-						P[a - 1] = 12200; P[a] = 10100; P[a + YW - 1] = 10100; P[a + YW] = 10100; j++; a++;
-					}
-				}
-			}
-		}
-	}
-	for (int r = 0; r < 256; r++) {
-		int a = r * YW;
-		for (int j = 0; j < 255; j++, a++) {
-			int v = P[a], w = P[a + 1];
-			if (v >= 5 && v <= 7) { if (w >= 5 && w <= 7) { P[a] = 10300; j++; a++; } }
-			else if (v <= -5 && v >= -7) { if (w <= -5 && w >= -7) { P[a] = 10204; j++; a++; } }
-		}
-	}
-}
-
 // ---- offsetY loop 4 (image_processing.c:312-519): coefficient -> byte
 NHW_HDN void y_offset_quant_image(const EncImg &im, int m1)
 {
@@ -131,66 +72,5 @@ NHW_HD void y_scan_strip(const EncImg &im, int strip /* 0..127 */)
 		s[0] = (uint8_t)r0[0]; s[1] = (uint8_t)r0[1]; s[2] = (uint8_t)r0[2]; s[3] = (uint8_t)r0[3];
 		s[4] = (uint8_t)r1[3]; s[5] = (uint8_t)r1[2]; s[6] = (uint8_t)r1[1]; s[7] = (uint8_t)r1[0];
 		s += 8;
-	}
-}
-
-// ---- E24: peephole passes over the 262144 luma bytes
-NHW_HDN void y_peephole_image(const EncImg &im)
-{
-	uint8_t *s = im.scan;
-	const int N = 4 * 65536;
-	for (int i = 0; i < N - 4; i++) {
-		if (s[i] != 128 && s[i + 1] == 128) {
-			if (s[i + 2] == 128) {
-				if (s[i + 3] == 128) {
-					int x = s[i], y = s[i + 4];
-					if ((x == 136 || x == 120) && (y == 136 || y == 120)) {
-						s[i] = (uint8_t)(132 + (x == 120 ? 2 : 0) + (y == 120 ? 1 : 0));
-						s[i + 4] = 201;
-						i += 4;
-					} else i += 3;
-				} else i += 2;
-			} else i++;
-		}
-	}
-	s[0] = s[1] = s[2] = s[3] = 128;
-	s[N - 4] = s[N - 3] = s[N - 2] = s[N - 1] = 128;
-	int sel1 = 0, sel2 = 0;
-	for (int i = 4; i < N - 4; i++) {
-		if (s[i] != 136 && s[i] != 120) continue;
-		const bool nxt = (s[i + 1] == 120 || s[i + 1] == 136);
-		if (s[i + 2] == 128 && nxt && s[i - 1] == 128 && s[i - 2] == 128 && s[i - 3] == 128 && s[i - 4] == 128) {
-			s[i + 1] = (uint8_t)(s[i + 1] == 120 ? 157 : 159);
-			sel2++;
-		} else if (s[i - 1] == 128 && nxt && s[i + 2] == 128 && s[i + 3] == 128 && s[i + 4] == 128 && s[i + 5] == 128) {
-			s[i + 1] = (uint8_t)(s[i + 1] == 120 ? 157 : 159);
-			sel2++;
-		} else if (s[i - 1] == 128 && s[i - 2] == 128 && s[i - 3] == 128 && s[i - 4] == 128 && s[i + 1] == 128) {
-			s[i] = (uint8_t)(s[i] == 136 ? 153 : 155);
-			sel1++;
-		} else if (s[i - 1] == 128 && s[i + 1] == 128 && s[i + 2] == 128 && s[i + 3] == 128 && s[i + 4] == 128) {
-			s[i] = (uint8_t)(s[i] == 136 ? 153 : 155);
-			sel1++;
-		}
-	}
-	im.hdr->select1 = sel1;
-	im.hdr->select2 = sel2;
-	for (int i = 0, count = 0; i < N; i++) {
-		while (s[i] == 128 && s[i + 1] == 128) {
-			count++;
-			if (count > 255) {
-				for (int k = 0; k < 4; k++) {
-					if (s[i + k] == 153) s[i + k] = 124;
-					else if (s[i + k] == 155) s[i + k] = 123;
-				}
-				i--;
-				count = 0;
-			} else i++;
-		}
-		if (count >= 252) {
-			if (s[i + 1] == 153) s[i + 1] = 124;
-			else if (s[i + 1] == 155) s[i + 1] = 123;
-		}
-		count = 0;
 	}
 }

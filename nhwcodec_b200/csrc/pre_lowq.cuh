@@ -634,17 +634,3 @@ NHW_HD void pre_low_walk_d_row(int16_t *Y, const int16_t *K, const uint8_t *M, c
 		if (back) { j--; s--; }
 	}
 }
-
-// ---- the whole stage ---------------------------------------------------------------------------------------------
-// Y: in/out.  O, K: scratch planes (O receives the copy).  M: 262144 bytes of scratch.
-NHW_HDN void pre_low_image(int16_t *Y, int16_t *O, int16_t *K, uint8_t *M, int q)
-{
-	const PreLowParams p = pre_low_params(q);
-	for (int i = 0; i < PW * PW; i++) { O[i] = Y[i]; M[i] = 0; }
-	// the kernel plane's border is never written by walk A and is read by the later walks: it reads as zero
-	for (int i = 0; i < PW; i++) { K[i] = 0; K[511 * PW + i] = 0; K[i * PW] = 0; K[i * PW + 511] = 0; }
-	pre_low_walk_a(O, K, p);
-	pre_low_walk_b(Y, O, K, M, p);
-	pre_low_walk_c(Y, K, M, p);
-	for (int r = 1; r < 511; r++) pre_low_walk_d_row(Y, K, M, p, r);
-}

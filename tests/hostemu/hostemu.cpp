@@ -17,6 +17,9 @@
 #include "../../nhwcodec_b200/csrc/enc_ll2_masks.cuh"
 #include "../../nhwcodec_b200/csrc/enc_lowq.cuh"
 #include "../../nhwcodec_b200/csrc/pre_lowq.cuh"
+#include "../../nhwcodec_b200/csrc/enc_hq.cuh"
+#include "../../nhwcodec_b200/csrc/dec_stages.cuh"
+#include "serial_forms.cuh"
 
 namespace {
 

@@ -96,3 +96,31 @@ def test_decoder_cli_known_answer(smooth_bmp, exe, tmp_path):
     data = open(out, "rb").read()
     assert len(data) == 786486
     assert hashlib.md5(data).hexdigest() == KAT_DEC_Q20
+
+
+def test_cli_top_down_bmp_and_q0(smooth_bmp, tmp_path):
+    """a negative-height (top-down) BMP is flipped before encoding, like the reference does (encoder/nhw_encoder.c:3089-3093):
+    the same picture stored both ways gives the same .nhw; -q0 -- which the reference accepts although its tables are then
+    indexed out of bounds -- is refused with the exit code of an encoder failure"""
+    import struct
+    data = open(smooth_bmp, "rb").read()
+    hd, pix = bytearray(data[:54]), data[54:]
+    hd[22:26] = struct.pack("<i", -512)
+    rows = [pix[i * 1536:(i + 1) * 1536] for i in range(512)]
+    td = tmp_path / "topdown.bmp"
+    td.write_bytes(bytes(hd) + b"".join(reversed(rows)))
+    out = str(tmp_path / "td.nhw")
+    for exe in ("cli/nhw-enc", "oracle/_ref/nhw-enc-dropin"):
+        path = os.path.join(ROOT, exe)
+        if not os.path.exists(path):
+            continue
+        r = subprocess.run([path, "-f", "-q20", str(td), out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert hashlib.md5(open(out, "rb").read()).hexdigest() == KAT_Q20, exe
+    canon = os.path.join(ROOT, "oracle/_ref/nhw-enc-canon")      # the reference itself on the same file
+    if os.path.exists(canon):
+        ref_out = str(tmp_path / "td_ref.nhw")
+        assert subprocess.run([canon, "-f", "-q20", str(td), ref_out], capture_output=True).returncode == 0
+        assert open(ref_out, "rb").read() == open(out, "rb").read()
+    r = subprocess.run([os.path.join(ROOT, "cli/nhw-enc"), "-f", "-q0", smooth_bmp, out], capture_output=True, text=True)
+    assert r.returncode == (-1) % 256 and "encode failed" in r.stderr

@@ -24,6 +24,8 @@ def test_synth_device_matches_host(codec):
 
 @pytest.mark.parametrize("q", [20, 23, 19, 18, 17, 16, 9, 1])
 def test_colorspace(codec, ref, q):
+    """the stage kernel of front.cu (nhw_stage_colorspace_device): the product path at q <= 16, a stage-level check of the
+    shared per-pixel arithmetic (color_core.cuh) at q >= 17, where the product kernel is the fused one (test_frontend_vs_taps)"""
     import torch
     imgs = _imgs()
     n = imgs.shape[0]
@@ -61,8 +63,10 @@ def test_pre_processing(codec, ref, q):
         assert bad.size == 0, (q, i, bad[:5], got[tuple(bad[0])], want[tuple(bad[0])])
 
 
-@pytest.mark.parametrize("q", [20, 22, 18, 16, 14, 13, 8, 2])
+@pytest.mark.parametrize("q", [17, 18, 19, 20, 21, 22, 23, 16, 14, 13, 8, 2])
 def test_frontend_vs_taps(codec, ref, q):
+    """the PRODUCT front end (q >= 17: the fused k_front_luma in each of its colour modes, with and without pre-sharpening and
+    the kept first pass; q <= 16: colour + state machine + plane-fed analysis) against the reference's stage taps"""
     import torch
     imgs = _imgs()
     n = imgs.shape[0]
