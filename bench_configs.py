@@ -221,11 +221,24 @@ def config4(args):
 
             def verify(k):
                 i = idx[k]
-                assert got[k] == ref.ref_encode(pix[k], args.quality), c0 + i
-                if i in dec:
-                    assert np.array_equal(dec[i], ref.ref_decode(got[k])), c0 + i
+                want = ref.ref_encode(pix[k], args.quality)
+                if got[k] != want:
+                    return (c0 + i, "stream", want)
+                if i in dec and not np.array_equal(dec[i], ref.ref_decode(got[k])):
+                    return (c0 + i, "pixels", None)
+                return None
 
-            list(pool.map(verify, range(len(idx))))   # the compiled reference releases the GIL: host threads in parallel
+            # (the compiled reference releases the GIL: host threads in parallel)
+            for k, res in enumerate(pool.map(verify, range(len(idx)))):
+                if res is not None:
+                    # say what differs, and ask the oracle a second time from this thread: an answer that changes between two
+                    # calls on the same pixels is the oracle's problem (the reference reads never-written memory), not the GPU's
+                    from nhwcodec_b200 import container
+                    again = ref.ref_encode(pix[k], args.quality)
+                    where = container.first_difference(got[k], res[2]) if res[2] is not None else "decoded pixels"
+                    raise AssertionError("image %d (%s): GPU vs oracle differ at %s; second oracle call %s the first, %s the GPU" % (
+                        res[0], res[1], where, "equals" if again == res[2] else "DIFFERS from",
+                        "equals" if again == got[k] else "differs from"))
             checked += len(idx)
     torch.cuda.synchronize()
     if dist is not None:

@@ -21,6 +21,16 @@ mkdir -p "$OUT" "$TMP"
 CC="${CC:-gcc}"
 # -ffp-contract=off: the reference's x86-64 gcc -O3 build has no FMA; keep it that way.
 CFLAGS="-O3 -fPIC -w -ffp-contract=off"
+# The canonical build also defines never-written AUTOMATIC variables as 0 (gcc >= 12: -ftrivial-auto-var-init=zero), exactly
+# as the zero-guard allocator does for the heap: wavlts2packet reads one entry past its codebook list out of a local array
+# (encoder/compress_pixel.c:58,412,446), and what the stack holds there -- leftovers of earlier frames, saved pointers whose
+# bytes depend on the heap layout -- otherwise decides the last byte of tree1 on about one image in a few thousand (and
+# differs between two calls on the same pixels from different threads).  A compiler flag, not a source change.
+CANON="-ftrivial-auto-var-init=zero"
+if ! echo 'int main(void){return 0;}' | $CC $CANON -x c - -o /dev/null 2>/dev/null; then
+	echo "build_ref.sh: this gcc has no -ftrivial-auto-var-init; the canonical oracle keeps stack-dependent reads" >&2
+	CANON=""
+fi
 WRAP="-Wl,--wrap=malloc,--wrap=calloc,--wrap=free,--wrap=exit"
 
 ENC_SRCS="colorspace.c compress_pixel.c filters.c image_processing.c wavelet_filterbank.c"
@@ -29,15 +39,18 @@ DEC_SRCS="compress_pixel.c filters.c wavelet_filterbank.c"
 # ---- encoder library (tap-instrumented nhw_encoder.c) ----
 python3 "$HERE/make_tapped.py" "$REF/encoder/nhw_encoder.c" "$HERE/taps_enc.txt" "$TMP/enc_tapped.c"
 objs=""
+cobjs=""
 for s in $ENC_SRCS; do
-	$CC $CFLAGS -I"$REF/encoder" -c "$REF/encoder/$s" -o "$TMP/enc_${s%.c}.o"
+	$CC $CFLAGS -I"$REF/encoder" -c "$REF/encoder/$s" -o "$TMP/enc_${s%.c}.o"                 # stock (timing build)
+	$CC $CFLAGS $CANON -I"$REF/encoder" -c "$REF/encoder/$s" -o "$TMP/encc_${s%.c}.o"         # canonical
 	objs="$objs $TMP/enc_${s%.c}.o"
+	cobjs="$cobjs $TMP/encc_${s%.c}.o"
 done
 # the q22/q23 side channel is computed inside wavelet_filterbank.c: the canonical library gets a tapped copy of it too
 python3 "$HERE/make_tapped.py" "$REF/encoder/wavelet_filterbank.c" "$HERE/taps_enc.txt" "$TMP/enc_wfb_tapped.c"
-$CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$TMP/enc_wfb_tapped.c" -o "$TMP/enc_wavelet_filterbank_tapped.o"
-tobjs="${objs/$TMP\/enc_wavelet_filterbank.o/$TMP/enc_wavelet_filterbank_tapped.o}"
-$CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$TMP/enc_tapped.c" -o "$TMP/enc_nhw_encoder.o"
+$CC $CFLAGS $CANON -I"$REF/encoder" -I"$HERE" -c "$TMP/enc_wfb_tapped.c" -o "$TMP/enc_wavelet_filterbank_tapped.o"
+tobjs="${cobjs/$TMP\/encc_wavelet_filterbank.o/$TMP/enc_wavelet_filterbank_tapped.o}"
+$CC $CFLAGS $CANON -I"$REF/encoder" -I"$HERE" -c "$TMP/enc_tapped.c" -o "$TMP/enc_nhw_encoder.o"
 $CC $CFLAGS -I"$REF/encoder" -I"$HERE" -c "$HERE/ref_enc_glue.c" -o "$TMP/enc_glue.o"
 $CC $CFLAGS -c "$HERE/zguard.c" -o "$TMP/zguard.o"
 $CC -shared -o "$OUT/libnhwref_enc.so" $tobjs "$TMP/enc_nhw_encoder.o" "$TMP/enc_glue.o" "$TMP/zguard.o" \
@@ -60,18 +73,18 @@ else
 fi
 objs=""
 for s in $DEC_SRCS; do
-	$CC $CFLAGS -I"$REF/decoder" -c "$REF/decoder/$s" -o "$TMP/dec_${s%.c}.o"
+	$CC $CFLAGS $CANON -I"$REF/decoder" -c "$REF/decoder/$s" -o "$TMP/dec_${s%.c}.o"
 	objs="$objs $TMP/dec_${s%.c}.o"
 done
-$CC $CFLAGS -I"$REF/decoder" -I"$HERE" -c "$DEC_MAIN" -o "$TMP/dec_nhw_decoder.o"
-$CC $CFLAGS -I"$REF/decoder" -Dmain=nhwref_dec_cli_main -c "$REF/decoder/nhw_decoder_cli.c" -o "$TMP/dec_cli.o"
+$CC $CFLAGS $CANON -I"$REF/decoder" -I"$HERE" -c "$DEC_MAIN" -o "$TMP/dec_nhw_decoder.o"
+$CC $CFLAGS $CANON -I"$REF/decoder" -Dmain=nhwref_dec_cli_main -c "$REF/decoder/nhw_decoder_cli.c" -o "$TMP/dec_cli.o"
 $CC $CFLAGS -I"$REF/decoder" -I"$HERE" -c "$HERE/ref_dec_glue.c" -o "$TMP/dec_glue.o"
 $CC -shared -o "$OUT/libnhwref_dec.so" $objs "$TMP/dec_nhw_decoder.o" "$TMP/dec_cli.o" "$TMP/dec_glue.o" "$TMP/zguard.o" \
 	$WRAP -Wl,-Bsymbolic -lm -lpthread
 
 # ---- CLIs ----
-(cd "$REF/encoder" && $CC -O3 -w -ffp-contract=off *.c "$TMP/zguard.o" -o "$OUT/nhw-enc-canon" $WRAP -lm)
-(cd "$REF/decoder" && $CC -O3 -w -ffp-contract=off *.c "$TMP/zguard.o" -o "$OUT/nhw-dec-canon" $WRAP -lm)
+(cd "$REF/encoder" && $CC -O3 -w -ffp-contract=off $CANON *.c "$TMP/zguard.o" -o "$OUT/nhw-enc-canon" $WRAP -lm)
+(cd "$REF/decoder" && $CC -O3 -w -ffp-contract=off $CANON *.c "$TMP/zguard.o" -o "$OUT/nhw-dec-canon" $WRAP -lm)
 (cd "$REF/encoder" && $CC -O3 -w *.c -o "$OUT/nhw-enc-stock" -lm)
 (cd "$REF/decoder" && $CC -O3 -w *.c -o "$OUT/nhw-dec-stock" -lm)
 

@@ -169,3 +169,16 @@ def test_oracle_does_not_depend_on_call_history(ref):
         ref.ref_encode(other, q)
         assert ref.ref_encode(x, 20) == first
     assert first[320] == 0x1C          # the run is not lengthened: never-written memory reads as 0
+
+
+def test_oracle_is_the_same_from_any_thread(ref):
+    """before the canonical build zero-initialised automatic variables (-ftrivial-auto-var-init=zero, oracle/build_ref.sh) the
+    one-past-the-list read of wavlts2packet could see a saved pointer's byte: two calls on the same pixels from two threads
+    disagreed on about one image in a few thousand (found by configs[4]'s 4096-image subsample check)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from nhwcodec_b200 import synth
+    imgs = [synth.natural(4000 + 15104 + 64 * k) for k in range(12)]
+    serial = [ref.ref_encode(im, 20) for im in imgs]
+    with ThreadPoolExecutor(8) as pool:
+        for _ in range(3):
+            assert list(pool.map(lambda im: ref.ref_encode(im, 20), imgs)) == serial
