@@ -164,8 +164,9 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 		t.lanes_encode = env_int("NHW_LANES_ENCODE", 4, 1, NHW_LANES);
 		t.subs_decode = env_int("NHW_SUBS_DECODE", 8, 1, NHW_MAX_SUB);
 		t.lanes_decode = env_int("NHW_LANES_DECODE", 4, 1, NHW_LANES);
-		t.dsf_streams = env_int("NHW_DSF_STREAMS", 4, 1, 32);
-		while (32 % t.dsf_streams) t.dsf_streams--;
+		t.dsf_streams = env_int("NHW_DSF_STREAMS", 0, 0, 32);   // 0: chosen per launch from the number of streams
+		while (t.dsf_streams && 32 % t.dsf_streams) t.dsf_streams--;
+		t.dsf_job_mask = env_int("NHW_DSF_JOBS", 15, 0, 15);
 		t.rows_grid_cap = sms * env_int("NHW_ROWS_CTAS_PER_SM", 24, 1, 64);
 		t.fetch_kernel = env_int("NHW_FETCH_KERNEL", 1, 0, 1);
 	}

@@ -162,8 +162,59 @@ NHW_HDN int dec_build_book(const uint8_t *tree, int size, int marker, int e_over
 	return n;
 }
 
+// ---- rank -> action.  What the decoders do with a symbol depends on the symbol alone (decoder/compress_pixel.c:153-441:
+// a chain of up to fifteen comparisons per symbol, 479-641 for chroma), so it is worked out once per codebook entry instead
+// of once per decoded symbol: the 16-bit book entries are widened IN PLACE (from the top down, entry i only overwrites
+// entries 2i and 2i + 1) to
+//   bits 0-1  kind: 0 literal   1 zero run   2 literal that arms the "mem2" rule (luma 136 / 120)   3 pair (luma 132..135)
+//   bits 8-15 run length (kind 1);  bit 8: the pair's second value is -11 (kind 3)
+//   bits 16-31 the literal / first value of the pair (int16)
+// The serial decoders are latency chains: this takes a dependent table look-up and the comparison chain off every symbol.
+#define NHW_ACT_ENTRIES 512
+NHW_HD uint32_t dec_action_of(int sym, bool luma)
+{
+	const int word = sym & 0xff, run = sym >> 8;
+	if (word == 0x80) return 1u | ((uint32_t)(run & 255) << 8);
+	int kind = 0, v, second_neg = 0;
+	const int x = word < 110 ? nhw_extra_value(word) : 0;
+	if (luma) {
+		if (word == 136) { v = 11; kind = 2; }
+		else if (word == 120) { v = -11; kind = 2; }
+		else if (word >= 132 && word <= 135) { v = word < 134 ? 11 : -11; kind = 3; second_neg = word & 1; }
+		else if (word == 127) v = 1008;
+		else if (word == 129) v = 1009;
+		else if (word == 125) v = 1006;
+		else if (word == 126) v = 1007;
+		else if (word == 121) v = 1010;
+		else if (word == 122) v = 1011;
+		else if (word == 124) v = 11;
+		else if (word == 123) v = -11;
+		else if (x > 0) v = 123 + (x << 3);
+		else if (x < 0) v = (x << 3) - 123;
+		else v = word > 0x80 ? word - 125 : word - 131;
+	} else {
+		if (word < 110 && x > 0) v = 123 + (x << 3);
+		else if (word < 110 && x < 0) v = (x << 3) - 123;
+		else if (word >= 110 && word == 124) v = 5005;
+		else if (word >= 110 && word == 126) v = 5006;
+		else if (word >= 110 && word == 122) v = 5003;
+		else if (word >= 110 && word == 130) v = 5004;
+		else v = word > 0x80 ? word - 125 : word - 131;
+	}
+	return (uint32_t)kind | ((uint32_t)second_neg << 8) | ((uint32_t)(uint16_t)(int16_t)v << 16);
+}
+NHW_HDN const uint32_t *dec_build_actions(uint16_t *book /* >= 1024 entries */, bool luma)
+{
+	uint32_t *act = reinterpret_cast<uint32_t *>(book);
+	for (int i = NHW_ACT_ENTRIES - 1; i >= 0; i--) {
+		const int sym = book[i];
+		act[i] = dec_action_of(sym, luma);
+	}
+	return act;
+}
+
 // ---- luma prefix decode + run / select-bit logic (compress_pixel.c:120-444)
-NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
+NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */, const uint32_t *act /* dec_build_actions */)
 {
 	const DecDesc *d = im.d;
 	const uint8_t *sel1 = im.blob + d->off_sel1, *sel2 = im.blob + d->off_sel2;
@@ -187,9 +238,9 @@ NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
 	while (br.pos < nbits + 64) {
 		const int dec = dec_next_rank(br, zone, im.lut);
 		if (dec < 0) return NHW_ERR_CODEBOOK_DEV;
-		const int sym = im.book[dec];
-		const int word = sym & 0xff, run = sym >> 8;
-		if (word == 0x80) {
+		const uint32_t a = act[dec];
+		if ((a & 3u) == 1u) {
+			const int run = (int)((a >> 8) & 255u);
 			mem++;
 			if (mem2 == 1) {
 				if (e >= 5 && z(e - 2) && z(e - 3) && z(e - 4) && z(e - 5)) { put(bit2(t2++) ? 11 : -11); }
@@ -212,29 +263,9 @@ NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
 			advance(run);
 		} else {
 			mem = 0; mem2 = 0; ac1 = 0;
-			bool done = true;
-			if (word == 136) { put(11); mem2 = 1; }
-			else if (word == 120) { put(-11); mem2 = 1; }
-			else if (word >= 132 && word <= 135) {
-				put(word < 134 ? 11 : -11);
-				advance(3);
-				put((word & 1) ? -11 : 11);
-			}
-			else if (word == 127) put(1008);
-			else if (word == 129) put(1009);
-			else if (word == 125) put(1006);
-			else if (word == 126) put(1007);
-			else if (word == 121) put(1010);
-			else if (word == 122) put(1011);
-			else if (word == 124) put(11);
-			else if (word == 123) put(-11);
-			else done = false;
-			if (!done) {
-				const int x = word < 110 ? nhw_extra_value(word) : 0;
-				if (x > 0) put(123 + (x << 3));
-				else if (x < 0) put((x << 3) - 123);
-				else put(word > 0x80 ? word - 125 : word - 131);
-			}
+			put((int)(int16_t)(a >> 16));
+			if ((a & 3u) == 2u) mem2 = 1;
+			else if ((a & 3u) == 3u) { advance(3); put((a & 0x100u) ? -11 : 11); }
 		}
 		if (e >= p1 - 1) return 0;
 	}
@@ -242,7 +273,7 @@ NHW_HDN int dec_prefix_luma(const DecImg &im, int16_t *im3 /* 262144, zeroed */)
 }
 
 // ---- chroma prefix decode (compress_pixel.c:479-641): no zone, no select bits
-NHW_HDN int dec_prefix_chroma(const DecImg &im, int16_t *im3 /* 131072, zeroed */)
+NHW_HDN int dec_prefix_chroma(const DecImg &im, int16_t *im3 /* 131072, zeroed */, const uint32_t *act /* dec_build_actions */)
 {
 	const DecDesc *d = im.d;
 	BitReader br;
@@ -253,20 +284,10 @@ NHW_HDN int dec_prefix_chroma(const DecImg &im, int16_t *im3 /* 131072, zeroed *
 	while (br.pos < nbits + 64) {
 		const int dec = dec_next_rank(br, false, im.lut);
 		if (dec < 0) return NHW_ERR_CODEBOOK_DEV;
-		const int sym = im.book[dec];
-		const int word = sym & 0xff;
-		if (word == 0x80) e += sym >> 8;
+		const uint32_t a = act[dec];
+		if (a & 1u) e += (int)((a >> 8) & 255u);
 		else {
-			const int x = word < 110 ? nhw_extra_value(word) : 0;
-			int v;
-			if (word < 110 && x > 0) v = 123 + (x << 3);
-			else if (word < 110 && x < 0) v = (x << 3) - 123;
-			else if (word >= 110 && word == 124) v = 5005;
-			else if (word >= 110 && word == 126) v = 5006;
-			else if (word >= 110 && word == 122) v = 5003;
-			else if (word >= 110 && word == 130) v = 5004;
-			else v = word > 0x80 ? word - 125 : word - 131;
-			if (e < 131072) im3[e] = (int16_t)v;   // (a run may carry e past the end: nothing is stored there)
+			if (e < 131072) im3[e] = (int16_t)(a >> 16);   // (a run may carry e past the end: nothing is stored there)
 			e++;
 		}
 		if (e >= p1 - 1) return 0;

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(32) kd_image_lut(DecBatch b, int n, F f)
 // carries DSF_STREAMS streams (one active lane in every 32 / DSF_STREAMS); the many more warps this makes
 // also hide each other's latency.  The prefix-code table is staged in shared memory.
 #define DSF_STREAMS 4
-__global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n, int spw)
+__global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n, int spw, int job_mask)
 {
 	__shared__ __align__(16) uint16_t slut[NHW_LUT_WORDS];
 	const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -123,20 +123,20 @@ __global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n, int sp
 	const int group = 32 / spw;
 	if (threadIdx.x % group) return;
 	const int i = blockIdx.x * spw + threadIdx.x / group, job = threadIdx.y;
-	if (i >= n || b.status[i] != 0) return;
+	if (i >= n || b.status[i] != 0 || !((job_mask >> job) & 1)) return;   // (job_mask: timing experiments only)
 	DecImg im = make_dec(b, i, 0);
 	im.lut = slut;
 	if (job == 0) {
 		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 4096;
 		dec_build_book(im.blob + im.d->off_tree1, im.d->size_tree1, 3, -1, im.book, btmp);
-		const int rc = dec_prefix_luma(im, im.proc);
+		const int rc = dec_prefix_luma(im, im.proc, dec_build_actions(im.book, true));
 		if (rc) b.status[i] = rc;
 	} else if (job == 1) {
 		im.book += 1024;
 		uint8_t *btmp = reinterpret_cast<uint8_t *>(im.book) + 4096;
 		for (int k = 0; k < 1024; k++) im.book[k] = 0;
 		dec_build_book(im.blob + im.d->off_tree2, im.d->size_tree2, 128, im.d->tree_end, im.book, btmp);
-		const int rc = dec_prefix_chroma(im, im.uvcoef);
+		const int rc = dec_prefix_chroma(im, im.uvcoef, dec_build_actions(im.book, false));
 		if (rc) b.status[i] = rc;
 	} else if (job == 2) {
 		dec_ll_dpcm(im);
@@ -876,8 +876,11 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 
 	// ---- luma
 	{
-		const int spw = c->tune.dsf_streams;
-		NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + spw - 1) / spw, dim3(32, 4), 0, b, n, spw);
+		// streams per warp: with few streams in flight one per warp is fastest (no divergence between the parsers, and there
+		// are warps to spare: 512 streams 2.6 ms vs 4.4 ms at four per warp); with thousands the warps themselves become the
+		// limit and sharing one pays (4096 streams: 5.7 ms at four per warp, 7.8 at two, 11.2 at one)
+		const int spw = c->tune.dsf_streams ? c->tune.dsf_streams : n <= 1536 ? 1 : n <= 3072 ? 2 : 4;
+		NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + spw - 1) / spw, dim3(32, 4), 0, b, n, spw, c->tune.dsf_job_mask);
 	}
 	NHW_LAUNCH_L(c, "d_descan_y", kd_descan_y, dim3(512, n), 128, 0, b);
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);

@@ -477,7 +477,7 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 	rc = dec_ll_dpcm(im);
 	if (rc) return rc;
 	dec_build_book(blob + d.off_tree1, d.size_tree1, 3, -1, im.book, btmp.data());
-	rc = dec_prefix_luma(im, im.proc);
+	rc = dec_prefix_luma(im, im.proc, dec_build_actions(im.book, true));
 	if (rc) return rc;
 	for (int s = 127; s >= 0; s--) dec_y_descan_strip(im.proc, im.jpeg, s);
 	dec_lists_image(im, ltmp.data());
@@ -546,7 +546,7 @@ static int host_decode(const uint8_t *blob, size_t len, uint8_t *rgb, uint8_t *y
 
 	std::fill(book.begin(), book.end(), 0);
 	dec_build_book(blob + d.off_tree2, d.size_tree2, 128, d.tree_end, im.book, btmp.data());
-	rc = dec_prefix_chroma(im, im.uvcoef);
+	rc = dec_prefix_chroma(im, im.uvcoef, dec_build_actions(im.book, false));
 	if (rc) return rc;
 	for (int v = 0; v < 2; v++) {
 		for (int s = 31; s >= 0; s--) dec_c_descan_strip(im.uvcoef, im.cjpeg, s, v);
