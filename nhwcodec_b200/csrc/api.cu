@@ -657,6 +657,7 @@ static int decode_batch_impl(nhw_ctx *c, const uint8_t *in, const uint64_t *offs
 			ok = ok && fetch_to_device(&w, w.offs_dev, w.offs_host, ctx_alias(w.offs_host), (size_t)cnt * sizeof(uint64_t), "H2D offs");
 			ok = ok && fetch_to_device(&w, w.status_dev, w.status_host, ctx_alias(w.status_host), (size_t)cnt * sizeof(int32_t), "H2D status");
 			if (!ok) return NHW_ERR_CUDA;
+			w.chroma_side = 0;
 			nhw::decode_chunk(&w, w.pack_dev, w.offs_dev, static_cast<const DecDesc *>(w.dec_desc_dev), w.status_dev, cnt, w.rgb, any_lowq, any_hq, yuv != nullptr);
 			if (rgb) cudaMemcpyAsync(rgb + (size_t)a * NHW_RGB_BYTES, w.rgb, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);
 			if (yuv) cudaMemcpyAsync(yuv + (size_t)a * NHW_RGB_BYTES, w.dec_yuv, (size_t)cnt * NHW_RGB_BYTES, cudaMemcpyDeviceToHost, w.stream);

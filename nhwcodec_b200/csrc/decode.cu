@@ -107,18 +107,18 @@ __global__ void __launch_bounds__(32) kd_image_lut(DecBatch b, int n, F f)
 		f(im, i);
 	}
 }
-// ---- the decoder's serial front: four independent single-thread jobs per image run side by side
-// (threadIdx.y = job) instead of one after the other: luma prefix decode, chroma prefix decode, LL byte
-// DPCM, side-channel list expansion.  The jobs are branchy bit-serial parsers: lanes of a warp working on
+// ---- the decoder's serial front: three independent single-thread jobs per image run side by side
+// (threadIdx.y = job) instead of one after the other: luma prefix decode, chroma prefix decode,
+// side-channel list expansion.  The jobs are branchy bit-serial parsers: lanes of a warp working on
 // different streams diverge at almost every step and the warp pays for every path taken, so a warp only
 // carries DSF_STREAMS streams (one active lane in every 32 / DSF_STREAMS); the many more warps this makes
 // also hide each other's latency.  The prefix-code table is staged in shared memory.
 #define DSF_STREAMS 4
-__global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n, int spw, int job_mask)
+__global__ void __launch_bounds__(96) kd_serial_front(DecBatch b, int n, int spw, int job_mask)
 {
 	__shared__ __align__(16) uint16_t slut[NHW_LUT_WORDS];
 	const int tid = threadIdx.y * 32 + threadIdx.x;
-	for (int k = tid; k < NHW_LUT_WORDS / 8; k += 128) reinterpret_cast<uint4 *>(slut)[k] = reinterpret_cast<const uint4 *>(b.lut)[k];
+	for (int k = tid; k < NHW_LUT_WORDS / 8; k += 96) reinterpret_cast<uint4 *>(slut)[k] = reinterpret_cast<const uint4 *>(b.lut)[k];
 	__syncthreads();
 	const int group = 32 / spw;
 	if (threadIdx.x % group) return;
@@ -138,11 +138,287 @@ __global__ void __launch_bounds__(128) kd_serial_front(DecBatch b, int n, int sp
 		dec_build_book(im.blob + im.d->off_tree2, im.d->size_tree2, 128, im.d->tree_end, im.book, btmp);
 		const int rc = dec_prefix_chroma(im, im.uvcoef, dec_build_actions(im.book, false));
 		if (rc) b.status[i] = rc;
-	} else if (job == 2) {
-		dec_ll_dpcm(im);
-	} else {
+	} else {   // (the LL bytes, once the fourth job here, have their parallel form: kd_ll_parallel)
 		dec_lists_image(im, reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(im.flags) + 131072));
 		dec_hq_lists_image(im, reinterpret_cast<uint32_t *>(im.aux));
+	}
+}
+
+// ---- LL bytes in parallel form (the serial statement is dec_ll_dpcm, dec_core.cuh; parse_file, decoder/nhw_decoder.c:1663-2026).
+// The coder looks sequential -- a cursor over code bytes, a cursor over output bytes, every value relative to the one before --
+// but each piece has the shape of a scan:
+//   * where codes start: a code is one byte, or two when its first byte lies in [64, 128) (part A, the 16384 luma bytes; part
+//     B, the chroma bytes, has one-byte codes only).  So position p starts a code unless p - 1 started a two-byte one: a bit
+//     that is reset by every one-byte lead and toggles along a run of two-byte leads -- a map {0, 1} -> {0, 1} per segment;
+//   * where a code's output goes, and which bytes of the side list (highres) it takes: sums of per-code counts;
+//   * the values: a code either sets the running value or adds its deltas to it (mod 256) -- maps "x -> a" / "x -> x + d".
+// One CTA per stream: a thread owns a contiguous run of code positions and walks it once per quantity; the per-thread
+// aggregates are combined by one thread (256 entries).  Part A ends at the first code whose output cursor has reached 16384;
+// part B starts on the byte after it with an absolute value.  Outputs a code writes beyond its part's end are dropped (the
+// serial form overwrites or never reads them).  A stream that ends early leaves the rest of the bytes as they were, as the
+// serial form does.
+struct LlCode { int R, nd, d[3], nabs, a[2]; };   // R copies of the running value, then nd deltas; or nabs absolute values
+
+__device__ __forceinline__ void ll_triple(int c0, int c1, LlCode &k)
+{
+	k.nd = 3;
+	k.d[0] = (((c0 >> 1) & 31) << 1) - 32;
+	k.d[1] = ((((c0 & 1) << 3) | (c1 >> 5)) << 1) - 16;
+	k.d[2] = ((c1 & 31) << 1) - 32;
+}
+// part A (luma LL bytes): code byte c, the byte after it c1 (used by the two-byte codes only), the stream's coder mode
+__device__ __forceinline__ LlCode ll_code_a(int c, int c1, int mode, bool side, int hr)
+{
+	LlCode k = {0, 0, {0, 0, 0}, 0, {0, 0}};
+	if (c >= 128) {
+		if (side) k.a[k.nabs++] = hr;
+		k.a[k.nabs++] = (c - 128) << 1;
+	} else if (c >= 64) ll_triple(c - 64, c1, k);
+	else if (mode == 0) {
+		if (c < 16) {
+			k.R = ((c >> 3) & 1) + 2;
+			const int t = c & 7;
+			if (t == 1) { k.nd = 1; k.d[0] = 2; }
+			else if (t == 2) { k.nd = 2; k.d[0] = 2; k.d[1] = -2; }
+			else if (t == 3) { k.nd = 2; k.d[0] = 2; k.d[1] = 0; }
+			else if (t == 4) { k.nd = 2; k.d[0] = -2; k.d[1] = 2; }
+			else if (t == 5) { k.nd = 2; k.d[0] = -2; k.d[1] = 0; }
+			else if (t == 6) { k.nd = 1; k.d[0] = -2; }
+			else if (t == 7) { k.nd = 1; k.d[0] = 4; }
+		} else if (c < 32) { k.nd = 2; k.d[0] = c >= 24 ? 4 : 2; k.d[1] = ((c & 7) << 1) - 8; }
+		else { const int x = c - 32; k.nd = 2; k.d[0] = ((x >> 3) << 1) - 6; k.d[1] = ((x & 7) << 1) - 8; }
+	} else if (mode == 1) {
+		if (c < 32) {
+			k.R = ((c >> 2) & 7) + 2;
+			const int t = c & 3;
+			if (t) { k.nd = 1; k.d[0] = t == 1 ? 2 : t == 2 ? -2 : 0; }
+		} else { const int x = c - 32; k.nd = 2; k.d[0] = ((x >> 3) << 1) - 4; k.d[1] = ((x & 7) << 1) - 8; }
+	} else k.R = (c & 63) + 2;
+	return k;
+}
+// part B (chroma LL bytes)
+__device__ __forceinline__ LlCode ll_code_b(int c)
+{
+	LlCode k = {0, 0, {0, 0, 0}, 0, {0, 0}};
+	if (c >= 192) {
+		const int x = c - 192, t = x >> 2, m = x & 3;
+		k.nd = 3;
+		k.d[0] = t < 2 ? 0 : (t == 2 || t == 4 || t == 5) ? 4 : -4;
+		k.d[1] = (t == 0 || t == 4 || t == 6) ? 4 : (t == 1 || t == 5 || t == 7) ? -4 : 0;
+		k.d[2] = m == 0 ? 0 : m == 1 ? 4 : m == 2 ? -4 : 8;
+	} else if (c >= 128) { k.nabs = 1; k.a[0] = (c - 128) << 2; }
+	else if (c >= 64) {
+		const int run = (c >> 3) & 7, t = c & 7;
+		if (run == 7) k.R = t + 7 + 2;
+		else {
+			k.R = run + 2;
+			if (t == 1) { k.nd = 1; k.d[0] = 4; }
+			else if (t == 2) { k.nd = 2; k.d[0] = 4; k.d[1] = -4; }
+			else if (t == 3) { k.nd = 3; k.d[0] = 4; k.d[1] = -4; k.d[2] = 0; }
+			else if (t == 4) { k.nd = 3; k.d[0] = -4; k.d[1] = 4; k.d[2] = 0; }
+			else if (t == 5) { k.nd = 2; k.d[0] = -4; k.d[1] = 4; }
+			else if (t == 6) { k.nd = 1; k.d[0] = -4; }
+			else if (t == 7) { k.nd = 1; k.d[0] = 8; }
+		}
+	} else { k.nd = 2; k.d[0] = ((c >> 3) << 2) - 16; k.d[1] = ((c & 7) << 2) - 16; }
+	return k;
+}
+// value maps: bit 8 set = "x -> low byte", clear = "x -> x + low byte"; then(f, g) = g after f
+__device__ __forceinline__ int ll_map_of(const LlCode &k)
+{
+	if (k.nabs) return 256 | (k.a[k.nabs - 1] & 255);
+	return (k.d[0] + k.d[1] + k.d[2]) & 255;
+}
+__device__ __forceinline__ int ll_map_then(int f, int g) { return (g & 256) ? g : ((f & 256) | ((f + g) & 255)); }
+__device__ __forceinline__ int ll_map_apply(int f, int x) { return (f & 256) ? (f & 255) : ((x + f) & 255); }
+
+// Per code byte, what the code does, as a table entry built once per CTA (the code tables depend on the stream's coder mode
+// and quality only): R | nd << 7 | nabs << 9 | d0 << 11 | d1 << 18 | d2 << 25 (deltas as 7-bit two's complement), and
+// the value map next to it.  The two-byte codes of part A take their deltas from both bytes and are worked out on the spot.
+#define LLP_THREADS 256
+__device__ __forceinline__ uint32_t ll_pack(const LlCode &k)
+{
+	return (uint32_t)k.R | ((uint32_t)k.nd << 7) | ((uint32_t)k.nabs << 9) | ((uint32_t)(k.d[0] & 127) << 11) |
+	       ((uint32_t)(k.d[1] & 127) << 18) | ((uint32_t)(k.d[2] & 127) << 25);
+}
+__device__ __forceinline__ int ll_d0(uint32_t e) { return (int)(e << 14) >> 25; }
+__device__ __forceinline__ int ll_d1(uint32_t e) { return (int)(e << 7) >> 25; }
+__device__ __forceinline__ int ll_d2(uint32_t e) { return (int)e >> 25; }
+__device__ __forceinline__ int ll_nout(uint32_t e) { return (int)(e & 127u) + (int)((e >> 7) & 3u) + (int)((e >> 9) & 3u); }
+
+__global__ void __launch_bounds__(LLP_THREADS) kd_ll_parallel(DecBatch b)
+{
+	__shared__ int s_a[LLP_THREADS + 1], s_b[LLP_THREADS + 1], s_c[LLP_THREADS + 1];
+	__shared__ uint32_t tabA[256], tabB[256];
+	__shared__ uint16_t mapA[256], mapB[256];
+	__shared__ int s_iB, s_ok, s_last;
+	if (b.status[blockIdx.x] != 0) return;
+	const DecImg im = make_dec(b, blockIdx.x, 0);
+	const DecDesc *d = im.d;
+	const uint8_t *ch = im.blob + d->off_ch_res, *hr = im.blob + d->off_highres;
+	const uint8_t *ub = im.blob + d->off_u64, *vb = im.blob + d->off_v64;
+	const int ch_len = d->end_ch_res, hr_len = d->highres_comp_len, q = d->quality, mode = d->byte0 & 3;
+	const bool side = q > 15;
+	uint8_t *o = im.res_comp;
+	const int t = threadIdx.x;
+	if (ch_len < 3) return;
+	{
+		const LlCode ka = ll_code_a(t, 0, mode, side, 0), kb = ll_code_b(t);
+		tabA[t] = ll_pack(ka);
+		mapA[t] = (uint16_t)ll_map_of(ka);
+		tabB[t] = ll_pack(kb);
+		mapB[t] = (uint16_t)ll_map_of(kb);
+	}
+	// the code at position p of part A as (entry, map); c1 = the byte after it
+	auto code_a = [&](int c, int c1, uint32_t &e, int &m) {
+		e = tabA[c];
+		m = mapA[c];
+		if (c >= 64 && c < 128) {
+			LlCode k = {0, 0, {0, 0, 0}, 0, {0, 0}};
+			ll_triple(c - 64, c1, k);
+			e = ll_pack(k);
+			m = ll_map_of(k);
+		}
+	};
+	// ================= part A: code positions 1 .. ch_len - 2 (every code may take a second byte) =================
+	const int nposA = ch_len - 2;                         // positions p = 1 + k, k in [0, nposA)
+	const int segA = (nposA + LLP_THREADS - 1) / LLP_THREADS;
+	const int p0 = 1 + t * segA, p1 = min(1 + (t + 1) * segA, 1 + nposA);
+	// ---- 1. which positions start a code: start[p + 1] = !(start[p] && two(p)); per segment, the map of that bit
+	int f0 = 0, f1 = 1;                                   // the bit at p1, given the bit at p0 was 0 / 1
+	for (int p = p0; p < p1; p++) {
+		const int c = ch[p];
+		const bool tw = c >= 64 && c < 128;
+		f0 = !(f0 && tw);
+		f1 = !(f1 && tw);
+	}
+	s_a[t] = f0 | (f1 << 1);
+	__syncthreads();
+	if (t == 0) {
+		int st = 1;                                        // position 1 starts a code
+		for (int k = 0; k < LLP_THREADS; k++) { const int m = s_a[k]; s_a[k] = st; st = (m >> st) & 1; }
+		s_last = st;                                       // does position ch_len - 1 start a code?
+		s_iB = 0x7fffffff;
+		s_ok = 1;
+	}
+	__syncthreads();
+	const int start0 = s_a[t];
+	__syncthreads();
+	// ---- 2. output and side-list cursors, and the segment's value map (a map does not depend on the side-list byte a code
+	// takes: such a code ends on an absolute value of its own).  Maps of segments beyond the end of part A are never used.
+	int nout = 0, nhr = 0, fmap = 0;                       // fmap: identity, x -> x + 0
+	{
+		int st = start0;
+		for (int p = p0; p < p1; p++) {
+			const int c = ch[p];
+			if (st) {
+				uint32_t e;
+				int m;
+				code_a(c, ch[p + 1], e, m);
+				nout += ll_nout(e);
+				nhr += (c >= 128 && side) ? 1 : 0;
+				fmap = ll_map_then(fmap, m);
+			}
+			st = !(st && c >= 64 && c < 128);
+		}
+	}
+	s_a[t] = nout;
+	s_b[t] = nhr;
+	s_c[t] = fmap;
+	__syncthreads();
+	if (t == 0) {
+		int j = 1, a = 0;
+		for (int k = 0; k < LLP_THREADS; k++) { const int x = s_a[k], y = s_b[k]; s_a[k] = j; s_b[k] = a; j += x; a += y; }
+		s_a[LLP_THREADS] = j;
+	} else if (t == 32) {
+		int x = ch[0];
+		for (int k = 0; k < LLP_THREADS; k++) { const int f = s_c[k]; s_c[k] = x; x = ll_map_apply(f, x); }
+		o[0] = ch[0];
+	}
+	__syncthreads();
+	const int j0 = s_a[t], a0 = s_b[t];
+	// ---- 3. the bytes of part A.  The first code whose output cursor has reached 16384 ends the part (it is not executed).
+	{
+		int st = start0, j = j0, a = a0, last = s_c[t];
+		auto put = [&](int v) { last = v & 255; if (j < 16384) o[j] = (uint8_t)last; j++; };
+		for (int p = p0; p < p1; p++) {
+			const int c = ch[p];
+			if (st) {
+				if (j >= 16384) { atomicMin(&s_iB, p); break; }
+				uint32_t e;
+				int m;
+				code_a(c, ch[p + 1], e, m);
+				const int nd = (int)((e >> 7) & 3u);
+				if (c >= 128) {
+					if (side) {
+						if (a >= hr_len) { s_ok = 0; break; }          // side list exhausted: the serial form stops here
+						put(hr[a++]);
+					}
+					put((c - 128) << 1);
+				} else {
+					for (int r = (int)(e & 127u); r > 0; r--) put(last);
+					if (nd > 0) put(last + ll_d0(e));
+					if (nd > 1) put(last + ll_d1(e));
+					if (nd > 2) put(last + ll_d2(e));
+				}
+			}
+			st = !(st && c >= 64 && c < 128);
+		}
+	}
+	__syncthreads();
+	// ================= part B: one absolute byte at iB, then one-byte codes =================
+	int iB = s_iB;
+	if (iB == 0x7fffffff) {
+		// no code of the scanned range saw the cursor at 16384: the very last code can still have carried it there, with
+		// part B starting at ch_len - 1 if that position starts a code; anything else is a short stream
+		if (s_a[LLP_THREADS] >= 16384 && s_last) iB = ch_len - 1;
+		else return;
+	}
+	if (!s_ok || iB >= ch_len) return;
+	const int nposB = ch_len - (iB + 1);                   // code positions iB + 1 .. ch_len - 1
+	const int segB = (nposB + LLP_THREADS - 1) / LLP_THREADS;
+	const int q0 = iB + 1 + t * segB, q1 = min(iB + 1 + (t + 1) * segB, ch_len);
+	nout = 0;
+	fmap = 0;
+	for (int p = q0; p < q1; p++) {
+		const int c = ch[p];
+		nout += ll_nout(tabB[c]);
+		fmap = ll_map_then(fmap, mapB[c]);
+	}
+	__syncthreads();
+	s_a[t] = nout;
+	s_c[t] = fmap;
+	__syncthreads();
+	auto lsb = [&](int j) {   // res_U_64 / res_V_64 LSB planes (nhw_decoder.c:1983-2026)
+		if (!side) return 0;
+		const int k = (j - 16384) & 4095;
+		const uint8_t *pl = j < 20480 ? ub : vb;
+		return ((pl[k >> 3] >> (7 - (k & 7))) & 1) << 1;
+	};
+	if (t == 0) {
+		int j = 16385;
+		for (int k = 0; k < LLP_THREADS; k++) { const int x = s_a[k]; s_a[k] = j; j += x; }
+	} else if (t == 32) {
+		int x = ch[iB];
+		o[16384] = (uint8_t)(x + lsb(16384));
+		for (int k = 0; k < LLP_THREADS; k++) { const int f = s_c[k]; s_c[k] = x; x = ll_map_apply(f, x); }
+	}
+	__syncthreads();
+	{
+		int j = s_a[t], last = s_c[t];
+		auto put = [&](int v) { last = v & 255; if (j < 24576) o[j] = (uint8_t)(last + lsb(j)); j++; };
+		for (int p = q0; p < q1 && j < 24576; p++) {
+			const int c = ch[p];
+			const uint32_t e = tabB[c];
+			const int nd = (int)((e >> 7) & 3u);
+			if ((e >> 9) & 3u) put((c - 128) << 2);
+			else {
+				for (int r = (int)(e & 127u); r > 0; r--) put(last);
+				if (nd > 0) put(last + ll_d0(e));
+				if (nd > 1) put(last + ll_d1(e));
+				if (nd > 2) put(last + ll_d2(e));
+			}
+		}
 	}
 }
 
@@ -869,6 +1145,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 	b.bytes = c->dec_bytes; b.yuv = c->dec_yuv;
 	b.lut = c->dec_lut;
 	const size_t YS = NHW_Y_SLOT, CS = NHW_C_SLOT;
+	const bool side = c->chroma_side && c->chroma_stream;
 
 	// coefficient planes start at zero: zero runs are skipped, not written (decoder/nhw_decoder.c:2029)
 	NHW_LAUNCH(c, kd_zero, dim3(262144 * 2 / 16 / 256, n), 256, 0, b.y_proc, YS, (size_t)(262144 * 2 / 16));
@@ -880,10 +1157,23 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 		// are warps to spare: 512 streams 2.6 ms vs 4.4 ms at four per warp); with thousands the warps themselves become the
 		// limit and sharing one pays (4096 streams: 5.7 ms at four per warp, 7.8 at two, 11.2 at one)
 		const int spw = c->tune.dsf_streams ? c->tune.dsf_streams : n <= 1536 ? 1 : n <= 3072 ? 2 : 4;
-		NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + spw - 1) / spw, dim3(32, 4), 0, b, n, spw, c->tune.dsf_job_mask);
+		if (side) cudaEventRecord(c->ev_chroma0, c->stream);   // (the LL kernel depends on what precedes the serial front only)
+		NHW_LAUNCH_L(c, "d_serial_front", kd_serial_front, (n + spw - 1) / spw, dim3(32, 3), 0, b, n, spw, c->tune.dsf_job_mask);
 	}
+	// the LL bytes next to the serial front, which leaves most issue slots idle (launched after it, so that its blocks -- whose
+	// longest chain sets the kernel's time -- are resident first): on the side stream when the chunk has the GPU to itself
+	// (device-resident calls), joined before their first reader (d_ll_y)
+	if (side) {
+		const cudaStream_t main_stream = c->stream;
+		cudaStreamWaitEvent(c->chroma_stream, c->ev_chroma0, 0);
+		c->stream = c->chroma_stream;
+		NHW_LAUNCH_L(c, "d_ll_bytes", kd_ll_parallel, n, LLP_THREADS, 0, b);
+		cudaEventRecord(c->ev_chroma1, c->chroma_stream);
+		c->stream = main_stream;
+	} else NHW_LAUNCH_L(c, "d_ll_bytes", kd_ll_parallel, n, LLP_THREADS, 0, b);
 	NHW_LAUNCH_L(c, "d_descan_y", kd_descan_y, dim3(512, n), 128, 0, b);
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
+	if (side) cudaStreamWaitEvent(c->stream, c->ev_chroma1, 0);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
 	NHW_LAUNCH_L(c, "d_shrink_y", kd_shrink_y, dim3(32, n), 256, 0, b);
 	if (any_lowq) NHW_LAUNCH_L(c, "d_shrink_y_lowq", kd_shrink_y_lowq, n, 256, 0, b);
@@ -916,7 +1206,9 @@ void decode_chunk_device(nhw_ctx *c, const uint8_t *in, size_t stride, const uin
 {
 	DecDesc *desc = static_cast<DecDesc *>(c->dec_desc_dev);
 	NHW_LAUNCH(c, kd_parse_headers, (n + 127) / 128, 128, 0, in, stride, len, offs, n, desc, c->offs_dev, c->status_dev);
+	c->chroma_side = (c->tune.chroma_stream && !c->profile && !c->dbg_label[0]) ? 1 : 0;
 	decode_chunk(c, in, c->offs_dev, desc, c->status_dev, n, rgb_dev, true, true, false);
+	c->chroma_side = 0;
 	if (status_dev) cudaMemcpyAsync(status_dev, c->status_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream);
 }
 

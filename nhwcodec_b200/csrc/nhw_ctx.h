@@ -18,7 +18,7 @@ struct NhwTuning {
 	int subs_encode, lanes_encode;   // NHW_SUBS_ENCODE (16), NHW_LANES_ENCODE (4): host-buffer encode waves
 	int subs_decode, lanes_decode;   // NHW_SUBS_DECODE (8), NHW_LANES_DECODE (4)
 	int dsf_streams;       // NHW_DSF_STREAMS    streams per warp in the decoder's serial front (0 = by batch size: 1, 2 or 4)
-	int dsf_job_mask;      // NHW_DSF_JOBS       timing experiments only: which of the four serial jobs run (15 = all)
+	int dsf_job_mask;      // NHW_DSF_JOBS       timing experiments only: which of the three serial jobs run (bit 0 luma, 1 chroma, 2 lists; 15 = all)
 	int rows_grid_cap;     // SM count x NHW_ROWS_CTAS_PER_SM (24): grid cap of the "thread = row" kernels
 	int fetch_kernel;      // NHW_FETCH_KERNEL   decode: stream bytes in pinned host memory are fetched by a kernel, not the copy engine (1)
 };

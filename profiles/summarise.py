@@ -23,7 +23,9 @@ def short(name):
     return name
 
 
-launches = os.path.join(ROOT, "gpurun_out", "launches.csv")
+launches = os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % tag)
+if not os.path.exists(launches):
+    launches = os.path.join(ROOT, "gpurun_out", "launches.csv")
 if os.path.exists(launches):
     rows = [r for r in csv.reader(open(launches)) if len(r) > 14 and r[0].isdigit()]
     agg = collections.OrderedDict()
@@ -35,20 +37,20 @@ if os.path.exists(launches):
         a[1] += ns
     total = sum(v[1] for v in agg.values())
     out.append("## Launch list (ncu --metrics gpu__time_duration.sum --clock-control none), %d launches, %.2f ms total\n" % (len(rows), total / 1e6))
-    out.append("bench.py --steps 2 --warmup 3 --no-cpu-baseline: the bench workload (batch 4096): device-API steps, one profiled pass, host-API encode and decode steps in 512-image sub-chunks, synth. Cold-cache, serialised: compare shares.\n")
+    out.append("bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary: the bench workload (batch 4096): device-API round-trip steps, one profiled pass, host-API encode and decode steps in sub-chunks, synth. Cold-cache, serialised: compare shares.\n")
     # the device-API encode steps alone (grids over 4096 images / 8192 planes): the shares bench.py's kernel table must agree with
     dev = collections.OrderedDict()
     for r in rows:
         g = [int(x) for x in re.findall(r"\d+", r[8])]
         nm = short(r[4])
-        if not (4096 in g or 8192 in g) or nm.startswith("void at::") or "kd_" in nm or "decode_chunk" in nm or nm in ("k_synth",):
+        if not (4096 in g or 8192 in g or 1024 in g) or nm.startswith("void at::") or nm in ("k_synth",):
             continue
         a = dev.setdefault(nm, [0, 0.0])
         a[0] += 1
         a[1] += float(r[14])
     dtot = sum(v[1] for v in dev.values())
     if dtot:
-        out.append("### Device-API encode steps only (grids over 4096 images), share of the step\n")
+        out.append("### Device-API round-trip steps only (grids over 4096 images / 8192 planes / 1024 four-stream blocks), share of the step\n")
         out.append("| kernel | launches | total ms | share |\n|---|---|---|---|")
         for k, (n, ns) in sorted(dev.items(), key=lambda kv: -kv[1][1])[:25]:
             out.append("| `%s` | %d | %.3f | %.1f%% |" % (k, n, ns / 1e6, 100 * ns / dtot))
@@ -63,7 +65,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size"]
-for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep"))):
+reps = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_%s_*.ncu-rep" % tag))) or sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep")))
+for rep in reps:
     try:
         txt = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], stderr=subprocess.DEVNULL, text=True)
     except Exception as e:
