@@ -1,5 +1,5 @@
 """tests/sweep_parity_gpu.py -- one-off wide parity sweep on a GPU box (not collected by pytest):
-    python tests/sweep_parity_gpu.py [images per (kind, quality)]
+    python tests/sweep_parity_gpu.py [images per (kind, quality)] [lowest quality, default 1]
 encodes kinds x qualities x seeds through libnhw_cuda and compares every stream with the compiled reference
 (oracle/_ref, 16 host threads), then decodes a subset and compares the pixels with the reference decoder."""
 import os
@@ -18,7 +18,8 @@ codec = Codec(device=0, max_batch=128)
 pool = ThreadPoolExecutor(16)
 bad = 0
 total = 0
-for q in range(17, 24):
+q_lo = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+for q in range(q_lo, 24):
     for kind, gen in (("natural", synth.natural), ("textured", synth.textured), ("noise", synth.noise)):
         seeds = [50000 + 997 * q + 13 * i for i in range(per)]
         imgs = np.stack(list(pool.map(gen, seeds)))

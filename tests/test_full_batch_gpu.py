@@ -1,8 +1,8 @@
 """BASELINE.json configs[1] at full size (batch 4096, -q20) on the GPU, checked through properties that do not need
-4096 oracle encodes: every image encodes (status 0), two runs give identical bytes, a chunked context
-(max_batch 1024 -> 4 chunks, and 4 lanes per chunk) gives the same bytes as one 4096-image chunk, and a
-1-in-128 sample equals the compiled reference.  Then a 512-image slice goes back through the decoder and
-is compared with the reference decoder on a sample."""
+4096 oracle encodes: every image encodes (status 0), two runs give identical bytes, and a 1-in-128 sample equals the
+compiled reference.  A 512-image slice then goes through the HOST API of a smaller context (16 sub-chunks of 32 images on
+four streams) and must give the same bytes, goes back through the decoder and is compared with the reference decoder on
+a sample.  test_host_api_waves_and_sub_chunks covers more images than max_batch (several waves of sub-chunks)."""
 import numpy as np
 import pytest
 
@@ -57,3 +57,34 @@ def test_batch_4096_properties(ref):
     assert psnr.min() > 30.0, psnr.min()
     big.close()
     small.close()
+
+
+def test_host_api_waves_and_sub_chunks(ref):
+    """130 images through a context with max_batch 48: three waves (48 + 48 + 34), each cut into 16 (encode) / 8 (decode)
+    sub-chunks of uneven size on four streams; host-API bytes == device-API bytes == oracle on a sample, in image order"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from nhwcodec_b200 import Codec, synth
+    n = 130
+    c = Codec(device=0, max_batch=48)
+    fs = [synth.natural, synth.textured, synth.noise]
+    imgs = np.stack([fs[i % 3](7700 + i) for i in range(n)])
+    for q in (20, 9):
+        streams, status = c.encode(imgs, q)
+        assert (status == 0).all()
+        t = torch.from_numpy(imgs).cuda()
+        out = torch.zeros((n, 1 << 19), dtype=torch.uint8, device="cuda")
+        ln = torch.zeros(n, dtype=torch.int32, device="cuda")
+        st = torch.zeros(n, dtype=torch.int32, device="cuda")
+        c.encode_device(t, q, out, ln, st)
+        lh = ln.cpu().numpy()
+        for i in range(n):
+            assert streams[i] == out[i, : int(lh[i])].cpu().numpy().tobytes(), (q, i)
+        for i in (0, 47, 48, 95, 96, 129):
+            assert streams[i] == ref.ref_encode(imgs[i], q), (q, i)
+        back, dstat = c.decode(streams)
+        assert (dstat == 0).all()
+        for i in (0, 5, 47, 48, 53, 96, 129):
+            assert np.array_equal(back[i], ref.ref_decode(streams[i])), (q, i)
+    c.close()
