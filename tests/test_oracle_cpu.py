@@ -182,3 +182,38 @@ def test_oracle_is_the_same_from_any_thread(ref):
     with ThreadPoolExecutor(8) as pool:
         for _ in range(3):
             assert list(pool.map(lambda im: ref.ref_encode(im, 20), imgs)) == serial
+
+
+def test_upstreamable_fix_gives_the_canonical_bytes(tmp_path):
+    """the reference with the source patch of oracle/ub_fixes.py (defined memory for its heap blocks,
+    zero-initialised codebook array), built the way a user builds it -- stock allocator, no special flags -- writes the bytes
+    of the canonical oracle (zero-guard allocator at link time + zero-initialised automatics), and its decoder the same pixels"""
+    import subprocess
+    from nhwcodec_b200 import synth
+    if not os.path.isdir("/root/reference/encoder"):
+        pytest.skip("reference sources are not on this machine")
+    subprocess.check_call([os.path.join(ROOT, "oracle", "build_fixed.sh")], stdout=subprocess.DEVNULL)
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    patch = open(os.path.join(ref_dir, "ub_fixes.patch"), encoding="latin-1").read()
+    removed = [l for l in patch.splitlines() if l.startswith("-") and not l.startswith("---")]
+    assert len(removed) == 1 and "codebook[580]" in removed[0]          # one reference line changes, everything else is added
+    cases = [("smooth", smooth_pixels(), (1, 8, 12, 16, 17, 20, 22, 23))]
+    cases += [("natural", synth.natural(2000 + i), (12, 20, 23)) for i in range(4)]
+    cases += [("textured", synth.textured(2100), (20,)), ("noise", synth.noise(2200), (20, 23))]
+    bmp = str(tmp_path / "x.bmp")
+    for name, pix, qs in cases:
+        with open(bmp, "wb") as f:
+            f.write(bmp_header() + pix.tobytes())
+        for q in qs:
+            outs = {}
+            for exe in ("nhw-enc-fixed", "nhw-enc-canon"):
+                out = str(tmp_path / (exe + ".nhw"))
+                assert subprocess.run([os.path.join(ref_dir, exe), "-f", "-q%d" % q, bmp, out], capture_output=True).returncode == 0
+                outs[exe] = open(out, "rb").read()
+            assert outs["nhw-enc-fixed"] == outs["nhw-enc-canon"], (name, q)
+            pix_out = {}
+            for exe in ("nhw-dec-fixed", "nhw-dec-canon"):
+                out = str(tmp_path / (exe + ".bmp"))
+                subprocess.run([os.path.join(ref_dir, exe), str(tmp_path / "nhw-enc-canon.nhw"), out], capture_output=True)
+                pix_out[exe] = open(out, "rb").read()
+            assert pix_out["nhw-dec-fixed"] == pix_out["nhw-dec-canon"], (name, q)
