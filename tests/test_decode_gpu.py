@@ -89,6 +89,39 @@ def test_decode_hostile_headers(codec, ref):
     assert status[-1] == 0 and np.array_equal(rgb[-1], ref.ref_decode(good))
 
 
+def test_decode_corrupted_ll_section_is_contained(codec, ref):
+    """random damage inside the LL byte section (and its side list) of otherwise valid streams: the parallel LL decoder
+    (kd_ll_parallel) must stay inside its buffers whatever the codes say -- no CUDA error, the context keeps working, and
+    an undamaged stream in the same batch still decodes exactly"""
+    from nhwcodec_b200 import container
+    rng = np.random.default_rng(5)
+    img = _mixed(1, 9700)[0]
+    batch = []
+    for q in (20, 12, 23):
+        good = ref.ref_encode(img, q)
+        h, sec = container.parse_nhw(good)
+        start = h["header_bytes"]
+        for name, data in sec.items():
+            if name == "ch_res":
+                break
+            start += len(data)
+        n = len(sec["ch_res"])
+        for k in range(20):
+            b = bytearray(good)
+            for _ in range(1 + k % 7):
+                b[start + int(rng.integers(0, n))] = int(rng.integers(0, 256))
+            if k % 5 == 0:        # also cut the section short by lying about where the words start is not possible; zero a run instead
+                a = start + int(rng.integers(0, max(n - 64, 1)))
+                b[a:a + 64] = bytes(64)
+            batch.append(bytes(b))
+        batch.append(good)
+    rgb, status = codec.decode(batch)
+    for i in (20, 41, 62):
+        assert status[i] == 0 and np.array_equal(rgb[i], ref.ref_decode(batch[i])), i
+    again, st2 = codec.decode([batch[20]])
+    assert st2[0] == 0 and np.array_equal(again[0], rgb[20])
+
+
 def test_decode_device_api(codec, ref):
     """device-resident decode (headers walked on the device): slots as written by the device encoder, and streams
     packed back to back; more streams than max_batch (16), mixed qualities, one corrupt stream in the middle"""
