@@ -169,6 +169,7 @@ int nhw_create(int device, int max_batch, nhw_ctx **out)
 		t.dsf_job_mask = env_int("NHW_DSF_JOBS", 15, 0, 15);
 		t.rows_grid_cap = sms * env_int("NHW_ROWS_CTAS_PER_SM", 24, 1, 64);
 		t.fetch_kernel = env_int("NHW_FETCH_KERNEL", 1, 0, 1);
+		t.plw_phases = env_int("NHW_PLW_PHASES", 15, 0, 15);
 	}
 	ok = ok && nhw::front_device_init(c) && nhw::encode_device_init(c) && nhw::decode_device_init(c);
 	// every workspace array is zero-filled once: guard bands and never-written borders must

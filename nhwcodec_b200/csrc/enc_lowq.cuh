@@ -145,23 +145,26 @@ NHW_HDN void y_e8_smooth_image(const EncImg &im, int q) { y_e8_smooth_band(im.pr
 // ---- E14 below q16.  q14/q15: pointwise.  q <= 13: thresholds chosen from a global count (q <= 12), then three
 // in-place walks that look at the parent sample in the level-2 snapshot (im.ll2s, flat index) and at both
 // neighbours, zeroing a cell together with one of them.
+// q14 / q15: pointwise, one row (256..511) at a time
+NHW_HD void y_e14_q14_row(const EncImg &im, int q, int ratio, int r)
+{
+	const int hi2 = q == 15 ? 19 : 20;
+	int16_t *row = im.proc + r * YW;
+	for (int j = 0; j < 256; j++) {
+		const int v = nhw_iabs(row[j]);
+		if (v >= ratio && v < 11) row[j] = 0;
+	}
+	for (int j = 256; j < 512; j++) {
+		const int v = nhw_iabs(row[j]);
+		if (v >= ratio && v < hi2) row[j] = (int16_t)(row[j] >= 14 ? 7 : row[j] <= -14 ? -7 : 0);
+	}
+}
 NHW_HDN void y_e14_lowq_image(const EncImg &im, int q, int ratio)
 {
 	int16_t *P = im.proc;
 	const int16_t *S = im.ll2s;
 	if (q >= 14) {
-		const int hi2 = q == 15 ? 19 : 20;
-		for (int r = 256; r < 512; r++) {
-			int16_t *row = P + r * YW;
-			for (int j = 0; j < 256; j++) {
-				const int v = nhw_iabs(row[j]);
-				if (v >= ratio && v < 11) row[j] = 0;
-			}
-			for (int j = 256; j < 512; j++) {
-				const int v = nhw_iabs(row[j]);
-				if (v >= ratio && v < hi2) row[j] = (int16_t)(row[j] >= 14 ? 7 : row[j] <= -14 ? -7 : 0);
-			}
-		}
+		for (int r = 256; r < 512; r++) y_e14_q14_row(im, q, ratio, r);
 		return;
 	}
 	int t1 = 15, t2 = 27, t3 = 10, t4 = 6, t5 = 3;   // q13

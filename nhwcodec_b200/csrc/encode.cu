@@ -1778,6 +1778,7 @@ static void encode_luma_lowq(nhw_ctx *c, const EncBatch &b, int n, int q, int ra
 		idwt_luma256(c, b, n);
 	}
 	if (q == 16) run_rows(c, "y_e14_rows", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e14_threshold_row(im, q, ratio, 256 + r); });
+	else if (q >= 14) run_rows(c, "y_e14_rows", b, n, 256, [=] __device__(const EncImg &im, int r) { y_e14_q14_row(im, q, ratio, 256 + r); });
 	else run_image(c, "y_e14_lowq", b, n, [=] __device__(const EncImg &im, int) { y_e14_lowq_image(im, q, ratio); });
 	if (q > 12) {
 		NHW_LAUNCH_L(c, "y_e16_residual", k_e16_residual, n, 256, 0, b, q);

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) k_pre_low_events(const int16_t *__restric
 
 __global__ void __launch_bounds__(32 * PLW_WARPS) k_pre_low_walk(int16_t *__restrict__ y, size_t ystride, const int16_t *__restrict__ copy,
                                                                    int16_t *__restrict__ kern, int16_t *__restrict__ marks, size_t astride,
-                                                                   int n, int q)
+                                                                   int n, int q, int phases)
 {
 	__shared__ __align__(16) int16_t sYa[PLW_WARPS][2 * PW], sKa[PLW_WARPS][2 * PW];
 	__shared__ __align__(16) uint8_t sMa[PLW_WARPS][2 * PW];
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(32 * PLW_WARPS) k_pre_low_walk(int16_t *__rest
 	auto load_row8 = [&](uint8_t *dst, const uint8_t *src) { reinterpret_cast<uint4 *>(dst)[lane] = reinterpret_cast<const uint4 *>(src)[lane]; };
 
 	// ---- walk A, marker rules: the event pixels in raster order
-	{
+	if (phases & 1) {
 		PreWalkA w = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 		for (int w0 = 0; w0 < PW * PW / 32; w0 += 32) {
 			const uint32_t mine = bits[w0 + lane];
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(32 * PLW_WARPS) k_pre_low_walk(int16_t *__rest
 		__syncwarp();
 	}
 	// ---- walk B, row by row through the window's second row
-	{
+	if (phases & 2) {
 		PairThrottle t;
 		t.init();
 		int a = 0;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(32 * PLW_WARPS) k_pre_low_walk(int16_t *__rest
 		}
 	}
 	// ---- walk C on the two-row window (rows r - 1, r)
-	{
+	if (phases & 4) {
 		PreWalkC w = {0, 0, 0, 0, 0, 0};
 		for (int r = 1; r < 511; r++) {
 			for (int h = 0; h < 2; h++) {
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(32 * PLW_WARPS) k_pre_low_walk(int16_t *__rest
 		}
 	}
 	// ---- walk D: rows are independent
-	for (int r = 1 + lane; r < 511; r += 32) pre_low_walk_d_row(Y, K, M, p, r);
+	if (phases & 8) for (int r = 1 + lane; r < 511; r += 32) pre_low_walk_d_row(Y, K, M, p, r);
 }
 
 // chroma pre-filter (pre_processing_UV, q <= 14): 4:2:0 bytes -> int16 plane with the +-1 / +-2 nudges applied
@@ -403,7 +403,7 @@ void pre_processing_lowq(nhw_ctx *c, int n, int quality, int16_t *y, size_t ystr
 	uint32_t *bits = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(scratch) + PW * PW);
 	NHW_LAUNCH(c, k_pre_low_events, dim3(PW * PW / 256, n), 256, 0, kern, AS, bits, AS / 2, p.sharp2);
 	NHW_LAUNCH_L(c, "k_pre_low_walk", k_pre_low_walk, (n + PLW_WARPS - 1) / PLW_WARPS, 32 * PLW_WARPS, 0, y, ystride, copy, kern, scratch,
-	             AS, n, quality);
+	             AS, n, quality, c->tune.plw_phases);
 }
 
 void chroma_pre_uv(nhw_ctx *c, int n_planes, int quality, const uint8_t *uv, int16_t *out, size_t oslot)

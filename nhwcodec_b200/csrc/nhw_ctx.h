@@ -20,6 +20,7 @@ struct NhwTuning {
 	int dsf_streams;       // NHW_DSF_STREAMS    streams per warp in the decoder's serial front (0 = by batch size: 1, 2 or 4)
 	int dsf_job_mask;      // NHW_DSF_JOBS       timing experiments only: which of the three serial jobs run (bit 0 luma, 1 chroma, 2 lists; 15 = all)
 	int rows_grid_cap;     // SM count x NHW_ROWS_CTAS_PER_SM (24): grid cap of the "thread = row" kernels
+	int plw_phases;        // NHW_PLW_PHASES     timing experiments only: which walks of the q <= 16 pre-sharpening run (15 = all)
 	int fetch_kernel;      // NHW_FETCH_KERNEL   decode: stream bytes in pinned host memory are fetched by a kernel, not the copy engine (1)
 };
 
