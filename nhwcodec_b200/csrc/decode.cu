@@ -716,12 +716,38 @@ __global__ void __launch_bounds__(256) kd_inv_rows_t(DecBatch b)
 		}
 		__syncthreads();
 	}
-	for (int kk = 0; kk < IRT_ROWS; kk++) {
-		const int16_t *row = J + (k0 + kk) * YW;
-		const int16_t *low = k0 < 256 ? tl + kk * IRT_LS : row;
-		int ev, od;
-		inverse_pair([&](int t) { return (int)low[t]; }, [&](int t) { return (int)row[256 + t]; }, tid, 256, false, ev, od);
-		*reinterpret_cast<uint32_t *>(to + kk * IRT_OS + 2 * tid) = (uint32_t)(uint16_t)ev | ((uint32_t)(uint16_t)od << 16);
+	// Two band rows at a time, 128 threads each; a thread makes pairs 2u and 2u + 1 from ONE 32-bit load per band (its
+	// own two cells; the neighbours come from the lanes next to it, the warp's edge cells from a second, scalar load).
+	// The first form read every cell it needed with 2-byte loads of its own -- three per pair, one row at a time: 80 % of
+	// the kernel's stall samples were waits for them.
+	{
+		const int half = tid >> 7, u = tid & 127, lane = tid & 31, t0 = 2 * u;
+		for (int kk = half; kk < IRT_ROWS; kk += 2) {
+			const int16_t *row = J + (k0 + kk) * YW;
+			const uint32_t hw = *reinterpret_cast<const uint32_t *>(row + 256 + t0);
+			const int h0 = (int16_t)(hw & 0xffffu), h1 = (int16_t)(hw >> 16);
+			int hm = __shfl_up_sync(0xffffffffu, h1, 1), hp = __shfl_down_sync(0xffffffffu, h0, 1);
+			if (lane == 0) hm = u ? (int)row[256 + t0 - 1] : h0;              // h[-1] = h[0]
+			if (lane == 31) hp = u < 127 ? (int)row[256 + t0 + 2] : h1;        // h[256] = h[255]
+			int l0, l1, l2;
+			if (k0 < 256) {
+				const int16_t *low = tl + kk * IRT_LS;
+				l0 = low[t0]; l1 = low[t0 + 1]; l2 = u < 127 ? (int)low[t0 + 2] : l1;
+			} else {
+				const uint32_t lw = *reinterpret_cast<const uint32_t *>(row + t0);
+				l0 = (int16_t)(lw & 0xffffu); l1 = (int16_t)(lw >> 16);
+				l2 = __shfl_down_sync(0xffffffffu, l0, 1);
+				if (lane == 31) l2 = u < 127 ? (int)row[t0 + 2] : l1;
+			}
+			// pairs t0 and t0 + 1 of upfilter53I + upfilter53III without normalisation (dwt_core.cuh: inverse_pair)
+			const int16_t ev0 = (int16_t)((int16_t)(l0 << 3) - ((h0 + hm) << 1));
+			const int16_t od0 = (int16_t)((int16_t)((l1 + l0) << 2) + (6 * h0 - h1 - hm));
+			const int16_t ev1 = (int16_t)((int16_t)(l1 << 3) - ((h1 + h0) << 1));
+			const int16_t od1 = (int16_t)((int16_t)(u < 127 ? ((l2 + l1) << 2) : (l1 << 3)) + (6 * h1 - hp - h0));
+			uint32_t *o = reinterpret_cast<uint32_t *>(to + kk * IRT_OS + 4 * u);   // (the tile's rows are 4-byte aligned only)
+			o[0] = (uint32_t)(uint16_t)ev0 | ((uint32_t)(uint16_t)od0 << 16);
+			o[1] = (uint32_t)(uint16_t)ev1 | ((uint32_t)(uint16_t)od1 << 16);
+		}
 	}
 	__syncthreads();
 	for (int item = tid; item < 512 * (IRT_ROWS / 8); item += 256) {
@@ -740,21 +766,27 @@ __global__ void __launch_bounds__(128) kd_descan_y(DecBatch b)
 {
 	if (b.status[blockIdx.y] != 0) return;
 	const DecImg im = make_dec(b, blockIdx.y, 0);
-	const int row = blockIdx.x, strip = threadIdx.x;
-	const uint2 v = *reinterpret_cast<const uint2 *>(im.proc + strip * 2048 + (row >> 1) * 8 + (row & 1) * 4);
-	uint2 o = v;
-	if (row & 1) {   // second row of a step is stored reversed
-		o.x = (v.y >> 16) | (v.y << 16);
-		o.y = (v.x >> 16) | (v.x << 16);
+	// a CTA takes four rows: the four 8-byte runs a strip contributes to them are one 32-byte sector of the scan
+	const int quad = blockIdx.x, strip = threadIdx.x, lane = strip & 31;
+	const uint4 *src = reinterpret_cast<const uint4 *>(im.proc + strip * 2048 + quad * 16);
+	const uint4 a = src[0], c = src[1];
+	const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const int row = 4 * quad + i;
+		uint2 o = make_uint2(w[2 * i], w[2 * i + 1]);
+		if (i & 1) {   // second row of a step is stored reversed
+			o.x = (w[2 * i + 1] >> 16) | (w[2 * i + 1] << 16);
+			o.y = (w[2 * i] >> 16) | (w[2 * i] << 16);
+		}
+		*reinterpret_cast<uint2 *>(im.jpeg + row * YW + strip * 4) = o;
+		// which cells hold a marker code (> 1000): one bit per cell, 16 words per row, for kd_y_markers
+		const uint32_t nib = ((int16_t)(o.x & 0xffff) > 1000 ? 1u : 0u) | ((int16_t)(o.x >> 16) > 1000 ? 2u : 0u) |
+		                     ((int16_t)(o.y & 0xffff) > 1000 ? 4u : 0u) | ((int16_t)(o.y >> 16) > 1000 ? 8u : 0u);
+		const uint32_t word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
+		if ((lane & 7) == 0) im.mbits[row * 16 + (strip >> 3)] = word;
 	}
-	*reinterpret_cast<uint2 *>(im.jpeg + row * YW + strip * 4) = o;
-	// which cells hold a marker code (> 1000): one bit per cell, 16 words per row, for kd_y_markers
-	const uint32_t nib = ((int16_t)(o.x & 0xffff) > 1000 ? 1u : 0u) | ((int16_t)(o.x >> 16) > 1000 ? 2u : 0u) |
-	                     ((int16_t)(o.y & 0xffff) > 1000 ? 4u : 0u) | ((int16_t)(o.y >> 16) > 1000 ? 8u : 0u);
-	const int lane = strip & 31;
-	const uint32_t word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
-	if ((lane & 7) == 0) im.mbits[row * 16 + (strip >> 3)] = word;
-	if (row == 0 && strip < 2) im.cmark[strip * (1 + DEC_CMARK_CAP)] = 0;   // the chroma marker lists start empty (kd_descan_uv)
+	if (quad == 0 && strip < 2) im.cmark[strip * (1 + DEC_CMARK_CAP)] = 0;   // the chroma marker lists start empty (kd_descan_uv)
 }
 // Chroma: the stream interleaves U and V, 8-column strips, two rows per step (the second one reversed): a thread takes
 // the 32 coefficients of one (strip, step) -- 64 contiguous bytes -- and writes the four 8-cell runs they hold (U and V,
@@ -1171,7 +1203,7 @@ void decode_chunk(nhw_ctx *c, const uint8_t *blobs, const uint64_t *offs, const 
 		cudaEventRecord(c->ev_chroma1, c->chroma_stream);
 		c->stream = main_stream;
 	} else NHW_LAUNCH_L(c, "d_ll_bytes", kd_ll_parallel, n, LLP_THREADS, 0, b);
-	NHW_LAUNCH_L(c, "d_descan_y", kd_descan_y, dim3(512, n), 128, 0, b);
+	NHW_LAUNCH_L(c, "d_descan_y", kd_descan_y, dim3(128, n), 128, 0, b);
 	NHW_LAUNCH_L(c, "d_markers_y", kd_y_markers, n, 256, 0, b);
 	if (side) cudaStreamWaitEvent(c->stream, c->ev_chroma1, 0);
 	NHW_LAUNCH_L(c, "d_ll_y", kd_y_ll, n, 256, 0, b);
