@@ -88,15 +88,23 @@ NHW_HD void dec_c_upsample_cell(const int16_t *P, uint8_t *out /* 512x512 */, in
 // cell to the right), the right and lower neighbours none -- so the test reads the plane after the
 // markers (J) for the former and a snapshot taken before them (S) for the latter.
 // W: cells of the right half written by a right-half marker.  A: cells holding an applied 1008/1009.
+// ATOMIC: several threads apply (non-overlapping) markers at once, so the bit masks are updated with atomicOr (device only)
+template <bool ATOMIC = false>
 NHW_HD void dec_marker_apply(int16_t *J, int s, bool lower, uint32_t *W, uint32_t *A)
 {
 	const int v = J[s];
 	if (v <= 1000) return;
 	const int j = s & 511;
+	auto set_bit = [&](uint32_t *M, int k) {
+#ifdef __CUDA_ARCH__
+		if (ATOMIC) { atomicOr(&M[k >> 5], 1u << (k & 31)); return; }
+#endif
+		M[k >> 5] |= 1u << (k & 31);
+	};
 	auto mark = [&](int t) {   // t in the right half of the lower rows
 		if (W && (t & 511) >= 256 && (t >> 9) >= 256 && (t >> 9) < 512) {
 			const int k = (((t >> 9) - 256) << 8) + ((t & 511) - 256);
-			W[k >> 5] |= 1u << (k & 31);
+			set_bit(W, k);
 		}
 	};
 	if (!lower) {
@@ -115,7 +123,7 @@ NHW_HD void dec_marker_apply(int16_t *J, int s, bool lower, uint32_t *W, uint32_
 		mark(s - 1); mark(s); if (j < 511) mark(s + 1);
 		if (A && j >= 256) {
 			const int k = (((s >> 9) - 256) << 8) + (j - 256);
-			A[k >> 5] |= 1u << (k & 31);
+			set_bit(A, k);
 		}
 	} else if (v == 1006 || v == 1007) {
 		const int16_t w = (int16_t)(v == 1006 ? -7 : 7);

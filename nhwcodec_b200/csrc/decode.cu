@@ -578,13 +578,38 @@ __global__ void __launch_bounds__(256) kd_y_markers(DecBatch b)
 			for (uint32_t m = mb[w0 + k]; m; m &= m - 1) cand[o++] = base + 32 * k + __ffs(m) - 1;
 	}
 	__syncthreads();
-	const int n12 = cnt[512], n3 = cnt[768];
-	if (tid == 0) {
-		const int n1 = cnt[256];
-		for (int k = 0; k < n1; k++) dec_marker_apply(J, cand[k], false, nullptr, nullptr);
-		for (int k = n1; k < n12; k++) dec_marker_apply(J, cand[k], true, nullptr, nullptr);
-	}
-	__syncthreads();
+	const int n1 = cnt[256], n12 = cnt[512], n3 = cnt[768];
+	// Applying the markers.  A marker writes constants into a footprint of at most 3 columns x 2 rows around itself
+	// (dec_marker_apply), so two markers interact only when they sit within two columns and one row of each other; such
+	// neighbours are rare.  A marker with no other marker bit in that window is applied by its own thread, whenever; the
+	// others are flagged and applied by one thread in sweep order afterwards.  (The three sweeps stay one after the other:
+	// a sweep may overwrite marker cells of the next.)
+	uint8_t *defer = reinterpret_cast<uint8_t *>(im.aux + 128 * YW);     // one flag per candidate (rows 128.. of the scratch plane)
+	auto crowded = [&](int s) {
+		const int r = s >> 9, c = s & 511;
+		// footprints that wrap around a row end (the plane is addressed flat) or reach column 255 from the right half meet
+		// writers far outside the window: those markers always take the ordered path
+		if (c <= 1 || c >= 510 || c == 256) return true;
+		for (int rr = max(r - 1, 0); rr <= min(r + 1, 511); rr++)
+			for (int cc = max(c - 2, 0); cc <= min(c + 2, 511); cc++)
+				if ((rr != r || cc != c) && ((mb[rr * 16 + (cc >> 5)] >> (cc & 31)) & 1u)) return true;
+		return false;
+	};
+	auto sweep = [&](int a, int bnd, bool lower, uint32_t *Wm, uint32_t *Am) {
+		for (int k = a + tid; k < bnd; k += 256) {
+			const int s = cand[k];
+			const bool d = crowded(s);
+			defer[k] = d ? 1 : 0;
+			if (!d) dec_marker_apply<true>(J, s, lower, Wm, Am);
+		}
+		__syncthreads();
+		if (tid == 0)
+			for (int k = a; k < bnd; k++)
+				if (defer[k]) dec_marker_apply(J, cand[k], lower, Wm, Am);
+		__syncthreads();
+	};
+	sweep(0, n1, false, nullptr, nullptr);
+	sweep(n1, n12, true, nullptr, nullptr);
 	if (im.d->quality >= 23 && n3 == n12) return;   // no right-half markers and no nudges (the rule is off at q23)
 	// snapshot of rows 255..511, columns 256..511, before the right-half markers
 	for (int idx = tid; idx < 257 * 32; idx += 256) {
@@ -592,9 +617,7 @@ __global__ void __launch_bounds__(256) kd_y_markers(DecBatch b)
 		*reinterpret_cast<uint4 *>(S + r * YW + 256 + c8) = *reinterpret_cast<const uint4 *>(J + r * YW + 256 + c8);
 	}
 	__syncthreads();
-	if (tid == 0)
-		for (int k = n12; k < n3; k++) dec_marker_apply(J, cand[k], true, W, A);
-	__syncthreads();
+	sweep(n12, n3, true, W, A);
 	if (im.d->quality >= 23) return;   // the nudge rule is off at q23 (nhw_decoder.c:588)
 	// One pass: every qualifying cell is nudged on its own count.  The reference's count variable is stale at its first
 	// use, so the FIRST qualifying cell (raster order) gets that stale value on top: found with an atomic min here and
