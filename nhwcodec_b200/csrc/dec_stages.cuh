@@ -141,11 +141,12 @@ NHW_HDN void dec_y_markers_image(const DecImg &im)
 
 // ---- D5-D7: LL2 fill, res4 parity restore, exw overrides (nhw_decoder.c:609-658)
 // res4 parity restore + exw overrides; returns where the chroma exw entries start
-NHW_HDN int dec_y_ll_overrides(const DecImg &im)
+// (res4_done: the parity restore has been applied already -- the CUDA kernel does it with a warp, kd_y_ll)
+NHW_HDN int dec_y_ll_overrides(const DecImg &im, bool res4_done = false)
 {
 	int16_t *J = im.jpeg;
 	const DecDesc *d = im.d;
-	if (d->quality > 17) {
+	if (d->quality > 17 && !res4_done) {
 		const uint8_t *r4 = im.blob + d->off_res4;
 		int count = 0;
 		for (int i = 0; i < d->res4_len && count < 128; i++) {   // (a well-formed list names 128 rows; more is garbage)

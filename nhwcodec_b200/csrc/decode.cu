@@ -646,7 +646,34 @@ __global__ void __launch_bounds__(256) kd_y_ll(DecBatch b)
 	const DecImg im = make_dec(b, blockIdx.x, 0);
 	for (int i = threadIdx.x; i < 16384; i += 256) im.jpeg[(i >> 7) * YW + (i & 127)] = im.res_comp[i];
 	__syncthreads();
-	if (threadIdx.x == 0) im.list_len[10] = dec_y_ll_overrides(im);
+	if (threadIdx.x >= 32) return;
+	// res4 parity restore (dec_y_ll_overrides' first loop) by one warp: an entry's row is the number of row-ending codes
+	// (>= 128) before it -- a ballot count -- and what it does to its four cells ("make it odd") does not depend on the
+	// order of the entries.  The serial form spent ~1 us per entry waiting for its own read-modify-writes.
+	const DecDesc *d = im.d;
+	const int lane = threadIdx.x;
+	if (d->quality > 17) {
+		const uint8_t *r4 = im.blob + d->off_res4;
+		int16_t *J = im.jpeg;
+		int base = 0;
+		for (int i0 = 0; i0 < d->res4_len && base < 128; i0 += 32) {
+			const int i = i0 + lane;
+			const int v = i < d->res4_len ? r4[i] : 0;
+			const uint32_t ends = __ballot_sync(0xffffffffu, v >= 128);
+			const int count = base + __popc(ends & ((1u << lane) - 1u));
+			if (i < d->res4_len && count < 128 && v != 128) {
+				const int col = v > 128 ? v - 129 : v - 1;
+				if (col >= 0 && col <= 124) {
+					const int e = (count << 9) + col;
+					for (int k = 0; k < 4; k++)
+						if (!(J[e + k] & 1)) J[e + k]++;
+				}
+			}
+			base += __popc(ends);
+		}
+		__syncwarp();
+	}
+	if (lane == 0) im.list_len[10] = dec_y_ll_overrides(im, true);
 }
 
 // ---- D14: conditional 5-tap smoothing at the flagged positions (dec_y_smooth_flags_plane).  The targets sit on even
