@@ -251,11 +251,14 @@ NHW_HD void throttle_over(PairThrottle &t)
 NHW_HD void throttle_under(PairThrottle &t)
 {
 	int *n = t.n, *u = t.u;
-	if (n[1] == 6 && !u[8]) { n[1]++; u[8]++; n[44] = -100000; }
-	else if (n[44] < -90000) { n[1]++; u[8]++; n[44] = 0; }
-	else if (n[44] < 3) n[44]++;
+	// (the walker is one thread on a latency chain: conditions are combined with & and | instead of && and ||, so the common
+	// case runs through a handful of compares instead of a ladder of branches -- profiles/r02_notes.md)
+	if (((n[1] == 6) & (u[8] == 0)) | (n[44] < -90000)) {
+		if (n[1] == 6 && !u[8]) { n[1]++; u[8]++; n[44] = -100000; }
+		else { n[1]++; u[8]++; n[44] = 0; }
+	} else if (n[44] < 3) n[44]++;
 	else { n[1] += 3; n[44] = 0; }
-	if (!(n[29] > 0 && (n[14] == 4 || n[14] == 5 || n[39] == 2 || n[41] > 0))) return;
+	if (!((n[29] > 0) & ((n[14] == 4) | (n[14] == 5) | (n[39] == 2) | (n[41] > 0)))) return;
 
 	if (n[4] < 2 && n[1] == 15 && (n[14] == 4 || (n[14] == 5 && n[32] > 2))) {
 		if (n[32] == 0 || n[32] == 2 || n[32] == 3 || (n[32] > 7 && n[32] < 500000)) {
@@ -404,21 +407,25 @@ NHW_HD void throttle_pair(PairThrottle &t, const PreLowParams &p, int row, int &
 		return;
 	}
 	// ---- weak turn
-	if (hitA) { yA = (int16_t)(yA + (kA > 0 ? 1 : -1)); n[1]++; n[4]++; }
-	if (hitB) { yB = (int16_t)(yB + (kB > 0 ? 1 : -1)); n[1]++; n[4]++; }
+	if (hitA | hitB) {
+		if (hitA) { yA = (int16_t)(yA + (kA > 0 ? 1 : -1)); n[1]++; n[4]++; }
+		if (hitB) { yB = (int16_t)(yB + (kB > 0 ? 1 : -1)); n[1]++; n[4]++; }
+	}
 	bool spent;                                  // n17: the weak-turn budget of this cycle is used up
-	if (n[4] < 10) spent = n[4] == n[10] && n[1] == n[11];
-	else if (n[4] > 10 || n[1] != 15) {
+	if (n[4] < 10) spent = (n[4] == n[10]) & (n[1] == n[11]);
+	else if ((n[4] > 10) | (n[1] != 15)) {
 		if (!n[18]) { spent = true; n[18] = 1; }
 		else { spent = false; n[18]++; if (n[18] > 15) n[18] = 0; }
-	} else spent = n[4] == n[10] && n[1] == n[11];
+	} else spent = (n[4] == n[10]) & (n[1] == n[11]);
 	n[17] = spent ? 1 : 0;
-	if (n[6] > 6000000) { n[6] = 0; n[22] = 0; }
-	else if (n[6] > 4000000) { n[6] = 0; n[22] = n[21] == 1 ? 1 : 0; }
-	if (spent || n[1] > 2000003) throttle_rearm(t);
+	if (n[6] > 4000000) {
+		if (n[6] > 6000000) { n[6] = 0; n[22] = 0; }
+		else { n[6] = 0; n[22] = n[21] == 1 ? 1 : 0; }
+	}
+	if (spent | (n[1] > 2000003)) throttle_rearm(t);
 	else if (n[1] >= 15) throttle_over(t);
 	else throttle_under(t);
-	if (n[8] > 6 && !n[4] && n[1] > 1 && n[1] < 15) {
+	if ((n[8] > 6) & (n[4] == 0) & (n[1] > 1) & (n[1] < 15)) {
 		n[5]++;
 		if (n[5] < 35) {
 			n[1] = 0;
@@ -426,7 +433,7 @@ NHW_HD void throttle_pair(PairThrottle &t, const PreLowParams &p, int row, int &
 			else { n[12] = 0; n[13]++; if (n[13] > 3) n[13] = 0; }
 		} else n[12] = 0;
 	}
-	if (n[1] > 15 && n[1] < 1000000) { n[1] = 0; n[4] = 0; n[29]++; }
+	if ((n[1] > 15) & (n[1] < 1000000)) { n[1] = 0; n[4] = 0; n[29]++; }
 }
 
 // the q <= 14 smoothing of walk B for one pixel: O = the plane before the stage, kv = the pixel's kernel value after
@@ -450,7 +457,7 @@ NHW_HD void pre_low_walk_b_row(PairThrottle &t, int &a, const PreLowParams &p, i
 		int kA = Kr[j], kB = Kr[j + 1];
 		throttle_pair(t, p, r, kA, kB, Yr[j], Yr[j + 1], Kr[j], Kr[j + 1]);
 		// opposite-sign pair just above the threshold: push them apart, and remember which way (M)
-		if (nhw_iabs(kA) > sh && nhw_iabs(kA) <= sh + 20 && nhw_iabs(kB) > sh && nhw_iabs(kB) <= sh + 20) {
+		if ((nhw_iabs(kA) > sh) & (nhw_iabs(kA) <= sh + 20) & (nhw_iabs(kB) > sh) & (nhw_iabs(kB) <= sh + 20)) {
 			if (kA > 0 && kB < 0) { Yr[j]++; Yr[j + 1]--; Mr[j] = 2; Mr[j + 1] = 3; }
 			else if (kA < 0 && kB > 0) { Yr[j]--; Yr[j + 1]++; Mr[j] = 3; Mr[j + 1] = 2; }
 		}
@@ -458,21 +465,23 @@ NHW_HD void pre_low_walk_b_row(PairThrottle &t, int &a, const PreLowParams &p, i
 			// the 10..32 / >= 23 rule of the q > 16 path, without its 176 / 201 part
 			int d0 = 0, d1 = 0;
 			const int ar = nhw_iabs(kA), ac = nhw_iabs(kB);
-			if (ar > 10 && ar < 32 && ac >= 23) {
+			if ((ar > 10) & (ar < 32) & (ac >= 23)) {
 				const int sg = kA > 0 ? 1 : -1;
 				if (ar < 16) { if (kB * sg > 0 && ac < 32 && ar > 11) d1 = sg; d0 = sg; }
 				else d0 = a ? sg : 2 * sg;
 				a = 0;
 			} else {
 				a = 0;
-				if (ac > 10 && ac < 32 && ar >= 23) {
+				if ((ac > 10) & (ac < 32) & (ar >= 23)) {
 					const int sg = kB > 0 ? 1 : -1;
 					if (ac < 16) { if (kA * sg > 0 && ar < 32 && ac > 11) d0 = sg; d1 = sg; }
 					else { d1 = 2 * sg; a = 1; }
 				}
 			}
-			Yr[j] = (int16_t)(Yr[j] + d0);
-			Yr[j + 1] = (int16_t)(Yr[j + 1] + d1);
+			if (d0 | d1) {
+				Yr[j] = (int16_t)(Yr[j] + d0);
+				Yr[j + 1] = (int16_t)(Yr[j + 1] + d1);
+			}
 		}
 	}
 }
@@ -518,21 +527,23 @@ NHW_HD void pre_low_walk_c_row(PreWalkC &w, const PreLowParams &p, int r, int16_
 		int kA = K[s];
 		j++; s++;
 		int kB = K[s];
-		if (nhw_iabs(kA) > 6000) {
-			walk_c_resolve(K[s - 1], kA, w.pa, w.na, s2);
-			if (!w.gate) { walk_c_resolve(K[s], kB, w.pb, w.nb, s2); w.gate = 1; }
-			else w.gate = 0;
-			if (!w.skip_first) { w.skip_first = 1; continue; }
-			w.skip_first = 0;
-		} else if (nhw_iabs(kB) > 6000) {
-			walk_c_resolve(K[s], kB, w.pb, w.nb, s2);
-			continue;
+		if ((nhw_iabs(kA) > 6000) | (nhw_iabs(kB) > 6000)) {
+			if (nhw_iabs(kA) > 6000) {
+				walk_c_resolve(K[s - 1], kA, w.pa, w.na, s2);
+				if (!w.gate) { walk_c_resolve(K[s], kB, w.pb, w.nb, s2); w.gate = 1; }
+				else w.gate = 0;
+				if (!w.skip_first) { w.skip_first = 1; continue; }
+				w.skip_first = 0;
+			} else {
+				walk_c_resolve(K[s], kB, w.pb, w.nb, s2);
+				continue;
+			}
 		}
 		// strong value next to a weak one (the stale kA / kB are used on purpose: a resolved marker still counts
 		// with its marker value here)
-		const bool strongA = nhw_iabs(kA) > sh + 20 && nhw_iabs(kB) > (sh >> 1) && nhw_iabs(kB) <= s2;
-		const bool strongB = !strongA && nhw_iabs(kB) > sh + 20 && nhw_iabs(kA) > (sh >> 1) && nhw_iabs(kA) <= s2;
-		if (strongA || strongB) {
+		const bool strongA = (nhw_iabs(kA) > sh + 20) & (nhw_iabs(kB) > (sh >> 1)) & (nhw_iabs(kB) <= s2);
+		const bool strongB = !strongA & (nhw_iabs(kB) > sh + 20) & (nhw_iabs(kA) > (sh >> 1)) & (nhw_iabs(kA) <= s2);
+		if (strongA | strongB) {
 			const int big = strongA ? kA : kB, small = strongA ? kB : kA;
 			const int at_big = strongA ? s - 1 : s, at_small = strongA ? s : s - 1;
 			if (big != 0) {
