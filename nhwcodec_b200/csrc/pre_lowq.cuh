@@ -436,6 +436,34 @@ NHW_HD void throttle_pair(PairThrottle &t, const PreLowParams &p, int row, int &
 	if ((n[1] > 15) & (n[1] < 1000000)) { n[1] = 0; n[4] = 0; n[29]++; }
 }
 
+// ---- the quiet stretch.  At most qualities nine pairs in ten have no value above the threshold, and the throttle then
+// runs on its own: a weak turn below the budget in which only n1, n44 (and once u8) move, until n1 passes 15 and the cycle
+// restarts.  Everything else throttle_pair looks at on that path (n4, n6, n8, n10, n11, n14, n29, n39, n41) stands still,
+// so it is summed up once in `steady` -- recomputed whenever the general path or a cycle restart has run -- and a quiet
+// pair then costs a dozen instructions instead of ~150.  throttle_quiet_step is exactly throttle_pair restricted to that
+// path (no hit, weak turn, budget not spent, n1 < 15, throttle_under's early return); it returns false, having changed
+// nothing, when the pair is not on it.
+NHW_HD bool throttle_steady(const PairThrottle &t)
+{
+	const int *n = t.n;
+	const bool busy = (n[29] > 0) & ((n[14] == 4) | (n[14] == 5) | (n[39] == 2) | (n[41] > 0));
+	return (n[4] < 10) & (n[6] <= 4000000) & !busy & !((n[8] > 6) & (n[4] == 0));
+}
+NHW_HD bool throttle_quiet_step(PairThrottle &t, bool &steady)
+{
+	int *n = t.n, *u = t.u;
+	const int n1 = n[1];
+	if (!((n1 != 0) & (n1 < 15) & !((n[4] == n[10]) & (n1 == n[11])))) return false;
+	n[17] = 0;
+	if (((n1 == 6) & (u[8] == 0)) | (n[44] < -90000)) {
+		if (n1 == 6 && !u[8]) { n[1]++; u[8]++; n[44] = -100000; }
+		else { n[1]++; u[8]++; n[44] = 0; }
+	} else if (n[44] < 3) n[44]++;
+	else { n[1] += 3; n[44] = 0; }
+	if (n[1] > 15) { n[1] = 0; n[4] = 0; n[29]++; steady = throttle_steady(t); }   // (n1 < 1000000 here)
+	return true;
+}
+
 // the q <= 14 smoothing of walk B for one pixel: O = the plane before the stage, kv = the pixel's kernel value after
 // walk A.  Pointwise (it reads O only), so it is applied to a whole row before the row's pairs are walked.
 NHW_HD bool pre_low_smooth_cell(const int16_t *O, int at, int kv, const PreLowParams &p, int &out)
@@ -451,11 +479,41 @@ NHW_HD bool pre_low_smooth_cell(const int16_t *O, int at, int kv, const PreLowPa
 // has been applied to Yr already.  `a` = the mid-range rule's one-pair memory, carried from row to row like the throttle.
 NHW_HD void pre_low_walk_b_row(PairThrottle &t, int &a, const PreLowParams &p, int r, int16_t *Yr, int16_t *Kr, uint8_t *Mr)
 {
-	const int sh = p.sharp;
+	const int sh = p.sharp, small_below = sh < 22 ? sh : 22;
+	bool steady = throttle_steady(t);
 	for (int j = 1; j < 510; j += 2) {
 		// the pair is columns (j, j + 1)
 		int kA = Kr[j], kB = Kr[j + 1];
-		throttle_pair(t, p, r, kA, kB, Yr[j], Yr[j + 1], Kr[j], Kr[j + 1]);
+		// a pair whose two values are both at most min(sharp, 22) in magnitude is below every rule of this walk: no hit, not
+		// an opposite-sign pair (both need > sharp), not a mid-range pair (one value would have to reach 23) -- only the
+		// throttle moves, and the mid-range rule forgets its one-pair memory
+		const int big = nhw_iabs(kA) > nhw_iabs(kB) ? nhw_iabs(kA) : nhw_iabs(kB);
+		{
+			// the commonest pair of all, as ONE branch (a lone thread pays tens of cycles for every branch it takes): small
+			// pair, steady throttle, weak turn below the budget, the plain n44 / n1 tick of throttle_under
+			int *n = t.n;
+			const int n1 = n[1], n44 = n[44];
+			const bool tick = (big <= small_below) & steady & (n1 != 0) & (n1 < 15) & !((n[4] == n[10]) & (n1 == n[11])) &
+			                  !(((n1 == 6) & (t.u[8] == 0)) | (n44 < -90000));
+			if (tick) {
+				const bool low = n44 < 3;
+				const int m1 = n1 + (low ? 0 : 3);
+				n[44] = low ? n44 + 1 : 0;
+				n[17] = 0;
+				a = 0;
+				if (m1 > 15) { n[1] = 0; n[4] = 0; n[29]++; steady = throttle_steady(t); }
+				else n[1] = m1;
+				continue;
+			}
+		}
+		if ((big <= small_below) & steady) {
+			if (throttle_quiet_step(t, steady)) { a = 0; continue; }
+		}
+		const bool quiet = big <= sh;
+		if (!(quiet && steady && throttle_quiet_step(t, steady))) {
+			throttle_pair(t, p, r, kA, kB, Yr[j], Yr[j + 1], Kr[j], Kr[j + 1]);
+			steady = throttle_steady(t);
+		}
 		// opposite-sign pair just above the threshold: push them apart, and remember which way (M)
 		if ((nhw_iabs(kA) > sh) & (nhw_iabs(kA) <= sh + 20) & (nhw_iabs(kB) > sh) & (nhw_iabs(kB) <= sh + 20)) {
 			if (kA > 0 && kB < 0) { Yr[j]++; Yr[j + 1]--; Mr[j] = 2; Mr[j + 1] = 3; }
