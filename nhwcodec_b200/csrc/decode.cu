@@ -1190,10 +1190,14 @@ namespace nhw {
 
 bool decode_device_init(nhw_ctx *c)
 {
-	static uint16_t lut[NHW_LUT_WORDS];   // (filled with the same values by every caller)
-	dec_build_lut(lut);
+	// Built ONCE, by whichever thread gets here first (function-local static: thread-safe initialisation).  It used to be a
+	// plain static array that every nhw_create zeroed and refilled: two threads creating contexts at the same time could
+	// upload a half-zeroed table, and every context of the device then failed on the rarer codes (NHW_ERR_CODEBOOK on noise
+	// images) until the next nhw_create repaired it -- seen once, right after tests/test_contexts_gpu.py.
+	struct Lut { uint16_t w[NHW_LUT_WORDS]; };
+	static const Lut *const table = [] { Lut *t = new Lut; dec_build_lut(t->w); return t; }();
 	void *p = nullptr;
-	if (!check(cudaMemcpyToSymbol(g_dec_lut, lut, sizeof(lut)), "prefix-code table") || !check(cudaGetSymbolAddress(&p, g_dec_lut), "prefix-code table"))
+	if (!check(cudaMemcpyToSymbol(g_dec_lut, table->w, sizeof(table->w)), "prefix-code table") || !check(cudaGetSymbolAddress(&p, g_dec_lut), "prefix-code table"))
 		return false;
 	c->dec_lut = static_cast<const uint16_t *>(p);
 	return check(cudaFuncSetAttribute(kd_inv_rows_t, cudaFuncAttributeMaxDynamicSharedMemorySize, IRT_SMEM), "attr kd_inv_rows_t");

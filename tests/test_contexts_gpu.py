@@ -65,3 +65,37 @@ def test_contexts_from_threads(ref):
     for t in ts:
         t.join()
     assert out[0] == want and out[1] == want
+
+
+def test_concurrent_creates_leave_the_device_tables_intact(ref):
+    """contexts created from several threads at once (each nhw_create uploads the per-device tables) while an older
+    context keeps decoding: the decoder's prefix-code table used to be rebuilt in a shared host array by every create, so
+    two creates at once could upload a half-zeroed table and break every context's decode of the rarer codes"""
+    import threading
+    import torch
+    from nhwcodec_b200 import Codec
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    old = Codec(device=0, max_batch=2)
+    noise = np.stack([synth.noise(9103), synth.noise(9106)])
+    streams = [ref.ref_encode(noise[i], 1) for i in range(2)]      # big alphabets: long, rare codes
+    want = [ref.ref_decode(s) for s in streams]
+    stop = [False]
+
+    def churn():
+        while not stop[0]:
+            Codec(device=0, max_batch=1).close()
+
+    ts = [threading.Thread(target=churn) for _ in range(3)]
+    for t in ts:
+        t.start()
+    try:
+        for _ in range(12):
+            rgb, st = old.decode(streams)
+            assert (st == 0).all(), st
+            assert np.array_equal(rgb[0], want[0]) and np.array_equal(rgb[1], want[1])
+    finally:
+        stop[0] = True
+        for t in ts:
+            t.join()
+        old.close()
